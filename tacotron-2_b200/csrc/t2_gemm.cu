@@ -1,0 +1,149 @@
+// t2_gemm.cu — host side of the tcgen05 GEMM engine: TMA tensor-map encoding and kernel launches.
+#include <mutex>
+
+#include "t2_gemm.cuh"
+#include "t2_gemm.h"
+
+namespace t2 {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D map over a channels-last bf16 activation tensor: dims (C, T, B, L), box (64, rows, 1, 1), 128B swizzle.
+static int encode_act_map(CUtensorMap* m, const ActT& a, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  T2_REQUIRE(fn != nullptr, T2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  T2_REQUIRE(a.ptr && (reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0, T2_ERR_INVALID_ARG,
+             "activation pointer must be non-null and 16-byte aligned");
+  T2_REQUIRE(a.ld % 8 == 0 && a.C >= 1 && a.C <= a.ld, T2_ERR_UNSUPPORTED_SHAPE,
+             "activation row pitch must be a multiple of 8 elements (ld=%d C=%d)", a.ld, a.C);
+  cuuint64_t dims[4] = {cuuint64_t(a.C), cuuint64_t(a.T), cuuint64_t(a.B), cuuint64_t(a.L)};
+  cuuint64_t strides[3] = {cuuint64_t(a.ld) * 2, cuuint64_t(a.ld) * 2 * a.T,
+                           cuuint64_t(a.ld) * 2 * a.T * a.B};
+  cuuint32_t box[4] = {64, cuuint32_t(box_rows), 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  T2_REQUIRE(r == CUDA_SUCCESS, T2_ERR_CUDA, "cuTensorMapEncodeTiled(act) failed: %d (C=%d T=%d B=%d L=%d ld=%d)",
+             int(r), a.C, a.T, a.B, a.L, a.ld);
+  return T2_OK;
+}
+
+// 3-D map over packed bf16 weights [L][N][K]: dims (K, N, L), box (64, rows, 1)
+static int encode_wt_map(CUtensorMap* m, const void* w, int N, int K, int L, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  T2_REQUIRE(fn != nullptr, T2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  T2_REQUIRE(w && (reinterpret_cast<uintptr_t>(w) & 15) == 0, T2_ERR_INVALID_ARG,
+             "weight pointer must be non-null and 16-byte aligned");
+  T2_REQUIRE(K % 8 == 0, T2_ERR_UNSUPPORTED_SHAPE, "packed weight K must be a multiple of 8 (K=%d)", K);
+  cuuint64_t dims[3] = {cuuint64_t(K), cuuint64_t(N), cuuint64_t(L)};
+  cuuint64_t strides[2] = {cuuint64_t(K) * 2, cuuint64_t(K) * 2 * N};
+  cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  T2_REQUIRE(r == CUDA_SUCCESS, T2_ERR_CUDA, "cuTensorMapEncodeTiled(weight) failed: %d (N=%d K=%d L=%d)", int(r),
+             N, K, L);
+  return T2_OK;
+}
+
+template <int EPI, int BN>
+static int launch_one(const GemmArgs& g, dim3 grid, cudaStream_t stream) {
+  using Cfg = ActGemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    T2_CHECK_CUDA(cudaFuncSetAttribute(act_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    configured = true;
+  }
+  act_gemm_kernel<EPI, BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(g);
+  T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+
+int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) {
+  T2_REQUIRE(c.na >= 1 && c.na <= 4 && c.nseg >= 1 && c.nseg <= kMaxSeg, T2_ERR_INVALID_ARG,
+             "act_gemm: bad map/segment count (%d, %d)", c.na, c.nseg);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  for (int i = 0; i < 4; ++i) {
+    int rc = encode_act_map(&g.amap[i], c.a[i < c.na ? i : 0], kBM);
+    if (rc) return rc;
+  }
+  int rc = encode_wt_map(&g.bmap, c.w, c.wN, c.wK, c.wL, BN);
+  if (rc) return rc;
+  int ktot = 0;
+  for (int s = 0; s < c.nseg; ++s) {
+    g.seg[s] = c.seg[s];
+    T2_REQUIRE(c.seg[s].map >= 0 && c.seg[s].map < c.na && c.seg[s].nkb > 0 && c.seg[s].nlayers > 0,
+               T2_ERR_INVALID_ARG, "act_gemm: bad segment %d", s);
+    ktot += c.seg[s].nkb * c.seg[s].nlayers * kBK;
+  }
+  T2_REQUIRE(ktot <= ((c.wK + kBK - 1) / kBK) * kBK, T2_ERR_INVALID_ARG,
+             "act_gemm: segments cover K=%d but packed weight has K=%d", ktot, c.wK);
+  g.nseg = c.nseg;
+  g.T = c.T;
+  g.tiles_per_b = (c.T + kBM - 1) / kBM;
+  g.b_layer = c.w_layer;
+  g.epi = c.epi;
+  dim3 grid(g.tiles_per_b * c.B, c.n_tiles, 1);
+#define T2_CASE(E, N) \
+  if (epi == E && BN == N) return launch_one<E, N>(g, grid, stream);
+  T2_CASE(EPI_GATE, 256)
+  T2_CASE(EPI_RES, 128)
+  T2_CASE(EPI_RES, 256)
+  T2_CASE(EPI_BIAS_ACT, 128)
+  T2_CASE(EPI_BIAS_ACT, 256)
+  T2_CASE(EPI_CE, 256)
+  T2_CASE(EPI_MOL, 32)
+  T2_CASE(EPI_SCALE_RELUMASK, 128)
+  T2_CASE(EPI_SCALE_RELUMASK, 256)
+  T2_CASE(EPI_GATE_BWD, 128)
+  T2_CASE(EPI_GATE_BWD, 256)
+  T2_CASE(EPI_DX, 128)
+  T2_CASE(EPI_DX, 256)
+#undef T2_CASE
+  return t2_set_error(T2_ERR_UNSUPPORTED_SHAPE, "act_gemm: no kernel for epilogue %d with BN=%d", epi, BN);
+}
+
+int launch_wgrad(const ActT* maps, int nmaps, const WgradTile* tiles_dev, int ntiles, float* out, int T,
+                 int B, cudaStream_t stream) {
+  T2_REQUIRE(nmaps >= 1 && nmaps <= 6 && ntiles >= 1, T2_ERR_INVALID_ARG, "wgrad: bad map/tile count");
+  WgradArgs g;
+  memset(&g, 0, sizeof(g));
+  for (int i = 0; i < 6; ++i) {
+    int rc = encode_act_map(&g.map[i], maps[i < nmaps ? i : 0], kBK);
+    if (rc) return rc;
+  }
+  g.tiles = tiles_dev;
+  g.out = out;
+  g.T = T;
+  g.B = B;
+  static bool configured = false;
+  if (!configured) {
+    T2_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    configured = true;
+  }
+  wgrad_gemm_kernel<<<ntiles, kGemmThreads, kWgSmemBytes, stream>>>(g);
+  T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+
+}  // namespace t2

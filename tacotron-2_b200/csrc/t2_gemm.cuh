@@ -1,0 +1,655 @@
+// t2_gemm.cuh — the tcgen05 GEMM engine all dense contractions of the WaveNet / Tacotron paths run on.
+//
+//   act_gemm  : D[128 positions, BN] = sum over K-segments A_seg[pos + shift, k] * W[n, k]
+//               A = channels-last bf16 activations [L, B, T, C] read by 4-D TMA (negative / past-the-end
+//               time coordinates are zero-filled by the TMA unit, which is exactly the causal left pad of
+//               wavenet_vocoder/models/modules.py:308-313), B = packed bf16 weights [N, Ktot] (K-major).
+//               fp32 accumulators live in TMEM; a fused epilogue (gate / residual / loss / ...) drains them.
+//   wgrad_gemm: dW[m, n] = sum over positions A[pos + sa, m] * B[pos + sb, n]; both operands are
+//               channels-last activations, i.e. MN-major UMMA operands, reduction over positions.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#pragma once
+#include "t2_common.cuh"
+#include "t2_gemm_types.h"
+
+namespace t2 {
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers (one thread = one row, 32 consecutive channels)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+    d[q] = u;
+  }
+}
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32]) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u = __ldg(s + q);
+    v[q * 8 + 0] = bf16lo(u.x); v[q * 8 + 1] = bf16hi(u.x);
+    v[q * 8 + 2] = bf16lo(u.y); v[q * 8 + 3] = bf16hi(u.y);
+    v[q * 8 + 4] = bf16lo(u.z); v[q * 8 + 5] = bf16hi(u.z);
+    v[q * 8 + 6] = bf16lo(u.w); v[q * 8 + 7] = bf16hi(u.w);
+  }
+}
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
+  float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) d[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+}
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues. Each runs per thread = per output row (b, t); `trow` is the TMEM address of the row's
+// first accumulator column, `valid` is false for rows past T (tail tile) — those rows must not store.
+// ------------------------------------------------------------------------------------------------
+template <int EPI, int BN>
+struct Epilogue;
+
+// tanh/sigmoid gate of ResidualConv1DGLU (wavenet_vocoder/models/modules.py:494-510).
+// tile columns [0,128) = 'a' (tanh) channels cb..cb+127, [128,256) = 'b' (sigmoid) channels.
+// ptr: 0 ta_out, 1 sb_out, 2 z_out (bf16 [pos, Gh]), 3 bias fp32 [2*Gh];  i0 = Gh
+template <>
+struct Epilogue<EPI_GATE, 256> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int Gh = e.i[0];
+    const int cb = n_tile * 128;
+    const float* bias = static_cast<const float*>(e.ptr[3]);
+    const size_t row = (size_t(b) * T + t) * Gh;
+    __nv_bfloat16* ta_o = static_cast<__nv_bfloat16*>(e.ptr[0]);
+    __nv_bfloat16* sb_o = static_cast<__nv_bfloat16*>(e.ptr[1]);
+    __nv_bfloat16* z_o = static_cast<__nv_bfloat16*>(e.ptr[2]);
+#pragma unroll 1
+    for (int j0 = 0; j0 < 128; j0 += 32) {
+      float a[32], g[32];
+      tmem_ld32f(trow + j0, a);
+      tmem_ld32f(trow + 128 + j0, g);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float ta = tanhf_(a[j] + __ldg(bias + cb + j0 + j));
+        float sb = sigmoidf_(g[j] + __ldg(bias + Gh + cb + j0 + j));
+        a[j] = ta;
+        g[j] = sb;
+      }
+      if (valid) {
+        if (ta_o) store_bf16x32(ta_o + row + cb + j0, a);
+        if (sb_o) store_bf16x32(sb_o + row + cb + j0, g);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] *= g[j];
+        store_bf16x32(z_o + row + cb + j0, a);
+      }
+    }
+  }
+};
+
+// residual output of the block (modules.py:512-520): x_out = (W_o z + b_o + x) * res_scale, plus the
+// dropped-out copy the NEXT layer's dilated conv consumes (modules.py:483-484).
+// ptr: 0 x_in, 1 x_out, 2 xd_out (nullable), 3 bias fp32 [R];  f0 res_scale, f1 dropout p;  i1 = layer
+template <int BN>
+struct Epilogue<EPI_RES, BN> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int R = BN;
+    const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
+    __nv_bfloat16* x_out = static_cast<__nv_bfloat16*>(e.ptr[1]);
+    __nv_bfloat16* xd_out = static_cast<__nv_bfloat16*>(e.ptr[2]);
+    const float* bias = static_cast<const float*>(e.ptr[3]);
+    const float rs = e.f[0], p = e.f[1];
+    const float keep_inv = 1.f / (1.f - p);
+    const size_t row = (size_t(b) * T + t) * R;
+#pragma unroll 1
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+      float acc[32], x[32];
+      tmem_ld32f(trow + j0, acc);
+      if (valid) {
+        load_bf16x32(x_in + row + j0, x);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + __ldg(bias + j0 + j) + x[j]) * rs;
+        store_bf16x32(x_out + row + j0, acc);
+        if (xd_out) {
+          const uint64_t base = (uint64_t(e.i[1]) << 40) + row + j0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            acc[j] = (hash_uniform(e.seed, base + j) >= p) ? acc[j] * keep_inv : 0.f;
+          store_bf16x32(xd_out + row + j0, acc);
+        }
+      }
+    }
+  }
+};
+
+// out = act(acc + bias).  ptr: 0 out bf16 [pos, ldo] (nullable), 1 bias fp32 (nullable), 2 out fp32
+// [pos, ldo] (nullable);  i0 = ldo, i1 = act (0 none, 1 relu), i2 = n_valid columns
+template <int BN>
+struct Epilogue<EPI_BIAS_ACT, BN> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int ldo = e.i[0], act = e.i[1], nvalid = e.i[2];
+    __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(e.ptr[0]);
+    const float* bias = static_cast<const float*>(e.ptr[1]);
+    float* of = static_cast<float*>(e.ptr[2]);
+    const size_t row = (size_t(b) * T + t) * ldo;
+#pragma unroll 1
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+      const int c0 = n_tile * BN + j0;
+      if (c0 >= nvalid) break;  // warp-uniform
+      float acc[32];
+      tmem_ld32f(trow + j0, acc);
+      if (!valid) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = acc[j];
+        if (bias && c0 + j < nvalid) v += __ldg(bias + c0 + j);
+        if (act == 1) v = fmaxf(v, 0.f);
+        acc[j] = v;
+      }
+      if (c0 + 32 <= nvalid) {
+        if (ob) store_bf16x32(ob + row + c0, acc);
+        if (of) store_f32x32(of + row + c0, acc);
+      } else {
+        for (int j = 0; j < 32 && c0 + j < nvalid; ++j) {
+          if (ob) ob[row + c0 + j] = __float2bfloat16(acc[j]);
+          if (of) of[row + c0 + j] = acc[j];
+        }
+      }
+    }
+  }
+};
+
+// 256-way softmax cross entropy against the NEXT sample (wavenet.py:488, modules.py:781-798).
+// ptr: 0 targets int32 [B,T], 1 lengths int32 [B], 2 bias fp32 [256], 3 loss_sum fp32, 4 nonzero-count fp32,
+//      5 dlogits bf16 [pos,256] (nullable; un-normalised softmax - onehot), 6 logits fp32 [pos,256] (nullable)
+template <>
+struct Epilogue<EPI_CE, 256> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int* tgt = static_cast<const int*>(e.ptr[0]);
+    const int* len = static_cast<const int*>(e.ptr[1]);
+    const float* bias = static_cast<const float*>(e.ptr[2]);
+    __nv_bfloat16* dl = static_cast<__nv_bfloat16*>(e.ptr[5]);
+    float* lo = static_cast<float*>(e.ptr[6]);
+    const size_t row = (size_t(b) * T + t) * 256;
+    const bool w = valid && (t + 1 < T) && (t + 1 < __ldg(len + b));
+    const int y = w ? __ldg(tgt + size_t(b) * T + t + 1) : -1;
+    float mx = -INFINITY, zy = 0.f;
+#pragma unroll 1
+    for (int j0 = 0; j0 < 256; j0 += 32) {
+      float v[32];
+      tmem_ld32f(trow + j0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] += __ldg(bias + j0 + j);
+        mx = fmaxf(mx, v[j]);
+        if (j0 + j == y) zy = v[j];
+      }
+      if (lo && valid) store_f32x32(lo + row + j0, v);
+    }
+    float se = 0.f;
+#pragma unroll 1
+    for (int j0 = 0; j0 < 256; j0 += 32) {
+      float v[32];
+      tmem_ld32f(trow + j0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) se += __expf(v[j] + __ldg(bias + j0 + j) - mx);
+    }
+    const float lse = mx + __logf(se);
+    float loss = w ? (lse - zy) : 0.f;
+    float cnt = (loss != 0.f) ? 1.f : 0.f;
+    if (dl) {
+      const float inv = 1.f / se;
+#pragma unroll 1
+      for (int j0 = 0; j0 < 256; j0 += 32) {
+        float v[32];
+        tmem_ld32f(trow + j0, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float pj = __expf(v[j] + __ldg(bias + j0 + j) - mx) * inv;
+            v[j] = w ? (pj - ((j0 + j == y) ? 1.f : 0.f)) : 0.f;
+          }
+          store_bf16x32(dl + row + j0, v);
+        }
+      }
+    }
+    loss = warp_sum(loss);
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(static_cast<float*>(e.ptr[3]), loss);
+      atomicAdd(static_cast<float*>(e.ptr[4]), cnt);
+    }
+  }
+};
+
+// Discretised mixture-of-logistics NLL (wavenet_vocoder/models/mixture.py:18-74; masked mean
+// modules.py:800-817) with its analytic gradient. Tile has 32 columns: [logit(nm) | mean(nm) | log_scale(nm)].
+// ptr: 0 targets f32 [B,T], 1 lengths, 2 bias fp32 [3nm], 3 loss_sum, 4 mask_sum, 5 dyhat bf16 [pos,32]
+//      (nullable, un-normalised), 6 yhat fp32 [pos,32] (nullable)
+// f0 log_scale_min, f1 1/(num_classes-1), f2 log((num_classes-1)/2);  i0 = nr_mix (<= 10)
+template <>
+struct Epilogue<EPI_MOL, 32> {
+  static __device__ __forceinline__ float softplus(float x) {
+    return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));
+  }
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const float* tgt = static_cast<const float*>(e.ptr[0]);
+    const int* len = static_cast<const int*>(e.ptr[1]);
+    const float* bias = static_cast<const float*>(e.ptr[2]);
+    __nv_bfloat16* dy = static_cast<__nv_bfloat16*>(e.ptr[5]);
+    float* yo = static_cast<float*>(e.ptr[6]);
+    const int nm = e.i[0];
+    const float lsm = e.f[0], hw = e.f[1], logc = e.f[2];
+    const size_t row = (size_t(b) * T + t) * 32;
+    const bool w = valid && (t + 1 < T) && (t + 1 < __ldg(len + b));
+    const float y = w ? __ldg(tgt + size_t(b) * T + t + 1) : 0.f;
+    float v[32];
+    tmem_ld32f(trow, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (j < 3 * nm) ? v[j] + __ldg(bias + j) : 0.f;
+    if (yo && valid) store_f32x32(yo + row, v);
+    // log-softmax of the mixture logits
+    float lmx = -INFINITY;
+    for (int k = 0; k < nm; ++k) lmx = fmaxf(lmx, v[k]);
+    float lse = 0.f;
+    for (int k = 0; k < nm; ++k) lse += __expf(v[k] - lmx);
+    lse = lmx + __logf(lse);
+    float tot[10], dm[10], ds[10];
+    float tmx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      tot[k] = -INFINITY; dm[k] = 0.f; ds[k] = 0.f;
+      if (k < nm) {
+        const float m = v[nm + k], sraw = v[2 * nm + k];
+        const float ls = fmaxf(sraw, lsm);
+        const float inv = __expf(-ls);
+        const float cy = y - m;
+        const float pin = inv * (cy + hw), nin = inv * (cy - hw), mid = inv * cy;
+        const float cp = sigmoidf_(pin), cn = sigmoidf_(nin);
+        const float delta = cp - cn;
+        float lp, dlp_dm, dlp_dls;  // derivatives of log-prob wrt mean and (clamped) log-scale
+        if (y < -0.999f) {
+          lp = pin - softplus(pin);
+          const float g = 1.f - cp;  // d/dpin
+          dlp_dm = -inv * g; dlp_dls = -pin * g;
+        } else if (y > 0.999f) {
+          lp = -softplus(nin);
+          const float g = -cn;  // d/dnin
+          dlp_dm = -inv * g; dlp_dls = -nin * g;
+        } else if (delta > 1e-5f) {
+          lp = __logf(fmaxf(delta, 1e-12f));
+          const float gp = cp * (1.f - cp) / delta, gn = -cn * (1.f - cn) / delta;
+          dlp_dm = -inv * (gp + gn); dlp_dls = -(pin * gp + nin * gn);
+        } else {
+          const float sm = sigmoidf_(mid);
+          lp = mid - ls - 2.f * softplus(mid) - logc;
+          const float g = 1.f - 2.f * sm;
+          dlp_dm = -inv * g; dlp_dls = -mid * g - 1.f;
+        }
+        tot[k] = lp + (v[k] - lse);
+        tmx = fmaxf(tmx, tot[k]);
+        dm[k] = dlp_dm;
+        ds[k] = (sraw >= lsm) ? dlp_dls : 0.f;
+      }
+    }
+    float tse = 0.f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+      if (k < nm) tse += __expf(tot[k] - tmx);
+    const float nll = -(tmx + __logf(tse));
+    if (dy && valid) {
+      float g[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = 0.f;
+      if (w) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k)
+          if (k < nm) {
+            const float post = __expf(tot[k] - tmx) / tse;   // posterior responsibility
+            const float prior = __expf(v[k] - lse);
+            g[k] = prior - post;
+            g[nm + k] = -post * dm[k];
+            g[2 * nm + k] = -post * ds[k];
+          }
+      }
+      store_bf16x32(dy + row, g);
+    }
+    float loss = warp_sum(w ? nll : 0.f);
+    float cnt = warp_sum(w ? 1.f : 0.f);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(static_cast<float*>(e.ptr[3]), loss);
+      atomicAdd(static_cast<float*>(e.ptr[4]), cnt);
+    }
+  }
+};
+
+// backward through ReLU: out = acc * scale * (h > 0).
+// ptr: 0 out bf16 [pos, ldo], 1 h bf16 [pos, ldo], 2 device scalar fp32* (nullable; multiplies 1/x);
+// f0 const scale; i0 = ldo
+template <int BN>
+struct Epilogue<EPI_SCALE_RELUMASK, BN> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int ldo = e.i[0];
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.ptr[0]);
+    const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(e.ptr[1]);
+    float s = e.f[0];
+    if (e.ptr[2]) s /= fmaxf(__ldg(static_cast<const float*>(e.ptr[2])), 1e-20f);
+    const size_t row = (size_t(b) * T + t) * ldo + size_t(n_tile) * BN;
+#pragma unroll 1
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+      float acc[32], hv[32];
+      tmem_ld32f(trow + j0, acc);
+      if (valid) {
+        load_bf16x32(h + row + j0, hv);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = hv[j] > 0.f ? acc[j] * s : 0.f;
+        store_bf16x32(out + row + j0, acc);
+      }
+    }
+  }
+};
+
+// backward of the gate: dz -> (da, db).  ptr: 0 ta, 1 sb (bf16 [pos,Gh]), 2 dg out (bf16 [pos,2Gh]); i0 = Gh
+template <int BN>
+struct Epilogue<EPI_GATE_BWD, BN> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int Gh = e.i[0];
+    const __nv_bfloat16* ta = static_cast<const __nv_bfloat16*>(e.ptr[0]);
+    const __nv_bfloat16* sb = static_cast<const __nv_bfloat16*>(e.ptr[1]);
+    __nv_bfloat16* dg = static_cast<__nv_bfloat16*>(e.ptr[2]);
+    const size_t pos = size_t(b) * T + t;
+    const int cb = n_tile * BN;
+#pragma unroll 1
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+      float dz[32], a[32], s[32];
+      tmem_ld32f(trow + j0, dz);
+      if (valid) {
+        load_bf16x32(ta + pos * Gh + cb + j0, a);
+        load_bf16x32(sb + pos * Gh + cb + j0, s);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float da = dz[j] * (1.f - a[j] * a[j]) * s[j];
+          const float db = dz[j] * a[j] * s[j] * (1.f - s[j]);
+          a[j] = da;
+          s[j] = db;
+        }
+        store_bf16x32(dg + pos * 2 * Gh + cb + j0, a);
+        store_bf16x32(dg + pos * 2 * Gh + Gh + cb + j0, s);
+      }
+    }
+  }
+};
+
+// gradient wrt the block input: dx = dropout_mask/keep * acc + res_scale * dx_out
+// ptr: 0 dxo bf16 [pos,R] (nullable), 1 dx_out bf16 [pos,R]; f0 res_scale, f1 dropout p; i1 = layer
+template <int BN>
+struct Epilogue<EPI_DX, BN> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
+                                             bool valid, uint32_t trow) {
+    const int R = BN;
+    const __nv_bfloat16* dxo = static_cast<const __nv_bfloat16*>(e.ptr[0]);
+    __nv_bfloat16* dx = static_cast<__nv_bfloat16*>(e.ptr[1]);
+    const float rs = e.f[0], p = e.f[1];
+    const float keep_inv = 1.f / (1.f - p);
+    const size_t row = (size_t(b) * T + t) * R;
+#pragma unroll 1
+    for (int j0 = 0; j0 < BN; j0 += 32) {
+      float acc[32], g[32];
+      tmem_ld32f(trow + j0, acc);
+      if (valid) {
+        if (p > 0.f) {
+          const uint64_t base = (uint64_t(e.i[1]) << 40) + row + j0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            acc[j] = (hash_uniform(e.seed, base + j) >= p) ? acc[j] * keep_inv : 0.f;
+        }
+        if (dxo) {
+          load_bf16x32(dxo + row + j0, g);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += rs * g[j];
+        }
+        store_bf16x32(dx + row + j0, acc);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// act_gemm kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct ActGemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;   // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int EPI, int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) act_gemm_kernel(const __grid_constant__ GemmArgs g) {
+  using Cfg = ActGemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int b = m_tile / g.tiles_per_b;
+  const int t0 = (m_tile - b * g.tiles_per_b) * kBM;
+
+  int total_kb = 0;
+  for (int s = 0; s < g.nseg; ++s) total_kb += g.seg[s].nkb * g.seg[s].nlayers;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&g.amap[i]);
+    tma_prefetch_desc(&g.bmap);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < Cfg::kStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      mbar_init(tmem_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int kb_global = 0;
+      for (int s = 0; s < g.nseg; ++s) {
+        const Seg sg = g.seg[s];
+        for (int l = 0; l < sg.nlayers; ++l) {
+          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            tma_load_4d(sa, &g.amap[sg.map], &full_bar[stage], sg.k0 + kb * kBK, t0 + sg.shift, b,
+                        sg.layer0 + l);
+            tma_load_3d(sb, &g.bmap, &full_bar[stage], kb_global * kBK, n_tile * BN, g.b_layer);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN < 16 ? 16 : BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field
+          umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
+                   (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + (threadIdx.x & 31);
+    const int t = t0 + r;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    Epilogue<EPI, BN>::run(g.epi, n_tile, b, t, g.T, t < g.T, trow);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad_gemm kernel: both operands MN-major (channels contiguous), reduction over positions.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgBN = 128;
+constexpr int kWgStages = 6;
+constexpr int kWgStageBytes = 2 * (2 * kBK * 128);  // A: 2 blocks of [64 pos x 128 B], B: same = 32 KB
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* empty_bar = full_bar + kWgStages;
+  uint64_t* tmem_full = empty_bar + kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5;
+  const WgradTile tile = g.tiles[blockIdx.x];
+  const int kb_per_b = (g.T + kBK - 1) / kBK;
+  const int total_kb = kb_per_b * g.B;
+
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      mbar_init(tmem_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<kWgBN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int kBlk = kBK * 128;  // bytes of one [64 pos x 64 ch] block
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int bb = 0; bb < g.B; ++bb)
+        for (int kb = 0; kb < kb_per_b; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kWgStageBytes);
+          uint8_t* sa = smem + stage * kWgStageBytes;
+          uint8_t* sb = sa + 2 * kBlk;
+          const int tpos = kb * kBK;
+          tma_load_4d(sa, &g.map[tile.a_map], &full_bar[stage], tile.a_ch0, tpos + tile.a_shift, bb, tile.a_layer);
+          tma_load_4d(sa + kBlk, &g.map[tile.a_map], &full_bar[stage], tile.a_ch0 + 64, tpos + tile.a_shift, bb, tile.a_layer);
+          tma_load_4d(sb, &g.map[tile.b_map], &full_bar[stage], tile.b_ch0, tpos + tile.b_shift, bb, tile.b_layer);
+          tma_load_4d(sb + kBlk, &g.map[tile.b_map], &full_bar[stage], tile.b_ch0 + 64, tpos + tile.b_shift, bb, tile.b_layer);
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, kWgBN, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kWgStageBytes);
+        const uint32_t sb = sa + 2 * kBlk;
+        // MN-major SW128: LBO = distance between 64-channel blocks, SBO = distance between 8-position groups
+        const uint64_t adesc = make_sdesc_sw128(sa, kBlk, 1024);
+        const uint64_t bdesc = make_sdesc_sw128(sb, kBlk, 1024);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // 16 positions = 2 swizzle atoms of 8 rows x 128 B = 2048 bytes -> +128 in the (addr>>4) field
+          umma_f16(tmem_base, adesc + uint64_t(k * 128), bdesc + uint64_t(k * 128), idesc,
+                   (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + (threadIdx.x & 31);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    float* out = g.out + tile.out_off + size_t(m) * tile.ldc;
+    float sc = tile.scale;
+    if (tile.div) sc /= fmaxf(__ldg(tile.div), 1e-20f);
+#pragma unroll 1
+    for (int j0 = 0; j0 < kWgBN; j0 += 32) {
+      float v[32];
+      tmem_ld32f(trow + j0, v);
+      if (m < tile.m_valid) {
+        for (int j = 0; j < 32; ++j) {
+          if (j0 + j < tile.n_valid) {
+            float r = v[j] * sc;
+            if (tile.accumulate) r += out[j0 + j];
+            out[j0 + j] = r;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kWgBN>(tmem_base);
+  }
+}
+
+}  // namespace t2
