@@ -43,6 +43,100 @@ int t2_dbg_conv_gemm(const void* d_a, int B, int T, int C, int ld, const int* sh
 int t2_dbg_wgrad(const void* d_a, int Ca, const void* d_bm, int Cb, int B, int T, int shift_a, float scale,
                  float* d_out, void* stream);
 
+
+/* ---- WaveNet vocoder: teacher-forced training path ---------------------------------------------------------
+ * Replaces wavenet_vocoder/models/wavenet.py:650-721 (WaveNet.step), :476-519 (add_loss), the layers of
+ * wavenet_vocoder/models/modules.py:184-521,539-654,736-817 and wavenet_vocoder/models/mixture.py:18-74.
+ * Field names follow the reference's hparams.py:187-228. */
+typedef struct {
+  int layers, stacks, residual_channels, gate_channels, skip_out_channels, kernel_size;
+  int cin_channels;          /* 80 (num_mels) or 0 = no local conditioning */
+  int out_channels;          /* 256 (mu-law softmax) or 3*nr_mix (MoL) */
+  int quantize_channels;     /* 256 or 65536 */
+  int input_type;            /* 0 'raw', 1 'mulaw', 2 'mulaw-quantize' */
+  int legacy, residual_legacy;
+  int upsample_type;         /* 0 'SubPixel', 1 '2D' (ConvTranspose2D) */
+  int n_upsample;
+  int upsample_scales[4];
+  int freq_axis_kernel_size;
+  float dropout;             /* wavenet_dropout */
+  float log_scale_min;
+  int B, T, Tc;              /* per-GPU batch, samples per item, conditioning frames per item */
+  int c_pre_upsampled;       /* 1: conditioning is given at sample rate [B, T, cin] fp32 (skip upsample net) */
+} t2_wn_config_t;
+
+typedef struct {
+  long long n_params;        /* fp32 master parameters (TF variable layouts, concatenated) */
+  long long packed_bytes;    /* bf16 GEMM-operand copies + derived fp32 biases */
+  long long workspace_bytes; /* activations saved for backward, gradients of activations, tables */
+  int n_tensors;
+} t2_wn_sizes_t;
+
+int t2_wn_sizes(const t2_wn_config_t* cfg, t2_wn_sizes_t* out);
+/* i-th parameter tensor: TF-style name, offset into the flat buffer, shape */
+int t2_wn_param_info(const t2_wn_config_t* cfg, int i, char* name, int name_cap, long long* offset, int* ndim,
+                     int* shape4);
+/* one-time: zero the packed buffer / workspace and upload the static job tables (synchronises the stream) */
+int t2_wn_init(const t2_wn_config_t* cfg, void* d_packed, void* d_workspace, void* stream);
+/* fp32 masters -> bf16 operand layouts (run after every optimizer step) */
+int t2_wn_pack_weights(const t2_wn_config_t* cfg, const float* d_params, void* d_packed, void* d_workspace,
+                       void* stream);
+/* forward + loss. d_x: int32 [B,T] mu-law indices (input_type 2) or fp32 [B,T] samples; d_c: fp32 [B,cin,Tc]
+ * (or [B,T,cin] when c_pre_upsampled); d_targets: int32 / fp32 [B,T]; d_lengths int32 [B].
+ * d_loss: fp32[2] = {sum of masked losses, normaliser} (loss = [0]/[1]); d_logits: optional fp32 [B,T,ldo]
+ * (ldo = 256, or 32 for MoL). save_for_backward=0 skips the backward stashes. */
+int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                  const void* d_x, const float* d_c, const void* d_targets, const int* d_lengths, float* d_loss,
+                  float* d_logits, int save_for_backward, unsigned long long seed, void* stream);
+/* backward of the last t2_wn_forward(save_for_backward=1): writes all parameter gradients (d loss / d theta) */
+int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                   const void* d_x, const float* d_c, float* d_grads, unsigned long long seed, void* stream);
+/* debug / test access to workspace tensors by name ("x", "z", "c_up", "h1", "dg", ...): returns device pointer,
+ * element count and element size */
+int t2_wn_workspace_tensor(const t2_wn_config_t* cfg, void* d_workspace, const char* name, void** ptr,
+                           long long* count, int* elem_bytes);
+
+/* ---- optimizer: tf.train.AdamOptimizer + per-tensor clip_by_norm/clip_by_value + EMA ------------------------
+ * Replaces wavenet.py:586-613 (and tacotron.py:429-437 with global_norm_clip > 0).
+ * d_offsets: int64 [n_tensors + 1] element offsets of the tensors inside the flat buffers.
+ * grad_scale multiplies every gradient first (1/world_size after an NCCL sum all-reduce).
+ * max_norm <= 0 disables per-tensor norm clipping; max_value <= 0 disables value clipping;
+ * global_norm_clip > 0 applies tf.clip_by_global_norm instead. d_ema may be NULL. d_scratch: fp32 [n_tensors+1]. */
+int t2_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, float* d_ema,
+                 const long long* d_offsets, int n_tensors, long long n_total, float lr, float beta1, float beta2,
+                 float eps, int step, float grad_scale, float max_norm, float max_value, float global_norm_clip,
+                 float ema_decay, float* d_scratch, void* stream);
+
+/* ---- audio front-end ----------------------------------------------------------------------------------------
+ * Replaces datasets/audio.py:22-25,61-77,178-182,225-270 and wavenet_vocoder/util.py:30-129. Field names follow
+ * hparams.py:63-111. */
+typedef struct {
+  int sample_rate, n_fft, hop_size, win_size, num_mels;
+  float fmin, fmax;
+  float magnitude_power;
+  float min_level_db, ref_level_db, max_abs_value;
+  int symmetric_mels, allow_clipping_in_normalization, signal_normalization;
+} t2_audio_config_t;
+
+int t2_stft_mel_plan_bytes(const t2_audio_config_t* cfg, long long* bytes);
+/* builds twiddles, the periodic Hann window and the sparse Slaney mel filterbank (librosa.filters.mel restated in
+ * fp64 on the host) into d_plan; synchronises the stream */
+int t2_stft_mel_plan_init(const t2_audio_config_t* cfg, void* d_plan, void* stream);
+int t2_stft_mel_frames(const t2_audio_config_t* cfg, int n_samples);
+/* melspectrogram (and optionally linearspectrogram) of B clips of n_samples fp32 samples.
+ * sample fed to the STFT = gain * (x[n] - preemphasis * x[n-1]); preemphasis = 0, gain = 1 is the plain
+ * datasets/audio.py:melspectrogram. d_mel: fp32 [B][frames][num_mels] (time_major=1, the layout the preprocessor
+ * saves, datasets/preprocessor.py:158) or [B][num_mels][frames] (time_major=0, what audio.melspectrogram returns);
+ * d_linear: NULL or fp32 [B][frames][n_fft/2+1] / [B][n_fft/2+1][frames]. */
+int t2_stft_mel_f32(const t2_audio_config_t* cfg, const void* d_plan, const float* d_wav, int B, int n_samples,
+                    float preemphasis, float gain, float* d_mel, float* d_linear, int time_major, void* stream);
+int t2_preemphasis_f32(const float* d_x, float* d_y, int B, int n_samples, float k, void* stream);
+/* mu-law (mu forced to 255 like util.py:48,67,99,127); quantise truncates toward zero */
+int t2_mulaw_quantize_f32_i32(const float* d_in, int* d_out, long long n, void* stream);
+int t2_inv_mulaw_quantize_i32_f32(const int* d_in, float* d_out, long long n, void* stream);
+int t2_mulaw_f32(const float* d_in, float* d_out, long long n, void* stream);
+int t2_inv_mulaw_f32(const float* d_in, float* d_out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

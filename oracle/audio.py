@@ -160,25 +160,49 @@ def librosa_pad_lr(x, fsize, fshift, pad_sides=1):
 
 
 # ---- wavenet_vocoder/util.py:30-129 (mu is forced to 255 whatever the argument) ---------------------------
+# dtype semantics: the reference feeds float32 wavs (librosa.load) through numpy-1.14 value-based casting, i.e.
+# every step runs in float32; float64 input stays float64. numpy's float32 log1p is platform dependent (glibc /
+# SVML, <= a few ulp), so the float32 path here is DEFINED as "log1p evaluated in float64 then rounded to float32"
+# (= a correctly rounded log1pf); every other step is a plain IEEE float32 op. The CUDA kernel follows the same
+# definition, which makes mu-law indices bit-reproducible across machines.
+def _log1p_like(x):
+    if x.dtype == np.float32:
+        return np.log1p(x.astype(np.float64)).astype(np.float32)
+    return np.log1p(x)
+
+
 def mulaw(x, mu=256):
     mu = 255
-    return np.sign(x) * np.log1p(mu * np.abs(x)) / np.log1p(mu)
+    x = np.asarray(x)
+    if x.dtype != np.float32:
+        x = x.astype(np.float64)
+    dt = x.dtype.type
+    return np.sign(x) * _log1p_like(dt(mu) * np.abs(x)) / _log1p_like(np.array(mu, dtype=dt))
 
 
 def inv_mulaw(y, mu=256):
     mu = 255
-    return np.sign(y) * (1.0 / mu) * ((1.0 + mu) ** np.abs(y) - 1.0)
+    y = np.asarray(y)
+    if y.dtype != np.float32:
+        y = y.astype(np.float64)
+    dt = y.dtype.type
+    if y.dtype == np.float32:  # pow evaluated in float64 and rounded (platform-independent definition, see above)
+        p = np.power(np.float64(1.0 + mu), np.abs(y).astype(np.float64)).astype(np.float32)
+    else:
+        p = np.power(dt(1.0 + mu), np.abs(y))
+    return np.sign(y) * dt(1.0 / mu) * (p - dt(1.0))
 
 
 def mulaw_quantize(x, mu=256):
     mu = 255
-    y = mulaw(np.asarray(x), mu)
-    return ((y + 1) / 2 * mu).astype(np.int64)  # astype(int) truncates toward zero (util.py:99-102,156)
+    y = mulaw(x, mu)
+    dt = y.dtype.type
+    return ((y + dt(1)) / dt(2) * dt(mu)).astype(np.int64)  # astype(int) truncates toward zero (util.py:99-102,156)
 
 
 def inv_mulaw_quantize(y, mu=256):
     mu = 255
-    y = 2 * np.asarray(y).astype(np.float32) / mu - 1
+    y = np.float32(2) * np.asarray(y).astype(np.float32) / np.float32(mu) - np.float32(1)
     return inv_mulaw(y, mu)
 
 

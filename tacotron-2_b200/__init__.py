@@ -4,3 +4,5 @@ The directory name is not a Python identifier; import it through ``t2_import.py`
 (``from t2_import import t2``), which registers this package as ``tacotron2_b200``.
 """
 from . import lib  # noqa: F401
+from . import wavenet  # noqa: F401
+from . import audio  # noqa: F401

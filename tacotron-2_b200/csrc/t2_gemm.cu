@@ -96,12 +96,13 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
                T2_ERR_INVALID_ARG, "act_gemm: bad segment %d", s);
     ktot += c.seg[s].nkb * c.seg[s].nlayers * kBK;
   }
-  T2_REQUIRE(ktot <= ((c.wK + kBK - 1) / kBK) * kBK, T2_ERR_INVALID_ARG,
+  T2_REQUIRE(c.w_k0 + ktot <= ((c.wK + kBK - 1) / kBK) * kBK, T2_ERR_INVALID_ARG,
              "act_gemm: segments cover K=%d but packed weight has K=%d", ktot, c.wK);
   g.nseg = c.nseg;
   g.T = c.T;
   g.tiles_per_b = (c.T + kBM - 1) / kBM;
   g.b_layer = c.w_layer;
+  g.b_k0 = c.w_k0;
   g.epi = c.epi;
   dim3 grid(g.tiles_per_b * c.B, c.n_tiles, 1);
 #define T2_CASE(E, N) \

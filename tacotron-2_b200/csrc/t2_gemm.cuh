@@ -175,7 +175,9 @@ struct Epilogue<EPI_BIAS_ACT, BN> {
 
 // 256-way softmax cross entropy against the NEXT sample (wavenet.py:488, modules.py:781-798).
 // ptr: 0 targets int32 [B,T], 1 lengths int32 [B], 2 bias fp32 [256], 3 loss_sum fp32, 4 nonzero-count fp32,
-//      5 dlogits bf16 [pos,256] (nullable; un-normalised softmax - onehot), 6 logits fp32 [pos,256] (nullable)
+//      5 dlogits bf16 [pos, ld] (nullable; un-normalised softmax - onehot, stored as an error-compensated bf16 PAIR:
+//        columns [0,256) = hi, [256,512) = lo = bf16(v - hi) — the target entry p_y - 1 sits next to 1.0 where a single
+//        bf16 has 2^-8 spacing, i.e. it would lose p_y entirely), 6 logits fp32 [pos,256] (nullable);  i1 = ld (>= 512)
 template <>
 struct Epilogue<EPI_CE, 256> {
   static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
@@ -186,6 +188,7 @@ struct Epilogue<EPI_CE, 256> {
     __nv_bfloat16* dl = static_cast<__nv_bfloat16*>(e.ptr[5]);
     float* lo = static_cast<float*>(e.ptr[6]);
     const size_t row = (size_t(b) * T + t) * 256;
+    const size_t drow = (size_t(b) * T + t) * size_t(e.i[1]);
     const bool w = valid && (t + 1 < T) && (t + 1 < __ldg(len + b));
     const int y = w ? __ldg(tgt + size_t(b) * T + t + 1) : -1;
     float mx = -INFINITY, zy = 0.f;
@@ -220,11 +223,17 @@ struct Epilogue<EPI_CE, 256> {
         tmem_ld32f(trow + j0, v);
         if (valid) {
 #pragma unroll
+          float lo[32];
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
             float pj = __expf(v[j] + __ldg(bias + j0 + j) - mx) * inv;
-            v[j] = w ? (pj - ((j0 + j == y) ? 1.f : 0.f)) : 0.f;
+            const float d = w ? (pj - ((j0 + j == y) ? 1.f : 0.f)) : 0.f;
+            const float hi = __bfloat162float(__float2bfloat16(d));
+            v[j] = hi;
+            lo[j] = d - hi;
           }
-          store_bf16x32(dl + row + j0, v);
+          store_bf16x32(dl + drow + j0, v);
+          store_bf16x32(dl + drow + 256 + j0, lo);
         }
       }
     }
@@ -239,9 +248,9 @@ struct Epilogue<EPI_CE, 256> {
 
 // Discretised mixture-of-logistics NLL (wavenet_vocoder/models/mixture.py:18-74; masked mean
 // modules.py:800-817) with its analytic gradient. Tile has 32 columns: [logit(nm) | mean(nm) | log_scale(nm)].
-// ptr: 0 targets f32 [B,T], 1 lengths, 2 bias fp32 [3nm], 3 loss_sum, 4 mask_sum, 5 dyhat bf16 [pos,32]
-//      (nullable, un-normalised), 6 yhat fp32 [pos,32] (nullable)
-// f0 log_scale_min, f1 1/(num_classes-1), f2 log((num_classes-1)/2);  i0 = nr_mix (<= 10)
+// ptr: 0 targets f32 [B,T], 1 lengths, 2 bias fp32 [3nm], 3 loss_sum, 4 mask_sum, 5 dyhat bf16 [pos, ld]
+//      (nullable, un-normalised; 32 columns written), 6 yhat fp32 [pos,32] (nullable)
+// f0 log_scale_min, f1 1/(num_classes-1), f2 log((num_classes-1)/2);  i0 = nr_mix (<= 10), i1 = ld
 template <>
 struct Epilogue<EPI_MOL, 32> {
   static __device__ __forceinline__ float softplus(float x) {
@@ -328,7 +337,7 @@ struct Epilogue<EPI_MOL, 32> {
             g[2 * nm + k] = -post * ds[k];
           }
       }
-      store_bf16x32(dy + row, g);
+      store_bf16x32(dy + (size_t(b) * T + t) * size_t(e.i[1]), g);
     }
     float loss = warp_sum(w ? nll : 0.f);
     float cnt = warp_sum(w ? 1.f : 0.f);
@@ -499,7 +508,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) act_gemm_kernel(const __grid_
             uint8_t* sb = sa + Cfg::kABytes;
             tma_load_4d(sa, &g.amap[sg.map], &full_bar[stage], sg.k0 + kb * kBK, t0 + sg.shift, b,
                         sg.layer0 + l);
-            tma_load_3d(sb, &g.bmap, &full_bar[stage], kb_global * kBK, n_tile * BN, g.b_layer);
+            tma_load_3d(sb, &g.bmap, &full_bar[stage], g.b_k0 + kb_global * kBK, n_tile * BN, g.b_layer);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -636,9 +645,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __gri
       if (m < tile.m_valid) {
         for (int j = 0; j < 32; ++j) {
           if (j0 + j < tile.n_valid) {
-            float r = v[j] * sc;
-            if (tile.accumulate) r += out[j0 + j];
-            out[j0 + j] = r;
+            const float r = v[j] * sc;
+            if (tile.accumulate == 2) atomicAdd(out + j0 + j, r);
+            else if (tile.accumulate == 1) out[j0 + j] += r;
+            else out[j0 + j] = r;
           }
         }
       }

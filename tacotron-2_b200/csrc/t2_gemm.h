@@ -24,7 +24,7 @@ struct ActGemmCall {
   Seg seg[kMaxSeg];
   int nseg;
   const void* w;   // packed bf16 weights [wL][wN][wK], K contiguous
-  int wN, wK, wL, w_layer;
+  int wN, wK, wL, w_layer, w_k0;
   int T, B;
   int n_tiles;     // grid.y
   EpiArgs epi;

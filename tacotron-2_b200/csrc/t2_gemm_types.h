@@ -34,6 +34,7 @@ struct GemmArgs {
   int T;             // time steps per batch item
   int tiles_per_b;   // ceil(T / 128)
   int b_layer;       // layer coordinate of the weight tensor map (3-D maps), else 0
+  int b_k0;          // first K column of the packed weight this GEMM consumes
   EpiArgs epi;
 };
 
@@ -56,7 +57,7 @@ struct WgradTile {
   int ldc;             // row pitch (elements) of the output
   int m_valid, n_valid;
   float scale;
-  int accumulate;      // 0: overwrite, 1: add to existing
+  int accumulate;      // 0: overwrite, 1: add to existing (single writer), 2: atomicAdd (several tiles share an output)
   const float* div;    // optional device scalar: result is divided by max(*div, tiny)
 };
 struct WgradArgs {

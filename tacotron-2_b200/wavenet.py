@@ -1,0 +1,198 @@
+"""Host side of the B200 WaveNet vocoder: owns device buffers (torch tensors) and drives libt2b200.so.
+
+Mirrors the reference's model object (wavenet_vocoder/models/wavenet.py): ``WaveNet(hparams)`` then
+``initialize`` / ``step`` (forward), ``add_loss`` (loss) and ``add_optimizer`` (Adam + clipping + EMA) collapse into
+``forward`` / ``backward`` / ``optimizer_step`` / ``train_step`` here, because there is no graph to build.
+All arithmetic runs in the CUDA library; torch is used for allocation, streams, CUDA graphs and NCCL.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import lib as L
+
+
+class WnConfig(ctypes.Structure):
+    _fields_ = [
+        ("layers", ctypes.c_int), ("stacks", ctypes.c_int), ("residual_channels", ctypes.c_int),
+        ("gate_channels", ctypes.c_int), ("skip_out_channels", ctypes.c_int), ("kernel_size", ctypes.c_int),
+        ("cin_channels", ctypes.c_int), ("out_channels", ctypes.c_int), ("quantize_channels", ctypes.c_int),
+        ("input_type", ctypes.c_int), ("legacy", ctypes.c_int), ("residual_legacy", ctypes.c_int),
+        ("upsample_type", ctypes.c_int), ("n_upsample", ctypes.c_int), ("upsample_scales", ctypes.c_int * 4),
+        ("freq_axis_kernel_size", ctypes.c_int), ("dropout", ctypes.c_float), ("log_scale_min", ctypes.c_float),
+        ("B", ctypes.c_int), ("T", ctypes.c_int), ("Tc", ctypes.c_int), ("c_pre_upsampled", ctypes.c_int),
+    ]
+
+
+class WnSizes(ctypes.Structure):
+    _fields_ = [("n_params", ctypes.c_longlong), ("packed_bytes", ctypes.c_longlong),
+                ("workspace_bytes", ctypes.c_longlong), ("n_tensors", ctypes.c_int)]
+
+
+_INPUT_TYPES = {"raw": 0, "mulaw": 1, "mulaw-quantize": 2}
+_UPSAMPLE_TYPES = {"SubPixel": 0, "2D": 1}
+
+
+def make_config(hp, B, T, c_pre_upsampled=False, dropout=None):
+    cfg = WnConfig()
+    cfg.layers, cfg.stacks = hp.layers, hp.stacks
+    cfg.residual_channels, cfg.gate_channels, cfg.skip_out_channels = (
+        hp.residual_channels, hp.gate_channels, hp.skip_out_channels)
+    cfg.kernel_size = hp.kernel_size
+    cfg.cin_channels = max(hp.cin_channels, 0)
+    cfg.out_channels, cfg.quantize_channels = hp.out_channels, hp.quantize_channels
+    cfg.input_type = _INPUT_TYPES[hp.input_type]
+    cfg.legacy, cfg.residual_legacy = int(hp.legacy), int(hp.residual_legacy)
+    if hp.upsample_type not in _UPSAMPLE_TYPES:
+        raise L.T2Error("upsample_type %r is not implemented on the B200 path" % hp.upsample_type)
+    cfg.upsample_type = _UPSAMPLE_TYPES[hp.upsample_type]
+    scales = list(hp.upsample_scales)
+    cfg.n_upsample = len(scales)
+    for i, s in enumerate(scales):
+        cfg.upsample_scales[i] = s
+    cfg.freq_axis_kernel_size = hp.freq_axis_kernel_size
+    cfg.dropout = hp.wavenet_dropout if dropout is None else dropout
+    cfg.log_scale_min = hp.log_scale_min
+    cfg.B, cfg.T = B, T
+    hop = 1
+    for s in scales:
+        hop *= s
+    cfg.c_pre_upsampled = int(c_pre_upsampled)
+    if cfg.cin_channels > 0 and not c_pre_upsampled:
+        if T % hop:
+            raise L.T2Error("T=%d is not a multiple of prod(upsample_scales)=%d" % (T, hop))
+        cfg.Tc = T // hop
+    else:
+        cfg.Tc = T
+    return cfg
+
+
+class WaveNet(object):
+    """B200 WaveNet (train path). Parameters live in ONE flat fp32 buffer in TensorFlow variable layouts."""
+
+    def __init__(self, hparams, B, T, device="cuda", c_pre_upsampled=False, dropout=None, training=True):
+        self.hp = hparams
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.cfg = make_config(hparams, B, T, c_pre_upsampled, dropout)
+        self.training = training
+        sz = WnSizes()
+        L.check(self.lib.t2_wn_sizes(ctypes.byref(self.cfg), ctypes.byref(sz)))
+        self.sizes = sz
+        self.n_params = sz.n_params
+        self.params = torch.zeros(sz.n_params, dtype=torch.float32, device=self.device)
+        self.packed = torch.empty(sz.packed_bytes, dtype=torch.uint8, device=self.device)
+        self.workspace = torch.empty(sz.workspace_bytes, dtype=torch.uint8, device=self.device)
+        self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.grads = self.m = self.v = self.ema = None
+        self.tensors = []  # (name, offset, shape)
+        name = ctypes.create_string_buffer(160)
+        off = ctypes.c_longlong()
+        nd = ctypes.c_int()
+        shp = (ctypes.c_int * 4)()
+        for i in range(sz.n_tensors):
+            L.check(self.lib.t2_wn_param_info(ctypes.byref(self.cfg), i, name, 160, ctypes.byref(off),
+                                              ctypes.byref(nd), shp))
+            self.tensors.append((name.value.decode(), off.value, tuple(shp[k] for k in range(nd.value))))
+        offs = [t[1] for t in self.tensors] + [sz.n_params]
+        self.offsets = torch.tensor(offs, dtype=torch.int64, device=self.device)
+        self.opt_scratch = torch.zeros(sz.n_tensors + 2, dtype=torch.float32, device=self.device)
+        self.global_step = 0
+        self.seed = int(hparams.wavenet_random_seed)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.t2_wn_init(ctypes.byref(self.cfg), L.ptr(self.packed), L.ptr(self.workspace),
+                                        L.stream_ptr()))
+        self._packed_dirty = True
+
+    # ---- parameters --------------------------------------------------------------------------------------
+    def load_params(self, params):
+        """params: {TF-style name: tensor in TF layout} (e.g. from oracle.wavenet.init_params)."""
+        flat = torch.zeros(self.n_params, dtype=torch.float32)
+        for name, off, shape in self.tensors:
+            t = params[name].detach().to(torch.float32).reshape(-1)
+            n = int(math.prod(shape))
+            assert t.numel() == n, "%s: expected %s got %s" % (name, shape, tuple(params[name].shape))
+            flat[off:off + n] = t
+        self.params.copy_(flat.to(self.device))
+        self._packed_dirty = True
+
+    def unflatten(self, flat):
+        flat = flat.detach().float().cpu()
+        return {name: flat[off:off + int(math.prod(shape))].reshape(shape).clone() for name, off, shape in self.tensors}
+
+    def export_params(self):
+        return self.unflatten(self.params)
+
+    def export_grads(self):
+        return self.unflatten(self.grads)
+
+    def pack(self):
+        L.check(self.lib.t2_wn_pack_weights(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
+                                            L.ptr(self.workspace), L.stream_ptr()))
+        self._packed_dirty = False
+
+    # ---- compute -----------------------------------------------------------------------------------------
+    def forward(self, x, c, targets, lengths, logits=None, save_for_backward=True, seed=None):
+        """x: int32 [B,T] (mulaw-quantize) or fp32 [B,T]; c: fp32 [B,cin,Tc]; returns loss_buf (sum, normaliser)."""
+        if self._packed_dirty:
+            self.pack()
+        self._last_x, self._last_c = x, c
+        self._last_seed = self.seed + self.global_step if seed is None else seed
+        L.check(self.lib.t2_wn_forward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
+                                       L.ptr(self.workspace), L.ptr(x), L.ptr(c), L.ptr(targets), L.ptr(lengths),
+                                       L.ptr(self.loss_buf), L.ptr(logits), int(save_for_backward),
+                                       ctypes.c_ulonglong(self._last_seed), L.stream_ptr()))
+        return self.loss_buf
+
+    def backward(self):
+        if self.grads is None:
+            self.grads = torch.zeros_like(self.params)
+        L.check(self.lib.t2_wn_backward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
+                                        L.ptr(self.workspace), L.ptr(self._last_x), L.ptr(self._last_c),
+                                        L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed), L.stream_ptr()))
+        return self.grads
+
+    def learning_rate(self):
+        hp = self.hp
+        if hp.wavenet_lr_schedule == "noam":
+            step = float(self.global_step + 1)
+            w = hp.wavenet_warmup
+            return max(hp.wavenet_learning_rate * w ** 0.5 * min(step * w ** -1.5, step ** -0.5), 1e-4)
+        return hp.wavenet_learning_rate * hp.wavenet_decay_rate ** (self.global_step / hp.wavenet_decay_steps)
+
+    def optimizer_step(self, grad_scale=1.0):
+        """Adam + per-tensor clip (wavenet.py:586-593) + EMA (:613) on the flat buffers."""
+        hp = self.hp
+        if self.m is None:
+            self.m = torch.zeros_like(self.params)
+            self.v = torch.zeros_like(self.params)
+            self.ema = self.params.clone()
+        lr = self.learning_rate()
+        clip = hp.wavenet_clip_gradients
+        L.check(self.lib.t2_adam_step(
+            L.ptr(self.params), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v), L.ptr(self.ema),
+            L.ptr(self.offsets), len(self.tensors), ctypes.c_longlong(self.n_params), ctypes.c_float(lr),
+            ctypes.c_float(hp.wavenet_adam_beta1), ctypes.c_float(hp.wavenet_adam_beta2),
+            ctypes.c_float(hp.wavenet_adam_epsilon), self.global_step + 1, ctypes.c_float(grad_scale),
+            ctypes.c_float(hp.wavenet_gradient_max_norm if clip else 0.0),
+            ctypes.c_float(hp.wavenet_gradient_max_value if clip else 0.0), ctypes.c_float(0.0),
+            ctypes.c_float(hp.wavenet_ema_decay), L.ptr(self.opt_scratch), L.stream_ptr()))
+        self.global_step += 1
+        self._packed_dirty = True
+        return lr
+
+    def workspace_tensor(self, name, shape=None):
+        p = ctypes.c_void_p()
+        cnt = ctypes.c_longlong()
+        eb = ctypes.c_int()
+        L.check(self.lib.t2_wn_workspace_tensor(ctypes.byref(self.cfg), L.ptr(self.workspace), name.encode(),
+                                                ctypes.byref(p), ctypes.byref(cnt), ctypes.byref(eb)))
+        off = p.value - self.workspace.data_ptr()
+        raw = self.workspace[off:off + cnt.value * eb.value]
+        t = raw.view(torch.bfloat16 if eb.value == 2 else torch.float32)
+        return t.reshape(shape) if shape is not None else t
+
+    def loss_value(self):
+        s, n = self.loss_buf.tolist()
+        return s / max(n, 1e-20)
