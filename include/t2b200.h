@@ -32,6 +32,8 @@ extern "C" {
 
 const char* t2_last_error(void);
 int t2_abi_version(void);
+/* kernels launched (or captured) by this library so far in this process */
+long long t2_launch_count(void);
 
 /* ---- engine-level test hooks (tests/test_gemm_engine.py) --------------------------------------------- */
 /* bf16 dilated-conv-as-GEMM on the tcgen05 engine: out[b,t,n] = act(sum_s sum_k a[b,t+shift_s,k] w[n,s*Kp+k] + bias[n])
@@ -84,13 +86,20 @@ int t2_wn_pack_weights(const t2_wn_config_t* cfg, const float* d_params, void* d
 /* forward + loss. d_x: int32 [B,T] mu-law indices (input_type 2) or fp32 [B,T] samples; d_c: fp32 [B,cin,Tc]
  * (or [B,T,cin] when c_pre_upsampled); d_targets: int32 / fp32 [B,T]; d_lengths int32 [B].
  * d_loss: fp32[2] = {sum of masked losses, normaliser} (loss = [0]/[1]); d_logits: optional fp32 [B,T,ldo]
- * (ldo = 256, or 32 for MoL). save_for_backward=0 skips the backward stashes. */
+ * (ldo = 256, or 32 for MoL). save_for_backward=0 skips the backward stashes. Dropout masks are a pure function of
+ * (seed + *d_step, layer, position, channel); d_step (device u64, nullable) lets a replayed CUDA graph advance. */
 int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
                   const void* d_x, const float* d_c, const void* d_targets, const int* d_lengths, float* d_loss,
-                  float* d_logits, int save_for_backward, unsigned long long seed, void* stream);
+                  float* d_logits, int save_for_backward, unsigned long long seed,
+                  const unsigned long long* d_step, void* stream);
 /* backward of the last t2_wn_forward(save_for_backward=1): writes all parameter gradients (d loss / d theta) */
 int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
-                   const void* d_x, const float* d_c, float* d_grads, unsigned long long seed, void* stream);
+                   const void* d_x, const float* d_c, float* d_grads, unsigned long long seed,
+                   const unsigned long long* d_step, void* stream);
+/* measurement hook for bench.py's roofline leg: average device time (CUDA events on `stream`) of `reps` launches of
+ * layer `layer`'s gate GEMM over the activations left in the workspace by the last forward; synchronises */
+int t2_wn_time_gate_gemm(const t2_wn_config_t* cfg, const void* d_packed, void* d_workspace, int layer, int reps,
+                         float* ms_per_launch, void* stream);
 /* debug / test access to workspace tensors by name ("x", "z", "c_up", "h1", "dg", ...): returns device pointer,
  * element count and element size */
 int t2_wn_workspace_tensor(const t2_wn_config_t* cfg, void* d_workspace, const char* name, void** ptr,

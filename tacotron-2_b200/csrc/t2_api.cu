@@ -9,7 +9,11 @@
 #include "t2_common.cuh"
 #include "t2_gemm.h"
 
+#include <atomic>
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void t2_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long t2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int t2_set_error(int code, const char* fmt, ...) {
   va_list ap;

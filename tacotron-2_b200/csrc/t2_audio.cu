@@ -346,7 +346,7 @@ extern "C" int t2_stft_mel_f32(const t2_audio_config_t* cfg, const void* d_plan,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long cap = (long long)sms * 4;  // 4 resident CTAs per SM (41 KB smem, 256 threads each)
   const unsigned grid = (unsigned)(total < cap ? total : cap);
-  stft_mel_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  stft_mel_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
@@ -354,7 +354,7 @@ extern "C" int t2_stft_mel_f32(const t2_audio_config_t* cfg, const void* d_plan,
 extern "C" int t2_preemphasis_f32(const float* d_x, float* d_y, int B, int n_samples, float k, void* stream) {
   const long long n = (long long)B * n_samples;
   T2_REQUIRE(d_x && d_y && n > 0, T2_ERR_INVALID_ARG, "preemphasis: bad arguments");
-  preemphasis_kernel<<<nblk(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, n_samples, n, k);
+  preemphasis_kernel<<<nblk(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, n_samples, n, k); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
@@ -362,7 +362,7 @@ extern "C" int t2_preemphasis_f32(const float* d_x, float* d_y, int B, int n_sam
   extern "C" int NAME(const TIN* d_in, TOUT* d_out, long long n, void* stream) {                  \
     T2_REQUIRE(d_in && d_out && n >= 0, T2_ERR_INVALID_ARG, #NAME ": bad arguments");             \
     if (n == 0) return T2_OK;                                                                     \
-    KERNEL<<<nblk(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_out, n);               \
+    KERNEL<<<nblk(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_out, n); t2_count_launch();               \
     T2_CHECK_CUDA(cudaGetLastError());                                                            \
     return T2_OK;                                                                                 \
   }

@@ -15,6 +15,8 @@
 
 // host-side error plumbing (defined in t2_api.cu)
 int t2_set_error(int code, const char* fmt, ...);
+// number of kernels this library has launched (or recorded into a capturing stream) in this process
+void t2_count_launch(int n = 1);
 #define T2_CHECK_CUDA(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \
@@ -52,11 +54,12 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-// tanh via exp: accurate to ~1e-7 relative over the useful range, saturates cleanly.
+// sigmoid / tanh on the SFU pipe: ex2.approx + rcp.approx (2 MUFU + 2-3 FMA-pipe ops per value, ~1e-7 absolute
+// error) instead of the IEEE-division sequence; the results are stored as bf16 anyway.
+__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) {
-  float e = __expf(-2.f * fabsf(x));
-  float t = (1.f - e) / (1.f + e);
+  const float e = __expf(-2.f * fabsf(x));
+  const float t = (1.f - e) * __frcp_rn(1.f + e);
   return copysignf(t, x);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -77,6 +80,16 @@ __device__ __host__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t id
 }
 __device__ __host__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
   return (hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f);  // [0,1)
+}
+// cheap per-element variant for dropout masks: fold (seed, stream) once per thread, then a murmur3-style 32-bit
+// finaliser per element index (the index may exceed 2^32: both halves are mixed in).
+__device__ __host__ __forceinline__ uint32_t hash_seed(uint64_t seed, uint32_t stream) {
+  return hash_u32(seed, stream);
+}
+__device__ __host__ __forceinline__ float hash_uniform32(uint32_t hs, uint64_t idx) {
+  uint32_t h = hs ^ (uint32_t(idx) * 0x9E3779B1u) ^ (uint32_t(idx >> 32) * 0x85EBCA77u);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return (h >> 8) * (1.0f / 16777216.0f);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -73,7 +73,8 @@ static int launch_one(const GemmArgs& g, dim3 grid, cudaStream_t stream) {
                                        Cfg::kSmemBytes));
     configured = true;
   }
-  act_gemm_kernel<EPI, BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(g);
+  act_gemm_kernel<EPI, BN><<<grid, kActGemmThreads, Cfg::kSmemBytes, stream>>>(g);
+  t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
@@ -143,6 +144,7 @@ int launch_wgrad(const ActT* maps, int nmaps, const WgradTile* tiles_dev, int nt
     configured = true;
   }
   wgrad_gemm_kernel<<<ntiles, kGemmThreads, kWgSmemBytes, stream>>>(g);
+  t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }

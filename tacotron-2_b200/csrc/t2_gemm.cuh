@@ -56,8 +56,97 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogues. Each runs per thread = per output row (b, t); `trow` is the TMEM address of the row's
-// first accumulator column, `valid` is false for rows past T (tail tile) — those rows must not store.
+// Epilogue staging: a thread owns one accumulator ROW (TMEM lane), but global memory wants a warp to touch one
+// row's contiguous bytes. Every epilogue therefore moves 32-row x 128-column bf16 tiles through a per-warp
+// shared-memory tile (the pipeline stages are free once the last MMA has committed): rows are written / read by
+// their owning lane, global traffic is issued with 16 lanes covering one 256-byte row segment.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTilePitch = 256 + 16;              // bytes per staged row: 128 bf16 + 16 B pad (bank spread)
+constexpr int kTileBytes = 32 * kTilePitch;       // 8704
+constexpr int kEpiTilesPerWarp = 4;
+constexpr int kEpiWarpBytes = kEpiTilesPerWarp * kTileBytes;
+
+constexpr int kActEpiWarps = 16;                               // 4 TMEM lane quarters x 4 column groups
+constexpr int kActGemmThreads = 64 + 32 * kActEpiWarps;        // + producer warp + MMA warp
+
+struct EpiCtx {
+  int n_tile, b, t, T;     // output column tile, batch item, this lane's time step, sequence length
+  bool valid;              // t < T
+  int lane;
+  int cg;                  // column group 0..3: this warp owns columns [32*cg, 32*cg+32) of every 128-column group
+  int qbar;                // named barrier shared by the 4 warps of this TMEM lane quarter
+  size_t row0;             // b*T + (first time step of this warp)
+  int nrows;               // valid rows among this warp's 32
+  uint32_t trow;           // TMEM address of this warp's lanes, column 0
+  uint8_t* wbuf;           // kEpiWarpBytes of shared memory shared by the 4 warps of this lane quarter
+};
+
+__device__ __forceinline__ void stage_put(uint8_t* tile, int lane, int cq, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(tile + lane * kTilePitch + cq * 64);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+    d[q] = u;
+  }
+}
+__device__ __forceinline__ void stage_get(const uint8_t* tile, int lane, int cq, float (&v)[32]) {
+  const uint4* s = reinterpret_cast<const uint4*>(tile + lane * kTilePitch + cq * 64);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = s[q];
+    v[q * 8 + 0] = bf16lo(u.x); v[q * 8 + 1] = bf16hi(u.x);
+    v[q * 8 + 2] = bf16lo(u.y); v[q * 8 + 3] = bf16hi(u.y);
+    v[q * 8 + 4] = bf16lo(u.z); v[q * 8 + 5] = bf16hi(u.z);
+    v[q * 8 + 6] = bf16lo(u.w); v[q * 8 + 7] = bf16hi(u.w);
+  }
+}
+__device__ __forceinline__ void quarter_sync(int id) {
+  asm volatile("bar.sync %0, 128;\n" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void load_f32x32(const float* p, float (&v)[32]) {
+  const float4* s = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = __ldg(s + q);
+    v[q * 4] = f.x; v[q * 4 + 1] = f.y; v[q * 4 + 2] = f.z; v[q * 4 + 3] = f.w;
+  }
+}
+// smem tile -> global rows g + r*ld (elements), 128 columns each; rows >= nrows are skipped.
+// NW warps cooperate (each moves 32/NW rows); with NW == 4 the quarter barrier orders it after every warp's puts.
+template <int NW>
+__device__ __forceinline__ void tile_flush(const uint8_t* tile, __nv_bfloat16* g, size_t ld, int nrows, const EpiCtx& c) {
+  if (NW == 4) quarter_sync(c.qbar); else __syncwarp();
+  const int ch = c.lane & 15, rh = c.lane >> 4;
+  const int it0 = NW == 4 ? c.cg * 4 : 0;
+#pragma unroll
+  for (int i = 0; i < 16 / NW; ++i) {
+    const int r = (it0 + i) * 2 + rh;
+    if (r < nrows)
+      *reinterpret_cast<uint4*>(g + size_t(r) * ld + ch * 8) = *reinterpret_cast<const uint4*>(tile + r * kTilePitch + ch * 16);
+  }
+  if (NW == 4) quarter_sync(c.qbar); else __syncwarp();
+}
+// global rows -> smem tile (rows >= nrows are zero-filled)
+template <int NW>
+__device__ __forceinline__ void tile_fill(uint8_t* tile, const __nv_bfloat16* g, size_t ld, int nrows, const EpiCtx& c) {
+  const int ch = c.lane & 15, rh = c.lane >> 4;
+  const int it0 = NW == 4 ? c.cg * 4 : 0;
+#pragma unroll
+  for (int i = 0; i < 16 / NW; ++i) {
+    const int r = (it0 + i) * 2 + rh;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r < nrows) u = __ldg(reinterpret_cast<const uint4*>(g + size_t(r) * ld + ch * 8));
+    *reinterpret_cast<uint4*>(tile + r * kTilePitch + ch * 16) = u;
+  }
+  if (NW == 4) quarter_sync(c.qbar); else __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues (one specialisation per fused op)
 // ------------------------------------------------------------------------------------------------
 template <int EPI, int BN>
 struct Epilogue;
@@ -67,45 +156,49 @@ struct Epilogue;
 // ptr: 0 ta_out, 1 sb_out, 2 z_out (bf16 [pos, Gh]), 3 bias fp32 [2*Gh];  i0 = Gh
 template <>
 struct Epilogue<EPI_GATE, 256> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int Gh = e.i[0];
-    const int cb = n_tile * 128;
+    const int cb = c.n_tile * 128;
     const float* bias = static_cast<const float*>(e.ptr[3]);
-    const size_t row = (size_t(b) * T + t) * Gh;
     __nv_bfloat16* ta_o = static_cast<__nv_bfloat16*>(e.ptr[0]);
     __nv_bfloat16* sb_o = static_cast<__nv_bfloat16*>(e.ptr[1]);
     __nv_bfloat16* z_o = static_cast<__nv_bfloat16*>(e.ptr[2]);
-#pragma unroll 1
-    for (int j0 = 0; j0 < 128; j0 += 32) {
-      float a[32], g[32];
-      tmem_ld32f(trow + j0, a);
-      tmem_ld32f(trow + 128 + j0, g);
+    uint8_t* t_ta = c.wbuf;
+    uint8_t* t_sb = c.wbuf + kTileBytes;
+    uint8_t* t_z = c.wbuf + 2 * kTileBytes;
+    {
+      const int cq = c.cg;
+      float a[32], g[32], ba[32], bb[32];
+      load_f32x32(bias + cb + cq * 32, ba);
+      load_f32x32(bias + Gh + cb + cq * 32, bb);
+      tmem_ld32f(c.trow + cq * 32, a);
+      tmem_ld32f(c.trow + 128 + cq * 32, g);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float ta = tanhf_(a[j] + __ldg(bias + cb + j0 + j));
-        float sb = sigmoidf_(g[j] + __ldg(bias + Gh + cb + j0 + j));
-        a[j] = ta;
-        g[j] = sb;
+        a[j] = tanhf_(a[j] + ba[j]);
+        g[j] = sigmoidf_(g[j] + bb[j]);
       }
-      if (valid) {
-        if (ta_o) store_bf16x32(ta_o + row + cb + j0, a);
-        if (sb_o) store_bf16x32(sb_o + row + cb + j0, g);
+      if (ta_o) { stage_put(t_ta, c.lane, cq, a); stage_put(t_sb, c.lane, cq, g); }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] *= g[j];
-        store_bf16x32(z_o + row + cb + j0, a);
-      }
+      for (int j = 0; j < 32; ++j) a[j] *= g[j];
+      stage_put(t_z, c.lane, cq, a);
     }
+    const size_t off = c.row0 * Gh + cb;
+    if (ta_o) {
+      tile_flush<4>(t_ta, ta_o + off, Gh, c.nrows, c);
+      tile_flush<4>(t_sb, sb_o + off, Gh, c.nrows, c);
+    }
+    tile_flush<4>(t_z, z_o + off, Gh, c.nrows, c);
   }
 };
 
 // residual output of the block (modules.py:512-520): x_out = (W_o z + b_o + x) * res_scale, plus the
 // dropped-out copy the NEXT layer's dilated conv consumes (modules.py:483-484).
-// ptr: 0 x_in, 1 x_out, 2 xd_out (nullable), 3 bias fp32 [R];  f0 res_scale, f1 dropout p;  i1 = layer
+// ptr: 0 x_in, 1 x_out, 2 xd_out (nullable), 3 bias fp32 [R], 7 device u64 added to the seed (nullable; lets a
+// replayed CUDA graph draw fresh masks);  f0 res_scale, f1 dropout p;  i1 = layer
 template <int BN>
 struct Epilogue<EPI_RES, BN> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int R = BN;
     const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
     __nv_bfloat16* x_out = static_cast<__nv_bfloat16*>(e.ptr[1]);
@@ -113,24 +206,34 @@ struct Epilogue<EPI_RES, BN> {
     const float* bias = static_cast<const float*>(e.ptr[3]);
     const float rs = e.f[0], p = e.f[1];
     const float keep_inv = 1.f / (1.f - p);
-    const size_t row = (size_t(b) * T + t) * R;
+    const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
+    const uint32_t hs = hash_seed(seed, uint32_t(e.i[1]));
+    const size_t row = (size_t(c.b) * c.T + c.t) * R;
+    uint8_t* t_x = c.wbuf;
+    uint8_t* t_o = c.wbuf + kTileBytes;
+    uint8_t* t_d = c.wbuf + 2 * kTileBytes;
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-      float acc[32], x[32];
-      tmem_ld32f(trow + j0, acc);
-      if (valid) {
-        load_bf16x32(x_in + row + j0, x);
+    for (int gq = 0; gq < BN / 128; ++gq) {
+      tile_fill<4>(t_x, x_in + c.row0 * R + gq * 128, R, c.nrows, c);
+      {
+        const int cq = c.cg;
+        const int j0 = gq * 128 + cq * 32;
+        float acc[32], x[32], bv[32];
+        load_f32x32(bias + j0, bv);
+        tmem_ld32f(c.trow + j0, acc);
+        stage_get(t_x, c.lane, cq, x);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + __ldg(bias + j0 + j) + x[j]) * rs;
-        store_bf16x32(x_out + row + j0, acc);
+        for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + bv[j] + x[j]) * rs;
+        stage_put(t_o, c.lane, cq, acc);
         if (xd_out) {
-          const uint64_t base = (uint64_t(e.i[1]) << 40) + row + j0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            acc[j] = (hash_uniform(e.seed, base + j) >= p) ? acc[j] * keep_inv : 0.f;
-          store_bf16x32(xd_out + row + j0, acc);
+            acc[j] = (hash_uniform32(hs, row + j0 + j) >= p) ? acc[j] * keep_inv : 0.f;
+          stage_put(t_d, c.lane, cq, acc);
         }
       }
+      tile_flush<4>(t_o, x_out + c.row0 * R + gq * 128, R, c.nrows, c);
+      if (xd_out) tile_flush<4>(t_d, xd_out + c.row0 * R + gq * 128, R, c.nrows, c);
     }
   }
 };
@@ -139,36 +242,44 @@ struct Epilogue<EPI_RES, BN> {
 // [pos, ldo] (nullable);  i0 = ldo, i1 = act (0 none, 1 relu), i2 = n_valid columns
 template <int BN>
 struct Epilogue<EPI_BIAS_ACT, BN> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int ldo = e.i[0], act = e.i[1], nvalid = e.i[2];
     __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(e.ptr[0]);
     const float* bias = static_cast<const float*>(e.ptr[1]);
     float* of = static_cast<float*>(e.ptr[2]);
-    const size_t row = (size_t(b) * T + t) * ldo;
+    const size_t row = (size_t(c.b) * c.T + c.t) * ldo;
+    uint8_t* t_o = c.wbuf;
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-      const int c0 = n_tile * BN + j0;
-      if (c0 >= nvalid) break;  // warp-uniform
-      float acc[32];
-      tmem_ld32f(trow + j0, acc);
-      if (!valid) continue;
+    for (int gq = 0; gq < BN / 128; ++gq) {
+      const int g0 = c.n_tile * BN + gq * 128;
+      if (g0 >= nvalid) break;  // warp-uniform
+      const bool full = g0 + 128 <= nvalid;
+      {
+        const int cq = c.cg;
+        const int c0 = g0 + cq * 32;
+        float acc[32];
+        if (c0 < nvalid) tmem_ld32f(c.trow + gq * 128 + cq * 32, acc);
+        else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v = acc[j];
-        if (bias && c0 + j < nvalid) v += __ldg(bias + c0 + j);
-        if (act == 1) v = fmaxf(v, 0.f);
-        acc[j] = v;
-      }
-      if (c0 + 32 <= nvalid) {
-        if (ob) store_bf16x32(ob + row + c0, acc);
-        if (of) store_f32x32(of + row + c0, acc);
-      } else {
-        for (int j = 0; j < 32 && c0 + j < nvalid; ++j) {
-          if (ob) ob[row + c0 + j] = __float2bfloat16(acc[j]);
-          if (of) of[row + c0 + j] = acc[j];
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = acc[j];
+          if (bias && c0 + j < nvalid) v += __ldg(bias + c0 + j);
+          if (act == 1) v = fmaxf(v, 0.f);
+          acc[j] = v;
+        }
+        if (ob && full) stage_put(t_o, c.lane, cq, acc);
+        if (c.valid && c0 < nvalid) {
+          if (of) {
+            if (c0 + 32 <= nvalid) store_f32x32(of + row + c0, acc);
+            else for (int j = 0; j < 32 && c0 + j < nvalid; ++j) of[row + c0 + j] = acc[j];
+          }
+          if (ob && !full) for (int j = 0; j < 32 && c0 + j < nvalid; ++j) ob[row + c0 + j] = __float2bfloat16(acc[j]);
         }
       }
+      if (ob && full) tile_flush<4>(t_o, ob + c.row0 * ldo + g0, ldo, c.nrows, c);
     }
   }
 };
@@ -180,35 +291,35 @@ struct Epilogue<EPI_BIAS_ACT, BN> {
 //        bf16 has 2^-8 spacing, i.e. it would lose p_y entirely), 6 logits fp32 [pos,256] (nullable);  i1 = ld (>= 512)
 template <>
 struct Epilogue<EPI_CE, 256> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
+    if (c.cg != 0) return;  // row-wise softmax: one warp per lane quarter walks all 256 columns
     const int* tgt = static_cast<const int*>(e.ptr[0]);
     const int* len = static_cast<const int*>(e.ptr[1]);
     const float* bias = static_cast<const float*>(e.ptr[2]);
     __nv_bfloat16* dl = static_cast<__nv_bfloat16*>(e.ptr[5]);
-    float* lo = static_cast<float*>(e.ptr[6]);
-    const size_t row = (size_t(b) * T + t) * 256;
-    const size_t drow = (size_t(b) * T + t) * size_t(e.i[1]);
-    const bool w = valid && (t + 1 < T) && (t + 1 < __ldg(len + b));
-    const int y = w ? __ldg(tgt + size_t(b) * T + t + 1) : -1;
+    float* lo_out = static_cast<float*>(e.ptr[6]);
+    const size_t ld = size_t(e.i[1]);
+    const size_t row = (size_t(c.b) * c.T + c.t) * 256;
+    const bool w = c.valid && (c.t + 1 < c.T) && (c.t + 1 < __ldg(len + c.b));
+    const int y = w ? __ldg(tgt + size_t(c.b) * c.T + c.t + 1) : -1;
     float mx = -INFINITY, zy = 0.f;
 #pragma unroll 1
     for (int j0 = 0; j0 < 256; j0 += 32) {
       float v[32];
-      tmem_ld32f(trow + j0, v);
+      tmem_ld32f(c.trow + j0, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         v[j] += __ldg(bias + j0 + j);
         mx = fmaxf(mx, v[j]);
         if (j0 + j == y) zy = v[j];
       }
-      if (lo && valid) store_f32x32(lo + row + j0, v);
+      if (lo_out && c.valid) store_f32x32(lo_out + row + j0, v);
     }
     float se = 0.f;
 #pragma unroll 1
     for (int j0 = 0; j0 < 256; j0 += 32) {
       float v[32];
-      tmem_ld32f(trow + j0, v);
+      tmem_ld32f(c.trow + j0, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) se += __expf(v[j] + __ldg(bias + j0 + j) - mx);
     }
@@ -217,29 +328,33 @@ struct Epilogue<EPI_CE, 256> {
     float cnt = (loss != 0.f) ? 1.f : 0.f;
     if (dl) {
       const float inv = 1.f / se;
+      uint8_t* t_hi = c.wbuf;
+      uint8_t* t_lo = c.wbuf + kTileBytes;
 #pragma unroll 1
-      for (int j0 = 0; j0 < 256; j0 += 32) {
-        float v[32];
-        tmem_ld32f(trow + j0, v);
-        if (valid) {
-#pragma unroll
-          float lo[32];
+      for (int gq = 0; gq < 2; ++gq) {
+#pragma unroll 1
+        for (int cq = 0; cq < 4; ++cq) {
+          const int j0 = gq * 128 + cq * 32;
+          float v[32], lo[32];
+          tmem_ld32f(c.trow + j0, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float pj = __expf(v[j] + __ldg(bias + j0 + j) - mx) * inv;
+            const float pj = __expf(v[j] + __ldg(bias + j0 + j) - mx) * inv;
             const float d = w ? (pj - ((j0 + j == y) ? 1.f : 0.f)) : 0.f;
             const float hi = __bfloat162float(__float2bfloat16(d));
             v[j] = hi;
             lo[j] = d - hi;
           }
-          store_bf16x32(dl + drow + j0, v);
-          store_bf16x32(dl + drow + 256 + j0, lo);
+          stage_put(t_hi, c.lane, cq, v);
+          stage_put(t_lo, c.lane, cq, lo);
         }
+        tile_flush<1>(t_hi, dl + c.row0 * ld + gq * 128, ld, c.nrows, c);
+        tile_flush<1>(t_lo, dl + c.row0 * ld + 256 + gq * 128, ld, c.nrows, c);
       }
     }
     loss = warp_sum(loss);
     cnt = warp_sum(cnt);
-    if ((threadIdx.x & 31) == 0) {
+    if (c.lane == 0) {
       atomicAdd(static_cast<float*>(e.ptr[3]), loss);
       atomicAdd(static_cast<float*>(e.ptr[4]), cnt);
     }
@@ -256,8 +371,8 @@ struct Epilogue<EPI_MOL, 32> {
   static __device__ __forceinline__ float softplus(float x) {
     return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));
   }
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
+    if (c.cg != 0) return;
     const float* tgt = static_cast<const float*>(e.ptr[0]);
     const int* len = static_cast<const int*>(e.ptr[1]);
     const float* bias = static_cast<const float*>(e.ptr[2]);
@@ -265,14 +380,14 @@ struct Epilogue<EPI_MOL, 32> {
     float* yo = static_cast<float*>(e.ptr[6]);
     const int nm = e.i[0];
     const float lsm = e.f[0], hw = e.f[1], logc = e.f[2];
-    const size_t row = (size_t(b) * T + t) * 32;
-    const bool w = valid && (t + 1 < T) && (t + 1 < __ldg(len + b));
-    const float y = w ? __ldg(tgt + size_t(b) * T + t + 1) : 0.f;
+    const size_t row = (size_t(c.b) * c.T + c.t) * 32;
+    const bool w = c.valid && (c.t + 1 < c.T) && (c.t + 1 < __ldg(len + c.b));
+    const float y = w ? __ldg(tgt + size_t(c.b) * c.T + c.t + 1) : 0.f;
     float v[32];
-    tmem_ld32f(trow, v);
+    tmem_ld32f(c.trow, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (j < 3 * nm) ? v[j] + __ldg(bias + j) : 0.f;
-    if (yo && valid) store_f32x32(yo + row, v);
+    if (yo && c.valid) store_f32x32(yo + row, v);
     // log-softmax of the mixture logits
     float lmx = -INFINITY;
     for (int k = 0; k < nm; ++k) lmx = fmaxf(lmx, v[k]);
@@ -322,7 +437,7 @@ struct Epilogue<EPI_MOL, 32> {
     for (int k = 0; k < 10; ++k)
       if (k < nm) tse += __expf(tot[k] - tmx);
     const float nll = -(tmx + __logf(tse));
-    if (dy && valid) {
+    if (dy && c.valid) {
       float g[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) g[j] = 0.f;
@@ -337,11 +452,11 @@ struct Epilogue<EPI_MOL, 32> {
             g[2 * nm + k] = -post * ds[k];
           }
       }
-      store_bf16x32(dy + (size_t(b) * T + t) * size_t(e.i[1]), g);
+      store_bf16x32(dy + (size_t(c.b) * c.T + c.t) * size_t(e.i[1]), g);
     }
     float loss = warp_sum(w ? nll : 0.f);
     float cnt = warp_sum(w ? 1.f : 0.f);
-    if ((threadIdx.x & 31) == 0) {
+    if (c.lane == 0) {
       atomicAdd(static_cast<float*>(e.ptr[3]), loss);
       atomicAdd(static_cast<float*>(e.ptr[4]), cnt);
     }
@@ -353,24 +468,28 @@ struct Epilogue<EPI_MOL, 32> {
 // f0 const scale; i0 = ldo
 template <int BN>
 struct Epilogue<EPI_SCALE_RELUMASK, BN> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int ldo = e.i[0];
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.ptr[0]);
     const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(e.ptr[1]);
     float s = e.f[0];
     if (e.ptr[2]) s /= fmaxf(__ldg(static_cast<const float*>(e.ptr[2])), 1e-20f);
-    const size_t row = (size_t(b) * T + t) * ldo + size_t(n_tile) * BN;
+    uint8_t* t_h = c.wbuf;
+    uint8_t* t_o = c.wbuf + kTileBytes;
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-      float acc[32], hv[32];
-      tmem_ld32f(trow + j0, acc);
-      if (valid) {
-        load_bf16x32(h + row + j0, hv);
+    for (int gq = 0; gq < BN / 128; ++gq) {
+      const size_t off = c.row0 * ldo + size_t(c.n_tile) * BN + gq * 128;
+      tile_fill<4>(t_h, h + off, ldo, c.nrows, c);
+      {
+        const int cq = c.cg;
+        float acc[32], hv[32];
+        tmem_ld32f(c.trow + gq * 128 + cq * 32, acc);
+        stage_get(t_h, c.lane, cq, hv);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = hv[j] > 0.f ? acc[j] * s : 0.f;
-        store_bf16x32(out + row + j0, acc);
+        stage_put(t_o, c.lane, cq, acc);
       }
+      tile_flush<4>(t_o, out + off, ldo, c.nrows, c);
     }
   }
 };
@@ -378,21 +497,26 @@ struct Epilogue<EPI_SCALE_RELUMASK, BN> {
 // backward of the gate: dz -> (da, db).  ptr: 0 ta, 1 sb (bf16 [pos,Gh]), 2 dg out (bf16 [pos,2Gh]); i0 = Gh
 template <int BN>
 struct Epilogue<EPI_GATE_BWD, BN> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int Gh = e.i[0];
     const __nv_bfloat16* ta = static_cast<const __nv_bfloat16*>(e.ptr[0]);
     const __nv_bfloat16* sb = static_cast<const __nv_bfloat16*>(e.ptr[1]);
     __nv_bfloat16* dg = static_cast<__nv_bfloat16*>(e.ptr[2]);
-    const size_t pos = size_t(b) * T + t;
-    const int cb = n_tile * BN;
+    uint8_t* t_a = c.wbuf;
+    uint8_t* t_s = c.wbuf + kTileBytes;
+    uint8_t* t_da = c.wbuf + 2 * kTileBytes;
+    uint8_t* t_db = c.wbuf + 3 * kTileBytes;
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-      float dz[32], a[32], s[32];
-      tmem_ld32f(trow + j0, dz);
-      if (valid) {
-        load_bf16x32(ta + pos * Gh + cb + j0, a);
-        load_bf16x32(sb + pos * Gh + cb + j0, s);
+    for (int gq = 0; gq < BN / 128; ++gq) {
+      const int cb = c.n_tile * BN + gq * 128;
+      tile_fill<4>(t_a, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
+      tile_fill<4>(t_s, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
+      {
+        const int cq = c.cg;
+        float dz[32], a[32], s[32];
+        tmem_ld32f(c.trow + gq * 128 + cq * 32, dz);
+        stage_get(t_a, c.lane, cq, a);
+        stage_get(t_s, c.lane, cq, s);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float da = dz[j] * (1.f - a[j] * a[j]) * s[j];
@@ -400,43 +524,52 @@ struct Epilogue<EPI_GATE_BWD, BN> {
           a[j] = da;
           s[j] = db;
         }
-        store_bf16x32(dg + pos * 2 * Gh + cb + j0, a);
-        store_bf16x32(dg + pos * 2 * Gh + Gh + cb + j0, s);
+        stage_put(t_da, c.lane, cq, a);
+        stage_put(t_db, c.lane, cq, s);
       }
+      tile_flush<4>(t_da, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
+      tile_flush<4>(t_db, dg + c.row0 * 2 * Gh + Gh + cb, 2 * Gh, c.nrows, c);
     }
   }
 };
 
 // gradient wrt the block input: dx = dropout_mask/keep * acc + res_scale * dx_out
-// ptr: 0 dxo bf16 [pos,R] (nullable), 1 dx_out bf16 [pos,R]; f0 res_scale, f1 dropout p; i1 = layer
+// ptr: 0 dxo bf16 [pos,R] (nullable), 1 dx_out bf16 [pos,R], 7 device u64 seed offset (nullable);
+// f0 res_scale, f1 dropout p; i1 = layer
 template <int BN>
 struct Epilogue<EPI_DX, BN> {
-  static __device__ __forceinline__ void run(const EpiArgs& e, int n_tile, int b, int t, int T,
-                                             bool valid, uint32_t trow) {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int R = BN;
     const __nv_bfloat16* dxo = static_cast<const __nv_bfloat16*>(e.ptr[0]);
     __nv_bfloat16* dx = static_cast<__nv_bfloat16*>(e.ptr[1]);
     const float rs = e.f[0], p = e.f[1];
     const float keep_inv = 1.f / (1.f - p);
-    const size_t row = (size_t(b) * T + t) * R;
+    const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
+    const uint32_t hs = hash_seed(seed, uint32_t(e.i[1]));
+    const size_t row = (size_t(c.b) * c.T + c.t) * R;
+    uint8_t* t_g = c.wbuf;
+    uint8_t* t_o = c.wbuf + kTileBytes;
 #pragma unroll 1
-    for (int j0 = 0; j0 < BN; j0 += 32) {
-      float acc[32], g[32];
-      tmem_ld32f(trow + j0, acc);
-      if (valid) {
+    for (int gq = 0; gq < BN / 128; ++gq) {
+      if (dxo) tile_fill<4>(t_g, dxo + c.row0 * R + gq * 128, R, c.nrows, c);
+      {
+        const int cq = c.cg;
+        const int j0 = gq * 128 + cq * 32;
+        float acc[32], g[32];
+        tmem_ld32f(c.trow + j0, acc);
         if (p > 0.f) {
-          const uint64_t base = (uint64_t(e.i[1]) << 40) + row + j0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            acc[j] = (hash_uniform(e.seed, base + j) >= p) ? acc[j] * keep_inv : 0.f;
+            acc[j] = (hash_uniform32(hs, row + j0 + j) >= p) ? acc[j] * keep_inv : 0.f;
         }
         if (dxo) {
-          load_bf16x32(dxo + row + j0, g);
+          stage_get(t_g, c.lane, cq, g);
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] += rs * g[j];
         }
-        store_bf16x32(dx + row + j0, acc);
+        stage_put(t_o, c.lane, cq, acc);
       }
+      tile_flush<4>(t_o, dx + c.row0 * R + gq * 128, R, c.nrows, c);
     }
   }
 };
@@ -452,10 +585,11 @@ struct ActGemmCfg {
   static constexpr int kStages = (BN >= 256) ? 4 : 6;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(BN < 128 || kStages * kStageBytes >= 4 * kEpiWarpBytes, "epilogue staging must fit in the pipeline stages");
 };
 
 template <int EPI, int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1) act_gemm_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __grid_constant__ GemmArgs g) {
   using Cfg = ActGemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -539,12 +673,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) act_gemm_kernel(const __grid_
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = q * 32 + (threadIdx.x & 31);
-    const int t = t0 + r;
+    EpiCtx c;
+    c.lane = threadIdx.x & 31;
+    c.cg = (warp - 2) >> 2;
+    c.qbar = 1 + q;
+    c.n_tile = n_tile; c.b = b; c.T = g.T;
+    const int tw = t0 + q * 32;          // first time step of this warp
+    c.t = tw + c.lane;
+    c.valid = c.t < g.T;
+    c.row0 = size_t(b) * g.T + tw;
+    c.nrows = g.T - tw < 0 ? 0 : (g.T - tw > 32 ? 32 : g.T - tw);
+    c.wbuf = smem + q * kEpiWarpBytes;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
-    Epilogue<EPI, BN>::run(g.epi, n_tile, b, t, g.T, t < g.T, trow);
+    c.trow = tmem_base + (uint32_t(q * 32) << 16);
+    Epilogue<EPI, BN>::run(g.epi, c);
   }
   tc_fence_before();
   __syncthreads();

@@ -57,25 +57,39 @@ struct AdamArgs {
   const float* norms;  // per-tensor sumsq; norms[nt] = global sumsq
 };
 __global__ void adam_kernel(AdamArgs a) {
-  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // 4 consecutive elements per thread: tensor offsets (and n) are multiples of 4, so they share one tensor
+  const long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (e >= a.n) return;
-  float g = a.g[e] * a.gscale;
+  float gs = a.gscale;
   if (a.gclip > 0.f) {
-    const float gn = sqrtf(a.norms[a.nt]);
-    g *= a.gclip / fmaxf(gn, a.gclip);
+    gs *= a.gclip / fmaxf(sqrtf(a.norms[a.nt]), a.gclip);
   } else if (a.max_norm > 0.f) {
     const int t = find_tensor(a.offs, a.nt, e);
-    const float tn = sqrtf(a.norms[t]);
-    g *= a.max_norm / fmaxf(tn, a.max_norm);
+    gs *= a.max_norm / fmaxf(sqrtf(a.norms[t]), a.max_norm);
   }
-  if (a.max_value > 0.f) g = fminf(fmaxf(g, -a.max_value), a.max_value);
-  const float m = a.b1 * a.m[e] + (1.f - a.b1) * g;
-  const float v = a.b2 * a.v[e] + (1.f - a.b2) * g * g;
-  a.m[e] = m;
-  a.v[e] = v;
-  const float p = a.p[e] - a.lr_t * m / (sqrtf(v) + a.eps);
-  a.p[e] = p;
-  if (a.ema) a.ema[e] -= (1.f - a.ema_decay) * (a.ema[e] - p);
+  const float4 g4 = *reinterpret_cast<const float4*>(a.g + e);
+  float4 m4 = *reinterpret_cast<const float4*>(a.m + e);
+  float4 v4 = *reinterpret_cast<const float4*>(a.v + e);
+  float4 p4 = *reinterpret_cast<const float4*>(a.p + e);
+  float4 e4 = a.ema ? *reinterpret_cast<const float4*>(a.ema + e) : make_float4(0, 0, 0, 0);
+  float* gp = const_cast<float*>(reinterpret_cast<const float*>(&g4));
+  float* mp = reinterpret_cast<float*>(&m4);
+  float* vp = reinterpret_cast<float*>(&v4);
+  float* pp = reinterpret_cast<float*>(&p4);
+  float* ep = reinterpret_cast<float*>(&e4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float g = gp[i] * gs;
+    if (a.max_value > 0.f) g = fminf(fmaxf(g, -a.max_value), a.max_value);
+    mp[i] = a.b1 * mp[i] + (1.f - a.b1) * g;
+    vp[i] = a.b2 * vp[i] + (1.f - a.b2) * g * g;
+    pp[i] = pp[i] - a.lr_t * mp[i] / (sqrtf(vp[i]) + a.eps);
+    ep[i] -= (1.f - a.ema_decay) * (ep[i] - pp[i]);
+  }
+  *reinterpret_cast<float4*>(a.m + e) = m4;
+  *reinterpret_cast<float4*>(a.v + e) = v4;
+  *reinterpret_cast<float4*>(a.p + e) = p4;
+  if (a.ema) *reinterpret_cast<float4*>(a.ema + e) = e4;
 }
 __global__ void total_kernel(float* norms, int nt) {
   float s = 0.f;
@@ -98,15 +112,16 @@ extern "C" int t2_adam_step(float* d_params, const float* d_grads, float* d_m, f
   const bool need_norms = max_norm > 0.f || global_norm_clip > 0.f;
   if (need_norms) {
     T2_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, (n_tensors + 1) * sizeof(float), st));
-    sumsq_kernel<<<(unsigned)((n_total + 4095) / 4096), 256, 0, st>>>(d_grads, d_offsets, n_tensors, n_total, grad_scale, d_scratch);
-    if (global_norm_clip > 0.f) total_kernel<<<1, 32, 0, st>>>(d_scratch, n_tensors);
+    sumsq_kernel<<<(unsigned)((n_total + 4095) / 4096), 256, 0, st>>>(d_grads, d_offsets, n_tensors, n_total, grad_scale, d_scratch); t2_count_launch();
+    if (global_norm_clip > 0.f) total_kernel<<<1, 32, 0, st>>>(d_scratch, n_tensors); t2_count_launch();
   }
   AdamArgs a;
   a.p = d_params; a.g = d_grads; a.m = d_m; a.v = d_v; a.ema = d_ema; a.offs = d_offsets; a.nt = n_tensors; a.n = n_total;
   a.lr_t = float(double(lr) * sqrt(1.0 - pow(double(beta2), step)) / (1.0 - pow(double(beta1), step)));
   a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.gscale = grad_scale; a.max_norm = max_norm; a.max_value = max_value;
   a.gclip = global_norm_clip; a.ema_decay = ema_decay; a.norms = d_scratch;
-  adam_kernel<<<(unsigned)((n_total + 255) / 256), 256, 0, st>>>(a);
+  T2_REQUIRE(n_total % 4 == 0, T2_ERR_INVALID_ARG, "adam: flat buffers must hold a multiple of 4 elements (16-byte aligned tensors)");
+  adam_kernel<<<(unsigned)((n_total / 4 + 255) / 256), 256, 0, st>>>(a); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }

@@ -356,7 +356,9 @@ __global__ void derived_bias_kernel(DerivedArgs a) {
 // first (embedding) 1x1 conv: one-hot input == row gather (wavenet.py:705; SURVEY §8a "embedding in disguise")
 __global__ void first_conv_kernel(const void* __restrict__ xin, int scalar_in, const float* __restrict__ W,
                                   const float* __restrict__ bias, bf16* __restrict__ x, bf16* __restrict__ xd,
-                                  long long npos, int R, float p, unsigned long long seed) {
+                                  long long npos, int R, float p, unsigned long long seed,
+                                  const unsigned long long* __restrict__ step) {
+  if (step) seed += *step;
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= npos * R) return;
   const long long pos = e / R;
@@ -367,7 +369,7 @@ __global__ void first_conv_kernel(const void* __restrict__ xin, int scalar_in, c
   x[e] = __float2bfloat16(v);
   if (xd != x && xd != nullptr) {
     const float keep_inv = 1.f / (1.f - p);
-    xd[e] = __float2bfloat16(hash_uniform(seed, (0ull << 40) + e) >= p ? v * keep_inv : 0.f);
+    xd[e] = __float2bfloat16(hash_uniform32(hash_seed(seed, 0u), (unsigned long long)e) >= p ? v * keep_inv : 0.f);
   }
 }
 __global__ void first_conv_bwd_kernel(const void* __restrict__ xin, int scalar_in, const bf16* __restrict__ dx0,
@@ -397,12 +399,28 @@ __global__ void colsum_kernel(const uint8_t* __restrict__ ws, float* __restrict_
   const long long r1 = r0 + rows_per < j.rows ? r0 + rows_per : j.rows;
   float sc = j.scale;
   if (j.div_scalar >= 0) sc /= fmaxf(scalars[j.div_scalar], 1e-20f);
-  for (int c = threadIdx.x; c < j.C; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += __bfloat162float(src[r * j.ld + c]);
-    acc *= sc;
-    atomicAdd(grads + j.dst_off + c, acc);
-    if (j.dst2_off >= 0) atomicAdd(grads + j.dst2_off + c, acc);
+  // one thread = one pair of adjacent columns (C and ld are even); 4 rows in flight per iteration
+  for (int c = 2 * threadIdx.x; c < j.C; c += 2 * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    long long r = r0;
+    for (; r + 4 <= r1; r += 4) {
+      uint32_t u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (r + i) * j.ld + c));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a0 += bf16lo(u[i]); a1 += bf16hi(u[i]); }
+    }
+    for (; r < r1; ++r) {
+      const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src + r * j.ld + c));
+      a0 += bf16lo(u); a1 += bf16hi(u);
+    }
+    a0 *= sc; a1 *= sc;
+    atomicAdd(grads + j.dst_off + c, a0);
+    if (c + 1 < j.C) atomicAdd(grads + j.dst_off + c + 1, a1);
+    if (j.dst2_off >= 0) {
+      atomicAdd(grads + j.dst2_off + c, a0);
+      if (c + 1 < j.C) atomicAdd(grads + j.dst2_off + c + 1, a1);
+    }
   }
 }
 
@@ -458,7 +476,7 @@ __global__ void upsample_bwd_param_kernel(const float* __restrict__ in, const fl
   const int Wo = W * s;
   float acc = 0.f;
   const long long n = (long long)B * H * W;
-  for (long long e = threadIdx.x; e < n; e += blockDim.x) {
+  for (long long e = blockIdx.z * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.z * blockDim.x) {
     const int w = int(e % W), h = int((e / W) % H), b = int(e / ((long long)W * H));
     const int xo = w * s + k;
     const float o = out[((long long)b * H + h) * Wo + xo];
@@ -482,7 +500,7 @@ __global__ void upsample_bwd_param_kernel(const float* __restrict__ in, const fl
       if (tap == ntap) {
         if (type == 0) atomicAdd(dbias + k, v); else atomicAdd(dbias, v);
       } else {
-        dK[tap * s + k] += v;  // unique (tap, k) per block
+        atomicAdd(dK + tap * s + k, v);
       }
     }
   }
@@ -522,6 +540,31 @@ __global__ void upsample_bwd_input_kernel(const float* __restrict__ out, const f
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e < n) out[e] = __float2bfloat16(in[e]);
+}
+
+// the per-layer gate GEMM: [x(t-2d) | x(t-d) | x(t) | c(t)] x Wg with the tanh*sigmoid epilogue
+ActGemmCall make_gate_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l, bool save) {
+  const long long BT = (long long)lo.B * lo.T;
+  const int d = lo.dil(l);
+  ActGemmCall g;
+  memset(&g, 0, sizeof(g));
+  g.a[0] = make_act(ws + lo.w_xd, lo.R, lo.T, lo.B, lo.L);
+  g.a[1] = make_act(ws + lo.w_cup, lo.C > 0 ? lo.C : 8, lo.T, lo.B, 1);
+  g.na = lo.C > 0 ? 2 : 1;
+  g.seg[0] = Seg{0, -2 * d, 0, lo.R / kBK, l, 1};
+  g.seg[1] = Seg{0, -d, 0, lo.R / kBK, l, 1};
+  g.seg[2] = Seg{0, 0, 0, lo.R / kBK, l, 1};
+  g.nseg = 3;
+  if (lo.C > 0) { g.seg[3] = Seg{1, 0, 0, 2, 0, 1}; g.nseg = 4; }
+  g.w = pk + lo.k_Wg; g.wN = lo.G; g.wK = lo.Kg; g.wL = lo.L; g.w_layer = l; g.w_k0 = 0;
+  g.T = lo.T; g.B = lo.B; g.n_tiles = lo.G / 256;
+  const long long lofs = (long long)l * BT * lo.Gh;
+  g.epi.ptr[0] = save ? reinterpret_cast<bf16*>(ws + lo.w_ta) + lofs : nullptr;
+  g.epi.ptr[1] = save ? reinterpret_cast<bf16*>(ws + lo.w_sb) + lofs : nullptr;
+  g.epi.ptr[2] = reinterpret_cast<bf16*>(ws + lo.w_z) + lofs;
+  g.epi.ptr[3] = const_cast<float*>(reinterpret_cast<const float*>(pk + lo.k_bias_g) + (long long)l * lo.G);
+  g.epi.i[0] = lo.Gh;
+  return g;
 }
 
 inline dim3 grid1d(long long n, int block = 256) { return dim3((unsigned)((n + block - 1) / block)); }
@@ -597,14 +640,14 @@ extern "C" int t2_wn_pack_weights(const t2_wn_config_t* cfg, const float* d_para
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   uint8_t* pk = static_cast<uint8_t*>(d_packed);
   pack_kernel<<<dim3(48, lo.n_packjobs), 256, 0, st>>>(d_params, reinterpret_cast<bf16*>(pk),
-                                                       reinterpret_cast<const PackJob*>(ws + lo.w_packjobs));
+                                                       reinterpret_cast<const PackJob*>(ws + lo.w_packjobs)); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   long long* d_offs = reinterpret_cast<long long*>(ws + lo.w_tables);
   float* d_scales = reinterpret_cast<float*>(ws + lo.w_tables + 3 * lo.L * sizeof(long long));
   DerivedArgs a;
   a.params = d_params; a.bias_g = reinterpret_cast<float*>(pk + lo.k_bias_g); a.bias_skip = reinterpret_cast<float*>(pk + lo.k_bias_skip);
   a.offs = d_offs; a.scales = d_scales; a.L = lo.L; a.G = lo.G; a.S = lo.S;
-  derived_bias_kernel<<<grid1d((long long)lo.L * lo.G), 256, 0, st>>>(a);
+  derived_bias_kernel<<<grid1d((long long)lo.L * lo.G), 256, 0, st>>>(a); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
@@ -612,7 +655,7 @@ extern "C" int t2_wn_pack_weights(const t2_wn_config_t* cfg, const float* d_para
 extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed,
                              void* d_workspace, const void* d_x, const float* d_c, const void* d_targets,
                              const int* d_lengths, float* d_loss, float* d_logits, int save_for_backward,
-                             unsigned long long seed, void* stream) {
+                             unsigned long long seed, const unsigned long long* d_step, void* stream) {
   Layout lo;
   int rc = build_layout(cfg, lo);
   if (rc) return rc;
@@ -629,7 +672,7 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
   if (lo.C > 0) {
     T2_REQUIRE(d_c != nullptr, T2_ERR_INVALID_ARG, "local conditioning enabled but d_c is NULL");
     if (cfg->c_pre_upsampled) {
-      f32_to_bf16_kernel<<<grid1d(BT * lo.C), 256, 0, st>>>(d_c, c_up, BT * lo.C);
+      f32_to_bf16_kernel<<<grid1d(BT * lo.C), 256, 0, st>>>(d_c, c_up, BT * lo.C); t2_count_launch();
     } else {
       const float* in = d_c;
       int W = lo.Tc;
@@ -638,7 +681,7 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
         float* out = reinterpret_cast<float*>(ws + lo.w_upout[i]);
         const bool last = i + 1 == lo.up_w.size();
         upsample_fwd_kernel<<<grid1d((long long)lo.B * lo.C * W * s), 256, 0, st>>>(
-            in, d_params + lo.p_up_k[i], d_params + lo.p_up_b[i], out, last ? c_up : nullptr, lo.B, lo.C, W, s, cfg->upsample_type);
+            in, d_params + lo.p_up_k[i], d_params + lo.p_up_b[i], out, last ? c_up : nullptr, lo.B, lo.C, W, s, cfg->upsample_type); t2_count_launch();
         in = out;
         W *= s;
       }
@@ -649,33 +692,13 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
   bf16* x_all = reinterpret_cast<bf16*>(ws + lo.w_x);
   bf16* xd_all = reinterpret_cast<bf16*>(ws + lo.w_xd);
   first_conv_kernel<<<grid1d(BT * lo.R), 256, 0, st>>>(d_x, lo.scalar_in ? 1 : 0, d_params + lo.p_in_k, d_params + lo.p_in_b,
-                                                       x_all, p > 0.f ? xd_all : x_all, BT, lo.R, p, seed);
+                                                       x_all, p > 0.f ? xd_all : x_all, BT, lo.R, p, seed, d_step); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   // 3. residual stack
-  bf16* ta_all = reinterpret_cast<bf16*>(ws + lo.w_ta);
-  bf16* sb_all = reinterpret_cast<bf16*>(ws + lo.w_sb);
   bf16* z_all = reinterpret_cast<bf16*>(ws + lo.w_z);
-  const ActT a_xd = make_act(xd_all, lo.R, lo.T, lo.B, lo.L);
-  const ActT a_c = make_act(c_up, lo.C > 0 ? lo.C : 8, lo.T, lo.B, 1);
   const ActT a_z = make_act(z_all, lo.Gh, lo.T, lo.B, lo.L);
   for (int l = 0; l < lo.L; ++l) {
-    const int d = lo.dil(l);
-    ActGemmCall g;
-    memset(&g, 0, sizeof(g));
-    g.a[0] = a_xd; g.a[1] = a_c; g.na = lo.C > 0 ? 2 : 1;
-    g.seg[0] = Seg{0, -2 * d, 0, lo.R / kBK, l, 1};
-    g.seg[1] = Seg{0, -d, 0, lo.R / kBK, l, 1};
-    g.seg[2] = Seg{0, 0, 0, lo.R / kBK, l, 1};
-    g.nseg = 3;
-    if (lo.C > 0) { g.seg[3] = Seg{1, 0, 0, 2, 0, 1}; g.nseg = 4; }
-    g.w = pk + lo.k_Wg; g.wN = lo.G; g.wK = lo.Kg; g.wL = lo.L; g.w_layer = l; g.w_k0 = 0;
-    g.T = lo.T; g.B = lo.B; g.n_tiles = lo.G / 256;
-    const long long lofs = (long long)l * BT * lo.Gh;
-    g.epi.ptr[0] = save_for_backward ? ta_all + lofs : nullptr;
-    g.epi.ptr[1] = save_for_backward ? sb_all + lofs : nullptr;
-    g.epi.ptr[2] = z_all + lofs;
-    g.epi.ptr[3] = const_cast<float*>(reinterpret_cast<const float*>(pk + lo.k_bias_g) + (long long)l * lo.G);
-    g.epi.i[0] = lo.Gh;
+    ActGemmCall g = make_gate_call(lo, ws, pk, l, save_for_backward != 0);
     rc = launch_act_gemm(EPI_GATE, 256, g, st);
     if (rc) return rc;
     if (l + 1 < lo.L) {
@@ -690,6 +713,7 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
       o.epi.ptr[2] = p > 0.f ? xd_all + (long long)(l + 1) * BT * lo.R : nullptr;
       o.epi.ptr[3] = const_cast<float*>(d_params + lo.p_o_b[l]);
       o.epi.f[0] = lo.res_scale; o.epi.f[1] = p; o.epi.i[1] = l + 1; o.epi.seed = seed;
+      o.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
       rc = launch_act_gemm(EPI_RES, lo.R, o, st);
       if (rc) return rc;
     }
@@ -753,7 +777,7 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
 
 extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed,
                               void* d_workspace, const void* d_x, const float* d_c, float* d_grads,
-                              unsigned long long seed, void* stream) {
+                              unsigned long long seed, const unsigned long long* d_step, void* stream) {
   Layout lo;
   int rc = build_layout(cfg, lo);
   if (rc) return rc;
@@ -834,6 +858,7 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
       g.epi.ptr[0] = top ? nullptr : dxin + (long long)(l + 1) * BT * lo.R;
       g.epi.ptr[1] = dxin + (long long)l * BT * lo.R;
       g.epi.f[0] = lo.res_scale; g.epi.f[1] = p; g.epi.i[1] = l; g.epi.seed = seed;
+      g.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
       rc = launch_act_gemm(EPI_DX, lo.R, g, st);
       if (rc) return rc;
     }
@@ -851,10 +876,10 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     if (rc) return rc;
   }
   // bias gradients
-  colsum_kernel<<<dim3(32, lo.n_colsum), 256, 0, st>>>(ws, d_grads, reinterpret_cast<const ColsumJob*>(ws + lo.w_colsum), scalars);
+  colsum_kernel<<<dim3(96, lo.n_colsum), 256, 0, st>>>(ws, d_grads, reinterpret_cast<const ColsumJob*>(ws + lo.w_colsum), scalars); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   // first conv
-  first_conv_bwd_kernel<<<dim3((unsigned)((BT + 63) / 64)), lo.R, 0, st>>>(d_x, lo.scalar_in ? 1 : 0, dxin, d_grads + lo.p_in_k, BT, lo.R);
+  first_conv_bwd_kernel<<<dim3((unsigned)((BT + 63) / 64)), lo.R, 0, st>>>(d_x, lo.scalar_in ? 1 : 0, dxin, d_grads + lo.p_in_k, BT, lo.R); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   // conditioning path
   if (lo.C > 0 && !cfg->c_pre_upsampled) {
@@ -877,12 +902,12 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
       const float* layer_in = i == 0 ? d_c : reinterpret_cast<const float*>(ws + lo.w_upout[i - 1]);
       const float* out = reinterpret_cast<const float*>(ws + lo.w_upout[i]);
       const int ntap = cfg->upsample_type == 0 ? 9 : 3;
-      upsample_bwd_param_kernel<<<dim3(s, ntap + 1), 256, 0, st>>>(layer_in, out, dout, cl, d_grads + lo.p_up_k[i], d_grads + lo.p_up_b[i],
-                                                                  lo.B, lo.C, W, s, cfg->upsample_type);
+      upsample_bwd_param_kernel<<<dim3(s, ntap + 1, 24), 256, 0, st>>>(layer_in, out, dout, cl, d_grads + lo.p_up_k[i], d_grads + lo.p_up_b[i],
+                                                                  lo.B, lo.C, W, s, cfg->upsample_type); t2_count_launch();
       if (i > 0) {
         float* din = reinterpret_cast<float*>(ws + lo.w_upgrad[pp]);
         upsample_bwd_input_kernel<<<grid1d((long long)lo.B * lo.C * W), 256, 0, st>>>(out, dout, cl, d_params + lo.p_up_k[i], din, lo.B, lo.C, W, s,
-                                                                                    cfg->upsample_type);
+                                                                                    cfg->upsample_type); t2_count_launch();
         dout = din;
         cl = 0;
         pp ^= 1;
@@ -914,4 +939,34 @@ extern "C" int t2_wn_workspace_tensor(const t2_wn_config_t* cfg, void* d_workspa
       return T2_OK;
     }
   return t2_set_error(T2_ERR_INVALID_ARG, "unknown workspace tensor '%s'", name);
+}
+
+// Times `reps` back-to-back launches of one layer's gate GEMM (the dominant kernel of the step) with CUDA events on
+// the launching stream; the workspace must hold the activations of a previous t2_wn_forward. Synchronises.
+extern "C" int t2_wn_time_gate_gemm(const t2_wn_config_t* cfg, const void* d_packed, void* d_workspace, int layer,
+                                    int reps, float* ms_per_launch, void* stream) {
+  Layout lo;
+  int rc = build_layout(cfg, lo);
+  if (rc) return rc;
+  T2_REQUIRE(layer >= 0 && layer < lo.L && reps >= 1 && ms_per_launch, T2_ERR_INVALID_ARG, "time_gate_gemm: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ActGemmCall g = make_gate_call(lo, static_cast<uint8_t*>(d_workspace), static_cast<const uint8_t*>(d_packed), layer, true);
+  cudaEvent_t e0, e1;
+  T2_CHECK_CUDA(cudaEventCreate(&e0));
+  T2_CHECK_CUDA(cudaEventCreate(&e1));
+  rc = launch_act_gemm(EPI_GATE, 256, g, st);  // warm-up
+  if (rc) return rc;
+  T2_CHECK_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; ++i) {
+    rc = launch_act_gemm(EPI_GATE, 256, g, st);
+    if (rc) return rc;
+  }
+  T2_CHECK_CUDA(cudaEventRecord(e1, st));
+  T2_CHECK_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  T2_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_per_launch = ms / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return T2_OK;
 }

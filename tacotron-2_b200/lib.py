@@ -24,6 +24,7 @@ def load():
                           "(there is no CPU fallback for the CUDA hot path)")
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.t2_last_error.restype = ctypes.c_char_p
+        _lib.t2_launch_count.restype = ctypes.c_longlong
     return _lib
 
 

@@ -100,6 +100,8 @@ class WaveNet(object):
         self.opt_scratch = torch.zeros(sz.n_tensors + 2, dtype=torch.float32, device=self.device)
         self.global_step = 0
         self.seed = int(hparams.wavenet_random_seed)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)  # added to the dropout seed on device
+        self._graph = None
         with torch.cuda.device(self.device):
             L.check(self.lib.t2_wn_init(ctypes.byref(self.cfg), L.ptr(self.packed), L.ptr(self.workspace),
                                         L.stream_ptr()))
@@ -138,11 +140,11 @@ class WaveNet(object):
         if self._packed_dirty:
             self.pack()
         self._last_x, self._last_c = x, c
-        self._last_seed = self.seed + self.global_step if seed is None else seed
+        self._last_seed = self.seed if seed is None else seed
         L.check(self.lib.t2_wn_forward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
                                        L.ptr(self.workspace), L.ptr(x), L.ptr(c), L.ptr(targets), L.ptr(lengths),
                                        L.ptr(self.loss_buf), L.ptr(logits), int(save_for_backward),
-                                       ctypes.c_ulonglong(self._last_seed), L.stream_ptr()))
+                                       ctypes.c_ulonglong(self._last_seed), L.ptr(self.step_dev), L.stream_ptr()))
         return self.loss_buf
 
     def backward(self):
@@ -150,8 +152,68 @@ class WaveNet(object):
             self.grads = torch.zeros_like(self.params)
         L.check(self.lib.t2_wn_backward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
                                         L.ptr(self.workspace), L.ptr(self._last_x), L.ptr(self._last_c),
-                                        L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed), L.stream_ptr()))
+                                        L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed),
+                                        L.ptr(self.step_dev), L.stream_ptr()))
         return self.grads
+
+    # ---- training step (the call a user makes) -----------------------------------------------------------
+    def capture(self, x, c, targets, lengths):
+        """Capture pack + forward + backward into a CUDA graph over STATIC input tensors (x, c, targets, lengths are
+        the buffers later steps must copy into). Adam runs outside the graph (its bias correction changes per step)."""
+        self._static = (x, c, targets, lengths)
+        if self.grads is None:
+            self.grads = torch.zeros_like(self.params)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture (sets kernel attributes, loads modules)
+            self.pack()
+            self.forward(x, c, targets, lengths)
+            self.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = self.lib.t2_launch_count()
+        with torch.cuda.graph(self._graph):
+            self.step_dev.add_(1)
+            self.pack()
+            self.forward(x, c, targets, lengths)
+            self.backward()
+        self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
+        return self._graph
+
+    def train_step(self, x=None, c=None, targets=None, lengths=None, world_size=1, process_group=None):
+        """One optimisation step: forward + loss + backward (+ gradient all-reduce) + clip + Adam + EMA.
+        With a captured graph, non-None arguments are copied into the static buffers first."""
+        if self._graph is not None:
+            for dst, src in zip(self._static, (x, c, targets, lengths)):
+                if src is not None and src is not dst:
+                    dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+        else:
+            n0 = self.lib.t2_launch_count()
+            self.step_dev.add_(1)
+            self.forward(x, c, targets, lengths)
+            self.backward()
+            self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
+        if world_size > 1:
+            import torch.distributed as dist
+            # the reference averages tower gradients, THEN clips, THEN applies Adam (wavenet.py:561-593)
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=process_group)
+        n0 = self.lib.t2_launch_count()
+        self.optimizer_step(grad_scale=1.0 / world_size)
+        self._opt_launches = self.lib.t2_launch_count() - n0
+        return self.loss_buf
+
+    @property
+    def launches_per_step(self):
+        """kernels of libt2b200 per optimisation step (graph replays re-launch the captured ones)"""
+        return getattr(self, "_fwd_bwd_launches", 0) + getattr(self, "_opt_launches", 0)
+
+    def time_gate_gemm(self, layer, reps=20):
+        ms = ctypes.c_float()
+        L.check(self.lib.t2_wn_time_gate_gemm(ctypes.byref(self.cfg), L.ptr(self.packed), L.ptr(self.workspace),
+                                              layer, reps, ctypes.byref(ms), L.stream_ptr()))
+        return ms.value
 
     def learning_rate(self):
         hp = self.hp

@@ -162,4 +162,5 @@ def test_dropout_statistics_and_determinism():
     assert abs(model.loss_value() - l1) < 1e-5          # same seed -> same masks (fp32 atomics reorder)
     model.forward(*args, seed=8)
     torch.cuda.synchronize()
-    assert abs(model.loss_value() - l1) > 1e-4
+    kept2 = model.workspace_tensor("xd", (hp.layers, B, T, 128)).float() != 0
+    assert (kept2 != kept).float().mean().item() > 0.2   # a different seed draws different masks
