@@ -226,7 +226,7 @@ def main():
     loss = model.loss_value()
 
     # roofline leg: the dominant kernel is the per-layer gate GEMM (24 launches / step, ~2/3 of the forward FLOPs)
-    gate_ms = [model.time_gate_gemm(l, reps=20) for l in (3, 9, 15, 21)]
+    gate_ms = [model.time_kernel(0, l, reps=20) for l in (3, 9, 15, 21)]
     gate_ms_avg = sum(gate_ms) / len(gate_ms)
     R, G, C = hp.residual_channels, hp.gate_channels, hp.cin_channels
     flops_per_launch = 2.0 * B_PER_GPU * T_STEP * G * (3 * R + C)

@@ -41,6 +41,8 @@ long long t2_launch_count(void);
 int t2_dbg_conv_gemm(const void* d_a, int B, int T, int C, int ld, const int* shifts, int nshift,
                      const void* d_w, int N, int BN, const float* d_bias, int relu, void* d_out_bf16,
                      float* d_out_f32, void* stream);
+/* debug: non-NULL => every GEMM CTA records 8 clock64() stamps at d_buf[cta*8 + slot]; NULL disables */
+int t2_dbg_set_timing_buffer(long long* d_buf);
 /* weight-gradient GEMM: out[m,n] = scale * sum_{b,t} a[b,t+shift_a,m] * bm[b,t,n]  (fp32 [Ca,Cb]); synchronises. */
 int t2_dbg_wgrad(const void* d_a, int Ca, const void* d_bm, int Cb, int B, int T, int shift_a, float scale,
                  float* d_out, void* stream);
@@ -97,9 +99,11 @@ int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void*
                    const void* d_x, const float* d_c, float* d_grads, unsigned long long seed,
                    const unsigned long long* d_step, void* stream);
 /* measurement hook for bench.py's roofline leg: average device time (CUDA events on `stream`) of `reps` launches of
- * layer `layer`'s gate GEMM over the activations left in the workspace by the last forward; synchronises */
-int t2_wn_time_gate_gemm(const t2_wn_config_t* cfg, const void* d_packed, void* d_workspace, int layer, int reps,
-                         float* ms_per_launch, void* stream);
+ * one per-layer GEMM over the state left in the workspace by the last forward/backward. which: 0 gate GEMM, 1 out
+ * GEMM, 2 dz + gate-backward GEMM, 3 dx GEMM. Re-running 1 / 3 rewrites x[l+1] / dx[l] with identical values.
+ * Synchronises. */
+int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                      int which, int layer, int reps, float* ms_per_launch, void* stream);
 /* debug / test access to workspace tensors by name ("x", "z", "c_up", "h1", "dg", ...): returns device pointer,
  * element count and element size */
 int t2_wn_workspace_tensor(const t2_wn_config_t* cfg, void* d_workspace, const char* name, void** ptr,

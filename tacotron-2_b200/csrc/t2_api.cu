@@ -74,3 +74,10 @@ extern "C" int t2_dbg_wgrad(const void* a, int Ca, const void* bm, int Cb, int B
   cudaFreeAsync(dt, st);
   return rc;
 }
+
+// debug: when non-NULL every act_gemm CTA writes 8 clock64() stamps (entry, setup done, first stage landed, MMAs issued,
+// accumulator ready, epilogue done, teardown) to d_buf[cta * 8 + slot]
+extern "C" int t2_dbg_set_timing_buffer(long long* d_buf) {
+  t2::set_timing_buffer(d_buf);
+  return T2_OK;
+}

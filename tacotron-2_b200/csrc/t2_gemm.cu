@@ -6,6 +6,9 @@
 
 namespace t2 {
 
+static long long* g_timing_buffer = nullptr;
+void set_timing_buffer(long long* p) { g_timing_buffer = p; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -104,6 +107,7 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
   g.tiles_per_b = (c.T + kBM - 1) / kBM;
   g.b_layer = c.w_layer;
   g.b_k0 = c.w_k0;
+  g.dbg = g_timing_buffer;
   g.epi = c.epi;
   dim3 grid(g.tiles_per_b * c.B, c.n_tiles, 1);
 #define T2_CASE(E, N) \

@@ -600,6 +600,8 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  long long* dbg = g.dbg ? g.dbg + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int b = m_tile / g.tiles_per_b;
   const int t0 = (m_tile - b * g.tiles_per_b) * kBM;
 
@@ -626,6 +628,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -656,6 +659,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (dbg && kb == 0) dbg[2] = clock64();
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
         const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
@@ -669,6 +673,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
         umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (dbg) dbg[3] = clock64();
       umma_commit(tmem_full);
     }
   } else {
@@ -687,10 +692,13 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     c.trow = tmem_base + (uint32_t(q * 32) << 16);
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
     Epilogue<EPI, BN>::run(g.epi, c);
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
   }
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);

@@ -30,6 +30,7 @@ struct ActGemmCall {
   EpiArgs epi;
 };
 
+void set_timing_buffer(long long* p);
 int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream);
 int launch_wgrad(const ActT* maps, int nmaps, const WgradTile* tiles_dev, int ntiles, float* out,
                  int T, int B, cudaStream_t stream);

@@ -35,6 +35,7 @@ struct GemmArgs {
   int tiles_per_b;   // ceil(T / 128)
   int b_layer;       // layer coordinate of the weight tensor map (3-D maps), else 0
   int b_k0;          // first K column of the packed weight this GEMM consumes
+  long long* dbg;    // optional: 8 clock64() stamps per CTA (see t2_dbg_set_timing_buffer)
   EpiArgs epi;
 };
 

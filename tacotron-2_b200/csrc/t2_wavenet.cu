@@ -567,6 +567,72 @@ ActGemmCall make_gate_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int
   return g;
 }
 
+ActGemmCall make_out_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, const float* params, int l, float p,
+                          unsigned long long seed, const unsigned long long* d_step) {
+  const long long BT = (long long)lo.B * lo.T;
+  bf16* x_all = reinterpret_cast<bf16*>(ws + lo.w_x);
+  bf16* xd_all = reinterpret_cast<bf16*>(ws + lo.w_xd);
+  ActGemmCall o;
+  memset(&o, 0, sizeof(o));
+  o.a[0] = make_act(ws + lo.w_z, lo.Gh, lo.T, lo.B, lo.L); o.na = 1;
+  o.seg[0] = Seg{0, 0, 0, lo.Gh / kBK, l, 1}; o.nseg = 1;
+  o.w = pk + lo.k_Wo; o.wN = lo.R; o.wK = lo.Gh; o.wL = lo.L; o.w_layer = l;
+  o.T = lo.T; o.B = lo.B; o.n_tiles = 1;
+  o.epi.ptr[0] = x_all + (long long)l * BT * lo.R;
+  o.epi.ptr[1] = x_all + (long long)(l + 1) * BT * lo.R;
+  o.epi.ptr[2] = p > 0.f ? xd_all + (long long)(l + 1) * BT * lo.R : nullptr;
+  o.epi.ptr[3] = const_cast<float*>(params + lo.p_o_b[l]);
+  o.epi.f[0] = lo.res_scale; o.epi.f[1] = p; o.epi.i[1] = l + 1; o.epi.seed = seed;
+  o.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
+  return o;
+}
+
+ActGemmCall make_dz_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l) {
+  const long long BT = (long long)lo.B * lo.T;
+  const bool top = l == lo.L - 1;
+  ActGemmCall g;
+  memset(&g, 0, sizeof(g));
+  g.a[0] = make_act(ws + lo.w_dxin, lo.R, lo.T, lo.B, lo.L);
+  g.a[1] = make_act(ws + lo.w_dskip, lo.S, lo.T, lo.B, 1);
+  g.na = 2;
+  if (top) {
+    g.seg[0] = Seg{1, 0, 0, lo.S / kBK, 0, 1}; g.nseg = 1; g.w_k0 = lo.R;
+  } else {
+    g.seg[0] = Seg{0, 0, 0, lo.R / kBK, l + 1, 1};
+    g.seg[1] = Seg{1, 0, 0, lo.S / kBK, 0, 1};
+    g.nseg = 2; g.w_k0 = 0;
+  }
+  const int bn_z = lo.Gh >= 256 ? 256 : 128;
+  g.w = pk + lo.k_WozT; g.wN = lo.Gh; g.wK = lo.R + lo.S; g.wL = lo.L; g.w_layer = l;
+  g.T = lo.T; g.B = lo.B; g.n_tiles = lo.Gh / bn_z;
+  const long long lofs = (long long)l * BT * lo.Gh;
+  g.epi.ptr[0] = reinterpret_cast<bf16*>(ws + lo.w_ta) + lofs;
+  g.epi.ptr[1] = reinterpret_cast<bf16*>(ws + lo.w_sb) + lofs;
+  g.epi.ptr[2] = reinterpret_cast<bf16*>(ws + lo.w_dg) + (long long)l * BT * lo.G;
+  g.epi.i[0] = lo.Gh;
+  return g;
+}
+
+ActGemmCall make_dx_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l, float p, unsigned long long seed,
+                         const unsigned long long* d_step) {
+  const long long BT = (long long)lo.B * lo.T;
+  const int d = lo.dil(l);
+  const bool top = l == lo.L - 1;
+  bf16* dxin = reinterpret_cast<bf16*>(ws + lo.w_dxin);
+  ActGemmCall g;
+  memset(&g, 0, sizeof(g));
+  g.a[0] = make_act(ws + lo.w_dg, lo.G, lo.T, lo.B, lo.L); g.na = 1;
+  for (int j = 0; j < 3; ++j) g.seg[j] = Seg{0, (2 - j) * d, 0, lo.G / kBK, l, 1};
+  g.nseg = 3;
+  g.w = pk + lo.k_WdT; g.wN = lo.R; g.wK = 3 * lo.G; g.wL = lo.L; g.w_layer = l;
+  g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
+  g.epi.ptr[0] = top ? nullptr : dxin + (long long)(l + 1) * BT * lo.R;
+  g.epi.ptr[1] = dxin + (long long)l * BT * lo.R;
+  g.epi.f[0] = lo.res_scale; g.epi.f[1] = p; g.epi.i[1] = l; g.epi.seed = seed;
+  g.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
+  return g;
+}
+
 inline dim3 grid1d(long long n, int block = 256) { return dim3((unsigned)((n + block - 1) / block)); }
 
 }  // namespace
@@ -702,18 +768,7 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
     rc = launch_act_gemm(EPI_GATE, 256, g, st);
     if (rc) return rc;
     if (l + 1 < lo.L) {
-      ActGemmCall o;
-      memset(&o, 0, sizeof(o));
-      o.a[0] = a_z; o.na = 1;
-      o.seg[0] = Seg{0, 0, 0, lo.Gh / kBK, l, 1}; o.nseg = 1;
-      o.w = pk + lo.k_Wo; o.wN = lo.R; o.wK = lo.Gh; o.wL = lo.L; o.w_layer = l;
-      o.T = lo.T; o.B = lo.B; o.n_tiles = 1;
-      o.epi.ptr[0] = x_all + (long long)l * BT * lo.R;
-      o.epi.ptr[1] = x_all + (long long)(l + 1) * BT * lo.R;
-      o.epi.ptr[2] = p > 0.f ? xd_all + (long long)(l + 1) * BT * lo.R : nullptr;
-      o.epi.ptr[3] = const_cast<float*>(d_params + lo.p_o_b[l]);
-      o.epi.f[0] = lo.res_scale; o.epi.f[1] = p; o.epi.i[1] = l + 1; o.epi.seed = seed;
-      o.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
+      ActGemmCall o = make_out_call(lo, ws, pk, d_params, l, p, seed, d_step);
       rc = launch_act_gemm(EPI_RES, lo.R, o, st);
       if (rc) return rc;
     }
@@ -826,42 +881,12 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
   const ActT a_dg = make_act(dg, lo.G, lo.T, lo.B, lo.L);
   const int bn_z = lo.Gh >= 256 ? 256 : 128;
   for (int l = lo.L - 1; l >= 0; --l) {
-    const int d = lo.dil(l);
-    const bool top = l == lo.L - 1;
-    {
-      ActGemmCall g;
-      memset(&g, 0, sizeof(g));
-      g.a[0] = a_dxin; g.a[1] = a_dskip; g.na = 2;
-      if (top) {
-        g.seg[0] = Seg{1, 0, 0, lo.S / kBK, 0, 1}; g.nseg = 1; g.w_k0 = lo.R;
-      } else {
-        g.seg[0] = Seg{0, 0, 0, lo.R / kBK, l + 1, 1};
-        g.seg[1] = Seg{1, 0, 0, lo.S / kBK, 0, 1};
-        g.nseg = 2; g.w_k0 = 0;
-      }
-      g.w = pk + lo.k_WozT; g.wN = lo.Gh; g.wK = lo.R + lo.S; g.wL = lo.L; g.w_layer = l;
-      g.T = lo.T; g.B = lo.B; g.n_tiles = lo.Gh / bn_z;
-      const long long lofs = (long long)l * BT * lo.Gh;
-      g.epi.ptr[0] = ta_all + lofs; g.epi.ptr[1] = sb_all + lofs; g.epi.ptr[2] = dg + (long long)l * BT * lo.G;
-      g.epi.i[0] = lo.Gh;
-      rc = launch_act_gemm(EPI_GATE_BWD, bn_z, g, st);
-      if (rc) return rc;
-    }
-    {
-      ActGemmCall g;
-      memset(&g, 0, sizeof(g));
-      g.a[0] = a_dg; g.na = 1;
-      for (int j = 0; j < 3; ++j) g.seg[j] = Seg{0, (2 - j) * d, 0, lo.G / kBK, l, 1};
-      g.nseg = 3;
-      g.w = pk + lo.k_WdT; g.wN = lo.R; g.wK = 3 * lo.G; g.wL = lo.L; g.w_layer = l;
-      g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
-      g.epi.ptr[0] = top ? nullptr : dxin + (long long)(l + 1) * BT * lo.R;
-      g.epi.ptr[1] = dxin + (long long)l * BT * lo.R;
-      g.epi.f[0] = lo.res_scale; g.epi.f[1] = p; g.epi.i[1] = l; g.epi.seed = seed;
-      g.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
-      rc = launch_act_gemm(EPI_DX, lo.R, g, st);
-      if (rc) return rc;
-    }
+    ActGemmCall gz = make_dz_call(lo, ws, pk, l);
+    rc = launch_act_gemm(EPI_GATE_BWD, bn_z, gz, st);
+    if (rc) return rc;
+    ActGemmCall gx = make_dx_call(lo, ws, pk, l, p, seed, d_step);
+    rc = launch_act_gemm(EPI_DX, lo.R, gx, st);
+    if (rc) return rc;
   }
   // weight gradients: one batched launch for the whole stack, one for the head
   {
@@ -941,24 +966,34 @@ extern "C" int t2_wn_workspace_tensor(const t2_wn_config_t* cfg, void* d_workspa
   return t2_set_error(T2_ERR_INVALID_ARG, "unknown workspace tensor '%s'", name);
 }
 
-// Times `reps` back-to-back launches of one layer's gate GEMM (the dominant kernel of the step) with CUDA events on
-// the launching stream; the workspace must hold the activations of a previous t2_wn_forward. Synchronises.
-extern "C" int t2_wn_time_gate_gemm(const t2_wn_config_t* cfg, const void* d_packed, void* d_workspace, int layer,
-                                    int reps, float* ms_per_launch, void* stream) {
+// Times `reps` back-to-back launches of one per-layer GEMM of the residual stack with CUDA events on the launching
+// stream: which = 0 gate (dilated conv + cin + tanh*sigmoid), 1 out 1x1 + residual, 2 dz + gate backward, 3 dx (data
+// gradient of the dilated conv). The workspace must hold the state of a previous forward (+ backward). Synchronises.
+extern "C" int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                                 int which, int layer, int reps, float* ms_per_launch, void* stream) {
   Layout lo;
   int rc = build_layout(cfg, lo);
   if (rc) return rc;
-  T2_REQUIRE(layer >= 0 && layer < lo.L && reps >= 1 && ms_per_launch, T2_ERR_INVALID_ARG, "time_gate_gemm: bad arguments");
+  T2_REQUIRE(layer >= 0 && layer < lo.L && reps >= 1 && ms_per_launch && which >= 0 && which <= 3, T2_ERR_INVALID_ARG,
+             "time_kernel: bad arguments");
+  T2_REQUIRE(which != 1 || layer + 1 < lo.L, T2_ERR_INVALID_ARG, "the last layer has no out GEMM");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ActGemmCall g = make_gate_call(lo, static_cast<uint8_t*>(d_workspace), static_cast<const uint8_t*>(d_packed), layer, true);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
+  ActGemmCall g;
+  int epi, bn;
+  if (which == 0) { g = make_gate_call(lo, ws, pk, layer, true); epi = EPI_GATE; bn = 256; }
+  else if (which == 1) { g = make_out_call(lo, ws, pk, d_params, layer, cfg->dropout, 1, nullptr); epi = EPI_RES; bn = lo.R; }
+  else if (which == 2) { g = make_dz_call(lo, ws, pk, layer); epi = EPI_GATE_BWD; bn = lo.Gh >= 256 ? 256 : 128; }
+  else { g = make_dx_call(lo, ws, pk, layer, cfg->dropout, 1, nullptr); epi = EPI_DX; bn = lo.R; }
   cudaEvent_t e0, e1;
   T2_CHECK_CUDA(cudaEventCreate(&e0));
   T2_CHECK_CUDA(cudaEventCreate(&e1));
-  rc = launch_act_gemm(EPI_GATE, 256, g, st);  // warm-up
+  rc = launch_act_gemm(epi, bn, g, st);  // warm-up
   if (rc) return rc;
   T2_CHECK_CUDA(cudaEventRecord(e0, st));
   for (int i = 0; i < reps; ++i) {
-    rc = launch_act_gemm(EPI_GATE, 256, g, st);
+    rc = launch_act_gemm(epi, bn, g, st);
     if (rc) return rc;
   }
   T2_CHECK_CUDA(cudaEventRecord(e1, st));

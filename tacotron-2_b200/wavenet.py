@@ -209,11 +209,15 @@ class WaveNet(object):
         """kernels of libt2b200 per optimisation step (graph replays re-launch the captured ones)"""
         return getattr(self, "_fwd_bwd_launches", 0) + getattr(self, "_opt_launches", 0)
 
-    def time_gate_gemm(self, layer, reps=20):
+    def time_kernel(self, which, layer, reps=20):
+        """which: 0 gate GEMM, 1 out GEMM, 2 dz/gate-backward GEMM, 3 dx GEMM -> average ms per launch"""
         ms = ctypes.c_float()
-        L.check(self.lib.t2_wn_time_gate_gemm(ctypes.byref(self.cfg), L.ptr(self.packed), L.ptr(self.workspace),
-                                              layer, reps, ctypes.byref(ms), L.stream_ptr()))
+        L.check(self.lib.t2_wn_time_kernel(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
+                                           L.ptr(self.workspace), which, layer, reps, ctypes.byref(ms), L.stream_ptr()))
         return ms.value
+
+    def time_gate_gemm(self, layer, reps=20):
+        return self.time_kernel(0, layer, reps)
 
     def learning_rate(self):
         hp = self.hp
