@@ -109,6 +109,25 @@ int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_params, const vo
 int t2_wn_workspace_tensor(const t2_wn_config_t* cfg, void* d_workspace, const char* name, void** ptr,
                            long long* count, int* elem_bytes);
 
+
+/* ---- WaveNet vocoder: Fast-WaveNet autoregressive synthesis ---------------------------------------------------
+ * Replaces WaveNet.incremental (wavenet_vocoder/models/wavenet.py:724-911), CausalConv1D incremental path
+ * (modules.py:273-303) and sample_from_discretized_mix_logistic (mixture.py:76-107). cfg->B = synthesis batch,
+ * cfg->T = samples to generate. cluster_size in {1,2,4,8,16}: CTAs per thread-block cluster sharing one batch group. */
+int t2_wn_ar_sizes(const t2_wn_config_t* cfg, int cluster_size, long long* packed_bytes, long long* workspace_bytes);
+/* fp32 masters -> slice-major bf16 synthesis weights + ring tables; run once per checkpoint; synchronises */
+int t2_wn_ar_pack(const t2_wn_config_t* cfg, int cluster_size, const float* d_params, void* d_packed_ar,
+                  void* d_workspace, void* stream);
+/* d_c: fp32 [B,cin,Tc] (feeder-normalised mels); d_initial: int32[B] (mu-law index, 127 = silence) or fp32[B];
+ * d_test_inputs: NULL or int32/fp32 [B,T] teacher-forcing inputs (the reference's wavenet_synth_debug path);
+ * d_u_a / d_u_b: NULL (on-device counter RNG from `seed`) or injected uniforms in (0,1): MoL d_u_a [B,T,nr_mix] mixture
+ * selection and d_u_b [B,T] logistic draw; mu-law d_u_a [B,T]. d_out_samples: int32 / fp32 [B,T];
+ * d_out_raw: NULL or fp32 [B,T,out_channels] network outputs (what the reference collects in tower_y_hat_eval). */
+int t2_wn_ar_generate(const t2_wn_config_t* cfg, int cluster_size, const float* d_params, const void* d_packed_ar,
+                      void* d_workspace, const float* d_c, const void* d_initial, const void* d_test_inputs,
+                      const float* d_u_a, const float* d_u_b, unsigned long long seed, void* d_out_samples,
+                      float* d_out_raw, void* stream);
+
 /* ---- optimizer: tf.train.AdamOptimizer + per-tensor clip_by_norm/clip_by_value + EMA ------------------------
  * Replaces wavenet.py:586-613 (and tacotron.py:429-437 with global_norm_clip > 0).
  * d_offsets: int64 [n_tensors + 1] element offsets of the tensors inside the flat buffers.

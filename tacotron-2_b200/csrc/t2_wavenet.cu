@@ -1005,3 +1005,527 @@ extern "C" int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_param
   cudaEventDestroy(e1);
   return T2_OK;
 }
+
+// =========================================================================================================
+// Fast-WaveNet autoregressive synthesis (wavenet_vocoder/models/wavenet.py:724-911, modules.py:273-303)
+// =========================================================================================================
+// One persistent kernel generates the whole utterance. A thread-block CLUSTER of CS CTAs owns `NI` batch items;
+// every layer's output channels are split across the cluster's CTAs, bf16 weights stream from L2 (the 27.6 MB of
+// the paper-width model stay L2-resident), activations live in shared memory as fp32 and are exchanged between
+// CTAs through distributed shared memory + one cluster barrier per stage (2 per layer). The reference's
+// convolution queues (O(d) concat shift per step, modules.py:285-288) become ring buffers in global memory.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace t2 {
+namespace {
+
+constexpr int kArThreads = 512;
+constexpr int kArMaxItems = 4;
+
+struct ArLayout {
+  int CS, ZC, RC, SC, FC, OC, K1;
+  long long per_rank_layer;        // bf16 elements per (layer, rank): 2*ZC*K1 + (RC+SC)*Gh
+  long long o_head1, o_head2;      // element offsets of the head blocks (after all layers)
+  long long n_weights;             // bf16 elements
+  long long o_bias;                // byte offset of the fp32 bias block
+  long long packed_bytes;
+  long long ring_slots_total;      // sum over layers of slots
+  long long workspace_bytes, w_cup, w_upout_base, w_ring, w_ringoff;
+  std::vector<int> ring_slots, ring_off;
+};
+
+int build_ar_layout(const Layout& lo, int CS, ArLayout& a) {
+  T2_REQUIRE(CS == 1 || CS == 2 || CS == 4 || CS == 8 || CS == 16, T2_ERR_INVALID_ARG, "cluster size must be 1,2,4,8,16");
+  a.CS = CS;
+  a.ZC = lo.Gh / CS; a.RC = lo.R / CS; a.SC = lo.S / CS; a.FC = lo.S / CS; a.OC = (lo.O + CS - 1) / CS;
+  a.K1 = 3 * lo.R + lo.C;
+  a.per_rank_layer = 2LL * a.ZC * a.K1 + (long long)(a.RC + a.SC) * lo.Gh;
+  a.o_head1 = a.per_rank_layer * CS * lo.L;
+  a.o_head2 = a.o_head1 + (long long)CS * a.FC * lo.S;
+  a.n_weights = a.o_head2 + (long long)CS * a.OC * lo.S;
+  a.o_bias = align_up(a.n_weights * 2, 256);
+  // biases fp32: per layer [G gate | R out], then skip_total [S], f1 [S], f2 [O padded to CS*OC]
+  a.packed_bytes = a.o_bias + 4LL * ((long long)lo.L * (lo.G + lo.R) + 2 * lo.S + CS * a.OC);
+  a.ring_slots.clear(); a.ring_off.clear();
+  long long off = 0;
+  for (int l = 0; l < lo.L; ++l) {
+    int need = 2 * lo.dil(l) + 1, s = 1;
+    while (s < need) s <<= 1;
+    a.ring_slots.push_back(s);
+    a.ring_off.push_back(int(off));
+    off += s;
+  }
+  a.ring_slots_total = off;
+  long long o = 0;
+  auto takeb = [&](long long bytes) { long long r = o; o = align_up(o + bytes, 256); return r; };
+  const long long BT = (long long)lo.B * lo.T;
+  a.w_cup = takeb(BT * (lo.C > 0 ? lo.C : 8) * 2);
+  a.w_upout_base = o;
+  for (size_t i = 0; i < lo.up_w.size(); ++i) takeb((long long)lo.B * lo.C * lo.up_w[i] * 4);
+  a.w_ring = takeb((long long)lo.B * off * lo.R * 4);
+  a.w_ringoff = takeb(2LL * lo.L * 4);
+  a.workspace_bytes = o;
+  return T2_OK;
+}
+
+struct ArPackArgs {
+  const float* params;
+  bf16* w;
+  float* bias;
+  const long long* offs;   // per layer: dil_k, dil_b, c_k, c_b, s_k, s_b, o_k, o_b  (8 per layer); then f1_k,f1_b,f2_k,f2_b
+  const float* skip_scale;
+  int L, R, G, Gh, S, C, O, CS, ZC, RC, SC, FC, OC, K1;
+  long long per_rank_layer, o_head1, o_head2, n_weights;
+};
+__global__ void ar_pack_kernel(ArPackArgs a) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < a.n_weights) {
+    float v = 0.f;
+    if (e < a.o_head1) {
+      const int lr = int(e / a.per_rank_layer);
+      const int l = lr / a.CS, r = lr % a.CS;
+      long long i = e % a.per_rank_layer;
+      const long long* o = a.offs + 8 * l;
+      if (i < 2LL * a.ZC * a.K1) {
+        const int row = int(i / a.K1), k = int(i % a.K1);
+        const int ch = (row < a.ZC) ? r * a.ZC + row : a.Gh + r * a.ZC + (row - a.ZC);
+        if (k < 3 * a.R) v = a.params[o[0] + (long long)(k / a.R) * a.R * a.G + (long long)(k % a.R) * a.G + ch];
+        else v = a.params[o[2] + (long long)(k - 3 * a.R) * a.G + ch];
+      } else {
+        i -= 2LL * a.ZC * a.K1;
+        const int row = int(i / a.Gh), k = int(i % a.Gh);
+        if (row < a.RC) v = a.params[o[6] + (long long)k * a.R + r * a.RC + row];
+        else v = a.params[o[4] + (long long)k * a.S + r * a.SC + (row - a.RC)] * a.skip_scale[l];
+      }
+    } else if (e < a.o_head2) {
+      const long long i = e - a.o_head1;
+      const int row = int(i / a.S), k = int(i % a.S);   // row = r*FC + j == output channel
+      v = a.params[a.offs[8 * a.L + 0] + (long long)k * a.S + row];
+    } else {
+      const long long i = e - a.o_head2;
+      const int row = int(i / a.S), k = int(i % a.S);
+      if (row < a.O) v = a.params[a.offs[8 * a.L + 2] + (long long)k * a.O + row];
+    }
+    a.w[e] = __float2bfloat16(v);
+  }
+  // biases
+  const long long nb = (long long)a.L * (a.G + a.R) + 2 * a.S + a.CS * a.OC;
+  if (e < nb) {
+    float v = 0.f;
+    const long long lg = (long long)a.L * (a.G + a.R);
+    if (e < lg) {
+      const int l = int(e / (a.G + a.R)), j = int(e % (a.G + a.R));
+      const long long* o = a.offs + 8 * l;
+      if (j < a.G) v = a.params[o[1] + j] + (a.C > 0 ? a.params[o[3] + j] : 0.f);
+      else v = a.params[o[7] + (j - a.G)];
+    } else if (e < lg + a.S) {
+      const int s = int(e - lg);
+      for (int l = 0; l < a.L; ++l) v += a.skip_scale[l] * a.params[a.offs[8 * l + 5] + s];
+    } else if (e < lg + 2 * a.S) {
+      v = a.params[a.offs[8 * a.L + 1] + (e - lg - a.S)];
+    } else {
+      const int j = int(e - lg - 2 * a.S);
+      if (j < a.O) v = a.params[a.offs[8 * a.L + 3] + j];
+    }
+    a.bias[e] = v;
+  }
+}
+
+struct ArArgs {
+  const bf16* w;            // slice-major weights
+  const float* bias;
+  const float* in_k;        // input_convolution kernel fp32 [cin][R]
+  const float* in_b;
+  const bf16* c_up;         // [B][T][C]
+  float* ring;              // [B][ring_slots_total][R]
+  const int* ring_off;      // [L] then ring_slots [L]
+  const void* initial;      // int32 [B] or f32 [B]
+  const void* test_inputs;  // nullable: int32 / f32 [B][T]
+  const float* u_a;         // MoL: [B][T][nm] mixture-selection uniforms; categorical: [B][T]; nullable
+  const float* u_b;         // MoL: [B][T] logistic uniforms; nullable
+  void* out_samples;        // int32 / f32 [B][T]
+  float* out_raw;           // nullable [B][T][O]
+  unsigned long long seed;
+  int B, T, L, R, G, Gh, S, C, O, Q, scalar_in, layers_per_stack;
+  int CS, ZC, RC, SC, FC, OC, K1;
+  long long per_rank_layer, o_head1, o_head2;
+  float res_scale, log_scale_min;
+  int items_per_cluster;
+};
+
+// y[o][it] = sum_k W[o][k] * x[it][k] for o in [0, nout): 16 warps stride the outputs, lanes stride 8-element K chunks
+template <int NI>
+__device__ __forceinline__ void ar_matvec(const bf16* __restrict__ W, int nout, int K, const float* __restrict__ x /*[NI][ldx]*/,
+                                          int ldx, float* __restrict__ y /*[NI][ldy] at column offset*/, int ldy, int ni) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = K >> 3;
+  for (int o = warp; o < nout; o += kArThreads / 32) {
+    float acc[NI];
+#pragma unroll
+    for (int it = 0; it < NI; ++it) acc[it] = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)o * K);
+    for (int c = lane; c < nchunk; c += 32) {
+      const uint4 u = __ldg(wr + c);
+      const float w0 = bf16lo(u.x), w1 = bf16hi(u.x), w2 = bf16lo(u.y), w3 = bf16hi(u.y);
+      const float w4 = bf16lo(u.z), w5 = bf16hi(u.z), w6 = bf16lo(u.w), w7 = bf16hi(u.w);
+#pragma unroll
+      for (int it = 0; it < NI; ++it) {
+        if (it < ni) {
+          const float4 a = *reinterpret_cast<const float4*>(x + it * ldx + c * 8);
+          const float4 b = *reinterpret_cast<const float4*>(x + it * ldx + c * 8 + 4);
+          acc[it] += w0 * a.x + w1 * a.y + w2 * a.z + w3 * a.w + w4 * b.x + w5 * b.y + w6 * b.z + w7 * b.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NI; ++it) {
+      const float s = warp_sum(acc[it]);
+      if (lane == 0 && it < ni) y[it * ldy + o] = s;
+    }
+  }
+}
+
+template <int NI>
+__global__ void __launch_bounds__(kArThreads, 1) wn_ar_kernel(ArArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = int(cluster.block_rank());
+  const int cid = blockIdx.x / a.CS;
+  const int item0 = cid * a.items_per_cluster;
+  int ni = a.B - item0;
+  if (ni > a.items_per_cluster) ni = a.items_per_cluster;
+  if (ni < 0) ni = 0;   // surplus clusters still take part in no barriers of other clusters; they just idle through
+  extern __shared__ __align__(16) float sm[];
+  const int ld1 = (a.K1 + 3) & ~3;
+  float* in1 = sm;                                  // [NI][ld1]  : x(t-2d) | x(t-d) | x(t) | c(t)
+  float* zbuf = in1 + NI * ld1;                     // [NI][Gh]
+  float* xbuf = zbuf + NI * a.Gh;                   // [NI][R]    : current layer input (full vector)
+  float* loc = xbuf + NI * a.R;                     // [NI][2*ZC] : this CTA's gate pre-activations / stage-2 outputs
+  float* skip = loc + NI * (2 * a.ZC > a.RC + a.SC ? 2 * a.ZC : a.RC + a.SC);   // [NI][SC] running skip sum (slice)
+  float* hbuf = skip + NI * a.SC;                   // [NI][S]    : head activations (full vector)
+  float* obuf = hbuf + NI * a.S;                    // [NI][CS*OC]: network output (full vector)
+  float* cur = obuf + NI * a.CS * a.OC;             // [NI]       : current input sample (scalar) or index
+  const int tid = threadIdx.x;
+  const float* bias_all = a.bias;
+  const float* b_skip = bias_all + (long long)a.L * (a.G + a.R);
+  const float* b_f1 = b_skip + a.S;
+  const float* b_f2 = b_f1 + a.S;
+  const int nm = a.O / 3;
+
+  for (int i = tid; i < NI; i += kArThreads)
+    if (i < ni) cur[i] = a.scalar_in ? static_cast<const float*>(a.initial)[item0 + i]
+                                     : float(static_cast<const int*>(a.initial)[item0 + i]);
+  __syncthreads();
+
+  for (int t = 0; t < a.T; ++t) {
+    // ---- first conv: x0 = W_in[idx] + b (one-hot) or x * w + b (scalar); every CTA builds the full vector ----
+    for (int i = tid; i < ni * a.R; i += kArThreads) {
+      const int it = i / a.R, r = i % a.R;
+      float v;
+      if (a.scalar_in) v = cur[it] * a.in_k[r] + a.in_b[r];
+      else v = a.in_k[(long long)int(cur[it]) * a.R + r] + a.in_b[r];
+      xbuf[it * a.R + r] = v;
+    }
+    for (int i = tid; i < ni * a.SC; i += kArThreads) skip[i] = 0.f;
+    __syncthreads();
+    for (int l = 0; l < a.L; ++l) {
+      const int d = 1 << (l % a.layers_per_stack);
+      const int slots = a.ring_off[a.L + l];
+      const long long roff = a.ring_off[l];
+      // ---- gather the stage-1 input: taps from the ring (zeros before t = 0), current x, conditioning ----
+      for (int i = tid; i < ni * ld1; i += kArThreads) {
+        const int it = i / ld1, k = i % ld1;
+        float v = 0.f;
+        if (k < 2 * a.R) {
+          const int tap = k / a.R, r = k % a.R;
+          const int tt = t - (2 - tap) * d;
+          if (tt >= 0) v = __ldcg(a.ring + ((long long)(item0 + it) * a.ring_off[2 * a.L] + roff + (tt & (slots - 1))) * a.R + r);
+        } else if (k < 3 * a.R) {
+          v = xbuf[it * a.R + (k - 2 * a.R)];
+        } else if (k < a.K1) {
+          v = __bfloat162float(a.c_up[((long long)(item0 + it) * a.T + t) * a.C + (k - 3 * a.R)]);
+        }
+        in1[i] = v;
+      }
+      __syncthreads();
+      // rank 0 publishes x_l(t) into the ring for later steps (read back no earlier than step t + d)
+      if (rank == 0)
+        for (int i = tid; i < ni * a.R; i += kArThreads) {
+          const int it = i / a.R, r = i % a.R;
+          a.ring[((long long)(item0 + it) * a.ring_off[2 * a.L] + roff + (t & (slots - 1))) * a.R + r] = xbuf[i];
+        }
+      // ---- stage 1: gate pre-activations for this CTA's ZC z-channels (a rows then b rows) ----
+      const bf16* w1 = a.w + ((long long)l * a.CS + rank) * a.per_rank_layer;
+      ar_matvec<NI>(w1, 2 * a.ZC, a.K1, in1, ld1, loc, 2 * a.ZC, ni);
+      __syncthreads();
+      const float* bg = bias_all + (long long)l * (a.G + a.R);
+      for (int i = tid; i < ni * a.ZC; i += kArThreads) {
+        const int it = i / a.ZC, j = i % a.ZC;
+        const int ch = rank * a.ZC + j;
+        const float av = loc[it * 2 * a.ZC + j] + bg[ch];
+        const float bv = loc[it * 2 * a.ZC + a.ZC + j] + bg[a.Gh + ch];
+        const float z = tanhf_(av) * sigmoidf_(bv);
+        for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(zbuf, r)[it * a.Gh + ch] = z;
+      }
+      cluster.sync();
+      // ---- stage 2: this CTA's RC residual-out channels and SC skip channels ----
+      const bf16* w2 = w1 + 2LL * a.ZC * a.K1;
+      ar_matvec<NI>(w2, a.RC + a.SC, a.Gh, zbuf, a.Gh, loc, a.RC + a.SC, ni);
+      __syncthreads();
+      for (int i = tid; i < ni * (a.RC + a.SC); i += kArThreads) {
+        const int it = i / (a.RC + a.SC), j = i % (a.RC + a.SC);
+        const float v = loc[it * (a.RC + a.SC) + j];
+        if (j < a.RC) {
+          const int ch = rank * a.RC + j;
+          const float xn = (v + bg[a.G + ch] + xbuf[it * a.R + ch]) * a.res_scale;
+          if (l + 1 < a.L)
+            for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(hbuf, r)[it * a.S + ch] = xn;  // staged in hbuf (R <= S)
+        } else {
+          skip[it * a.SC + (j - a.RC)] += v;   // scale_l folded into the packed skip weights
+        }
+      }
+      cluster.sync();
+      if (l + 1 < a.L) {
+        for (int i = tid; i < ni * a.R; i += kArThreads) xbuf[(i / a.R) * a.R + i % a.R] = hbuf[(i / a.R) * a.S + i % a.R];
+        __syncthreads();
+      }
+    }
+    // ---- head: relu(skips + b) -> f1 -> relu -> f2 ----
+    for (int i = tid; i < ni * a.SC; i += kArThreads) {
+      const int it = i / a.SC, j = i % a.SC, ch = rank * a.SC + j;
+      const float v = fmaxf(skip[i] + b_skip[ch], 0.f);
+      for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(hbuf, r)[it * a.S + ch] = v;
+    }
+    cluster.sync();
+    ar_matvec<NI>(a.w + a.o_head1 + (long long)rank * a.FC * a.S, a.FC, a.S, hbuf, a.S, loc, a.FC, ni);
+    __syncthreads();
+    cluster.sync();   // every CTA has finished reading hbuf (h1) before it is overwritten with h2
+    for (int i = tid; i < ni * a.FC; i += kArThreads) {
+      const int it = i / a.FC, j = i % a.FC, ch = rank * a.FC + j;
+      const float v = fmaxf(loc[it * a.FC + j] + b_f1[ch], 0.f);
+      for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(hbuf, r)[it * a.S + ch] = v;
+    }
+    cluster.sync();
+    ar_matvec<NI>(a.w + a.o_head2 + (long long)rank * a.OC * a.S, a.OC, a.S, hbuf, a.S, loc, a.OC, ni);
+    __syncthreads();
+    for (int i = tid; i < ni * a.OC; i += kArThreads) {
+      const int it = i / a.OC, j = i % a.OC, ch = rank * a.OC + j;
+      const float v = loc[it * a.OC + j] + b_f2[ch];
+      for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(obuf, r)[it * a.CS * a.OC + ch] = v;
+    }
+    cluster.sync();
+    // ---- sample (identically in every CTA: same inputs, same uniforms) ----
+    if (tid < 32 * NI) {
+      const int it = tid >> 5, lane = tid & 31;
+      if (it < ni) {
+        const int bi = item0 + it;
+        const float* y = obuf + it * a.CS * a.OC;
+        if (rank == 0 && a.out_raw)
+          for (int j = lane; j < a.O; j += 32) a.out_raw[((long long)bi * a.T + t) * a.O + j] = y[j];
+        float nxt;
+        if (a.scalar_in) {
+          // sample_from_discretized_mix_logistic (mixture.py:76-107): Gumbel-max over the mixture logits
+          float best = -INFINITY;
+          int bk = 0;
+          for (int k = 0; k < nm; ++k) {
+            float u = a.u_a ? a.u_a[((long long)bi * a.T + t) * nm + k]
+                            : 1e-5f + (1.f - 2e-5f) * hash_uniform(a.seed, ((unsigned long long)bi * a.T + t) * 16 + k);
+            const float g = y[k] - __logf(-__logf(u));
+            if (g > best) { best = g; bk = k; }
+          }
+          const float mean = y[nm + bk];
+          const float ls = fmaxf(y[2 * nm + bk], a.log_scale_min);
+          const float u = a.u_b ? a.u_b[(long long)bi * a.T + t]
+                                : 1e-5f + (1.f - 2e-5f) * hash_uniform(a.seed, ((unsigned long long)bi * a.T + t) * 16 + 15);
+          float x = mean + __expf(ls) * (__logf(u) - __logf(1.f - u));
+          nxt = fminf(fmaxf(x, -1.f), 1.f);
+          if (rank == 0 && lane == 0) static_cast<float*>(a.out_samples)[(long long)bi * a.T + t] = nxt;
+        } else {
+          // categorical sample from softmax(logits) by inverse CDF (tf.multinomial on raw logits, wavenet.py:865)
+          float mx = -INFINITY;
+          for (int j = lane; j < a.O; j += 32) mx = fmaxf(mx, y[j]);
+          mx = warp_max(mx);
+          float se = 0.f;
+          for (int j = lane; j < a.O; j += 32) se += __expf(y[j] - mx);
+          se = warp_sum(se);
+          const float u = (a.u_a ? a.u_a[(long long)bi * a.T + t]
+                                 : hash_uniform(a.seed, (unsigned long long)bi * a.T + t)) * se;
+          // lane-blocked scan: each lane owns O/32 consecutive classes
+          const int per = (a.O + 31) / 32;
+          float part = 0.f;
+          for (int j = lane * per; j < (lane + 1) * per && j < a.O; ++j) part += __expf(y[j] - mx);
+          float incl = part;
+          for (int o = 1; o < 32; o <<= 1) {
+            const float nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+          }
+          const float excl = incl - part;
+          int pick = -1;
+          if (u >= excl && u < incl) {
+            float c = excl;
+            pick = lane * per;
+            for (int j = lane * per; j < (lane + 1) * per && j < a.O; ++j) { c += __expf(y[j] - mx); pick = j; if (c > u) break; }
+          }
+          pick = __reduce_max_sync(0xffffffffu, pick);
+          if (pick < 0) pick = a.O - 1;
+          nxt = float(pick);
+          if (rank == 0 && lane == 0) static_cast<int*>(a.out_samples)[(long long)bi * a.T + t] = pick;
+        }
+        if (a.test_inputs)
+          nxt = a.scalar_in ? static_cast<const float*>(a.test_inputs)[(long long)bi * a.T + t]
+                            : float(static_cast<const int*>(a.test_inputs)[(long long)bi * a.T + t]);
+        if (lane == 0) cur[it] = nxt;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace t2
+
+typedef struct {
+  long long packed_bytes, workspace_bytes;
+} t2_wn_ar_sizes_t_;
+
+extern "C" int t2_wn_ar_sizes(const t2_wn_config_t* cfg, int cluster_size, long long* packed_bytes, long long* workspace_bytes) {
+  Layout lo;
+  int rc = build_layout(cfg, lo);
+  if (rc) return rc;
+  ArLayout a;
+  rc = build_ar_layout(lo, cluster_size, a);
+  if (rc) return rc;
+  T2_REQUIRE(lo.Gh % cluster_size == 0 && lo.R % cluster_size == 0 && lo.S % cluster_size == 0 && lo.R <= lo.S + 0,
+             T2_ERR_UNSUPPORTED_SHAPE, "channel counts must divide by the cluster size and R <= S");
+  *packed_bytes = a.packed_bytes;
+  *workspace_bytes = a.workspace_bytes;
+  return T2_OK;
+}
+
+extern "C" int t2_wn_ar_pack(const t2_wn_config_t* cfg, int cluster_size, const float* d_params, void* d_packed_ar,
+                             void* d_workspace, void* stream) {
+  Layout lo;
+  int rc = build_layout(cfg, lo);
+  if (rc) return rc;
+  ArLayout a;
+  rc = build_ar_layout(lo, cluster_size, a);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<long long> offs(8 * lo.L + 4);
+  for (int l = 0; l < lo.L; ++l) {
+    long long* o = &offs[8 * l];
+    o[0] = lo.p_dil_k[l]; o[1] = lo.p_dil_b[l]; o[2] = lo.C > 0 ? lo.p_c_k[l] : 0; o[3] = lo.C > 0 ? lo.p_c_b[l] : 0;
+    o[4] = lo.p_s_k[l]; o[5] = lo.p_s_b[l]; o[6] = lo.p_o_k[l]; o[7] = lo.p_o_b[l];
+  }
+  offs[8 * lo.L] = lo.p_f1_k; offs[8 * lo.L + 1] = lo.p_f1_b; offs[8 * lo.L + 2] = lo.p_f2_k; offs[8 * lo.L + 3] = lo.p_f2_b;
+  // tables go through a temporary device allocation (this entry point synchronises; it runs once per checkpoint)
+  long long* d_offs = nullptr;
+  float* d_scale = nullptr;
+  T2_CHECK_CUDA(cudaMallocAsync(&d_offs, offs.size() * sizeof(long long), st));
+  T2_CHECK_CUDA(cudaMallocAsync(&d_scale, lo.L * sizeof(float), st));
+  T2_CHECK_CUDA(cudaMemcpyAsync(d_offs, offs.data(), offs.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+  T2_CHECK_CUDA(cudaMemcpyAsync(d_scale, lo.skip_scale.data(), lo.L * sizeof(float), cudaMemcpyHostToDevice, st));
+  ArPackArgs p;
+  p.params = d_params; p.w = static_cast<bf16*>(d_packed_ar);
+  p.bias = reinterpret_cast<float*>(static_cast<uint8_t*>(d_packed_ar) + a.o_bias);
+  p.offs = d_offs; p.skip_scale = d_scale;
+  p.L = lo.L; p.R = lo.R; p.G = lo.G; p.Gh = lo.Gh; p.S = lo.S; p.C = lo.C; p.O = lo.O; p.CS = a.CS; p.ZC = a.ZC; p.RC = a.RC;
+  p.SC = a.SC; p.FC = a.FC; p.OC = a.OC; p.K1 = a.K1; p.per_rank_layer = a.per_rank_layer; p.o_head1 = a.o_head1;
+  p.o_head2 = a.o_head2; p.n_weights = a.n_weights;
+  ar_pack_kernel<<<grid1d(a.n_weights), 256, 0, st>>>(p); t2_count_launch();
+  T2_CHECK_CUDA(cudaGetLastError());
+  // ring tables
+  std::vector<int> rt(2 * lo.L + 1);
+  for (int l = 0; l < lo.L; ++l) { rt[l] = a.ring_off[l]; rt[lo.L + l] = a.ring_slots[l]; }
+  rt[2 * lo.L] = int(a.ring_slots_total);
+  T2_CHECK_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d_workspace) + a.w_ringoff, rt.data(), rt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  T2_CHECK_CUDA(cudaStreamSynchronize(st));
+  cudaFreeAsync(d_offs, st);
+  cudaFreeAsync(d_scale, st);
+  return T2_OK;
+}
+
+extern "C" int t2_wn_ar_generate(const t2_wn_config_t* cfg, int cluster_size, const float* d_params, const void* d_packed_ar,
+                                 void* d_workspace, const float* d_c, const void* d_initial, const void* d_test_inputs,
+                                 const float* d_u_a, const float* d_u_b, unsigned long long seed, void* d_out_samples,
+                                 float* d_out_raw, void* stream) {
+  Layout lo;
+  int rc = build_layout(cfg, lo);
+  if (rc) return rc;
+  ArLayout al;
+  rc = build_ar_layout(lo, cluster_size, al);
+  if (rc) return rc;
+  T2_REQUIRE(lo.C > 0, T2_ERR_UNSUPPORTED_SHAPE, "AR synthesis needs local conditioning");
+  T2_REQUIRE(lo.R <= lo.S, T2_ERR_UNSUPPORTED_SHAPE, "AR synthesis needs residual_channels <= skip_out_channels");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(d_packed_ar);
+  const long long BT = (long long)lo.B * lo.T;
+  // conditioning -> c_up (bf16 channels-last), same kernels as the training path
+  bf16* c_up = reinterpret_cast<bf16*>(ws + al.w_cup);
+  if (cfg->c_pre_upsampled) {
+    f32_to_bf16_kernel<<<grid1d(BT * lo.C), 256, 0, st>>>(d_c, c_up, BT * lo.C); t2_count_launch();
+  } else {
+    const float* in = d_c;
+    int W = lo.Tc;
+    long long o = al.w_upout_base;
+    for (size_t i = 0; i < lo.up_w.size(); ++i) {
+      const int s = cfg->upsample_scales[i];
+      float* out = reinterpret_cast<float*>(ws + o);
+      o = align_up(o + (long long)lo.B * lo.C * lo.up_w[i] * 4, 256);
+      const bool last = i + 1 == lo.up_w.size();
+      upsample_fwd_kernel<<<grid1d((long long)lo.B * lo.C * W * s), 256, 0, st>>>(
+          in, d_params + lo.p_up_k[i], d_params + lo.p_up_b[i], out, last ? c_up : nullptr, lo.B, lo.C, W, s, cfg->upsample_type);
+      t2_count_launch();
+      in = out;
+      W *= s;
+    }
+  }
+  T2_CHECK_CUDA(cudaGetLastError());
+  ArArgs a;
+  memset(&a, 0, sizeof(a));
+  a.w = reinterpret_cast<const bf16*>(pk);
+  a.bias = reinterpret_cast<const float*>(pk + al.o_bias);
+  a.in_k = d_params + lo.p_in_k; a.in_b = d_params + lo.p_in_b;
+  a.c_up = c_up;
+  a.ring = reinterpret_cast<float*>(ws + al.w_ring);
+  a.ring_off = reinterpret_cast<const int*>(ws + al.w_ringoff);
+  a.initial = d_initial; a.test_inputs = d_test_inputs; a.u_a = d_u_a; a.u_b = d_u_b;
+  a.out_samples = d_out_samples; a.out_raw = d_out_raw; a.seed = seed;
+  a.B = lo.B; a.T = lo.T; a.L = lo.L; a.R = lo.R; a.G = lo.G; a.Gh = lo.Gh; a.S = lo.S; a.C = lo.C; a.O = lo.O; a.Q = lo.Q;
+  a.scalar_in = lo.scalar_in ? 1 : 0; a.layers_per_stack = lo.L / cfg->stacks;
+  a.CS = al.CS; a.ZC = al.ZC; a.RC = al.RC; a.SC = al.SC; a.FC = al.FC; a.OC = al.OC; a.K1 = al.K1;
+  a.per_rank_layer = al.per_rank_layer; a.o_head1 = al.o_head1; a.o_head2 = al.o_head2;
+  a.res_scale = lo.res_scale; a.log_scale_min = cfg->log_scale_min;
+  // clusters: as many as fit on the device, but never more than batch items
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int n_clusters = sms / al.CS;
+  if (n_clusters > lo.B) n_clusters = lo.B;
+  if (n_clusters < 1) n_clusters = 1;
+  int ipc = (lo.B + n_clusters - 1) / n_clusters;
+  while (ipc > kArMaxItems) { ++n_clusters; ipc = (lo.B + n_clusters - 1) / n_clusters; }  // more clusters than fit run in waves
+  n_clusters = (lo.B + ipc - 1) / ipc;
+  a.items_per_cluster = ipc;
+  const int ld1 = (al.K1 + 3) & ~3;
+  const int locw = 2 * al.ZC > al.RC + al.SC ? 2 * al.ZC : al.RC + al.SC;
+  const size_t smem = sizeof(float) * size_t(kArMaxItems) * (ld1 + lo.Gh + lo.R + locw + al.SC + lo.S + al.CS * al.OC + 1) + 64;
+  auto kern = wn_ar_kernel<kArMaxItems>;
+  T2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  if (al.CS > 8) T2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  T2_CHECK_CUDA(cudaMemsetAsync(ws + al.w_ring, 0, (size_t)lo.B * al.ring_slots_total * lo.R * 4, st));
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(n_clusters * al.CS);
+  lc.blockDim = dim3(kArThreads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = al.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  T2_CHECK_CUDA(cudaLaunchKernelEx(&lc, kern, a));
+  t2_count_launch();
+  return T2_OK;
+}

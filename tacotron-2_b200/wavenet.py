@@ -262,3 +262,48 @@ class WaveNet(object):
     def loss_value(self):
         s, n = self.loss_buf.tolist()
         return s / max(n, 1e-20)
+
+
+class WaveNetSynthesizer(object):
+    """Fast-WaveNet autoregressive generation on the B200 (wavenet_vocoder/synthesizer.py + WaveNet.incremental)."""
+
+    def __init__(self, hparams, B, T, cluster_size=8, device="cuda"):
+        self.hp = hparams
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.cfg = make_config(hparams, B, T, False, 0.0)
+        self.cs = cluster_size
+        sz = WnSizes()
+        L.check(self.lib.t2_wn_sizes(ctypes.byref(self.cfg), ctypes.byref(sz)))
+        self.n_params = sz.n_params
+        self.params = torch.zeros(sz.n_params, dtype=torch.float32, device=self.device)
+        pb, wb = ctypes.c_longlong(), ctypes.c_longlong()
+        L.check(self.lib.t2_wn_ar_sizes(ctypes.byref(self.cfg), self.cs, ctypes.byref(pb), ctypes.byref(wb)))
+        self.packed = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
+        self.workspace = torch.zeros(wb.value, dtype=torch.uint8, device=self.device)
+        self.tensors = []
+        name = ctypes.create_string_buffer(160)
+        off, nd, shp = ctypes.c_longlong(), ctypes.c_int(), (ctypes.c_int * 4)()
+        for i in range(sz.n_tensors):
+            L.check(self.lib.t2_wn_param_info(ctypes.byref(self.cfg), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp))
+            self.tensors.append((name.value.decode(), off.value, tuple(shp[k] for k in range(nd.value))))
+
+    def load_params(self, params):
+        flat = torch.zeros(self.n_params, dtype=torch.float32)
+        for name, off, shape in self.tensors:
+            flat[off:off + int(math.prod(shape))] = params[name].detach().float().reshape(-1)
+        self.params.copy_(flat.to(self.device))
+        L.check(self.lib.t2_wn_ar_pack(ctypes.byref(self.cfg), self.cs, L.ptr(self.params), L.ptr(self.packed),
+                                       L.ptr(self.workspace), L.stream_ptr()))
+
+    def generate(self, c, initial, test_inputs=None, u_a=None, u_b=None, seed=0, return_raw=False):
+        """c: fp32 [B,cin,Tc]; initial: int32/fp32 [B]. Returns samples [B,T] (and raw outputs [B,T,out])."""
+        B, T = self.cfg.B, self.cfg.T
+        scalar = self.cfg.input_type != 2
+        out = torch.empty(B, T, dtype=torch.float32 if scalar else torch.int32, device=self.device)
+        raw = torch.empty(B, T, self.cfg.out_channels, dtype=torch.float32, device=self.device) if return_raw else None
+        L.check(self.lib.t2_wn_ar_generate(ctypes.byref(self.cfg), self.cs, L.ptr(self.params), L.ptr(self.packed),
+                                           L.ptr(self.workspace), L.ptr(c), L.ptr(initial), L.ptr(test_inputs),
+                                           L.ptr(u_a), L.ptr(u_b), ctypes.c_ulonglong(seed), L.ptr(out), L.ptr(raw),
+                                           L.stream_ptr()))
+        return (out, raw) if return_raw else out
