@@ -1,0 +1,323 @@
+"""ORACLE (test infrastructure, not product code): fp32 PyTorch-CPU restatement of the reference's Tacotron-2
+mel-spectrogram predictor (training / GTA graph, teacher forcing, outputs_per_step = 1, predict_linear = False).
+
+Only tests/, __graft_entry__.smoke() and bench / tools CPU-baseline legs may import this.
+
+Follows, function by function:
+  Tacotron.initialize / add_loss / add_optimizer          tacotron/models/tacotron.py:104-200, 273-369, 371-463
+  conv1d, EncoderConvolutions, EncoderRNN, ZoneoutLSTMCell  tacotron/models/modules.py:379-391, 145-174, 177-217, 81-142
+  Prenet, DecoderRNN, FrameProjection, StopProjection      tacotron/models/modules.py:220-342
+  Postnet                                                  tacotron/models/modules.py:345-376
+  LocationSensitiveAttention, _location_sensitive_score    tacotron/models/attention.py:38-70, 95-226
+  TacotronDecoderCell.__call__ (step order)                tacotron/models/Architecture_wrappers.py:169-213
+  TacoTrainingHelper (go frame, teacher forcing)           tacotron/models/helpers.py:62-128
+TF-layer semantics (LSTMCell gate order i,j,f,o + forget_bias 1, BahdanauAttention memory / score masking, batch-norm
+eps 1e-3 with biased batch variance, 'same' conv padding, tf.losses.mean_squared_error) are restated from the public
+TF 1.x definitions.
+
+PARITY UNPINNED by the reference (no tests / golden vectors; TensorFlow 1.x is not importable here). Pinned instead:
+parameter count 27.19 M, alignments are a masked probability distribution, zero-length-padding
+invariance of the encoder, zoneout / dropout off == deterministic, gradient check of the hand-derived pieces the CUDA
+path mirrors (tests/test_oracle_tacotron.py).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+N_SYMBOLS = 66  # tacotron/utils/symbols.py:9-17
+
+
+def param_shapes(hp):
+    E, C = hp.embedding_dim, hp.enc_conv_channels
+    H, D, A = hp.encoder_lstm_units, hp.decoder_lstm_units, hp.attention_dim
+    M = hp.num_mels * hp.outputs_per_step
+    P = hp.postnet_channels
+    k_enc, k_post, k_att = hp.enc_conv_kernel_size[0], hp.postnet_kernel_size[0], hp.attention_kernel[0]
+    sh = {"inputs_embedding": (N_SYMBOLS, E)}
+    cin = E
+    for i in range(hp.enc_conv_num_layers):
+        p = "encoder_convolutions/conv_layer_%d/" % (i + 1)
+        sh[p + "kernel"] = (k_enc, cin, C)
+        sh[p + "bias"] = (C,)
+        for n in ("gamma", "beta", "moving_mean", "moving_variance"):
+            sh[p + n] = (C,)
+        cin = C
+    for d in ("fw", "bw"):
+        sh["encoder_LSTM/%s/kernel" % d] = (C + H, 4 * H)
+        sh["encoder_LSTM/%s/bias" % d] = (4 * H,)
+    sh["attention/memory_layer/kernel"] = (2 * H, A)
+    sh["attention/query_layer/kernel"] = (D, A)
+    sh["attention/location_features_convolution/kernel"] = (k_att, 1, hp.attention_filters)
+    sh["attention/location_features_convolution/bias"] = (hp.attention_filters,)
+    sh["attention/location_features_layer/kernel"] = (hp.attention_filters, A)
+    sh["attention/attention_variable_projection"] = (A,)
+    sh["attention/attention_bias"] = (A,)
+    pin = hp.num_mels
+    for i, n in enumerate(hp.prenet_layers):
+        sh["decoder_prenet/dense_%d/kernel" % (i + 1)] = (pin, n)
+        sh["decoder_prenet/dense_%d/bias" % (i + 1)] = (n,)
+        pin = n
+    lin = pin + 2 * H
+    for i in range(hp.decoder_layers):
+        sh["decoder_LSTM/cell_%d/kernel" % (i + 1)] = (lin + D, 4 * D)
+        sh["decoder_LSTM/cell_%d/bias" % (i + 1)] = (4 * D,)
+        lin = D
+    sh["linear_transform_projection/kernel"] = (D + 2 * H, M)
+    sh["linear_transform_projection/bias"] = (M,)
+    sh["stop_token_projection/kernel"] = (D + 2 * H, hp.outputs_per_step)
+    sh["stop_token_projection/bias"] = (hp.outputs_per_step,)
+    cin = hp.num_mels
+    for i in range(hp.postnet_num_layers):
+        p = "postnet_convolutions/conv_layer_%d/" % (i + 1)
+        sh[p + "kernel"] = (k_post, cin, P)
+        sh[p + "bias"] = (P,)
+        for n in ("gamma", "beta", "moving_mean", "moving_variance"):
+            sh[p + n] = (P,)
+        cin = P
+    sh["postnet_projection/kernel"] = (P, hp.num_mels)
+    sh["postnet_projection/bias"] = (hp.num_mels,)
+    return sh
+
+
+NON_TRAINABLE = ("moving_mean", "moving_variance")
+
+
+def is_trainable(name):
+    return not name.endswith(NON_TRAINABLE)
+
+
+def is_regularized(name):
+    """tacotron.py:343-345: every trainable variable whose name has none of these substrings."""
+    if not is_trainable(name):
+        return False
+    return not any(s in name for s in ("bias", "Bias", "_projection", "inputs_embedding", "RNN", "LSTM"))
+
+
+def init_params(hp, seed=None, random_bias=False):
+    gen = torch.Generator().manual_seed(hp.tacotron_random_seed if seed is None else seed)
+    params = {}
+    for name, shape in param_shapes(hp).items():
+        if name.endswith("gamma") or name.endswith("moving_variance"):
+            params[name] = torch.ones(shape)
+        elif name.endswith(("beta", "moving_mean")):
+            params[name] = torch.zeros(shape)
+        elif name.endswith("bias"):
+            params[name] = torch.randn(shape, generator=gen) * 0.1 if random_bias else torch.zeros(shape)
+        else:
+            if len(shape) == 1:
+                fan_in = fan_out = shape[0]
+            elif len(shape) == 2:
+                fan_in, fan_out = shape
+            else:
+                fan_in, fan_out = shape[0] * shape[1], shape[0] * shape[2]
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            params[name] = (torch.rand(shape, generator=gen) * 2 - 1) * lim
+    return params
+
+
+# ---------------------------------------------------------------------------------------------------------
+# layers
+# ---------------------------------------------------------------------------------------------------------
+def conv_block(x, params, prefix, activation, training, drop_rate, drop_mask=None, stats_out=None):
+    """modules.py:379-391 with batch_norm_position='after': conv('same') -> activation -> BN -> dropout.
+    x [B, T, Cin] channels-last."""
+    k = params[prefix + "kernel"]  # [kw, in, out]
+    kw = k.shape[0]
+    y = F.conv1d(x.transpose(1, 2), k.permute(2, 1, 0).contiguous(), params[prefix + "bias"],
+                 padding=(kw - 1) // 2).transpose(1, 2)
+    if activation == "relu":
+        y = F.relu(y)
+    elif activation == "tanh":
+        y = torch.tanh(y)
+    if training:
+        mean = y.mean(dim=(0, 1))
+        var = y.var(dim=(0, 1), unbiased=False)
+        if stats_out is not None:
+            stats_out[prefix] = (mean.detach(), var.detach())
+    else:
+        mean, var = params[prefix + "moving_mean"], params[prefix + "moving_variance"]
+    y = (y - mean) / torch.sqrt(var + 1e-3) * params[prefix + "gamma"] + params[prefix + "beta"]
+    if training and drop_rate > 0:
+        if drop_mask is None:
+            drop_mask = (torch.rand_like(y) >= drop_rate).float() / (1 - drop_rate)
+        y = y * drop_mask
+    return y
+
+
+def lstm_cell(x, c, h, kernel, bias):
+    """tf.nn.rnn_cell.LSTMCell: z = [x, h] W + b; i, j, f, o; forget_bias = 1."""
+    z = torch.cat([x, h], dim=-1) @ kernel + bias
+    i, j, f, o = z.chunk(4, dim=-1)
+    new_c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+    new_h = torch.sigmoid(o) * torch.tanh(new_c)
+    return new_c, new_h
+
+
+def zoneout(prev, new, rate, training, mask=None):
+    """modules.py:133-138."""
+    if training:
+        if rate == 0:
+            return new
+        if mask is None:
+            mask = (torch.rand_like(new) >= rate).float()
+        return mask * (new - prev) + prev
+    return (1 - rate) * new + rate * prev
+
+
+def encoder_rnn(x, lengths, params, hp, training, zmasks=None):
+    """bidirectional_dynamic_rnn of ZoneoutLSTMCell with sequence_length (modules.py:207-217): past the length the
+    output is zero and the state is carried; the backward direction walks the reversed (per length) sequence."""
+    B, T, _ = x.shape
+    H = hp.encoder_lstm_units
+    z = hp.tacotron_zoneout_rate
+    outs = []
+    for d in ("fw", "bw"):
+        K, b = params["encoder_LSTM/%s/kernel" % d], params["encoder_LSTM/%s/bias" % d]
+        c = torch.zeros(B, H)
+        h = torch.zeros(B, H)
+        out = [None] * T
+        order = range(T) if d == "fw" else range(T - 1, -1, -1)
+        for t in order:
+            live = (t < lengths).float().unsqueeze(-1)
+            nc, nh = lstm_cell(x[:, t], c, h, K, b)
+            mc = zmasks[(d, "c", t)] if zmasks else None
+            mh = zmasks[(d, "h", t)] if zmasks else None
+            zc = zoneout(c, nc, z, training, mc)
+            zh = zoneout(h, nh, z, training, mh)
+            c = live * zc + (1 - live) * c
+            h = live * zh + (1 - live) * h
+            out[t] = live * nh
+        outs.append(torch.stack(out, dim=1))
+    return torch.cat(outs, dim=-1)
+
+
+def prenet(x, params, hp, drop_masks=None):
+    """modules.py:240-251: dropout is ALWAYS on."""
+    for i in range(len(hp.prenet_layers)):
+        x = F.relu(x @ params["decoder_prenet/dense_%d/kernel" % (i + 1)] + params["decoder_prenet/dense_%d/bias" % (i + 1)])
+        r = hp.tacotron_dropout_rate
+        if r > 0:
+            m = drop_masks[i] if drop_masks else (torch.rand_like(x) >= r).float() / (1 - r)
+            x = x * m
+    return x
+
+
+def attention_step(query, cum, keys, values, mask, params):
+    """attention.py:169-226 + _compute_attention :10-35. query [B, D]; cum [B, T_in]; returns (context, alignments)."""
+    pq = (query @ params["attention/query_layer/kernel"]).unsqueeze(1)              # [B, 1, A]
+    kf = params["attention/location_features_convolution/kernel"]                      # [31, 1, 32]
+    f = F.conv1d(cum.unsqueeze(1), kf.permute(2, 1, 0).contiguous(), params["attention/location_features_convolution/bias"],
+                 padding=(kf.shape[0] - 1) // 2).transpose(1, 2)                       # [B, T_in, 32]
+    pl = f @ params["attention/location_features_layer/kernel"]                        # [B, T_in, A]
+    e = (params["attention/attention_variable_projection"] *
+         torch.tanh(keys + pq + pl + params["attention/attention_bias"])).sum(-1)      # [B, T_in]
+    e = torch.where(mask > 0, e, torch.full_like(e, -float("inf")))                    # _maybe_mask_score
+    a = torch.softmax(e, dim=-1)
+    ctx = torch.bmm(a.unsqueeze(1), values).squeeze(1)
+    return ctx, a
+
+
+def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks=None, stats_out=None):
+    """Training / GTA graph with teacher forcing ratio 1. inputs [B, T_in] int64; mel_targets [B, T_out, num_mels].
+    Returns dict(decoder_output, mel_outputs, stop_logits, alignments [B, T_out, T_in])."""
+    masks = masks or {}
+    B, T_in = inputs.shape
+    T_out = mel_targets.shape[1]
+    D = hp.decoder_lstm_units
+    zr = hp.tacotron_zoneout_rate
+    x = params["inputs_embedding"][inputs]
+    for i in range(hp.enc_conv_num_layers):
+        x = conv_block(x, params, "encoder_convolutions/conv_layer_%d/" % (i + 1), "relu", training,
+                       hp.tacotron_dropout_rate, masks.get(("enc_drop", i)), stats_out)
+    memory = encoder_rnn(x, input_lengths, params, hp, training, masks.get("enc_zone"))
+    mask = (torch.arange(T_in)[None, :] < input_lengths[:, None]).float()
+    values = memory * mask.unsqueeze(-1)                                     # BahdanauAttention memory masking
+    keys = values @ params["attention/memory_layer/kernel"]
+    # TacoTrainingHelper: step t consumes the go frame (t = 0) or target frame t - 1 (teacher forcing, r = 1)
+    dec_in = torch.cat([torch.zeros(B, 1, hp.num_mels), mel_targets[:, :-1, :]], dim=1)
+    pre = prenet(dec_in, params, hp, masks.get("prenet_drop"))               # [B, T_out, 256]
+    c1 = torch.zeros(B, D); h1 = torch.zeros(B, D); c2 = torch.zeros(B, D); h2 = torch.zeros(B, D)
+    ctx = torch.zeros(B, values.shape[-1])
+    cum = torch.zeros(B, T_in)
+    K1, b1 = params["decoder_LSTM/cell_1/kernel"], params["decoder_LSTM/cell_1/bias"]
+    K2, b2 = params["decoder_LSTM/cell_2/kernel"], params["decoder_LSTM/cell_2/bias"]
+    frames, stops, aligns = [], [], []
+    zm = masks.get("dec_zone")
+    for t in range(T_out):
+        nc1, nh1 = lstm_cell(torch.cat([pre[:, t], ctx], dim=-1), c1, h1, K1, b1)
+        c1n = zoneout(c1, nc1, zr, training, zm[(1, "c", t)] if zm else None)
+        h1n = zoneout(h1, nh1, zr, training, zm[(1, "h", t)] if zm else None)
+        nc2, nh2 = lstm_cell(nh1, c2, h2, K2, b2)                            # layer 2 sees the UN-zoned output
+        c2n = zoneout(c2, nc2, zr, training, zm[(2, "c", t)] if zm else None)
+        h2n = zoneout(h2, nh2, zr, training, zm[(2, "h", t)] if zm else None)
+        c1, h1, c2, h2 = c1n, h1n, c2n, h2n
+        ctx, a = attention_step(nh2, cum, keys, values, mask, params)
+        cum = cum + a                                                        # cumulative_weights
+        pin = torch.cat([nh2, ctx], dim=-1)
+        frames.append(pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"])
+        stops.append(pin @ params["stop_token_projection/kernel"] + params["stop_token_projection/bias"])
+        aligns.append(a)
+    decoder_output = torch.stack(frames, dim=1)
+    stop_logits = torch.stack(stops, dim=1).squeeze(-1)
+    if hp.clip_outputs:
+        decoder_output = torch.clamp(decoder_output, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+    y = decoder_output
+    for i in range(hp.postnet_num_layers):
+        act = "tanh" if i < hp.postnet_num_layers - 1 else None
+        y = conv_block(y, params, "postnet_convolutions/conv_layer_%d/" % (i + 1), act, training,
+                       hp.tacotron_dropout_rate, masks.get(("post_drop", i)), stats_out)
+    residual = y @ params["postnet_projection/kernel"] + params["postnet_projection/bias"]
+    mel_outputs = decoder_output + residual
+    if hp.clip_outputs:
+        mel_outputs = torch.clamp(mel_outputs, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+    return {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_logits": stop_logits,
+            "alignments": torch.stack(aligns, dim=1)}
+
+
+def loss_fn(out, mel_targets, stop_targets, params, hp):
+    """tacotron.py:315-354 with mask_decoder=False: plain means over padded tensors + L2 regulariser."""
+    before = F.mse_loss(out["decoder_output"], mel_targets)
+    after = F.mse_loss(out["mel_outputs"], mel_targets)
+    stop = F.binary_cross_entropy_with_logits(out["stop_logits"], stop_targets)
+    reg = sum((v * v).sum() / 2 for k, v in params.items() if is_regularized(k)) * hp.tacotron_reg_weight
+    return before + after + stop + reg, {"before": before, "after": after, "stop": stop, "reg": reg}
+
+
+def learning_rate(hp, global_step):
+    """tacotron.py:439-463."""
+    if not hp.tacotron_decay_learning_rate:
+        return hp.tacotron_initial_learning_rate
+    lr = hp.tacotron_initial_learning_rate * hp.tacotron_decay_rate ** (
+        (global_step - hp.tacotron_start_decay) / hp.tacotron_decay_steps)
+    return min(max(lr, hp.tacotron_final_learning_rate), hp.tacotron_initial_learning_rate)
+
+
+def train_step(params, inputs, input_lengths, mel_targets, stop_targets, hp, masks=None):
+    ps = {k: (v.clone().requires_grad_(True) if is_trainable(k) else v.clone()) for k, v in params.items()}
+    out = forward(ps, inputs, input_lengths, mel_targets, hp, True, masks)
+    loss, parts = loss_fn(out, mel_targets, stop_targets, ps, hp)
+    names = [k for k in ps if is_trainable(k)]
+    gr = torch.autograd.grad(loss, [ps[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(ps[k])) for k, g in zip(names, gr)}
+    return loss.detach(), grads, {k: v.detach() for k, v in out.items()}, {k: v.detach() for k, v in parts.items()}
+
+
+def adam_step(params, grads, state, hp, global_step):
+    """tacotron.py:393, 429-437: clip_by_global_norm(1.0) then Adam."""
+    lr = learning_rate(hp, global_step)
+    b1, b2, eps = hp.tacotron_adam_beta1, hp.tacotron_adam_beta2, hp.tacotron_adam_epsilon
+    state["t"] = state.get("t", 0) + 1
+    t = state["t"]
+    lr_t = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    if hp.tacotron_clip_gradients:
+        gn = torch.sqrt(sum((g * g).sum() for g in grads.values()))
+        scale = 1.0 / max(gn.item(), 1.0)
+        grads = {k: g * scale for k, g in grads.items()}
+    for k, g in grads.items():
+        m = state.setdefault("m", {}).setdefault(k, torch.zeros_like(g))
+        v = state.setdefault("v", {}).setdefault(k, torch.zeros_like(g))
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        params[k] = params[k] - lr_t * m / (v.sqrt() + eps)
+    return lr
