@@ -128,6 +128,47 @@ int t2_wn_ar_generate(const t2_wn_config_t* cfg, int cluster_size, const float* 
                       const float* d_u_a, const float* d_u_b, unsigned long long seed, void* d_out_samples,
                       float* d_out_raw, void* stream);
 
+
+/* ---- Tacotron-2 mel predictor: training graph (teacher forcing, outputs_per_step = 1, predict_linear = False) ----
+ * Replaces tacotron/models/tacotron.py:104-200,315-354, tacotron/models/modules.py:81-455,
+ * tacotron/models/attention.py:38-226 and Architecture_wrappers.py:169-213. Names follow hparams.py:121-176,238-283. */
+typedef struct {
+  int B, T_in, T_out;
+  int n_symbols, num_mels, embedding_dim;
+  int enc_conv_layers, enc_conv_kernel, enc_conv_channels, encoder_lstm_units;
+  int attention_dim, attention_filters, attention_kernel;
+  int prenet1, prenet2, decoder_lstm_units;
+  int postnet_layers, postnet_kernel, postnet_channels;
+  int clip_outputs;
+  float dropout_rate;        /* tacotron_dropout_rate (conv blocks in training; prenet always) */
+  float zoneout_rate;        /* tacotron_zoneout_rate */
+  float reg_weight;          /* tacotron_reg_weight */
+  float max_abs_value, lower_bound_decay;
+} t2_taco_config_t;
+
+int t2_taco_sizes(const t2_taco_config_t* cfg, long long* n_params, long long* packed_bytes, long long* workspace_bytes,
+                  int* n_tensors);
+int t2_taco_param_info(const t2_taco_config_t* cfg, int i, char* name, int name_cap, long long* offset, int* ndim,
+                       int* shape4, int* trainable);
+int t2_taco_init(const t2_taco_config_t* cfg, void* d_packed, void* d_workspace, void* stream);
+int t2_taco_pack_weights(const t2_taco_config_t* cfg, const float* d_params, void* d_packed, void* d_workspace, void* stream);
+/* forward + losses. d_inputs int32 [B,T_in] (0-padded character ids), d_input_lengths int32 [B], d_mel_targets fp32
+ * [B,T_out,num_mels] (padded with -max_abs_value), d_stop_targets fp32 [B,T_out]. d_loss fp32[4] = {before MSE, after
+ * MSE, stop-token CE, L2 regularisation}; total = sum. training=1: batch-norm batch statistics (moving stats in
+ * d_params are updated), conv dropout, stochastic zoneout. */
+int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace,
+                    const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets,
+                    const float* d_stop_targets, float* d_loss, int training, unsigned long long seed,
+                    const unsigned long long* d_step, void* stream);
+/* backward of the last t2_taco_forward(training=1): d(total loss)/d(theta) into the flat gradient buffer (non-trainable
+ * batch-norm moving statistics get 0) */
+int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                     const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets,
+                     const float* d_stop_targets, float* d_grads, unsigned long long seed,
+                     const unsigned long long* d_step, void* stream);
+int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr,
+                             long long* count, int* elem_bytes);
+
 /* ---- optimizer: tf.train.AdamOptimizer + per-tensor clip_by_norm/clip_by_value + EMA ------------------------
  * Replaces wavenet.py:586-613 (and tacotron.py:429-437 with global_norm_clip > 0).
  * d_offsets: int64 [n_tensors + 1] element offsets of the tensors inside the flat buffers.

@@ -6,3 +6,4 @@ The directory name is not a Python identifier; import it through ``t2_import.py`
 from . import lib  # noqa: F401
 from . import wavenet  # noqa: F401
 from . import audio  # noqa: F401
+from . import tacotron  # noqa: F401

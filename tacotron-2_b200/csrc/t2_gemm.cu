@@ -125,6 +125,8 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
   T2_CASE(EPI_GATE_BWD, 256)
   T2_CASE(EPI_DX, 128)
   T2_CASE(EPI_DX, 256)
+  T2_CASE(EPI_LSTM, 32)
+  T2_CASE(EPI_TOUT, 32)
 #undef T2_CASE
   return t2_set_error(T2_ERR_UNSUPPORTED_SHAPE, "act_gemm: no kernel for epilogue %d with BN=%d", epi, BN);
 }

@@ -79,6 +79,8 @@ struct EpiCtx {
   int nrows;               // valid rows among this warp's 32
   uint32_t trow;           // TMEM address of this warp's lanes, column 0
   uint8_t* wbuf;           // kEpiWarpBytes of shared memory shared by the 4 warps of this lane quarter
+  uint8_t* smem_all;       // start of the (free after the mainloop) pipeline shared memory, CTA-wide scratch
+  int m_tile;              // index of this CTA's 128-row tile
 };
 
 __device__ __forceinline__ void stage_put(uint8_t* tile, int lane, int cq, const float (&v)[32]) {
@@ -238,8 +240,9 @@ struct Epilogue<EPI_RES, BN> {
   }
 };
 
-// out = act(acc + bias).  ptr: 0 out bf16 [pos, ldo] (nullable), 1 bias fp32 (nullable), 2 out fp32
-// [pos, ldo] (nullable);  i0 = ldo, i1 = act (0 none, 1 relu), i2 = n_valid columns
+// out = dropout(act(acc + bias)).  ptr: 0 out bf16 [pos, ldo] (nullable), 1 bias fp32 (nullable), 2 out fp32
+// [pos, ldo] (nullable), 7 device u64 seed offset (nullable);  i0 = ldo, i1 = act (0 none, 1 relu, 2 tanh),
+// i2 = n_valid columns, i3 = dropout hash stream;  f1 = dropout rate (0 = off; mask = hash(seed, stream, pos*ldo + col))
 template <int BN>
 struct Epilogue<EPI_BIAS_ACT, BN> {
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
@@ -249,6 +252,10 @@ struct Epilogue<EPI_BIAS_ACT, BN> {
     float* of = static_cast<float*>(e.ptr[2]);
     const size_t row = (size_t(c.b) * c.T + c.t) * ldo;
     uint8_t* t_o = c.wbuf;
+    const float pdrop = e.f[1];
+    const float keep_inv = 1.f / (1.f - pdrop);
+    const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
+    const uint32_t hs = hash_seed(seed, uint32_t(e.i[3]));
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
       const int g0 = c.n_tile * BN + gq * 128;
@@ -268,6 +275,8 @@ struct Epilogue<EPI_BIAS_ACT, BN> {
           float v = acc[j];
           if (bias && c0 + j < nvalid) v += __ldg(bias + c0 + j);
           if (act == 1) v = fmaxf(v, 0.f);
+          else if (act == 2) v = tanhf_(v);
+          if (pdrop > 0.f) v = (hash_uniform32(hs, row + c0 + j) >= pdrop) ? v * keep_inv : 0.f;
           acc[j] = v;
         }
         if (ob && full) stage_put(t_o, c.lane, cq, acc);
@@ -574,6 +583,113 @@ struct Epilogue<EPI_DX, BN> {
   }
 };
 
+// LSTM cell on a SWAPPED GEMM: accumulator rows = gate pre-activations of 32 hidden units (tile row p: gate = p/32
+// in i,j,f,o order, unit = 32*m_tile + p%32 — the packed recurrent weight rows are permuted accordingly), columns =
+// batch items. Implements tf.nn.rnn_cell.LSTMCell (forget_bias 1) wrapped by ZoneoutLSTMCell
+// (tacotron/models/modules.py:81-142): the carried state is zoned, the OUTPUT is the un-zoned new h (:118,142).
+// ptr: 0 pre fp32 (row of batch item b = pre + b*i3; gate-major [4H]; nullable), 1 bias fp32 [4H] (nullable),
+//      2 c_prev fp32 [B][H], 3 c_out fp32 [B][H], 4 h_prev bf16 (+ b*i4), 5 h_state_out bf16 (+ b*i5),
+//      6 h_out bf16 (+ b*i6; un-zoned, zero past the sequence length), 7 gate stash bf16 [B][4H] (nullable),
+//      8 tanh(c_new) stash bf16 [B][H] (nullable), 9 lengths int32 [B] (nullable), 10 device u64 seed offset
+// i0 = H, i1 = B, i3 = pre stride, i4/i5/i6 = row strides, i7 = time step, i8 = hash stream, i9 = training
+// f0 = zoneout rate
+template <>
+struct Epilogue<EPI_LSTM, 32> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
+    const int H = e.i[0], nb = e.i[1];
+    float* ex = reinterpret_cast<float*>(c.smem_all);  // [4 gates][32 units][33]
+    const int q = c.qbar - 1;
+    if (c.cg == 0) {
+      float v[32];
+      tmem_ld32f(c.trow, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ex[(q * 32 + c.lane) * 33 + j] = v[j];
+    }
+    asm volatile("bar.sync 5, 512;\n" ::: "memory");
+    const float* pre = static_cast<const float*>(e.ptr[0]);
+    const float* bias = static_cast<const float*>(e.ptr[1]);
+    const float* c_prev = static_cast<const float*>(e.ptr[2]);
+    float* c_out = static_cast<float*>(e.ptr[3]);
+    const __nv_bfloat16* h_prev = static_cast<const __nv_bfloat16*>(e.ptr[4]);
+    __nv_bfloat16* h_state = static_cast<__nv_bfloat16*>(e.ptr[5]);
+    __nv_bfloat16* h_out = static_cast<__nv_bfloat16*>(e.ptr[6]);
+    __nv_bfloat16* gst = static_cast<__nv_bfloat16*>(e.ptr[7]);
+    __nv_bfloat16* tst = static_cast<__nv_bfloat16*>(e.ptr[8]);
+    const int* lens = static_cast<const int*>(e.ptr[9]);
+    const unsigned long long seed = e.seed + (e.ptr[10] ? *static_cast<const unsigned long long*>(e.ptr[10]) : 0ull);
+    const uint32_t hs_c = hash_seed(seed, uint32_t(e.i[8]) * 2u), hs_h = hash_seed(seed, uint32_t(e.i[8]) * 2u + 1u);
+    const float z = e.f[0];
+    const int t = e.i[7];
+    const int etid = (c.cg * 4 + q) * 32 + c.lane;
+    const int u0 = c.m_tile * 32, b0 = c.n_tile * 32;
+#pragma unroll 1
+    for (int p = etid; p < 1024; p += 512) {
+      const int bl = p >> 5, ul = p & 31;
+      const int b = b0 + bl, u = u0 + ul;
+      if (b >= nb || u >= H) continue;
+      float zi = ex[(0 * 32 + ul) * 33 + bl], zj = ex[(1 * 32 + ul) * 33 + bl];
+      float zf = ex[(2 * 32 + ul) * 33 + bl], zo = ex[(3 * 32 + ul) * 33 + bl];
+      if (pre) {
+        const float* pr = pre + size_t(b) * e.i[3];
+        zi += pr[u]; zj += pr[H + u]; zf += pr[2 * H + u]; zo += pr[3 * H + u];
+      }
+      if (bias) { zi += bias[u]; zj += bias[H + u]; zf += bias[2 * H + u]; zo += bias[3 * H + u]; }
+      float gi = sigmoidf_(zi), gj = tanhf_(zj), gf = sigmoidf_(zf + 1.f), go = sigmoidf_(zo);
+      const float cp = c_prev[size_t(b) * H + u];
+      const float hp = __bfloat162float(h_prev[size_t(b) * e.i[4] + u]);
+      const float cn = gf * cp + gi * gj;
+      const float tc = tanhf_(cn);
+      const float hn = go * tc;
+      const bool live = lens ? (t < lens[b]) : true;
+      float cs, hsv, ho = hn;
+      if (e.i[9]) {
+        const uint64_t idx = (uint64_t(t) * nb + b) * H + u;
+        cs = (z <= 0.f || hash_uniform32(hs_c, idx) >= z) ? cn : cp;
+        hsv = (z <= 0.f || hash_uniform32(hs_h, idx) >= z) ? hn : hp;
+      } else {
+        cs = (1.f - z) * cn + z * cp;
+        hsv = (1.f - z) * hn + z * hp;
+      }
+      float tcs = tc;
+      if (!live) { cs = cp; hsv = hp; ho = 0.f; gi = gj = gf = go = 0.f; tcs = 0.f; }
+      c_out[size_t(b) * H + u] = cs;
+      h_state[size_t(b) * e.i[5] + u] = __float2bfloat16(hsv);
+      h_out[size_t(b) * e.i[6] + u] = __float2bfloat16(ho);
+      if (gst) {
+        __nv_bfloat16* g = gst + size_t(b) * 4 * H;
+        g[u] = __float2bfloat16(gi); g[H + u] = __float2bfloat16(gj);
+        g[2 * H + u] = __float2bfloat16(gf); g[3 * H + u] = __float2bfloat16(go);
+      }
+      if (tst) tst[size_t(b) * H + u] = __float2bfloat16(tcs);
+    }
+  }
+};
+
+// transposed fp32 output of a swapped GEMM: accumulator rows = features k, columns = batch items b.
+// rows [0, i0) -> ptr0[b*i1 + k], rows [i0, i3) -> ptr1[b*i4 + (k - i0)]; i2 / i5 = 1: accumulate (+=); i6 = B
+template <>
+struct Epilogue<EPI_TOUT, 32> {
+  static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
+    if (c.cg != 0) return;
+    const int k = c.t, nb = e.i[6];
+    float v[32];
+    tmem_ld32f(c.trow, v);
+    float* dst; int ld, acc, kk;
+    if (k < e.i[0]) { dst = static_cast<float*>(e.ptr[0]); ld = e.i[1]; acc = e.i[2]; kk = k; }
+    else if (k < e.i[3]) { dst = static_cast<float*>(e.ptr[1]); ld = e.i[4]; acc = e.i[5]; kk = k - e.i[0]; }
+    else return;
+    if (!dst) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int b = c.n_tile * 32 + j;
+      if (b < nb) {
+        float* d = dst + size_t(b) * ld + kk;
+        *d = acc ? *d + v[j] : v[j];
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // act_gemm kernel
 // ------------------------------------------------------------------------------------------------
@@ -689,6 +805,8 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     c.row0 = size_t(b) * g.T + tw;
     c.nrows = g.T - tw < 0 ? 0 : (g.T - tw > 32 ? 32 : g.T - tw);
     c.wbuf = smem + q * kEpiWarpBytes;
+    c.smem_all = smem;
+    c.m_tile = m_tile;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     c.trow = tmem_base + (uint32_t(q * 32) << 16);

@@ -20,9 +20,9 @@ struct Seg {
 };
 
 struct EpiArgs {
-  void* ptr[8];
-  float f[4];
-  int i[6];
+  void* ptr[12];
+  float f[6];
+  int i[12];
   unsigned long long seed;
 };
 
@@ -48,6 +48,8 @@ enum EpiKind {
   EPI_SCALE_RELUMASK = 5,
   EPI_GATE_BWD = 6,
   EPI_DX = 7,
+  EPI_LSTM = 8,   // swapped GEMM (rows = gate units, cols = batch) + LSTM cell + zoneout
+  EPI_TOUT = 9,   // swapped GEMM, transposed fp32 output (rows = features, cols = batch)
 };
 
 

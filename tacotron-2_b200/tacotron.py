@@ -1,0 +1,146 @@
+"""Host side of the B200 Tacotron-2 mel predictor (training graph). Mirrors tacotron/models/tacotron.py: the
+reference's ``initialize`` + ``add_loss`` + ``add_optimizer`` become ``forward`` / ``backward`` / ``optimizer_step``."""
+import ctypes
+import math
+
+import torch
+
+from . import lib as L
+
+N_SYMBOLS = 66
+
+
+class TacoConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "B", "T_in", "T_out", "n_symbols", "num_mels", "embedding_dim", "enc_conv_layers", "enc_conv_kernel",
+        "enc_conv_channels", "encoder_lstm_units", "attention_dim", "attention_filters", "attention_kernel", "prenet1",
+        "prenet2", "decoder_lstm_units", "postnet_layers", "postnet_kernel", "postnet_channels", "clip_outputs")] + [
+        (n, ctypes.c_float) for n in ("dropout_rate", "zoneout_rate", "reg_weight", "max_abs_value", "lower_bound_decay")]
+
+
+def make_config(hp, B, T_in, T_out):
+    if hp.outputs_per_step != 1 or hp.predict_linear or hp.mask_decoder or len(hp.prenet_layers) != 2 or hp.decoder_layers != 2:
+        raise L.T2Error("B200 Tacotron path covers outputs_per_step=1, predict_linear=False, mask_decoder=False, "
+                        "2 prenet layers, 2 decoder LSTM layers")
+    c = TacoConfig()
+    c.B, c.T_in, c.T_out = B, T_in, T_out
+    c.n_symbols, c.num_mels, c.embedding_dim = N_SYMBOLS, hp.num_mels, hp.embedding_dim
+    c.enc_conv_layers, c.enc_conv_kernel, c.enc_conv_channels = hp.enc_conv_num_layers, hp.enc_conv_kernel_size[0], hp.enc_conv_channels
+    c.encoder_lstm_units = hp.encoder_lstm_units
+    c.attention_dim, c.attention_filters, c.attention_kernel = hp.attention_dim, hp.attention_filters, hp.attention_kernel[0]
+    c.prenet1, c.prenet2 = hp.prenet_layers
+    c.decoder_lstm_units = hp.decoder_lstm_units
+    c.postnet_layers, c.postnet_kernel, c.postnet_channels = hp.postnet_num_layers, hp.postnet_kernel_size[0], hp.postnet_channels
+    c.clip_outputs = int(hp.clip_outputs)
+    c.dropout_rate, c.zoneout_rate, c.reg_weight = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate, hp.tacotron_reg_weight
+    c.max_abs_value, c.lower_bound_decay = hp.max_abs_value, hp.lower_bound_decay
+    return c
+
+
+class Tacotron(object):
+    def __init__(self, hparams, B, T_in, T_out, device="cuda"):
+        self.hp = hparams
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.cfg = make_config(hparams, B, T_in, T_out)
+        n, pb, wb, nt = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
+        L.check(self.lib.t2_taco_sizes(ctypes.byref(self.cfg), ctypes.byref(n), ctypes.byref(pb), ctypes.byref(wb), ctypes.byref(nt)))
+        self.n_params = n.value
+        self.params = torch.zeros(n.value, dtype=torch.float32, device=self.device)
+        self.packed = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
+        self.workspace = torch.empty(wb.value, dtype=torch.uint8, device=self.device)
+        self.loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.grads = self.m = self.v = None
+        self.tensors = []
+        name = ctypes.create_string_buffer(160)
+        off, nd, shp, tr = ctypes.c_longlong(), ctypes.c_int(), (ctypes.c_int * 4)(), ctypes.c_int()
+        for i in range(nt.value):
+            L.check(self.lib.t2_taco_param_info(ctypes.byref(self.cfg), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp, ctypes.byref(tr)))
+            self.tensors.append((name.value.decode(), off.value, tuple(shp[k] for k in range(nd.value)), bool(tr.value)))
+        self.offsets = torch.tensor([t[1] for t in self.tensors] + [n.value], dtype=torch.int64, device=self.device)
+        self.opt_scratch = torch.zeros(len(self.tensors) + 2, dtype=torch.float32, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.global_step = 0
+        self.seed = int(hparams.tacotron_random_seed)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.t2_taco_init(ctypes.byref(self.cfg), L.ptr(self.packed), L.ptr(self.workspace), L.stream_ptr()))
+        self._dirty = True
+
+    def load_params(self, params):
+        flat = torch.zeros(self.n_params, dtype=torch.float32)
+        for name, off, shape, _ in self.tensors:
+            flat[off:off + int(math.prod(shape))] = params[name].detach().float().reshape(-1)
+        self.params.copy_(flat.to(self.device))
+        self._dirty = True
+
+    def unflatten(self, flat, trainable_only=False):
+        flat = flat.detach().float().cpu()
+        return {n: flat[o:o + int(math.prod(s))].reshape(s).clone() for n, o, s, tr in self.tensors if tr or not trainable_only}
+
+    def export_params(self):
+        return self.unflatten(self.params)
+
+    def export_grads(self):
+        return self.unflatten(self.grads, trainable_only=True)
+
+    def pack(self):
+        L.check(self.lib.t2_taco_pack_weights(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace), L.stream_ptr()))
+        self._dirty = False
+
+    def forward(self, inputs, input_lengths, mel_targets, stop_targets, training=True, seed=None):
+        if self._dirty:
+            self.pack()
+        self._last = (inputs, input_lengths, mel_targets, stop_targets)
+        self._last_seed = self.seed if seed is None else seed
+        L.check(self.lib.t2_taco_forward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace),
+                                         L.ptr(inputs), L.ptr(input_lengths), L.ptr(mel_targets), L.ptr(stop_targets),
+                                         L.ptr(self.loss_buf), int(training), ctypes.c_ulonglong(self._last_seed),
+                                         L.ptr(self.step_dev), L.stream_ptr()))
+        return self.loss_buf
+
+    def backward(self):
+        if self.grads is None:
+            self.grads = torch.zeros_like(self.params)
+        inputs, input_lengths, mel_targets, stop_targets = self._last
+        L.check(self.lib.t2_taco_backward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace),
+                                          L.ptr(inputs), L.ptr(input_lengths), L.ptr(mel_targets), L.ptr(stop_targets),
+                                          L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed), L.ptr(self.step_dev),
+                                          L.stream_ptr()))
+        return self.grads
+
+    def learning_rate(self):
+        hp = self.hp
+        if not hp.tacotron_decay_learning_rate:
+            return hp.tacotron_initial_learning_rate
+        lr = hp.tacotron_initial_learning_rate * hp.tacotron_decay_rate ** (
+            (self.global_step - hp.tacotron_start_decay) / hp.tacotron_decay_steps)
+        return min(max(lr, hp.tacotron_final_learning_rate), hp.tacotron_initial_learning_rate)
+
+    def optimizer_step(self, grad_scale=1.0):
+        """clip_by_global_norm(1.0) + Adam (tacotron.py:393,429-437) on the flat buffers."""
+        hp = self.hp
+        if self.m is None:
+            self.m = torch.zeros_like(self.params)
+            self.v = torch.zeros_like(self.params)
+        lr = self.learning_rate()
+        L.check(self.lib.t2_adam_step(
+            L.ptr(self.params), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v), L.ptr(None), L.ptr(self.offsets),
+            len(self.tensors), ctypes.c_longlong(self.n_params), ctypes.c_float(lr), ctypes.c_float(hp.tacotron_adam_beta1),
+            ctypes.c_float(hp.tacotron_adam_beta2), ctypes.c_float(hp.tacotron_adam_epsilon), self.global_step + 1,
+            ctypes.c_float(grad_scale), ctypes.c_float(0.0), ctypes.c_float(0.0),
+            ctypes.c_float(1.0 if hp.tacotron_clip_gradients else 0.0), ctypes.c_float(0.0), L.ptr(self.opt_scratch), L.stream_ptr()))
+        self.global_step += 1
+        self._dirty = True
+        return lr
+
+    def workspace_tensor(self, name, shape=None):
+        p, cnt, eb = ctypes.c_void_p(), ctypes.c_longlong(), ctypes.c_int()
+        L.check(self.lib.t2_taco_workspace_tensor(ctypes.byref(self.cfg), L.ptr(self.workspace), name.encode(), ctypes.byref(p),
+                                                  ctypes.byref(cnt), ctypes.byref(eb)))
+        off = p.value - self.workspace.data_ptr()
+        t = self.workspace[off:off + cnt.value * eb.value].view(torch.bfloat16 if eb.value == 2 else torch.float32)
+        return t.reshape(shape) if shape is not None else t
+
+    def losses(self):
+        b, a, s, r = self.loss_buf.tolist()
+        return {"before": b, "after": a, "stop": s, "reg": r, "total": b + a + s + r}
