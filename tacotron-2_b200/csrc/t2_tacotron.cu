@@ -62,7 +62,7 @@ struct TL {  // layout
   long long w_dmel, w_dY, w_ddec_tm, w_dPI, w_dh1ext, w_dh2ext, w_dhs1, w_dhs2, w_dcs1, w_dcs2, w_dg1, w_dg2, w_dgstep;
   long long w_dctxl, w_dctx_all, w_dq_all, w_dcum, w_cumrun, w_dkeys, w_dvalues, w_attacc, w_dpn2, w_dpn1;
   long long w_dencpre[2], w_dx3, w_encdh[2], w_encdc[2], w_encdg, w_demb, w_tiles, w_packjobs, w_regtab;
-  long long w_ddecf, w_encdgall[2], w_dkeysb, w_dz;
+  long long w_ddecf, w_encdgall[2], w_dkeysb, w_dz, w_attU;
   std::vector<int> tile_off, tile_cnt;  // per wgrad launch (fixed order, see build_tiles)
   long long workspace_bytes;
   int n_packjobs, n_reg;
@@ -246,7 +246,8 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   lo.w_dcum = takeb(B * Ti * 4); lo.w_cumrun = takeb(B * Ti * 4);
   lo.w_dkeys = takeb(B * Ti * lo.A * 4);
   lo.w_dvalues = takeb(B * Ti * 2 * lo.H * 4);
-  lo.w_attacc = takeb(B * (lo.F * lo.A + lo.KA * lo.F + lo.F + 2 * lo.A) * 4);
+  lo.w_attacc = takeb(B * (lo.KA + 2) * lo.A * 4);
+  lo.w_attU = takeb((2 * lo.KA + 4) * lo.A * 4);
   lo.w_dpn2 = takeb(To * B * lo.P2 * 2); lo.w_dpn1 = takeb(To * B * lo.P1 * 2);
   for (int d = 0; d < 2; ++d) {
     lo.w_dencpre[d] = takeb(B * Ti * 4 * lo.H * 2);       // bf16 gate grads [B][Ti][4H] (batch-major, = dpre)
@@ -405,87 +406,145 @@ __global__ void decin_kernel(const float* __restrict__ tgt, bf16* __restrict__ o
 }
 
 // ---- location-sensitive attention, one CTA per batch item per decoder step (attention.py:169-226) -------------
+// The location branch conv1d(k=31, 1 -> F) followed by dense(F -> A) is linear in the cumulative alignments, so it is
+// evaluated as ONE 31-tap filter bank U[k][a] = sum_f K[k][f] Wl[f][a] with offset u0[a] = sum_f bK[f] Wl[f][a] + b_a[a]
+// (built once per forward by att_prep_kernel); the backward pass differentiates through the same factorisation.
+constexpr int kAttThreads = 512;
+__global__ void att_prep_kernel(const float* __restrict__ K, const float* __restrict__ bK, const float* __restrict__ Wl,
+                                const float* __restrict__ ba, float* __restrict__ U, int KA, int F, int A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (KA + 1) * A) return;
+  const int k = i / A, a = i % A;
+  float acc = 0.f;
+  if (k < KA) { for (int f = 0; f < F; ++f) acc += K[k * F + f] * Wl[f * A + a]; }
+  else { acc = ba[a]; for (int f = 0; f < F; ++f) acc += bK[f] * Wl[f * A + a]; }
+  U[i] = acc;   // rows 0..KA-1: U, row KA: u0
+}
 struct AttArgs {
   const bf16* h2out; int ld_h2;            // query source: PI_all[t][b][0:D]
-  const bf16* WqT;                          // [A][D]
-  const float* K; const float* bK; const float* Wl; const float* v; const float* ba;
+  const bf16* WqT;                          // [A][D] bf16
+  const float* U;                           // [KA + 1][A]
+  const float* v;
   const float* keys;                        // [B][Ti][A] fp32
-  const bf16* values;                       // [B][Ti][2H]
+  const bf16* values;                       // [B][Ti][C2]
   const int* lens;
   float* cum;                               // [B][Ti] running cumulative alignments (in/out)
   float* alpha;                             // [B][Ti] output for this step
-  bf16* ctx_a; int ld_a;                    // context -> S1_all[t+1][b][0:2H]
+  bf16* ctx_a; int ld_a;                    // context -> S1_all[t+1][b][0:C2]
   bf16* ctx_b; int ld_b;                    // context -> PI_all[t][b][D:]
-  int B, Ti, D, A, F, KA, C2;
+  int B, Ti, D, A, KA, C2;
 };
-__global__ void __launch_bounds__(256) att_fwd_kernel(AttArgs a) {
-  extern __shared__ float sm[];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* cum = sm;                     // [Ti]
-  float* q = cum + a.Ti;               // [A]
-  float* locf = q + a.A;               // [Ti][F]
-  float* e = locf + a.Ti * a.F;        // [Ti]
-  float* red = e + a.Ti;               // [32]
-  for (int j = tid; j < a.Ti; j += 256) cum[j] = a.cum[(long long)b * a.Ti + j];
-  // q = h2out . Wq
-  const bf16* h = a.h2out + (long long)b * a.ld_h2;
-  for (int o = warp; o < a.A; o += 8) {
+// q[a] = sum_k h[k] WqT[a][k]: 4 threads per output, 8-wide bf16 loads
+__device__ __forceinline__ void att_query(const bf16* __restrict__ WqT, const float* __restrict__ hs, float* __restrict__ q, int A, int D) {
+  for (int o = threadIdx.x >> 2; o < A; o += kAttThreads >> 2) {
+    const int part = threadIdx.x & 3;
+    const int kq = D >> 2;
+    const uint4* w = reinterpret_cast<const uint4*>(WqT + (long long)o * D + part * kq);
+    const float* h = hs + part * kq;
     float acc = 0.f;
-    const bf16* w = a.WqT + (long long)o * a.D;
-    for (int k = lane; k < a.D; k += 32) acc += __bfloat162float(w[k]) * __bfloat162float(h[k]);
-    acc = warp_sum(acc);
-    if (lane == 0) q[o] = acc;
+    for (int c = 0; c < (kq >> 3); ++c) {
+      const uint4 u = __ldg(w + c);
+      const float* hh = h + c * 8;
+      acc += bf16lo(u.x) * hh[0] + bf16hi(u.x) * hh[1] + bf16lo(u.y) * hh[2] + bf16hi(u.y) * hh[3] + bf16lo(u.z) * hh[4] +
+             bf16hi(u.z) * hh[5] + bf16lo(u.w) * hh[6] + bf16hi(u.w) * hh[7];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (part == 0) q[o] = acc;
   }
+}
+__global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Ti = a.Ti, A = a.A, half = a.KA / 2;
+  const int Tip = (Ti + 3) & ~3, cumlen = (Ti + 2 * half + 5) & ~3;
+  float* U = sm;                        // [(KA+1)][A]
+  float* cum = U + (a.KA + 1) * A;      // [Ti + 2*half] zero-padded halo
+  float* q = cum + cumlen;              // [A]
+  float* e = q + A;                     // [Ti]
+  float* hs = e + Tip;                  // [D] query source as fp32
+  float* part = hs + a.D;               // [8][C2] context partials
+  float* red = part + 8 * a.C2;         // [32]
+  for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) U[i] = a.U[i];
+  for (int i = tid; i < Ti + 2 * half; i += kAttThreads) {
+    const int j = i - half;
+    cum[i] = (j >= 0 && j < Ti) ? a.cum[(long long)b * Ti + j] : 0.f;
+  }
+  for (int i = tid; i < a.D; i += kAttThreads) hs[i] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
   __syncthreads();
-  const int half = a.KA / 2;
-  for (int i = tid; i < a.Ti * a.F; i += 256) {
-    const int j = i / a.F, f = i % a.F;
-    float acc = a.bK[f];
-    for (int k = 0; k < a.KA; ++k) { const int jj = j + k - half; if (jj >= 0 && jj < a.Ti) acc += a.K[k * a.F + f] * cum[jj]; }
-    locf[i] = acc;
-  }
+  att_query(a.WqT, hs, q, A, a.D);
   __syncthreads();
   const int len = a.lens[b];
-  for (int j = warp; j < a.Ti; j += 8) {
+  const int nq = A >> 2;   // float4 groups per row (<= 32)
+  for (int j = warp; j < Ti; j += kAttThreads / 32) {
     float acc = 0.f;
-    for (int c = lane; c < a.A; c += 32) {
-      float pl = 0.f;
-      for (int f = 0; f < a.F; ++f) pl += locf[j * a.F + f] * a.Wl[f * a.A + c];
-      acc += a.v[c] * tanhf(a.keys[((long long)b * a.Ti + j) * a.A + c] + q[c] + pl + a.ba[c]);
+    if (lane < nq && j < len) {
+      const int c = lane * 4;
+      float4 pl = *reinterpret_cast<const float4*>(U + a.KA * A + c);   // u0
+      for (int k = 0; k < a.KA; ++k) {
+        const float cj = cum[j + k];
+        const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
+        pl.x += cj * u.x; pl.y += cj * u.y; pl.z += cj * u.z; pl.w += cj * u.w;
+      }
+      const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j) * A + c));
+      const float4 qq = *reinterpret_cast<const float4*>(q + c);
+      const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
+      acc = vv.x * tanhf_(ky.x + qq.x + pl.x) + vv.y * tanhf_(ky.y + qq.y + pl.y) + vv.z * tanhf_(ky.z + qq.z + pl.z) +
+            vv.w * tanhf_(ky.w + qq.w + pl.w);
     }
     acc = warp_sum(acc);
     if (lane == 0) e[j] = j < len ? acc : -INFINITY;
   }
   __syncthreads();
   float mx = -INFINITY;
-  for (int j = tid; j < a.Ti; j += 256) mx = fmaxf(mx, e[j]);
+  for (int j = tid; j < Ti; j += kAttThreads) mx = fmaxf(mx, e[j]);
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
   mx = red[0];
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  for (int w = 1; w < kAttThreads / 32; ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float s = 0.f;
-  for (int j = tid; j < a.Ti; j += 256) { const float p = j < len ? __expf(e[j] - mx) : 0.f; e[j] = p; s += p; }
+  for (int j = tid; j < Ti; j += kAttThreads) { const float p = j < len ? __expf(e[j] - mx) : 0.f; e[j] = p; s += p; }
   s = warp_sum(s);
   if (lane == 0) red[warp] = s;
   __syncthreads();
   s = 0.f;
-  for (int w = 0; w < 8; ++w) s += red[w];
+  for (int w = 0; w < kAttThreads / 32; ++w) s += red[w];
   const float inv = 1.f / s;
-  for (int j = tid; j < a.Ti; j += 256) {
+  for (int j = tid; j < Ti; j += kAttThreads) {
     const float al = e[j] * inv;
     e[j] = al;
-    a.alpha[(long long)b * a.Ti + j] = al;
-    a.cum[(long long)b * a.Ti + j] = cum[j] + al;
+    a.alpha[(long long)b * Ti + j] = al;
+    a.cum[(long long)b * Ti + j] = cum[j + half] + al;
   }
   __syncthreads();
-  for (int c = tid; c < a.C2; c += 256) {
+  // context = alpha . values: 8 row groups x (C2/8) column chunks of 8 channels
+  {
+    const int nch = a.C2 >> 3;                 // uint4 chunks per row
+    const int rg = tid / nch, ch = tid % nch;  // kAttThreads >= 8 * nch for C2 <= 512
+    if (rg < 8) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int j = rg; j < len; j += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.values + ((long long)b * Ti + j) * a.C2) + ch);
+        const float al = e[j];
+        acc[0] += al * bf16lo(u.x); acc[1] += al * bf16hi(u.x); acc[2] += al * bf16lo(u.y); acc[3] += al * bf16hi(u.y);
+        acc[4] += al * bf16lo(u.z); acc[5] += al * bf16hi(u.z); acc[6] += al * bf16lo(u.w); acc[7] += al * bf16hi(u.w);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part[rg * a.C2 + ch * 8 + i] = acc[i];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C2; c += kAttThreads) {
     float acc = 0.f;
-    for (int j = 0; j < len; ++j) acc += e[j] * __bfloat162float(a.values[((long long)b * a.Ti + j) * a.C2 + c]);
-    const bf16 r = __float2bfloat16(acc);
-    if (a.ctx_a) a.ctx_a[(long long)b * a.ld_a + c] = r;
-    a.ctx_b[(long long)b * a.ld_b + c] = r;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc += part[r * a.C2 + c];
+    const bf16 r16 = __float2bfloat16(acc);
+    if (a.ctx_a) a.ctx_a[(long long)b * a.ld_a + c] = r16;
+    a.ctx_b[(long long)b * a.ld_b + c] = r16;
   }
 }
 
@@ -775,7 +834,7 @@ int lstm_bwd_gemm(const StepCtx& s, const void* wT, int K, int H4, const void* d
 // ---- attention backward, one CTA per batch item per step ----------------------------------------------------------
 struct AttBwd {
   const bf16* h2out; int ld_h2; const bf16* WqT; const float* Wq;   // Wq fp32 [D][A]
-  const float* K; const float* bK; const float* Wl; const float* v; const float* ba;
+  const float* U; const float* v;
   const float* keys; const bf16* values; const int* lens;
   const float* alpha;      // [B][Ti] of this step
   float* cumrun;           // [B][Ti]: cum_t on entry, cum_{t-1} on exit
@@ -786,153 +845,195 @@ struct AttBwd {
   bf16* dctx_save;         // [B][C2]
   bf16* dq_save;           // [B][A]
   float* dkeys;            // [B][Ti][A] accumulated
-  float* acc;              // per item: dWl [F][A] | dK [KA][F] | dbK [F] | dv [A] | dba [A]
-  int B, Ti, D, A, F, KA, C2;
+  float* acc;              // per item: dU [(KA+1)][A] (row KA = d u0) | dv [A]
+  int B, Ti, D, A, KA, C2;
 };
-__global__ void __launch_bounds__(256) att_bwd_kernel(AttBwd a) {
-  extern __shared__ float sm[];
+__global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Ti = a.Ti, A = a.A, F = a.F, half = a.KA / 2;
-  float* cump = sm;                 // [Ti]
-  float* al = cump + Ti;            // [Ti]
-  float* q = al + Ti;               // [A]
-  float* locf = q + A;              // [Ti][F]
-  float* dlocf = locf + Ti * F;     // [Ti][F]
-  float* de = dlocf + Ti * F;       // [Ti]
-  float* dq = de + Ti;              // [A]
-  float* dctx = dq + A;             // [C2]
-  float* dEs = dctx + a.C2;         // [Ti][A]
-  float* red = dEs + Ti * A;        // [32]
+  const int Ti = a.Ti, A = a.A, half = a.KA / 2, NW = kAttThreads / 32;
+  const int Tip = (Ti + 3) & ~3, cumlen = (Ti + 2 * half + 5) & ~3;
+  float* U = sm;                          // [(KA+1)][A]
+  float* cum = U + (a.KA + 1) * A;        // [Ti + 2*half] cum_{t-1}, zero-padded
+  float* q = cum + cumlen;                // [A]
+  float* al = q + A;                      // [Ti]
+  float* de = al + Tip;                   // [Ti]
+  float* hs = de + Tip;                   // [D]
+  float* dctx = hs + a.D;                 // [C2]
+  float* dq = dctx + a.C2;                // [A]
+  float* dv = dq + A;                     // [A]
+  float* dE = dv + A;                     // [Ti + 2*half][A], rows shifted by `half`, zero halo
+  float* red = dE + (Ti + 2 * half) * A;  // [32]
   const int len = a.lens[b];
-  for (int j = tid; j < Ti; j += 256) {
-    const float aj = a.alpha[(long long)b * Ti + j];
-    al[j] = aj;
-    const float cp = a.cumrun[(long long)b * Ti + j] - aj;
-    cump[j] = cp;
-    a.cumrun[(long long)b * Ti + j] = cp;
+  for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) U[i] = a.U[i];
+  for (int i = tid; i < Ti + 2 * half; i += kAttThreads) {
+    const int j = i - half;
+    float cp = 0.f;
+    if (j >= 0 && j < Ti) {
+      const float aj = a.alpha[(long long)b * Ti + j];
+      al[j] = aj;
+      cp = a.cumrun[(long long)b * Ti + j] - aj;
+      a.cumrun[(long long)b * Ti + j] = cp;
+    }
+    cum[i] = cp;
   }
-  for (int c = tid; c < a.C2; c += 256) {
+  for (int i = tid; i < a.D; i += kAttThreads) hs[i] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
+  for (int c = tid; c < a.C2; c += kAttThreads) {
     const float g = a.dPI[(long long)b * a.ld_dPI + a.D + c] + a.dctxl[(long long)b * a.C2 + c];
     dctx[c] = g;
     a.dctx_save[(long long)b * a.C2 + c] = __float2bfloat16(g);
   }
-  const bf16* h = a.h2out + (long long)b * a.ld_h2;
-  for (int o = warp; o < A; o += 8) {
-    float acc = 0.f;
-    const bf16* w = a.WqT + (long long)o * a.D;
-    for (int k = lane; k < a.D; k += 32) acc += __bfloat162float(w[k]) * __bfloat162float(h[k]);
-    acc = warp_sum(acc);
-    if (lane == 0) q[o] = acc;
+  for (int i = tid; i < A; i += kAttThreads) { dq[i] = 0.f; dv[i] = 0.f; }
+  for (int i = tid; i < 2 * half * A; i += kAttThreads) {   // zero halo rows of dE
+    const int r = i / A, c = i % A;
+    dE[(r < half ? r : Ti + r) * A + c] = 0.f;
   }
   __syncthreads();
-  for (int i = tid; i < Ti * F; i += 256) {
-    const int j = i / F, f = i % F;
-    float acc = a.bK[f];
-    for (int k = 0; k < a.KA; ++k) { const int jj = j + k - half; if (jj >= 0 && jj < Ti) acc += a.K[k * F + f] * cump[jj]; }
-    locf[i] = acc;
-  }
-  // d alpha and softmax backward
+  att_query(a.WqT, hs, q, A, a.D);
+  // d alpha[j] = dctx . values[j] + dcum[j] : one warp per row, 8-wide bf16 loads
   float part = 0.f;
-  for (int j = warp; j < Ti; j += 8) {
+  for (int j = warp; j < Ti; j += NW) {
     float acc = 0.f;
-    if (j < len)
-      for (int c = lane; c < a.C2; c += 32) acc += dctx[c] * __bfloat162float(a.values[((long long)b * Ti + j) * a.C2 + c]);
+    if (j < len) {
+      const uint4* vr = reinterpret_cast<const uint4*>(a.values + ((long long)b * Ti + j) * a.C2);
+      for (int ch = lane; ch < (a.C2 >> 3); ch += 32) {
+        const uint4 u = __ldg(vr + ch);
+        const float* d = dctx + ch * 8;
+        acc += d[0] * bf16lo(u.x) + d[1] * bf16hi(u.x) + d[2] * bf16lo(u.y) + d[3] * bf16hi(u.y) + d[4] * bf16lo(u.z) + d[5] * bf16hi(u.z) +
+               d[6] * bf16lo(u.w) + d[7] * bf16hi(u.w);
+      }
+    }
     acc = warp_sum(acc);
     if (lane == 0) {
       const float da = j < len ? acc + a.dcum[(long long)b * Ti + j] : 0.f;
-      de[j] = da;                      // holds d alpha for now
+      de[j] = da;
       part += al[j] * da;
     }
   }
   if (lane == 0) red[warp] = part;
   __syncthreads();
   float dot = 0.f;
-  for (int w = 0; w < 8; ++w) dot += red[w];
+  for (int w = 0; w < NW; ++w) dot += red[w];
   __syncthreads();
-  for (int j = tid; j < Ti; j += 256) de[j] = al[j] * (de[j] - dot);
+  for (int j = tid; j < Ti; j += kAttThreads) de[j] = al[j] * (de[j] - dot);
   __syncthreads();
-  // energies backward: thread = (attention channel c, row parity)
+  // energies backward: warp per row, lane = 4 channels
   {
-    const int c = tid % A, jp = tid / A, np = 256 / A;   // A = 128 -> 2 row groups
-    float dv = 0.f, dqa = 0.f;
-    float dwl[32];
-#pragma unroll
-    for (int f = 0; f < 32; ++f) dwl[f] = 0.f;
-    const float vc = a.v[c], bac = a.ba[c], qc = q[c];
-    for (int j = jp; j < Ti; j += np) {
-      float dE = 0.f;
-      if (j < len) {
-        float pl = 0.f;
-        for (int f = 0; f < F; ++f) pl += locf[j * F + f] * a.Wl[f * A + c];
-        const float th = tanhf(a.keys[((long long)b * Ti + j) * A + c] + qc + pl + bac);
-        dE = de[j] * vc * (1.f - th * th);
-        dv += de[j] * th;
-        dqa += dE;
-        a.dkeys[((long long)b * Ti + j) * A + c] += dE;
-        for (int f = 0; f < F; ++f) dwl[f] += locf[j * F + f] * dE;
+    const int nq = A >> 2;
+    float4 sdq = make_float4(0, 0, 0, 0), sdv = make_float4(0, 0, 0, 0);
+    for (int j = warp; j < Ti; j += NW) {
+      if (lane < nq) {
+        const int c = lane * 4;
+        float4 d4 = make_float4(0, 0, 0, 0);
+        if (j < len) {
+          float4 pl = *reinterpret_cast<const float4*>(U + a.KA * A + c);
+          for (int k = 0; k < a.KA; ++k) {
+            const float cj = cum[j + k];
+            const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
+            pl.x += cj * u.x; pl.y += cj * u.y; pl.z += cj * u.z; pl.w += cj * u.w;
+          }
+          float4* kp = reinterpret_cast<float4*>(a.dkeys + ((long long)b * Ti + j) * A + c);
+          const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j) * A + c));
+          const float4 qq = *reinterpret_cast<const float4*>(q + c);
+          const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
+          const float dej = de[j];
+          const float t0 = tanhf_(ky.x + qq.x + pl.x), t1 = tanhf_(ky.y + qq.y + pl.y), t2 = tanhf_(ky.z + qq.z + pl.z),
+                      t3 = tanhf_(ky.w + qq.w + pl.w);
+          d4.x = dej * vv.x * (1.f - t0 * t0); d4.y = dej * vv.y * (1.f - t1 * t1);
+          d4.z = dej * vv.z * (1.f - t2 * t2); d4.w = dej * vv.w * (1.f - t3 * t3);
+          sdv.x += dej * t0; sdv.y += dej * t1; sdv.z += dej * t2; sdv.w += dej * t3;
+          sdq.x += d4.x; sdq.y += d4.y; sdq.z += d4.z; sdq.w += d4.w;
+          float4 kk = *kp;
+          kk.x += d4.x; kk.y += d4.y; kk.z += d4.z; kk.w += d4.w;
+          *kp = kk;
+        }
+        *reinterpret_cast<float4*>(dE + (j + half) * A + c) = d4;
       }
-      dEs[j * A + c] = dE;
     }
-    // combine the row groups through shared memory (dq) and global per-item accumulators
-    float* accp = a.acc + (long long)b * (F * A + a.KA * F + F + 2 * A);
-    if (jp == 0) dq[c] = 0.f;
-    __syncthreads();
-    atomicAdd(&dq[c], dqa);
-    for (int f = 0; f < F; ++f) atomicAdd(accp + f * A + c, dwl[f]);
-    atomicAdd(accp + F * A + a.KA * F + F + c, dv);
-    atomicAdd(accp + F * A + a.KA * F + F + A + c, dqa);
+    if (lane < nq) {
+      const int c = lane * 4;
+      atomicAdd(&dq[c], sdq.x); atomicAdd(&dq[c + 1], sdq.y); atomicAdd(&dq[c + 2], sdq.z); atomicAdd(&dq[c + 3], sdq.w);
+      atomicAdd(&dv[c], sdv.x); atomicAdd(&dv[c + 1], sdv.y); atomicAdd(&dv[c + 2], sdv.z); atomicAdd(&dv[c + 3], sdv.w);
+    }
   }
   __syncthreads();
-  for (int c = tid; c < A; c += 256) a.dq_save[(long long)b * A + c] = __float2bfloat16(dq[c]);
-  for (int i = tid; i < Ti * F; i += 256) {
-    const int j = i / F, f = i % F;
+  float* accp = a.acc + (long long)b * ((a.KA + 2) * A);
+  for (int c = tid; c < A; c += kAttThreads) {
+    a.dq_save[(long long)b * A + c] = __float2bfloat16(dq[c]);
+    accp[a.KA * A + c] += dq[c];          // d u0 (also the gradient of attention_bias)
+    accp[(a.KA + 1) * A + c] += dv[c];
+  }
+  // dU[k][a] += sum_j cum_{t-1}[j + k - half] dE[j][a]
+  for (int i = tid; i < a.KA * A; i += kAttThreads) {
+    const int k = i / A, c = i % A;
     float acc = 0.f;
-    for (int c = 0; c < A; ++c) acc += dEs[j * A + c] * a.Wl[f * A + c];
-    dlocf[i] = acc;
+    for (int j = 0; j < len; ++j) acc += cum[j + k] * dE[(j + half) * A + c];
+    accp[i] += acc;
   }
-  __syncthreads();
-  {
-    float* accp = a.acc + (long long)b * (F * A + a.KA * F + F + 2 * A) + F * A;
-    for (int i = tid; i < a.KA * F + F; i += 256) {
-      float acc = 0.f;
-      if (i < a.KA * F) {
-        const int k = i / F, f = i % F;
-        for (int j = 0; j < Ti; ++j) { const int jj = j + k - half; if (jj >= 0 && jj < Ti) acc += dlocf[j * F + f] * cump[jj]; }
-      } else {
-        const int f = i - a.KA * F;
-        for (int j = 0; j < Ti; ++j) acc += dlocf[j * F + f];
-      }
-      accp[i] += acc;
-    }
-    for (int i = tid; i < Ti; i += 256) {
-      float acc = a.dcum[(long long)b * Ti + i];
+  // dcum_{t-1}[i] = dcum_t[i] + sum_{k,a} dE[i - k + half][a] U[k][a]   (warp per i, lane = 4 channels)
+  for (int i = warp; i < Ti; i += NW) {
+    float acc = 0.f;
+    if (lane < (A >> 2)) {
+      const int c = lane * 4;
       for (int k = 0; k < a.KA; ++k) {
-        const int j = i - k + half;
-        if (j >= 0 && j < Ti)
-          for (int f = 0; f < F; ++f) acc += dlocf[j * F + f] * a.K[k * F + f];
+        const float4 d4 = *reinterpret_cast<const float4*>(dE + (i - k + 2 * half) * A + c);   // row (i - k + half) + half
+        const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
+        acc += d4.x * u.x + d4.y * u.y + d4.z * u.z + d4.w * u.w;
       }
-      a.dcum[(long long)b * Ti + i] = acc;
     }
+    acc = warp_sum(acc);
+    if (lane == 0) a.dcum[(long long)b * Ti + i] += acc;
   }
-  for (int k = tid; k < a.D; k += 256) {
+  // dh2ext = dPI[:, 0:D] + dq . Wq^T
+  for (int k = tid; k < a.D; k += kAttThreads) {
     float acc = a.dPI[(long long)b * a.ld_dPI + k];
-    const float* w = a.Wq + (long long)k * A;
-    for (int c = 0; c < A; ++c) acc += dq[c] * w[c];
+    const float4* w = reinterpret_cast<const float4*>(a.Wq + (long long)k * A);
+    for (int c = 0; c < (A >> 2); ++c) {
+      const float4 ww = __ldg(w + c);
+      acc += dq[c * 4] * ww.x + dq[c * 4 + 1] * ww.y + dq[c * 4 + 2] * ww.z + dq[c * 4 + 3] * ww.w;
+    }
     a.dh2ext[(long long)b * a.D + k] = acc;
   }
 }
-// reduce the per-item attention accumulators over the batch into the gradient buffer
-__global__ void att_acc_reduce_kernel(const float* __restrict__ acc, float* __restrict__ grads, int B, int n, long long o_wl, int n_wl,
-                                      long long o_k, int n_k, long long o_bk, int n_bk, long long o_v, long long o_ba, int A) {
+// after the loop: reduce the per-item accumulators over the batch and push dU / du0 / dv through the U = K . Wl
+// factorisation: dK = dU Wl^T, dWl = K^T dU + bK (x) du0, dbK = Wl du0, d attention_bias = du0, dv
+__global__ void att_finish_kernel(const float* __restrict__ acc, const float* __restrict__ K, const float* __restrict__ bK,
+                                  const float* __restrict__ Wl, float* __restrict__ grads, int B, int KA, int F, int A, long long o_k,
+                                  long long o_bk, long long o_wl, long long o_v, long long o_ba, float* __restrict__ scratch) {
+  // phase 1 (all blocks): reduce over the batch into scratch [(KA+2)][A]
+  const int n = (KA + 2) * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += acc[(long long)b * n + i];
+    scratch[i] = s;
+  }
+}
+__global__ void att_finish2_kernel(const float* __restrict__ dU, const float* __restrict__ K, const float* __restrict__ bK,
+                                   const float* __restrict__ Wl, float* __restrict__ grads, int KA, int F, int A, long long o_k, long long o_bk,
+                                   long long o_wl, long long o_v, long long o_ba) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < B; ++b) s += acc[(long long)b * n + i];
-  if (i < n_wl) grads[o_wl + i] += s;
-  else if (i < n_wl + n_k) grads[o_k + (i - n_wl)] += s;
-  else if (i < n_wl + n_k + n_bk) grads[o_bk + (i - n_wl - n_k)] += s;
-  else if (i < n_wl + n_k + n_bk + A) grads[o_v + (i - n_wl - n_k - n_bk)] += s;
-  else grads[o_ba + (i - n_wl - n_k - n_bk - A)] += s;
+  const float* du0 = dU + KA * A;
+  const float* dv = dU + (KA + 1) * A;
+  if (i < KA * F) {            // dK[k][f] = sum_a dU[k][a] Wl[f][a]
+    const int k = i / F, f = i % F;
+    float s = 0.f;
+    for (int c = 0; c < A; ++c) s += dU[k * A + c] * Wl[f * A + c];
+    grads[o_k + i] += s;
+  } else if (i < KA * F + F * A) {   // dWl[f][a] = sum_k K[k][f] dU[k][a] + bK[f] du0[a]
+    const int j = i - KA * F, f = j / A, c = j % A;
+    float s = bK[f] * du0[c];
+    for (int k = 0; k < KA; ++k) s += K[k * F + f] * dU[k * A + c];
+    grads[o_wl + j] += s;
+  } else if (i < KA * F + F * A + F) {   // dbK[f] = sum_a Wl[f][a] du0[a]
+    const int f = i - KA * F - F * A;
+    float s = 0.f;
+    for (int c = 0; c < A; ++c) s += Wl[f * A + c] * du0[c];
+    grads[o_bk + f] += s;
+  } else if (i < KA * F + F * A + F + A) {
+    const int c = i - KA * F - F * A - F;
+    grads[o_v + c] += dv[c];
+    grads[o_ba + c] += du0[c];
+  }
 }
 // dvalues[b][j][c] += sum_t alpha[t][b][j] * dctx[t][b][c]; then apply the memory mask in place
 __global__ void dvalues_ctx_kernel(const float* __restrict__ alpha, const bf16* __restrict__ dctx, const int* __restrict__ lens,
@@ -1109,7 +1210,10 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   T2_CHECK_CUDA(cudaMemsetAsync(c2, 0, (size_t)B * D * 4, st));
   float* cum = reinterpret_cast<float*>(ws + lo.w_cum);
   T2_CHECK_CUDA(cudaMemsetAsync(cum, 0, (size_t)B * Ti * 4, st));
-  const size_t att_smem = sizeof(float) * (2 * Ti + lo.A + (size_t)Ti * lo.F + 32);
+  float* attU = reinterpret_cast<float*>(ws + lo.w_attU);
+  att_prep_kernel<<<g1((lo.KA + 1) * lo.A), 256, 0, st>>>(d_params + lo.p_lck, d_params + lo.p_lcb, d_params + lo.p_lfl, d_params + lo.p_ba, attU,
+                                                       lo.KA, lo.F, lo.A); t2_count_launch();
+  const size_t att_smem = sizeof(float) * (size_t)((lo.KA + 1) * lo.A + Ti + lo.KA + 8 + lo.A + Ti + 4 + D + 8 * 2 * H + 32) + 64;
   T2_CHECK_CUDA(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
   for (int t = 0; t < To; ++t) {
     bf16* S1t = S1 + (long long)t * B * K1r;
@@ -1130,12 +1234,12 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
     if (rc) return rc;
     AttArgs a;
     a.h2out = PIt; a.ld_h2 = PIK; a.WqT = reinterpret_cast<const bf16*>(pk + lo.k_qT);
-    a.K = d_params + lo.p_lck; a.bK = d_params + lo.p_lcb; a.Wl = d_params + lo.p_lfl; a.v = d_params + lo.p_v; a.ba = d_params + lo.p_ba;
+    a.U = attU; a.v = d_params + lo.p_v;
     a.keys = keys; a.values = values; a.lens = d_input_lengths; a.cum = cum;
     a.alpha = reinterpret_cast<float*>(ws + lo.w_alpha) + (long long)t * B * Ti;
     a.ctx_a = S1n; a.ld_a = K1r; a.ctx_b = PIt + D; a.ld_b = PIK;
-    a.B = B; a.Ti = Ti; a.D = D; a.A = lo.A; a.F = lo.F; a.KA = lo.KA; a.C2 = 2 * H;
-    att_fwd_kernel<<<B, 256, att_smem, st>>>(a); t2_count_launch();
+    a.B = B; a.Ti = Ti; a.D = D; a.A = lo.A; a.KA = lo.KA; a.C2 = 2 * H;
+    att_fwd_kernel<<<B, kAttThreads, att_smem, st>>>(a); t2_count_launch();
   }
   T2_CHECK_CUDA(cudaGetLastError());
   // frame + stop projections for all steps at once
@@ -1263,7 +1367,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   float* cumrun = reinterpret_cast<float*>(ws + lo.w_cumrun);
   float* dkeys = reinterpret_cast<float*>(ws + lo.w_dkeys);
   float* attacc = reinterpret_cast<float*>(ws + lo.w_attacc);
-  const int nacc = lo.F * A + lo.KA * lo.F + lo.F + 2 * A;
+  const int nacc = (lo.KA + 2) * A;
   for (float* p : {dhs1, dhs2, dcs1, dcs2}) T2_CHECK_CUDA(cudaMemsetAsync(p, 0, (size_t)B * D * 4, st));
   T2_CHECK_CUDA(cudaMemsetAsync(dctxl, 0, (size_t)B * 2 * H * 4, st));
   T2_CHECK_CUDA(cudaMemsetAsync(dcum, 0, (size_t)B * Ti * 4, st));
@@ -1274,18 +1378,19 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   bf16* dg2 = reinterpret_cast<bf16*>(ws + lo.w_dg2);
   bf16* dctx_all = reinterpret_cast<bf16*>(ws + lo.w_dctx_all);
   bf16* dq_all = reinterpret_cast<bf16*>(ws + lo.w_dq_all);
-  const size_t ab_smem = sizeof(float) * (size_t)(2 * Ti + A + 2 * Ti * lo.F + Ti + A + 2 * H + Ti * A + 32);
+  const size_t ab_smem = sizeof(float) * (size_t)((lo.KA + 1) * A + Ti + lo.KA + 8 + A + 2 * Ti + 8 + D + 2 * H + 2 * A + (Ti + lo.KA) * A + 32) + 64;
+  const float* attU = reinterpret_cast<const float*>(ws + lo.w_attU);
   T2_CHECK_CUDA(cudaFuncSetAttribute(att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ab_smem)));
   for (int t = To - 1; t >= 0; --t) {
     AttBwd a;
     a.h2out = PI + (long long)t * B * PIK; a.ld_h2 = PIK; a.WqT = reinterpret_cast<const bf16*>(pk + lo.k_qT); a.Wq = d_params + lo.p_qry;
-    a.K = d_params + lo.p_lck; a.bK = d_params + lo.p_lcb; a.Wl = d_params + lo.p_lfl; a.v = d_params + lo.p_v; a.ba = d_params + lo.p_ba;
+    a.U = attU; a.v = d_params + lo.p_v;
     a.keys = reinterpret_cast<const float*>(ws + lo.w_keys); a.values = reinterpret_cast<const bf16*>(ws + lo.w_values); a.lens = d_input_lengths;
     a.alpha = reinterpret_cast<const float*>(ws + lo.w_alpha) + (long long)t * B * Ti; a.cumrun = cumrun; a.dcum = dcum;
     a.dPI = dPI + (long long)t * B * PIK; a.ld_dPI = PIK; a.dctxl = dctxl; a.dh2ext = dh2ext;
     a.dctx_save = dctx_all + (long long)t * B * 2 * H; a.dq_save = dq_all + (long long)t * B * A; a.dkeys = dkeys; a.acc = attacc;
-    a.B = B; a.Ti = Ti; a.D = D; a.A = A; a.F = lo.F; a.KA = lo.KA; a.C2 = 2 * H;
-    att_bwd_kernel<<<B, 256, ab_smem, st>>>(a); t2_count_launch();
+    a.B = B; a.Ti = Ti; a.D = D; a.A = A; a.KA = lo.KA; a.C2 = 2 * H;
+    att_bwd_kernel<<<B, kAttThreads, ab_smem, st>>>(a); t2_count_launch();
     CellBwd c2;
     c2.dh_ext = dh2ext; c2.ld_ext = D; c2.dhs = dhs2; c2.dcs = dcs2;
     c2.gst = reinterpret_cast<const bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D; c2.tst = reinterpret_cast<const bf16*>(ws + lo.w_t2) + (long long)t * B * D;
@@ -1332,8 +1437,14 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
     colsum_bf16_kernel<<<64, 256, 0, st>>>(dz2, TB, lo.P2, lo.P2, d_grads + lo.p_p2b, 1.f); t2_count_launch();
     colsum_bf16_kernel<<<64, 256, 0, st>>>(dpn1, TB, lo.P1, lo.P1, d_grads + lo.p_p1b, 1.f); t2_count_launch();
   }
-  att_acc_reduce_kernel<<<g1(nacc), 256, 0, st>>>(attacc, d_grads, B, nacc, lo.p_lfl, lo.F * A, lo.p_lck, lo.KA * lo.F, lo.p_lcb, lo.F, lo.p_v,
-                                                  lo.p_ba, A); t2_count_launch();
+  {
+    float* scratch = reinterpret_cast<float*>(ws + lo.w_attU) + (lo.KA + 1) * A;   // [(KA+2)][A] reduced accumulators
+    att_finish_kernel<<<g1(nacc), 256, 0, st>>>(attacc, d_params + lo.p_lck, d_params + lo.p_lcb, d_params + lo.p_lfl, d_grads, B, lo.KA, lo.F, A,
+                                                lo.p_lck, lo.p_lcb, lo.p_lfl, lo.p_v, lo.p_ba, scratch); t2_count_launch();
+    att_finish2_kernel<<<g1(lo.KA * lo.F + lo.F * A + lo.F + A), 256, 0, st>>>(scratch, d_params + lo.p_lck, d_params + lo.p_lcb, d_params + lo.p_lfl,
+                                                                             d_grads, lo.KA, lo.F, A, lo.p_lck, lo.p_lcb, lo.p_lfl, lo.p_v,
+                                                                             lo.p_ba); t2_count_launch();
+  }
   // ---- attention memory: keys / values ----
   bf16* dkeysb = reinterpret_cast<bf16*>(ws + lo.w_dkeysb);
   f32_to_bf16_k<<<g1((long long)B * Ti * A), 256, 0, st>>>(dkeys, dkeysb, (long long)B * Ti * A); t2_count_launch();
