@@ -147,6 +147,50 @@ __device__ __forceinline__ void tile_fill(uint8_t* tile, const __nv_bfloat16* g,
   if (NW == 4) quarter_sync(c.qbar); else __syncwarp();
 }
 
+// Column sums across a warp: lane r holds v[0..31] (row r of a 32x32 tile); on return lane j holds sum_r v_r[j].
+// Recursive halving: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 full warp reductions.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool up = lane & 16;
+    const float send = up ? v[j] : v[j + 16];
+    const float keep = up ? v[j + 16] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool up = lane & 8;
+    const float send = up ? v[j] : v[j + 8];
+    const float keep = up ? v[j + 8] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool up = lane & 4;
+    const float send = up ? v[j] : v[j + 4];
+    const float keep = up ? v[j + 4] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const bool up = lane & 2;
+    const float send = up ? v[j] : v[j + 2];
+    const float keep = up ? v[j + 2] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];   // lane l owns column (bit-reversed mapping resolved below): column index = colsum32_col(lane)
+}
+// column owned by `lane` after warp_colsum32: at each halving step a lane with the bit set keeps the upper half
+__device__ __forceinline__ int colsum32_col(int lane) {
+  return ((lane & 16) ? 16 : 0) + ((lane & 8) ? 8 : 0) + ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + ((lane & 1) ? 1 : 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Epilogues (one specialisation per fused op)
 // ------------------------------------------------------------------------------------------------
@@ -473,8 +517,8 @@ struct Epilogue<EPI_MOL, 32> {
 };
 
 // backward through ReLU: out = acc * scale * (h > 0).
-// ptr: 0 out bf16 [pos, ldo], 1 h bf16 [pos, ldo], 2 device scalar fp32* (nullable; multiplies 1/x);
-// f0 const scale; i0 = ldo
+// ptr: 0 out bf16 [pos, ldo], 1 h bf16 [pos, ldo], 2 device scalar fp32* (nullable; multiplies 1/x),
+//      3 fp32 [ldo] column sums of `out` accumulated with atomics (nullable: bias gradient);  f0 const scale; i0 = ldo
 template <int BN>
 struct Epilogue<EPI_SCALE_RELUMASK, BN> {
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
@@ -497,13 +541,18 @@ struct Epilogue<EPI_SCALE_RELUMASK, BN> {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = hv[j] > 0.f ? acc[j] * s : 0.f;
         stage_put(t_o, c.lane, cq, acc);
+        if (e.ptr[3]) {
+          const float cs = warp_colsum32(acc, c.lane);
+          atomicAdd(static_cast<float*>(e.ptr[3]) + c.n_tile * BN + gq * 128 + cq * 32 + colsum32_col(c.lane), cs);
+        }
       }
       tile_flush<4>(t_o, out + off, ldo, c.nrows, c);
     }
   }
 };
 
-// backward of the gate: dz -> (da, db).  ptr: 0 ta, 1 sb (bf16 [pos,Gh]), 2 dg out (bf16 [pos,2Gh]); i0 = Gh
+// backward of the gate: dz -> (da, db).  ptr: 0 ta, 1 sb (bf16 [pos,Gh]), 2 dg out (bf16 [pos,2Gh]), 3 / 4 fp32 [2Gh]
+// gate-bias gradients (column sums of dg, atomics; nullable — dilated-conv bias and cin-conv bias get the same sum); i0 = Gh
 template <int BN>
 struct Epilogue<EPI_GATE_BWD, BN> {
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
@@ -535,6 +584,16 @@ struct Epilogue<EPI_GATE_BWD, BN> {
         }
         stage_put(t_da, c.lane, cq, a);
         stage_put(t_db, c.lane, cq, s);
+        if (e.ptr[3]) {
+          const float ca = warp_colsum32(a, c.lane), cb2 = warp_colsum32(s, c.lane);
+          const int col = cb + cq * 32 + colsum32_col(c.lane);
+          atomicAdd(static_cast<float*>(e.ptr[3]) + col, ca);
+          atomicAdd(static_cast<float*>(e.ptr[3]) + Gh + col, cb2);
+          if (e.ptr[4]) {
+            atomicAdd(static_cast<float*>(e.ptr[4]) + col, ca);
+            atomicAdd(static_cast<float*>(e.ptr[4]) + Gh + col, cb2);
+          }
+        }
       }
       tile_flush<4>(t_da, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
       tile_flush<4>(t_db, dg + c.row0 * 2 * Gh + Gh + cb, 2 * Gh, c.nrows, c);
@@ -543,8 +602,9 @@ struct Epilogue<EPI_GATE_BWD, BN> {
 };
 
 // gradient wrt the block input: dx = dropout_mask/keep * acc + res_scale * dx_out
-// ptr: 0 dxo bf16 [pos,R] (nullable), 1 dx_out bf16 [pos,R], 7 device u64 seed offset (nullable);
-// f0 res_scale, f1 dropout p; i1 = layer
+// ptr: 0 dxo bf16 [pos,R] (nullable), 1 dx_out bf16 [pos,R], 2 fp32 [R] += f2 * column sums of dx_out (nullable: bias
+// gradient of the 1x1 that produced this layer's input), 7 device u64 seed offset (nullable);
+// f0 res_scale, f1 dropout p, f2 bias-gradient scale; i1 = layer
 template <int BN>
 struct Epilogue<EPI_DX, BN> {
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
@@ -577,6 +637,10 @@ struct Epilogue<EPI_DX, BN> {
           for (int j = 0; j < 32; ++j) acc[j] += rs * g[j];
         }
         stage_put(t_o, c.lane, cq, acc);
+        if (e.ptr[2]) {
+          const float cs = warp_colsum32(acc, c.lane);
+          atomicAdd(static_cast<float*>(e.ptr[2]) + j0 + colsum32_col(c.lane), cs * e.f[2]);
+        }
       }
       tile_flush<4>(t_o, dx + c.row0 * R + gq * 128, R, c.nrows, c);
     }

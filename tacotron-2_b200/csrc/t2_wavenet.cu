@@ -69,6 +69,7 @@ struct Layout {
   long long packed_bytes;
   // workspace (byte offsets)
   long long w_cup, w_x, w_xd, w_ta, w_sb, w_z, w_h1, w_h2, w_dlog, w_dh2, w_dskip, w_dxin, w_dg, w_dcup;
+  long long w_skipsum;
   long long w_upgrad[2], w_scalars, w_tiles_main, w_tiles_head, w_packjobs, w_colsum, w_tables;
   std::vector<long long> w_upout;
   std::vector<int> up_w;  // width after each upsample layer
@@ -209,6 +210,7 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   lo.w_dg = takeb(L * BT * lo.G * 2);
   lo.w_dcup = takeb(BT * (lo.C > 0 ? lo.C : 8) * 4);
   lo.w_scalars = takeb(64 * 4);
+  lo.w_skipsum = takeb(lo.S * 4);
 
   // ---- pack jobs ----
   lo.packjobs.clear();
@@ -285,15 +287,9 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
     ColsumJob j; j.src_off = src; j.rows = rows; j.C = C; j.ld = ld; j.dst_off = dst; j.dst2_off = dst2; j.scale = scale;
     j.div_scalar = div; lo.colsums.push_back(j);
   };
-  for (int l = 0; l < lo.L; ++l) {
-    cs(lo.w_dg + (long long)l * BT * lo.G * 2, BT, lo.G, lo.G, lo.p_dil_b[l], lo.C > 0 ? lo.p_c_b[l] : -1, 1.f, -1);
-    if (l < lo.L - 1) cs(lo.w_dxin + (long long)(l + 1) * BT * lo.R * 2, BT, lo.R, lo.R, lo.p_o_b[l], -1, lo.res_scale, -1);
-    cs(lo.w_dskip, BT, lo.S, lo.S, lo.p_s_b[l], -1, lo.skip_scale[l], -1);
-  }
-  cs(lo.w_dh2, BT, lo.S, lo.S, lo.p_f1_b, -1, 1.f, -1);
+  // (all other bias gradients are column sums fused into the GEMM epilogues that produce dg / dx / dskip / dh2)
   cs(lo.w_dlog, BT, lo.O, lo.ldo, lo.p_f2_b, -1, 1.f, 1);
   if (!lo.mol) cs(lo.w_dlog + 256 * 2, BT, lo.O, lo.ldo, lo.p_f2_b, -1, 1.f, 1);
-  cs(lo.w_dxin, BT, lo.R, lo.R, lo.p_in_b, -1, 1.f, -1);
   lo.n_colsum = int(lo.colsums.size());
 
   lo.w_tiles_main = takeb((long long)lo.n_tiles_main * sizeof(WgradTile));
@@ -309,23 +305,37 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
 // small kernels
 // ------------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ params, bf16* __restrict__ packed, const PackJob* __restrict__ jobs) {
+  // 32x32 tiles through shared memory: reads are coalesced along the source's fast axis (N), writes along the
+  // destination's fast axis (K for the transposing jobs)
+  __shared__ float tile[32][33];
   const PackJob j = jobs[blockIdx.y];
-  const long long n = (long long)j.K * j.N;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int k = int(e / j.N), c = int(e % j.N);
-    const float v = params[j.src_off + e] * j.scale;
-    long long d;
-    if (j.transpose) {
-      int row = c;
-      if (j.perm_gh > 0) {
-        const int half = c / j.perm_gh, idx = c % j.perm_gh;
-        row = (idx / 128) * 256 + half * 128 + (idx % 128);
-      }
-      d = j.dst_off + (long long)row * j.dst_ld + j.col0 + k;
-    } else {
-      d = j.dst_off + (long long)k * j.dst_ld + j.col0 + c;
+  const int tiles_n = (j.N + 31) / 32, tiles_k = (j.K + 31) / 32;
+  for (int ti = blockIdx.x; ti < tiles_n * tiles_k; ti += gridDim.x) {
+    const int k0 = (ti / tiles_n) * 32, n0 = (ti % tiles_n) * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int k = k0 + r, n = n0 + threadIdx.x;
+      tile[r][threadIdx.x] = (k < j.K && n < j.N) ? params[j.src_off + (long long)k * j.N + n] * j.scale : 0.f;
     }
-    packed[d] = __float2bfloat16(v);
+    __syncthreads();
+    if (j.transpose) {
+      for (int r = threadIdx.y; r < 32; r += 8) {
+        const int n = n0 + r, k = k0 + threadIdx.x;
+        if (n < j.N && k < j.K) {
+          int row = n;
+          if (j.perm_gh > 0) {
+            const int half = n / j.perm_gh, idx = n % j.perm_gh;
+            row = (idx / 128) * 256 + half * 128 + (idx % 128);
+          }
+          packed[j.dst_off + (long long)row * j.dst_ld + j.col0 + k] = __float2bfloat16(tile[threadIdx.x][r]);
+        }
+      }
+    } else {
+      for (int r = threadIdx.y; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + threadIdx.x;
+        if (n < j.N && k < j.K) packed[j.dst_off + (long long)k * j.dst_ld + j.col0 + n] = __float2bfloat16(tile[r][threadIdx.x]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -464,45 +474,60 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ in, const float* _
   out[e] = acc;
   if (out_cl) out_cl[((long long)b * Wo + xo) * H + h] = __float2bfloat16(acc);
 }
-// d_pre = d_out * (out > 0); accumulates dK, dbias (atomics after a block reduce) and writes d_in.
-// d_out is either fp32 [B][H][Wo] (cl = 0) or channels-last fp32 [B][Wo][H] (cl = 1)
-__global__ void upsample_bwd_param_kernel(const float* __restrict__ in, const float* __restrict__ out, const float* __restrict__ dout,
-                                          int cl, float* __restrict__ dK, float* __restrict__ dbias, int B, int H, int W, int s,
-                                          int type) {
-  // one block per (k, tap): reduces over all (b, h, w)
-  const int k = blockIdx.x;
-  const int tap = blockIdx.y;  // SubPixel: 0..8 taps, 9 = bias ; 2D: 0..2 taps, 3 = bias
-  const int ntap = type == 0 ? 9 : 3;
-  const int Wo = W * s;
-  float acc = 0.f;
-  const long long n = (long long)B * H * W;
-  for (long long e = blockIdx.z * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.z * blockDim.x) {
-    const int w = int(e % W), h = int((e / W) % H), b = int(e / ((long long)W * H));
-    const int xo = w * s + k;
-    const float o = out[((long long)b * H + h) * Wo + xo];
-    if (o <= 0.f) continue;
-    const float g = cl ? dout[((long long)b * Wo + xo) * H + h] : dout[((long long)b * H + h) * Wo + xo];
-    if (tap == ntap) { acc += g; continue; }
-    int hh, ww;
-    if (type == 0) { hh = h + tap / 3 - 1; ww = w + tap % 3 - 1; }
-    else { hh = h + 1 - tap; ww = w; }
-    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    acc += g * in[((long long)b * H + hh) * W + ww];
+// channels-last fp32 [B][T][C] -> [B][C][T] (tiled transpose) so the upsampling backward reads contiguously
+__global__ void cl_to_chw_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (t < T && c < C) ? in[((long long)b * T + t) * C + c] : 0.f;
   }
-  __shared__ float red[32];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) {
-      if (tap == ntap) {
-        if (type == 0) atomicAdd(dbias + k, v); else atomicAdd(dbias, v);
-      } else {
-        atomicAdd(dK + tap * s + k, v);
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + threadIdx.x;
+    if (t < T && c < C) out[((long long)b * C + c) * T + t] = tile[threadIdx.x][r];
+  }
+}
+// d_pre = d_out * (out > 0); accumulates dK [ntap][s] and dbias through a shared-memory table (one global atomic per
+// table entry per block). d_out / out are [B][H][W*s]; consecutive threads walk consecutive output samples.
+__global__ void upsample_bwd_param_kernel(const float* __restrict__ in, const float* __restrict__ out, const float* __restrict__ dout,
+                                          float* __restrict__ dK, float* __restrict__ dbias, int B, int H, int W, int s, int type) {
+  __shared__ float acc[10 * 32];
+  const int ntap = type == 0 ? 9 : 3;
+  for (int i = threadIdx.x; i < (ntap + 1) * s; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int Wo = W * s;
+  const long long n = (long long)B * H * Wo;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    if (out[e] <= 0.f) continue;
+    const float g = dout[e];
+    const int xo = int(e % Wo), h = int((e / Wo) % H), b = int(e / ((long long)Wo * H));
+    const int w = xo / s, k = xo % s;
+    atomicAdd(&acc[ntap * s + k], g);
+    const float* ib = in + (long long)b * H * W;
+    if (type == 0) {
+      for (int dh = 0; dh < 3; ++dh) {
+        const int hh = h + dh - 1;
+        if (hh < 0 || hh >= H) continue;
+        for (int dw = 0; dw < 3; ++dw) {
+          const int ww = w + dw - 1;
+          if (ww >= 0 && ww < W) atomicAdd(&acc[(dh * 3 + dw) * s + k], g * ib[hh * W + ww]);
+        }
+      }
+    } else {
+      for (int q = 0; q < 3; ++q) {
+        const int hh = h + 1 - q;
+        if (hh >= 0 && hh < H) atomicAdd(&acc[q * s + k], g * ib[hh * W + w]);
       }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (ntap + 1) * s; i += blockDim.x) {
+    const float v = acc[i];
+    if (v == 0.f) continue;
+    if (i < ntap * s) atomicAdd(dK + i, v);
+    else if (type == 0) atomicAdd(dbias + (i - ntap * s), v);
+    else atomicAdd(dbias, v);
   }
 }
 __global__ void upsample_bwd_input_kernel(const float* __restrict__ out, const float* __restrict__ dout, int cl,
@@ -536,6 +561,14 @@ __global__ void upsample_bwd_input_kernel(const float* __restrict__ out, const f
     }
   }
   din[e] = acc;
+}
+// skip-conv bias gradients: db_s[l] = skip_scale[l] * column sums of dskip (table layout: offs[3l+2] = skip bias offset)
+__global__ void skip_bias_kernel(const float* __restrict__ skipsum, float* __restrict__ grads, const long long* __restrict__ offs,
+                                 const float* __restrict__ scales, int L, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * S) return;
+  const int l = i / S, s = i % S;
+  grads[offs[3 * l + 2] + s] = scales[l] * skipsum[s];
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -587,7 +620,7 @@ ActGemmCall make_out_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, cons
   return o;
 }
 
-ActGemmCall make_dz_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l) {
+ActGemmCall make_dz_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l, float* grads) {
   const long long BT = (long long)lo.B * lo.T;
   const bool top = l == lo.L - 1;
   ActGemmCall g;
@@ -609,12 +642,14 @@ ActGemmCall make_dz_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l
   g.epi.ptr[0] = reinterpret_cast<bf16*>(ws + lo.w_ta) + lofs;
   g.epi.ptr[1] = reinterpret_cast<bf16*>(ws + lo.w_sb) + lofs;
   g.epi.ptr[2] = reinterpret_cast<bf16*>(ws + lo.w_dg) + (long long)l * BT * lo.G;
+  g.epi.ptr[3] = grads ? grads + lo.p_dil_b[l] : nullptr;
+  g.epi.ptr[4] = (grads && lo.C > 0) ? grads + lo.p_c_b[l] : nullptr;
   g.epi.i[0] = lo.Gh;
   return g;
 }
 
 ActGemmCall make_dx_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l, float p, unsigned long long seed,
-                         const unsigned long long* d_step) {
+                         const unsigned long long* d_step, float* grads) {
   const long long BT = (long long)lo.B * lo.T;
   const int d = lo.dil(l);
   const bool top = l == lo.L - 1;
@@ -630,6 +665,9 @@ ActGemmCall make_dx_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int l
   g.epi.ptr[1] = dxin + (long long)l * BT * lo.R;
   g.epi.f[0] = lo.res_scale; g.epi.f[1] = p; g.epi.i[1] = l; g.epi.seed = seed;
   g.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
+  // dx of layer l is the gradient of x_l = output of layer l-1's out-1x1 (or of the first conv): fused bias gradient
+  g.epi.ptr[2] = grads ? grads + (l > 0 ? lo.p_o_b[l - 1] : lo.p_in_b) : nullptr;
+  g.epi.f[2] = l > 0 ? lo.res_scale : 1.f;
   return g;
 }
 
@@ -705,7 +743,7 @@ extern "C" int t2_wn_pack_weights(const t2_wn_config_t* cfg, const float* d_para
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   uint8_t* pk = static_cast<uint8_t*>(d_packed);
-  pack_kernel<<<dim3(48, lo.n_packjobs), 256, 0, st>>>(d_params, reinterpret_cast<bf16*>(pk),
+  pack_kernel<<<dim3(32, lo.n_packjobs), dim3(32, 8), 0, st>>>(d_params, reinterpret_cast<bf16*>(pk),
                                                        reinterpret_cast<const PackJob*>(ws + lo.w_packjobs)); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   long long* d_offs = reinterpret_cast<long long*>(ws + lo.w_tables);
@@ -843,6 +881,7 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
   float* scalars = reinterpret_cast<float*>(ws + lo.w_scalars);
   const float p = cfg->dropout;
   T2_CHECK_CUDA(cudaMemsetAsync(d_grads, 0, lo.n_params * sizeof(float), st));
+  T2_CHECK_CUDA(cudaMemsetAsync(ws + lo.w_skipsum, 0, lo.S * sizeof(float), st));
   bf16* h1 = reinterpret_cast<bf16*>(ws + lo.w_h1);
   bf16* h2 = reinterpret_cast<bf16*>(ws + lo.w_h2);
   bf16* dlog = reinterpret_cast<bf16*>(ws + lo.w_dlog);
@@ -861,6 +900,7 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     g.w = pk + lo.k_Wf2T; g.wN = lo.S; g.wK = lo.Op; g.wL = 1;
     g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
     g.epi.ptr[0] = dh2; g.epi.ptr[1] = h2; g.epi.ptr[2] = scalars + 1; g.epi.f[0] = 1.f; g.epi.i[0] = lo.S;
+    g.epi.ptr[3] = d_grads + lo.p_f1_b;
     rc = launch_act_gemm(EPI_SCALE_RELUMASK, lo.S, g, st);
     if (rc) return rc;
   }
@@ -872,19 +912,23 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     g.w = pk + lo.k_Wf1T; g.wN = lo.S; g.wK = lo.S; g.wL = 1;
     g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
     g.epi.ptr[0] = dskip; g.epi.ptr[1] = h1; g.epi.ptr[2] = nullptr; g.epi.f[0] = 1.f; g.epi.i[0] = lo.S;
+    g.epi.ptr[3] = ws + lo.w_skipsum;
     rc = launch_act_gemm(EPI_SCALE_RELUMASK, lo.S, g, st);
     if (rc) return rc;
   }
+  skip_bias_kernel<<<grid1d((long long)lo.L * lo.S), 256, 0, st>>>(reinterpret_cast<const float*>(ws + lo.w_skipsum), d_grads,
+      reinterpret_cast<const long long*>(ws + lo.w_tables), reinterpret_cast<const float*>(ws + lo.w_tables + 3 * lo.L * sizeof(long long)), lo.L, lo.S);
+  t2_count_launch();
   // residual stack, top down
   const ActT a_dxin = make_act(dxin, lo.R, lo.T, lo.B, lo.L);
   const ActT a_dskip = make_act(dskip, lo.S, lo.T, lo.B, 1);
   const ActT a_dg = make_act(dg, lo.G, lo.T, lo.B, lo.L);
   const int bn_z = lo.Gh >= 256 ? 256 : 128;
   for (int l = lo.L - 1; l >= 0; --l) {
-    ActGemmCall gz = make_dz_call(lo, ws, pk, l);
+    ActGemmCall gz = make_dz_call(lo, ws, pk, l, d_grads);
     rc = launch_act_gemm(EPI_GATE_BWD, bn_z, gz, st);
     if (rc) return rc;
-    ActGemmCall gx = make_dx_call(lo, ws, pk, l, p, seed, d_step);
+    ActGemmCall gx = make_dx_call(lo, ws, pk, l, p, seed, d_step, d_grads);
     rc = launch_act_gemm(EPI_DX, lo.R, gx, st);
     if (rc) return rc;
   }
@@ -919,22 +963,24 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     g.epi.i[0] = lo.C; g.epi.i[1] = 0; g.epi.i[2] = lo.C;
     rc = launch_act_gemm(EPI_BIAS_ACT, 128, g, st);
     if (rc) return rc;
-    const float* dout = dcup;
-    int cl = 1, pp = 0;
+    // dc_up arrives channels-last from the GEMM: transpose once into [B][C][T]
+    float* dchw = reinterpret_cast<float*>(ws + lo.w_upgrad[1]);
+    cl_to_chw_kernel<<<dim3((lo.T + 31) / 32, (lo.C + 31) / 32, lo.B), dim3(32, 8), 0, st>>>(dcup, dchw, lo.T, lo.C); t2_count_launch();
+    const float* dout = dchw;
+    int pp = 0;
     for (int i = int(lo.up_w.size()) - 1; i >= 0; --i) {
       const int s = cfg->upsample_scales[i];
       const int W = lo.up_w[i] / s;
+      T2_REQUIRE(s <= 32, T2_ERR_UNSUPPORTED_SHAPE, "upsample scale > 32");
       const float* layer_in = i == 0 ? d_c : reinterpret_cast<const float*>(ws + lo.w_upout[i - 1]);
       const float* out = reinterpret_cast<const float*>(ws + lo.w_upout[i]);
-      const int ntap = cfg->upsample_type == 0 ? 9 : 3;
-      upsample_bwd_param_kernel<<<dim3(s, ntap + 1, 24), 256, 0, st>>>(layer_in, out, dout, cl, d_grads + lo.p_up_k[i], d_grads + lo.p_up_b[i],
-                                                                  lo.B, lo.C, W, s, cfg->upsample_type); t2_count_launch();
+      upsample_bwd_param_kernel<<<296, 256, 0, st>>>(layer_in, out, dout, d_grads + lo.p_up_k[i], d_grads + lo.p_up_b[i], lo.B, lo.C, W, s,
+                                                     cfg->upsample_type); t2_count_launch();
       if (i > 0) {
         float* din = reinterpret_cast<float*>(ws + lo.w_upgrad[pp]);
-        upsample_bwd_input_kernel<<<grid1d((long long)lo.B * lo.C * W), 256, 0, st>>>(out, dout, cl, d_params + lo.p_up_k[i], din, lo.B, lo.C, W, s,
+        upsample_bwd_input_kernel<<<grid1d((long long)lo.B * lo.C * W), 256, 0, st>>>(out, dout, 0, d_params + lo.p_up_k[i], din, lo.B, lo.C, W, s,
                                                                                     cfg->upsample_type); t2_count_launch();
         dout = din;
-        cl = 0;
         pp ^= 1;
       }
       T2_CHECK_CUDA(cudaGetLastError());
@@ -984,8 +1030,8 @@ extern "C" int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_param
   int epi, bn;
   if (which == 0) { g = make_gate_call(lo, ws, pk, layer, true); epi = EPI_GATE; bn = 256; }
   else if (which == 1) { g = make_out_call(lo, ws, pk, d_params, layer, cfg->dropout, 1, nullptr); epi = EPI_RES; bn = lo.R; }
-  else if (which == 2) { g = make_dz_call(lo, ws, pk, layer); epi = EPI_GATE_BWD; bn = lo.Gh >= 256 ? 256 : 128; }
-  else { g = make_dx_call(lo, ws, pk, layer, cfg->dropout, 1, nullptr); epi = EPI_DX; bn = lo.R; }
+  else if (which == 2) { g = make_dz_call(lo, ws, pk, layer, nullptr); epi = EPI_GATE_BWD; bn = lo.Gh >= 256 ? 256 : 128; }
+  else { g = make_dx_call(lo, ws, pk, layer, cfg->dropout, 1, nullptr, nullptr); epi = EPI_DX; bn = lo.R; }
   cudaEvent_t e0, e1;
   T2_CHECK_CUDA(cudaEventCreate(&e0));
   T2_CHECK_CUDA(cudaEventCreate(&e1));

@@ -108,6 +108,44 @@ class Tacotron(object):
                                           L.stream_ptr()))
         return self.grads
 
+    def capture(self, inputs, input_lengths, mel_targets, stop_targets):
+        """Capture pack + forward + backward (~7.5k kernel nodes at B=32, T_out=800) into one CUDA graph over static inputs."""
+        self._static = (inputs, input_lengths, mel_targets, stop_targets)
+        if self.grads is None:
+            self.grads = torch.zeros_like(self.params)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.pack()
+            self.forward(*self._static)
+            self.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.step_dev.add_(1)
+            self.pack()
+            self.forward(*self._static)
+            self.backward()
+        return self._graph
+
+    def train_step(self, inputs=None, input_lengths=None, mel_targets=None, stop_targets=None, world_size=1):
+        """forward + losses + backward (+ NCCL all-reduce) + clip_by_global_norm + Adam (tacotron.py:406-437 order)."""
+        if getattr(self, "_graph", None) is not None:
+            for dst, src in zip(self._static, (inputs, input_lengths, mel_targets, stop_targets)):
+                if src is not None and src is not dst:
+                    dst.copy_(src, non_blocking=True)
+            self._graph.replay()
+        else:
+            self.step_dev.add_(1)
+            self.forward(inputs, input_lengths, mel_targets, stop_targets)
+            self.backward()
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        self.optimizer_step(grad_scale=1.0 / world_size)
+        return self.loss_buf
+
     def learning_rate(self):
         hp = self.hp
         if not hp.tacotron_decay_learning_rate:

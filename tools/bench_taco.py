@@ -27,7 +27,7 @@ def batch(hp, B, T_in, T_out, seed=3):
 
 
 def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 5
     hp = hparams.copy()
     hp.parse("predict_linear=False")
     B, T_in, T_out = 32, 160, 800
@@ -37,11 +37,15 @@ def main():
     args = (inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda())
     lib = t2.lib.load()
 
+    use_graph = "--graph" in sys.argv
+    if use_graph:
+        model.capture(*args)
+
     def step():
-        model.step_dev.add_(1)
-        model.forward(*args)
-        model.backward()
-        model.optimizer_step()
+        if use_graph:
+            model.train_step()
+        else:
+            model.train_step(*args)
 
     for _ in range(2):
         step()
@@ -56,7 +60,7 @@ def main():
     ms = e0.elapsed_time(e1) / steps
     launches = (lib.t2_launch_count() - n0) // steps
     out = {"metric": "tacotron_train_mel_frames_per_sec", "value": B * T_out / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
-           "config": {"workload": "tacotron_train r=1 B=32 T_in=160 T_out=800 predict_linear=False, bf16 GEMM operands / fp32 state, eager launches"},
+           "config": {"workload": "tacotron_train r=1 B=32 T_in=160 T_out=800 predict_linear=False, bf16 GEMM operands / fp32 state, " + ("CUDA graph" if use_graph else "eager launches")},
            "kernel_launches_per_step": int(launches), "loss": model.losses()}
     # bounded CPU baseline: the oracle (fp32, autograd) on B=4 of the same shapes
     Bc = 4
