@@ -62,6 +62,13 @@ __device__ __forceinline__ float tanhf_(float x) {
   const float t = (1.f - e) * __frcp_rn(1.f + e);
   return copysignf(t, x);
 }
+// single-MUFU forms for values that are stored as bf16 right away (tanh.approx: max rel error 2^-11, bf16 keeps 2^-9)
+__device__ __forceinline__ float tanh_approx_(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_approx_(float x) { return fmaf(0.5f, tanh_approx_(0.5f * x), 0.5f); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -86,10 +93,19 @@ __device__ __host__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i
 __device__ __host__ __forceinline__ uint32_t hash_seed(uint64_t seed, uint32_t stream) {
   return hash_u32(seed, stream);
 }
-__device__ __host__ __forceinline__ float hash_uniform32(uint32_t hs, uint64_t idx) {
+__device__ __host__ __forceinline__ uint32_t hash_bits32(uint32_t hs, uint64_t idx) {
   uint32_t h = hs ^ (uint32_t(idx) * 0x9E3779B1u) ^ (uint32_t(idx >> 32) * 0x85EBCA77u);
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return (h >> 8) * (1.0f / 16777216.0f);
+  return h;
+}
+__device__ __host__ __forceinline__ float hash_uniform32(uint32_t hs, uint64_t idx) {
+  return (hash_bits32(hs, idx) >> 8) * (1.0f / 16777216.0f);
+}
+// dropout keep-decision for element idx: one 32-bit hash serves the element pair (idx & ~1): 16 bits each,
+// i.e. the drop probability is quantised to 1/65536
+__device__ __host__ __forceinline__ bool hash_keep16(uint32_t hs, uint64_t idx, uint32_t thr16) {
+  const uint32_t h = hash_bits32(hs, idx >> 1);
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thr16;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -67,16 +67,17 @@ static int encode_wt_map(CUtensorMap* m, const void* w, int N, int K, int L, int
   return T2_OK;
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, int NT = 1>
 static int launch_one(const GemmArgs& g, dim3 grid, cudaStream_t stream) {
   using Cfg = ActGemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    T2_CHECK_CUDA(cudaFuncSetAttribute(act_gemm_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    T2_CHECK_CUDA(cudaFuncSetAttribute(act_gemm_kernel<EPI, BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     configured = true;
   }
-  act_gemm_kernel<EPI, BN><<<grid, kActGemmThreads, Cfg::kSmemBytes, stream>>>(g);
+  grid.y = (grid.y + NT - 1) / NT;
+  act_gemm_kernel<EPI, BN, NT><<<grid, kActGemmThreads, Cfg::kSmemBytes, stream>>>(g);
   t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
@@ -112,6 +113,7 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
   dim3 grid(g.tiles_per_b * c.B, c.n_tiles, 1);
 #define T2_CASE(E, N) \
   if (epi == E && BN == N) return launch_one<E, N>(g, grid, stream);
+  if (epi == EPI_GATE && BN == 256 && c.n_tiles % 2 == 0) return launch_one<EPI_GATE, 256, 2>(g, grid, stream);
   T2_CASE(EPI_GATE, 256)
   T2_CASE(EPI_RES, 128)
   T2_CASE(EPI_RES, 256)

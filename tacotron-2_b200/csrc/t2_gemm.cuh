@@ -63,7 +63,7 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kTilePitch = 256 + 16;              // bytes per staged row: 128 bf16 + 16 B pad (bank spread)
 constexpr int kTileBytes = 32 * kTilePitch;       // 8704
-constexpr int kEpiTilesPerWarp = 4;
+constexpr int kEpiTilesPerWarp = 2;          // dedicated staging (not aliased with the pipeline stages)
 constexpr int kEpiWarpBytes = kEpiTilesPerWarp * kTileBytes;
 
 constexpr int kActEpiWarps = 16;                               // 4 TMEM lane quarters x 4 column groups
@@ -209,9 +209,9 @@ struct Epilogue<EPI_GATE, 256> {
     __nv_bfloat16* ta_o = static_cast<__nv_bfloat16*>(e.ptr[0]);
     __nv_bfloat16* sb_o = static_cast<__nv_bfloat16*>(e.ptr[1]);
     __nv_bfloat16* z_o = static_cast<__nv_bfloat16*>(e.ptr[2]);
-    uint8_t* t_ta = c.wbuf;
-    uint8_t* t_sb = c.wbuf + kTileBytes;
-    uint8_t* t_z = c.wbuf + 2 * kTileBytes;
+    uint8_t* t0 = c.wbuf;
+    uint8_t* t1 = c.wbuf + kTileBytes;
+    const size_t off = c.row0 * Gh + cb;
     {
       const int cq = c.cg;
       float a[32], g[32], ba[32], bb[32];
@@ -221,20 +221,20 @@ struct Epilogue<EPI_GATE, 256> {
       tmem_ld32f(c.trow + 128 + cq * 32, g);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        a[j] = tanhf_(a[j] + ba[j]);
-        g[j] = sigmoidf_(g[j] + bb[j]);
+        a[j] = tanh_approx_(a[j] + ba[j]);
+        g[j] = sigmoid_approx_(g[j] + bb[j]);
       }
-      if (ta_o) { stage_put(t_ta, c.lane, cq, a); stage_put(t_sb, c.lane, cq, g); }
+      if (ta_o) stage_put(t0, c.lane, cq, a);
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] *= g[j];
-      stage_put(t_z, c.lane, cq, a);
+      stage_put(t1, c.lane, cq, a);
+      if (ta_o) {
+        tile_flush<4>(t0, ta_o + off, Gh, c.nrows, c);
+        stage_put(t0, c.lane, cq, g);
+        tile_flush<4>(t0, sb_o + off, Gh, c.nrows, c);
+      }
     }
-    const size_t off = c.row0 * Gh + cb;
-    if (ta_o) {
-      tile_flush<4>(t_ta, ta_o + off, Gh, c.nrows, c);
-      tile_flush<4>(t_sb, sb_o + off, Gh, c.nrows, c);
-    }
-    tile_flush<4>(t_z, z_o + off, Gh, c.nrows, c);
+    tile_flush<4>(t1, z_o + off, Gh, c.nrows, c);
   }
 };
 
@@ -257,7 +257,6 @@ struct Epilogue<EPI_RES, BN> {
     const size_t row = (size_t(c.b) * c.T + c.t) * R;
     uint8_t* t_x = c.wbuf;
     uint8_t* t_o = c.wbuf + kTileBytes;
-    uint8_t* t_d = c.wbuf + 2 * kTileBytes;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
       tile_fill<4>(t_x, x_in + c.row0 * R + gq * 128, R, c.nrows, c);
@@ -271,15 +270,19 @@ struct Epilogue<EPI_RES, BN> {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + bv[j] + x[j]) * rs;
         stage_put(t_o, c.lane, cq, acc);
+        tile_flush<4>(t_o, x_out + c.row0 * R + gq * 128, R, c.nrows, c);
         if (xd_out) {
+          const uint32_t thr = uint32_t(p * 65536.f);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            acc[j] = (hash_uniform32(hs, row + j0 + j) >= p) ? acc[j] * keep_inv : 0.f;
-          stage_put(t_d, c.lane, cq, acc);
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t h = hash_bits32(hs, (row + j0 + j) >> 1);
+            acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
+            acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
+          }
+          stage_put(t_o, c.lane, cq, acc);
+          tile_flush<4>(t_o, xd_out + c.row0 * R + gq * 128, R, c.nrows, c);
         }
       }
-      tile_flush<4>(t_o, x_out + c.row0 * R + gq * 128, R, c.nrows, c);
-      if (xd_out) tile_flush<4>(t_d, xd_out + c.row0 * R + gq * 128, R, c.nrows, c);
     }
   }
 };
@@ -560,43 +563,41 @@ struct Epilogue<EPI_GATE_BWD, BN> {
     const __nv_bfloat16* ta = static_cast<const __nv_bfloat16*>(e.ptr[0]);
     const __nv_bfloat16* sb = static_cast<const __nv_bfloat16*>(e.ptr[1]);
     __nv_bfloat16* dg = static_cast<__nv_bfloat16*>(e.ptr[2]);
-    uint8_t* t_a = c.wbuf;
-    uint8_t* t_s = c.wbuf + kTileBytes;
-    uint8_t* t_da = c.wbuf + 2 * kTileBytes;
-    uint8_t* t_db = c.wbuf + 3 * kTileBytes;
+    uint8_t* t0 = c.wbuf;
+    uint8_t* t1 = c.wbuf + kTileBytes;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
       const int cb = c.n_tile * BN + gq * 128;
-      tile_fill<4>(t_a, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
-      tile_fill<4>(t_s, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
-      {
-        const int cq = c.cg;
-        float dz[32], a[32], s[32];
-        tmem_ld32f(c.trow + gq * 128 + cq * 32, dz);
-        stage_get(t_a, c.lane, cq, a);
-        stage_get(t_s, c.lane, cq, s);
+      const int cq = c.cg;
+      float dz[32], a[32], s[32];
+      tile_fill<4>(t0, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
+      stage_get(t0, c.lane, cq, a);
+      quarter_sync(c.qbar);   // everyone has read ta before the tile is refilled with sb
+      tile_fill<4>(t0, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
+      stage_get(t0, c.lane, cq, s);
+      tmem_ld32f(c.trow + gq * 128 + cq * 32, dz);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float da = dz[j] * (1.f - a[j] * a[j]) * s[j];
-          const float db = dz[j] * a[j] * s[j] * (1.f - s[j]);
-          a[j] = da;
-          s[j] = db;
-        }
-        stage_put(t_da, c.lane, cq, a);
-        stage_put(t_db, c.lane, cq, s);
-        if (e.ptr[3]) {
-          const float ca = warp_colsum32(a, c.lane), cb2 = warp_colsum32(s, c.lane);
-          const int col = cb + cq * 32 + colsum32_col(c.lane);
-          atomicAdd(static_cast<float*>(e.ptr[3]) + col, ca);
-          atomicAdd(static_cast<float*>(e.ptr[3]) + Gh + col, cb2);
-          if (e.ptr[4]) {
-            atomicAdd(static_cast<float*>(e.ptr[4]) + col, ca);
-            atomicAdd(static_cast<float*>(e.ptr[4]) + Gh + col, cb2);
-          }
+      for (int j = 0; j < 32; ++j) {
+        const float da = dz[j] * (1.f - a[j] * a[j]) * s[j];
+        const float db = dz[j] * a[j] * s[j] * (1.f - s[j]);
+        a[j] = da;
+        s[j] = db;
+      }
+      stage_put(t1, c.lane, cq, a);
+      tile_flush<4>(t1, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
+      stage_put(t1, c.lane, cq, s);
+      tile_flush<4>(t1, dg + c.row0 * 2 * Gh + Gh + cb, 2 * Gh, c.nrows, c);
+      if (e.ptr[3]) {
+        const float ca = warp_colsum32(a, c.lane), cb2 = warp_colsum32(s, c.lane);
+        const int col = cb + cq * 32 + colsum32_col(c.lane);
+        atomicAdd(static_cast<float*>(e.ptr[3]) + col, ca);
+        atomicAdd(static_cast<float*>(e.ptr[3]) + Gh + col, cb2);
+        if (e.ptr[4]) {
+          atomicAdd(static_cast<float*>(e.ptr[4]) + col, ca);
+          atomicAdd(static_cast<float*>(e.ptr[4]) + Gh + col, cb2);
         }
       }
-      tile_flush<4>(t_da, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
-      tile_flush<4>(t_db, dg + c.row0 * 2 * Gh + Gh + cb, 2 * Gh, c.nrows, c);
+      quarter_sync(c.qbar);   // t0 is refilled by the next column group
     }
   }
 };
@@ -627,9 +628,13 @@ struct Epilogue<EPI_DX, BN> {
         float acc[32], g[32];
         tmem_ld32f(c.trow + j0, acc);
         if (p > 0.f) {
+          const uint32_t thr = uint32_t(p * 65536.f);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            acc[j] = (hash_uniform32(hs, row + j0 + j) >= p) ? acc[j] * keep_inv : 0.f;
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t h = hash_bits32(hs, (row + j0 + j) >> 1);
+            acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
+            acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
+          }
         }
         if (dxo) {
           stage_get(t_g, c.lane, cq, g);
@@ -762,24 +767,29 @@ struct ActGemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;   // 16 KB
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : 6;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(BN < 128 || kStages * kStageBytes >= 4 * kEpiWarpBytes, "epilogue staging must fit in the pipeline stages");
+  static constexpr int kStages = (BN >= 256) ? 3 : 4;
+  static constexpr int kStagingBytes = 4 * kEpiWarpBytes;      // 4 lane quarters x 2 tiles, never aliased with the stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int EPI, int BN>
+// NT = output column tiles processed by one CTA, each with its own TMEM accumulator: the epilogue of tile h overlaps
+// the MMAs of tile h+1 (used by the gate GEMM: 2 x 256 columns per CTA -> 120 CTAs, one wave, instead of 240)
+template <int EPI, int BN, int NT>
 __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __grid_constant__ GemmArgs g) {
   using Cfg = ActGemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;      // [NT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + NT);
+  constexpr int kTmemCols = (NT * BN) < 32 ? 32 : NT * BN;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
 
   const int warp = threadIdx.x >> 5;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int m_tile = blockIdx.x;
   long long* dbg = g.dbg ? g.dbg + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int b = m_tile / g.tiles_per_b;
@@ -798,11 +808,11 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
-      mbar_init(tmem_full, 1);
+      for (int i = 0; i < NT; ++i) mbar_init(&tmem_full[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tmem_alloc<kTmemCols>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -814,19 +824,22 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      int kb_global = 0;
-      for (int s = 0; s < g.nseg; ++s) {
-        const Seg sg = g.seg[s];
-        for (int l = 0; l < sg.nlayers; ++l) {
-          for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            uint8_t* sb = sa + Cfg::kABytes;
-            tma_load_4d(sa, &g.amap[sg.map], &full_bar[stage], sg.k0 + kb * kBK, t0 + sg.shift, b,
-                        sg.layer0 + l);
-            tma_load_3d(sb, &g.bmap, &full_bar[stage], g.b_k0 + kb_global * kBK, n_tile * BN, g.b_layer);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      for (int h = 0; h < NT; ++h) {
+        const int n_tile = blockIdx.y * NT + h;
+        int kb_global = 0;
+        for (int s = 0; s < g.nseg; ++s) {
+          const Seg sg = g.seg[s];
+          for (int l = 0; l < sg.nlayers; ++l) {
+            for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              uint8_t* sa = smem + stage * Cfg::kStageBytes;
+              uint8_t* sb = sa + Cfg::kABytes;
+              tma_load_4d(sa, &g.amap[sg.map], &full_bar[stage], sg.k0 + kb * kBK, t0 + sg.shift, b,
+                          sg.layer0 + l);
+              tma_load_3d(sb, &g.bmap, &full_bar[stage], g.b_k0 + kb_global * kBK, n_tile * BN, g.b_layer);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -836,25 +849,28 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN < 16 ? 16 : BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (dbg && kb == 0) dbg[2] = clock64();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
-        const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
-        const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
+      for (int h = 0; h < NT; ++h) {
+        const uint32_t tmem_d = tmem_base + uint32_t(h * BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (dbg && kb == 0 && h == 0) dbg[2] = clock64();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field
-          umma_f16(tmem_base, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
-                   (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr>>4) field
+            umma_f16(tmem_d, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (dbg && h == NT - 1) dbg[3] = clock64();
+        umma_commit(&tmem_full[h]);
       }
-      if (dbg) dbg[3] = clock64();
-      umma_commit(tmem_full);
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -862,28 +878,32 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     c.lane = threadIdx.x & 31;
     c.cg = (warp - 2) >> 2;
     c.qbar = 1 + q;
-    c.n_tile = n_tile; c.b = b; c.T = g.T;
+    c.b = b; c.T = g.T;
     const int tw = t0 + q * 32;          // first time step of this warp
     c.t = tw + c.lane;
     c.valid = c.t < g.T;
     c.row0 = size_t(b) * g.T + tw;
     c.nrows = g.T - tw < 0 ? 0 : (g.T - tw > 32 ? 32 : g.T - tw);
-    c.wbuf = smem + q * kEpiWarpBytes;
-    c.smem_all = smem;
+    c.wbuf = staging + q * kEpiWarpBytes;
+    c.smem_all = staging;
     c.m_tile = m_tile;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    c.trow = tmem_base + (uint32_t(q * 32) << 16);
-    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
-    Epilogue<EPI, BN>::run(g.epi, c);
-    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
+#pragma unroll 1
+    for (int h = 0; h < NT; ++h) {
+      c.n_tile = blockIdx.y * NT + h;
+      mbar_wait(&tmem_full[h], 0);
+      tc_fence_after();
+      c.trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(h * BN);
+      if (dbg && threadIdx.x == 64 && h == 0) dbg[4] = clock64();
+      Epilogue<EPI, BN>::run(g.epi, c);
+      if (dbg && threadIdx.x == 64 && h == NT - 1) dbg[5] = clock64();
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[6] = clock64();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 

@@ -379,7 +379,7 @@ __global__ void first_conv_kernel(const void* __restrict__ xin, int scalar_in, c
   x[e] = __float2bfloat16(v);
   if (xd != x && xd != nullptr) {
     const float keep_inv = 1.f / (1.f - p);
-    xd[e] = __float2bfloat16(hash_uniform32(hash_seed(seed, 0u), (unsigned long long)e) >= p ? v * keep_inv : 0.f);
+    xd[e] = __float2bfloat16(hash_keep16(hash_seed(seed, 0u), (unsigned long long)e, uint32_t(p * 65536.f)) ? v * keep_inv : 0.f);
   }
 }
 __global__ void first_conv_bwd_kernel(const void* __restrict__ xin, int scalar_in, const bf16* __restrict__ dx0,
