@@ -197,6 +197,10 @@ __device__ __forceinline__ int colsum32_col(int lane) {
 template <int EPI, int BN>
 struct Epilogue;
 
+// epilogues whose inputs can be loaded while the mainloop is still running define prefetch(); others do not
+template <int EPI>
+struct EpiHasPrefetch { static constexpr bool value = EPI == EPI_RES || EPI == EPI_SCALE_RELUMASK || EPI == EPI_GATE_BWD || EPI == EPI_DX; };
+
 // tanh/sigmoid gate of ResidualConv1DGLU (wavenet_vocoder/models/modules.py:494-510).
 // tile columns [0,128) = 'a' (tanh) channels cb..cb+127, [128,256) = 'b' (sigmoid) channels.
 // ptr: 0 ta_out, 1 sb_out, 2 z_out (bf16 [pos, Gh]), 3 bias fp32 [2*Gh];  i0 = Gh
@@ -244,9 +248,15 @@ struct Epilogue<EPI_GATE, 256> {
 // replayed CUDA graph draw fresh masks);  f0 res_scale, f1 dropout p;  i1 = layer
 template <int BN>
 struct Epilogue<EPI_RES, BN> {
+  // the x tiles (residual input) do not depend on this kernel's MMAs: load them while the mainloop runs
+  static __device__ __forceinline__ void prefetch(const EpiArgs& e, const EpiCtx& c) {
+    const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
+#pragma unroll
+    for (int gq = 0; gq < BN / 128; ++gq)
+      tile_fill<4>(c.wbuf + gq * kTileBytes, x_in + c.row0 * BN + gq * 128, BN, c.nrows, c);
+  }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int R = BN;
-    const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
     __nv_bfloat16* x_out = static_cast<__nv_bfloat16*>(e.ptr[1]);
     __nv_bfloat16* xd_out = static_cast<__nv_bfloat16*>(e.ptr[2]);
     const float* bias = static_cast<const float*>(e.ptr[3]);
@@ -255,33 +265,29 @@ struct Epilogue<EPI_RES, BN> {
     const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
     const uint32_t hs = hash_seed(seed, uint32_t(e.i[1]));
     const size_t row = (size_t(c.b) * c.T + c.t) * R;
-    uint8_t* t_x = c.wbuf;
-    uint8_t* t_o = c.wbuf + kTileBytes;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
-      tile_fill<4>(t_x, x_in + c.row0 * R + gq * 128, R, c.nrows, c);
-      {
-        const int cq = c.cg;
-        const int j0 = gq * 128 + cq * 32;
-        float acc[32], x[32], bv[32];
-        load_f32x32(bias + j0, bv);
-        tmem_ld32f(c.trow + j0, acc);
-        stage_get(t_x, c.lane, cq, x);
+      uint8_t* tile = c.wbuf + gq * kTileBytes;   // holds x on entry, reused in place for the outputs
+      const int cq = c.cg;
+      const int j0 = gq * 128 + cq * 32;
+      float acc[32], x[32], bv[32];
+      load_f32x32(bias + j0, bv);
+      tmem_ld32f(c.trow + j0, acc);
+      stage_get(tile, c.lane, cq, x);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + bv[j] + x[j]) * rs;
-        stage_put(t_o, c.lane, cq, acc);
-        tile_flush<4>(t_o, x_out + c.row0 * R + gq * 128, R, c.nrows, c);
-        if (xd_out) {
-          const uint32_t thr = uint32_t(p * 65536.f);
+      for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + bv[j] + x[j]) * rs;
+      stage_put(tile, c.lane, cq, acc);      // same rows/columns this lane just read
+      tile_flush<4>(tile, x_out + c.row0 * R + gq * 128, R, c.nrows, c);
+      if (xd_out) {
+        const uint32_t thr = uint32_t(p * 65536.f);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const uint32_t h = hash_bits32(hs, (row + j0 + j) >> 1);
-            acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
-            acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
-          }
-          stage_put(t_o, c.lane, cq, acc);
-          tile_flush<4>(t_o, xd_out + c.row0 * R + gq * 128, R, c.nrows, c);
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t h = hash_bits32(hs, (row + j0 + j) >> 1);
+          acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
+          acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
         }
+        stage_put(tile, c.lane, cq, acc);
+        tile_flush<4>(tile, xd_out + c.row0 * R + gq * 128, R, c.nrows, c);
       }
     }
   }
@@ -524,32 +530,34 @@ struct Epilogue<EPI_MOL, 32> {
 //      3 fp32 [ldo] column sums of `out` accumulated with atomics (nullable: bias gradient);  f0 const scale; i0 = ldo
 template <int BN>
 struct Epilogue<EPI_SCALE_RELUMASK, BN> {
+  static __device__ __forceinline__ void prefetch(const EpiArgs& e, const EpiCtx& c) {
+    const int ldo = e.i[0];
+    const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(e.ptr[1]);
+#pragma unroll
+    for (int gq = 0; gq < BN / 128; ++gq)
+      tile_fill<4>(c.wbuf + gq * kTileBytes, h + c.row0 * ldo + size_t(c.n_tile) * BN + gq * 128, ldo, c.nrows, c);
+  }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int ldo = e.i[0];
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.ptr[0]);
-    const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(e.ptr[1]);
     float s = e.f[0];
     if (e.ptr[2]) s /= fmaxf(__ldg(static_cast<const float*>(e.ptr[2])), 1e-20f);
-    uint8_t* t_h = c.wbuf;
-    uint8_t* t_o = c.wbuf + kTileBytes;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
       const size_t off = c.row0 * ldo + size_t(c.n_tile) * BN + gq * 128;
-      tile_fill<4>(t_h, h + off, ldo, c.nrows, c);
-      {
-        const int cq = c.cg;
-        float acc[32], hv[32];
-        tmem_ld32f(c.trow + gq * 128 + cq * 32, acc);
-        stage_get(t_h, c.lane, cq, hv);
+      uint8_t* tile = c.wbuf + gq * kTileBytes;
+      const int cq = c.cg;
+      float acc[32], hv[32];
+      tmem_ld32f(c.trow + gq * 128 + cq * 32, acc);
+      stage_get(tile, c.lane, cq, hv);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = hv[j] > 0.f ? acc[j] * s : 0.f;
-        stage_put(t_o, c.lane, cq, acc);
-        if (e.ptr[3]) {
-          const float cs = warp_colsum32(acc, c.lane);
-          atomicAdd(static_cast<float*>(e.ptr[3]) + c.n_tile * BN + gq * 128 + cq * 32 + colsum32_col(c.lane), cs);
-        }
+      for (int j = 0; j < 32; ++j) acc[j] = hv[j] > 0.f ? acc[j] * s : 0.f;
+      stage_put(tile, c.lane, cq, acc);
+      tile_flush<4>(tile, out + off, ldo, c.nrows, c);
+      if (e.ptr[3]) {
+        const float cs = warp_colsum32(acc, c.lane);
+        atomicAdd(static_cast<float*>(e.ptr[3]) + c.n_tile * BN + gq * 128 + cq * 32 + colsum32_col(c.lane), cs);
       }
-      tile_flush<4>(t_o, out + off, ldo, c.nrows, c);
     }
   }
 };
@@ -558,6 +566,12 @@ struct Epilogue<EPI_SCALE_RELUMASK, BN> {
 // gate-bias gradients (column sums of dg, atomics; nullable — dilated-conv bias and cin-conv bias get the same sum); i0 = Gh
 template <int BN>
 struct Epilogue<EPI_GATE_BWD, BN> {
+  static __device__ __forceinline__ void prefetch(const EpiArgs& e, const EpiCtx& c) {
+    const int Gh = e.i[0];
+    const int cb = c.n_tile * BN;
+    tile_fill<4>(c.wbuf, static_cast<const __nv_bfloat16*>(e.ptr[0]) + c.row0 * Gh + cb, Gh, c.nrows, c);
+    tile_fill<4>(c.wbuf + kTileBytes, static_cast<const __nv_bfloat16*>(e.ptr[1]) + c.row0 * Gh + cb, Gh, c.nrows, c);
+  }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int Gh = e.i[0];
     const __nv_bfloat16* ta = static_cast<const __nv_bfloat16*>(e.ptr[0]);
@@ -570,11 +584,12 @@ struct Epilogue<EPI_GATE_BWD, BN> {
       const int cb = c.n_tile * BN + gq * 128;
       const int cq = c.cg;
       float dz[32], a[32], s[32];
-      tile_fill<4>(t0, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
+      if (gq > 0) {   // group 0 was prefetched during the mainloop
+        tile_fill<4>(t0, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
+        tile_fill<4>(t1, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
+      }
       stage_get(t0, c.lane, cq, a);
-      quarter_sync(c.qbar);   // everyone has read ta before the tile is refilled with sb
-      tile_fill<4>(t0, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
-      stage_get(t0, c.lane, cq, s);
+      stage_get(t1, c.lane, cq, s);
       tmem_ld32f(c.trow + gq * 128 + cq * 32, dz);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -583,9 +598,9 @@ struct Epilogue<EPI_GATE_BWD, BN> {
         a[j] = da;
         s[j] = db;
       }
-      stage_put(t1, c.lane, cq, a);
-      tile_flush<4>(t1, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
+      stage_put(t0, c.lane, cq, a);     // in place: this lane's own rows / columns
       stage_put(t1, c.lane, cq, s);
+      tile_flush<4>(t0, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
       tile_flush<4>(t1, dg + c.row0 * 2 * Gh + Gh + cb, 2 * Gh, c.nrows, c);
       if (e.ptr[3]) {
         const float ca = warp_colsum32(a, c.lane), cb2 = warp_colsum32(s, c.lane);
@@ -597,7 +612,6 @@ struct Epilogue<EPI_GATE_BWD, BN> {
           atomicAdd(static_cast<float*>(e.ptr[4]) + Gh + col, cb2);
         }
       }
-      quarter_sync(c.qbar);   // t0 is refilled by the next column group
     }
   }
 };
@@ -608,6 +622,13 @@ struct Epilogue<EPI_GATE_BWD, BN> {
 // f0 res_scale, f1 dropout p, f2 bias-gradient scale; i1 = layer
 template <int BN>
 struct Epilogue<EPI_DX, BN> {
+  static __device__ __forceinline__ void prefetch(const EpiArgs& e, const EpiCtx& c) {
+    const __nv_bfloat16* dxo = static_cast<const __nv_bfloat16*>(e.ptr[0]);
+    if (!dxo) return;
+#pragma unroll
+    for (int gq = 0; gq < BN / 128; ++gq)
+      tile_fill<4>(c.wbuf + gq * kTileBytes, dxo + c.row0 * BN + gq * 128, BN, c.nrows, c);
+  }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int R = BN;
     const __nv_bfloat16* dxo = static_cast<const __nv_bfloat16*>(e.ptr[0]);
@@ -617,37 +638,33 @@ struct Epilogue<EPI_DX, BN> {
     const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
     const uint32_t hs = hash_seed(seed, uint32_t(e.i[1]));
     const size_t row = (size_t(c.b) * c.T + c.t) * R;
-    uint8_t* t_g = c.wbuf;
-    uint8_t* t_o = c.wbuf + kTileBytes;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
-      if (dxo) tile_fill<4>(t_g, dxo + c.row0 * R + gq * 128, R, c.nrows, c);
-      {
-        const int cq = c.cg;
-        const int j0 = gq * 128 + cq * 32;
-        float acc[32], g[32];
-        tmem_ld32f(c.trow + j0, acc);
-        if (p > 0.f) {
-          const uint32_t thr = uint32_t(p * 65536.f);
+      uint8_t* tile = c.wbuf + gq * kTileBytes;
+      const int cq = c.cg;
+      const int j0 = gq * 128 + cq * 32;
+      float acc[32], g[32];
+      tmem_ld32f(c.trow + j0, acc);
+      if (p > 0.f) {
+        const uint32_t thr = uint32_t(p * 65536.f);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const uint32_t h = hash_bits32(hs, (row + j0 + j) >> 1);
-            acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
-            acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
-          }
-        }
-        if (dxo) {
-          stage_get(t_g, c.lane, cq, g);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] += rs * g[j];
-        }
-        stage_put(t_o, c.lane, cq, acc);
-        if (e.ptr[2]) {
-          const float cs = warp_colsum32(acc, c.lane);
-          atomicAdd(static_cast<float*>(e.ptr[2]) + j0 + colsum32_col(c.lane), cs * e.f[2]);
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t h = hash_bits32(hs, (row + j0 + j) >> 1);
+          acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
+          acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
         }
       }
-      tile_flush<4>(t_o, dx + c.row0 * R + gq * 128, R, c.nrows, c);
+      if (dxo) {
+        stage_get(tile, c.lane, cq, g);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += rs * g[j];
+      }
+      stage_put(tile, c.lane, cq, acc);
+      tile_flush<4>(tile, dx + c.row0 * R + gq * 128, R, c.nrows, c);
+      if (e.ptr[2]) {
+        const float cs = warp_colsum32(acc, c.lane);
+        atomicAdd(static_cast<float*>(e.ptr[2]) + j0 + colsum32_col(c.lane), cs * e.f[2]);
+      }
     }
   }
 };
@@ -887,6 +904,10 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     c.wbuf = staging + q * kEpiWarpBytes;
     c.smem_all = staging;
     c.m_tile = m_tile;
+    if constexpr (EpiHasPrefetch<EPI>::value && NT == 1) {
+      c.n_tile = blockIdx.y;
+      Epilogue<EPI, BN>::prefetch(g.epi, c);
+    }
 #pragma unroll 1
     for (int h = 0; h < NT; ++h) {
       c.n_tile = blockIdx.y * NT + h;

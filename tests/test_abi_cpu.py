@@ -1,0 +1,77 @@
+"""CPU-side checks of the C-ABI: the in-tree library loads, exports every function include/t2b200.h declares, reports
+errors through return codes (no GPU compute is launched here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "t2b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(t2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from t2_import import t2
+    lib = t2.lib.load()
+    names = _declared()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.t2_abi_version() == 1
+
+
+def test_errors_are_return_codes_with_messages():
+    from t2_import import t2
+    lib = t2.lib.load()
+    lib.t2_last_error.restype = ctypes.c_char_p
+    cfg = t2.wavenet.WnConfig()          # all zeros: invalid
+    sz = t2.wavenet.WnSizes()
+    rc = lib.t2_wn_sizes(ctypes.byref(cfg), ctypes.byref(sz))
+    assert rc < 0 and len(lib.t2_last_error()) > 0
+    with pytest.raises(t2.lib.T2Error):
+        t2.lib.check(rc)
+
+
+def test_layout_queries_match_the_oracle_parameter_tables():
+    """host logic without a GPU: the C++ layout enumerates the same (name, shape) list as the oracle"""
+    from hparams import hparams, paper_hparams
+    from oracle import tacotron as ot
+    from oracle import wavenet as ow
+    from t2_import import t2
+    lib = t2.lib.load()
+    hp = paper_hparams()
+    hp.parse("input_type=mulaw-quantize,quantize_channels=256,out_channels=256,upsample_type=SubPixel,upsample_scales=[11,25]")
+    cfg = t2.wavenet.make_config(hp, 2, 275 * 4)
+    sz = t2.wavenet.WnSizes()
+    t2.lib.check(lib.t2_wn_sizes(ctypes.byref(cfg), ctypes.byref(sz)))
+    name = ctypes.create_string_buffer(160)
+    off, nd, shp = ctypes.c_longlong(), ctypes.c_int(), (ctypes.c_int * 4)()
+    got = []
+    for i in range(sz.n_tensors):
+        t2.lib.check(lib.t2_wn_param_info(ctypes.byref(cfg), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp))
+        got.append((name.value.decode(), tuple(shp[k] for k in range(nd.value))))
+    assert got == [(k, tuple(v)) for k, v in ow.param_shapes(hp).items()]
+    hp2 = hparams.copy()
+    hp2.set_hparam("predict_linear", False)
+    tc = t2.tacotron.make_config(hp2, 4, 40, 80)
+    n, pb, wb, nt, tr = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+    t2.lib.check(lib.t2_taco_sizes(ctypes.byref(tc), ctypes.byref(n), ctypes.byref(pb), ctypes.byref(wb), ctypes.byref(nt)))
+    got = []
+    for i in range(nt.value):
+        t2.lib.check(lib.t2_taco_param_info(ctypes.byref(tc), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp, ctypes.byref(tr)))
+        got.append((name.value.decode(), tuple(shp[k] for k in range(nd.value)), bool(tr.value)))
+    assert got == [(k, tuple(v), ot.is_trainable(k)) for k, v in ot.param_shapes(hp2).items()]
+
+
+def test_product_path_has_no_oracle_import():
+    """the shipped package must never route through the CPU oracle"""
+    pkg = os.path.join(ROOT, "tacotron-2_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, f)).read(), f
+    assert "oracle" not in open(os.path.join(ROOT, "datasets", "audio.py")).read()
