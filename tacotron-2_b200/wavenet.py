@@ -109,7 +109,7 @@ class WaveNet(object):
 
     # ---- parameters --------------------------------------------------------------------------------------
     def load_params(self, params):
-        """params: {TF-style name: tensor in TF layout} (e.g. from oracle.wavenet.init_params)."""
+        """params: {TF-style name: tensor in TF layout}."""
         flat = torch.zeros(self.n_params, dtype=torch.float32)
         for name, off, shape in self.tensors:
             t = params[name].detach().to(torch.float32).reshape(-1)
