@@ -166,6 +166,20 @@ int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_params, const v
                      const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets,
                      const float* d_stop_targets, float* d_grads, unsigned long long seed,
                      const unsigned long long* d_step, void* stream);
+/* Free-running synthesis (TacoTestHelper, tacotron/models/helpers.py:6-59; tacotron.py:150-200 with is_training = False:
+ * inference batch-norm, deterministic zoneout blend, prenet dropout still on). cfg->T_out is max_iters (hparams.py:138).
+ *   t2_taco_infer_begin   encoder, zero decoder state, go frame
+ *   t2_taco_infer_steps   decoder steps [t_begin, t_end): each feeds back its own raw frame (helpers.py:56). The stop logit
+ *                         of step t is workspace "projection_rows"[t][b][num_mels]; the CALLER applies the stop rule
+ *                         (every row round(sigmoid) == 1, helpers.py:40-54; r = 1) between chunks - no host sync inside.
+ *   t2_taco_infer_finish  clip, postnet, residual over the first T_used frames; workspace "decoder_output" /
+ *                         "mel_outputs" are then COMPACT [B][T_used][num_mels], "stop_logits" [B][T_used]. */
+int t2_taco_infer_begin(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace,
+                        const int* d_inputs, const int* d_input_lengths, void* stream);
+int t2_taco_infer_steps(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace,
+                        const int* d_input_lengths, int t_begin, int t_end, unsigned long long seed, void* stream);
+int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, int T_used,
+                         void* stream);
 int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr,
                              long long* count, int* elem_bytes);
 

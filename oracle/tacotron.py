@@ -275,6 +275,59 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
             "alignments": torch.stack(aligns, dim=1)}
 
 
+def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=None):
+    """Free-running inference graph (tacotron.py:150-200 with is_training = is_evaluating = gta = False):
+    TacoTestHelper (helpers.py:6-59) feeds the last predicted frame back (raw, before clipping) and finishes after the
+    first step where round(sigmoid(stop)) is 1 for EVERY batch row (r = 1 makes stop_at_any irrelevant), or at
+    hparams.max_iters; batch-norm uses moving statistics, zoneout its deterministic blend, prenet dropout stays on
+    (prenet_masks[t] = list of per-layer masks to inject; None with rate 0). Stop output is the sigmoid (modules.py:340-342)."""
+    B, T_in = inputs.shape
+    D = hp.decoder_lstm_units
+    zr = hp.tacotron_zoneout_rate
+    max_iters = hp.max_iters if max_iters is None else max_iters
+    x = params["inputs_embedding"][inputs]
+    for i in range(hp.enc_conv_num_layers):
+        x = conv_block(x, params, "encoder_convolutions/conv_layer_%d/" % (i + 1), "relu", False, hp.tacotron_dropout_rate)
+    memory = encoder_rnn(x, input_lengths, params, hp, False)
+    mask = (torch.arange(T_in)[None, :] < input_lengths[:, None]).float()
+    values = memory * mask.unsqueeze(-1)
+    keys = values @ params["attention/memory_layer/kernel"]
+    c1 = torch.zeros(B, D); h1 = torch.zeros(B, D); c2 = torch.zeros(B, D); h2 = torch.zeros(B, D)
+    ctx = torch.zeros(B, values.shape[-1])
+    cum = torch.zeros(B, T_in)
+    K1, b1 = params["decoder_LSTM/cell_1/kernel"], params["decoder_LSTM/cell_1/bias"]
+    K2, b2 = params["decoder_LSTM/cell_2/kernel"], params["decoder_LSTM/cell_2/bias"]
+    frame = torch.zeros(B, hp.num_mels)                                           # go frame
+    frames, stops, aligns = [], [], []
+    for t in range(max_iters):
+        pre = prenet(frame, params, hp, prenet_masks[t] if prenet_masks else None)
+        nc1, nh1 = lstm_cell(torch.cat([pre, ctx], dim=-1), c1, h1, K1, b1)
+        c1n, h1n = zoneout(c1, nc1, zr, False), zoneout(h1, nh1, zr, False)
+        nc2, nh2 = lstm_cell(nh1, c2, h2, K2, b2)
+        c2n, h2n = zoneout(c2, nc2, zr, False), zoneout(h2, nh2, zr, False)
+        c1, h1, c2, h2 = c1n, h1n, c2n, h2n
+        ctx, a = attention_step(nh2, cum, keys, values, mask, params)
+        cum = cum + a
+        pin = torch.cat([nh2, ctx], dim=-1)
+        frame = pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"]
+        stop = torch.sigmoid(pin @ params["stop_token_projection/kernel"] + params["stop_token_projection/bias"])
+        frames.append(frame); stops.append(stop); aligns.append(a)
+        if bool(torch.round(stop).bool().all()):
+            break
+    decoder_output = torch.stack(frames, dim=1)
+    if hp.clip_outputs:
+        decoder_output = torch.clamp(decoder_output, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+    y = decoder_output
+    for i in range(hp.postnet_num_layers):
+        act = "tanh" if i < hp.postnet_num_layers - 1 else None
+        y = conv_block(y, params, "postnet_convolutions/conv_layer_%d/" % (i + 1), act, False, hp.tacotron_dropout_rate)
+    mel_outputs = decoder_output + y @ params["postnet_projection/kernel"] + params["postnet_projection/bias"]
+    if hp.clip_outputs:
+        mel_outputs = torch.clamp(mel_outputs, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+    return {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_token_prediction": torch.stack(stops, dim=1).squeeze(-1),
+            "alignments": torch.stack(aligns, dim=1)}
+
+
 def loss_fn(out, mel_targets, stop_targets, params, hp):
     """tacotron.py:315-354 with mask_decoder=False: plain means over padded tensors + L2 regulariser."""
     before = F.mse_loss(out["decoder_output"], mel_targets)

@@ -563,12 +563,10 @@ __global__ void dec_finish_kernel(const float* __restrict__ projo, const float* 
       const float d = clip ? fminf(fmaxf(v, lo), hi) : v;
       const long long o = ((long long)b * To + t) * M + m;
       dec_bm[o] = __float2bfloat16(d); dec_f[o] = d;
-      const float df = d - tgt[o];
-      l0 = df * df;
+      if (tgt) { const float df = d - tgt[o]; l0 = df * df; }
     } else {
-      const float z = stop_tgt[(long long)b * To + t];
       stop[(long long)b * To + t] = v;
-      l2 = fmaxf(v, 0.f) - v * z + log1pf(__expf(-fabsf(v)));
+      if (stop_tgt) { const float z = stop_tgt[(long long)b * To + t]; l2 = fmaxf(v, 0.f) - v * z + log1pf(__expf(-fabsf(v))); }
     }
   }
   l0 = warp_sum(l0); l2 = warp_sum(l2);
@@ -584,8 +582,7 @@ __global__ void mel_finish_kernel(const float* __restrict__ dec_f, const float* 
     float v = dec_f[e] + resid[pos * 128 + m];
     if (clip) v = fminf(fmaxf(v, lo), hi);
     mel[e] = v;
-    const float d = v - tgt[e];
-    l = d * d;
+    if (tgt) { const float d = v - tgt[e]; l = d * d; }
   }
   l = warp_sum(l);
   if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(scal + 1, l);
@@ -1136,30 +1133,20 @@ extern "C" int t2_taco_pack_weights(const t2_taco_config_t* cfg, const float* d_
   return T2_OK;
 }
 
-// forward + losses. d_inputs int32 [B][T_in]; d_input_lengths int32 [B]; d_mel_targets fp32 [B][T_out][M];
-// d_stop_targets fp32 [B][T_out]. d_loss fp32[4] = {before, after, stop, regularisation} (already normalised).
-extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, const int* d_inputs,
-                               const int* d_input_lengths, const float* d_mel_targets, const float* d_stop_targets, float* d_loss,
-                               int training, unsigned long long seed, const unsigned long long* d_step, void* stream) {
-  TL lo;
-  int rc = build(cfg, lo, nullptr);
-  if (rc) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
-  const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
-  StepCtx s{&lo, ws, pk, d_params, st, seed, d_step, training};
-  const int B = lo.B, Ti = lo.Ti, To = lo.To, H = lo.H, D = lo.D;
-  float* scal = reinterpret_cast<float*>(ws + lo.w_scal);
-  T2_CHECK_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(float), st));
-  // ---- encoder ----
+// ---- encoder: embedding -> conv blocks -> BiLSTM -> masked values -> attention keys (tacotron.py:113-131) ----
+static int encoder_fwd(const StepCtx& s, const int* d_inputs, const int* d_input_lengths, int training) {
+  const TL& lo = *s.lo;
+  uint8_t* ws = s.ws; const uint8_t* pk = s.pk; const float* d_params = s.params; cudaStream_t st = s.st;
+  const int B = lo.B, Ti = lo.Ti, H = lo.H;
+  int rc;
   bf16* emb = reinterpret_cast<bf16*>(ws + lo.w_emb);
   embed_fwd_kernel<<<g1((long long)B * Ti * lo.E), 256, 0, st>>>(d_inputs, d_params + lo.p_emb, emb, (long long)B * Ti, lo.E); t2_count_launch();
   const void* x = emb;
   for (auto& L : lo.enc) { rc = conv_block_fwd(s, L, x, Ti, training); if (rc) return rc; x = ws + L.w_x; }
   for (int d = 0; d < 2; ++d) {
     float* pre = reinterpret_cast<float*>(ws + lo.w_encpre[d]);
-    rc = conv_gemm(x, lo.C, Ti, B, pk + lo.k_encWx[d], 4 * H, lo.C, 1, nullptr, 256, d_params + lo.p_elb[d], 0, nullptr, pre, 4 * H, 4 * H, 0.f, 0, 0,
-                   nullptr, st);
+    rc = conv_gemm(x, lo.C, Ti, B, pk + lo.k_encWx[d], 4 * H, lo.C, 1, nullptr, 256, const_cast<float*>(d_params) + lo.p_elb[d], 0, nullptr, pre, 4 * H,
+                   4 * H, 0.f, 0, 0, nullptr, st);
     if (rc) return rc;
     bf16* hh = reinterpret_cast<bf16*>(ws + lo.w_ench[d]);
     float* cc = reinterpret_cast<float*>(ws + lo.w_encc[d]);
@@ -1180,8 +1167,83 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   mask_values_kernel<<<g1((long long)B * Ti * 2 * H), 256, 0, st>>>(reinterpret_cast<bf16*>(ws + lo.w_memory), d_input_lengths, values, B, Ti, 2 * H);
   t2_count_launch();
   float* keys = reinterpret_cast<float*>(ws + lo.w_keys);
-  rc = conv_gemm(values, 2 * H, Ti, B, pk + lo.k_mem, lo.A, 2 * H, 1, nullptr, 128, nullptr, 0, nullptr, keys, lo.A, lo.A, 0.f, 0, 0, nullptr, st);
+  return conv_gemm(values, 2 * H, Ti, B, pk + lo.k_mem, lo.A, 2 * H, 1, nullptr, 128, nullptr, 0, nullptr, keys, lo.A, lo.A, 0.f, 0, 0, nullptr, st);
+}
+
+struct DecBufs { bf16 *S1, *S2, *PI, *values; float *c1, *c2, *cum, *attU, *keys, *pre1; size_t att_smem; int K1r, K2, PIK; };
+// zero initial decoder state (Architecture_wrappers.py:134-167) + the merged location filter bank
+static int decoder_reset(const StepCtx& s, DecBufs& d) {
+  const TL& lo = *s.lo;
+  uint8_t* ws = s.ws; const float* d_params = s.params; cudaStream_t st = s.st;
+  const int B = lo.B, Ti = lo.Ti, H = lo.H, D = lo.D;
+  d.K1r = 2 * H + D; d.K2 = 2 * D; d.PIK = D + 2 * H;
+  d.S1 = reinterpret_cast<bf16*>(ws + lo.w_S1); d.S2 = reinterpret_cast<bf16*>(ws + lo.w_S2); d.PI = reinterpret_cast<bf16*>(ws + lo.w_PI);
+  d.c1 = reinterpret_cast<float*>(ws + lo.w_c1); d.c2 = reinterpret_cast<float*>(ws + lo.w_c2);
+  d.cum = reinterpret_cast<float*>(ws + lo.w_cum); d.attU = reinterpret_cast<float*>(ws + lo.w_attU);
+  d.keys = reinterpret_cast<float*>(ws + lo.w_keys); d.values = reinterpret_cast<bf16*>(ws + lo.w_values);
+  d.pre1 = reinterpret_cast<float*>(ws + lo.w_pre1);
+  T2_CHECK_CUDA(cudaMemsetAsync(d.S1, 0, (size_t)B * d.K1r * 2, st));
+  T2_CHECK_CUDA(cudaMemsetAsync(d.S2, 0, (size_t)B * d.K2 * 2, st));
+  T2_CHECK_CUDA(cudaMemsetAsync(d.c1, 0, (size_t)B * D * 4, st));
+  T2_CHECK_CUDA(cudaMemsetAsync(d.c2, 0, (size_t)B * D * 4, st));
+  T2_CHECK_CUDA(cudaMemsetAsync(d.cum, 0, (size_t)B * Ti * 4, st));
+  att_prep_kernel<<<g1((lo.KA + 1) * lo.A), 256, 0, st>>>(d_params + lo.p_lck, d_params + lo.p_lcb, d_params + lo.p_lfl, d_params + lo.p_ba, d.attU,
+                                                       lo.KA, lo.F, lo.A); t2_count_launch();
+  d.att_smem = sizeof(float) * (size_t)((lo.KA + 1) * lo.A + Ti + lo.KA + 8 + lo.A + Ti + 4 + D + 8 * 2 * H + 32) + 64;
+  T2_CHECK_CUDA(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d.att_smem)));
+  T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+// decoder step t: LSTM-1 (prenet part of its gates precomputed in pre1[t]), LSTM-2, attention (Architecture_wrappers.py:169-213)
+static int decoder_step(const StepCtx& s, const DecBufs& d, const int* d_input_lengths, int t) {
+  const TL& lo = *s.lo;
+  uint8_t* ws = s.ws; const uint8_t* pk = s.pk; const float* d_params = s.params; cudaStream_t st = s.st;
+  const int B = lo.B, Ti = lo.Ti, H = lo.H, D = lo.D, K1r = d.K1r, K2 = d.K2, PIK = d.PIK;
+  bf16* S1t = d.S1 + (long long)t * B * K1r;
+  bf16* S1n = d.S1 + (long long)(t + 1) * B * K1r;
+  bf16* S2t = d.S2 + (long long)t * B * K2;
+  bf16* S2n = d.S2 + (long long)(t + 1) * B * K2;
+  bf16* PIt = d.PI + (long long)t * B * PIK;
+  // LSTM 1: state operand [ctx_{t-1} | h1_{t-1}], input part precomputed in pre1[t]
+  int rc = lstm_step(s, pk + lo.k_l1r, D, K1r, S1t, B, d.pre1 + (long long)t * B * 4 * D, 4 * D, nullptr, d.c1 + (long long)t * B * D,
+                     d.c1 + (long long)(t + 1) * B * D, S1t + 2 * H, K1r, S1n + 2 * H, K1r, S2t, K2,
+                     reinterpret_cast<bf16*>(ws + lo.w_g1) + (long long)t * B * 4 * D, reinterpret_cast<bf16*>(ws + lo.w_t1) + (long long)t * B * D,
+                     nullptr, t, 4, lo.c.zoneout_rate);
   if (rc) return rc;
+  // LSTM 2: state operand [h1out_t | h2_{t-1}]
+  rc = lstm_step(s, pk + lo.k_l2, D, K2, S2t, B, nullptr, 0, d_params + lo.p_l2b, d.c2 + (long long)t * B * D, d.c2 + (long long)(t + 1) * B * D,
+                 S2t + D, K2, S2n + D, K2, PIt, PIK, reinterpret_cast<bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D,
+                 reinterpret_cast<bf16*>(ws + lo.w_t2) + (long long)t * B * D, nullptr, t, 5, lo.c.zoneout_rate);
+  if (rc) return rc;
+  AttArgs a;
+  a.h2out = PIt; a.ld_h2 = PIK; a.WqT = reinterpret_cast<const bf16*>(pk + lo.k_qT);
+  a.U = d.attU; a.v = d_params + lo.p_v;
+  a.keys = d.keys; a.values = d.values; a.lens = d_input_lengths; a.cum = d.cum;
+  a.alpha = reinterpret_cast<float*>(ws + lo.w_alpha) + (long long)t * B * Ti;
+  a.ctx_a = S1n; a.ld_a = K1r; a.ctx_b = PIt + D; a.ld_b = PIK;
+  a.B = B; a.Ti = Ti; a.D = D; a.A = lo.A; a.KA = lo.KA; a.C2 = 2 * H;
+  att_fwd_kernel<<<B, kAttThreads, d.att_smem, st>>>(a); t2_count_launch();
+  return T2_OK;
+}
+
+// forward + losses. d_inputs int32 [B][T_in]; d_input_lengths int32 [B]; d_mel_targets fp32 [B][T_out][M];
+// d_stop_targets fp32 [B][T_out]. d_loss fp32[4] = {before, after, stop, regularisation} (already normalised).
+extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, const int* d_inputs,
+                               const int* d_input_lengths, const float* d_mel_targets, const float* d_stop_targets, float* d_loss,
+                               int training, unsigned long long seed, const unsigned long long* d_step, void* stream) {
+  TL lo;
+  int rc = build(cfg, lo, nullptr);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
+  StepCtx s{&lo, ws, pk, d_params, st, seed, d_step, training};
+  const int B = lo.B, Ti = lo.Ti, To = lo.To, H = lo.H, D = lo.D;
+  float* scal = reinterpret_cast<float*>(ws + lo.w_scal);
+  T2_CHECK_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(float), st));
+  rc = encoder_fwd(s, d_inputs, d_input_lengths, training);
+  if (rc) return rc;
+  const void* x = nullptr;
   // ---- decoder: everything that does not depend on the recurrence is batched over time (teacher forcing) ----
   bf16* decin = reinterpret_cast<bf16*>(ws + lo.w_decin);
   decin_kernel<<<g1((long long)To * B * lo.M), 256, 0, st>>>(d_mel_targets, decin, B, To, lo.M); t2_count_launch();
@@ -1198,49 +1260,12 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   rc = conv_gemm(pn2, lo.P2, TB, 1, pk + lo.k_l1x, 4 * D, lo.P2, 1, nullptr, 256, d_params + lo.p_l1b, 0, nullptr, pre1, 4 * D, 4 * D, 0.f, 0, 0,
                  nullptr, st);
   if (rc) return rc;
-  const int K1r = 2 * H + D, K2 = 2 * D, PIK = D + 2 * H;
-  bf16* S1 = reinterpret_cast<bf16*>(ws + lo.w_S1);
-  bf16* S2 = reinterpret_cast<bf16*>(ws + lo.w_S2);
-  bf16* PI = reinterpret_cast<bf16*>(ws + lo.w_PI);
-  float* c1 = reinterpret_cast<float*>(ws + lo.w_c1);
-  float* c2 = reinterpret_cast<float*>(ws + lo.w_c2);
-  T2_CHECK_CUDA(cudaMemsetAsync(S1, 0, (size_t)B * K1r * 2, st));
-  T2_CHECK_CUDA(cudaMemsetAsync(S2, 0, (size_t)B * K2 * 2, st));
-  T2_CHECK_CUDA(cudaMemsetAsync(c1, 0, (size_t)B * D * 4, st));
-  T2_CHECK_CUDA(cudaMemsetAsync(c2, 0, (size_t)B * D * 4, st));
-  float* cum = reinterpret_cast<float*>(ws + lo.w_cum);
-  T2_CHECK_CUDA(cudaMemsetAsync(cum, 0, (size_t)B * Ti * 4, st));
-  float* attU = reinterpret_cast<float*>(ws + lo.w_attU);
-  att_prep_kernel<<<g1((lo.KA + 1) * lo.A), 256, 0, st>>>(d_params + lo.p_lck, d_params + lo.p_lcb, d_params + lo.p_lfl, d_params + lo.p_ba, attU,
-                                                       lo.KA, lo.F, lo.A); t2_count_launch();
-  const size_t att_smem = sizeof(float) * (size_t)((lo.KA + 1) * lo.A + Ti + lo.KA + 8 + lo.A + Ti + 4 + D + 8 * 2 * H + 32) + 64;
-  T2_CHECK_CUDA(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(att_smem)));
-  for (int t = 0; t < To; ++t) {
-    bf16* S1t = S1 + (long long)t * B * K1r;
-    bf16* S1n = S1 + (long long)(t + 1) * B * K1r;
-    bf16* S2t = S2 + (long long)t * B * K2;
-    bf16* S2n = S2 + (long long)(t + 1) * B * K2;
-    bf16* PIt = PI + (long long)t * B * PIK;
-    // LSTM 1: state operand [ctx_{t-1} | h1_{t-1}], input part precomputed in pre1[t]
-    rc = lstm_step(s, pk + lo.k_l1r, D, K1r, S1t, B, pre1 + (long long)t * B * 4 * D, 4 * D, nullptr, c1 + (long long)t * B * D,
-                   c1 + (long long)(t + 1) * B * D, S1t + 2 * H, K1r, S1n + 2 * H, K1r, S2t, K2,
-                   reinterpret_cast<bf16*>(ws + lo.w_g1) + (long long)t * B * 4 * D, reinterpret_cast<bf16*>(ws + lo.w_t1) + (long long)t * B * D,
-                   nullptr, t, 4, lo.c.zoneout_rate);
-    if (rc) return rc;
-    // LSTM 2: state operand [h1out_t | h2_{t-1}]
-    rc = lstm_step(s, pk + lo.k_l2, D, K2, S2t, B, nullptr, 0, d_params + lo.p_l2b, c2 + (long long)t * B * D, c2 + (long long)(t + 1) * B * D,
-                   S2t + D, K2, S2n + D, K2, PIt, PIK, reinterpret_cast<bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D,
-                   reinterpret_cast<bf16*>(ws + lo.w_t2) + (long long)t * B * D, nullptr, t, 5, lo.c.zoneout_rate);
-    if (rc) return rc;
-    AttArgs a;
-    a.h2out = PIt; a.ld_h2 = PIK; a.WqT = reinterpret_cast<const bf16*>(pk + lo.k_qT);
-    a.U = attU; a.v = d_params + lo.p_v;
-    a.keys = keys; a.values = values; a.lens = d_input_lengths; a.cum = cum;
-    a.alpha = reinterpret_cast<float*>(ws + lo.w_alpha) + (long long)t * B * Ti;
-    a.ctx_a = S1n; a.ld_a = K1r; a.ctx_b = PIt + D; a.ld_b = PIK;
-    a.B = B; a.Ti = Ti; a.D = D; a.A = lo.A; a.KA = lo.KA; a.C2 = 2 * H;
-    att_fwd_kernel<<<B, kAttThreads, att_smem, st>>>(a); t2_count_launch();
-  }
+  const int PIK = D + 2 * H;
+  DecBufs db;
+  rc = decoder_reset(s, db);
+  if (rc) return rc;
+  bf16* PI = db.PI;
+  for (int t = 0; t < To; ++t) { rc = decoder_step(s, db, d_input_lengths, t); if (rc) return rc; }
   T2_CHECK_CUDA(cudaGetLastError());
   // frame + stop projections for all steps at once
   float* projo = reinterpret_cast<float*>(ws + lo.w_projo);
@@ -1273,6 +1298,122 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   return T2_OK;
 }
 
+// ======================================================================================================
+// free-running synthesis (TacoTestHelper, helpers.py:6-59; tacotron.py:150-200 with is_training = False)
+// ======================================================================================================
+// projo[t] += bias; next decoder input = the raw (un-clipped) frame just predicted (helpers.py:56)
+__global__ void proj_bias_feedback_kernel(float* __restrict__ p, const float* __restrict__ fb, const float* __restrict__ sb, bf16* __restrict__ next_in,
+                                          int B, int M) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * (M + 1)) return;
+  const int m = e % (M + 1), b = e / (M + 1);
+  const float v = p[b * 128 + m] + (m < M ? fb[m] : sb[0]);
+  p[b * 128 + m] = v;
+  if (m < M && next_in) next_in[b * M + m] = __float2bfloat16(v);
+}
+
+// encoder + zero decoder state + go frame. inputs int32 [B][T_in], lengths int32 [B].
+extern "C" int t2_taco_infer_begin(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, const int* d_inputs,
+                                   const int* d_input_lengths, void* stream) {
+  TL lo;
+  int rc = build(cfg, lo, nullptr);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  StepCtx s{&lo, ws, static_cast<const uint8_t*>(d_packed), d_params, st, 0ull, nullptr, 0};
+  rc = encoder_fwd(s, d_inputs, d_input_lengths, 0);
+  if (rc) return rc;
+  DecBufs db;
+  rc = decoder_reset(s, db);
+  if (rc) return rc;
+  T2_CHECK_CUDA(cudaMemsetAsync(ws + lo.w_decin, 0, (size_t)lo.B * lo.M * 2, st));   // go frame (helpers.py:31)
+  return T2_OK;
+}
+
+// decoder steps [t_begin, t_end) of the free-running loop; t_end <= cfg->T_out (= max_iters). After the call
+// workspace "stop_logits_tm" [T_out][B] (col M of the projection rows) holds the stop logits of the finished steps:
+// the host applies the helper's rule (all rows round(sigmoid) == 1, helpers.py:40-54) and decides whether to continue.
+extern "C" int t2_taco_infer_steps(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace,
+                                   const int* d_input_lengths, int t_begin, int t_end, unsigned long long seed, void* stream) {
+  TL lo;
+  int rc = build(cfg, lo, nullptr);
+  if (rc) return rc;
+  T2_REQUIRE(t_begin >= 0 && t_begin <= t_end && t_end <= lo.To, T2_ERR_INVALID_ARG, "bad step range [%d, %d)", t_begin, t_end);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
+  StepCtx s{&lo, ws, pk, d_params, st, seed, nullptr, 0};
+  const int B = lo.B, D = lo.D, H = lo.H, PIK = D + 2 * H;
+  DecBufs db;
+  db.K1r = 2 * H + D; db.K2 = 2 * D; db.PIK = PIK;
+  db.S1 = reinterpret_cast<bf16*>(ws + lo.w_S1); db.S2 = reinterpret_cast<bf16*>(ws + lo.w_S2); db.PI = reinterpret_cast<bf16*>(ws + lo.w_PI);
+  db.c1 = reinterpret_cast<float*>(ws + lo.w_c1); db.c2 = reinterpret_cast<float*>(ws + lo.w_c2);
+  db.cum = reinterpret_cast<float*>(ws + lo.w_cum); db.attU = reinterpret_cast<float*>(ws + lo.w_attU);
+  db.keys = reinterpret_cast<float*>(ws + lo.w_keys); db.values = reinterpret_cast<bf16*>(ws + lo.w_values);
+  db.pre1 = reinterpret_cast<float*>(ws + lo.w_pre1);
+  db.att_smem = sizeof(float) * (size_t)((lo.KA + 1) * lo.A + lo.Ti + lo.KA + 8 + lo.A + lo.Ti + 4 + D + 8 * 2 * H + 32) + 64;
+  bf16* decin = reinterpret_cast<bf16*>(ws + lo.w_decin);
+  bf16* pn1 = reinterpret_cast<bf16*>(ws + lo.w_pn1);
+  bf16* pn2 = reinterpret_cast<bf16*>(ws + lo.w_pn2);
+  float* projo = reinterpret_cast<float*>(ws + lo.w_projo);
+  for (int t = t_begin; t < t_end; ++t) {
+    const unsigned long long seed_t = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(t + 1);   // fresh prenet masks per step
+    bf16* x0 = decin + (long long)t * B * lo.M;
+    bf16* x1 = pn1 + (long long)t * B * lo.P1;
+    bf16* x2 = pn2 + (long long)t * B * lo.P2;
+    rc = conv_gemm(x0, lo.M, B, 1, pk + lo.k_p1, lo.P1, 128, 1, nullptr, lo.P1 >= 256 ? 256 : 128, d_params + lo.p_p1b, 1, x1, nullptr, lo.P1,
+                   lo.P1, lo.c.dropout_rate, 20, seed_t, nullptr, st);
+    if (rc) return rc;
+    rc = conv_gemm(x1, lo.P1, B, 1, pk + lo.k_p2, lo.P2, lo.P1, 1, nullptr, lo.P2 >= 256 ? 256 : 128, d_params + lo.p_p2b, 1, x2, nullptr, lo.P2,
+                   lo.P2, lo.c.dropout_rate, 21, seed_t, nullptr, st);
+    if (rc) return rc;
+    rc = conv_gemm(x2, lo.P2, B, 1, pk + lo.k_l1x, 4 * D, lo.P2, 1, nullptr, 256, d_params + lo.p_l1b, 0, nullptr,
+                   db.pre1 + (long long)t * B * 4 * D, 4 * D, 4 * D, 0.f, 0, 0, nullptr, st);
+    if (rc) return rc;
+    rc = decoder_step(s, db, d_input_lengths, t);
+    if (rc) return rc;
+    float* pt = projo + (long long)t * B * 128;
+    rc = conv_gemm(db.PI + (long long)t * B * PIK, PIK, B, 1, pk + lo.k_proj, lo.M + 1, PIK, 1, nullptr, 128, nullptr, 0, nullptr, pt, 128, lo.M + 1,
+                   0.f, 0, 0, nullptr, st);
+    if (rc) return rc;
+    proj_bias_feedback_kernel<<<g1((long long)B * (lo.M + 1)), 256, 0, st>>>(pt, d_params + lo.p_fb, d_params + lo.p_sb,
+                                                                            t + 1 < lo.To ? decin + (long long)(t + 1) * B * lo.M : nullptr, B, lo.M);
+    t2_count_launch();
+  }
+  T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+
+// clip, postnet (inference batch-norm) and residual over the T_used decoded frames. Results (compact, batch-major):
+// workspace "decoder_output" / "mel_outputs" [B][T_used][M], "stop_logits" [B][T_used]; alignments stay [T_out][B][T_in].
+extern "C" int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, int T_used, void* stream) {
+  TL lo;
+  int rc = build(cfg, lo, nullptr);
+  if (rc) return rc;
+  T2_REQUIRE(T_used >= 1 && T_used <= lo.To, T2_ERR_INVALID_ARG, "T_used %d outside [1, %d]", T_used, lo.To);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
+  StepCtx s{&lo, ws, pk, d_params, st, 0ull, nullptr, 0};
+  const int B = lo.B;
+  float* scal = reinterpret_cast<float*>(ws + lo.w_scal);
+  const float lo_c = -lo.c.max_abs_value - lo.c.lower_bound_decay, hi_c = lo.c.max_abs_value;
+  bf16* dec_bm = reinterpret_cast<bf16*>(ws + lo.w_decbm);
+  float* dec_f = reinterpret_cast<float*>(ws + lo.w_decf);
+  dec_finish_kernel<<<g1((long long)B * T_used * (lo.M + 1)), 256, 0, st>>>(reinterpret_cast<float*>(ws + lo.w_projo), nullptr, nullptr, dec_bm, dec_f,
+                                                                            reinterpret_cast<float*>(ws + lo.w_stop), scal, B, T_used, lo.M,
+                                                                            lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
+  const void* x = dec_bm;
+  for (auto& L : lo.post) { rc = conv_block_fwd(s, L, x, T_used, 0); if (rc) return rc; x = ws + L.w_x; }
+  float* resid = reinterpret_cast<float*>(ws + lo.w_resid);
+  rc = conv_gemm(x, lo.PC, T_used, B, pk + lo.k_pp, lo.M, lo.PC, 1, nullptr, 128, d_params + lo.p_ppb, 0, nullptr, resid, 128, lo.M, 0.f, 0, 0, nullptr, st);
+  if (rc) return rc;
+  mel_finish_kernel<<<g1((long long)B * T_used * lo.M), 256, 0, st>>>(dec_f, resid, nullptr, reinterpret_cast<float*>(ws + lo.w_mel), scal,
+                                                                      (long long)B * T_used, lo.M, lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
+  T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+
 extern "C" int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr, long long* count,
                                         int* elem_bytes) {
   TL lo;
@@ -1284,7 +1425,7 @@ extern "C" int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_wor
   const E table[] = {
       {"memory", lo.w_memory, B * Ti * 2 * lo.H, 2}, {"keys", lo.w_keys, B * Ti * lo.A, 4}, {"alignments", lo.w_alpha, To * B * Ti, 4},
       {"decoder_output", lo.w_decf, B * To * lo.M, 4}, {"mel_outputs", lo.w_mel, B * To * lo.M, 4}, {"stop_logits", lo.w_stop, B * To, 4},
-      {"enc_conv_out", lo.enc.back().w_x, B * Ti * lo.C, 2}, {"prenet", lo.w_pn2, To * B * lo.P2, 2}, {"proj_in", lo.w_PI, To * B * (lo.D + 2 * lo.H), 2},
+      {"projection_rows", lo.w_projo, To * B * 128, 4}, {"enc_conv_out", lo.enc.back().w_x, B * Ti * lo.C, 2}, {"prenet", lo.w_pn2, To * B * lo.P2, 2}, {"proj_in", lo.w_PI, To * B * (lo.D + 2 * lo.H), 2},
   };
   for (const E& e : table)
     if (strcmp(e.n, name) == 0) { *ptr = ws + e.off; *count = e.cnt; *elem_bytes = e.eb; return T2_OK; }

@@ -108,6 +108,39 @@ class Tacotron(object):
                                           L.stream_ptr()))
         return self.grads
 
+    def synthesize(self, inputs, input_lengths, max_iters=None, chunk=64, seed=None):
+        """Free-running synthesis (TacoTestHelper, helpers.py:6-59): feed back the predicted frame, stop after the first
+        step at which EVERY batch row has round(sigmoid(stop)) == 1 (r = 1) or at max_iters (<= T_out of this instance).
+        The stop rule is evaluated on the host between chunks of `chunk` steps; frames decoded past the stop step are
+        discarded, which is what the reference's dynamic_decode returns. Returns dict(mel_outputs [B, T, M],
+        decoder_output [B, T, M], alignments [B, T, T_in], stop_token_prediction [B, T] (sigmoid), T)."""
+        if self._dirty:
+            self.pack()
+        To = self.cfg.T_out if max_iters is None else min(max_iters, self.cfg.T_out)
+        seed = self.seed if seed is None else seed
+        cfg, B, M = ctypes.byref(self.cfg), self.cfg.B, self.cfg.num_mels
+        L.check(self.lib.t2_taco_infer_begin(cfg, L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace), L.ptr(inputs),
+                                             L.ptr(input_lengths), L.stream_ptr()))
+        rows = self.workspace_tensor("projection_rows", (self.cfg.T_out, B, 128))
+        t, T_used = 0, To
+        while t < To:
+            t_end = min(t + chunk, To)
+            L.check(self.lib.t2_taco_infer_steps(cfg, L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace),
+                                                 L.ptr(input_lengths), t, t_end, ctypes.c_ulonglong(seed), L.stream_ptr()))
+            done = (rows[t:t_end, :, M] > 0).all(dim=1)      # round(sigmoid(z)) == 1  <=>  z > 0 (half rounds to even: 0)
+            hit = torch.nonzero(done)
+            if hit.numel():
+                T_used = t + int(hit[0, 0]) + 1
+                break
+            t = t_end
+        L.check(self.lib.t2_taco_infer_finish(cfg, L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace), T_used, L.stream_ptr()))
+        Ti = self.cfg.T_in
+        return {"T": T_used,
+                "mel_outputs": self.workspace_tensor("mel_outputs", (B, T_used, M)).clone(),
+                "decoder_output": self.workspace_tensor("decoder_output", (B, T_used, M)).clone(),
+                "stop_token_prediction": torch.sigmoid(self.workspace_tensor("stop_logits", (B, T_used))),
+                "alignments": self.workspace_tensor("alignments", (self.cfg.T_out, B, Ti))[:T_used].transpose(0, 1).clone()}
+
     def capture(self, inputs, input_lengths, mel_targets, stop_targets):
         """Capture pack + forward + backward (~7.5k kernel nodes at B=32, T_out=800) into one CUDA graph over static inputs."""
         self._static = (inputs, input_lengths, mel_targets, stop_targets)
@@ -177,7 +210,12 @@ class Tacotron(object):
                                                   ctypes.byref(cnt), ctypes.byref(eb)))
         off = p.value - self.workspace.data_ptr()
         t = self.workspace[off:off + cnt.value * eb.value].view(torch.bfloat16 if eb.value == 2 else torch.float32)
-        return t.reshape(shape) if shape is not None else t
+        if shape is None:
+            return t
+        n = 1
+        for d in shape:
+            n *= d
+        return t[:n].reshape(shape)        # compact results (synthesis) use a prefix of the buffer
 
     def losses(self):
         b, a, s, r = self.loss_buf.tolist()

@@ -84,3 +84,24 @@ def test_zoneout_and_losses():
     ot.adam_step(p2, grads, st, hp, 0)
     assert ot.learning_rate(hp, 0) == 1e-3 and abs(ot.learning_rate(hp, 40000 + 18000) - 5e-4) < 1e-9
     assert ot.learning_rate(hp, 10 ** 7) == 1e-4
+
+
+def test_free_running_equals_teacher_forcing_on_its_own_outputs():
+    """TacoTestHelper feeds frame t-1 back; TacoTrainingHelper with targets := those frames must reproduce the run
+    (is_training = False on both sides: same batch-norm statistics and zoneout blend)."""
+    hp = small_hp(tacotron_zoneout_rate=0.1, tacotron_dropout_rate=0.0)
+    params = ot.init_params(hp, seed=5, random_bias=True)
+    params["stop_token_projection/bias"] = torch.full((1,), -6.0)
+    g = torch.Generator().manual_seed(5)
+    inputs = torch.randint(2, 66, (2, 17), generator=g)
+    lens = torch.tensor([17, 11])
+    syn = ot.synthesize(params, inputs, lens, hp, max_iters=9)
+    assert syn["mel_outputs"].shape == (2, 9, hp.num_mels)
+    assert syn["decoder_output"].abs().max() < hp.max_abs_value          # nothing clipped: raw frame == decoder output
+    tf_ = ot.forward(params, inputs, lens, syn["decoder_output"], hp, training=False)
+    assert (tf_["decoder_output"] - syn["decoder_output"]).abs().max() < 1e-5
+    assert (tf_["mel_outputs"] - syn["mel_outputs"]).abs().max() < 1e-5
+    assert (torch.sigmoid(tf_["stop_logits"]) - syn["stop_token_prediction"]).abs().max() < 1e-6
+    # stop rule: a +6 bias finishes at the first step and keeps that step's frame
+    params["stop_token_projection/bias"] = torch.full((1,), 6.0)
+    assert ot.synthesize(params, inputs, lens, hp, max_iters=9)["mel_outputs"].shape[1] == 1

@@ -104,3 +104,84 @@ def test_adam_global_norm_clip_matches_oracle():
     p_new = model.export_params()
     for k in p_ref:
         assert (p_new[k] - p_ref[k]).abs().max().item() < 2e-6, k
+
+
+def _trained_like_stats(params, seed):
+    """non-trivial batch-norm moving statistics so that the inference path is really exercised"""
+    g = torch.Generator().manual_seed(seed)
+    for k in params:
+        if k.endswith("moving_mean"):
+            params[k] = torch.randn(params[k].shape, generator=g) * 0.1
+        elif k.endswith("moving_variance"):
+            params[k] = torch.rand(params[k].shape, generator=g) * 0.5 + 0.75
+    return params
+
+
+def test_free_running_synthesis_matches_oracle():
+    """TacoTestHelper path: own predictions fed back, inference batch-norm / zoneout blend, stop rule on the host.
+    Tolerances as in the teacher-forced test, a little wider on the frames since bf16 errors are fed back 24 times."""
+    hp = _hp(tacotron_zoneout_rate=0.1)
+    B, T_in, steps = 3, 40, 24
+    params = _trained_like_stats(ot.init_params(hp, seed=41, random_bias=True), 41)
+    params["stop_token_projection/bias"] = torch.full((1,), -6.0)        # never stops: runs to max_iters
+    inputs, lens, _, _ = _batch(hp, B, T_in, steps, 41)
+    ref = ot.synthesize(params, inputs, lens, hp, max_iters=steps)
+    model = t2.tacotron.Tacotron(hp, B, T_in, steps)
+    model.load_params(params)
+    out = model.synthesize(inputs.int().cuda(), lens.int().cuda(), chunk=10)
+    assert out["T"] == steps == ref["mel_outputs"].shape[1]
+    e_al = (out["alignments"].cpu() - ref["alignments"]).abs().max().item()
+    e_dec = (out["decoder_output"].cpu() - ref["decoder_output"]).abs()
+    e_mel = (out["mel_outputs"].cpu() - ref["mel_outputs"]).abs()
+    e_stop = (out["stop_token_prediction"].cpu() - ref["stop_token_prediction"]).abs().max().item()
+    print("synthesis: align %.3g | dec max %.3g mean %.3g | mel max %.3g mean %.3g | stop %.3g" % (
+        e_al, e_dec.max(), e_dec.mean(), e_mel.max(), e_mel.mean(), e_stop))
+    assert e_al < 2e-2 and e_dec.mean().item() < 1.5e-2 and e_mel.mean().item() < 4e-2 and e_stop < 1e-2
+
+
+def test_synthesis_stop_rule():
+    """finished <=> every row's stop probability rounds to 1 (helpers.py:40-54): the frame of that step is kept."""
+    hp = _hp()
+    B, T_in, max_iters = 2, 20, 40
+    params = ot.init_params(hp, seed=42, random_bias=True)
+    inputs, lens, _, _ = _batch(hp, B, T_in, max_iters, 42)
+    model = t2.tacotron.Tacotron(hp, B, T_in, max_iters)
+    params["stop_token_projection/bias"] = torch.full((1,), 6.0)          # stops at the very first step
+    model.load_params(params)
+    out = model.synthesize(inputs.int().cuda(), lens.int().cuda(), chunk=16)
+    ref = ot.synthesize(params, inputs, lens, hp, max_iters=max_iters)
+    assert out["T"] == 1 == ref["mel_outputs"].shape[1]
+    assert (out["mel_outputs"].cpu() - ref["mel_outputs"]).abs().mean().item() < 4e-2
+    # a stop vector that crosses zero mid-sequence: the stop logit follows the decoder state, so make the projection
+    # read a time ramp out of the cumulative-free part: use the oracle's own decision as the expectation
+    params["stop_token_projection/bias"] = torch.full((1,), 0.0)
+    params["stop_token_projection/kernel"] = params["stop_token_projection/kernel"] * 8
+    model.load_params(params)
+    ref = ot.synthesize(params, inputs, lens, hp, max_iters=max_iters)
+    out = model.synthesize(inputs.int().cuda(), lens.int().cuda(), chunk=7)
+    margin = (torch.logit(ref["stop_token_prediction"].clamp(1e-6, 1 - 1e-6))).abs().min().item()
+    print("oracle stops after %d steps (min |logit| %.3g), cuda after %d" % (ref["mel_outputs"].shape[1], margin, out["T"]))
+    if margin > 0.05:        # no marginal decisions: the two must agree exactly
+        assert out["T"] == ref["mel_outputs"].shape[1]
+
+
+def test_gta_mode_uses_inference_statistics():
+    """GTA / eval graph: teacher forcing with is_training = False (tacotron.py:157-160): moving-average batch norm,
+    no conv dropout, deterministic zoneout blend."""
+    hp = _hp(tacotron_zoneout_rate=0.1)
+    B, T_in, T_out = 3, 40, 24
+    params = _trained_like_stats(ot.init_params(hp, seed=43, random_bias=True), 43)
+    inputs, lens, mel, stop = _batch(hp, B, T_in, T_out, 43)
+    ref = ot.forward(params, inputs, lens, mel, hp, training=False)
+    model = t2.tacotron.Tacotron(hp, B, T_in, T_out)
+    model.load_params(params)
+    model.forward(inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda(), training=False)
+    torch.cuda.synchronize()
+    melo = model.workspace_tensor("mel_outputs", (B, T_out, hp.num_mels)).cpu()
+    al = model.workspace_tensor("alignments", (T_out, B, T_in)).float().cpu().transpose(0, 1)
+    assert (al - ref["alignments"]).abs().max().item() < 2e-2
+    assert (melo - ref["mel_outputs"]).abs().mean().item() < 4e-2
+    p_after = model.export_params()
+    for k in params:
+        if "moving_" in k:
+            assert torch.equal(p_after[k], params[k]), k          # inference must not touch the moving statistics
