@@ -37,16 +37,16 @@ def workload_hparams():
 B_PER_GPU, T_STEP = 2, 7680
 
 
-def synth_batch(hp, B, T, seed):
-    """Synthetic LJSpeech-shaped batch: AR(2) 'speech-like' noise -> mu-law indices; mels ~ U[0,1]."""
+def synth_batch(hp, B, T, seed, quantize):
+    """Synthetic LJSpeech-shaped batch: AR(2) 'speech-like' noise -> mu-law indices; mels ~ U[0,1].
+    quantize: float32 [B,T] -> int indices (the CUDA mu-law kernel on the GPU arm, the oracle on the CPU arm)."""
     import numpy as np
     from scipy.signal import lfilter
-    from oracle import audio as oa
     rng = np.random.default_rng(seed)
     e = rng.standard_normal((B, T + 64))
     w = lfilter([1.0], [1.0, -1.6, 0.8], e, axis=1)[:, 64:]
     w = (w / np.abs(w).max() * 0.6).astype(np.float32)
-    idx = oa.mulaw_quantize(w).astype(np.int32)
+    idx = quantize(w).astype(np.int32)
     c = rng.random((B, hp.cin_channels, T // 256), dtype=np.float32)
     lengths = np.full((B,), T, dtype=np.int32)
     return idx, c, lengths
@@ -99,7 +99,8 @@ def cpu_reference_run(hp, steps, warmup, B, T):
     from oracle import wavenet as ow
     ncores = os.cpu_count() or 1
     params = ow.init_params(hp, seed=5339)
-    idx, c, lengths = synth_batch(hp, B, T, 2)
+    from oracle import audio as oa
+    idx, c, lengths = synth_batch(hp, B, T, 2, oa.mulaw_quantize)
     # pick the intra-op thread count that runs this graph fastest on this host (oversubscribing a 128-core box
     # with 128 threads on these small convolutions is ~5x slower than 32): probe a short forward at each setting
     best = (None, 1e30)
@@ -178,9 +179,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = t2.lib.load()
     model = t2.wavenet.WaveNet(hp, B_PER_GPU, T_STEP, device=dev)
-    from oracle import wavenet as ow  # parameter initialiser only (glorot + NN_init), not on the measured path
-    model.load_params(ow.init_params(hp, seed=5339))
-    idx, c, lengths = synth_batch(hp, B_PER_GPU, T_STEP, 2 + rank)
+    model.init_variables(seed=5339)
+    idx, c, lengths = synth_batch(hp, B_PER_GPU, T_STEP, 2 + rank,
+                                  lambda w: t2.audio.mulaw_quantize(torch.from_numpy(w).to(dev)).cpu().numpy())
     pin = [torch.from_numpy(a).pin_memory() for a in (idx, c, idx, lengths)]
     static = [p.to(dev) for p in pin]
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()

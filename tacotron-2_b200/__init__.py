@@ -7,3 +7,4 @@ from . import lib  # noqa: F401
 from . import wavenet  # noqa: F401
 from . import audio  # noqa: F401
 from . import tacotron  # noqa: F401
+from . import init  # noqa: F401

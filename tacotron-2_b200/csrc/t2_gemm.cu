@@ -1,4 +1,5 @@
 // t2_gemm.cu — host side of the tcgen05 GEMM engine: TMA tensor-map encoding and kernel launches.
+#include <stdlib.h>
 #include <mutex>
 
 #include "t2_gemm.cuh"
@@ -67,6 +68,13 @@ static int encode_wt_map(CUtensorMap* m, const void* w, int N, int K, int L, int
   return T2_OK;
 }
 
+// programmatic dependent launch for the GEMM kernels (T2_PDL=0 in the environment turns it off for A/B measurements)
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("T2_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <int EPI, int BN, int NT = 1>
 static int launch_one(const GemmArgs& g, dim3 grid, cudaStream_t stream) {
   using Cfg = ActGemmCfg<BN>;
@@ -77,9 +85,15 @@ static int launch_one(const GemmArgs& g, dim3 grid, cudaStream_t stream) {
     configured = true;
   }
   grid.y = (grid.y + NT - 1) / NT;
-  act_gemm_kernel<EPI, BN, NT><<<grid, kActGemmThreads, Cfg::kSmemBytes, stream>>>(g);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(kActGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  T2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, act_gemm_kernel<EPI, BN, NT>, g));
   t2_count_launch();
-  T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
 
@@ -151,9 +165,15 @@ int launch_wgrad(const ActT* maps, int nmaps, const WgradTile* tiles_dev, int nt
     T2_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     configured = true;
   }
-  wgrad_gemm_kernel<<<ntiles, kGemmThreads, kWgSmemBytes, stream>>>(g);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ntiles); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = kWgSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  T2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel, g));
   t2_count_launch();
-  T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
 

@@ -835,6 +835,9 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is CTA-local set-up and overlaps the previous kernel's tail under PDL; global memory from here on
+  pdl_wait();
+  pdl_launch_dependents();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -961,6 +964,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // (the tile table read above is written once at init, never by a preceding kernel)
+  pdl_launch_dependents();
   constexpr int kBlk = kBK * 128;  // bytes of one [64 pos x 64 ch] block
 
   if (warp == 0) {

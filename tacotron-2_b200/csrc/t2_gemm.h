@@ -31,6 +31,20 @@ struct ActGemmCall {
 };
 
 void set_timing_buffer(long long* p);
+bool pdl_enabled();
+// launch any kernel with the programmatic-dependent-launch attribute (the kernel must call pdl_wait() before it touches
+// global memory; see t2_common.cuh)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream);
 int launch_wgrad(const ActT* maps, int nmaps, const WgradTile* tiles_dev, int ntiles, float* out,
                  int T, int B, cudaStream_t stream);

@@ -455,6 +455,8 @@ __device__ __forceinline__ void att_query(const bf16* __restrict__ WqT, const fl
 }
 __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
   extern __shared__ __align__(16) float sm[];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Ti = a.Ti, A = a.A, half = a.KA / 2;
   const int Tip = (Ti + 3) & ~3, cumlen = (Ti + 2 * half + 5) & ~3;
@@ -782,6 +784,8 @@ struct CellBwd {
   float zone; unsigned long long seed; const unsigned long long* step;
 };
 __global__ void lstm_cell_bwd_kernel(CellBwd a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= (long long)a.B * a.H) return;
   const int b = int(e / a.H), u = int(e % a.H);
@@ -847,6 +851,8 @@ struct AttBwd {
 };
 __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
   extern __shared__ __align__(16) float sm[];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Ti = a.Ti, A = a.A, half = a.KA / 2, NW = kAttThreads / 32;
   const int Tip = (Ti + 3) & ~3, cumlen = (Ti + 2 * half + 5) & ~3;
@@ -1222,7 +1228,7 @@ static int decoder_step(const StepCtx& s, const DecBufs& d, const int* d_input_l
   a.alpha = reinterpret_cast<float*>(ws + lo.w_alpha) + (long long)t * B * Ti;
   a.ctx_a = S1n; a.ld_a = K1r; a.ctx_b = PIt + D; a.ld_b = PIK;
   a.B = B; a.Ti = Ti; a.D = D; a.A = lo.A; a.KA = lo.KA; a.C2 = 2 * H;
-  att_fwd_kernel<<<B, kAttThreads, d.att_smem, st>>>(a); t2_count_launch();
+  T2_CHECK_CUDA(launch_pdl(att_fwd_kernel, dim3(B), dim3(kAttThreads), d.att_smem, st, a)); t2_count_launch();
   return T2_OK;
 }
 
@@ -1304,6 +1310,8 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
 // projo[t] += bias; next decoder input = the raw (un-clipped) frame just predicted (helpers.py:56)
 __global__ void proj_bias_feedback_kernel(float* __restrict__ p, const float* __restrict__ fb, const float* __restrict__ sb, bf16* __restrict__ next_in,
                                           int B, int M) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B * (M + 1)) return;
   const int m = e % (M + 1), b = e / (M + 1);
@@ -1376,8 +1384,8 @@ extern "C" int t2_taco_infer_steps(const t2_taco_config_t* cfg, float* d_params,
     rc = conv_gemm(db.PI + (long long)t * B * PIK, PIK, B, 1, pk + lo.k_proj, lo.M + 1, PIK, 1, nullptr, 128, nullptr, 0, nullptr, pt, 128, lo.M + 1,
                    0.f, 0, 0, nullptr, st);
     if (rc) return rc;
-    proj_bias_feedback_kernel<<<g1((long long)B * (lo.M + 1)), 256, 0, st>>>(pt, d_params + lo.p_fb, d_params + lo.p_sb,
-                                                                            t + 1 < lo.To ? decin + (long long)(t + 1) * B * lo.M : nullptr, B, lo.M);
+    T2_CHECK_CUDA(launch_pdl(proj_bias_feedback_kernel, dim3(g1((long long)B * (lo.M + 1))), dim3(256), 0, st, pt, d_params + lo.p_fb,
+                             d_params + lo.p_sb, t + 1 < lo.To ? decin + (long long)(t + 1) * B * lo.M : (bf16*)nullptr, B, lo.M));
     t2_count_launch();
   }
   T2_CHECK_CUDA(cudaGetLastError());
@@ -1531,21 +1539,21 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
     a.dPI = dPI + (long long)t * B * PIK; a.ld_dPI = PIK; a.dctxl = dctxl; a.dh2ext = dh2ext;
     a.dctx_save = dctx_all + (long long)t * B * 2 * H; a.dq_save = dq_all + (long long)t * B * A; a.dkeys = dkeys; a.acc = attacc;
     a.B = B; a.Ti = Ti; a.D = D; a.A = A; a.KA = lo.KA; a.C2 = 2 * H;
-    att_bwd_kernel<<<B, kAttThreads, ab_smem, st>>>(a); t2_count_launch();
+    T2_CHECK_CUDA(launch_pdl(att_bwd_kernel, dim3(B), dim3(kAttThreads), ab_smem, st, a)); t2_count_launch();
     CellBwd c2;
     c2.dh_ext = dh2ext; c2.ld_ext = D; c2.dhs = dhs2; c2.dcs = dcs2;
     c2.gst = reinterpret_cast<const bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D; c2.tst = reinterpret_cast<const bf16*>(ws + lo.w_t2) + (long long)t * B * D;
     c2.c_prev = reinterpret_cast<const float*>(ws + lo.w_c2) + (long long)t * B * D;
     c2.dg_a = dg2 + (long long)t * B * 4 * D; c2.ld_a = 4 * D; c2.dg_b = nullptr; c2.ld_b = 0; c2.lens = nullptr; c2.t = t; c2.B = B; c2.H = D; c2.stream = 5;
     c2.zone = lo.c.zoneout_rate; c2.seed = seed; c2.step = d_step;
-    lstm_cell_bwd_kernel<<<g1((long long)B * D), 256, 0, st>>>(c2); t2_count_launch();
+    T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * D)), dim3(256), 0, st, c2)); t2_count_launch();
     rc = lstm_bwd_gemm(s, pk + lo.k_l2T, K2, 4 * D, c2.dg_a, B, dh1ext, D, D, 0, dhs2, D, 1);
     if (rc) return rc;
     CellBwd c1 = c2;
     c1.dh_ext = dh1ext; c1.dhs = dhs1; c1.dcs = dcs1;
     c1.gst = reinterpret_cast<const bf16*>(ws + lo.w_g1) + (long long)t * B * 4 * D; c1.tst = reinterpret_cast<const bf16*>(ws + lo.w_t1) + (long long)t * B * D;
     c1.c_prev = reinterpret_cast<const float*>(ws + lo.w_c1) + (long long)t * B * D; c1.dg_a = dg1 + (long long)t * B * 4 * D; c1.stream = 4;
-    lstm_cell_bwd_kernel<<<g1((long long)B * D), 256, 0, st>>>(c1); t2_count_launch();
+    T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * D)), dim3(256), 0, st, c1)); t2_count_launch();
     rc = lstm_bwd_gemm(s, pk + lo.k_l1rT, K1r, 4 * D, c1.dg_a, B, dctxl, 2 * H, 2 * H, 0, dhs1, D, 1);
     if (rc) return rc;
   }
@@ -1617,7 +1625,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
       c.c_prev = reinterpret_cast<const float*>(ws + lo.w_encc[d]) + (long long)sidx * B * H;
       c.dg_a = dgall + (long long)sidx * B * 4 * H; c.ld_a = 4 * H; c.dg_b = dpre + (long long)t * 4 * H; c.ld_b = (long long)Ti * 4 * H;
       c.lens = d_input_lengths; c.t = t; c.B = B; c.H = H; c.stream = 2 + d; c.zone = lo.c.zoneout_rate; c.seed = seed; c.step = d_step;
-      lstm_cell_bwd_kernel<<<g1((long long)B * H), 256, 0, st>>>(c); t2_count_launch();
+      T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * H)), dim3(256), 0, st, c)); t2_count_launch();
       rc = lstm_bwd_gemm(s, pk + lo.k_encWrT[d], H, 4 * H, c.dg_a, B, edh, H, H, 1, nullptr, 0, 0);
       if (rc) return rc;
     }

