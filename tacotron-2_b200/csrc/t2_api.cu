@@ -54,14 +54,14 @@ extern "C" int t2_dbg_wgrad(const void* a, int Ca, const void* bm, int Cb, int B
   ActT maps[2] = {make_act(a, Ca, T, B), make_act(bm, Cb, T, B)};
   std::vector<WgradTile> tiles;
   for (int m0 = 0; m0 < Ca; m0 += 128)
-    for (int n0 = 0; n0 < Cb; n0 += 128) {
+    for (int n0 = 0; n0 < Cb; n0 += 256) {
       WgradTile t;
       memset(&t, 0, sizeof(t));
       t.a_map = 0; t.a_ch0 = m0; t.a_shift = shift_a; t.a_layer = 0;
       t.b_map = 1; t.b_ch0 = n0; t.b_shift = 0; t.b_layer = 0;
       t.out_off = (long long)m0 * Cb + n0; t.ldc = Cb;
       t.m_valid = Ca - m0 < 128 ? Ca - m0 : 128;
-      t.n_valid = Cb - n0 < 128 ? Cb - n0 : 128;
+      t.n_valid = Cb - n0 < 256 ? Cb - n0 : 256;
       t.scale = scale; t.accumulate = 0; t.div = nullptr;
       tiles.push_back(t);
     }

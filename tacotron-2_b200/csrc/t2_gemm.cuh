@@ -934,9 +934,9 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 // wgrad_gemm kernel: both operands MN-major (channels contiguous), reduction over positions.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgBN = 128;
-constexpr int kWgStages = 6;
-constexpr int kWgStageBytes = 2 * (2 * kBK * 128);  // A: 2 blocks of [64 pos x 128 B], B: same = 32 KB
+constexpr int kWgBN = 256;      // up to 256 output columns per tile: the A block pair is reused for twice the MMA work
+constexpr int kWgStages = 4;
+constexpr int kWgStageBytes = 6 * (kBK * 128);  // A: 2 blocks of [64 pos x 128 B] (16 KB), B: up to 4 blocks (32 KB)
 constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024 + 256;
 
 __global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradArgs g) {
@@ -950,6 +950,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __gri
   const WgradTile tile = g.tiles[blockIdx.x];
   const int kb_per_b = (g.T + kBK - 1) / kBK;
   const int total_kb = kb_per_b * g.B;
+  const int nblk = (tile.n_valid + 63) >> 6;   // 64-channel B blocks this tile needs (1..4)
 
   if (warp == 1) {
     if (elect_one()) {
@@ -974,20 +975,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __gri
       for (int bb = 0; bb < g.B; ++bb)
         for (int kb = 0; kb < kb_per_b; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kWgStageBytes);
+          mbar_expect_tx(&full_bar[stage], uint32_t(2 + nblk) * kBlk);
           uint8_t* sa = smem + stage * kWgStageBytes;
           uint8_t* sb = sa + 2 * kBlk;
           const int tpos = kb * kBK;
           tma_load_4d(sa, &g.map[tile.a_map], &full_bar[stage], tile.a_ch0, tpos + tile.a_shift, bb, tile.a_layer);
           tma_load_4d(sa + kBlk, &g.map[tile.a_map], &full_bar[stage], tile.a_ch0 + 64, tpos + tile.a_shift, bb, tile.a_layer);
-          tma_load_4d(sb, &g.map[tile.b_map], &full_bar[stage], tile.b_ch0, tpos + tile.b_shift, bb, tile.b_layer);
-          tma_load_4d(sb + kBlk, &g.map[tile.b_map], &full_bar[stage], tile.b_ch0 + 64, tpos + tile.b_shift, bb, tile.b_layer);
+          for (int i = 0; i < nblk; ++i)
+            tma_load_4d(sb + i * kBlk, &g.map[tile.b_map], &full_bar[stage], tile.b_ch0 + 64 * i, tpos + tile.b_shift, bb, tile.b_layer);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, kWgBN, 1, 1);
+      const uint32_t idesc = make_idesc_bf16(kBM, nblk * 64, 1, 1);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) wgrad_gemm_kernel(const __gri
     float sc = tile.scale;
     if (tile.div) sc /= fmaxf(__ldg(tile.div), 1e-20f);
 #pragma unroll 1
-    for (int j0 = 0; j0 < kWgBN; j0 += 32) {
+    for (int j0 = 0; j0 < tile.n_valid; j0 += 32) {   // (warp-uniform bound)
       float v[32];
       tmem_ld32f(trow + j0, v);
       if (m < tile.m_valid) {

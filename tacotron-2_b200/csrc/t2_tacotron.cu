@@ -687,8 +687,8 @@ void wg_tile(std::vector<WgradTile>& v, int am, int ach, int ash, int bm, int bc
 // dense [Ca x Cb] gradient of a 1x1 map: A channels [a0, a0+Ca), B channels [b0, b0+Cb)
 void wg_dense(std::vector<WgradTile>& v, int am, int a0, int Ca, int bm, int b0, int Cb, long long off, int ldc, int shift = 0) {
   for (int m0 = 0; m0 < Ca; m0 += 128)
-    for (int n0 = 0; n0 < Cb; n0 += 128)
-      wg_tile(v, am, a0 + m0, shift, bm, b0 + n0, off + (long long)m0 * ldc + n0, ldc, Ca - m0 < 128 ? Ca - m0 : 128, Cb - n0 < 128 ? Cb - n0 : 128);
+    for (int n0 = 0; n0 < Cb; n0 += 256)   // wgrad_gemm_kernel tiles: 128 x (up to) 256
+      wg_tile(v, am, a0 + m0, shift, bm, b0 + n0, off + (long long)m0 * ldc + n0, ldc, Ca - m0 < 128 ? Ca - m0 : 128, Cb - n0 < 256 ? Cb - n0 : 256);
 }
 enum { WG_PP = 0, WG_POST0 = 1 /* .. +postnet layers */ };
 void build_tiles(const TL& lo, std::vector<WgL>& L) {

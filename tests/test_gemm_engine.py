@@ -70,6 +70,9 @@ def test_conv_gemm(B, T, C, N, BN, shifts):
     (2, 256, 256, 512, 0),
     (2, 300, 80, 256, 0),     # ragged T, Ca not a multiple of 64
     (2, 512, 256, 256, -16),
+    (1, 128, 128, 192, 0),    # 3 column blocks of 64
+    (2, 200, 64, 320, 3),     # one full 256-wide tile + a 64-wide remainder
+    (1, 64, 128, 64, 0),
 ])
 def test_wgrad(B, T, Ca, Cb, shift):
     lib = L.load()
