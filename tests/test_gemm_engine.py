@@ -88,6 +88,8 @@ def test_wgrad(B, T, Ca, Cb, shift):
     sa = torch.zeros_like(af)
     if shift < 0:
         sa[:, -shift:, :] = af[:, :T + shift, :]
+    elif shift > 0:
+        sa[:, :T - shift, :] = af[:, shift:, :]
     else:
         sa = af
     ref = 0.5 * torch.einsum("btm,btn->mn", sa, g.float())
