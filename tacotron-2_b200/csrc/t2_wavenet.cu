@@ -9,6 +9,7 @@
 //   gate : [x(t-2d) | x(t-d) | x(t) | c(t)] (K = 3R + 128) x Wg -> tanh*sigmoid epilogue -> z (+ stashes)
 //   out  : z (K = G/2) x Wo -> (o + b + x) * sqrt(.5) epilogue -> x_next
 // the skip 1x1 of ALL layers is deferred into one K = L*G/2 GEMM (skips never round-trip through HBM).
+#include <stdlib.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -307,34 +308,49 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
 // small kernels
 // ------------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ params, bf16* __restrict__ packed, const PackJob* __restrict__ jobs) {
-  // 32x32 tiles through shared memory: reads are coalesced along the source's fast axis (N), writes along the
-  // destination's fast axis (K for the transposing jobs)
-  __shared__ float tile[32][33];
+  // 64x64 tiles through shared memory: float2 reads along the source's fast axis (N), bf16x2 writes along the
+  // destination's fast axis (K for the transposing jobs). All offsets / leading dimensions in the job table are even.
+  __shared__ float tile[64][65];
   const PackJob j = jobs[blockIdx.y];
-  const int tiles_n = (j.N + 31) / 32, tiles_k = (j.K + 31) / 32;
+  const int tiles_n = (j.N + 63) / 64, tiles_k = (j.K + 63) / 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool vec_src = ((j.N | int(j.src_off)) & 1) == 0;
+  const bool vec_dst = ((j.dst_ld | j.col0 | int(j.dst_off)) & 1) == 0;
   for (int ti = blockIdx.x; ti < tiles_n * tiles_k; ti += gridDim.x) {
-    const int k0 = (ti / tiles_n) * 32, n0 = (ti % tiles_n) * 32;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-      const int k = k0 + r, n = n0 + threadIdx.x;
-      tile[r][threadIdx.x] = (k < j.K && n < j.N) ? params[j.src_off + (long long)k * j.N + n] * j.scale : 0.f;
+    const int k0 = (ti / tiles_n) * 64, n0 = (ti % tiles_n) * 64;
+    for (int r = ty; r < 64; r += 8) {
+      const int k = k0 + r, n = n0 + 2 * tx;
+      float a = 0.f, b = 0.f;
+      if (k < j.K) {
+        const float* src = params + j.src_off + (long long)k * j.N + n;
+        if (vec_src && n + 1 < j.N) { const float2 v = *reinterpret_cast<const float2*>(src); a = v.x; b = v.y; }
+        else { if (n < j.N) a = src[0]; if (n + 1 < j.N) b = src[1]; }
+      }
+      tile[r][2 * tx] = a * j.scale; tile[r][2 * tx + 1] = b * j.scale;
     }
     __syncthreads();
     if (j.transpose) {
-      for (int r = threadIdx.y; r < 32; r += 8) {
-        const int n = n0 + r, k = k0 + threadIdx.x;
+      for (int r = ty; r < 64; r += 8) {
+        const int n = n0 + r, k = k0 + 2 * tx;
         if (n < j.N && k < j.K) {
           int row = n;
           if (j.perm_gh > 0) {
             const int half = n / j.perm_gh, idx = n % j.perm_gh;
             row = (idx / 128) * 256 + half * 128 + (idx % 128);
           }
-          packed[j.dst_off + (long long)row * j.dst_ld + j.col0 + k] = __float2bfloat16(tile[threadIdx.x][r]);
+          bf16* dst = packed + j.dst_off + (long long)row * j.dst_ld + j.col0 + k;
+          if (vec_dst && k + 1 < j.K) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(tile[2 * tx][r], tile[2 * tx + 1][r]);
+          else { dst[0] = __float2bfloat16(tile[2 * tx][r]); if (k + 1 < j.K) dst[1] = __float2bfloat16(tile[2 * tx + 1][r]); }
         }
       }
     } else {
-      for (int r = threadIdx.y; r < 32; r += 8) {
-        const int k = k0 + r, n = n0 + threadIdx.x;
-        if (n < j.N && k < j.K) packed[j.dst_off + (long long)k * j.dst_ld + j.col0 + n] = __float2bfloat16(tile[r][threadIdx.x]);
+      for (int r = ty; r < 64; r += 8) {
+        const int k = k0 + r, n = n0 + 2 * tx;
+        if (n < j.N && k < j.K) {
+          bf16* dst = packed + j.dst_off + (long long)k * j.dst_ld + j.col0 + n;
+          if (vec_dst && n + 1 < j.N) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(tile[r][2 * tx], tile[r][2 * tx + 1]);
+          else { dst[0] = __float2bfloat16(tile[r][2 * tx]); if (n + 1 < j.N) dst[1] = __float2bfloat16(tile[r][2 * tx + 1]); }
+        }
       }
     }
     __syncthreads();
@@ -783,7 +799,7 @@ extern "C" int t2_wn_pack_weights(const t2_wn_config_t* cfg, const float* d_para
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   uint8_t* pk = static_cast<uint8_t*>(d_packed);
-  pack_kernel<<<dim3(32, lo.n_packjobs), dim3(32, 8), 0, st>>>(d_params, reinterpret_cast<bf16*>(pk),
+  pack_kernel<<<dim3(16, lo.n_packjobs), dim3(32, 8), 0, st>>>(d_params, reinterpret_cast<bf16*>(pk),
                                                        reinterpret_cast<const PackJob*>(ws + lo.w_packjobs)); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   long long* d_offs = reinterpret_cast<long long*>(ws + lo.w_tables);
@@ -908,6 +924,23 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
   return T2_OK;
 }
 
+// side stream + fork/join events for the independent tail of the backward pass (created once per process; T2_SIDE_STREAM=0
+// in the environment keeps everything on the caller's stream)
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; };
+static SideStream* side_stream() {
+  static SideStream ss;
+  static int state = 0;   // 0 unknown, 1 ready, -1 disabled
+  if (state == 0) {
+    const char* e = getenv("T2_SIDE_STREAM");
+    if (e && e[0] == '0') state = -1;
+    else if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess) state = 1;
+    else state = -1;
+  }
+  return state == 1 ? &ss : nullptr;
+}
+
 extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed,
                               void* d_workspace, const void* d_x, const float* d_c, float* d_grads,
                               unsigned long long seed, const unsigned long long* d_step, void* stream) {
@@ -972,6 +1005,16 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     rc = launch_act_gemm(EPI_DX, lo.R, gx, st);
     if (rc) return rc;
   }
+  // From here on two independent tails: (A) the weight-gradient GEMMs (fill the machine), (B) the conditioning path
+  // (K = L*G data-gradient GEMM, transposes, upsampling-net backward) + first-conv gradient: latency-bound small kernels.
+  // (B) runs on a side stream (fork/join through events, capturable into the caller's CUDA graph) and hides under (A).
+  cudaStream_t sb = st;
+  SideStream* side = side_stream();
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    sb = side->s;
+  }
   // weight gradients: one batched launch for the whole stack, one for the head
   {
     ActT maps[6] = {make_act(ws + lo.w_xd, lo.R, lo.T, lo.B, lo.L), a_dg,
@@ -988,7 +1031,7 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
   colsum_kernel<<<dim3(96, lo.n_colsum), 256, 0, st>>>(ws, d_grads, reinterpret_cast<const ColsumJob*>(ws + lo.w_colsum), scalars); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   // first conv
-  first_conv_bwd_kernel<<<dim3((unsigned)((BT + 63) / 64)), lo.R, 0, st>>>(d_x, lo.scalar_in ? 1 : 0, dxin, d_grads + lo.p_in_k, BT, lo.R); t2_count_launch();
+  first_conv_bwd_kernel<<<dim3((unsigned)((BT + 63) / 64)), lo.R, 0, sb>>>(d_x, lo.scalar_in ? 1 : 0, dxin, d_grads + lo.p_in_k, BT, lo.R); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   // conditioning path
   if (lo.C > 0 && !cfg->c_pre_upsampled) {
@@ -1001,11 +1044,11 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
     g.epi.ptr[0] = nullptr; g.epi.ptr[1] = nullptr; g.epi.ptr[2] = dcup;
     g.epi.i[0] = lo.C; g.epi.i[1] = 0; g.epi.i[2] = lo.C;
-    rc = launch_act_gemm(EPI_BIAS_ACT, 128, g, st);
+    rc = launch_act_gemm(EPI_BIAS_ACT, 128, g, sb);
     if (rc) return rc;
     // dc_up arrives channels-last from the GEMM: transpose once into [B][C][T]
     float* dchw = reinterpret_cast<float*>(ws + lo.w_upgrad[1]);
-    cl_to_chw_kernel<<<dim3((lo.T + 31) / 32, (lo.C + 31) / 32, lo.B), dim3(32, 8), 0, st>>>(dcup, dchw, lo.T, lo.C); t2_count_launch();
+    cl_to_chw_kernel<<<dim3((lo.T + 31) / 32, (lo.C + 31) / 32, lo.B), dim3(32, 8), 0, sb>>>(dcup, dchw, lo.T, lo.C); t2_count_launch();
     const float* dout = dchw;
     int pp = 0;
     for (int i = int(lo.up_w.size()) - 1; i >= 0; --i) {
@@ -1014,17 +1057,21 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
       T2_REQUIRE(s <= 32, T2_ERR_UNSUPPORTED_SHAPE, "upsample scale > 32");
       const float* layer_in = i == 0 ? d_c : reinterpret_cast<const float*>(ws + lo.w_upout[i - 1]);
       const float* out = reinterpret_cast<const float*>(ws + lo.w_upout[i]);
-      upsample_bwd_param_kernel<<<s * ((296 + s - 1) / s), 256, 0, st>>>(layer_in, out, dout, d_grads + lo.p_up_k[i], d_grads + lo.p_up_b[i], lo.B, lo.C, W, s,
+      upsample_bwd_param_kernel<<<s * ((296 + s - 1) / s), 256, 0, sb>>>(layer_in, out, dout, d_grads + lo.p_up_k[i], d_grads + lo.p_up_b[i], lo.B, lo.C, W, s,
                                                      cfg->upsample_type); t2_count_launch();
       if (i > 0) {
         float* din = reinterpret_cast<float*>(ws + lo.w_upgrad[pp]);
-        upsample_bwd_input_kernel<<<grid1d(4LL * lo.B * lo.C * W), 256, 0, st>>>(out, dout, 0, d_params + lo.p_up_k[i], din, lo.B, lo.C, W, s,
+        upsample_bwd_input_kernel<<<grid1d(4LL * lo.B * lo.C * W), 256, 0, sb>>>(out, dout, 0, d_params + lo.p_up_k[i], din, lo.B, lo.C, W, s,
                                                                                     cfg->upsample_type); t2_count_launch();
         dout = din;
         pp ^= 1;
       }
       T2_CHECK_CUDA(cudaGetLastError());
     }
+  }
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->join, sb));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   }
   return T2_OK;
 }
