@@ -442,6 +442,7 @@ __device__ __forceinline__ void att_query(const bf16* __restrict__ WqT, const fl
     const uint4* w = reinterpret_cast<const uint4*>(WqT + (long long)o * D + part * kq);
     const float* h = hs + part * kq;
     float acc = 0.f;
+#pragma unroll 8
     for (int c = 0; c < (kq >> 3); ++c) {
       const uint4 u = __ldg(w + c);
       const float* hh = h + c * 8;
@@ -453,22 +454,47 @@ __device__ __forceinline__ void att_query(const bf16* __restrict__ WqT, const fl
     if (part == 0) q[o] = acc;
   }
 }
+// Location features for kAttR CONSECUTIVE memory rows j0 .. j0+R-1 and this lane's 4 channels:
+//   pl[r] = u0 + sum_k cum[j0 + r + k] * U[k]      (cum = zero-padded halo array, index j + k <-> position j + k - half)
+// Register blocking over rows: one LDS.128 of U[k] and one scalar LDS of the sliding cum window feed 4*R FMAs (the
+// row-at-a-time form did 2 shared-memory loads per 4 FMAs and was shared-memory-bandwidth bound).
+constexpr int kAttR = 10;
+__device__ __forceinline__ void loc_features(const float* __restrict__ U, const float* __restrict__ cum, int j0, int KA, int A, int c,
+                                             float4 (&pl)[kAttR]) {
+  const float4 u0 = *reinterpret_cast<const float4*>(U + KA * A + c);
+  float w[kAttR];
+#pragma unroll
+  for (int r = 0; r < kAttR; ++r) { pl[r] = u0; w[r] = cum[j0 + r]; }
+  for (int k = 0; k < KA; ++k) {
+    const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
+#pragma unroll
+    for (int r = 0; r < kAttR; ++r) { pl[r].x += w[r] * u.x; pl[r].y += w[r] * u.y; pl[r].z += w[r] * u.z; pl[r].w += w[r] * u.w; }
+#pragma unroll
+    for (int r = 0; r + 1 < kAttR; ++r) w[r] = w[r + 1];
+    w[kAttR - 1] = cum[j0 + k + kAttR];
+  }
+}
+__host__ __device__ inline int att_tipr(int Ti) { return (Ti + kAttR - 1) / kAttR * kAttR; }
+__host__ __device__ inline int att_cumlen(int Ti, int KA) { return (att_tipr(Ti) + KA + 16 + 3) & ~3; }   // zero-padded cum window
+inline size_t att_fwd_smem(int Ti, int KA, int A, int D, int C2) {
+  return sizeof(float) * (size_t)((KA + 1) * A + att_cumlen(Ti, KA) + A + ((Ti + 3) & ~3) + D + 8 * C2 + 32) + 64;
+}
 __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
   extern __shared__ __align__(16) float sm[];
   pdl_wait();
   pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Ti = a.Ti, A = a.A, half = a.KA / 2;
-  const int Tip = (Ti + 3) & ~3, cumlen = (Ti + 2 * half + 5) & ~3;
+  const int Ti = a.Ti, A = a.A, half = a.KA / 2, NW = kAttThreads / 32;
+  const int Tip = (Ti + 3) & ~3, cumlen = att_cumlen(Ti, a.KA);
   float* U = sm;                        // [(KA+1)][A]
-  float* cum = U + (a.KA + 1) * A;      // [Ti + 2*half] zero-padded halo
+  float* cum = U + (a.KA + 1) * A;      // [cumlen] zero-padded halo
   float* q = cum + cumlen;              // [A]
   float* e = q + A;                     // [Ti]
   float* hs = e + Tip;                  // [D] query source as fp32
   float* part = hs + a.D;               // [8][C2] context partials
   float* red = part + 8 * a.C2;         // [32]
   for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) U[i] = a.U[i];
-  for (int i = tid; i < Ti + 2 * half; i += kAttThreads) {
+  for (int i = tid; i < cumlen; i += kAttThreads) {
     const int j = i - half;
     cum[i] = (j >= 0 && j < Ti) ? a.cum[(long long)b * Ti + j] : 0.f;
   }
@@ -478,24 +504,35 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
   __syncthreads();
   const int len = a.lens[b];
   const int nq = A >> 2;   // float4 groups per row (<= 32)
-  for (int j = warp; j < Ti; j += kAttThreads / 32) {
-    float acc = 0.f;
-    if (lane < nq && j < len) {
-      const int c = lane * 4;
-      float4 pl = *reinterpret_cast<const float4*>(U + a.KA * A + c);   // u0
-      for (int k = 0; k < a.KA; ++k) {
-        const float cj = cum[j + k];
-        const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
-        pl.x += cj * u.x; pl.y += cj * u.y; pl.z += cj * u.z; pl.w += cj * u.w;
+  const int nchunk = (Ti + kAttR - 1) / kAttR;
+  for (int ch = warp; ch < nchunk; ch += NW) {
+    const int j0 = ch * kAttR, c = lane * 4;
+    float er[kAttR];
+#pragma unroll
+    for (int r = 0; r < kAttR; ++r) er[r] = 0.f;
+    if (j0 < len) {   // warp-uniform
+      if (lane < nq) {
+        float4 pl[kAttR];
+        loc_features(U, cum, j0, a.KA, A, c, pl);
+        const float4 qq = *reinterpret_cast<const float4*>(q + c);
+        const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
+#pragma unroll
+        for (int r = 0; r < kAttR; ++r) {
+          if (j0 + r < len) {
+            const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j0 + r) * A + c));
+            er[r] = vv.x * tanhf_(ky.x + qq.x + pl[r].x) + vv.y * tanhf_(ky.y + qq.y + pl[r].y) + vv.z * tanhf_(ky.z + qq.z + pl[r].z) +
+                    vv.w * tanhf_(ky.w + qq.w + pl[r].w);
+          }
+        }
       }
-      const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j) * A + c));
-      const float4 qq = *reinterpret_cast<const float4*>(q + c);
-      const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
-      acc = vv.x * tanhf_(ky.x + qq.x + pl.x) + vv.y * tanhf_(ky.y + qq.y + pl.y) + vv.z * tanhf_(ky.z + qq.z + pl.z) +
-            vv.w * tanhf_(ky.w + qq.w + pl.w);
+#pragma unroll
+      for (int r = 0; r < kAttR; ++r) er[r] = warp_sum(er[r]);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) e[j] = j < len ? acc : -INFINITY;
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kAttR; ++r)
+        if (j0 + r < Ti) e[j0 + r] = j0 + r < len ? er[r] : -INFINITY;
+    }
   }
   __syncthreads();
   float mx = -INFINITY;
@@ -529,8 +566,10 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      const uint4* vp = reinterpret_cast<const uint4*>(a.values + (long long)b * Ti * a.C2) + ch;
+#pragma unroll 4
       for (int j = rg; j < len; j += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(a.values + ((long long)b * Ti + j) * a.C2) + ch);
+        const uint4 u = __ldg(vp + (long long)j * nch);
         const float al = e[j];
         acc[0] += al * bf16lo(u.x); acc[1] += al * bf16hi(u.x); acc[2] += al * bf16lo(u.y); acc[3] += al * bf16hi(u.y);
         acc[4] += al * bf16lo(u.z); acc[5] += al * bf16hi(u.z); acc[6] += al * bf16lo(u.w); acc[7] += al * bf16hi(u.w);
@@ -849,15 +888,20 @@ struct AttBwd {
   float* acc;              // per item: dU [(KA+1)][A] (row KA = d u0) | dv [A]
   int B, Ti, D, A, KA, C2;
 };
+inline size_t att_bwd_smem(int Ti, int KA, int A, int D, int C2) {
+  const int Tip = (Ti + 3) & ~3;
+  return sizeof(float) * (size_t)((KA + 1) * A + att_cumlen(Ti, KA) + A + 2 * Tip + D + C2 + 2 * A + (att_tipr(Ti) + 2 * (KA / 2)) * A + 32) + 64;
+}
 __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
   extern __shared__ __align__(16) float sm[];
   pdl_wait();
   pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Ti = a.Ti, A = a.A, half = a.KA / 2, NW = kAttThreads / 32;
-  const int Tip = (Ti + 3) & ~3, cumlen = (Ti + 2 * half + 5) & ~3;
+  const int Tip = (Ti + 3) & ~3, cumlen = att_cumlen(Ti, a.KA), TiR = att_tipr(Ti);
+  const int nE = (TiR + 2 * half) * A;    // dE rows: position j lives in row j + half; everything else stays zero
   float* U = sm;                          // [(KA+1)][A]
-  float* cum = U + (a.KA + 1) * A;        // [Ti + 2*half] cum_{t-1}, zero-padded
+  float* cum = U + (a.KA + 1) * A;        // [cumlen] cum_{t-1}, zero-padded
   float* q = cum + cumlen;                // [A]
   float* al = q + A;                      // [Ti]
   float* de = al + Tip;                   // [Ti]
@@ -865,11 +909,11 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
   float* dctx = hs + a.D;                 // [C2]
   float* dq = dctx + a.C2;                // [A]
   float* dv = dq + A;                     // [A]
-  float* dE = dv + A;                     // [Ti + 2*half][A], rows shifted by `half`, zero halo
-  float* red = dE + (Ti + 2 * half) * A;  // [32]
+  float* dE = dv + A;                     // [TiR + 2*half][A]
+  float* red = dE + nE;                   // [32]
   const int len = a.lens[b];
   for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) U[i] = a.U[i];
-  for (int i = tid; i < Ti + 2 * half; i += kAttThreads) {
+  for (int i = tid; i < cumlen; i += kAttThreads) {
     const int j = i - half;
     float cp = 0.f;
     if (j >= 0 && j < Ti) {
@@ -887,30 +931,38 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
     a.dctx_save[(long long)b * a.C2 + c] = __float2bfloat16(g);
   }
   for (int i = tid; i < A; i += kAttThreads) { dq[i] = 0.f; dv[i] = 0.f; }
-  for (int i = tid; i < 2 * half * A; i += kAttThreads) {   // zero halo rows of dE
-    const int r = i / A, c = i % A;
-    dE[(r < half ? r : Ti + r) * A + c] = 0.f;
-  }
+  for (int i = tid * 4; i < nE; i += kAttThreads * 4) *reinterpret_cast<float4*>(dE + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   att_query(a.WqT, hs, q, A, a.D);
-  // d alpha[j] = dctx . values[j] + dcum[j] : one warp per row, 8-wide bf16 loads
+  // d alpha[j] = dctx . values[j] + dcum[j] : one warp per row, 8-wide bf16 loads, two rows in flight
   float part = 0.f;
-  for (int j = warp; j < Ti; j += NW) {
-    float acc = 0.f;
-    if (j < len) {
-      const uint4* vr = reinterpret_cast<const uint4*>(a.values + ((long long)b * Ti + j) * a.C2);
-      for (int ch = lane; ch < (a.C2 >> 3); ch += 32) {
-        const uint4 u = __ldg(vr + ch);
+  {
+    const int nch = a.C2 >> 3;
+    const uint4* vb = reinterpret_cast<const uint4*>(a.values + (long long)b * Ti * a.C2);
+    for (int j = warp; j < Ti; j += 2 * NW) {
+      const int j2 = j + NW;
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int ch = lane; ch < nch; ch += 32) {
+        uint4 u0 = make_uint4(0, 0, 0, 0), u1 = make_uint4(0, 0, 0, 0);
+        if (j < len) u0 = __ldg(vb + (long long)j * nch + ch);
+        if (j2 < len) u1 = __ldg(vb + (long long)j2 * nch + ch);
         const float* d = dctx + ch * 8;
-        acc += d[0] * bf16lo(u.x) + d[1] * bf16hi(u.x) + d[2] * bf16lo(u.y) + d[3] * bf16hi(u.y) + d[4] * bf16lo(u.z) + d[5] * bf16hi(u.z) +
-               d[6] * bf16lo(u.w) + d[7] * bf16hi(u.w);
+        acc0 += d[0] * bf16lo(u0.x) + d[1] * bf16hi(u0.x) + d[2] * bf16lo(u0.y) + d[3] * bf16hi(u0.y) + d[4] * bf16lo(u0.z) +
+                d[5] * bf16hi(u0.z) + d[6] * bf16lo(u0.w) + d[7] * bf16hi(u0.w);
+        acc1 += d[0] * bf16lo(u1.x) + d[1] * bf16hi(u1.x) + d[2] * bf16lo(u1.y) + d[3] * bf16hi(u1.y) + d[4] * bf16lo(u1.z) +
+                d[5] * bf16hi(u1.z) + d[6] * bf16lo(u1.w) + d[7] * bf16hi(u1.w);
       }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float da = j < len ? acc + a.dcum[(long long)b * Ti + j] : 0.f;
-      de[j] = da;
-      part += al[j] * da;
+      acc0 = warp_sum(acc0); acc1 = warp_sum(acc1);
+      if (lane == 0) {
+        const float da0 = j < len ? acc0 + a.dcum[(long long)b * Ti + j] : 0.f;
+        de[j] = da0;
+        part += al[j] * da0;
+        if (j2 < Ti) {
+          const float da1 = j2 < len ? acc1 + a.dcum[(long long)b * Ti + j2] : 0.f;
+          de[j2] = da1;
+          part += al[j2] * da1;
+        }
+      }
     }
   }
   if (lane == 0) red[warp] = part;
@@ -920,41 +972,38 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
   __syncthreads();
   for (int j = tid; j < Ti; j += kAttThreads) de[j] = al[j] * (de[j] - dot);
   __syncthreads();
-  // energies backward: warp per row, lane = 4 channels
+  // energies backward: kAttR consecutive rows per warp pass, lane = 4 channels (same register blocking as the forward)
   {
-    const int nq = A >> 2;
+    const int nq = A >> 2, c = lane * 4;
+    const int nchunk = (Ti + kAttR - 1) / kAttR;
     float4 sdq = make_float4(0, 0, 0, 0), sdv = make_float4(0, 0, 0, 0);
-    for (int j = warp; j < Ti; j += NW) {
-      if (lane < nq) {
-        const int c = lane * 4;
-        float4 d4 = make_float4(0, 0, 0, 0);
+    for (int ch = warp; ch < nchunk; ch += NW) {
+      const int j0 = ch * kAttR;
+      if (j0 >= len || lane >= nq) continue;
+      float4 pl[kAttR];
+      loc_features(U, cum, j0, a.KA, A, c, pl);
+      const float4 qq = *reinterpret_cast<const float4*>(q + c);
+      const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
+#pragma unroll
+      for (int r = 0; r < kAttR; ++r) {
+        const int j = j0 + r;
         if (j < len) {
-          float4 pl = *reinterpret_cast<const float4*>(U + a.KA * A + c);
-          for (int k = 0; k < a.KA; ++k) {
-            const float cj = cum[j + k];
-            const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
-            pl.x += cj * u.x; pl.y += cj * u.y; pl.z += cj * u.z; pl.w += cj * u.w;
-          }
-          float4* kp = reinterpret_cast<float4*>(a.dkeys + ((long long)b * Ti + j) * A + c);
           const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j) * A + c));
-          const float4 qq = *reinterpret_cast<const float4*>(q + c);
-          const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
           const float dej = de[j];
-          const float t0 = tanhf_(ky.x + qq.x + pl.x), t1 = tanhf_(ky.y + qq.y + pl.y), t2 = tanhf_(ky.z + qq.z + pl.z),
-                      t3 = tanhf_(ky.w + qq.w + pl.w);
+          const float t0 = tanhf_(ky.x + qq.x + pl[r].x), t1 = tanhf_(ky.y + qq.y + pl[r].y), t2 = tanhf_(ky.z + qq.z + pl[r].z),
+                      t3 = tanhf_(ky.w + qq.w + pl[r].w);
+          float4 d4;
           d4.x = dej * vv.x * (1.f - t0 * t0); d4.y = dej * vv.y * (1.f - t1 * t1);
           d4.z = dej * vv.z * (1.f - t2 * t2); d4.w = dej * vv.w * (1.f - t3 * t3);
           sdv.x += dej * t0; sdv.y += dej * t1; sdv.z += dej * t2; sdv.w += dej * t3;
           sdq.x += d4.x; sdq.y += d4.y; sdq.z += d4.z; sdq.w += d4.w;
-          float4 kk = *kp;
-          kk.x += d4.x; kk.y += d4.y; kk.z += d4.z; kk.w += d4.w;
-          *kp = kk;
+          // accumulate over decoder steps without reading back (vector reduction, no load latency on the chain)
+          atomicAdd(reinterpret_cast<float4*>(a.dkeys + ((long long)b * Ti + j) * A + c), d4);
+          *reinterpret_cast<float4*>(dE + (j + half) * A + c) = d4;
         }
-        *reinterpret_cast<float4*>(dE + (j + half) * A + c) = d4;
       }
     }
     if (lane < nq) {
-      const int c = lane * 4;
       atomicAdd(&dq[c], sdq.x); atomicAdd(&dq[c + 1], sdq.y); atomicAdd(&dq[c + 2], sdq.z); atomicAdd(&dq[c + 3], sdq.w);
       atomicAdd(&dv[c], sdv.x); atomicAdd(&dv[c + 1], sdv.y); atomicAdd(&dv[c + 2], sdv.z); atomicAdd(&dv[c + 3], sdv.w);
     }
@@ -966,36 +1015,72 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
     accp[a.KA * A + c] += dq[c];          // d u0 (also the gradient of attention_bias)
     accp[(a.KA + 1) * A + c] += dv[c];
   }
-  // dU[k][a] += sum_j cum_{t-1}[j + k - half] dE[j][a]
-  for (int i = tid; i < a.KA * A; i += kAttThreads) {
-    const int k = i / A, c = i % A;
-    float acc = 0.f;
-    for (int j = 0; j < len; ++j) acc += cum[j + k] * dE[(j + half) * A + c];
-    accp[i] += acc;
+  // dU[k][c] += sum_j cum_{t-1}[j + k - half] dE[j][c]: thread = (channel c, group of <= 8 taps); one dE load and one
+  // cum load (sliding window) feed 8 FMAs
+  {
+    const int groups = kAttThreads / A, tpg = (a.KA + groups - 1) / groups;   // tpg <= 8 (A <= 128, KA <= 31)
+    const int c = tid % A, kg = tid / A;
+    if (kg < groups && kg * tpg < a.KA) {
+      const int k0 = kg * tpg;
+      float acc[8], w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i] = 0.f; w[i] = cum[k0 + i]; }
+      for (int j = 0; j < len; ++j) {
+        const float d = dE[(j + half) * A + c];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += w[i] * d;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) w[i] = w[i + 1];
+        w[7] = cum[j + 1 + k0 + 7];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < tpg && k0 + i < a.KA) accp[(k0 + i) * A + c] += acc[i];
+    }
   }
-  // dcum_{t-1}[i] = dcum_t[i] + sum_{k,a} dE[i - k + half][a] U[k][a]   (warp per i, lane = 4 channels)
-  for (int i = warp; i < Ti; i += NW) {
-    float acc = 0.f;
-    if (lane < (A >> 2)) {
-      const int c = lane * 4;
-      for (int k = 0; k < a.KA; ++k) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dE + (i - k + 2 * half) * A + c);   // row (i - k + half) + half
-        const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
-        acc += d4.x * u.x + d4.y * u.y + d4.z * u.z + d4.w * u.w;
+  // dcum_{t-1}[i] = dcum_t[i] + sum_{k,c} dE[i - k + half][c] U[k][c]: kAttR consecutive i per warp pass, the dE rows slide
+  // through a register window (row index of (i, k) is i - k + 2*half)
+  {
+    const int nq = A >> 2, c = lane * 4;
+    const int nchunk = (Ti + kAttR - 1) / kAttR;
+    for (int ch = warp; ch < nchunk; ch += NW) {
+      const int i0 = ch * kAttR;
+      float acc[kAttR];
+#pragma unroll
+      for (int r = 0; r < kAttR; ++r) acc[r] = 0.f;
+      if (lane < nq) {
+        float4 w[kAttR];
+#pragma unroll
+        for (int r = 0; r < kAttR; ++r) w[r] = *reinterpret_cast<const float4*>(dE + (i0 + r + 2 * half) * A + c);
+        for (int k = 0; k < a.KA; ++k) {
+          const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
+#pragma unroll
+          for (int r = 0; r < kAttR; ++r) acc[r] += w[r].x * u.x + w[r].y * u.y + w[r].z * u.z + w[r].w * u.w;
+#pragma unroll
+          for (int r = kAttR - 1; r > 0; --r) w[r] = w[r - 1];
+          if (k + 1 < a.KA) w[0] = *reinterpret_cast<const float4*>(dE + (i0 - (k + 1) + 2 * half) * A + c);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kAttR; ++r) acc[r] = warp_sum(acc[r]);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < kAttR; ++r)
+          if (i0 + r < Ti) atomicAdd(a.dcum + (long long)b * Ti + i0 + r, acc[r]);
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) a.dcum[(long long)b * Ti + i] += acc;
   }
-  // dh2ext = dPI[:, 0:D] + dq . Wq^T
-  for (int k = tid; k < a.D; k += kAttThreads) {
-    float acc = a.dPI[(long long)b * a.ld_dPI + k];
-    const float4* w = reinterpret_cast<const float4*>(a.Wq + (long long)k * A);
-    for (int c = 0; c < (A >> 2); ++c) {
-      const float4 ww = __ldg(w + c);
-      acc += dq[c * 4] * ww.x + dq[c * 4 + 1] * ww.y + dq[c * 4 + 2] * ww.z + dq[c * 4 + 3] * ww.w;
+  // dh2ext = dPI[:, 0:D] + dq . Wq^T   (bf16 [A][D] copy of the query weights: coalesced along D)
+  for (int k2 = tid; k2 < (a.D >> 1); k2 += kAttThreads) {
+    const float2 g = *reinterpret_cast<const float2*>(a.dPI + (long long)b * a.ld_dPI + 2 * k2);
+    float a0 = g.x, a1 = g.y;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a.WqT) + k2;
+#pragma unroll 8
+    for (int c = 0; c < A; ++c) {
+      const uint32_t u = __ldg(w + (long long)c * (a.D >> 1));
+      a0 += dq[c] * bf16lo(u); a1 += dq[c] * bf16hi(u);
     }
-    a.dh2ext[(long long)b * a.D + k] = acc;
+    *reinterpret_cast<float2*>(a.dh2ext + (long long)b * a.D + 2 * k2) = make_float2(a0, a1);
   }
 }
 // after the loop: reduce the per-item accumulators over the batch and push dU / du0 / dv through the U = K . Wl
@@ -1195,7 +1280,7 @@ static int decoder_reset(const StepCtx& s, DecBufs& d) {
   T2_CHECK_CUDA(cudaMemsetAsync(d.cum, 0, (size_t)B * Ti * 4, st));
   att_prep_kernel<<<g1((lo.KA + 1) * lo.A), 256, 0, st>>>(d_params + lo.p_lck, d_params + lo.p_lcb, d_params + lo.p_lfl, d_params + lo.p_ba, d.attU,
                                                        lo.KA, lo.F, lo.A); t2_count_launch();
-  d.att_smem = sizeof(float) * (size_t)((lo.KA + 1) * lo.A + Ti + lo.KA + 8 + lo.A + Ti + 4 + D + 8 * 2 * H + 32) + 64;
+  d.att_smem = att_fwd_smem(Ti, lo.KA, lo.A, D, 2 * H);
   T2_CHECK_CUDA(cudaFuncSetAttribute(att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(d.att_smem)));
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
@@ -1359,7 +1444,7 @@ extern "C" int t2_taco_infer_steps(const t2_taco_config_t* cfg, float* d_params,
   db.cum = reinterpret_cast<float*>(ws + lo.w_cum); db.attU = reinterpret_cast<float*>(ws + lo.w_attU);
   db.keys = reinterpret_cast<float*>(ws + lo.w_keys); db.values = reinterpret_cast<bf16*>(ws + lo.w_values);
   db.pre1 = reinterpret_cast<float*>(ws + lo.w_pre1);
-  db.att_smem = sizeof(float) * (size_t)((lo.KA + 1) * lo.A + lo.Ti + lo.KA + 8 + lo.A + lo.Ti + 4 + D + 8 * 2 * H + 32) + 64;
+  db.att_smem = att_fwd_smem(lo.Ti, lo.KA, lo.A, D, 2 * H);
   bf16* decin = reinterpret_cast<bf16*>(ws + lo.w_decin);
   bf16* pn1 = reinterpret_cast<bf16*>(ws + lo.w_pn1);
   bf16* pn2 = reinterpret_cast<bf16*>(ws + lo.w_pn2);
@@ -1527,7 +1612,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   bf16* dg2 = reinterpret_cast<bf16*>(ws + lo.w_dg2);
   bf16* dctx_all = reinterpret_cast<bf16*>(ws + lo.w_dctx_all);
   bf16* dq_all = reinterpret_cast<bf16*>(ws + lo.w_dq_all);
-  const size_t ab_smem = sizeof(float) * (size_t)((lo.KA + 1) * A + Ti + lo.KA + 8 + A + 2 * Ti + 8 + D + 2 * H + 2 * A + (Ti + lo.KA) * A + 32) + 64;
+  const size_t ab_smem = att_bwd_smem(Ti, lo.KA, A, D, 2 * H);
   const float* attU = reinterpret_cast<const float*>(ws + lo.w_attU);
   T2_CHECK_CUDA(cudaFuncSetAttribute(att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ab_smem)));
   for (int t = To - 1; t >= 0; --t) {
