@@ -125,6 +125,11 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
   g.dbg = g_timing_buffer;
   g.epi = c.epi;
   dim3 grid(g.tiles_per_b * c.B, c.n_tiles, 1);
+  if (c.ksplit > 1) {
+    T2_REQUIRE(epi == EPI_TOUT && c.ksplit * kBK <= ktot, T2_ERR_INVALID_ARG,
+               "act_gemm: split-K needs an atomically accumulating epilogue and at least one k-block per slice");
+    grid.z = c.ksplit;
+  }
 #define T2_CASE(E, N) \
   if (epi == E && BN == N) return launch_one<E, N>(g, grid, stream);
   if (epi == EPI_GATE && BN == 256 && c.n_tiles % 2 == 0) return launch_one<EPI_GATE, 256, 2>(g, grid, stream);

@@ -752,7 +752,8 @@ struct Epilogue<EPI_LSTM, 32> {
 };
 
 // transposed fp32 output of a swapped GEMM: accumulator rows = features k, columns = batch items b.
-// rows [0, i0) -> ptr0[b*i1 + k], rows [i0, i3) -> ptr1[b*i4 + (k - i0)]; i2 / i5 = 1: accumulate (+=); i6 = B
+// rows [0, i0) -> ptr0[b*i1 + k], rows [i0, i3) -> ptr1[b*i4 + (k - i0)]; i2 / i5 = 0 overwrite, 1 accumulate (+=), 2 atomic
+// accumulate (required with split-K); i6 = B
 template <>
 struct Epilogue<EPI_TOUT, 32> {
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
@@ -770,7 +771,8 @@ struct Epilogue<EPI_TOUT, 32> {
       const int b = c.n_tile * 32 + j;
       if (b < nb) {
         float* d = dst + size_t(b) * ld + kk;
-        *d = acc ? *d + v[j] : v[j];
+        if (acc == 2) atomicAdd(d, v[j]);      // split-K: several CTAs own slices of the reduction
+        else *d = acc ? *d + v[j] : v[j];
       }
     }
   }
@@ -812,8 +814,12 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   const int b = m_tile / g.tiles_per_b;
   const int t0 = (m_tile - b * g.tiles_per_b) * kBM;
 
-  int total_kb = 0;
-  for (int s = 0; s < g.nseg; ++s) total_kb += g.seg[s].nkb * g.seg[s].nlayers;
+  int all_kb = 0;
+  for (int s = 0; s < g.nseg; ++s) all_kb += g.seg[s].nkb * g.seg[s].nlayers;
+  // split-K: gridDim.z CTAs share one output tile, each reducing a contiguous slice of the k-blocks (the epilogue must
+  // then accumulate atomically)
+  const int kb_lo = int((long long)all_kb * blockIdx.z / gridDim.z), kb_hi = int((long long)all_kb * (blockIdx.z + 1) / gridDim.z);
+  const int total_kb = kb_hi - kb_lo;
 
   if (warp == 0 && elect_one()) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&g.amap[i]);
@@ -851,6 +857,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
           const Seg sg = g.seg[s];
           for (int l = 0; l < sg.nlayers; ++l) {
             for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
+              if (kb_global < kb_lo || kb_global >= kb_hi) continue;
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
               uint8_t* sa = smem + stage * Cfg::kStageBytes;

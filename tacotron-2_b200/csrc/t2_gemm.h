@@ -27,6 +27,7 @@ struct ActGemmCall {
   int wN, wK, wL, w_layer, w_k0;
   int T, B;
   int n_tiles;     // grid.y
+  int ksplit;      // grid.z: CTAs sharing one output tile over slices of K (0/1 = off; epilogue must accumulate atomically)
   EpiArgs epi;
 };
 

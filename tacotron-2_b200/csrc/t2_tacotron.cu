@@ -814,7 +814,8 @@ __global__ void reg_grad_kernel(const float* __restrict__ params, float* __restr
 
 // backward of one LSTM cell + zoneout (see EPI_LSTM): produces the pre-activation gate gradients and the state grads
 struct CellBwd {
-  const float* dh_ext; long long ld_ext;      // grad wrt the un-zoned output h_new: dh_ext[b*ld_ext + u]
+  float* dh_ext; long long ld_ext;            // grad wrt the un-zoned output h_new: dh_ext[b*ld_ext + u]
+  int zero_ext;                                // clear dh_ext after reading (its producer accumulates atomically, split-K)
   float* dhs; float* dcs;                      // [B][H] running grads wrt the carried (zoned) state (in/out)
   const bf16* gst; const bf16* tst; const float* c_prev;
   bf16* dg_a; long long ld_a;                  // gate grads, gate-major [4H] per batch row (row stride ld_a)
@@ -841,6 +842,7 @@ __global__ void lstm_cell_bwd_kernel(CellBwd a) {
     const bool mh = a.zone <= 0.f || hash_uniform32(hash_seed(seed, uint32_t(a.stream) * 2u + 1u), idx) >= a.zone;
     const float dhs = a.dhs[e], dcs = a.dcs[e];
     const float dh_new = a.dh_ext[(long long)b * a.ld_ext + u] + (mh ? dhs : 0.f);
+    if (a.zero_ext) a.dh_ext[(long long)b * a.ld_ext + u] = 0.f;
     const float dc_new = (mc ? dcs : 0.f) + dh_new * go * (1.f - tc * tc);
     dzo = dh_new * tc * go * (1.f - go);
     dzi = dc_new * gj * gi * (1.f - gi);
@@ -859,13 +861,15 @@ __global__ void lstm_cell_bwd_kernel(CellBwd a) {
 
 // backward step GEMM: dS^T [K rows][B] = W^T-packed [K][4H] x dgates [B][4H]^T, rows split over two fp32 destinations
 int lstm_bwd_gemm(const StepCtx& s, const void* wT, int K, int H4, const void* dg, int B, float* dst0, int rows0, int ld0, int acc0, float* dst1,
-                  int ld1, int acc1) {
+                  int ld1, int acc1, int ksplit) {
   ActGemmCall g;
   memset(&g, 0, sizeof(g));
   g.a[0] = make_act(wT, H4, K, 1, 1, H4); g.na = 1;
   g.seg[0] = Seg{0, 0, 0, H4 / kBK, 0, 1}; g.nseg = 1;
   g.w = dg; g.wN = B; g.wK = H4; g.wL = 1;
   g.T = K; g.B = 1; g.n_tiles = (B + 31) / 32;
+  // few output tiles (K / 128 <= 16) but a long reduction (4H): slice the reduction over `ksplit` CTAs per tile
+  g.ksplit = ksplit;
   g.epi.ptr[0] = dst0; g.epi.ptr[1] = dst1;
   g.epi.i[0] = rows0; g.epi.i[1] = ld0; g.epi.i[2] = acc0; g.epi.i[3] = K; g.epi.i[4] = ld1; g.epi.i[5] = acc1; g.epi.i[6] = B;
   return launch_act_gemm(EPI_TOUT, 32, g, s.st);
@@ -880,7 +884,7 @@ struct AttBwd {
   float* cumrun;           // [B][Ti]: cum_t on entry, cum_{t-1} on exit
   float* dcum;             // [B][Ti] running grad wrt cum_t (in) / cum_{t-1} (out)
   const float* dPI; int ld_dPI;   // dPI_all[t]: [B][PIK] fp32
-  const float* dctxl;      // [B][C2] grad wrt ctx_t from LSTM-1 of step t+1
+  float* dctxl;            // [B][C2] grad wrt ctx_t from LSTM-1 of step t+1 (read, then cleared for the split-K accumulation)
   float* dh2ext;           // [B][D] out: grad wrt the un-zoned LSTM-2 output of this step
   bf16* dctx_save;         // [B][C2]
   bf16* dq_save;           // [B][A]
@@ -927,6 +931,7 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
   for (int i = tid; i < a.D; i += kAttThreads) hs[i] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
   for (int c = tid; c < a.C2; c += kAttThreads) {
     const float g = a.dPI[(long long)b * a.ld_dPI + a.D + c] + a.dctxl[(long long)b * a.C2 + c];
+    a.dctxl[(long long)b * a.C2 + c] = 0.f;
     dctx[c] = g;
     a.dctx_save[(long long)b * a.C2 + c] = __float2bfloat16(g);
   }
@@ -1604,6 +1609,8 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   const int nacc = (lo.KA + 2) * A;
   for (float* p : {dhs1, dhs2, dcs1, dcs2}) T2_CHECK_CUDA(cudaMemsetAsync(p, 0, (size_t)B * D * 4, st));
   T2_CHECK_CUDA(cudaMemsetAsync(dctxl, 0, (size_t)B * 2 * H * 4, st));
+  T2_CHECK_CUDA(cudaMemsetAsync(dh1ext, 0, (size_t)B * D * 4, st));
+  const int ks_dec = (4 * D / kBK) >= 16 ? 8 : 1, ks_enc = (4 * H / kBK) >= 16 ? 8 : 1;   // k-blocks per slice >= 2
   T2_CHECK_CUDA(cudaMemsetAsync(dcum, 0, (size_t)B * Ti * 4, st));
   T2_CHECK_CUDA(cudaMemsetAsync(dkeys, 0, (size_t)B * Ti * A * 4, st));
   T2_CHECK_CUDA(cudaMemsetAsync(attacc, 0, (size_t)B * nacc * 4, st));
@@ -1626,20 +1633,20 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
     a.B = B; a.Ti = Ti; a.D = D; a.A = A; a.KA = lo.KA; a.C2 = 2 * H;
     T2_CHECK_CUDA(launch_pdl(att_bwd_kernel, dim3(B), dim3(kAttThreads), ab_smem, st, a)); t2_count_launch();
     CellBwd c2;
-    c2.dh_ext = dh2ext; c2.ld_ext = D; c2.dhs = dhs2; c2.dcs = dcs2;
+    c2.dh_ext = dh2ext; c2.zero_ext = 0; c2.ld_ext = D; c2.dhs = dhs2; c2.dcs = dcs2;
     c2.gst = reinterpret_cast<const bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D; c2.tst = reinterpret_cast<const bf16*>(ws + lo.w_t2) + (long long)t * B * D;
     c2.c_prev = reinterpret_cast<const float*>(ws + lo.w_c2) + (long long)t * B * D;
     c2.dg_a = dg2 + (long long)t * B * 4 * D; c2.ld_a = 4 * D; c2.dg_b = nullptr; c2.ld_b = 0; c2.lens = nullptr; c2.t = t; c2.B = B; c2.H = D; c2.stream = 5;
     c2.zone = lo.c.zoneout_rate; c2.seed = seed; c2.step = d_step;
     T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * D)), dim3(256), 0, st, c2)); t2_count_launch();
-    rc = lstm_bwd_gemm(s, pk + lo.k_l2T, K2, 4 * D, c2.dg_a, B, dh1ext, D, D, 0, dhs2, D, 1);
+    rc = lstm_bwd_gemm(s, pk + lo.k_l2T, K2, 4 * D, c2.dg_a, B, dh1ext, D, D, 2, dhs2, D, 2, ks_dec);   // dh1ext: zeroed by its consumer
     if (rc) return rc;
     CellBwd c1 = c2;
-    c1.dh_ext = dh1ext; c1.dhs = dhs1; c1.dcs = dcs1;
+    c1.dh_ext = dh1ext; c1.zero_ext = 1; c1.dhs = dhs1; c1.dcs = dcs1;
     c1.gst = reinterpret_cast<const bf16*>(ws + lo.w_g1) + (long long)t * B * 4 * D; c1.tst = reinterpret_cast<const bf16*>(ws + lo.w_t1) + (long long)t * B * D;
     c1.c_prev = reinterpret_cast<const float*>(ws + lo.w_c1) + (long long)t * B * D; c1.dg_a = dg1 + (long long)t * B * 4 * D; c1.stream = 4;
     T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * D)), dim3(256), 0, st, c1)); t2_count_launch();
-    rc = lstm_bwd_gemm(s, pk + lo.k_l1rT, K1r, 4 * D, c1.dg_a, B, dctxl, 2 * H, 2 * H, 0, dhs1, D, 1);
+    rc = lstm_bwd_gemm(s, pk + lo.k_l1rT, K1r, 4 * D, c1.dg_a, B, dctxl, 2 * H, 2 * H, 2, dhs1, D, 2, ks_dec);  // dctxl: zeroed by att_bwd
     if (rc) return rc;
   }
   T2_CHECK_CUDA(cudaGetLastError());
@@ -1704,14 +1711,14 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
     for (int sidx = Ti - 1; sidx >= 0; --sidx) {
       const int t = d == 0 ? sidx : Ti - 1 - sidx;
       CellBwd c;
-      c.dh_ext = dvalues + (long long)t * 2 * H + d * H; c.ld_ext = (long long)Ti * 2 * H; c.dhs = edh; c.dcs = edc;
+      c.zero_ext = 0; c.dh_ext = dvalues + (long long)t * 2 * H + d * H; c.ld_ext = (long long)Ti * 2 * H; c.dhs = edh; c.dcs = edc;
       c.gst = reinterpret_cast<const bf16*>(ws + lo.w_encg[d]) + (long long)sidx * B * 4 * H;
       c.tst = reinterpret_cast<const bf16*>(ws + lo.w_enct[d]) + (long long)sidx * B * H;
       c.c_prev = reinterpret_cast<const float*>(ws + lo.w_encc[d]) + (long long)sidx * B * H;
       c.dg_a = dgall + (long long)sidx * B * 4 * H; c.ld_a = 4 * H; c.dg_b = dpre + (long long)t * 4 * H; c.ld_b = (long long)Ti * 4 * H;
       c.lens = d_input_lengths; c.t = t; c.B = B; c.H = H; c.stream = 2 + d; c.zone = lo.c.zoneout_rate; c.seed = seed; c.step = d_step;
       T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * H)), dim3(256), 0, st, c)); t2_count_launch();
-      rc = lstm_bwd_gemm(s, pk + lo.k_encWrT[d], H, 4 * H, c.dg_a, B, edh, H, H, 1, nullptr, 0, 0);
+      rc = lstm_bwd_gemm(s, pk + lo.k_encWrT[d], H, 4 * H, c.dg_a, B, edh, H, H, 2, nullptr, 0, 0, ks_enc);
       if (rc) return rc;
     }
     {
