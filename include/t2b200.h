@@ -180,6 +180,8 @@ int t2_taco_infer_steps(const t2_taco_config_t* cfg, float* d_params, const void
                         const int* d_input_lengths, int t_begin, int t_end, unsigned long long seed, void* stream);
 int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, int T_used,
                          void* stream);
+/* tools only: clock64() phase stamps of the attention kernels into a device buffer of 32 int64 (NULL turns them off) */
+int t2_dbg_att_stamps(long long* d_buf);
 int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr,
                              long long* count, int* elem_bytes);
 

@@ -56,10 +56,16 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 // sigmoid / tanh on the SFU pipe: ex2.approx + rcp.approx (2 MUFU + 2-3 FMA-pipe ops per value, ~1e-7 absolute
 // error) instead of the IEEE-division sequence; the results are stored as bf16 anyway.
-__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.f + __expf(-x)); }
+// MUFU.RCP (<= 1 ulp): the IEEE-rounded __frcp_rn expands to a ~10-instruction fix-up sequence per call
+__device__ __forceinline__ float frcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return frcp_fast(1.f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) {
   const float e = __expf(-2.f * fabsf(x));
-  const float t = (1.f - e) * __frcp_rn(1.f + e);
+  const float t = (1.f - e) * frcp_fast(1.f + e);
   return copysignf(t, x);
 }
 // single-MUFU forms for values that are stored as bf16 right away (tanh.approx: max rel error 2^-11, bf16 keeps 2^-9)

@@ -410,6 +410,8 @@ __global__ void decin_kernel(const float* __restrict__ tgt, bf16* __restrict__ o
 // evaluated as ONE 31-tap filter bank U[k][a] = sum_f K[k][f] Wl[f][a] with offset u0[a] = sum_f bK[f] Wl[f][a] + b_a[a]
 // (built once per forward by att_prep_kernel); the backward pass differentiates through the same factorisation.
 constexpr int kAttThreads = 512;
+__device__ long long* g_att_dbg = nullptr;   // optional phase stamps (tools only): [0..15] forward, [16..31] backward
+#define ATT_STAMP(i) do { if (g_att_dbg && blockIdx.x == 0 && threadIdx.x == 0) g_att_dbg[i] = clock64(); } while (0)
 __global__ void att_prep_kernel(const float* __restrict__ K, const float* __restrict__ bK, const float* __restrict__ Wl,
                                 const float* __restrict__ ba, float* __restrict__ U, int KA, int F, int A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -434,109 +436,151 @@ struct AttArgs {
   bf16* ctx_b; int ld_b;                    // context -> PI_all[t][b][D:]
   int B, Ti, D, A, KA, C2;
 };
-// q[a] = sum_k h[k] WqT[a][k]: 4 threads per output, 8-wide bf16 loads
+// q[a] = sum_k h[k] WqT[a][k]: one warp per output row (two rows in flight), lanes stride the row in 16-byte pieces so
+// that every load instruction reads 512 contiguous bytes (the 4-threads-per-output form touched 32 sectors per load)
+// A length-D fp32 vector that is dotted against 16-byte bf16 pieces lives in shared memory in a SPLIT layout: element
+// 8p + x of the vector sits at xs[(x >> 2) * (D/2) + 4p + (x & 3)], so lane p reads two float4 at a 16-byte lane stride
+// (conflict-free); the natural layout (32-byte lane stride) made every one of these loads an 8-way bank conflict.
+__device__ __forceinline__ int split8(int i, int D) { return ((i >> 2) & 1) * (D >> 1) + ((i >> 3) << 2) + (i & 3); }
+__device__ __forceinline__ float dot8s(const uint4 u, const float* __restrict__ xs, int p, int D) {
+  const float4 lo = *reinterpret_cast<const float4*>(xs + 4 * p), hi = *reinterpret_cast<const float4*>(xs + (D >> 1) + 4 * p);
+  return bf16lo(u.x) * lo.x + bf16hi(u.x) * lo.y + bf16lo(u.y) * lo.z + bf16hi(u.y) * lo.w + bf16lo(u.z) * hi.x +
+         bf16hi(u.z) * hi.y + bf16lo(u.w) * hi.z + bf16hi(u.w) * hi.w;
+}
+// q[a] = sum_k h[k] WqT[a][k]: one warp per output row (two rows in flight), lanes stride the row in 16-byte pieces so
+// that every load instruction reads 512 contiguous bytes; hs is in the split layout above
 __device__ __forceinline__ void att_query(const bf16* __restrict__ WqT, const float* __restrict__ hs, float* __restrict__ q, int A, int D) {
-  for (int o = threadIdx.x >> 2; o < A; o += kAttThreads >> 2) {
-    const int part = threadIdx.x & 3;
-    const int kq = D >> 2;
-    const uint4* w = reinterpret_cast<const uint4*>(WqT + (long long)o * D + part * kq);
-    const float* h = hs + part * kq;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < (kq >> 3); ++c) {
-      const uint4 u = __ldg(w + c);
-      const float* hh = h + c * 8;
-      acc += bf16lo(u.x) * hh[0] + bf16hi(u.x) * hh[1] + bf16lo(u.y) * hh[2] + bf16hi(u.y) * hh[3] + bf16lo(u.z) * hh[4] +
-             bf16hi(u.z) * hh[5] + bf16lo(u.w) * hh[6] + bf16hi(u.w) * hh[7];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = kAttThreads / 32;
+  const int n16 = D >> 3;   // 16-byte pieces per row
+  for (int o = warp; o < A; o += 2 * NW) {
+    const int o2 = o + NW;
+    const uint4* w0 = reinterpret_cast<const uint4*>(WqT + (long long)o * D);
+    const uint4* w1 = reinterpret_cast<const uint4*>(WqT + (long long)(o2 < A ? o2 : o) * D);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int i = lane; i < n16; i += 32) {
+      const uint4 u0 = __ldg(w0 + i), u1 = __ldg(w1 + i);
+      a0 += dot8s(u0, hs, i, D);
+      a1 += dot8s(u1, hs, i, D);
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (part == 0) q[o] = acc;
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if (lane == 0) { q[o] = a0; if (o2 < A) q[o2] = a1; }
   }
 }
-// Location features for kAttR CONSECUTIVE memory rows j0 .. j0+R-1 and this lane's 4 channels:
-//   pl[r] = u0 + sum_k cum[j0 + r + k] * U[k]      (cum = zero-padded halo array, index j + k <-> position j + k - half)
-// Register blocking over rows: one LDS.128 of U[k] and one scalar LDS of the sliding cum window feed 4*R FMAs (the
-// row-at-a-time form did 2 shared-memory loads per 4 FMAs and was shared-memory-bandwidth bound).
-constexpr int kAttR = 10;
-__device__ __forceinline__ void loc_features(const float* __restrict__ U, const float* __restrict__ cum, int j0, int KA, int A, int c,
-                                             float4 (&pl)[kAttR]) {
-  const float4 u0 = *reinterpret_cast<const float4*>(U + KA * A + c);
-  float w[kAttR];
+// ---- the location filter bank on tensor cores -------------------------------------------------------------------
+// pl[j][n] = u0[n] + sum_k cum[j + k - half] U[k][n] is a [T_in x 32] Toeplitz matrix times the [32 x A] filter bank
+// (row KA of the bank is the offset u0, matched by a column of ones): per batch item 160 x 32 x 128 - far too small for a
+// tcgen05 tile pipeline, so it runs as warp-level mma.sync.m16n8k8 TF32 (fp32 accumulate) straight out of shared memory;
+// the Toeplitz operand is never materialised (fragments read cum[j + k]). The same instruction computes the three
+// products of the backward pass (dU = T^T dE, P = dE U^T for dcum). The scalar FMA form was issue/shared-memory bound:
+// 20 k (forward) / 55 k (backward) cycles per step at T_in = 160 (tools/att_phases.py).
+__device__ __forceinline__ uint32_t f2tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+// D(16x8) += A(16x8, row) * B(8x8, col); g = lane >> 2, t = lane & 3:
+//   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4) | b0 (k=t, n=g) b1 (k=t+4, n=g) | c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__host__ __device__ inline int att_ti16(int Ti) { return (Ti + 15) & ~15; }
+__host__ __device__ inline int att_cumlen(int Ti, int KA) { return (att_ti16(Ti) + KA + 16 + 3) & ~3; }   // zero-padded cum window
+__host__ __device__ inline int att_erows(int Ti, int KA) { return (att_ti16(Ti) + 2 * (KA / 2) + 15) & ~15; } // rows of dE (backward)
+constexpr int kAttPad = 8;   // row padding (floats) of the filter bank / dE tiles in shared memory: conflict-free fragments
+// Toeplitz element T[j][k]: cum window for the taps, a column of ones for the offset row, zero beyond
+__device__ __forceinline__ float toep(const float* __restrict__ cum, int j, int k, int KA) {
+  return k < KA ? cum[j + k] : (k == KA ? 1.f : 0.f);
+}
+// pl for the 16 rows j0.. and the 64 channels n0..: acc[nt] = C fragment of n-tile nt (8 channels each)
+__device__ __forceinline__ void loc_tile(const float* __restrict__ Us, int AP, const float* __restrict__ cum, int KA, int j0, int n0,
+                                         float (&acc)[8][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int r = 0; r < kAttR; ++r) { pl[r] = u0; w[r] = cum[j0 + r]; }
-  for (int k = 0; k < KA; ++k) {
-    const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
+  for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
-    for (int r = 0; r < kAttR; ++r) { pl[r].x += w[r] * u.x; pl[r].y += w[r] * u.y; pl[r].z += w[r] * u.z; pl[r].w += w[r] * u.w; }
+  for (int ks = 0; ks < 4; ++ks) {
+    const int k = ks * 8 + t;
+    uint32_t af[4];
+    af[0] = f2tf32(toep(cum, j0 + g, k, KA)); af[1] = f2tf32(toep(cum, j0 + g + 8, k, KA));
+    af[2] = f2tf32(toep(cum, j0 + g, k + 4, KA)); af[3] = f2tf32(toep(cum, j0 + g + 8, k + 4, KA));
+    const bool v0 = k <= KA, v1 = k + 4 <= KA;
 #pragma unroll
-    for (int r = 0; r + 1 < kAttR; ++r) w[r] = w[r + 1];
-    w[kAttR - 1] = cum[j0 + k + kAttR];
+    for (int nt = 0; nt < 8; ++nt) {
+      const int n = n0 + nt * 8 + g;
+      const uint32_t b0 = v0 ? f2tf32(Us[k * AP + n]) : 0u, b1 = v1 ? f2tf32(Us[(k + 4) * AP + n]) : 0u;
+      mma_tf32(acc[nt], af, b0, b1);
+    }
   }
 }
-__host__ __device__ inline int att_tipr(int Ti) { return (Ti + kAttR - 1) / kAttR * kAttR; }
-__host__ __device__ inline int att_cumlen(int Ti, int KA) { return (att_tipr(Ti) + KA + 16 + 3) & ~3; }   // zero-padded cum window
 inline size_t att_fwd_smem(int Ti, int KA, int A, int D, int C2) {
-  return sizeof(float) * (size_t)((KA + 1) * A + att_cumlen(Ti, KA) + A + ((Ti + 3) & ~3) + D + 8 * C2 + 32) + 64;
+  return sizeof(float) * (size_t)((KA + 1) * (A + kAttPad) + att_cumlen(Ti, KA) + A + ((Ti + 3) & ~3) + D + 8 * C2 + 32) + 64;
 }
 __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
   extern __shared__ __align__(16) float sm[];
   pdl_wait();
   pdl_launch_dependents();
+  ATT_STAMP(0);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Ti = a.Ti, A = a.A, half = a.KA / 2, NW = kAttThreads / 32;
+  const int Ti = a.Ti, A = a.A, AP = A + kAttPad, half = a.KA / 2, NW = kAttThreads / 32;
   const int Tip = (Ti + 3) & ~3, cumlen = att_cumlen(Ti, a.KA);
-  float* U = sm;                        // [(KA+1)][A]
-  float* cum = U + (a.KA + 1) * A;      // [cumlen] zero-padded halo
+  float* Us = sm;                       // [(KA+1)][AP] filter bank, row KA = offset u0
+  float* cum = Us + (a.KA + 1) * AP;    // [cumlen] zero-padded halo
   float* q = cum + cumlen;              // [A]
   float* e = q + A;                     // [Ti]
   float* hs = e + Tip;                  // [D] query source as fp32
   float* part = hs + a.D;               // [8][C2] context partials
   float* red = part + 8 * a.C2;         // [32]
-  for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) U[i] = a.U[i];
+  for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) Us[(i / A) * AP + (i % A)] = a.U[i];
   for (int i = tid; i < cumlen; i += kAttThreads) {
     const int j = i - half;
     cum[i] = (j >= 0 && j < Ti) ? a.cum[(long long)b * Ti + j] : 0.f;
   }
-  for (int i = tid; i < a.D; i += kAttThreads) hs[i] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
+  for (int i = tid; i < a.D; i += kAttThreads) hs[split8(i, a.D)] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
+  for (int i = tid; i < Tip; i += kAttThreads) e[i] = 0.f;
   __syncthreads();
+  ATT_STAMP(1);
   att_query(a.WqT, hs, q, A, a.D);
   __syncthreads();
+  ATT_STAMP(2);
   const int len = a.lens[b];
-  const int nq = A >> 2;   // float4 groups per row (<= 32)
-  const int nchunk = (Ti + kAttR - 1) / kAttR;
-  for (int ch = warp; ch < nchunk; ch += NW) {
-    const int j0 = ch * kAttR, c = lane * 4;
-    float er[kAttR];
+  {
+    // energies: units of 16 memory rows x 64 channels; e[j] += sum over the unit's channels of v tanh(keys + q + pl)
+    const int g = lane >> 2, t = lane & 3;
+    const int n_nh = A >> 6, n_units = ((len + 15) >> 4) * n_nh;
+    for (int u = warp; u < n_units; u += NW) {
+      const int j0 = (u / n_nh) * 16, n0 = (u % n_nh) * 64;
+      float acc[8][4];
+      loc_tile(Us, AP, cum, a.KA, j0, n0, acc);
+      const int r0 = j0 + g, r1 = r0 + 8;
+      const float* k0p = a.keys + ((long long)b * Ti + (r0 < len ? r0 : 0)) * A + n0 + 2 * t;
+      const float* k1p = a.keys + ((long long)b * Ti + (r1 < len ? r1 : 0)) * A + n0 + 2 * t;
+      float2 ky0[8], ky1[8];
 #pragma unroll
-    for (int r = 0; r < kAttR; ++r) er[r] = 0.f;
-    if (j0 < len) {   // warp-uniform
-      if (lane < nq) {
-        float4 pl[kAttR];
-        loc_features(U, cum, j0, a.KA, A, c, pl);
-        const float4 qq = *reinterpret_cast<const float4*>(q + c);
-        const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
+      for (int nt = 0; nt < 8; ++nt) { ky0[nt] = __ldg(reinterpret_cast<const float2*>(k0p + nt * 8)); ky1[nt] = __ldg(reinterpret_cast<const float2*>(k1p + nt * 8)); }
+      float e0 = 0.f, e1 = 0.f;
 #pragma unroll
-        for (int r = 0; r < kAttR; ++r) {
-          if (j0 + r < len) {
-            const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j0 + r) * A + c));
-            er[r] = vv.x * tanhf_(ky.x + qq.x + pl[r].x) + vv.y * tanhf_(ky.y + qq.y + pl[r].y) + vv.z * tanhf_(ky.z + qq.z + pl[r].z) +
-                    vv.w * tanhf_(ky.w + qq.w + pl[r].w);
-          }
-        }
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = n0 + nt * 8 + 2 * t;
+        const float2 qq = *reinterpret_cast<const float2*>(q + c);
+        const float2 vv = __ldg(reinterpret_cast<const float2*>(a.v + c));
+        e0 += vv.x * tanhf_(ky0[nt].x + qq.x + acc[nt][0]) + vv.y * tanhf_(ky0[nt].y + qq.y + acc[nt][1]);
+        e1 += vv.x * tanhf_(ky1[nt].x + qq.x + acc[nt][2]) + vv.y * tanhf_(ky1[nt].y + qq.y + acc[nt][3]);
       }
-#pragma unroll
-      for (int r = 0; r < kAttR; ++r) er[r] = warp_sum(er[r]);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < kAttR; ++r)
-        if (j0 + r < Ti) e[j0 + r] = j0 + r < len ? er[r] : -INFINITY;
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 1); e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, 1); e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+      if (t == 0) {
+        if (r0 < len) atomicAdd(&e[r0], e0);
+        if (r1 < len) atomicAdd(&e[r1], e1);
+      }
     }
   }
   __syncthreads();
+  ATT_STAMP(3);
   float mx = -INFINITY;
-  for (int j = tid; j < Ti; j += kAttThreads) mx = fmaxf(mx, e[j]);
+  for (int j = tid; j < len; j += kAttThreads) mx = fmaxf(mx, e[j]);
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
@@ -558,6 +602,7 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
     a.cum[(long long)b * Ti + j] = cum[j + half] + al;
   }
   __syncthreads();
+  ATT_STAMP(4);
   // context = alpha . values: 8 row groups x (C2/8) column chunks of 8 channels
   {
     const int nch = a.C2 >> 3;                 // uint4 chunks per row
@@ -579,6 +624,7 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
     }
   }
   __syncthreads();
+  ATT_STAMP(5);
   for (int c = tid; c < a.C2; c += kAttThreads) {
     float acc = 0.f;
 #pragma unroll
@@ -587,6 +633,7 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
     if (a.ctx_a) a.ctx_a[(long long)b * a.ld_a + c] = r16;
     a.ctx_b[(long long)b * a.ld_b + c] = r16;
   }
+  ATT_STAMP(6);
 }
 
 // ---- output heads / losses ---------------------------------------------------------------------------------------
@@ -894,29 +941,33 @@ struct AttBwd {
 };
 inline size_t att_bwd_smem(int Ti, int KA, int A, int D, int C2) {
   const int Tip = (Ti + 3) & ~3;
-  return sizeof(float) * (size_t)((KA + 1) * A + att_cumlen(Ti, KA) + A + 2 * Tip + D + C2 + 2 * A + (att_tipr(Ti) + 2 * (KA / 2)) * A + 32) + 64;
+  return sizeof(float) * (size_t)((KA + 1) * (A + kAttPad) + att_cumlen(Ti, KA) + A + 4 * Tip + D + C2 + 2 * A +
+                                  att_erows(Ti, KA) * (A + kAttPad) + 32) + 64;
 }
 __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
   extern __shared__ __align__(16) float sm[];
   pdl_wait();
   pdl_launch_dependents();
+  ATT_STAMP(16);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Ti = a.Ti, A = a.A, half = a.KA / 2, NW = kAttThreads / 32;
-  const int Tip = (Ti + 3) & ~3, cumlen = att_cumlen(Ti, a.KA), TiR = att_tipr(Ti);
-  const int nE = (TiR + 2 * half) * A;    // dE rows: position j lives in row j + half; everything else stays zero
-  float* U = sm;                          // [(KA+1)][A]
-  float* cum = U + (a.KA + 1) * A;        // [cumlen] cum_{t-1}, zero-padded
+  const int g = lane >> 2, t = lane & 3;
+  const int Ti = a.Ti, A = a.A, AP = A + kAttPad, half = a.KA / 2, NW = kAttThreads / 32;
+  const int Tip = (Ti + 3) & ~3, cumlen = att_cumlen(Ti, a.KA), RE = att_erows(Ti, a.KA);
+  float* Us = sm;                         // [(KA+1)][AP]
+  float* cum = Us + (a.KA + 1) * AP;      // [cumlen] cum_{t-1}, zero-padded
   float* q = cum + cumlen;                // [A]
   float* al = q + A;                      // [Ti]
   float* de = al + Tip;                   // [Ti]
-  float* hs = de + Tip;                   // [D]
+  float* dcs = de + Tip;                  // [Ti] incoming dcum_t
+  float* dca = dcs + Tip;                 // [Ti] location-path contribution to dcum_{t-1}
+  float* hs = dca + Tip;                  // [D]
   float* dctx = hs + a.D;                 // [C2]
   float* dq = dctx + a.C2;                // [A]
   float* dv = dq + A;                     // [A]
-  float* dE = dv + A;                     // [TiR + 2*half][A]
-  float* red = dE + nE;                   // [32]
+  float* dE = dv + A;                     // [RE][AP]: position j lives in row j + half; everything else stays zero
+  float* red = dE + RE * AP;              // [32]
   const int len = a.lens[b];
-  for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) U[i] = a.U[i];
+  for (int i = tid; i < (a.KA + 1) * A; i += kAttThreads) Us[(i / A) * AP + (i % A)] = a.U[i];
   for (int i = tid; i < cumlen; i += kAttThreads) {
     const int j = i - half;
     float cp = 0.f;
@@ -925,168 +976,191 @@ __global__ void __launch_bounds__(kAttThreads) att_bwd_kernel(AttBwd a) {
       al[j] = aj;
       cp = a.cumrun[(long long)b * Ti + j] - aj;
       a.cumrun[(long long)b * Ti + j] = cp;
+      dcs[j] = a.dcum[(long long)b * Ti + j];
+      dca[j] = 0.f;
     }
     cum[i] = cp;
   }
-  for (int i = tid; i < a.D; i += kAttThreads) hs[i] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
+  for (int i = tid; i < a.D; i += kAttThreads) hs[split8(i, a.D)] = __bfloat162float(a.h2out[(long long)b * a.ld_h2 + i]);
   for (int c = tid; c < a.C2; c += kAttThreads) {
-    const float g = a.dPI[(long long)b * a.ld_dPI + a.D + c] + a.dctxl[(long long)b * a.C2 + c];
+    const float gg = a.dPI[(long long)b * a.ld_dPI + a.D + c] + a.dctxl[(long long)b * a.C2 + c];
     a.dctxl[(long long)b * a.C2 + c] = 0.f;
-    dctx[c] = g;
-    a.dctx_save[(long long)b * a.C2 + c] = __float2bfloat16(g);
+    dctx[split8(c, a.C2)] = gg;            // split layout: dotted against 16-byte bf16 pieces of the values rows
+    a.dctx_save[(long long)b * a.C2 + c] = __float2bfloat16(gg);
   }
   for (int i = tid; i < A; i += kAttThreads) { dq[i] = 0.f; dv[i] = 0.f; }
-  for (int i = tid * 4; i < nE; i += kAttThreads * 4) *reinterpret_cast<float4*>(dE + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid * 4; i < RE * AP; i += kAttThreads * 4) *reinterpret_cast<float4*>(dE + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
+  ATT_STAMP(17);
   att_query(a.WqT, hs, q, A, a.D);
-  // d alpha[j] = dctx . values[j] + dcum[j] : one warp per row, 8-wide bf16 loads, two rows in flight
+  ATT_STAMP(18);
+  // d alpha[j] = dctx . values[j] + dcum[j] : one warp per row, 8-wide bf16 loads, four rows in flight
   float part = 0.f;
   {
     const int nch = a.C2 >> 3;
     const uint4* vb = reinterpret_cast<const uint4*>(a.values + (long long)b * Ti * a.C2);
-    for (int j = warp; j < Ti; j += 2 * NW) {
-      const int j2 = j + NW;
-      float acc0 = 0.f, acc1 = 0.f;
+    for (int j = warp; j < len; j += 4 * NW) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int ch = lane; ch < nch; ch += 32) {
-        uint4 u0 = make_uint4(0, 0, 0, 0), u1 = make_uint4(0, 0, 0, 0);
-        if (j < len) u0 = __ldg(vb + (long long)j * nch + ch);
-        if (j2 < len) u1 = __ldg(vb + (long long)j2 * nch + ch);
-        const float* d = dctx + ch * 8;
-        acc0 += d[0] * bf16lo(u0.x) + d[1] * bf16hi(u0.x) + d[2] * bf16lo(u0.y) + d[3] * bf16hi(u0.y) + d[4] * bf16lo(u0.z) +
-                d[5] * bf16hi(u0.z) + d[6] * bf16lo(u0.w) + d[7] * bf16hi(u0.w);
-        acc1 += d[0] * bf16lo(u1.x) + d[1] * bf16hi(u1.x) + d[2] * bf16lo(u1.y) + d[3] * bf16hi(u1.y) + d[4] * bf16lo(u1.z) +
-                d[5] * bf16hi(u1.z) + d[6] * bf16lo(u1.w) + d[7] * bf16hi(u1.w);
+        uint4 u[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int jr = j + r * NW;
+          u[r] = jr < len ? __ldg(vb + (long long)jr * nch + ch) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] += dot8s(u[r], dctx, ch, a.C2);
       }
-      acc0 = warp_sum(acc0); acc1 = warp_sum(acc1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
       if (lane == 0) {
-        const float da0 = j < len ? acc0 + a.dcum[(long long)b * Ti + j] : 0.f;
-        de[j] = da0;
-        part += al[j] * da0;
-        if (j2 < Ti) {
-          const float da1 = j2 < len ? acc1 + a.dcum[(long long)b * Ti + j2] : 0.f;
-          de[j2] = da1;
-          part += al[j2] * da1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int jr = j + r * NW;
+          if (jr < len) { const float da = acc[r] + dcs[jr]; de[jr] = da; part += al[jr] * da; }
         }
       }
     }
+    for (int j = len + tid; j < Ti; j += kAttThreads) de[j] = 0.f;
   }
   if (lane == 0) red[warp] = part;
   __syncthreads();
+  ATT_STAMP(19);
   float dot = 0.f;
   for (int w = 0; w < NW; ++w) dot += red[w];
   __syncthreads();
-  for (int j = tid; j < Ti; j += kAttThreads) de[j] = al[j] * (de[j] - dot);
+  for (int j = tid; j < Ti; j += kAttThreads) de[j] = j < len ? al[j] * (de[j] - dot) : 0.f;
   __syncthreads();
-  // energies backward: kAttR consecutive rows per warp pass, lane = 4 channels (same register blocking as the forward)
+  // energies backward: units of 16 rows x 64 channels (pl recomputed on the tensor cores, see loc_tile)
   {
-    const int nq = A >> 2, c = lane * 4;
-    const int nchunk = (Ti + kAttR - 1) / kAttR;
-    float4 sdq = make_float4(0, 0, 0, 0), sdv = make_float4(0, 0, 0, 0);
-    for (int ch = warp; ch < nchunk; ch += NW) {
-      const int j0 = ch * kAttR;
-      if (j0 >= len || lane >= nq) continue;
-      float4 pl[kAttR];
-      loc_features(U, cum, j0, a.KA, A, c, pl);
-      const float4 qq = *reinterpret_cast<const float4*>(q + c);
-      const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + c));
+    const int n_nh = A >> 6, n_units = ((len + 15) >> 4) * n_nh;
+    for (int u = warp; u < n_units; u += NW) {
+      const int j0 = (u / n_nh) * 16, n0 = (u % n_nh) * 64;
+      float acc[8][4];
+      loc_tile(Us, AP, cum, a.KA, j0, n0, acc);
+      const int r0 = j0 + g, r1 = r0 + 8;
+      const bool ok0 = r0 < len, ok1 = r1 < len;
+      const long long kr0 = ((long long)b * Ti + (ok0 ? r0 : 0)) * A + n0 + 2 * t, kr1 = ((long long)b * Ti + (ok1 ? r1 : 0)) * A + n0 + 2 * t;
+      float2 ky0[8], ky1[8];
 #pragma unroll
-      for (int r = 0; r < kAttR; ++r) {
-        const int j = j0 + r;
-        if (j < len) {
-          const float4 ky = __ldg(reinterpret_cast<const float4*>(a.keys + ((long long)b * Ti + j) * A + c));
-          const float dej = de[j];
-          const float t0 = tanhf_(ky.x + qq.x + pl[r].x), t1 = tanhf_(ky.y + qq.y + pl[r].y), t2 = tanhf_(ky.z + qq.z + pl[r].z),
-                      t3 = tanhf_(ky.w + qq.w + pl[r].w);
-          float4 d4;
-          d4.x = dej * vv.x * (1.f - t0 * t0); d4.y = dej * vv.y * (1.f - t1 * t1);
-          d4.z = dej * vv.z * (1.f - t2 * t2); d4.w = dej * vv.w * (1.f - t3 * t3);
-          sdv.x += dej * t0; sdv.y += dej * t1; sdv.z += dej * t2; sdv.w += dej * t3;
-          sdq.x += d4.x; sdq.y += d4.y; sdq.z += d4.z; sdq.w += d4.w;
-          // accumulate over decoder steps without reading back (vector reduction, no load latency on the chain)
-          atomicAdd(reinterpret_cast<float4*>(a.dkeys + ((long long)b * Ti + j) * A + c), d4);
-          *reinterpret_cast<float4*>(dE + (j + half) * A + c) = d4;
+      for (int nt = 0; nt < 8; ++nt) {
+        ky0[nt] = __ldg(reinterpret_cast<const float2*>(a.keys + kr0 + nt * 8));
+        ky1[nt] = __ldg(reinterpret_cast<const float2*>(a.keys + kr1 + nt * 8));
+      }
+      const float de0 = ok0 ? de[r0] : 0.f, de1 = ok1 ? de[r1] : 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = n0 + nt * 8 + 2 * t;
+        const float2 qq = *reinterpret_cast<const float2*>(q + c);
+        const float2 vv = __ldg(reinterpret_cast<const float2*>(a.v + c));
+        const float t00 = tanhf_(ky0[nt].x + qq.x + acc[nt][0]), t01 = tanhf_(ky0[nt].y + qq.y + acc[nt][1]);
+        const float t10 = tanhf_(ky1[nt].x + qq.x + acc[nt][2]), t11 = tanhf_(ky1[nt].y + qq.y + acc[nt][3]);
+        const float2 d0 = make_float2(de0 * vv.x * (1.f - t00 * t00), de0 * vv.y * (1.f - t01 * t01));
+        const float2 d1 = make_float2(de1 * vv.x * (1.f - t10 * t10), de1 * vv.y * (1.f - t11 * t11));
+        // column sums over the unit's 16 rows: this lane's two rows, then the 8 row groups (lanes with equal t)
+        float sq0 = d0.x + d1.x, sq1 = d0.y + d1.y, sv0 = de0 * t00 + de1 * t10, sv1 = de0 * t01 + de1 * t11;
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) {
+          sq0 += __shfl_xor_sync(0xffffffffu, sq0, m); sq1 += __shfl_xor_sync(0xffffffffu, sq1, m);
+          sv0 += __shfl_xor_sync(0xffffffffu, sv0, m); sv1 += __shfl_xor_sync(0xffffffffu, sv1, m);
+        }
+        if (g == 0) { atomicAdd(&dq[c], sq0); atomicAdd(&dq[c + 1], sq1); atomicAdd(&dv[c], sv0); atomicAdd(&dv[c + 1], sv1); }
+        if (ok0) {
+          atomicAdd(reinterpret_cast<float2*>(a.dkeys + kr0 + nt * 8), d0);    // accumulates over decoder steps, no read-back
+          *reinterpret_cast<float2*>(dE + (r0 + half) * AP + c) = d0;
+        }
+        if (ok1) {
+          atomicAdd(reinterpret_cast<float2*>(a.dkeys + kr1 + nt * 8), d1);
+          *reinterpret_cast<float2*>(dE + (r1 + half) * AP + c) = d1;
         }
       }
     }
-    if (lane < nq) {
-      atomicAdd(&dq[c], sdq.x); atomicAdd(&dq[c + 1], sdq.y); atomicAdd(&dq[c + 2], sdq.z); atomicAdd(&dq[c + 3], sdq.w);
-      atomicAdd(&dv[c], sdv.x); atomicAdd(&dv[c + 1], sdv.y); atomicAdd(&dv[c + 2], sdv.z); atomicAdd(&dv[c + 3], sdv.w);
-    }
   }
   __syncthreads();
+  ATT_STAMP(20);
   float* accp = a.acc + (long long)b * ((a.KA + 2) * A);
   for (int c = tid; c < A; c += kAttThreads) {
     a.dq_save[(long long)b * A + c] = __float2bfloat16(dq[c]);
     accp[a.KA * A + c] += dq[c];          // d u0 (also the gradient of attention_bias)
     accp[(a.KA + 1) * A + c] += dv[c];
   }
-  // dU[k][c] += sum_j cum_{t-1}[j + k - half] dE[j][c]: thread = (channel c, group of <= 8 taps); one dE load and one
-  // cum load (sliding window) feed 8 FMAs
+  // dU[k][c] += sum_j cum_{t-1}[j + k - half] dE[j][c] = (T^T dE)[k][c]: M = 32 taps (2 m-tiles), N = A (one n-tile per
+  // warp pass), K = memory rows
   {
-    const int groups = kAttThreads / A, tpg = (a.KA + groups - 1) / groups;   // tpg <= 8 (A <= 128, KA <= 31)
-    const int c = tid % A, kg = tid / A;
-    if (kg < groups && kg * tpg < a.KA) {
-      const int k0 = kg * tpg;
-      float acc[8], w[8];
+    const int nks = (len + 7) >> 3;
+    for (int nt = warp; nt < (A >> 3); nt += NW) {
+      float acc[2][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { acc[i] = 0.f; w[i] = cum[k0 + i]; }
-      for (int j = 0; j < len; ++j) {
-        const float d = dE[(j + half) * A + c];
+      for (int m = 0; m < 2; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+      for (int ks = 0; ks < nks; ++ks) {
+        const int j = ks * 8 + t;
+        const uint32_t b0 = f2tf32(dE[(j + half) * AP + nt * 8 + g]), b1 = f2tf32(dE[(j + 4 + half) * AP + nt * 8 + g]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w[i] * d;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) w[i] = w[i + 1];
-        w[7] = cum[j + 1 + k0 + 7];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i < tpg && k0 + i < a.KA) accp[(k0 + i) * A + c] += acc[i];
-    }
-  }
-  // dcum_{t-1}[i] = dcum_t[i] + sum_{k,c} dE[i - k + half][c] U[k][c]: kAttR consecutive i per warp pass, the dE rows slide
-  // through a register window (row index of (i, k) is i - k + 2*half)
-  {
-    const int nq = A >> 2, c = lane * 4;
-    const int nchunk = (Ti + kAttR - 1) / kAttR;
-    for (int ch = warp; ch < nchunk; ch += NW) {
-      const int i0 = ch * kAttR;
-      float acc[kAttR];
-#pragma unroll
-      for (int r = 0; r < kAttR; ++r) acc[r] = 0.f;
-      if (lane < nq) {
-        float4 w[kAttR];
-#pragma unroll
-        for (int r = 0; r < kAttR; ++r) w[r] = *reinterpret_cast<const float4*>(dE + (i0 + r + 2 * half) * A + c);
-        for (int k = 0; k < a.KA; ++k) {
-          const float4 u = *reinterpret_cast<const float4*>(U + k * A + c);
-#pragma unroll
-          for (int r = 0; r < kAttR; ++r) acc[r] += w[r].x * u.x + w[r].y * u.y + w[r].z * u.z + w[r].w * u.w;
-#pragma unroll
-          for (int r = kAttR - 1; r > 0; --r) w[r] = w[r - 1];
-          if (k + 1 < a.KA) w[0] = *reinterpret_cast<const float4*>(dE + (i0 - (k + 1) + 2 * half) * A + c);
+        for (int m = 0; m < 2; ++m) {
+          const int k = m * 16 + g;
+          uint32_t af[4];
+          af[0] = f2tf32(k < a.KA ? cum[j + k] : 0.f); af[1] = f2tf32(k + 8 < a.KA ? cum[j + k + 8] : 0.f);
+          af[2] = f2tf32(k < a.KA ? cum[j + 4 + k] : 0.f); af[3] = f2tf32(k + 8 < a.KA ? cum[j + 4 + k + 8] : 0.f);
+          mma_tf32(acc[m], af, b0, b1);
         }
       }
 #pragma unroll
-      for (int r = 0; r < kAttR; ++r) acc[r] = warp_sum(acc[r]);
-      if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < kAttR; ++r)
-          if (i0 + r < Ti) atomicAdd(a.dcum + (long long)b * Ti + i0 + r, acc[r]);
+      for (int m = 0; m < 2; ++m) {
+        const int k0 = m * 16 + g, k1 = k0 + 8, c = nt * 8 + 2 * t;
+        if (k0 < a.KA) atomicAdd(reinterpret_cast<float2*>(accp + k0 * A + c), make_float2(acc[m][0], acc[m][1]));
+        if (k1 < a.KA) atomicAdd(reinterpret_cast<float2*>(accp + k1 * A + c), make_float2(acc[m][2], acc[m][3]));
       }
     }
   }
+  ATT_STAMP(21);
+  // dcum_{t-1}[i] = dcum_t[i] + sum_k P[i - k + 2*half][k] with P = dE U^T ([RE rows] x [32 taps], K = A): one m-tile of
+  // dE rows per warp pass, the anti-diagonal sums go through shared-memory atomics
+  {
+    for (int mt = warp; mt < (RE >> 4); mt += NW) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      if (mt * 16 >= len + 2 * half) continue;     // rows past the last written position are zero (warp-uniform)
+      float acc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      for (int ks = 0; ks < (A >> 3); ++ks) {
+        const int c = ks * 8 + t;
+        uint32_t af[4];
+        af[0] = f2tf32(dE[r0 * AP + c]); af[1] = f2tf32(dE[r1 * AP + c]);
+        af[2] = f2tf32(dE[r0 * AP + c + 4]); af[3] = f2tf32(dE[r1 * AP + c + 4]);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int tap = n * 8 + g;
+          const uint32_t b0 = tap < a.KA ? f2tf32(Us[tap * AP + c]) : 0u, b1 = tap < a.KA ? f2tf32(Us[tap * AP + c + 4]) : 0u;
+          mma_tf32(acc[n], af, b0, b1);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const int tap = n * 8 + 2 * t + (x & 1), r = (x & 2) ? r1 : r0;
+          const int i = r + tap - 2 * half;
+          if (tap < a.KA && i >= 0 && i < Ti) atomicAdd(&dca[i], acc[n][x]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Ti; i += kAttThreads) a.dcum[(long long)b * Ti + i] = dcs[i] + dca[i];
+  ATT_STAMP(22);
   // dh2ext = dPI[:, 0:D] + dq . Wq^T   (bf16 [A][D] copy of the query weights: coalesced along D)
   for (int k2 = tid; k2 < (a.D >> 1); k2 += kAttThreads) {
-    const float2 g = *reinterpret_cast<const float2*>(a.dPI + (long long)b * a.ld_dPI + 2 * k2);
-    float a0 = g.x, a1 = g.y;
+    const float2 gg = *reinterpret_cast<const float2*>(a.dPI + (long long)b * a.ld_dPI + 2 * k2);
+    float a0 = gg.x, a1 = gg.y;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a.WqT) + k2;
-#pragma unroll 8
+#pragma unroll 16
     for (int c = 0; c < A; ++c) {
       const uint32_t u = __ldg(w + (long long)c * (a.D >> 1));
       a0 += dq[c] * bf16lo(u); a1 += dq[c] * bf16hi(u);
     }
     *reinterpret_cast<float2*>(a.dh2ext + (long long)b * a.D + 2 * k2) = make_float2(a0, a1);
   }
+  ATT_STAMP(23);
 }
 // after the loop: reduce the per-item accumulators over the batch and push dU / du0 / dv through the U = K . Wl
 // factorisation: dK = dU Wl^T, dWl = K^T dU + bK (x) du0, dbK = Wl du0, d attention_bias = du0, dv
@@ -1509,6 +1583,12 @@ extern "C" int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params
   mel_finish_kernel<<<g1((long long)B * T_used * lo.M), 256, 0, st>>>(dec_f, resid, nullptr, reinterpret_cast<float*>(ws + lo.w_mel), scal,
                                                                       (long long)B * T_used, lo.M, lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+
+// tools only: device buffer of 32 int64 that receives clock64() phase stamps of the attention kernels (NULL = off)
+extern "C" int t2_dbg_att_stamps(long long* d_buf) {
+  T2_CHECK_CUDA(cudaMemcpyToSymbol(g_att_dbg, &d_buf, sizeof(d_buf)));
   return T2_OK;
 }
 
