@@ -786,7 +786,9 @@ struct ActGemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;   // 16 KB
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 3 : 4;
+  // latency-bound pipelines: ~2.3k cycles TMA round trip / stages = cycles per k-block; the narrow swapped GEMMs of the
+  // recurrences (BN = 32, 20 KB stages) take 6 stages
+  static constexpr int kStages = (BN >= 256) ? 3 : (BN <= 32 ? 6 : 4);
   static constexpr int kStagingBytes = 4 * kEpiWarpBytes;      // 4 lane quarters x 2 tiles, never aliased with the stages
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
