@@ -275,23 +275,52 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
 // kernels
 // ------------------------------------------------------------------------------------------------------
 __global__ void tpack_kernel(const float* __restrict__ params, bf16* __restrict__ packed, const PJ* __restrict__ jobs) {
+  // 64x64 tiles through shared memory: float2 reads along the source's fast axis (N), bf16x2 writes along the destination's
+  // fast axis (K for the transposing jobs); scalar fallbacks when an offset / leading dimension is odd
+  __shared__ float tile[64][65];
   const PJ j = jobs[blockIdx.y];
-  const long long n = (long long)j.K * j.N;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const int k = int(e / j.N), c = int(e % j.N);
-    const float v = params[j.src_off + e] * j.scale;
-    long long d;
-    if (j.transpose) {
-      int row = c;
-      if (j.perm_h > 0) {  // gate-major column c = g*H + u  ->  EPI_LSTM row (u/32)*128 + g*32 + u%32
-        const int g = c / j.perm_h, u = c % j.perm_h;
-        row = (u / 32) * 128 + g * 32 + (u % 32);
+  const int tiles_n = (j.N + 63) / 64, tiles_k = (j.K + 63) / 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool vec_src = ((j.N | int(j.src_off)) & 1) == 0;
+  const bool vec_dst = ((j.dst_ld | j.col0 | int(j.dst_off)) & 1) == 0;
+  for (int ti = blockIdx.x; ti < tiles_n * tiles_k; ti += gridDim.x) {
+    const int k0 = (ti / tiles_n) * 64, n0 = (ti % tiles_n) * 64;
+    for (int r = ty; r < 64; r += 8) {
+      const int k = k0 + r, n = n0 + 2 * tx;
+      float a = 0.f, b = 0.f;
+      if (k < j.K) {
+        const float* src = params + j.src_off + (long long)k * j.N + n;
+        if (vec_src && n + 1 < j.N) { const float2 v = *reinterpret_cast<const float2*>(src); a = v.x; b = v.y; }
+        else { if (n < j.N) a = src[0]; if (n + 1 < j.N) b = src[1]; }
       }
-      d = j.dst_off + (long long)row * j.dst_ld + j.col0 + k;
-    } else {
-      d = j.dst_off + (long long)k * j.dst_ld + j.col0 + c;
+      tile[r][2 * tx] = a * j.scale; tile[r][2 * tx + 1] = b * j.scale;
     }
-    packed[d] = __float2bfloat16(v);
+    __syncthreads();
+    if (j.transpose) {
+      for (int r = ty; r < 64; r += 8) {
+        const int n = n0 + r, k = k0 + 2 * tx;
+        if (n < j.N && k < j.K) {
+          int row = n;
+          if (j.perm_h > 0) {  // gate-major column n = g*H + u  ->  EPI_LSTM row (u/32)*128 + g*32 + u%32
+            const int g = n / j.perm_h, u = n % j.perm_h;
+            row = (u / 32) * 128 + g * 32 + (u % 32);
+          }
+          bf16* dst = packed + j.dst_off + (long long)row * j.dst_ld + j.col0 + k;
+          if (vec_dst && k + 1 < j.K) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(tile[2 * tx][r], tile[2 * tx + 1][r]);
+          else { dst[0] = __float2bfloat16(tile[2 * tx][r]); if (k + 1 < j.K) dst[1] = __float2bfloat16(tile[2 * tx + 1][r]); }
+        }
+      }
+    } else {
+      for (int r = ty; r < 64; r += 8) {
+        const int k = k0 + r, n = n0 + 2 * tx;
+        if (n < j.N && k < j.K) {
+          bf16* dst = packed + j.dst_off + (long long)k * j.dst_ld + j.col0 + n;
+          if (vec_dst && n + 1 < j.N) *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(tile[r][2 * tx], tile[r][2 * tx + 1]);
+          else { dst[0] = __float2bfloat16(tile[r][2 * tx]); if (n + 1 < j.N) dst[1] = __float2bfloat16(tile[r][2 * tx + 1]); }
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1296,7 +1325,7 @@ extern "C" int t2_taco_pack_weights(const t2_taco_config_t* cfg, const float* d_
   int rc = build(cfg, lo, nullptr);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  tpack_kernel<<<dim3(32, lo.n_packjobs), 256, 0, st>>>(d_params, static_cast<bf16*>(d_packed),
+  tpack_kernel<<<dim3(32, lo.n_packjobs), dim3(32, 8), 0, st>>>(d_params, static_cast<bf16*>(d_packed),
                                                         reinterpret_cast<const PJ*>(static_cast<uint8_t*>(d_workspace) + lo.w_packjobs));
   t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
