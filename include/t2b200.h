@@ -182,6 +182,7 @@ int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params, const voi
                          void* stream);
 /* tools only: clock64() phase stamps of the attention kernels into a device buffer of 32 int64 (NULL turns them off) */
 int t2_dbg_att_stamps(long long* d_buf);
+int t2_dbg_ar_stamps(long long* d_buf);    /* same for one layer pass of the AR synthesis kernel (16 int64) */
 int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr,
                              long long* count, int* elem_bytes);
 

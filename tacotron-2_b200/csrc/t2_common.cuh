@@ -197,6 +197,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(NCOLS)
                : "memory");
 }
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map): bytes % 16 == 0, both addresses 16-byte aligned;
+// completion is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
 // while its predecessor in the stream is still running; it must not touch global memory before pdl_wait() (returns once
 // every prerequisite grid has completed and flushed). pdl_launch_dependents() lets the NEXT kernel's CTAs start early.

@@ -1169,6 +1169,8 @@ namespace t2 {
 namespace {
 
 constexpr int kArThreads = 512;
+__device__ long long* g_ar_dbg = nullptr;   // tools only: clock64 stamps of (t = 64, l = 7) in CTA 0
+#define AR_STAMP(i) do { if (g_ar_dbg && blockIdx.x == 0 && threadIdx.x == 0 && t == 64 && l == 7) g_ar_dbg[i] = clock64(); } while (0)
 constexpr int kArMaxItems = 4;
 
 struct ArLayout {
@@ -1300,36 +1302,50 @@ struct ArArgs {
   long long per_rank_layer, o_head1, o_head2;
   float res_scale, log_scale_min;
   int items_per_cluster;
+  int prefetch;             // 1: this CTA's per-layer weight slice is double-buffered in shared memory (bulk async copies)
 };
 
-// y[o][it] = sum_k W[o][k] * x[it][k] for o in [0, nout): 16 warps stride the outputs, lanes stride 8-element K chunks
+// y[it][o] = sum_k W[o][k] * x[it][k] for o in [0, nout): all outputs of a pass run side by side - a group of GS lanes
+// (GS = 512 / nout rounded down to a power of two, <= 32) owns one output row and strides its 16-byte chunks, the partial
+// sums meet in log2(GS) shuffles. (The warp-per-output form serialised 2 rows x 5 shuffle levels x NI per warp.)
 template <int NI>
 __device__ __forceinline__ void ar_matvec(const bf16* __restrict__ W, int nout, int K, const float* __restrict__ x /*[NI][ldx]*/,
-                                          int ldx, float* __restrict__ y /*[NI][ldy] at column offset*/, int ldy, int ni) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                          int ldx, float* __restrict__ y /*[NI][ldy]*/, int ldy, int ni) {
+  int gs = 32;
+  while (gs > 1 && gs * nout > kArThreads) gs >>= 1;
+  const int per_pass = kArThreads / gs;
+  const int sub = threadIdx.x % gs;
   const int nchunk = K >> 3;
-  for (int o = warp; o < nout; o += kArThreads / 32) {
+  for (int o0 = 0; o0 < nout; o0 += per_pass) {
+    const int o = o0 + threadIdx.x / gs;
+    const bool live = o < nout;
     float acc[NI];
 #pragma unroll
     for (int it = 0; it < NI; ++it) acc[it] = 0.f;
-    const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)o * K);
-    for (int c = lane; c < nchunk; c += 32) {
-      const uint4 u = __ldg(wr + c);
-      const float w0 = bf16lo(u.x), w1 = bf16hi(u.x), w2 = bf16lo(u.y), w3 = bf16hi(u.y);
-      const float w4 = bf16lo(u.z), w5 = bf16hi(u.z), w6 = bf16lo(u.w), w7 = bf16hi(u.w);
+    if (live) {
+      const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)o * K);
+#pragma unroll 2
+      for (int c = sub; c < nchunk; c += gs) {
+        const uint4 u = wr[c];          // generic load: the slice is either in L2 (global) or prefetched into shared memory
+        const float w0 = bf16lo(u.x), w1 = bf16hi(u.x), w2 = bf16lo(u.y), w3 = bf16hi(u.y);
+        const float w4 = bf16lo(u.z), w5 = bf16hi(u.z), w6 = bf16lo(u.w), w7 = bf16hi(u.w);
 #pragma unroll
-      for (int it = 0; it < NI; ++it) {
-        if (it < ni) {
-          const float4 a = *reinterpret_cast<const float4*>(x + it * ldx + c * 8);
-          const float4 b = *reinterpret_cast<const float4*>(x + it * ldx + c * 8 + 4);
-          acc[it] += w0 * a.x + w1 * a.y + w2 * a.z + w3 * a.w + w4 * b.x + w5 * b.y + w6 * b.z + w7 * b.w;
+        for (int it = 0; it < NI; ++it) {
+          if (it < ni) {
+            const float4 p = *reinterpret_cast<const float4*>(x + it * ldx + c * 8);
+            const float4 q = *reinterpret_cast<const float4*>(x + it * ldx + c * 8 + 4);
+            acc[it] += w0 * p.x + w1 * p.y + w2 * p.z + w3 * p.w + w4 * q.x + w5 * q.y + w6 * q.z + w7 * q.w;
+          }
         }
       }
     }
 #pragma unroll
     for (int it = 0; it < NI; ++it) {
-      const float s = warp_sum(acc[it]);
-      if (lane == 0 && it < ni) y[it * ldy + o] = s;
+      if (it < ni) {      // block-uniform
+        float v = acc[it];
+        for (int m = gs >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (live && sub == 0) y[it * ldy + o] = v;
+      }
     }
   }
 }
@@ -1345,25 +1361,72 @@ __global__ void __launch_bounds__(kArThreads, 1) wn_ar_kernel(ArArgs a) {
   if (ni < 0) ni = 0;   // surplus clusters still take part in no barriers of other clusters; they just idle through
   extern __shared__ __align__(16) float sm[];
   const int ld1 = (a.K1 + 3) & ~3;
+  const int nbs = 2 * a.ZC + a.RC;                  // bias slice per layer: a rows | b rows | residual-out rows
   float* in1 = sm;                                  // [NI][ld1]  : x(t-2d) | x(t-d) | x(t) | c(t)
-  float* zbuf = in1 + NI * ld1;                     // [NI][Gh]
+  float* zbuf = in1 + NI * ld1;                     // [NI][Gh]   : full z vector (pulled from the cluster)
   float* xbuf = zbuf + NI * a.Gh;                   // [NI][R]    : current layer input (full vector)
-  float* loc = xbuf + NI * a.R;                     // [NI][2*ZC] : this CTA's gate pre-activations / stage-2 outputs
+  float* zsl = xbuf + NI * a.R;                     // [NI][ZC]   : this CTA's z slice, read remotely by the cluster
+  float* xsl = zsl + NI * a.ZC;                     // [NI][RC]   : this CTA's slice of the next layer input, read remotely
+  float* loc = xsl + NI * a.RC;                     // [NI][2*ZC] : this CTA's gate pre-activations / stage-2 outputs
   float* skip = loc + NI * (2 * a.ZC > a.RC + a.SC ? 2 * a.ZC : a.RC + a.SC);   // [NI][SC] running skip sum (slice)
   float* hbuf = skip + NI * a.SC;                   // [NI][S]    : head activations (full vector)
   float* obuf = hbuf + NI * a.S;                    // [NI][CS*OC]: network output (full vector)
-  float* cur = obuf + NI * a.CS * a.OC;             // [NI]       : current input sample (scalar) or index
+  float* bsl = obuf + NI * a.CS * a.OC;             // [L][nbs]   : this CTA's bias slices (cluster.sync flushes L1: keep them here)
+  float* cvec = bsl + a.L * nbs;                    // [NI][C]    : conditioning frame of the current step
+  int* rofs = reinterpret_cast<int*>(cvec + NI * ((a.C + 3) & ~3));   // [2L+1] ring offsets / slots / total
+  float* cur = reinterpret_cast<float*>(rofs + ((2 * a.L + 1 + 3) & ~3));   // [NI] current input sample (scalar) or index
+  // weight prefetch: two slots of per_rank_layer bf16 + two mbarriers behind the activation buffers (16-byte aligned)
+  uint64_t* wbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(cur + NI) + 15) & ~uintptr_t(15));
+  bf16* wslot = reinterpret_cast<bf16*>(wbar + 2);
+  const uint32_t wbytes = uint32_t(a.per_rank_layer * 2);
   const int tid = threadIdx.x;
+  if (a.prefetch && tid == 0) {
+    mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1);
+    fence_barrier_init();
+  }
   const float* bias_all = a.bias;
   const float* b_skip = bias_all + (long long)a.L * (a.G + a.R);
   const float* b_f1 = b_skip + a.S;
   const float* b_f2 = b_f1 + a.S;
   const int nm = a.O / 3;
 
+  for (int i = tid; i < a.L * nbs; i += kArThreads) {
+    const int l = i / nbs, j = i % nbs;
+    const float* bgl = bias_all + (long long)l * (a.G + a.R);
+    bsl[i] = j < a.ZC ? bgl[rank * a.ZC + j] : (j < 2 * a.ZC ? bgl[a.Gh + rank * a.ZC + (j - a.ZC)] : bgl[a.G + rank * a.RC + (j - 2 * a.ZC)]);
+  }
+  for (int i = tid; i < 2 * a.L + 1; i += kArThreads) rofs[i] = a.ring_off[i];
   for (int i = tid; i < NI; i += kArThreads)
     if (i < ni) cur[i] = a.scalar_in ? static_cast<const float*>(a.initial)[item0 + i]
                                      : float(static_cast<const int*>(a.initial)[item0 + i]);
   __syncthreads();
+  if (a.prefetch && tid == 0) {   // slice of layer 0 -> slot 0
+    mbar_expect_tx(&wbar[0], wbytes);
+    bulk_load_1d(wslot, a.w + (long long)rank * a.per_rank_layer, wbytes, &wbar[0]);
+  }
+  uint32_t wphase = 0;            // bit s = parity to wait for on slot s
+  long long seq = 0;              // (t, l) sequence number: slot = seq & 1
+  // ring taps of the NEXT layer are fetched into registers one layer ahead (their producers ran >= one time step ago)
+  constexpr int kTapRegs = (NI * 2 * 512 + kArThreads - 1) / kArThreads;   // R <= 512
+  float tapv[kTapRegs];
+  auto fetch_taps = [&](int tt0, int l) {
+    const int d = 1 << (l % a.layers_per_stack);
+    const int slots = rofs[a.L + l];
+    const long long roff = rofs[l];
+#pragma unroll
+    for (int j = 0; j < kTapRegs; ++j) {
+      const int i = tid + j * kArThreads;
+      float v = 0.f;
+      if (i < ni * 2 * a.R) {
+        const int it = i / (2 * a.R), k = i % (2 * a.R);
+        const int tap = k / a.R, r = k % a.R;
+        const int tt = tt0 - (2 - tap) * d;
+        if (tt >= 0) v = __ldcg(a.ring + ((long long)(item0 + it) * rofs[2 * a.L] + roff + (tt & (slots - 1))) * a.R + r);
+      }
+      tapv[j] = v;
+    }
+  };
+  fetch_taps(0, 0);
 
   for (int t = 0; t < a.T; ++t) {
     // ---- first conv: x0 = W_in[idx] + b (one-hot) or x * w + b (scalar); every CTA builds the full vector ----
@@ -1375,68 +1438,96 @@ __global__ void __launch_bounds__(kArThreads, 1) wn_ar_kernel(ArArgs a) {
       xbuf[it * a.R + r] = v;
     }
     for (int i = tid; i < ni * a.SC; i += kArThreads) skip[i] = 0.f;
+    for (int i = tid; i < ni * a.C; i += kArThreads)     // conditioning frame of this step, once (not once per layer)
+      cvec[(i / a.C) * ((a.C + 3) & ~3) + i % a.C] = __bfloat162float(a.c_up[((long long)(item0 + i / a.C) * a.T + t) * a.C + i % a.C]);
     __syncthreads();
     for (int l = 0; l < a.L; ++l) {
-      const int d = 1 << (l % a.layers_per_stack);
-      const int slots = a.ring_off[a.L + l];
-      const long long roff = a.ring_off[l];
-      // ---- gather the stage-1 input: taps from the ring (zeros before t = 0), current x, conditioning ----
-      for (int i = tid; i < ni * ld1; i += kArThreads) {
-        const int it = i / ld1, k = i % ld1;
+      const int slots = rofs[a.L + l];
+      const long long roff = rofs[l];
+      AR_STAMP(0);
+      // ---- gather the stage-1 input: taps (prefetched registers), current x, conditioning ----
+#pragma unroll
+      for (int j = 0; j < kTapRegs; ++j) {
+        const int i = tid + j * kArThreads;
+        if (i < ni * 2 * a.R) in1[(i / (2 * a.R)) * ld1 + i % (2 * a.R)] = tapv[j];
+      }
+      for (int i = tid; i < ni * (ld1 - 2 * a.R); i += kArThreads) {
+        const int it = i / (ld1 - 2 * a.R), k = 2 * a.R + i % (ld1 - 2 * a.R);
         float v = 0.f;
-        if (k < 2 * a.R) {
-          const int tap = k / a.R, r = k % a.R;
-          const int tt = t - (2 - tap) * d;
-          if (tt >= 0) v = __ldcg(a.ring + ((long long)(item0 + it) * a.ring_off[2 * a.L] + roff + (tt & (slots - 1))) * a.R + r);
-        } else if (k < 3 * a.R) {
-          v = xbuf[it * a.R + (k - 2 * a.R)];
-        } else if (k < a.K1) {
-          v = __bfloat162float(a.c_up[((long long)(item0 + it) * a.T + t) * a.C + (k - 3 * a.R)]);
-        }
-        in1[i] = v;
+        if (k < 3 * a.R) v = xbuf[it * a.R + (k - 2 * a.R)];
+        else if (k < a.K1) v = cvec[it * ((a.C + 3) & ~3) + (k - 3 * a.R)];
+        in1[it * ld1 + k] = v;
       }
       __syncthreads();
+      AR_STAMP(1);
       // rank 0 publishes x_l(t) into the ring for later steps (read back no earlier than step t + d)
       if (rank == 0)
         for (int i = tid; i < ni * a.R; i += kArThreads) {
           const int it = i / a.R, r = i % a.R;
-          a.ring[((long long)(item0 + it) * a.ring_off[2 * a.L] + roff + (t & (slots - 1))) * a.R + r] = xbuf[i];
+          a.ring[((long long)(item0 + it) * rofs[2 * a.L] + roff + (t & (slots - 1))) * a.R + r] = xbuf[i];
         }
       // ---- stage 1: gate pre-activations for this CTA's ZC z-channels (a rows then b rows) ----
       const bf16* w1 = a.w + ((long long)l * a.CS + rank) * a.per_rank_layer;
+      if (a.prefetch) {
+        const int slot = int(seq & 1);
+        mbar_wait(&wbar[slot], (wphase >> slot) & 1u);       // this layer's slice has landed
+        wphase ^= 1u << slot;
+        w1 = wslot + (long long)slot * a.per_rank_layer;
+        if (tid == 0 && (t + 1 < a.T || l + 1 < a.L)) {      // next layer's slice -> the other slot (free since the last cluster.sync)
+          const int ln = l + 1 < a.L ? l + 1 : 0;
+          mbar_expect_tx(&wbar[slot ^ 1], wbytes);
+          bulk_load_1d(wslot + (long long)(slot ^ 1) * a.per_rank_layer, a.w + ((long long)ln * a.CS + rank) * a.per_rank_layer, wbytes,
+                       &wbar[slot ^ 1]);
+        }
+      }
+      ++seq;
+      AR_STAMP(2);
       ar_matvec<NI>(w1, 2 * a.ZC, a.K1, in1, ld1, loc, 2 * a.ZC, ni);
       __syncthreads();
-      const float* bg = bias_all + (long long)l * (a.G + a.R);
+      AR_STAMP(3);
+      // taps of the next layer (or of layer 0 at the next time step): issued now, consumed after two cluster barriers
+      if (l + 1 < a.L) fetch_taps(t, l + 1);
+      else if (t + 1 < a.T) fetch_taps(t + 1, 0);
+      const float* bg = bsl + l * nbs;
       for (int i = tid; i < ni * a.ZC; i += kArThreads) {
         const int it = i / a.ZC, j = i % a.ZC;
-        const int ch = rank * a.ZC + j;
-        const float av = loc[it * 2 * a.ZC + j] + bg[ch];
-        const float bv = loc[it * 2 * a.ZC + a.ZC + j] + bg[a.Gh + ch];
-        const float z = tanhf_(av) * sigmoidf_(bv);
-        for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(zbuf, r)[it * a.Gh + ch] = z;
+        const float av = loc[it * 2 * a.ZC + j] + bg[j];
+        const float bv = loc[it * 2 * a.ZC + a.ZC + j] + bg[a.ZC + j];
+        zsl[it * a.ZC + j] = tanhf_(av) * sigmoidf_(bv);      // local slice; the cluster PULLS it after the barrier
       }
+      AR_STAMP(4);
       cluster.sync();
+      AR_STAMP(5);
+      // pull the full z vector: 16-byte pieces from the owners' slices through distributed shared memory
+      for (int i = tid; i < ni * (a.Gh >> 2); i += kArThreads) {
+        const int it = i / (a.Gh >> 2), ch = (i % (a.Gh >> 2)) << 2;
+        const int r = ch / a.ZC, j = ch % a.ZC;
+        *reinterpret_cast<float4*>(zbuf + it * a.Gh + ch) = *reinterpret_cast<const float4*>(cluster.map_shared_rank(zsl, r) + it * a.ZC + j);
+      }
+      __syncthreads();
       // ---- stage 2: this CTA's RC residual-out channels and SC skip channels ----
       const bf16* w2 = w1 + 2LL * a.ZC * a.K1;
       ar_matvec<NI>(w2, a.RC + a.SC, a.Gh, zbuf, a.Gh, loc, a.RC + a.SC, ni);
       __syncthreads();
+      AR_STAMP(6);
       for (int i = tid; i < ni * (a.RC + a.SC); i += kArThreads) {
         const int it = i / (a.RC + a.SC), j = i % (a.RC + a.SC);
         const float v = loc[it * (a.RC + a.SC) + j];
-        if (j < a.RC) {
-          const int ch = rank * a.RC + j;
-          const float xn = (v + bg[a.G + ch] + xbuf[it * a.R + ch]) * a.res_scale;
-          if (l + 1 < a.L)
-            for (int r = 0; r < a.CS; ++r) cluster.map_shared_rank(hbuf, r)[it * a.S + ch] = xn;  // staged in hbuf (R <= S)
-        } else {
-          skip[it * a.SC + (j - a.RC)] += v;   // scale_l folded into the packed skip weights
-        }
+        if (j < a.RC) xsl[it * a.RC + j] = (v + bg[2 * a.ZC + j] + xbuf[it * a.R + rank * a.RC + j]) * a.res_scale;
+        else skip[it * a.SC + (j - a.RC)] += v;   // scale_l folded into the packed skip weights
       }
+      AR_STAMP(7);
       cluster.sync();
+      AR_STAMP(8);
       if (l + 1 < a.L) {
-        for (int i = tid; i < ni * a.R; i += kArThreads) xbuf[(i / a.R) * a.R + i % a.R] = hbuf[(i / a.R) * a.S + i % a.R];
+        for (int i = tid; i < ni * (a.R >> 2); i += kArThreads) {
+          const int it = i / (a.R >> 2), ch = (i % (a.R >> 2)) << 2;
+          const int r = ch / a.RC, j = ch % a.RC;
+          *reinterpret_cast<float4*>(xbuf + it * a.R + ch) = *reinterpret_cast<const float4*>(cluster.map_shared_rank(xsl, r) + it * a.RC + j);
+        }
         __syncthreads();
       }
+      AR_STAMP(9);
     }
     // ---- head: relu(skips + b) -> f1 -> relu -> f2 ----
     for (int i = tid; i < ni * a.SC; i += kArThreads) {
@@ -1535,6 +1626,12 @@ __global__ void __launch_bounds__(kArThreads, 1) wn_ar_kernel(ArArgs a) {
 typedef struct {
   long long packed_bytes, workspace_bytes;
 } t2_wn_ar_sizes_t_;
+
+// tools only: device buffer of 16 int64 receiving clock64() stamps of one AR layer pass (NULL = off)
+extern "C" int t2_dbg_ar_stamps(long long* d_buf) {
+  T2_CHECK_CUDA(cudaMemcpyToSymbol(t2::g_ar_dbg, &d_buf, sizeof(d_buf)));
+  return T2_OK;
+}
 
 extern "C" int t2_wn_ar_sizes(const t2_wn_config_t* cfg, int cluster_size, long long* packed_bytes, long long* workspace_bytes) {
   Layout lo;
@@ -1658,8 +1755,17 @@ extern "C" int t2_wn_ar_generate(const t2_wn_config_t* cfg, int cluster_size, co
   a.items_per_cluster = ipc;
   const int ld1 = (al.K1 + 3) & ~3;
   const int locw = 2 * al.ZC > al.RC + al.SC ? 2 * al.ZC : al.RC + al.SC;
-  const size_t smem = sizeof(float) * size_t(kArMaxItems) * (ld1 + lo.Gh + lo.R + locw + al.SC + lo.S + al.CS * al.OC + 1) + 64;
-  auto kern = wn_ar_kernel<kArMaxItems>;
+  T2_REQUIRE(al.ZC % 4 == 0 && al.RC % 4 == 0, T2_ERR_UNSUPPORTED_SHAPE, "AR synthesis: channel slices per CTA must be multiples of 4");
+  const int NIt = ipc <= 1 ? 1 : (ipc <= 2 ? 2 : kArMaxItems);     // kernel instantiation: items per cluster pass
+  size_t smem = sizeof(float) * (size_t(NIt) * (ld1 + lo.Gh + lo.R + al.ZC + al.RC + locw + al.SC + lo.S + al.CS * al.OC + ((lo.C + 3) & ~3) + 1) +
+                                 size_t(lo.L) * (2 * al.ZC + al.RC) + ((2 * lo.L + 1 + 3) & ~3)) + 64;
+  // double-buffered shared-memory copy of this CTA's per-layer weight slice when it fits next to the activations
+  // (paper widths: 70.6 KB per slice at cluster size 16); otherwise the slices stream from L2 as before
+  const size_t wslots = 2 * size_t(al.per_rank_layer) * 2 + 64;
+  a.prefetch = (al.per_rank_layer % 8 == 0 && smem + wslots <= 232448 - 1024) ? 1 : 0;
+  if (const char* e = getenv("T2_AR_PREFETCH")) { if (e[0] == '0') a.prefetch = 0; }
+  if (a.prefetch) smem += wslots;
+  void (*kern)(ArArgs) = NIt == 1 ? wn_ar_kernel<1> : (NIt == 2 ? wn_ar_kernel<2> : wn_ar_kernel<kArMaxItems>);
   T2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (al.CS > 8) T2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   T2_CHECK_CUDA(cudaMemsetAsync(ws + al.w_ring, 0, (size_t)lo.B * al.ring_slots_total * lo.R * 4, st));
