@@ -262,7 +262,8 @@ def main():
                     "h2d_bytes_per_step": int(sum(p.numel() * p.element_size() for p in pin)), "d2h_bytes_per_step": 8,
                     "ms_per_step": results["e2e"] / args.steps},
             "gpu_launches": int(model.launches_per_step * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "act_gemm_kernel<EPI_GATE,256> (per-layer dilated-conv + cin gate GEMM)",
+            "roofline": {"bound": "tensor", "kernel": "act_gemm_kernel<EPI_GATE,256,NT=2> (per-layer dilated-conv + cin gate GEMM)",
+                         "timing": "CUDA events around 20 back-to-back launches replayed from one CUDA graph, averaged over layers 3/9/15/21",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "flops_per_launch": flops_per_launch, "ms_per_launch": gate_ms_avg,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s"},
