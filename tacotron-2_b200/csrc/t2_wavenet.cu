@@ -926,7 +926,7 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
 
 // side stream + fork/join events for the independent tail of the backward pass (created once per process; T2_SIDE_STREAM=0
 // in the environment keeps everything on the caller's stream)
-struct SideStream { cudaStream_t s; cudaEvent_t fork, join; };
+struct SideStream { cudaStream_t s; cudaEvent_t fork, fork2, join; };
 static SideStream* side_stream() {
   static SideStream ss;
   static int state = 0;   // 0 unknown, 1 ready, -1 disabled
@@ -935,6 +935,7 @@ static SideStream* side_stream() {
     if (e && e[0] == '0') state = -1;
     else if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss.fork2, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess) state = 1;
     else state = -1;
   }
@@ -992,6 +993,24 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
   skip_bias_kernel<<<grid1d((long long)lo.L * lo.S), 256, 0, st>>>(reinterpret_cast<const float*>(ws + lo.w_skipsum), d_grads,
       reinterpret_cast<const long long*>(ws + lo.w_tables), reinterpret_cast<const float*>(ws + lo.w_tables + 3 * lo.L * sizeof(long long)), lo.L, lo.S);
   t2_count_launch();
+  // The head's weight gradients (6 tiles with a 15360-long reduction: ~100 us on 6 SMs) and the bias column sums of dlog
+  // depend only on the head backward above: they run on the side stream underneath the whole residual-stack chain below,
+  // which leaves 28 SMs idle (120 M tiles on 148 SMs).
+  SideStream* side = side_stream();
+  cudaStream_t sb = st;
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+    sb = side->s;
+  }
+  {
+    ActT hmaps[4] = {make_act(h1, lo.S, lo.T, lo.B), make_act(dh2, lo.S, lo.T, lo.B), make_act(h2, lo.S, lo.T, lo.B),
+                     make_act(dlog, lo.ldo, lo.T, lo.B)};
+    rc = launch_wgrad(hmaps, 4, reinterpret_cast<const WgradTile*>(ws + lo.w_tiles_head), lo.n_tiles_head, d_grads, lo.T, lo.B, sb);
+    if (rc) return rc;
+    colsum_kernel<<<dim3(96, lo.n_colsum), 256, 0, sb>>>(ws, d_grads, reinterpret_cast<const ColsumJob*>(ws + lo.w_colsum), scalars); t2_count_launch();
+    T2_CHECK_CUDA(cudaGetLastError());
+  }
   // residual stack, top down
   const ActT a_dxin = make_act(dxin, lo.R, lo.T, lo.B, lo.L);
   const ActT a_dskip = make_act(dskip, lo.S, lo.T, lo.B, 1);
@@ -1005,31 +1024,21 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     rc = launch_act_gemm(EPI_DX, lo.R, gx, st);
     if (rc) return rc;
   }
-  // From here on two independent tails: (A) the weight-gradient GEMMs (fill the machine), (B) the conditioning path
-  // (K = L*G data-gradient GEMM, transposes, upsampling-net backward) + first-conv gradient: latency-bound small kernels.
-  // (B) runs on a side stream (fork/join through events, capturable into the caller's CUDA graph) and hides under (A).
-  cudaStream_t sb = st;
-  SideStream* side = side_stream();
+  // From here on two independent tails: (A) the batched weight-gradient GEMM of the stack (fills the machine), (B) the
+  // conditioning path (K = L*G data-gradient GEMM, transposes, upsampling-net backward) + first-conv gradient: latency-bound
+  // small kernels. (B) continues on the side stream (fork/join through events, capturable into the caller's CUDA graph).
   if (side) {
-    T2_CHECK_CUDA(cudaEventRecord(side->fork, st));
-    T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
-    sb = side->s;
+    T2_CHECK_CUDA(cudaEventRecord(side->fork2, st));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork2, 0));
   }
-  // weight gradients: one batched launch for the whole stack, one for the head
+  // weight gradients of the stack: one batched launch
   {
     ActT maps[6] = {make_act(ws + lo.w_xd, lo.R, lo.T, lo.B, lo.L), a_dg,
                     make_act(ws + lo.w_cup, lo.C > 0 ? lo.C : 8, lo.T, lo.B, 1),
                     make_act(ws + lo.w_z, lo.Gh, lo.T, lo.B, lo.L), a_dxin, a_dskip};
     rc = launch_wgrad(maps, 6, reinterpret_cast<const WgradTile*>(ws + lo.w_tiles_main), lo.n_tiles_main, d_grads, lo.T, lo.B, st);
     if (rc) return rc;
-    ActT hmaps[4] = {make_act(h1, lo.S, lo.T, lo.B), make_act(dh2, lo.S, lo.T, lo.B), make_act(h2, lo.S, lo.T, lo.B),
-                     make_act(dlog, lo.ldo, lo.T, lo.B)};
-    rc = launch_wgrad(hmaps, 4, reinterpret_cast<const WgradTile*>(ws + lo.w_tiles_head), lo.n_tiles_head, d_grads, lo.T, lo.B, st);
-    if (rc) return rc;
   }
-  // bias gradients
-  colsum_kernel<<<dim3(96, lo.n_colsum), 256, 0, st>>>(ws, d_grads, reinterpret_cast<const ColsumJob*>(ws + lo.w_colsum), scalars); t2_count_launch();
-  T2_CHECK_CUDA(cudaGetLastError());
   // first conv
   first_conv_bwd_kernel<<<dim3((unsigned)((BT + 63) / 64)), lo.R, 0, sb>>>(d_x, lo.scalar_in ? 1 : 0, dxin, d_grads + lo.p_in_k, BT, lo.R); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
