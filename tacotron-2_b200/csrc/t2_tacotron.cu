@@ -13,6 +13,7 @@
 //     Backward-through-time uses the transposed weights the same way (EPI_TOUT) and stashes gate gradients so that
 //     every recurrent weight gradient is ONE wgrad GEMM over all time steps afterwards.
 //   * one attention CTA per batch item per step (query projection, location conv, energies, masked softmax, context).
+#include <stdlib.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -1332,6 +1333,23 @@ extern "C" int t2_taco_pack_weights(const t2_taco_config_t* cfg, const float* d_
   return T2_OK;
 }
 
+// The two directions of the encoder BiLSTM are independent chains of small launches (8-16 CTAs each): the backward
+// direction runs on a side stream (fork / join through events; capturable; T2_SIDE_STREAM=0 keeps one stream).
+struct TacoSide { cudaStream_t s; cudaEvent_t fork, join; };
+static TacoSide* taco_side() {
+  static TacoSide ss;
+  static int state = 0;   // 0 unknown, 1 ready, -1 disabled
+  if (state == 0) {
+    const char* e = getenv("T2_SIDE_STREAM");
+    if (e && e[0] == '0') state = -1;
+    else if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess) state = 1;
+    else state = -1;
+  }
+  return state == 1 ? &ss : nullptr;
+}
+
 // ---- encoder: embedding -> conv blocks -> BiLSTM -> masked values -> attention keys (tacotron.py:113-131) ----
 static int encoder_fwd(const StepCtx& s, const int* d_inputs, const int* d_input_lengths, int training) {
   const TL& lo = *s.lo;
@@ -1342,25 +1360,36 @@ static int encoder_fwd(const StepCtx& s, const int* d_inputs, const int* d_input
   embed_fwd_kernel<<<g1((long long)B * Ti * lo.E), 256, 0, st>>>(d_inputs, d_params + lo.p_emb, emb, (long long)B * Ti, lo.E); t2_count_launch();
   const void* x = emb;
   for (auto& L : lo.enc) { rc = conv_block_fwd(s, L, x, Ti, training); if (rc) return rc; x = ws + L.w_x; }
+  TacoSide* side = taco_side();
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+  }
   for (int d = 0; d < 2; ++d) {
+    cudaStream_t sx = (d == 1 && side) ? side->s : st;
+    StepCtx sc = s; sc.st = sx;
     float* pre = reinterpret_cast<float*>(ws + lo.w_encpre[d]);
     rc = conv_gemm(x, lo.C, Ti, B, pk + lo.k_encWx[d], 4 * H, lo.C, 1, nullptr, 256, const_cast<float*>(d_params) + lo.p_elb[d], 0, nullptr, pre, 4 * H,
-                   4 * H, 0.f, 0, 0, nullptr, st);
+                   4 * H, 0.f, 0, 0, nullptr, sx);
     if (rc) return rc;
     bf16* hh = reinterpret_cast<bf16*>(ws + lo.w_ench[d]);
     float* cc = reinterpret_cast<float*>(ws + lo.w_encc[d]);
-    T2_CHECK_CUDA(cudaMemsetAsync(hh, 0, (size_t)B * H * 2, st));
-    T2_CHECK_CUDA(cudaMemsetAsync(cc, 0, (size_t)B * H * 4, st));
+    T2_CHECK_CUDA(cudaMemsetAsync(hh, 0, (size_t)B * H * 2, sx));
+    T2_CHECK_CUDA(cudaMemsetAsync(cc, 0, (size_t)B * H * 4, sx));
     bf16* memory = reinterpret_cast<bf16*>(ws + lo.w_memory);
     for (int sidx = 0; sidx < Ti; ++sidx) {
       const int t = d == 0 ? sidx : Ti - 1 - sidx;
-      rc = lstm_step(s, pk + lo.k_encWr[d], H, H, hh + (long long)sidx * B * H, B, pre + (long long)t * 4 * H, Ti * 4 * H, nullptr,
+      rc = lstm_step(sc, pk + lo.k_encWr[d], H, H, hh + (long long)sidx * B * H, B, pre + (long long)t * 4 * H, Ti * 4 * H, nullptr,
                      cc + (long long)sidx * B * H, cc + (long long)(sidx + 1) * B * H, hh + (long long)sidx * B * H, H,
                      hh + (long long)(sidx + 1) * B * H, H, memory + (long long)t * 2 * H + d * H, Ti * 2 * H,
                      reinterpret_cast<bf16*>(ws + lo.w_encg[d]) + (long long)sidx * B * 4 * H,
                      reinterpret_cast<bf16*>(ws + lo.w_enct[d]) + (long long)sidx * B * H, d_input_lengths, t, 2 + d, lo.c.zoneout_rate);
       if (rc) return rc;
     }
+  }
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->join, side->s));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   }
   bf16* values = reinterpret_cast<bf16*>(ws + lo.w_values);
   mask_values_kernel<<<g1((long long)B * Ti * 2 * H), 256, 0, st>>>(reinterpret_cast<bf16*>(ws + lo.w_memory), d_input_lengths, values, B, Ti, 2 * H);
@@ -1810,11 +1839,18 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   t2_count_launch();
   // ---- encoder BiLSTM, backward through time ----
   const void* x3 = ws + lo.enc.back().w_x;
+  TacoSide* side = taco_side();
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+  }
   for (int d = 0; d < 2; ++d) {
+    cudaStream_t sx = (d == 1 && side) ? side->s : st;
+    StepCtx sc = s; sc.st = sx;
     float* edh = reinterpret_cast<float*>(ws + lo.w_encdh[d]);
     float* edc = reinterpret_cast<float*>(ws + lo.w_encdc[d]);
-    T2_CHECK_CUDA(cudaMemsetAsync(edh, 0, (size_t)B * H * 4, st));
-    T2_CHECK_CUDA(cudaMemsetAsync(edc, 0, (size_t)B * H * 4, st));
+    T2_CHECK_CUDA(cudaMemsetAsync(edh, 0, (size_t)B * H * 4, sx));
+    T2_CHECK_CUDA(cudaMemsetAsync(edc, 0, (size_t)B * H * 4, sx));
     bf16* dgall = reinterpret_cast<bf16*>(ws + lo.w_encdgall[d]);
     bf16* dpre = reinterpret_cast<bf16*>(ws + lo.w_dencpre[d]);
     for (int sidx = Ti - 1; sidx >= 0; --sidx) {
@@ -1826,17 +1862,21 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
       c.c_prev = reinterpret_cast<const float*>(ws + lo.w_encc[d]) + (long long)sidx * B * H;
       c.dg_a = dgall + (long long)sidx * B * 4 * H; c.ld_a = 4 * H; c.dg_b = dpre + (long long)t * 4 * H; c.ld_b = (long long)Ti * 4 * H;
       c.lens = d_input_lengths; c.t = t; c.B = B; c.H = H; c.stream = 2 + d; c.zone = lo.c.zoneout_rate; c.seed = seed; c.step = d_step;
-      T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * H)), dim3(256), 0, st, c)); t2_count_launch();
-      rc = lstm_bwd_gemm(s, pk + lo.k_encWrT[d], H, 4 * H, c.dg_a, B, edh, H, H, 2, nullptr, 0, 0, ks_enc);
+      T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * H)), dim3(256), 0, sx, c)); t2_count_launch();
+      rc = lstm_bwd_gemm(sc, pk + lo.k_encWrT[d], H, 4 * H, c.dg_a, B, edh, H, H, 2, nullptr, 0, 0, ks_enc);
       if (rc) return rc;
     }
     {
       ActT maps[2] = {make_act(ws + lo.w_ench[d], H, Ti * B, 1), make_act(dgall, 4 * H, Ti * B, 1)};
-      rc = launch_wgrad(maps, 2, TILES(li), NT(li), d_grads, Ti * B, 1, st); if (rc) return rc; ++li;
+      rc = launch_wgrad(maps, 2, TILES(li), NT(li), d_grads, Ti * B, 1, sx); if (rc) return rc; ++li;
       ActT maps2[2] = {make_act(x3, lo.C, Ti, B), make_act(dpre, 4 * H, Ti, B)};
-      rc = launch_wgrad(maps2, 2, TILES(li), NT(li), d_grads, Ti, B, st); if (rc) return rc; ++li;
-      colsum_bf16_kernel<<<64, 256, 0, st>>>(dpre, (long long)B * Ti, 4 * H, 4 * H, d_grads + lo.p_elb[d], 1.f); t2_count_launch();
+      rc = launch_wgrad(maps2, 2, TILES(li), NT(li), d_grads, Ti, B, sx); if (rc) return rc; ++li;
+      colsum_bf16_kernel<<<64, 256, 0, sx>>>(dpre, (long long)B * Ti, 4 * H, 4 * H, d_grads + lo.p_elb[d], 1.f); t2_count_launch();
     }
+  }
+  if (side) {
+    T2_CHECK_CUDA(cudaEventRecord(side->join, side->s));
+    T2_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   }
   // dx3 = dpre_fw x Wx_fw^T + dpre_bw x Wx_bw^T
   bf16* dx3 = reinterpret_cast<bf16*>(ws + lo.w_dx3);
