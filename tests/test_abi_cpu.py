@@ -108,3 +108,42 @@ def test_product_initialiser_matches_reference_init_rules():
     assert all((p[n] == 0).all() for n in p if n.endswith(("beta", "moving_mean", "bias")))
     e = p["inputs_embedding"]
     assert e.abs().max() <= math.sqrt(6.0 / sum(e.shape))
+
+
+def test_reference_python_surface_validates_like_the_reference():
+    """create_model / initialize argument checks fire before any GPU work (tacotron.py:41-54, wavenet models/__init__.py:6-9)"""
+    import torch
+    from hparams import hparams
+    from tacotron.models import create_model as create_taco
+    from wavenet_vocoder.models import create_model as create_wn
+    from wavenet_vocoder import util
+    with pytest.raises(Exception, match="Unknown model"):
+        create_taco("Tacotron3", hparams)
+    with pytest.raises(Exception, match="Unknow model"):
+        hp = hparams.copy()
+        hp.parse("input_type=raw,out_channels=30")
+        create_wn("WaveRNN", hp)
+    bad = hparams.copy()
+    bad.parse("input_type=mulaw-quantize,quantize_channels=256,out_channels=30")
+    with pytest.raises(RuntimeError):
+        create_wn("WaveNet", bad)
+    m = create_taco("Tacotron", hparams)
+    ids, lens = torch.zeros(2, 5, dtype=torch.int32), torch.tensor([5, 4])
+    mel, stop = torch.zeros(2, 7, hparams.num_mels), torch.zeros(2, 7)
+    with pytest.raises(ValueError):
+        m.initialize(ids, lens, stop_token_targets=stop)                    # stop targets without mel targets
+    with pytest.raises(ValueError):
+        m.initialize(ids, lens, mel_targets=mel)                            # mel targets without stop targets
+    with pytest.raises(ValueError):
+        m.initialize(ids, lens, mel, stop, is_training=True)                # predict_linear=True (default) without linear targets
+    hp_mel = hparams.copy()
+    hp_mel.set_hparam("predict_linear", False)
+    with pytest.raises(RuntimeError):
+        create_taco("Tacotron", hp_mel).initialize(ids, lens, mel, stop, is_training=True, is_evaluating=True)
+    with pytest.raises(ValueError):
+        m.initialize(ids, lens, mel, gta=True, linear_targets=mel)
+    assert util.is_mulaw_quantize("mulaw-quantize") and util.is_scalar_input("raw") and not util.is_raw("mulaw")
+    with pytest.raises(AssertionError):
+        util.is_mulaw("pcm")
+    mask = util.sequence_mask([3, 1], max_len=4, expand=False)
+    assert mask.tolist() == [[1, 1, 1, 0], [1, 0, 0, 0]] and util.sequence_mask([2, 1]).shape == (2, 2, 1)
