@@ -58,3 +58,28 @@ def test_pad_lr_alignment():
     x = np.zeros(22050)
     l, r = audio.librosa_pad_lr(x, 2048, 275)
     assert (len(x) + l + r) == (len(x) // 275 + 1) * 275
+
+
+def test_mulaw_properties():
+    """size-independent properties of the companding family (wavenet_vocoder/util.py:30-129): odd symmetry, monotone,
+    indices cover [0, 255], expand(compress(x)) == x, quantise(expand(q)) within one bin (truncation)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    @settings(max_examples=60, deadline=None)
+    @given(hnp.arrays(np.float32, hnp.array_shapes(min_dims=1, max_dims=1, min_side=1, max_side=257),
+                      elements=st.floats(-1, 1, width=32)))
+    def check(x):
+        y = audio.mulaw(x)
+        assert np.all(np.abs(y) <= 1.0 + 1e-6)
+        assert np.allclose(audio.mulaw(-x), -y, atol=1e-7)
+        assert np.allclose(audio.inv_mulaw(y), x, atol=2e-6)
+        q = audio.mulaw_quantize(x)
+        assert q.min() >= 0 and q.max() <= 255
+        xs = np.sort(x)
+        assert np.all(np.diff(audio.mulaw_quantize(xs)) >= 0)                  # monotone
+        back = audio.mulaw_quantize(audio.inv_mulaw_quantize(q).astype(np.float32))
+        assert np.abs(back - q).max() <= 1
+    check()
+    assert audio.mulaw_quantize(np.zeros(0, np.float32)).shape == (0,)          # empty input
