@@ -41,7 +41,8 @@ long long t2_launch_count(void);
 int t2_dbg_conv_gemm(const void* d_a, int B, int T, int C, int ld, const int* shifts, int nshift,
                      const void* d_w, int N, int BN, const float* d_bias, int relu, void* d_out_bf16,
                      float* d_out_f32, void* stream);
-/* debug: non-NULL => every GEMM CTA records 8 clock64() stamps at d_buf[cta*8 + slot]; NULL disables */
+/* debug: non-NULL => every GEMM CTA records 16 int64 stamps (clock64 phases, %globaltimer at entry / after the dependent-launch
+ * wait / exit, SM id) at d_buf[(launch_offset + cta)*16 + slot], consecutive launches append; NULL disables */
 int t2_dbg_set_timing_buffer(long long* d_buf);
 /* weight-gradient GEMM: out[m,n] = scale * sum_{b,t} a[b,t+shift_a,m] * bm[b,t,n]  (fp32 [Ca,Cb]); synchronises. */
 int t2_dbg_wgrad(const void* d_a, int Ca, const void* d_bm, int Cb, int B, int T, int shift_a, float scale,
@@ -181,6 +182,14 @@ int t2_taco_infer_steps(const t2_taco_config_t* cfg, float* d_params, const void
 int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, int T_used,
                          void* stream);
 /* tools only: clock64() phase stamps of the attention kernels into a device buffer of 32 int64 (NULL turns them off) */
+/* Counter-hash RNG behind the in-kernel dropout / zoneout masks (SURVEY.md §7 "stochastic ops in parity"):
+ * d_out[i] = U[0,1) drawn for element (first_index + i) of hash stream `stream_id` under `seed` (= the seed passed to
+ * t2_taco_forward / t2_wn_forward plus the device step counter). Element kept / updated iff d_out[i] >= rate.
+ * Tacotron stream ids: encoder conv dropout 10+i, prenet 20 / 21, postnet conv dropout 30+i (element = linear index of
+ * the layer output), zoneout (c, h) = 2*s, 2*s+1 with s = 52 / 53 (encoder fw / bw), 54 / 55 (decoder LSTM 1 / 2) and
+ * element = (t*B + b)*H + unit. Replaces tf.layers.dropout / tf.nn.dropout draws of tacotron/models/modules.py:133-134,249,389. */
+int t2_rng_uniform_f32(unsigned long long seed, unsigned int stream_id, long long first_index, long long n, float* d_out,
+                       void* stream);
 int t2_dbg_att_stamps(long long* d_buf);
 int t2_dbg_ar_stamps(long long* d_buf);    /* same for one layer pass of the AR synthesis kernel (16 int64) */
 int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr,

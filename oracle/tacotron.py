@@ -203,6 +203,11 @@ def prenet(x, params, hp, drop_masks=None):
     return x
 
 
+def location_sensitive_score(W_query, W_fil, W_keys, v_a, b_a):
+    """attention.py:38-70: energy = sum_units v_a * tanh(W_keys + W_query + W_fil + b_a). [B,1,A], [B,T,A], [B,T,A] -> [B,T]."""
+    return (v_a * torch.tanh(W_keys + W_query + W_fil + b_a)).sum(-1)
+
+
 def attention_step(query, cum, keys, values, mask, params):
     """attention.py:169-226 + _compute_attention :10-35. query [B, D]; cum [B, T_in]; returns (context, alignments)."""
     pq = (query @ params["attention/query_layer/kernel"]).unsqueeze(1)              # [B, 1, A]
@@ -210,8 +215,8 @@ def attention_step(query, cum, keys, values, mask, params):
     f = F.conv1d(cum.unsqueeze(1), kf.permute(2, 1, 0).contiguous(), params["attention/location_features_convolution/bias"],
                  padding=(kf.shape[0] - 1) // 2).transpose(1, 2)                       # [B, T_in, 32]
     pl = f @ params["attention/location_features_layer/kernel"]                        # [B, T_in, A]
-    e = (params["attention/attention_variable_projection"] *
-         torch.tanh(keys + pq + pl + params["attention/attention_bias"])).sum(-1)      # [B, T_in]
+    e = location_sensitive_score(pq, pl, keys, params["attention/attention_variable_projection"],
+                                 params["attention/attention_bias"])                   # [B, T_in]
     e = torch.where(mask > 0, e, torch.full_like(e, -float("inf")))                    # _maybe_mask_score
     a = torch.softmax(e, dim=-1)
     ctx = torch.bmm(a.unsqueeze(1), values).squeeze(1)

@@ -507,10 +507,11 @@ def adam_step(params, grads, state, hp, global_step):
     return lr
 
 
-def train_step(params, x, c, y, lengths, hp, c_is_upsampled=False):
-    """One teacher-forced forward + loss + autograd backward. Returns (loss, grads, y_hat)."""
+def train_step(params, x, c, y, lengths, hp, c_is_upsampled=False, dropout_masks=None):
+    """One teacher-forced forward + loss + autograd backward. Returns (loss, grads, y_hat).
+    dropout_masks: optional per-layer [B, R, T] masks already scaled by 1/keep (modules.py:483-484 draws them with tf.layers.dropout)."""
     ps = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    y_hat = step(x, c, ps, hp, c_is_upsampled=c_is_upsampled)
+    y_hat = step(x, c, ps, hp, dropout_masks=dropout_masks, c_is_upsampled=c_is_upsampled)
     loss = loss_fn(y_hat, y, lengths, hp)
     used = [k for k in ps]
     gr = torch.autograd.grad(loss, [ps[k] for k in used], allow_unused=True)

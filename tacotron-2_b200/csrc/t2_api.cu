@@ -75,9 +75,27 @@ extern "C" int t2_dbg_wgrad(const void* a, int Ca, const void* bm, int Cb, int B
   return rc;
 }
 
-// debug: when non-NULL every act_gemm CTA writes 8 clock64() stamps (entry, setup done, first stage landed, MMAs issued,
-// accumulator ready, epilogue done, teardown) to d_buf[cta * 8 + slot]
+// debug: when non-NULL every act_gemm CTA writes stamps to d_buf[(launch offset + cta) * 16 + slot]: slots 0-6 clock64() at entry,
+// setup done, first stage landed, MMAs issued, accumulator ready, epilogue done, teardown; 8-10 %globaltimer (ns) at entry, after the
+// programmatic-dependent-launch wait, at exit; 11 = SM id. Each launch advances the offset by its CTA count.
 extern "C" int t2_dbg_set_timing_buffer(long long* d_buf) {
   t2::set_timing_buffer(d_buf);
+  return T2_OK;
+}
+
+// The counter-hash behind every in-kernel dropout / zoneout mask, exported so that a parity test can rebuild the exact
+// masks a training step drew and feed them to the CPU oracle: out[i] = hash_uniform32(hash_seed(seed, stream), i0 + i).
+// An element is KEPT (dropout) / UPDATED (zoneout) iff out[i] >= rate.
+__global__ void rng_uniform_kernel(unsigned long long seed, unsigned int stream, long long i0, long long n, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = t2::hash_uniform32(t2::hash_seed(seed, stream), (unsigned long long)(i0 + i));
+}
+extern "C" int t2_rng_uniform_f32(unsigned long long seed, unsigned int stream_id, long long first_index, long long n, float* d_out,
+                                  void* stream) {
+  T2_REQUIRE(n >= 0 && (n == 0 || d_out != nullptr), T2_ERR_INVALID_ARG, "rng_uniform: bad arguments");
+  if (n == 0) return T2_OK;
+  rng_uniform_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, stream_id, first_index, n, d_out);
+  t2_count_launch();
+  T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }

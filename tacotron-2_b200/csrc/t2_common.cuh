@@ -82,6 +82,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ long long smid() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+
 // Counter-based RNG used for in-kernel dropout / zoneout / sampling: one 32-bit hash per
 // (seed, stream, index). SplitMix-style finaliser; quality is ample for Bernoulli masks.
 __device__ __host__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {

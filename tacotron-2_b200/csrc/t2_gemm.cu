@@ -125,6 +125,8 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
   g.dbg = g_timing_buffer;
   g.epi = c.epi;
   dim3 grid(g.tiles_per_b * c.B, c.n_tiles, 1);
+  // every launch gets its own slice of the timing buffer (so a captured graph stamps each of its kernel nodes separately)
+  if (g_timing_buffer) g_timing_buffer += size_t(grid.x) * grid.y * (c.ksplit > 1 ? c.ksplit : 1) * kDbgSlots;
   if (c.ksplit > 1) {
     T2_REQUIRE(epi == EPI_TOUT && c.ksplit * kBK <= ktot, T2_ERR_INVALID_ARG,
                "act_gemm: split-K needs an atomically accumulating epilogue and at least one k-block per slice");

@@ -811,8 +811,8 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int m_tile = blockIdx.x;
-  long long* dbg = g.dbg ? g.dbg + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
-  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  long long* dbg = g.dbg ? g.dbg + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kDbgSlots : nullptr;
+  if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[8] = globaltimer_ns(); dbg[11] = smid(); }
   const int b = m_tile / g.tiles_per_b;
   const int t0 = (m_tile - b * g.tiles_per_b) * kBM;
 
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   // everything above is CTA-local set-up and overlaps the previous kernel's tail under PDL; global memory from here on
   pdl_wait();
   pdl_launch_dependents();
-  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  if (dbg && threadIdx.x == 0) { dbg[1] = clock64(); dbg[9] = globaltimer_ns(); }
 
   if (warp == 0) {
     if (elect_one()) {
@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   }
   tc_fence_before();
   __syncthreads();
-  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
+  if (dbg && threadIdx.x == 0) { dbg[6] = clock64(); dbg[10] = globaltimer_ns(); }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);

@@ -9,6 +9,7 @@ constexpr int kBM = 128;      // positions per tile (UMMA M)
 constexpr int kBK = 64;       // K elements per pipeline stage (= one 128-byte swizzle row of bf16)
 constexpr int kMaxSeg = 8;
 constexpr int kGemmThreads = 192;
+constexpr int kDbgSlots = 16;  // int64 stamps per CTA in the optional timing buffer (t2_dbg_set_timing_buffer)
 
 struct Seg {
   int map;      // which A tensor map
@@ -35,7 +36,7 @@ struct GemmArgs {
   int tiles_per_b;   // ceil(T / 128)
   int b_layer;       // layer coordinate of the weight tensor map (3-D maps), else 0
   int b_k0;          // first K column of the packed weight this GEMM consumes
-  long long* dbg;    // optional: 8 clock64() stamps per CTA (see t2_dbg_set_timing_buffer)
+  long long* dbg;    // optional: kDbgSlots stamps per CTA (see t2_dbg_set_timing_buffer)
   EpiArgs epi;
 };
 

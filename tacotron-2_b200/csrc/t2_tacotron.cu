@@ -1383,7 +1383,7 @@ static int encoder_fwd(const StepCtx& s, const int* d_inputs, const int* d_input
                      cc + (long long)sidx * B * H, cc + (long long)(sidx + 1) * B * H, hh + (long long)sidx * B * H, H,
                      hh + (long long)(sidx + 1) * B * H, H, memory + (long long)t * 2 * H + d * H, Ti * 2 * H,
                      reinterpret_cast<bf16*>(ws + lo.w_encg[d]) + (long long)sidx * B * 4 * H,
-                     reinterpret_cast<bf16*>(ws + lo.w_enct[d]) + (long long)sidx * B * H, d_input_lengths, t, 2 + d, lo.c.zoneout_rate);
+                     reinterpret_cast<bf16*>(ws + lo.w_enct[d]) + (long long)sidx * B * H, d_input_lengths, t, 52 + d, lo.c.zoneout_rate);
       if (rc) return rc;
     }
   }
@@ -1436,12 +1436,12 @@ static int decoder_step(const StepCtx& s, const DecBufs& d, const int* d_input_l
   int rc = lstm_step(s, pk + lo.k_l1r, D, K1r, S1t, B, d.pre1 + (long long)t * B * 4 * D, 4 * D, nullptr, d.c1 + (long long)t * B * D,
                      d.c1 + (long long)(t + 1) * B * D, S1t + 2 * H, K1r, S1n + 2 * H, K1r, S2t, K2,
                      reinterpret_cast<bf16*>(ws + lo.w_g1) + (long long)t * B * 4 * D, reinterpret_cast<bf16*>(ws + lo.w_t1) + (long long)t * B * D,
-                     nullptr, t, 4, lo.c.zoneout_rate);
+                     nullptr, t, 54, lo.c.zoneout_rate);
   if (rc) return rc;
   // LSTM 2: state operand [h1out_t | h2_{t-1}]
   rc = lstm_step(s, pk + lo.k_l2, D, K2, S2t, B, nullptr, 0, d_params + lo.p_l2b, d.c2 + (long long)t * B * D, d.c2 + (long long)(t + 1) * B * D,
                  S2t + D, K2, S2n + D, K2, PIt, PIK, reinterpret_cast<bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D,
-                 reinterpret_cast<bf16*>(ws + lo.w_t2) + (long long)t * B * D, nullptr, t, 5, lo.c.zoneout_rate);
+                 reinterpret_cast<bf16*>(ws + lo.w_t2) + (long long)t * B * D, nullptr, t, 55, lo.c.zoneout_rate);
   if (rc) return rc;
   AttArgs a;
   a.h2out = PIt; a.ld_h2 = PIK; a.WqT = reinterpret_cast<const bf16*>(pk + lo.k_qT);
@@ -1665,6 +1665,22 @@ extern "C" int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_wor
   };
   for (const E& e : table)
     if (strcmp(e.n, name) == 0) { *ptr = ws + e.off; *count = e.cnt; *elem_bytes = e.eb; return T2_OK; }
+  // per-layer conv-block tensors: "enc_conv_y<i>" / "enc_conv_x<i>" / "post_conv_y<i>" / "post_conv_x<i>" (y = conv + activation,
+  // x = batch norm + dropout; bf16 [B][T][C]) and the postnet projection "postnet_residual" (fp32 [B][T_out][128])
+  if (strcmp(name, "postnet_residual") == 0) { *ptr = ws + lo.w_resid; *count = B * To * 128; *elem_bytes = 4; return T2_OK; }
+  for (int which = 0; which < 2; ++which) {
+    const std::vector<ConvL>& v = which == 0 ? lo.enc : lo.post;
+    const char* pre = which == 0 ? "enc_conv_" : "post_conv_";
+    const size_t pl = strlen(pre);
+    if (strncmp(name, pre, pl) == 0 && (name[pl] == 'x' || name[pl] == 'y') && name[pl + 1] >= '0' && name[pl + 1] <= '9') {
+      const int i = name[pl + 1] - '0';
+      if (i < int(v.size())) {
+        *ptr = ws + (name[pl] == 'x' ? v[i].w_x : v[i].w_y);
+        *count = B * (which == 0 ? Ti : To) * v[i].cout; *elem_bytes = 2;
+        return T2_OK;
+      }
+    }
+  }
   return t2_set_error(T2_ERR_INVALID_ARG, "unknown workspace tensor '%s'", name);
 }
 
@@ -1774,7 +1790,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
     c2.dh_ext = dh2ext; c2.zero_ext = 0; c2.ld_ext = D; c2.dhs = dhs2; c2.dcs = dcs2;
     c2.gst = reinterpret_cast<const bf16*>(ws + lo.w_g2) + (long long)t * B * 4 * D; c2.tst = reinterpret_cast<const bf16*>(ws + lo.w_t2) + (long long)t * B * D;
     c2.c_prev = reinterpret_cast<const float*>(ws + lo.w_c2) + (long long)t * B * D;
-    c2.dg_a = dg2 + (long long)t * B * 4 * D; c2.ld_a = 4 * D; c2.dg_b = nullptr; c2.ld_b = 0; c2.lens = nullptr; c2.t = t; c2.B = B; c2.H = D; c2.stream = 5;
+    c2.dg_a = dg2 + (long long)t * B * 4 * D; c2.ld_a = 4 * D; c2.dg_b = nullptr; c2.ld_b = 0; c2.lens = nullptr; c2.t = t; c2.B = B; c2.H = D; c2.stream = 55;
     c2.zone = lo.c.zoneout_rate; c2.seed = seed; c2.step = d_step;
     T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * D)), dim3(256), 0, st, c2)); t2_count_launch();
     rc = lstm_bwd_gemm(s, pk + lo.k_l2T, K2, 4 * D, c2.dg_a, B, dh1ext, D, D, 2, dhs2, D, 2, ks_dec);   // dh1ext: zeroed by its consumer
@@ -1782,7 +1798,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
     CellBwd c1 = c2;
     c1.dh_ext = dh1ext; c1.zero_ext = 1; c1.dhs = dhs1; c1.dcs = dcs1;
     c1.gst = reinterpret_cast<const bf16*>(ws + lo.w_g1) + (long long)t * B * 4 * D; c1.tst = reinterpret_cast<const bf16*>(ws + lo.w_t1) + (long long)t * B * D;
-    c1.c_prev = reinterpret_cast<const float*>(ws + lo.w_c1) + (long long)t * B * D; c1.dg_a = dg1 + (long long)t * B * 4 * D; c1.stream = 4;
+    c1.c_prev = reinterpret_cast<const float*>(ws + lo.w_c1) + (long long)t * B * D; c1.dg_a = dg1 + (long long)t * B * 4 * D; c1.stream = 54;
     T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * D)), dim3(256), 0, st, c1)); t2_count_launch();
     rc = lstm_bwd_gemm(s, pk + lo.k_l1rT, K1r, 4 * D, c1.dg_a, B, dctxl, 2 * H, 2 * H, 2, dhs1, D, 2, ks_dec);  // dctxl: zeroed by att_bwd
     if (rc) return rc;
@@ -1861,7 +1877,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
       c.tst = reinterpret_cast<const bf16*>(ws + lo.w_enct[d]) + (long long)sidx * B * H;
       c.c_prev = reinterpret_cast<const float*>(ws + lo.w_encc[d]) + (long long)sidx * B * H;
       c.dg_a = dgall + (long long)sidx * B * 4 * H; c.ld_a = 4 * H; c.dg_b = dpre + (long long)t * 4 * H; c.ld_b = (long long)Ti * 4 * H;
-      c.lens = d_input_lengths; c.t = t; c.B = B; c.H = H; c.stream = 2 + d; c.zone = lo.c.zoneout_rate; c.seed = seed; c.step = d_step;
+      c.lens = d_input_lengths; c.t = t; c.B = B; c.H = H; c.stream = 52 + d; c.zone = lo.c.zoneout_rate; c.seed = seed; c.step = d_step;
       T2_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(g1((long long)B * H)), dim3(256), 0, sx, c)); t2_count_launch();
       rc = lstm_bwd_gemm(sc, pk + lo.k_encWrT[d], H, 4 * H, c.dg_a, B, edh, H, H, 2, nullptr, 0, 0, ks_enc);
       if (rc) return rc;

@@ -222,6 +222,16 @@ class Tacotron(object):
             n *= d
         return t[:n].reshape(shape)        # compact results (synthesis) use a prefix of the buffer
 
+    def rng_uniform(self, stream_id, n, seed=None, first_index=0):
+        """The U[0,1) draws behind the in-kernel dropout / zoneout masks of hash stream `stream_id` (include/t2b200.h,
+        t2_rng_uniform_f32) for the step that ran with `seed` (default: this model's seed + the device step counter)."""
+        if seed is None:
+            seed = getattr(self, "_last_seed", self.seed) + int(self.step_dev.item())
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        L.check(self.lib.t2_rng_uniform_f32(ctypes.c_ulonglong(seed), ctypes.c_uint(stream_id), ctypes.c_longlong(first_index),
+                                            ctypes.c_longlong(n), L.ptr(out), L.stream_ptr()))
+        return out
+
     def losses(self):
         b, a, s, r = self.loss_buf.tolist()
         return {"before": b, "after": a, "stop": s, "reg": r, "total": b + a + s + r}

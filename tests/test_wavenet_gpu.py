@@ -19,6 +19,7 @@ import torch
 from hparams import hparams
 from oracle import wavenet as ow
 from t2_import import t2
+from parity_util import record
 
 pytestmark = pytest.mark.gpu
 
@@ -85,6 +86,8 @@ def _run(hp, B, T, seed, loss_tol=1e-3):
     err = (lg - ref).abs()
     print("loss cuda %.6f oracle %.6f | logits max err %.4g mean err %.4g (ref absmax %.3g)" % (
         loss, loss_ref.item(), err.max().item(), err.mean().item(), ref.abs().max().item()))
+    record("wavenet_small_%s_L%d_R%d_B%dxT%d" % (hp.input_type, hp.layers, hp.residual_channels, B, T), loss_abs_err=abs(loss - loss_ref.item()),
+           logits_max_err=err.max().item(), logits_mean_err=err.mean().item(), cup_max_err=(cup - cup_ref).abs().max().item())
     assert err.max().item() < 4e-2 and err.mean().item() < 6e-3
     assert abs(loss - loss_ref.item()) < loss_tol
     grads = model.export_grads()
@@ -105,6 +108,7 @@ def _run(hp, B, T, seed, loss_tol=1e-3):
             print("\n".join(report))
         assert not bad, "gradient mismatch vs %s oracle:\n" % tag + "\n".join(bad)
         print("worst per-tensor relative gradient error vs %s oracle: %.4g" % (tag, worst))
+        record("wavenet_small_%s_L%d_R%d_B%dxT%d_grads_vs_%s" % (hp.input_type, hp.layers, hp.residual_channels, B, T, tag), worst_rel=worst)
     return model, params
 
 
