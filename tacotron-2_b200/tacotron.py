@@ -18,10 +18,33 @@ class TacoConfig(ctypes.Structure):
         (n, ctypes.c_float) for n in ("dropout_rate", "zoneout_rate", "reg_weight", "max_abs_value", "lower_bound_decay")]
 
 
+def unsupported_hparams(hp):
+    """hparam-gated variants of the reference graph that change the arithmetic and that this path does NOT implement: every one
+    is rejected instead of silently training a different model. Returns a list of human-readable reasons."""
+    bad = []
+    def need(name, ok, why):
+        if name in hp and not ok(getattr(hp, name)):
+            bad.append("%s=%r (%s)" % (name, getattr(hp, name), why))
+    need("outputs_per_step", lambda v: v == 1, "reduction factor r > 1: tacotron.py:141-143, helpers.py:77")
+    need("predict_linear", lambda v: not v, "CBHG post-processing net + linear loss: tacotron.py:203-219, modules.py:19-78")
+    need("mask_decoder", lambda v: not v, "masked losses: modules.py:412-455")
+    need("prenet_layers", lambda v: len(v) == 2, "2 prenet layers")
+    need("decoder_layers", lambda v: v == 2, "2 decoder LSTM layers")
+    need("smoothing", lambda v: not v, "smoothing normalisation instead of softmax: attention.py:72-92")
+    need("cumulative_weights", lambda v: bool(v), "non-cumulative location features: attention.py:220-224")
+    need("batch_norm_position", lambda v: v == "after", "batch norm before the activation: modules.py:386-389")
+    need("mask_encoder", lambda v: bool(v), "un-masked encoder memory")
+    need("tacotron_teacher_forcing_mode", lambda v: v == "constant", "scheduled teacher forcing: helpers.py:135-169")
+    need("tacotron_teacher_forcing_ratio", lambda v: float(v) == 1.0, "per-step teacher-forcing draw: helpers.py:121-124")
+    need("tacotron_fine_tuning", lambda v: not v, "frozen embedding / encoder variables: tacotron.py:401")
+    need("cross_entropy_pos_weight", lambda v: float(v) == 1.0, "weighted stop-token loss only exists in the masked loss path")
+    return bad
+
+
 def make_config(hp, B, T_in, T_out):
-    if hp.outputs_per_step != 1 or hp.predict_linear or hp.mask_decoder or len(hp.prenet_layers) != 2 or hp.decoder_layers != 2:
-        raise L.T2Error("B200 Tacotron path covers outputs_per_step=1, predict_linear=False, mask_decoder=False, "
-                        "2 prenet layers, 2 decoder LSTM layers")
+    bad = unsupported_hparams(hp)
+    if bad:
+        raise L.T2Error("hparams not implemented on the B200 Tacotron path (they would change the model): " + "; ".join(bad))
     c = TacoConfig()
     c.B, c.T_in, c.T_out = B, T_in, T_out
     c.n_symbols, c.num_mels, c.embedding_dim = N_SYMBOLS, hp.num_mels, hp.embedding_dim
@@ -32,7 +55,10 @@ def make_config(hp, B, T_in, T_out):
     c.decoder_lstm_units = hp.decoder_lstm_units
     c.postnet_layers, c.postnet_kernel, c.postnet_channels = hp.postnet_num_layers, hp.postnet_kernel_size[0], hp.postnet_channels
     c.clip_outputs = int(hp.clip_outputs)
-    c.dropout_rate, c.zoneout_rate, c.reg_weight = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate, hp.tacotron_reg_weight
+    reg_weight = hp.tacotron_reg_weight
+    if getattr(hp, "tacotron_scale_regularization", False):       # tacotron.py:334-338
+        reg_weight *= 1.0 / (2 * hp.max_abs_value) if hp.symmetric_mels else 1.0 / hp.max_abs_value
+    c.dropout_rate, c.zoneout_rate, c.reg_weight = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate, reg_weight
     c.max_abs_value, c.lower_bound_decay = hp.max_abs_value, hp.lower_bound_decay
     return c
 
@@ -160,11 +186,13 @@ class Tacotron(object):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
+        n0 = self.lib.t2_launch_count()
         with torch.cuda.graph(self._graph):
             self.step_dev.add_(1)
             self.pack()
             self.forward(*self._static)
             self.backward()
+        self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
         return self._graph
 
     def train_step(self, inputs=None, input_lengths=None, mel_targets=None, stop_targets=None, world_size=1):
@@ -175,14 +203,23 @@ class Tacotron(object):
                     dst.copy_(src, non_blocking=True)
             self._graph.replay()
         else:
+            n0 = self.lib.t2_launch_count()
             self.step_dev.add_(1)
             self.forward(inputs, input_lengths, mel_targets, stop_targets)
             self.backward()
+            self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
         if world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        n0 = self.lib.t2_launch_count()
         self.optimizer_step(grad_scale=1.0 / world_size)
+        self._opt_launches = self.lib.t2_launch_count() - n0
         return self.loss_buf
+
+    @property
+    def launches_per_step(self):
+        """kernels of libt2b200 per optimisation step (graph replays re-launch the captured ones)"""
+        return getattr(self, "_fwd_bwd_launches", 0) + getattr(self, "_opt_launches", 0)
 
     def learning_rate(self):
         hp = self.hp

@@ -34,7 +34,27 @@ _INPUT_TYPES = {"raw": 0, "mulaw": 1, "mulaw-quantize": 2}
 _UPSAMPLE_TYPES = {"SubPixel": 0, "2D": 1}
 
 
+def unsupported_hparams(hp):
+    """hparam-gated variants of the reference WaveNet that change the arithmetic and are NOT implemented here"""
+    bad = []
+    def need(name, ok, why):
+        if name in hp and not ok(getattr(hp, name)):
+            bad.append("%s=%r (%s)" % (name, getattr(hp, name), why))
+    need("wavenet_weight_normalization", lambda v: not v, "weight normalisation with data-dependent init: modules.py:44-177")
+    need("use_bias", lambda v: bool(v), "bias-free convolutions")
+    need("gin_channels", lambda v: v is None or v <= 0, "global (speaker) conditioning: wavenet.py:151-158,669-678")
+    need("kernel_size", lambda v: v == 3, "kernel_size 3")
+    need("upsample_type", lambda v: v in _UPSAMPLE_TYPES, "Resize / 1D / NearestNeighbor upsamplers: modules.py:524-536,657-733")
+    need("upsample_activation", lambda v: v in ("Relu", "relu", "RELU"), "LeakyRelu / linear upsampling activations: wavenet.py:190-201")
+    need("freq_axis_kernel_size", lambda v: v == 3, "freq_axis_kernel_size 3")
+    need("input_type", lambda v: v in _INPUT_TYPES, "raw | mulaw | mulaw-quantize")
+    return bad
+
+
 def make_config(hp, B, T, c_pre_upsampled=False, dropout=None):
+    bad = unsupported_hparams(hp)
+    if bad:
+        raise L.T2Error("hparams not implemented on the B200 WaveNet path (they would change the model): " + "; ".join(bad))
     cfg = WnConfig()
     cfg.layers, cfg.stacks = hp.layers, hp.stacks
     cfg.residual_channels, cfg.gate_channels, cfg.skip_out_channels = (

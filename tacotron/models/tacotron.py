@@ -7,31 +7,44 @@ otherwise), `add_loss()` publishes the four loss terms, `add_optimizer(global_st
 (`tower_mel_outputs`, `tower_alignments`, `tower_stop_token_prediction`, `tower_decoder_output`, `loss`,
 `before_loss`, `after_loss`, `stop_token_loss`, `regularization_loss`, `learning_rate`, `gradients`). One process per
 GPU replaces the towers. predict_linear / CBHG, outputs_per_step > 1 and mask_decoder are out of scope."""
+import collections
+
 import torch
 
 from t2_import import t2
+
+# Engines are specialised to (B, T_in, T_out) and the reference feeder pads every batch to its own maxima (tacotron/feeder.py:
+# 231-256). Padding further is NOT transparent here (batch-norm statistics include the padded frames, modules.py:388), so shapes
+# are kept exact and at most `_MAX_ENGINES` engines (with their BPTT workspaces) stay alive, least recently used first out;
+# parameters, Adam state and gradients are shared between them.
+_MAX_ENGINES = 4
 
 
 class Tacotron(object):
     def __init__(self, hparams):
         self._hparams = hparams
-        self._engines = {}
+        self._engines = collections.OrderedDict()
         self._pending = None
 
     def _engine(self, B, T_in, T_out):
         key = (B, T_in, T_out)
-        if key not in self._engines:
-            eng = t2.tacotron.Tacotron(self._hparams, B, T_in, T_out)
-            if self._engines:
-                first = next(iter(self._engines.values()))
-                eng.params, eng.m, eng.v, eng.global_step = first.params, first.m, first.v, first.global_step
-            elif self._pending is not None:
-                eng.load_params(self._pending)
-                self._pending = None
-            else:
-                eng.init_variables()
-            self._engines[key] = eng
-        return self._engines[key]
+        if key in self._engines:
+            self._engines.move_to_end(key)
+            return self._engines[key]
+        donor = next(reversed(self._engines.values())) if self._engines else None
+        while len(self._engines) >= _MAX_ENGINES:                      # evict BEFORE allocating the new workspace
+            _, old = self._engines.popitem(last=False)
+            old.workspace = old.packed = None
+        eng = t2.tacotron.Tacotron(self._hparams, B, T_in, T_out)
+        if donor is not None:
+            eng.params, eng.m, eng.v, eng.grads, eng.global_step = donor.params, donor.m, donor.v, donor.grads, donor.global_step
+        elif self._pending is not None:
+            eng.load_params(self._pending)
+            self._pending = None
+        else:
+            eng.init_variables()
+        self._engines[key] = eng
+        return eng
 
     def load_variables(self, name_to_tensor):
         if self._engines:
@@ -116,7 +129,7 @@ class Tacotron(object):
             dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
         self.learning_rate = eng.optimizer_step(grad_scale=1.0 / world)
         for other in self._engines.values():
-            other.global_step, other.m, other.v, other._dirty = eng.global_step, eng.m, eng.v, True
+            other.global_step, other.m, other.v, other.grads, other._dirty = eng.global_step, eng.m, eng.v, eng.grads, True
         self.gradients = eng.grads
         self.optimize = None
         return self.learning_rate

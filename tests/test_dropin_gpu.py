@@ -35,9 +35,36 @@ def test_wavenet_create_model_train_eval_synthesize():
     assert losses[-1] < 0.9 * losses[0], losses
     model.initialize(idx, c, None, lengths)                                         # evaluation: y only
     assert float(model.add_loss()) < losses[0] and model.is_evaluating
-    model.initialize(None, c[:1, :, :4], None, None, synthesis_length=64)           # synthesis
+    # synthesis (wavenet.py:408-456): c is [batch, frames, cin]; the length is Tc * hop whatever synthesis_length says; the
+    # published y_hat is the DECODED waveform (inv_mulaw_quantize of the sampled indices), float in [-1, 1]
+    model.initialize(None, c[:1, :, :4].transpose(1, 2).contiguous(), None, None, synthesis_length=999)
     out = model.tower_y_hat[0]
-    assert out.shape == (1, 64) and int(out.min()) >= 0 and int(out.max()) <= 255
+    assert out.shape == (1, 64) and out.dtype == torch.float32 and float(out.min()) >= -1.0 and float(out.max()) <= 1.0
+    with pytest.raises(ValueError):
+        model.initialize(None, c[:1, :, :4], None, None)                            # channels-first c is rejected like the reference does
+    # batches of other lengths (the reference feeder pads each batch to its own maximum): lengths that are not a multiple of the
+    # 8-hop bucket are padded internally, results are sliced back, old engines are evicted (unbounded engine cache)
+    hp2 = hp.copy()
+    hp2.add_hparam("keep_logits", True)
+    m2 = create_model("WaveNet", hp2)
+    for T2 in (496, 256, 384, 128, 496):
+        m2.initialize(idx[:, :T2].unsqueeze(-1), c[:, :, :T2 // 16], None, torch.tensor([T2, T2 - 9]).cuda(), x=x[:, :, :T2])
+        assert m2.tower_y_hat[0].shape == (B, 256, T2) and m2.tower_upsampled_local_features[0].shape[1] == T2
+        l_a = float(m2.add_loss())
+        m2.add_optimizer()
+        assert l_a == l_a and len(m2._engines) <= 3
+    # padding to the bucket does not change the loss: T = 496 (padded to 512) vs the exact-size engine of the product API
+    from t2_import import t2
+    eng = t2.wavenet.WaveNet(hp, B, 496)
+    eng.params.copy_(m2.variables)
+    eng._packed_dirty = True
+    eng.cfg.dropout = 0.0
+    for e in m2._engines.values():
+        e.cfg.dropout = 0.0
+    len496 = torch.tensor([496, 400]).int().cuda()
+    eng.forward(idx[:, :496].int().contiguous(), c[:, :, :31].contiguous(), idx[:, :496].int().contiguous(), len496)
+    m2.initialize(idx[:, :496].unsqueeze(-1), c[:, :, :31], None, len496, x=x[:, :, :496])
+    assert abs(float(m2.add_loss()) - eng.loss_value()) < 2e-5
 
 
 def test_tacotron_create_model_train_gta_synthesize():

@@ -7,19 +7,28 @@ the loss, `add_optimizer(global_step)` runs backward (+ NCCL mean over ranks) + 
 calls the three per batch; the attribute names the reference's loops read (`loss`, `learning_rate`, `tower_y_hat`,
 `tower_upsampled_local_features`, ...) are kept. Tensors are torch CUDA tensors; one process per GPU replaces towers
 (`wavenet_num_gpus` is the world size of torch.distributed)."""
+import collections
+
 import torch
 
 from datasets.audio import get_hop_size
 from t2_import import t2
-from wavenet_vocoder.util import is_mulaw_quantize, is_scalar_input
+from wavenet_vocoder.util import is_mulaw, is_mulaw_quantize, is_scalar_input
+
+# Engines are specialised to (B, T): the reference feeders pad every batch to its own maximum, so shapes change from step to
+# step. T is therefore rounded up to a multiple of `_BUCKET_FRAMES` hops (right padding cannot influence earlier outputs of a
+# causal network and the loss is length-masked), and at most `_MAX_ENGINES` shape-specialised engines (workspaces of 1.6-13 GB
+# at the paper widths) stay alive, least recently used first out. Parameters, Adam state, EMA and gradients are shared.
+_BUCKET_FRAMES = 8
+_MAX_ENGINES = 3
 
 
 class WaveNet(object):
     def __init__(self, hparams, init=False):
         self._hparams = hparams
         self._init = init               # data-dependent weight-norm init of the reference: weight norm is out of scope (§8)
-        self._engines = {}
-        self._synths = {}
+        self._engines = collections.OrderedDict()
+        self._synths = collections.OrderedDict()
         self._state = None               # (params, m, v, ema, global_step) shared between shape-specialised engines
         self.variables = None
         self.ema = None
@@ -36,16 +45,21 @@ class WaveNet(object):
 
     def _engine(self, B, T):
         key = (B, T)
-        if key not in self._engines:
-            eng = t2.wavenet.WaveNet(self._hparams, B, T)
-            if self._engines:
-                first = next(iter(self._engines.values()))
-                eng.params, eng.m, eng.v, eng.ema = first.params, first.m, first.v, first.ema     # shared flat buffers
-                eng.global_step = first.global_step
-            else:
-                eng.init_variables()
-            self._engines[key] = eng
-        return self._engines[key]
+        if key in self._engines:
+            self._engines.move_to_end(key)
+            return self._engines[key]
+        donor = next(reversed(self._engines.values())) if self._engines else None
+        while len(self._engines) >= _MAX_ENGINES:                      # evict BEFORE allocating the new workspace
+            _, old = self._engines.popitem(last=False)
+            old.workspace = old.packed = None
+        eng = t2.wavenet.WaveNet(self._hparams, B, T)
+        if donor is not None:
+            eng.params, eng.m, eng.v, eng.ema, eng.grads = donor.params, donor.m, donor.v, donor.ema, donor.grads   # shared flat buffers
+            eng.global_step = donor.global_step
+        else:
+            eng.init_variables()
+        self._engines[key] = eng
+        return eng
 
     def load_variables(self, name_to_tensor):
         """restore from {TF variable name: array}"""
@@ -74,6 +88,16 @@ class WaveNet(object):
             xin = src.float().contiguous() if scalar else src.int().contiguous()
             tin = tgt.float().contiguous() if scalar else tgt.int().contiguous()
             B, T = xin.shape
+            hop = get_hop_size(hp) if self.local_conditioning_enabled() else 1
+            if self.local_conditioning_enabled() and T % hop:
+                raise t2.lib.T2Error("audio length %d is not a multiple of hop_size %d (wavenet_vocoder/feeder.py:400-401 guarantees it)" % (T, hop))
+            Tb = -(-T // (hop * _BUCKET_FRAMES)) * (hop * _BUCKET_FRAMES)
+            if Tb != T:                                                # right-pad to the bucket; lengths keep masking the loss
+                xin = torch.nn.functional.pad(xin, (0, Tb - T), value=0.0 if scalar else (hp.quantize_channels - 1) // 2)
+                tin = torch.nn.functional.pad(tin, (0, Tb - T), value=0.0 if scalar else (hp.quantize_channels - 1) // 2)
+                if c is not None:
+                    c = torch.nn.functional.pad(c, (0, Tb // hop - c.shape[-1]))
+            self._T_valid, T = T, Tb
             eng = self._engine(B, T)
             if getattr(self, "_pending", None) is not None:
                 eng.load_params(self._pending)
@@ -85,21 +109,36 @@ class WaveNet(object):
             eng.step_dev.add_(1)
             eng.forward(xin, c.float().contiguous(), tin, input_lengths.int().contiguous(), logits=self._logits,
                         save_for_backward=self.is_training)
-            self.tower_y = [tin]
+            Tv = self._T_valid
+            self.tower_y = [tin[:, :Tv]]
             self.tower_input_lengths = [input_lengths]
             self.tower_c = [c]
-            self.tower_upsampled_local_features = [eng.workspace_tensor("c_up", (B, T, hp.cin_channels))]
-            self.tower_y_hat = [self._logits[:, :, :hp.out_channels].transpose(1, 2)] if self._logits is not None else []
+            self.tower_upsampled_local_features = [eng.workspace_tensor("c_up", (B, T, hp.cin_channels))[:, :Tv]]
+            self.tower_y_hat = [self._logits[:, :Tv, :hp.out_channels].transpose(1, 2)] if self._logits is not None else []
             self.variables = eng.params
             self.ema = eng.ema
         else:
-            B = c.shape[0]
-            T = int(synthesis_length) if synthesis_length is not None else c.shape[-1] * get_hop_size(hp)
+            # wavenet.py:408-427: c arrives as [batch, local_condition_time, cin_channels]; the synthesis length is OVERWRITTEN by
+            # Tc * hop_size and c is transposed to channels-first
+            if c is None:
+                raise NotImplementedError("unconditional synthesis (cin_channels < 0) is out of scope (SURVEY.md §8)")
+            if c.dim() != 3 or c.shape[-1] != hp.cin_channels:
+                raise ValueError("Expected 3 dimension shape [batch_size(1), time_length, %d] for local condition features but found %s"
+                                 % (hp.cin_channels, tuple(c.shape)))
+            B, Tc = c.shape[0], c.shape[1]
+            T = Tc * get_hop_size(hp)
+            c = c.transpose(1, 2)
             key = (B, T)
-            if key not in self._synths:
+            if key in self._synths:
+                self._synths.move_to_end(key)
+            else:
+                while len(self._synths) >= _MAX_ENGINES:
+                    self._synths.popitem(last=False)
                 self._synths[key] = t2.wavenet.WaveNetSynthesizer(hp, B, T, cluster_size=getattr(hp, "synthesis_cluster_size", 16))
             syn = self._synths[key]
-            src = next(iter(self._engines.values())) if self._engines else None
+            # the live weights, not the EMA shadow: the reference's checkpoints store the live values under the shadow names
+            # (wavenet_vocoder/train.py:75-83), so that is what its synthesizer restores
+            src = next(reversed(self._engines.values())) if self._engines else None
             if src is not None:
                 syn.load_params(src.export_params())
             elif getattr(self, "_pending", None) is not None:
@@ -110,7 +149,12 @@ class WaveNet(object):
             if not scalar:
                 initial.fill_((hp.quantize_channels - 1) // 2)                      # mulaw_quantize(0) (wavenet.py:341-348)
             out = syn.generate(c.float().contiguous(), initial, test_inputs=test_inputs)
-            self.tower_y_hat = [out]
+            # wavenet.py:450-456: the published y_hat is the decoded waveform in [-1, 1]
+            if is_mulaw_quantize(hp.input_type):
+                out = t2.audio.inv_mulaw_quantize(out.contiguous())
+            elif is_mulaw(hp.input_type):
+                out = t2.audio.inv_mulaw(out.contiguous())
+            self.tower_y_hat = [out.reshape(B, -1)]
             self.tower_synth_upsampled_local_features = []
         return self
 
@@ -136,7 +180,7 @@ class WaveNet(object):
         self.learning_rate = eng.optimizer_step(grad_scale=1.0 / world)
         for other in self._engines.values():                        # buffers are shared; keep counters in step
             other.global_step = eng.global_step
-            other.m, other.v, other.ema = eng.m, eng.v, eng.ema
+            other.m, other.v, other.ema, other.grads = eng.m, eng.v, eng.ema, eng.grads
             other._packed_dirty = True
         self.gradients = eng.grads
         self.optimize = None                                        # already applied (nothing left to sess.run)
