@@ -81,3 +81,66 @@ def mulaw(x, mu=256):
 
 def inv_mulaw(y, mu=256):
     return t2.audio.inv_mulaw(_to_dev(y).reshape(-1)).cpu().numpy().reshape(np.shape(y))
+
+
+# ---- wav IO and silence trimming (reference datasets/audio.py:11-52): host-side plumbing around the kernels --------------------
+def load_wav(path, sr):
+    """librosa.core.load(path, sr)[0] without librosa: float32 mono in [-1, 1], polyphase-resampled to `sr` when needed."""
+    from scipy.io import wavfile
+    from scipy.signal import resample_poly
+    rate, data = wavfile.read(path)
+    if data.dtype.kind == "i":
+        data = data.astype(np.float32) / float(np.iinfo(data.dtype).max + 1)
+    elif data.dtype.kind == "u":
+        data = (data.astype(np.float32) - 128.0) / 128.0
+    data = data.astype(np.float32)
+    if data.ndim == 2:
+        data = data.mean(axis=1)
+    if rate != sr:
+        from math import gcd
+        g = gcd(int(rate), int(sr))
+        data = resample_poly(data, sr // g, rate // g).astype(np.float32)
+    return data
+
+
+def save_wav(wav, path, sr):
+    from scipy.io import wavfile
+    wav = wav * (32767 / max(0.01, np.max(np.abs(wav))))
+    wavfile.write(path, sr, wav.astype(np.int16))
+
+
+def save_wavenet_wav(wav, path, sr, inv_preemphasize=False, k=0.97):
+    save_wav(np.asarray(wav, dtype=np.float32), path, sr)
+
+
+def inv_preemphasis(wav, k, inv_preemphasize=True):
+    if not inv_preemphasize:
+        return wav
+    from scipy import signal
+    return signal.lfilter([1], [1, -k], wav)
+
+
+def start_and_end_indices(quantized, silence_threshold=2):
+    """first / last sample whose mu-law index is more than `silence_threshold` away from 127 (audio.py:33-44)"""
+    q = np.asarray(quantized).astype(np.int64)
+    loud = np.nonzero(np.abs(q - 127) > silence_threshold)[0]
+    assert loud.size > 0
+    start = int(loud[0])
+    tail = loud[loud >= 2]
+    end = int(tail[-1]) if tail.size else start
+    return start, end
+
+
+def trim_silence(wav, hparams):
+    """librosa.effects.trim(wav, top_db, frame_length, hop_length)[0] (audio.py:46-52): keep from the first to the last frame whose
+    RMS power is within trim_top_db of the loudest frame (centred frames, zero-padded edges... reflect-padded in librosa)."""
+    n, hop, top_db = hparams.trim_fft_size, hparams.trim_hop_size, hparams.trim_top_db
+    y = np.pad(np.asarray(wav, dtype=np.float64), n // 2, mode="reflect")
+    frames = 1 + (len(y) - n) // hop
+    idx = np.arange(n)[None, :] + hop * np.arange(frames)[:, None]
+    mse = np.mean(y[idx] ** 2, axis=1)
+    db = 10.0 * np.log10(np.maximum(1e-10, mse)) - 10.0 * np.log10(np.maximum(1e-10, mse.max()))
+    keep = np.nonzero(db > -top_db)[0]
+    if keep.size == 0:
+        return wav[:0]
+    return wav[int(keep[0]) * hop:min(len(wav), (int(keep[-1]) + 1) * hop)]

@@ -187,3 +187,14 @@ def hparams_debug_string():
     values = hparams.values()
     hp = ["  %s: %s" % (name, values[name]) for name in sorted(values) if name != "sentences"]
     return "Hyperparameters:\n" + "\n".join(hp)
+
+
+# default evaluation sentences of `synthesize.py --mode eval` when no --text_list is given (the reference ships its own list in
+# hparams.py; any plain-English lines work)
+sentences = [
+    "The quick brown fox jumps over the lazy dog.",
+    "Speech synthesis turns written text into an audible waveform.",
+    "A vocoder conditioned on mel spectrograms generates one sample at a time.",
+    "Attention aligns every decoder step with the characters it is reading.",
+    "Does the quality of the voice depend on the size of the training set?",
+]

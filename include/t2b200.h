@@ -99,6 +99,14 @@ int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, const void* 
 int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
                    const void* d_x, const float* d_c, float* d_grads, unsigned long long seed,
                    const unsigned long long* d_step, void* stream);
+/* Phased backward for data-parallel training (wavenet.py:561-593: tower gradients are averaged after backward). The weight
+ * gradients of the residual stack come from `n_groups` launches over layer groups whose parameters are CONTIGUOUS ranges of the
+ * flat gradient buffer, so the caller can all-reduce group g while group g+1 computes. phase -1: everything (== t2_wn_backward);
+ * 0: data-gradient chain, head, conditioning tails; 1 + g: weight gradients of layers [g*L/n, (g+1)*L/n); 100: join of the
+ * library's side stream (call after the last group, before reading gradients of the head / upsampling / first-conv tensors). */
+int t2_wn_backward_phased(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                          const void* d_x, const float* d_c, float* d_grads, unsigned long long seed,
+                          const unsigned long long* d_step, int phase, int n_groups, void* stream);
 /* measurement hook for bench.py's roofline leg: average device time (CUDA events on `stream`) of `reps` launches of
  * one per-layer GEMM over the state left in the workspace by the last forward/backward. which: 0 gate GEMM, 1 out
  * GEMM, 2 dz + gate-backward GEMM, 3 dx GEMM. Re-running 1 / 3 rewrites x[l+1] / dx[l] with identical values.

@@ -788,7 +788,10 @@ struct ActGemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // latency-bound pipelines: ~2.3k cycles TMA round trip / stages = cycles per k-block; the narrow swapped GEMMs of the
   // recurrences (BN = 32, 20 KB stages) take 6 stages
-  static constexpr int kStages = (BN >= 256) ? 3 : (BN <= 32 ? 6 : 4);
+#ifndef T2_STAGES_256
+#define T2_STAGES_256 3
+#endif
+  static constexpr int kStages = (BN >= 256) ? T2_STAGES_256 : (BN <= 32 ? 6 : 4);
   static constexpr int kStagingBytes = 4 * kEpiWarpBytes;      // 4 lane quarters x 2 tiles, never aliased with the stages
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -811,6 +814,10 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int m_tile = blockIdx.x;
+  // Thread-block cluster along M (launch attribute; 1 = no cluster): the weight tile of a pipeline stage is identical for every M
+  // tile, so each CTA of the cluster fetches 1/cs of its rows and MULTICASTS them to all peers (one L2 read feeds cs SMs).
+  const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = uint16_t((1u << cs) - 1u);
   long long* dbg = g.dbg ? g.dbg + ((size_t(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kDbgSlots : nullptr;
   if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[8] = globaltimer_ns(); dbg[11] = smid(); }
   const int b = m_tile / g.tiles_per_b;
@@ -831,7 +838,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     if (elect_one()) {
       for (int i = 0; i < Cfg::kStages; ++i) {
         mbar_init(&full_bar[i], 1);
-        mbar_init(&empty_bar[i], 1);
+        mbar_init(&empty_bar[i], cs);     // a stage is free once EVERY CTA of the cluster has consumed it (peers multicast into it)
       }
       for (int i = 0; i < NT; ++i) mbar_init(&tmem_full[i], 1);
       fence_barrier_init();
@@ -842,6 +849,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (cs > 1) cluster_sync_all();      // peers' barriers are initialised before any remote arrive / multicast write
   const uint32_t tmem_base = *tmem_slot;
   // everything above is CTA-local set-up and overlaps the previous kernel's tail under PDL; global memory from here on
   pdl_wait();
@@ -866,7 +874,13 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
               uint8_t* sb = sa + Cfg::kABytes;
               tma_load_4d(sa, &g.amap[sg.map], &full_bar[stage], sg.k0 + kb * kBK, t0 + sg.shift, b,
                           sg.layer0 + l);
-              tma_load_3d(sb, &g.bmap, &full_bar[stage], g.b_k0 + kb_global * kBK, n_tile * BN, g.b_layer);
+              if (cs == 1) {
+                tma_load_3d(sb, &g.bmap, &full_bar[stage], g.b_k0 + kb_global * kBK, n_tile * BN, g.b_layer);
+              } else {
+                const int rows = BN / int(cs);     // this CTA's slice of the weight tile (whole 8-row swizzle atoms: 1024-byte aligned)
+                tma_load_3d_mc(sb + crank * rows * (kBK * 2), &g.bmap, &full_bar[stage], g.b_k0 + kb_global * kBK,
+                               n_tile * BN + int(crank) * rows, g.b_layer, cmask);
+              }
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -894,7 +908,8 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
             umma_f16(tmem_d, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
                      (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cs == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], cmask);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         if (dbg && h == NT - 1) dbg[3] = clock64();
@@ -937,6 +952,162 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+  // no CTA may leave while a peer can still arrive on its barriers (the last multicast commits of the peers' MMA warps)
+  if (cs > 1) cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// act_gemm2 kernel: the same GEMM on CTA PAIRS (tcgen05 cta_group::2, cluster of 2 along M).
+//   One MMA covers 256 positions (128 per CTA) x BN columns; each CTA stages its own activation rows and only HALF of the weight
+//   tile (BN/2 rows), so a pipeline stage is 16 KB + BN/2*128 B instead of 16 KB + BN*128 B: fewer bytes per MMA cycle AND more
+//   stages in flight (measured on B200: the 1-CTA kernel is bound by bytes in flight per SM - 3 -> 2 stages costs +24..30 %).
+//   Roles: every CTA runs a TMA producer (its loads complete on the LEADER's full barrier) and the 16 epilogue warps (own TMEM
+//   rows); the leader's MMA thread issues for both SMs and commits, by multicast, to the empty / accumulator-ready barriers of both.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct ActGemm2Cfg {
+  static constexpr int kABytes = kBM * kBK * 2;          // 16 KB: this CTA's 128 positions
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;     // this CTA's half of the weight tile rows
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = 4 * kEpiWarpBytes;
+  static constexpr int kStages = (232448 - kStagingBytes - 1024 - 256) / kStageBytes > 6 ? 6 : (232448 - kStagingBytes - 1024 - 256) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+  static_assert(kStages >= 3 && kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <int EPI, int BN, int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kActGemmThreads, 1) act_gemm2_kernel(const __grid_constant__ GemmArgs g) {
+  using Cfg = ActGemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;      // [NT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + NT);
+  constexpr int kTmemCols = (NT * BN) < 32 ? 32 : NT * BN;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
+
+  const int warp = threadIdx.x >> 5;
+  const int m_tile = blockIdx.x;
+  const uint32_t crank = cluster_ctarank();      // 0 = leader of the pair
+  long long* dbg = g.dbg ? g.dbg + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * kDbgSlots : nullptr;
+  if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[8] = globaltimer_ns(); dbg[11] = smid(); }
+  const int b = m_tile / g.tiles_per_b;
+  const int t0 = (m_tile - b * g.tiles_per_b) * kBM;
+  int total_kb = 0;
+  for (int s = 0; s < g.nseg; ++s) total_kb += g.seg[s].nkb * g.seg[s].nlayers;
+
+  if (warp == 0 && elect_one()) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&g.amap[i]);
+    tma_prefetch_desc(&g.bmap);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < NT; ++i) mbar_init(&tmem_full[i], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair<kTmemCols>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();            // both CTAs' barriers are initialised and both TMEM halves allocated before any cross-CTA signal
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (dbg && threadIdx.x == 0) { dbg[1] = clock64(); dbg[9] = globaltimer_ns(); }
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int h = 0; h < NT; ++h) {
+        const int n_tile = blockIdx.y * NT + h;
+        int kb_global = 0;
+        for (int s = 0; s < g.nseg; ++s) {
+          const Seg sg = g.seg[s];
+          for (int l = 0; l < sg.nlayers; ++l) {
+            for (int kb = 0; kb < sg.nkb; ++kb, ++kb_global) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              // both CTAs' bytes for this stage complete on the leader's barrier: the leader arms it with the pair's total
+              if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              const uint32_t lead_bar = mapa_cluster(&full_bar[stage], 0);
+              uint8_t* sa = smem + stage * Cfg::kStageBytes;
+              uint8_t* sb = sa + Cfg::kABytes;
+              tma_load_4d_pair(sa, &g.amap[sg.map], lead_bar, sg.k0 + kb * kBK, t0 + sg.shift, b, sg.layer0 + l);
+              tma_load_3d_pair(sb, &g.bmap, lead_bar, g.b_k0 + kb_global * kBK, n_tile * BN + int(crank) * (BN / 2), g.b_layer);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int h = 0; h < NT; ++h) {
+        const uint32_t tmem_d = tmem_base + uint32_t(h * BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (dbg && kb == 0 && h == 0) dbg[2] = clock64();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16_pair(tmem_d, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage], 3);     // frees the stage in both CTAs
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (dbg && h == NT - 1) dbg[3] = clock64();
+        umma_commit_pair(&tmem_full[h], 3);           // accumulator half h is complete in both CTAs' TMEM
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    EpiCtx c;
+    c.lane = threadIdx.x & 31;
+    c.cg = (warp - 2) >> 2;
+    c.qbar = 1 + q;
+    c.b = b; c.T = g.T;
+    const int tw = t0 + q * 32;
+    c.t = tw + c.lane;
+    c.valid = c.t < g.T;
+    c.row0 = size_t(b) * g.T + tw;
+    c.nrows = g.T - tw < 0 ? 0 : (g.T - tw > 32 ? 32 : g.T - tw);
+    c.wbuf = staging + q * kEpiWarpBytes;
+    c.smem_all = staging;
+    c.m_tile = m_tile;
+    if constexpr (EpiHasPrefetch<EPI>::value && NT == 1) {
+      c.n_tile = blockIdx.y;
+      Epilogue<EPI, BN>::prefetch(g.epi, c);
+    }
+#pragma unroll 1
+    for (int h = 0; h < NT; ++h) {
+      c.n_tile = blockIdx.y * NT + h;
+      mbar_wait(&tmem_full[h], 0);
+      tc_fence_after();
+      c.trow = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(h * BN);
+      if (dbg && threadIdx.x == 64 && h == 0) dbg[4] = clock64();
+      Epilogue<EPI, BN>::run(g.epi, c);
+      if (dbg && threadIdx.x == 64 && h == NT - 1) dbg[5] = clock64();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) { dbg[6] = clock64(); dbg[10] = globaltimer_ns(); }
+  cluster_sync_all();            // the peer's epilogue has drained its TMEM half / nobody signals this CTA any more
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 

@@ -79,6 +79,7 @@ struct Layout {
   std::vector<PackJob> packjobs;
   std::vector<ColsumJob> colsums;
   std::vector<WgradTile> tiles_main, tiles_head;
+  std::vector<int> tile_start;   // [L + 1]: first entry of tiles_main that belongs to layer l (the table is layer-major)
   int dil(int l) const { return 1 << (l % (L / c.stacks)); }
 };
 
@@ -251,8 +252,10 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   };
   const int WN = 256;   // output columns per weight-gradient tile (wgrad_gemm_kernel: kWgBN)
   auto nmin = [&](int rem) { return rem < WN ? rem : WN; };
+  lo.tile_start.assign(lo.L + 1, 0);
   for (int l = 0; l < lo.L; ++l) {
     const int d = lo.dil(l);
+    lo.tile_start[l] = int(lo.tiles_main.size());
     for (int j = 0; j < 3; ++j)
       for (int m0 = 0; m0 < lo.R; m0 += 128)
         for (int n0 = 0; n0 < lo.G; n0 += WN)
@@ -282,6 +285,7 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
       }
   }
   lo.n_tiles_main = int(lo.tiles_main.size());
+  lo.tile_start[lo.L] = lo.n_tiles_main;
   lo.n_tiles_head = int(lo.tiles_head.size());
 
   // ---- column-sum (bias gradient) jobs ----
@@ -945,10 +949,42 @@ static SideStream* side_stream() {
 extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed,
                               void* d_workspace, const void* d_x, const float* d_c, float* d_grads,
                               unsigned long long seed, const unsigned long long* d_step, void* stream) {
+  return t2_wn_backward_phased(cfg, d_params, d_packed, d_workspace, d_x, d_c, d_grads, seed, d_step, -1, 1, stream);
+}
+
+// Phased form for data-parallel training: the weight gradients of the residual stack are produced by `n_groups` launches (layer
+// groups, top of the parameter buffer first) so that the caller can start the gradient all-reduce of a group's contiguous
+// parameter range while the next group's GEMM runs. phase -1: everything in one call (== t2_wn_backward); phase 0: the data-gradient
+// chain + head + conditioning tails (no stack weight gradients, side stream NOT yet joined); phase 1 + g: weight gradients of layer
+// group g (layers [g*L/n, (g+1)*L/n)); phase 100: join the side stream. wavenet.py:561-593 averages tower gradients after backward.
+extern "C" int t2_wn_backward_phased(const t2_wn_config_t* cfg, const float* d_params, const void* d_packed,
+                                     void* d_workspace, const void* d_x, const float* d_c, float* d_grads,
+                                     unsigned long long seed, const unsigned long long* d_step, int phase, int n_groups, void* stream) {
   Layout lo;
   int rc = build_layout(cfg, lo);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  T2_REQUIRE(n_groups >= 1 && n_groups <= lo.L && (phase == -1 || phase == 100 || (phase >= 0 && phase <= n_groups)), T2_ERR_INVALID_ARG,
+             "backward_phased: bad phase %d / n_groups %d", phase, n_groups);
+  if (phase >= 1 && phase <= n_groups) {
+    uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+    const int g = phase - 1;
+    const int l0 = int((long long)lo.L * g / n_groups), l1 = int((long long)lo.L * (g + 1) / n_groups);
+    const int t0 = lo.tile_start[l0], t1 = lo.tile_start[l1];
+    ActT maps[6] = {make_act(ws + lo.w_xd, lo.R, lo.T, lo.B, lo.L), make_act(ws + lo.w_dg, lo.G, lo.T, lo.B, lo.L),
+                    make_act(ws + lo.w_cup, lo.C > 0 ? lo.C : 8, lo.T, lo.B, 1),
+                    make_act(ws + lo.w_z, lo.Gh, lo.T, lo.B, lo.L), make_act(ws + lo.w_dxin, lo.R, lo.T, lo.B, lo.L),
+                    make_act(ws + lo.w_dskip, lo.S, lo.T, lo.B, 1)};
+    return launch_wgrad(maps, 6, reinterpret_cast<const WgradTile*>(ws + lo.w_tiles_main) + t0, t1 - t0, d_grads, lo.T, lo.B, st);
+  }
+  if (phase == 100) {
+    SideStream* side = side_stream();
+    if (side) {
+      T2_CHECK_CUDA(cudaEventRecord(side->join, side->s));
+      T2_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    }
+    return T2_OK;
+  }
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
   const long long BT = (long long)lo.B * lo.T;
@@ -1032,7 +1068,7 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
     T2_CHECK_CUDA(cudaStreamWaitEvent(side->s, side->fork2, 0));
   }
   // weight gradients of the stack: one batched launch
-  {
+  if (phase == -1) {
     ActT maps[6] = {make_act(ws + lo.w_xd, lo.R, lo.T, lo.B, lo.L), a_dg,
                     make_act(ws + lo.w_cup, lo.C > 0 ? lo.C : 8, lo.T, lo.B, 1),
                     make_act(ws + lo.w_z, lo.Gh, lo.T, lo.B, lo.L), a_dxin, a_dskip};
@@ -1078,7 +1114,7 @@ extern "C" int t2_wn_backward(const t2_wn_config_t* cfg, const float* d_params, 
       T2_CHECK_CUDA(cudaGetLastError());
     }
   }
-  if (side) {
+  if (side && phase == -1) {
     T2_CHECK_CUDA(cudaEventRecord(side->join, sb));
     T2_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
   }

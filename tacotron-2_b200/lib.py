@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt2b200.so")
+LIB_PATH = os.environ.get("T2_LIB") or os.path.join(_HERE, "libt2b200.so")     # T2_LIB: experiment builds (tools/)
 _lib = None
 
 

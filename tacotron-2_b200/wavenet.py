@@ -172,43 +172,105 @@ class WaveNet(object):
                                        ctypes.c_ulonglong(self._last_seed), L.ptr(self.step_dev), L.stream_ptr()))
         return self.loss_buf
 
-    def backward(self):
+    def backward(self, phase=-1, n_groups=1):
+        """phase -1: the whole backward. Phased form (data-parallel overlap, include/t2b200.h t2_wn_backward_phased): 0 = data-gradient
+        chain + head + conditioning tails, 1 + g = weight gradients of layer group g, 100 = join of the library's side stream."""
         if self.grads is None:
             self.grads = torch.zeros_like(self.params)
-        L.check(self.lib.t2_wn_backward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
-                                        L.ptr(self.workspace), L.ptr(self._last_x), L.ptr(self._last_c),
-                                        L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed),
-                                        L.ptr(self.step_dev), L.stream_ptr()))
+        L.check(self.lib.t2_wn_backward_phased(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
+                                               L.ptr(self.workspace), L.ptr(self._last_x), L.ptr(self._last_c),
+                                               L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed),
+                                               L.ptr(self.step_dev), int(phase), int(n_groups), L.stream_ptr()))
         return self.grads
 
+    def grad_buckets(self, n_groups):
+        """[(start, end)] element ranges of the flat gradient buffer: one per layer group (final after that group's weight-gradient
+        launch) followed by the two ranges outside the residual stack (input conv; head + upsampling net: final after the join)."""
+        off = {name: o for name, o, _ in self.tensors}
+        L_ = self.cfg.layers
+        first = lambda l: off["ResidualConv1DGLU_%d/residual_block_causal_conv/kernel" % l]
+        stack_end = off["final_convolution_1/kernel"]
+        bounds = [first(L_ * g // n_groups) for g in range(n_groups)] + [stack_end]
+        groups = [(bounds[g], bounds[g + 1]) for g in range(n_groups)]
+        rest = [(0, first(0)), (stack_end, self.n_params)]
+        return groups, [r for r in rest if r[1] > r[0]]
+
     # ---- training step (the call a user makes) -----------------------------------------------------------
-    def capture(self, x, c, targets, lengths):
-        """Capture pack + forward + backward into a CUDA graph over STATIC input tensors (x, c, targets, lengths are
-        the buffers later steps must copy into). Adam runs outside the graph (its bias correction changes per step)."""
+    def capture(self, x, c, targets, lengths, overlap_groups=1):
+        """Capture pack + forward + backward into CUDA graph(s) over STATIC input tensors (x, c, targets, lengths are
+        the buffers later steps must copy into). Adam runs outside the graph (its bias correction changes per step).
+        overlap_groups > 1 (data parallel): the step is captured as `overlap_groups` graphs cut after each layer group's
+        weight-gradient GEMM, so that train_step can start that group's NCCL all-reduce (eagerly, on the process group's stream)
+        while the next graph computes the next group (the monolithic all-reduce after the graph was fully exposed)."""
         self._static = (x, c, targets, lengths)
         if self.grads is None:
             self.grads = torch.zeros_like(self.params)
+        G = max(1, int(overlap_groups))
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture (sets kernel attributes, loads modules)
             self.pack()
             self.forward(x, c, targets, lengths)
             self.backward()
+            if G > 1:
+                self.backward(0, G)
+                for g in range(G):
+                    self.backward(1 + g, G)
+                self.backward(100, G)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
         n0 = self.lib.t2_launch_count()
-        with torch.cuda.graph(self._graph):
-            self.step_dev.add_(1)
-            self.pack()
-            self.forward(x, c, targets, lengths)
-            self.backward()
+        self._graphs = []
+        if G == 1:
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.step_dev.add_(1)
+                self.pack()
+                self.forward(x, c, targets, lengths)
+                self.backward()
+        else:
+            pool = None
+            for g in range(G):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, pool=pool):
+                    if g == 0:
+                        self.step_dev.add_(1)
+                        self.pack()
+                        self.forward(x, c, targets, lengths)
+                        self.backward(0, G)
+                    self.backward(1 + g, G)
+                    if g == G - 1:
+                        self.backward(100, G)
+                pool = gr.pool()
+                self._graphs.append(gr)
+            self._graph = self._graphs[0]
+            self._buckets = self.grad_buckets(G)
         self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
         return self._graph
 
     def train_step(self, x=None, c=None, targets=None, lengths=None, world_size=1, process_group=None):
         """One optimisation step: forward + loss + backward (+ gradient all-reduce) + clip + Adam + EMA.
         With a captured graph, non-None arguments are copied into the static buffers first."""
+        if self._graph is not None and getattr(self, "_graphs", None):
+            import torch.distributed as dist
+            for dst, src in zip(self._static, (x, c, targets, lengths)):
+                if src is not None and src is not dst:
+                    dst.copy_(src, non_blocking=True)
+            groups, rest = self._buckets
+            works = []
+            for gr, (a, b) in zip(self._graphs, groups):
+                gr.replay()
+                if world_size > 1:   # starts when this graph has finished, overlaps the next graph (the PG's own stream)
+                    works.append(dist.all_reduce(self.grads[a:b], op=dist.ReduceOp.SUM, group=process_group, async_op=True))
+            if world_size > 1:
+                for a, b in rest:
+                    works.append(dist.all_reduce(self.grads[a:b], op=dist.ReduceOp.SUM, group=process_group, async_op=True))
+                for w in works:
+                    w.wait()
+            n0 = self.lib.t2_launch_count()
+            self.optimizer_step(grad_scale=1.0 / world_size)
+            self._opt_launches = self.lib.t2_launch_count() - n0
+            return self.loss_buf
         if self._graph is not None:
             for dst, src in zip(self._static, (x, c, targets, lengths)):
                 if src is not None and src is not dst:

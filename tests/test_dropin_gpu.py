@@ -53,18 +53,20 @@ def test_wavenet_create_model_train_eval_synthesize():
         l_a = float(m2.add_loss())
         m2.add_optimizer()
         assert l_a == l_a and len(m2._engines) <= 3
-    # padding to the bucket does not change the loss: T = 496 (padded to 512) vs the exact-size engine of the product API
+    # padding to the bucket does not change the loss: T = 496 (padded to 512 inside the drop-in) vs the exact-size engine of the
+    # product API, same variables, dropout off
     from t2_import import t2
-    eng = t2.wavenet.WaveNet(hp, B, 496)
-    eng.params.copy_(m2.variables)
-    eng._packed_dirty = True
-    eng.cfg.dropout = 0.0
-    for e in m2._engines.values():
-        e.cfg.dropout = 0.0
+    hp3 = hp.copy()
+    hp3.set_hparam("wavenet_dropout", 0.0)
+    eng = t2.wavenet.WaveNet(hp3, B, 496)
+    eng.init_variables(seed=3)
+    m3 = create_model("WaveNet", hp3)
+    m3.load_variables(eng.export_params())
     len496 = torch.tensor([496, 400]).int().cuda()
     eng.forward(idx[:, :496].int().contiguous(), c[:, :, :31].contiguous(), idx[:, :496].int().contiguous(), len496)
-    m2.initialize(idx[:, :496].unsqueeze(-1), c[:, :, :31], None, len496, x=x[:, :, :496])
-    assert abs(float(m2.add_loss()) - eng.loss_value()) < 2e-5
+    m3.initialize(idx[:, :496].unsqueeze(-1), c[:, :, :31], None, len496, x=x[:, :, :496])
+    torch.cuda.synchronize()
+    assert abs(float(m3.add_loss()) - eng.loss_value()) < 2e-5
 
 
 def test_tacotron_create_model_train_gta_synthesize():

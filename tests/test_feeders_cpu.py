@@ -1,0 +1,112 @@
+"""Feeders and on-disk formats on synthetic data, no GPU: the batch contract of tacotron/feeder.py:198-256 and
+wavenet_vocoder/feeder.py:295-428 (padding values, token targets, hop-aligned crops, [0, 1] conditioning, deterministic split),
+plus the padding helpers against the vectors produced by executing the reference's own feeder code."""
+import os
+
+import numpy as np
+import pytest
+
+from hparams import hparams
+
+R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_exec.npz"))
+
+
+def _make_dataset(root, n=48, hop=275, seed=0):
+    rng = np.random.default_rng(seed)
+    for d in ("audio", "mels", "linear"):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    rows = []
+    for i in range(1, n + 1):
+        frames = int(rng.integers(20, 90))
+        np.save(os.path.join(root, "audio", "audio-%d.npy" % i), rng.integers(0, 256, frames * hop).astype(np.int16))
+        np.save(os.path.join(root, "mels", "mel-%d.npy" % i), rng.uniform(-4.5, 4.5, (frames, 80)).astype(np.float32))
+        text = "".join(rng.choice(list("abcdefghij klmnop, qrstu!"), int(rng.integers(8, 40))))
+        rows.append("audio-%d.npy|mel-%d.npy|linear-%d.npy|%d|%d|%s" % (i, i, i, frames * hop, frames, text))
+    path = os.path.join(root, "train.txt")
+    open(path, "w", encoding="utf-8").write("\n".join(rows) + "\n")
+    return path
+
+
+def test_padding_helpers_match_reference_executed_vectors():
+    from tacotron import feeder as tf_
+    from wavenet_vocoder import feeder as wf
+    assert np.array_equal(tf_.pad_input(np.arange(1, 8, dtype=np.int32), 10, 0), R["feeder_pad_input"])
+    assert np.array_equal(tf_.pad_target(R["feeder_target_in"], 9, float(R["taco_target_pad"])), R["feeder_pad_target"])
+    assert np.array_equal(tf_.pad_token_target(np.zeros(7, dtype=np.float32), 9, 1.0), R["feeder_pad_token_target"])
+    assert [tf_._round_up(n, 3) for n in range(8)] == R["feeder_round_up"].tolist()
+    assert [tf_._round_down(n, 3) for n in range(8)] == R["feeder_round_down"].tolist()
+    got = [[wf._ensure_divisible(n, 275, True), wf._ensure_divisible(n, 275, False)] for n in (274, 275, 276, 8000, 12000)]
+    assert got == R["wn_ensure_divisible"].tolist()
+
+
+def test_text_front_end():
+    from tacotron.utils.symbols import symbols
+    from tacotron.utils.text import sequence_to_text, text_to_sequence
+    assert len(symbols) == 66 and symbols[0] == "_" and symbols[1] == "~"
+    seq = text_to_sequence("Hello,  World_~ 9!", ["english_cleaners"])
+    assert seq[-1] == 1 and 0 not in seq and sequence_to_text(seq) == "hello, world !~"      # digits / pad / eos symbols dropped, EOS appended
+
+
+def test_tacotron_feeder_batches(tmp_path):
+    from tacotron.feeder import Feeder
+    hp = hparams.copy()
+    hp.parse("tacotron_batch_size=4,tacotron_test_size=8,tacotron_test_batches=None")
+    path = _make_dataset(str(tmp_path))
+    f = Feeder(path, hp)
+    assert len(f._test_meta) == 8 and len(f._train_meta) == 40 and f.test_steps == 2
+    f2 = Feeder(path, hp)
+    assert [m[0] for m in f2._test_meta] == [m[0] for m in f._test_meta]                      # deterministic split (random_state)
+    group = f.train_group()
+    assert len(group) == 32
+    for b in group[:6] + f.test_batches():
+        B, T_in = b["inputs"].shape
+        assert B == 4 and b["mel_targets"].shape[0] == 4 and b["mel_targets"].shape[2] == 80
+        To = b["mel_targets"].shape[1]
+        assert To == b["targets_lengths"].max() and b["token_targets"].shape[1] == To          # (len - 1 zeros) + 1, rounded to r (feeder.py:240-243)
+        for i in range(B):
+            n, L = int(b["targets_lengths"][i]), int(b["input_lengths"][i])
+            assert (b["inputs"][i, L:] == 0).all() and b["inputs"][i, L - 1] == 1               # zero padding after the EOS id
+            assert (b["mel_targets"][i, n:] == -hp.max_abs_value).all()                         # symmetric mels: pad with -max_abs_value
+            assert (b["token_targets"][i, :n - 1] == 0).all() and (b["token_targets"][i, n - 1:] == 1).all()
+    # batches of a group hold utterances of similar length (sorted in groups of 32 batches, then shuffled)
+    spans = [int(b["targets_lengths"].max() - b["targets_lengths"].min()) for b in group]
+    assert np.mean(spans) < 12
+    r0, r1 = Feeder(path, hp, rank=0, world_size=2), Feeder(path, hp, rank=1, world_size=2)
+    assert len(r0.train_group()) == 16 and len(r1.train_group()) == 16
+
+
+def test_tacotron_feeder_thread(tmp_path):
+    from tacotron.feeder import Feeder
+    hp = hparams.copy()
+    hp.parse("tacotron_batch_size=4,tacotron_test_size=8,tacotron_test_batches=None")
+    f = Feeder(_make_dataset(str(tmp_path)), hp).start()
+    try:
+        b = [f.next_batch(timeout=60) for _ in range(3)]
+        assert all(x["inputs"].dtype.is_floating_point is False and x["mel_targets"].shape[0] == 4 for x in b)
+    finally:
+        f.stop()
+
+
+def test_wavenet_feeder_batches(tmp_path):
+    from wavenet_vocoder.feeder import Feeder
+    hp = hparams.copy()
+    hp.parse("input_type=mulaw-quantize,quantize_channels=256,out_channels=256,wavenet_batch_size=4,wavenet_test_size=8,"
+             "wavenet_test_batches=None,max_time_steps=8000,train_with_GTA=False")
+    root = str(tmp_path)
+    path = _make_dataset(root)
+    # the preprocessor's train.txt names files relative to audio/ and mels/: the WaveNet feeder joins base_dir + row entries, which is
+    # what the GTA map.txt (full paths) and wavenet_preprocess maps provide; mimic a map with relative paths
+    rows = [l.strip().split("|") for l in open(path, encoding="utf-8")]
+    mp = os.path.join(root, "map.txt")
+    open(mp, "w").write("\n".join("audio/%s|mels/%s|mels/%s|<no_g>|%s" % (r[0], r[1], r[1], r[5]) for r in rows) + "\n")
+    f = Feeder(mp, root, hp)
+    assert f.test_steps == 2 and len(f._train_meta) == 40
+    hop = 275
+    limit = 8000 - 8000 % hop
+    for b in f.train_group()[:8] + f.test_batches():
+        x, c, L = b["inputs"], b["local_condition_features"], b["input_lengths"]
+        assert x.dtype == np.int32 and x.shape[0] == 4 and b["targets"].shape == x.shape + (1,)
+        assert x.shape[1] == L.max() and (L % hop == 0).all() and L.max() <= limit            # hop-aligned crops below max_time_steps
+        assert c.shape == (4, 80, x.shape[1] // hop) and c.min() >= 0.0 and c.max() <= 1.0      # clip +-4 -> [0, 1] (feeder.py:323-335)
+        for i in range(4):
+            assert (x[i, L[i]:] == 0).all() and (c[i, :, L[i] // hop:] == 0).all()             # audio zero-padded, mels padded with the range minimum -> 0
