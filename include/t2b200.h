@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define T2B200_ABI_VERSION 1
+#define T2B200_ABI_VERSION 2
 
 #define T2_OK 0
 #define T2_ERR_INVALID_ARG (-1)
@@ -56,7 +56,7 @@ int t2_dbg_wgrad(const void* d_a, int Ca, const void* d_bm, int Cb, int B, int T
 typedef struct {
   int layers, stacks, residual_channels, gate_channels, skip_out_channels, kernel_size;
   int cin_channels;          /* 80 (num_mels) or 0 = no local conditioning */
-  int out_channels;          /* 256 (mu-law softmax) or 3*nr_mix (MoL) */
+  int out_channels;          /* 256 (mu-law softmax), 3*nr_mix (MoL) or 2 (single Gaussian: mean, log-scale) */
   int quantize_channels;     /* 256 or 65536 */
   int input_type;            /* 0 'raw', 1 'mulaw', 2 'mulaw-quantize' */
   int legacy, residual_legacy;
@@ -68,6 +68,11 @@ typedef struct {
   float log_scale_min;
   int B, T, Tc;              /* per-GPU batch, samples per item, conditioning frames per item */
   int c_pre_upsampled;       /* 1: conditioning is given at sample rate [B, T, cin] fp32 (skip upsample net) */
+  float log_scale_min_gauss; /* single-Gaussian head (out_channels == 2): clamp of the predicted log-scale (hparams.py:196) */
+  int cdf_loss;              /* Gaussian head: 1 = log(CDF+ - CDF-) loss, 0 = log-density (gaussian.py:18-33) */
+  int split_bf16;            /* 1 = "fp32-class" forward: activations and weights travel as bf16 hi + lo pairs (3 tensor-core products per
+                              * contraction, fp32 accumulate; ~2^-17 relative operand error instead of 2^-9). Forward / loss only, dropout 0:
+                              * the parity mode that shows the bf16-mode deviation from the reference's fp32 graph is storage rounding. */
 } t2_wn_config_t;
 
 typedef struct {
@@ -153,6 +158,9 @@ typedef struct {
   float zoneout_rate;        /* tacotron_zoneout_rate */
   float reg_weight;          /* tacotron_reg_weight */
   float max_abs_value, lower_bound_decay;
+  int split_bf16;            /* 1 = "fp32-class" convolution stacks: the embedding, the encoder conv blocks + the BiLSTM input projection and
+                              * the postnet conv blocks + projection run on bf16 hi + lo operand pairs with fp32 pre-batch-norm activations
+                              * (forward / losses only). The recurrences (LSTMs, attention) keep bf16 operands / fp32 state. */
 } t2_taco_config_t;
 
 int t2_taco_sizes(const t2_taco_config_t* cfg, long long* n_params, long long* packed_bytes, long long* workspace_bytes,

@@ -374,9 +374,46 @@ def masked_mol_loss(y_hat, y, lengths, hp):
     return (losses * mask).sum() / mask.sum()
 
 
+def gaussian_maximum_likelihood_estimation_loss(y_hat, y, log_scale_min_gauss, num_classes, use_cdf=True, reduce=True):
+    """gaussian.py:5-37. y_hat [B, 2, T] (mean, log_scale), y [B, T, 1] -> [B, T, 1] (reduce=False)."""
+    y_hat = y_hat.transpose(1, 2)
+    mean = y_hat[:, :, 0]
+    log_scale = torch.clamp(y_hat[:, :, 1], min=log_scale_min_gauss)
+    y = y.squeeze(-1)
+    if use_cdf:
+        scale = torch.exp(log_scale)
+        cdf_plus = torch.special.ndtr((y + 1. / (num_classes - 1) - mean) / scale)
+        cdf_min = torch.special.ndtr((y - 1. / (num_classes - 1) - mean) / scale)
+        log_prob = torch.log(torch.clamp(cdf_plus - cdf_min, min=1e-12))
+    else:
+        log_prob = -0.5 * (np.log(2. * np.pi) + 2. * log_scale + (y - mean) ** 2 * torch.exp(-2. * log_scale))
+    if reduce:
+        return -log_prob.sum()
+    return -log_prob.unsqueeze(-1)
+
+
+def masked_gaussian_loss(y_hat, y, lengths, hp):
+    """wavenet.py:491-492 + modules.py:819-836. y_hat [B, 2, T], y [B, T] float."""
+    T = y_hat.shape[-1]
+    mask = sequence_mask(lengths, T)[:, 1:].unsqueeze(-1)
+    losses = gaussian_maximum_likelihood_estimation_loss(y_hat[:, :, :-1], y[:, 1:].unsqueeze(-1), hp.log_scale_min_gauss,
+                                                         hp.quantize_channels, use_cdf=hp.cdf_loss, reduce=False)
+    return (losses * mask).sum() / mask.sum()
+
+
+def sample_from_gaussian(y, log_scale_min_gauss, normal):
+    """gaussian.py:39-52 with the standard-normal draw injected. y [B, 2, T] -> [B, T]."""
+    y = y.transpose(1, 2)
+    mean = y[:, :, 0]
+    scale = torch.exp(torch.clamp(y[:, :, 1], min=log_scale_min_gauss))
+    return torch.clamp(mean + scale * normal, -1., 1.)
+
+
 def loss_fn(y_hat, y, lengths, hp):
     if is_mulaw_quantize(hp.input_type):
         return masked_cross_entropy(y_hat, y, lengths)
+    if hp.out_channels == 2:
+        return masked_gaussian_loss(y_hat, y, lengths, hp)
     return masked_mol_loss(y_hat, y, lengths, hp)
 
 

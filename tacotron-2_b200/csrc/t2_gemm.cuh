@@ -55,6 +55,28 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// Split-bf16 ("fp32-class") mode: an fp32 value travels as hi = bf16(v) and lo = bf16(v - hi) in channels [0,C) and [C,2C) of a row
+// of pitch 2C; a GEMM then contracts [hi | lo | hi] against [W_hi | W_hi | W_lo] (the lo x lo term, 2^-18 relative, is dropped).
+// These epilogue paths favour clarity over speed (one thread = one row, direct global loads / stores): they exist to show that
+// the bf16-mode deviation from the fp32 reference graph is storage rounding and nothing else (tests/test_precision_modes_gpu.py).
+__device__ __forceinline__ void store_split32(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float (&v)[32]) {
+  float hi[32], lo[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    hi[j] = __bfloat162float(__float2bfloat16(v[j]));
+    lo[j] = v[j] - hi[j];
+  }
+  store_bf16x32(dst_hi, hi);
+  store_bf16x32(dst_lo, lo);
+}
+__device__ __forceinline__ void load_split32(const __nv_bfloat16* src_hi, const __nv_bfloat16* src_lo, float (&v)[32]) {
+  float lo[32];
+  load_bf16x32(src_hi, v);
+  load_bf16x32(src_lo, lo);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] += lo[j];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Epilogue staging: a thread owns one accumulator ROW (TMEM lane), but global memory wants a warp to touch one
 // row's contiguous bytes. Every epilogue therefore moves 32-row x 128-column bf16 tiles through a per-warp
@@ -216,6 +238,21 @@ struct Epilogue<EPI_GATE, 256> {
     uint8_t* t0 = c.wbuf;
     uint8_t* t1 = c.wbuf + kTileBytes;
     const size_t off = c.row0 * Gh + cb;
+    if (e.i[11]) {   // split-bf16 mode: accurate tanh / sigmoid, z written as hi | lo (row pitch 2 Gh); forward only (no stashes)
+      const int cq = c.cg;
+      float a[32], g[32], ba[32], bb[32];
+      load_f32x32(bias + cb + cq * 32, ba);
+      load_f32x32(bias + Gh + cb + cq * 32, bb);
+      tmem_ld32f(c.trow + cq * 32, a);
+      tmem_ld32f(c.trow + 128 + cq * 32, g);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = tanhf_(a[j] + ba[j]) * sigmoidf_(g[j] + bb[j]);
+      if (c.valid) {
+        __nv_bfloat16* zr = z_o + (size_t(c.b) * c.T + c.t) * (2 * Gh) + cb + cq * 32;
+        store_split32(zr, zr + Gh, a);
+      }
+      return;
+    }
     {
       const int cq = c.cg;
       float a[32], g[32], ba[32], bb[32];
@@ -250,6 +287,7 @@ template <int BN>
 struct Epilogue<EPI_RES, BN> {
   // the x tiles (residual input) do not depend on this kernel's MMAs: load them while the mainloop runs
   static __device__ __forceinline__ void prefetch(const EpiArgs& e, const EpiCtx& c) {
+    if (e.i[11]) return;   // split-bf16 mode reads x directly in run()
     const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
 #pragma unroll
     for (int gq = 0; gq < BN / 128; ++gq)
@@ -261,6 +299,24 @@ struct Epilogue<EPI_RES, BN> {
     __nv_bfloat16* xd_out = static_cast<__nv_bfloat16*>(e.ptr[2]);
     const float* bias = static_cast<const float*>(e.ptr[3]);
     const float rs = e.f[0], p = e.f[1];
+    if (e.i[11]) {   // split-bf16 mode: x_in / x_out rows are [hi(R) | lo(R)]
+      const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
+      const size_t r2 = (size_t(c.b) * c.T + c.t) * (2 * R);
+#pragma unroll 1
+      for (int gq = 0; gq < BN / 128; ++gq) {
+        const int j0 = gq * 128 + c.cg * 32;
+        float acc[32], x[32], bv[32];
+        load_f32x32(bias + j0, bv);
+        tmem_ld32f(c.trow + j0, acc);
+        if (c.valid) {
+          load_split32(x_in + r2 + j0, x_in + r2 + R + j0, x);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + bv[j] + x[j]) * rs;
+          store_split32(x_out + r2 + j0, x_out + r2 + R + j0, acc);
+        }
+      }
+      return;
+    }
     const float keep_inv = 1.f / (1.f - p);
     const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
     const uint32_t hs = hash_seed(seed, uint32_t(e.i[1]));
@@ -309,6 +365,34 @@ struct Epilogue<EPI_BIAS_ACT, BN> {
     const float keep_inv = 1.f / (1.f - pdrop);
     const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
     const uint32_t hs = hash_seed(seed, uint32_t(e.i[3]));
+    if (e.i[11]) {   // split-bf16 mode: bf16 output rows are [hi(ldo) | lo(ldo)] (pitch 2 ldo); fp32 output unchanged; no dropout
+#pragma unroll 1
+      for (int gq = 0; gq < BN / 128; ++gq) {
+        const int c0 = c.n_tile * BN + gq * 128 + c.cg * 32;
+        if (c0 >= nvalid) continue;
+        float acc[32];
+        tmem_ld32f(c.trow + gq * 128 + c.cg * 32, acc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = acc[j];
+          if (bias && c0 + j < nvalid) v += __ldg(bias + c0 + j);
+          if (act == 1) v = fmaxf(v, 0.f);
+          else if (act == 2) v = tanhf_(v);
+          acc[j] = c0 + j < nvalid ? v : 0.f;
+        }
+        if (!c.valid) continue;
+        if (of) for (int j = 0; j < 32 && c0 + j < nvalid; ++j) of[row + c0 + j] = acc[j];
+        if (ob) {
+          __nv_bfloat16* r2 = ob + (size_t(c.b) * c.T + c.t) * (2 * size_t(ldo)) + c0;
+          if (c0 + 32 <= ldo) store_split32(r2, r2 + ldo, acc);
+          else for (int j = 0; j < 32 && c0 + j < ldo; ++j) {
+            const __nv_bfloat16 h = __float2bfloat16(acc[j]);
+            r2[j] = h; r2[ldo + j] = __float2bfloat16(acc[j] - __bfloat162float(h));
+          }
+        }
+      }
+      return;
+    }
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
       const int g0 = c.n_tile * BN + gq * 128;
@@ -428,6 +512,8 @@ struct Epilogue<EPI_CE, 256> {
 // ptr: 0 targets f32 [B,T], 1 lengths, 2 bias fp32 [3nm], 3 loss_sum, 4 mask_sum, 5 dyhat bf16 [pos, ld]
 //      (nullable, un-normalised; 32 columns written), 6 yhat fp32 [pos,32] (nullable)
 // f0 log_scale_min, f1 1/(num_classes-1), f2 log((num_classes-1)/2);  i0 = nr_mix (<= 10), i1 = ld
+// i2 != 0: single-Gaussian head instead (wavenet_vocoder/models/gaussian.py:5-37): columns [mean | log_scale], f3 = log_scale_min_gauss,
+// i2 = 1 log-density loss, i2 = 2 log(CDF(y + 1/(nc-1)) - CDF(y - 1/(nc-1))) loss
 template <>
 struct Epilogue<EPI_MOL, 32> {
   static __device__ __forceinline__ float softplus(float x) {
@@ -447,6 +533,50 @@ struct Epilogue<EPI_MOL, 32> {
     const float y = w ? __ldg(tgt + size_t(c.b) * c.T + c.t + 1) : 0.f;
     float v[32];
     tmem_ld32f(c.trow, v);
+    if (e.i[2] != 0) {   // ---- single Gaussian ----
+      const float lsg = e.f[3];
+      const float m = v[0] + __ldg(bias), sraw = v[1] + __ldg(bias + 1);
+      if (yo && c.valid) {
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0.f;
+        o[0] = m; o[1] = sraw;
+        store_f32x32(yo + row, o);
+      }
+      const float ls = fmaxf(sraw, lsg);
+      float nll, dm, dls;
+      if (e.i[2] == 1) {
+        const float iv = __expf(-2.f * ls), d = y - m;
+        nll = 0.5f * (1.8378770664093453f + 2.f * ls + d * d * iv);
+        dm = -d * iv;
+        dls = 1.f - d * d * iv;
+      } else {
+        const float inv = __expf(-ls);
+        const float zp = (y + hw - m) * inv, zn = (y - hw - m) * inv;
+        const float P = normcdff(zp) - normcdff(zn);
+        nll = -__logf(fmaxf(P, 1e-12f));
+        if (P > 1e-12f) {
+          const float pp = 0.3989422804014327f * __expf(-0.5f * zp * zp), pn = 0.3989422804014327f * __expf(-0.5f * zn * zn);
+          dm = (pp - pn) * inv / P;
+          dls = (pp * zp - pn * zn) / P;
+        } else { dm = 0.f; dls = 0.f; }
+      }
+      if (sraw < lsg) dls = 0.f;
+      if (dy && c.valid) {
+        float g[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = 0.f;
+        if (w) { g[0] = dm; g[1] = dls; }
+        store_bf16x32(dy + (size_t(c.b) * c.T + c.t) * size_t(e.i[1]), g);
+      }
+      float loss = warp_sum(w ? nll : 0.f);
+      float cnt = warp_sum(w ? 1.f : 0.f);
+      if (c.lane == 0) {
+        atomicAdd(static_cast<float*>(e.ptr[3]), loss);
+        atomicAdd(static_cast<float*>(e.ptr[4]), cnt);
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = (j < 3 * nm) ? v[j] + __ldg(bias + j) : 0.f;
     if (yo && c.valid) store_f32x32(yo + row, v);

@@ -69,7 +69,7 @@ struct TL {  // layout
   int n_packjobs, n_reg;
 };
 
-struct PJ { long long src_off; int K, N; long long dst_off; int dst_ld, transpose, col0; float scale; int perm_h; };
+struct PJ { long long src_off; int K, N; long long dst_off; int dst_ld, transpose, col0; float scale; int perm_h; int part; };   // part 2: bf16(w - bf16(w))
 
 long long addp(TL& lo, const std::string& name, std::initializer_list<int> shape, bool trainable = true) {
   PT p; p.name = name; p.off = lo.n_params; p.ndim = int(shape.size());
@@ -147,13 +147,23 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   auto takeb = [&](long long bytes) { long long r = o; o = al256(o + bytes); return r; };
   auto pj = [&](long long src, int K, int N, long long dst_bytes, int ld, int tr, int col0, int perm = 0) {
     PJ j; j.src_off = src; j.K = K; j.N = N; j.dst_off = dst_bytes / 2; j.dst_ld = ld; j.transpose = tr; j.col0 = col0; j.scale = 1.f;
-    j.perm_h = perm; jobs.push_back(j);
+    j.perm_h = perm; j.part = 0; jobs.push_back(j);
+  };
+  const bool split = cfg->split_bf16 != 0;
+  // split-bf16 operand: the K slot [col, col + slot) of the plain layout becomes [W_hi | W_hi | W_lo]
+  auto pj3 = [&](long long src, int K, int N, long long dst_bytes, int ld, int col, int slot) {
+    pj(src, K, N, dst_bytes, ld, 1, col);
+    pj(src, K, N, dst_bytes, ld, 1, col + slot);
+    pj(src, K, N, dst_bytes, ld, 1, col + 2 * slot);
+    jobs.back().part = 2;
   };
   auto conv_pack = [&](ConvL& L) {
     L.cinp = (L.cin + 63) / 64 * 64;
-    L.k_w = takeb(2LL * L.cout * L.k * L.cinp);
+    L.k_w = takeb(2LL * L.cout * L.k * L.cinp * (split ? 3 : 1));
     L.k_wT = takeb(2LL * L.cinp * L.k * L.cout);
     for (int j = 0; j < L.k; ++j) {
+      if (split) pj3(L.p_k + (long long)j * L.cin * L.cout, L.cin, L.cout, L.k_w, 3 * L.k * L.cinp, 3 * j * L.cinp, L.cinp);
+      else
       pj(L.p_k + (long long)j * L.cin * L.cout, L.cin, L.cout, L.k_w, L.k * L.cinp, 1, j * L.cinp);      // fwd: [cout][tap j | cin]
       pj(L.p_k + (long long)j * L.cin * L.cout, L.cin, L.cout, L.k_wT, L.k * L.cout, 0, j * L.cout);     // dgrad: [cin][tap j | cout]
     }
@@ -161,8 +171,9 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   for (auto& L : lo.enc) conv_pack(L);
   for (auto& L : lo.post) conv_pack(L);
   for (int d = 0; d < 2; ++d) {
-    lo.k_encWx[d] = takeb(2LL * 4 * lo.H * lo.C);            // [4H][C]  input projection (natural gate order)
-    pj(lo.p_elk[d], lo.C, 4 * lo.H, lo.k_encWx[d], lo.C, 1, 0);
+    lo.k_encWx[d] = takeb(2LL * 4 * lo.H * lo.C * (split ? 3 : 1));            // [4H][C]  input projection (natural gate order)
+    if (split) pj3(lo.p_elk[d], lo.C, 4 * lo.H, lo.k_encWx[d], 3 * lo.C, 0, lo.C);
+    else pj(lo.p_elk[d], lo.C, 4 * lo.H, lo.k_encWx[d], lo.C, 1, 0);
     lo.k_encWr[d] = takeb(2LL * 4 * lo.H * lo.H);            // [4H perm][H] recurrent, rows permuted for EPI_LSTM
     pj(lo.p_elk[d] + (long long)lo.C * 4 * lo.H, lo.H, 4 * lo.H, lo.k_encWr[d], lo.H, 1, 0, lo.H);
     lo.k_encWrT[d] = takeb(2LL * lo.H * 4 * lo.H);           // [H][4H] for the backward step
@@ -187,11 +198,13 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   lo.k_proj = takeb(2LL * 128 * PIK);                         // rows 0..M-1 frame projection, row M stop projection
   pj(lo.p_fk, PIK, lo.M, lo.k_proj, PIK, 1, 0);
   { PJ j; j.src_off = lo.p_sk; j.K = PIK; j.N = 1; j.dst_off = lo.k_proj / 2 + (long long)lo.M * PIK; j.dst_ld = PIK; j.transpose = 1; j.col0 = 0;
-    j.scale = 1.f; j.perm_h = 0; jobs.push_back(j); }
+    j.scale = 1.f; j.perm_h = 0; j.part = 0; jobs.push_back(j); }
   lo.k_projT = takeb(2LL * PIK * 128);                        // [PIK][128]: cols 0..M-1 Wf, col M Ws
   pj(lo.p_fk, PIK, lo.M, lo.k_projT, 128, 0, 0);
   pj(lo.p_sk, PIK, 1, lo.k_projT, 128, 0, lo.M);
-  lo.k_pp = takeb(2LL * lo.M * lo.PC); pj(lo.p_ppk, lo.PC, lo.M, lo.k_pp, lo.PC, 1, 0);
+  lo.k_pp = takeb(2LL * 128 * lo.PC * (split ? 3 : 1));
+  if (split) pj3(lo.p_ppk, lo.PC, lo.M, lo.k_pp, 3 * lo.PC, 0, lo.PC);
+  else pj(lo.p_ppk, lo.PC, lo.M, lo.k_pp, lo.PC, 1, 0);
   lo.k_ppT = takeb(2LL * lo.PC * 128); pj(lo.p_ppk, lo.PC, lo.M, lo.k_ppT, 128, 0, 0);
   lo.k_qT = takeb(2LL * lo.A * lo.D); pj(lo.p_qry, lo.D, lo.A, lo.k_qT, lo.D, 1, 0);   // [A][D] for the attention kernel
   lo.packed_bytes = o;
@@ -200,9 +213,10 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   // ---- workspace ----
   o = 0;
   const long long B = lo.B, Ti = lo.Ti, To = lo.To;
-  lo.w_emb = takeb(B * Ti * lo.E * 2);
+  const long long xm = split ? 2 : 1;       // split-bf16: stored conv-stack activations are [hi | lo]; pre-batch-norm activations fp32
+  lo.w_emb = takeb(B * Ti * lo.E * 2 * xm);
   auto conv_ws = [&](ConvL& L, long long T) {
-    L.w_y = takeb(B * T * L.cout * 2); L.w_x = takeb(B * T * L.cout * 2); L.w_stats = takeb(8LL * L.cout * 4);
+    L.w_y = takeb(B * T * L.cout * (split ? 4 : 2)); L.w_x = takeb(B * T * L.cout * 2 * xm); L.w_stats = takeb(8LL * L.cout * 4);
   };
   for (auto& L : lo.enc) conv_ws(L, Ti);
   for (int d = 0; d < 2; ++d) {
@@ -228,7 +242,7 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   lo.w_cum = takeb(B * Ti * 4);
   lo.w_alpha = takeb(To * B * Ti * 4);
   lo.w_projo = takeb(To * B * 128 * 4);
-  lo.w_decbm = takeb(B * To * lo.M * 2); lo.w_decf = takeb(B * To * lo.M * 4); lo.w_stop = takeb(B * To * 4);
+  lo.w_decbm = takeb(split ? B * To * 256 * 2 : B * To * lo.M * 2);     /* split: [hi(M) padded to 128 | lo(M) padded to 128] */ lo.w_decf = takeb(B * To * lo.M * 4); lo.w_stop = takeb(B * To * 4);
   for (auto& L : lo.post) conv_ws(L, To);
   lo.w_resid = takeb(B * To * 128 * 4); lo.w_mel = takeb(B * To * lo.M * 4);
   lo.w_scal = takeb(64 * 4);
@@ -294,7 +308,9 @@ __global__ void tpack_kernel(const float* __restrict__ params, bf16* __restrict_
         if (vec_src && n + 1 < j.N) { const float2 v = *reinterpret_cast<const float2*>(src); a = v.x; b = v.y; }
         else { if (n < j.N) a = src[0]; if (n + 1 < j.N) b = src[1]; }
       }
-      tile[r][2 * tx] = a * j.scale; tile[r][2 * tx + 1] = b * j.scale;
+      a *= j.scale; b *= j.scale;
+      if (j.part == 2) { a -= __bfloat162float(__float2bfloat16(a)); b -= __bfloat162float(__float2bfloat16(b)); }
+      tile[r][2 * tx] = a; tile[r][2 * tx + 1] = b;
     }
     __syncthreads();
     if (j.transpose) {
@@ -325,10 +341,15 @@ __global__ void tpack_kernel(const float* __restrict__ params, bf16* __restrict_
   }
 }
 
-__global__ void embed_fwd_kernel(const int* __restrict__ idx, const float* __restrict__ table, bf16* __restrict__ out, long long npos, int E) {
+__global__ void embed_fwd_kernel(const int* __restrict__ idx, const float* __restrict__ table, bf16* __restrict__ out, long long npos, int E,
+                                 int split) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= npos * E) return;
-  out[e] = __float2bfloat16(table[(long long)idx[e / E] * E + e % E]);
+  const float v = table[(long long)idx[e / E] * E + e % E];
+  if (!split) { out[e] = __float2bfloat16(v); return; }
+  const bf16 hi = __float2bfloat16(v);
+  bf16* row = out + (e / E) * 2 * E + e % E;       // rows [hi(E) | lo(E)]
+  row[0] = hi; row[E] = __float2bfloat16(v - __bfloat162float(hi));
 }
 __global__ void embed_bwd_kernel(const int* __restrict__ idx, const bf16* __restrict__ dx, float* __restrict__ dtable, long long npos, int E) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -337,19 +358,23 @@ __global__ void embed_bwd_kernel(const int* __restrict__ idx, const bf16* __rest
 }
 
 // per-channel sum / sum of squares of y [rows][C] (bf16) -> stats[0..C), stats[C..2C)
-__global__ void bn_stats_kernel(const bf16* __restrict__ y, float* __restrict__ stats, long long rows, int C) {
+__device__ __forceinline__ float ld_act(const bf16* p, long long i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ld_act(const float* p, long long i) { return p[i]; }
+template <typename TY>
+__global__ void bn_stats_kernel(const TY* __restrict__ y, float* __restrict__ stats, long long rows, int C) {
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f, q = 0.f;
-    for (long long r = r0; r < r1; ++r) { const float v = __bfloat162float(y[r * C + c]); s += v; q += v * v; }
+    for (long long r = r0; r < r1; ++r) { const float v = ld_act(y, r * C + c); s += v; q += v * v; }
     atomicAdd(stats + c, s); atomicAdd(stats + C + c, q);
   }
 }
 // x = dropout(((y - mean) * rstd) * gamma + beta); writes mean / rstd into stats[2C..4C), updates the moving stats
-__global__ void bn_apply_kernel(const bf16* __restrict__ y, bf16* __restrict__ x, float* __restrict__ stats, const float* __restrict__ gamma,
+template <typename TY>
+__global__ void bn_apply_kernel(const TY* __restrict__ y, bf16* __restrict__ x, float* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* __restrict__ mm, float* __restrict__ mv, long long rows, int C,
-                                int training, float p, unsigned long long seed, const unsigned long long* step, int stream) {
+                                int training, float p, unsigned long long seed, const unsigned long long* step, int stream, int split) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= rows * C) return;
   const int c = int(e % C);
@@ -363,12 +388,15 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ y, bf16* __restrict__ x
       mm[c] = 0.99f * mm[c] + 0.01f * mean; mv[c] = 0.99f * mv[c] + 0.01f * var;
     }
   } else { mean = mm[c]; rstd = rsqrtf(mv[c] + 1e-3f); }
-  float v = (__bfloat162float(y[e]) - mean) * rstd * gamma[c] + beta[c];
+  float v = (ld_act(y, e) - mean) * rstd * gamma[c] + beta[c];
   if (training && p > 0.f) {
     if (step) seed += *step;
     v = hash_uniform32(hash_seed(seed, uint32_t(stream)), (unsigned long long)e) >= p ? v / (1.f - p) : 0.f;
   }
-  x[e] = __float2bfloat16(v);
+  if (!split) { x[e] = __float2bfloat16(v); return; }
+  const bf16 hi = __float2bfloat16(v);
+  bf16* row = x + (e / C) * 2 * C + c;             // rows [hi(C) | lo(C)]
+  row[0] = hi; row[C] = __float2bfloat16(v - __bfloat162float(hi));
 }
 // backward sums: sg[c] = sum g, sgx[c] = sum g * xhat   (g = dout * dropout mask)
 __global__ void bn_bwd_stats_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const float* __restrict__ stats,
@@ -671,7 +699,7 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
 // loss sums: scal[0] += sum (dec - tgt)^2, scal[2] += sum BCE(stop)
 __global__ void dec_finish_kernel(const float* __restrict__ projo, const float* __restrict__ tgt, const float* __restrict__ stop_tgt,
                                   bf16* __restrict__ dec_bm, float* __restrict__ dec_f, float* __restrict__ stop, float* __restrict__ scal,
-                                  int B, int To, int M, int clip, float lo, float hi) {
+                                  int B, int To, int M, int clip, float lo, float hi, int split) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float l0 = 0.f, l2 = 0.f;
   if (e < (long long)B * To * (M + 1)) {
@@ -680,7 +708,13 @@ __global__ void dec_finish_kernel(const float* __restrict__ projo, const float* 
     if (m < M) {
       const float d = clip ? fminf(fmaxf(v, lo), hi) : v;
       const long long o = ((long long)b * To + t) * M + m;
-      dec_bm[o] = __float2bfloat16(d); dec_f[o] = d;
+      dec_f[o] = d;
+      if (!split) dec_bm[o] = __float2bfloat16(d);
+      else {   // rows [hi(M) zero-padded to 128 | lo(M) zero-padded to 128] (the buffer is cleared once at init)
+        const bf16 h = __float2bfloat16(d);
+        bf16* row = dec_bm + ((long long)b * To + t) * 256 + m;
+        row[0] = h; row[128] = __float2bfloat16(d - __bfloat162float(h));
+      }
       if (tgt) { const float df = d - tgt[o]; l0 = df * df; }
     } else {
       stop[(long long)b * To + t] = v;
@@ -726,15 +760,30 @@ __global__ void loss_norm_kernel(const float* s, float* out, float n_mel, float 
 }
 
 // generic helper: 1x1 / k-tap conv GEMM through the engine
+// split != 0 ("fp32-class" conv stacks): the input rows are [hi | lo], each half `C` channels zero-padded to Cp = ceil(C / 64) * 64; per
+// tap one segment over both halves against [W_hi | W_hi] and one over the hi half against [W_lo] (wK = 3 * ntaps * Cp); a bf16 output is
+// written as [hi(ldo) | lo(ldo)]
 int conv_gemm(const void* a, int C, long long T, int Bn, const void* w, int N, int wK, int ntaps, const int* shifts, int BN, float* bias,
               int act, void* out_bf16, float* out_f32, int ldo, int nvalid, float pdrop, int stream_id, unsigned long long seed,
-              const unsigned long long* d_step, cudaStream_t st) {
+              const unsigned long long* d_step, cudaStream_t st, int split = 0) {
   ActGemmCall g;
   memset(&g, 0, sizeof(g));
-  g.a[0] = make_act(a, C, int(T), Bn, 1, C); g.na = 1;
   const int nkb = (C + kBK - 1) / kBK;
+  if (split) {
+    const int Cp = nkb * kBK;
+    g.a[0] = make_act(a, 2 * Cp, int(T), Bn, 1, 2 * Cp); g.na = 1;
+    g.nseg = 0;
+    for (int s = 0; s < ntaps; ++s) {
+      g.seg[g.nseg++] = Seg{0, shifts ? shifts[s] : 0, 0, 2 * nkb, 0, 1};
+      g.seg[g.nseg++] = Seg{0, shifts ? shifts[s] : 0, 0, nkb, 0, 1};
+    }
+    T2_REQUIRE(g.nseg <= kMaxSeg && pdrop == 0.f, T2_ERR_UNSUPPORTED_SHAPE, "split conv_gemm: too many taps / dropout in the epilogue");
+    g.epi.i[11] = 1;
+  } else {
+  g.a[0] = make_act(a, C, int(T), Bn, 1, C); g.na = 1;
   for (int s = 0; s < ntaps; ++s) g.seg[s] = Seg{0, shifts ? shifts[s] : 0, 0, nkb, 0, 1};
   g.nseg = ntaps;
+  }
   g.w = w; g.wN = N; g.wK = wK; g.wL = 1;
   g.T = int(T); g.B = Bn; g.n_tiles = (nvalid + BN - 1) / BN;
   g.epi.ptr[0] = out_bf16; g.epi.ptr[1] = bias; g.epi.ptr[2] = out_f32; g.epi.ptr[7] = const_cast<unsigned long long*>(d_step);
@@ -769,21 +818,30 @@ int conv_block_fwd(const StepCtx& s, const ConvL& L, const void* x_in, long long
   const TL& lo = *s.lo;
   int shifts[8];
   for (int j = 0; j < L.k; ++j) shifts[j] = j - (L.k - 1) / 2;
+  const int split = lo.c.split_bf16;
   bf16* y = reinterpret_cast<bf16*>(s.ws + L.w_y);
-  int rc = conv_gemm(x_in, L.cin, T, lo.B, s.pk + L.k_w, L.cout, L.k * L.cinp, L.k, shifts, L.cout % 256 == 0 ? 256 : 128,
-                     const_cast<float*>(s.params + L.p_b), L.act, y,
-                     nullptr, L.cout, L.cout, 0.f, 0, 0, nullptr, s.st);
+  float* yf = reinterpret_cast<float*>(s.ws + L.w_y);     // split mode keeps the pre-batch-norm activation in fp32
+  int rc = conv_gemm(x_in, L.cin, T, lo.B, s.pk + L.k_w, L.cout, L.k * L.cinp * (split ? 3 : 1), L.k, shifts, L.cout % 256 == 0 ? 256 : 128,
+                     const_cast<float*>(s.params + L.p_b), L.act, split ? nullptr : y,
+                     split ? yf : nullptr, L.cout, L.cout, 0.f, 0, 0, nullptr, s.st, split);
   if (rc) return rc;
   float* stats = reinterpret_cast<float*>(s.ws + L.w_stats);
   const long long rows = (long long)lo.B * T;
   if (training) {
     T2_CHECK_CUDA(cudaMemsetAsync(stats, 0, 2 * L.cout * sizeof(float), s.st));
-    bn_stats_kernel<<<64, 256, 0, s.st>>>(y, stats, rows, L.cout); t2_count_launch();
+    if (split) bn_stats_kernel<float><<<64, 256, 0, s.st>>>(yf, stats, rows, L.cout);
+    else bn_stats_kernel<bf16><<<64, 256, 0, s.st>>>(y, stats, rows, L.cout);
+    t2_count_launch();
   }
   float* pp = const_cast<float*>(s.params);
-  bn_apply_kernel<<<g1(rows * L.cout), 256, 0, s.st>>>(y, reinterpret_cast<bf16*>(s.ws + L.w_x), stats, s.params + L.p_gamma, s.params + L.p_beta,
+  if (split)
+    bn_apply_kernel<float><<<g1(rows * L.cout), 256, 0, s.st>>>(yf, reinterpret_cast<bf16*>(s.ws + L.w_x), stats, s.params + L.p_gamma, s.params + L.p_beta,
+                                                         pp + L.p_mm, pp + L.p_mv, rows, L.cout, training, lo.c.dropout_rate, s.seed, s.d_step, L.stream, 1);
+  else
+    bn_apply_kernel<bf16><<<g1(rows * L.cout), 256, 0, s.st>>>(y, reinterpret_cast<bf16*>(s.ws + L.w_x), stats, s.params + L.p_gamma, s.params + L.p_beta,
                                                        pp + L.p_mm, pp + L.p_mv, rows, L.cout, training, lo.c.dropout_rate, s.seed, s.d_step,
-                                                       L.stream); t2_count_launch();
+                                                       L.stream, 0);
+  t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
@@ -1357,7 +1415,7 @@ static int encoder_fwd(const StepCtx& s, const int* d_inputs, const int* d_input
   const int B = lo.B, Ti = lo.Ti, H = lo.H;
   int rc;
   bf16* emb = reinterpret_cast<bf16*>(ws + lo.w_emb);
-  embed_fwd_kernel<<<g1((long long)B * Ti * lo.E), 256, 0, st>>>(d_inputs, d_params + lo.p_emb, emb, (long long)B * Ti, lo.E); t2_count_launch();
+  embed_fwd_kernel<<<g1((long long)B * Ti * lo.E), 256, 0, st>>>(d_inputs, d_params + lo.p_emb, emb, (long long)B * Ti, lo.E, lo.c.split_bf16); t2_count_launch();
   const void* x = emb;
   for (auto& L : lo.enc) { rc = conv_block_fwd(s, L, x, Ti, training); if (rc) return rc; x = ws + L.w_x; }
   TacoSide* side = taco_side();
@@ -1369,8 +1427,8 @@ static int encoder_fwd(const StepCtx& s, const int* d_inputs, const int* d_input
     cudaStream_t sx = (d == 1 && side) ? side->s : st;
     StepCtx sc = s; sc.st = sx;
     float* pre = reinterpret_cast<float*>(ws + lo.w_encpre[d]);
-    rc = conv_gemm(x, lo.C, Ti, B, pk + lo.k_encWx[d], 4 * H, lo.C, 1, nullptr, 256, const_cast<float*>(d_params) + lo.p_elb[d], 0, nullptr, pre, 4 * H,
-                   4 * H, 0.f, 0, 0, nullptr, sx);
+    rc = conv_gemm(x, lo.C, Ti, B, pk + lo.k_encWx[d], 4 * H, lo.C * (lo.c.split_bf16 ? 3 : 1), 1, nullptr, 256, const_cast<float*>(d_params) + lo.p_elb[d], 0,
+                   nullptr, pre, 4 * H, 4 * H, 0.f, 0, 0, nullptr, sx, lo.c.split_bf16);
     if (rc) return rc;
     bf16* hh = reinterpret_cast<bf16*>(ws + lo.w_ench[d]);
     float* cc = reinterpret_cast<float*>(ws + lo.w_encc[d]);
@@ -1509,12 +1567,13 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   float* dec_f = reinterpret_cast<float*>(ws + lo.w_decf);
   dec_finish_kernel<<<g1((long long)B * To * (lo.M + 1)), 256, 0, st>>>(projo, d_mel_targets, d_stop_targets, dec_bm, dec_f,
                                                                         reinterpret_cast<float*>(ws + lo.w_stop), scal, B, To, lo.M,
-                                                                        lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
+                                                                        lo.c.clip_outputs, lo_c, hi_c, lo.c.split_bf16); t2_count_launch();
   // ---- postnet ----
   x = dec_bm;
   for (auto& L : lo.post) { rc = conv_block_fwd(s, L, x, To, training); if (rc) return rc; x = ws + L.w_x; }
   float* resid = reinterpret_cast<float*>(ws + lo.w_resid);
-  rc = conv_gemm(x, lo.PC, To, B, pk + lo.k_pp, lo.M, lo.PC, 1, nullptr, 128, d_params + lo.p_ppb, 0, nullptr, resid, 128, lo.M, 0.f, 0, 0, nullptr, st);
+  rc = conv_gemm(x, lo.PC, To, B, pk + lo.k_pp, lo.M, lo.PC * (lo.c.split_bf16 ? 3 : 1), 1, nullptr, 128, d_params + lo.p_ppb, 0, nullptr, resid, 128, lo.M,
+                 0.f, 0, 0, nullptr, st, lo.c.split_bf16);
   if (rc) return rc;
   mel_finish_kernel<<<g1((long long)B * To * lo.M), 256, 0, st>>>(dec_f, resid, d_mel_targets, reinterpret_cast<float*>(ws + lo.w_mel), scal,
                                                                   (long long)B * To, lo.M, lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
@@ -1632,11 +1691,12 @@ extern "C" int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params
   float* dec_f = reinterpret_cast<float*>(ws + lo.w_decf);
   dec_finish_kernel<<<g1((long long)B * T_used * (lo.M + 1)), 256, 0, st>>>(reinterpret_cast<float*>(ws + lo.w_projo), nullptr, nullptr, dec_bm, dec_f,
                                                                             reinterpret_cast<float*>(ws + lo.w_stop), scal, B, T_used, lo.M,
-                                                                            lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
+                                                                            lo.c.clip_outputs, lo_c, hi_c, lo.c.split_bf16); t2_count_launch();
   const void* x = dec_bm;
   for (auto& L : lo.post) { rc = conv_block_fwd(s, L, x, T_used, 0); if (rc) return rc; x = ws + L.w_x; }
   float* resid = reinterpret_cast<float*>(ws + lo.w_resid);
-  rc = conv_gemm(x, lo.PC, T_used, B, pk + lo.k_pp, lo.M, lo.PC, 1, nullptr, 128, d_params + lo.p_ppb, 0, nullptr, resid, 128, lo.M, 0.f, 0, 0, nullptr, st);
+  rc = conv_gemm(x, lo.PC, T_used, B, pk + lo.k_pp, lo.M, lo.PC * (lo.c.split_bf16 ? 3 : 1), 1, nullptr, 128, d_params + lo.p_ppb, 0, nullptr, resid, 128, lo.M,
+                 0.f, 0, 0, nullptr, st, lo.c.split_bf16);
   if (rc) return rc;
   mel_finish_kernel<<<g1((long long)B * T_used * lo.M), 256, 0, st>>>(dec_f, resid, nullptr, reinterpret_cast<float*>(ws + lo.w_mel), scal,
                                                                       (long long)B * T_used, lo.M, lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
@@ -1691,6 +1751,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   TL lo;
   int rc = build(cfg, lo, nullptr);
   if (rc) return rc;
+  T2_REQUIRE(!lo.c.split_bf16, T2_ERR_INVALID_ARG, "split_bf16 (fp32-class conv stacks) mode has no backward pass");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   const uint8_t* pk = static_cast<const uint8_t*>(d_packed);

@@ -35,6 +35,7 @@ struct PackJob {
   int col0;
   float scale;
   int perm_gh;        // >0: gate row permutation with this G/2
+  int part;           // 0 / 1: bf16(w) ; 2: bf16(w - bf16(w)), the low half of the split-bf16 operand
 };
 struct ColsumJob {
   long long src_off;  // byte offset in workspace of a bf16 [rows][ld] matrix
@@ -57,7 +58,9 @@ struct ParamT {
 struct Layout {
   t2_wn_config_t c;
   int L, R, G, Gh, S, C, O, Q, B, T, Tc, Kg, ldo, Op;
-  bool scalar_in, mol;
+  bool split;   // split-bf16 forward (t2_wn_config_t.split_bf16)
+  int xm;       // channel multiplier of the stored activations: 2 in split mode (hi | lo), else 1
+  bool scalar_in, mol, gauss;   // mol: scalar-input head (mixture of logistics, or a single Gaussian when gauss)
   float res_scale;
   std::vector<float> skip_scale;
   // params
@@ -103,6 +106,9 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   lo.L = cfg->layers; lo.R = cfg->residual_channels; lo.G = cfg->gate_channels; lo.Gh = lo.G / 2;
   lo.S = cfg->skip_out_channels; lo.C = cfg->cin_channels; lo.O = cfg->out_channels;
   lo.Q = cfg->quantize_channels; lo.B = cfg->B; lo.T = cfg->T; lo.Tc = cfg->Tc;
+  lo.split = cfg->split_bf16 != 0;
+  lo.xm = lo.split ? 2 : 1;
+  T2_REQUIRE(!lo.split || cfg->dropout == 0.f, T2_ERR_INVALID_ARG, "split_bf16 (fp32-class forward) needs dropout = 0");
   lo.scalar_in = cfg->input_type != 2;
   lo.mol = lo.scalar_in;
   T2_REQUIRE(lo.L >= 1 && cfg->stacks >= 1 && lo.L % cfg->stacks == 0, T2_ERR_INVALID_ARG, "layers %% stacks != 0");
@@ -111,8 +117,10 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   T2_REQUIRE(lo.S == 128 || lo.S == 256, T2_ERR_UNSUPPORTED_SHAPE, "skip_out_channels must be 128 or 256 (got %d)", lo.S);
   T2_REQUIRE(lo.Gh == 128 || lo.Gh == 256, T2_ERR_UNSUPPORTED_SHAPE, "gate_channels must be 256 or 512 (got %d)", lo.G);
   T2_REQUIRE(lo.C == 0 || (lo.C % 8 == 0 && lo.C <= 128), T2_ERR_UNSUPPORTED_SHAPE, "cin_channels must be 0 or a multiple of 8 <= 128");
+  lo.gauss = lo.scalar_in && lo.O == 2;
   if (lo.mol) {
-    T2_REQUIRE(lo.O % 3 == 0 && lo.O <= 30, T2_ERR_UNSUPPORTED_SHAPE, "scalar input needs a MoL head with <= 10 mixtures (out_channels=%d)", lo.O);
+    T2_REQUIRE(lo.gauss || (lo.O % 3 == 0 && lo.O >= 3 && lo.O <= 30), T2_ERR_UNSUPPORTED_SHAPE,
+               "scalar input needs out_channels = 2 (Gaussian) or 3 * nr_mix <= 30 (mixture of logistics), got %d", lo.O);
   } else {
     T2_REQUIRE(lo.O == 256 && lo.Q == 256, T2_ERR_UNSUPPORTED_SHAPE, "mulaw-quantize needs out_channels == quantize_channels == 256");
   }
@@ -177,11 +185,12 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   long long o = 0;
   auto takeb = [&](long long bytes) { long long r = o; o = align_up(o + bytes, 256); return r; };
   const long long L = lo.L;
-  lo.k_Wg = takeb(L * lo.G * lo.Kg * 2);
-  lo.k_Wo = takeb(L * lo.R * lo.Gh * 2);
-  lo.k_Ws = takeb((long long)lo.S * L * lo.Gh * 2);
-  lo.k_Wf1 = takeb((long long)lo.S * lo.S * 2);
-  lo.k_Wf2 = takeb((long long)lo.O * lo.S * 2);
+  const long long km = lo.split ? 3 : 1;   // split-bf16: every forward K segment becomes [W_hi | W_hi | W_lo]
+  lo.k_Wg = takeb(L * lo.G * lo.Kg * km * 2);
+  lo.k_Wo = takeb(L * lo.R * lo.Gh * km * 2);
+  lo.k_Ws = takeb((long long)lo.S * L * lo.Gh * km * 2);
+  lo.k_Wf1 = takeb((long long)lo.S * lo.S * km * 2);
+  lo.k_Wf2 = takeb((long long)(lo.O < 32 ? 32 : lo.O) * lo.S * km * 2);
   lo.k_WozT = takeb(L * lo.Gh * (lo.R + lo.S) * 2);
   lo.k_WdT = takeb(L * lo.R * 3 * lo.G * 2);
   lo.k_WcT = takeb((long long)(lo.C > 0 ? lo.C : 8) * L * lo.G * 2);
@@ -193,18 +202,18 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   // ---- workspace ----
   o = 0;
   const long long BT = (long long)lo.B * lo.T;
-  lo.w_cup = takeb(BT * (lo.C > 0 ? lo.C : 8) * 2);
+  lo.w_cup = takeb(BT * (lo.split ? 256 : (lo.C > 0 ? lo.C : 8)) * 2);     // split: [hi(C) pad 128 | lo(C) pad 128]
   lo.w_upout.clear();
   for (size_t i = 0; i < lo.up_w.size(); ++i) lo.w_upout.push_back(takeb((long long)lo.B * lo.C * lo.up_w[i] * 4));
   lo.w_upgrad[0] = takeb(BT * (lo.C > 0 ? lo.C : 8) * 4);
   lo.w_upgrad[1] = takeb(BT * (lo.C > 0 ? lo.C : 8) * 4);
-  lo.w_x = takeb(L * BT * lo.R * 2);
+  lo.w_x = takeb(L * BT * lo.R * 2 * lo.xm);
   lo.w_xd = cfg->dropout > 0.f ? takeb(L * BT * lo.R * 2) : lo.w_x;
   lo.w_ta = takeb(L * BT * lo.Gh * 2);
   lo.w_sb = takeb(L * BT * lo.Gh * 2);
-  lo.w_z = takeb(L * BT * lo.Gh * 2);
-  lo.w_h1 = takeb(BT * lo.S * 2);
-  lo.w_h2 = takeb(BT * lo.S * 2);
+  lo.w_z = takeb(L * BT * lo.Gh * 2 * lo.xm);
+  lo.w_h1 = takeb(BT * lo.S * 2 * lo.xm);
+  lo.w_h2 = takeb(BT * lo.S * 2 * lo.xm);
   lo.w_dlog = takeb(BT * lo.ldo * 2);
   lo.w_dh2 = takeb(BT * lo.S * 2);
   lo.w_dskip = takeb(BT * lo.S * 2);
@@ -218,14 +227,30 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
   lo.packjobs.clear();
   auto pj = [&](long long src, int K, int N, long long dst_bytes, int ld, int transpose, int col0, float scale, int perm) {
     PackJob j; j.src_off = src; j.K = K; j.N = N; j.dst_off = dst_bytes / 2; j.dst_ld = ld; j.transpose = transpose;
-    j.col0 = col0; j.scale = scale; j.perm_gh = perm; lo.packjobs.push_back(j);
+    j.col0 = col0; j.scale = scale; j.perm_gh = perm; j.part = 0; lo.packjobs.push_back(j);
+  };
+  // split-bf16 forward operand: the K range [col0, col0 + slot) of the plain layout becomes [W_hi | W_hi | W_lo], slot columns each
+  auto pj3 = [&](long long src, int K, int N, long long dst_bytes, int ld, int col_hi, int col_lo, int slot, float scale, int perm) {
+    pj(src, K, N, dst_bytes, ld, 1, col_hi, scale, perm);
+    pj(src, K, N, dst_bytes, ld, 1, col_hi + slot, scale, perm);
+    pj(src, K, N, dst_bytes, ld, 1, col_lo, scale, perm);
+    lo.packjobs.back().part = 2;
   };
   for (int l = 0; l < lo.L; ++l) {
-    const long long wg = lo.k_Wg + (long long)l * lo.G * lo.Kg * 2;
+    const long long wg = lo.k_Wg + (long long)l * lo.G * lo.Kg * km * 2;
+    if (lo.split) {
+      const int R = lo.R, Gh = lo.Gh;
+      for (int j = 0; j < 3; ++j) pj3(lo.p_dil_k[l] + (long long)j * R * lo.G, R, lo.G, wg, 3 * lo.Kg, j * 3 * R, j * 3 * R + 2 * R, R, 1.f, Gh);
+      if (lo.C > 0) pj3(lo.p_c_k[l], lo.C, lo.G, wg, 3 * lo.Kg, 9 * R, 9 * R + 256, 128, 1.f, Gh);
+      pj3(lo.p_o_k[l], Gh, R, lo.k_Wo + (long long)l * R * Gh * 3 * 2, 3 * Gh, 0, 2 * Gh, Gh, 1.f, 0);
+      // skip GEMM: K runs over [all layers: hi | hi] then [all layers: lo]
+      pj3(lo.p_s_k[l], Gh, lo.S, lo.k_Ws, 3 * lo.L * Gh, l * 2 * Gh, 2 * lo.L * Gh + l * Gh, Gh, lo.skip_scale[l], 0);
+    } else {
     for (int j = 0; j < 3; ++j) pj(lo.p_dil_k[l] + (long long)j * lo.R * lo.G, lo.R, lo.G, wg, lo.Kg, 1, j * lo.R, 1.f, lo.Gh);
     if (lo.C > 0) pj(lo.p_c_k[l], lo.C, lo.G, wg, lo.Kg, 1, 3 * lo.R, 1.f, lo.Gh);
     pj(lo.p_o_k[l], lo.Gh, lo.R, lo.k_Wo + (long long)l * lo.R * lo.Gh * 2, lo.Gh, 1, 0, 1.f, 0);
     pj(lo.p_s_k[l], lo.Gh, lo.S, lo.k_Ws, lo.L * lo.Gh, 1, l * lo.Gh, lo.skip_scale[l], 0);
+    }
     const long long woz = lo.k_WozT + (long long)l * lo.Gh * (lo.R + lo.S) * 2;
     pj(lo.p_o_k[l], lo.Gh, lo.R, woz, lo.R + lo.S, 0, 0, lo.res_scale, 0);
     pj(lo.p_s_k[l], lo.Gh, lo.S, woz, lo.R + lo.S, 0, lo.R, lo.skip_scale[l], 0);
@@ -233,8 +258,13 @@ int build_layout(const t2_wn_config_t* cfg, Layout& lo) {
     for (int j = 0; j < 3; ++j) pj(lo.p_dil_k[l] + (long long)j * lo.R * lo.G, lo.R, lo.G, wd, 3 * lo.G, 0, j * lo.G, 1.f, 0);
     if (lo.C > 0) pj(lo.p_c_k[l], lo.C, lo.G, lo.k_WcT, lo.L * lo.G, 0, l * lo.G, 1.f, 0);
   }
-  pj(lo.p_f1_k, lo.S, lo.S, lo.k_Wf1, lo.S, 1, 0, 1.f, 0);
-  pj(lo.p_f2_k, lo.S, lo.O, lo.k_Wf2, lo.S, 1, 0, 1.f, 0);
+  if (lo.split) {
+    pj3(lo.p_f1_k, lo.S, lo.S, lo.k_Wf1, 3 * lo.S, 0, 2 * lo.S, lo.S, 1.f, 0);
+    pj3(lo.p_f2_k, lo.S, lo.O, lo.k_Wf2, 3 * lo.S, 0, 2 * lo.S, lo.S, 1.f, 0);
+  } else {
+    pj(lo.p_f1_k, lo.S, lo.S, lo.k_Wf1, lo.S, 1, 0, 1.f, 0);
+    pj(lo.p_f2_k, lo.S, lo.O, lo.k_Wf2, lo.S, 1, 0, 1.f, 0);
+  }
   pj(lo.p_f1_k, lo.S, lo.S, lo.k_Wf1T, lo.S, 0, 0, 1.f, 0);
   pj(lo.p_f2_k, lo.S, lo.O, lo.k_Wf2T, lo.Op, 0, 0, 1.f, 0);
   if (!lo.mol) pj(lo.p_f2_k, lo.S, lo.O, lo.k_Wf2T, lo.Op, 0, 256, 1.f, 0);
@@ -330,7 +360,9 @@ __global__ void pack_kernel(const float* __restrict__ params, bf16* __restrict__
         if (vec_src && n + 1 < j.N) { const float2 v = *reinterpret_cast<const float2*>(src); a = v.x; b = v.y; }
         else { if (n < j.N) a = src[0]; if (n + 1 < j.N) b = src[1]; }
       }
-      tile[r][2 * tx] = a * j.scale; tile[r][2 * tx + 1] = b * j.scale;
+      a *= j.scale; b *= j.scale;
+      if (j.part == 2) { a -= __bfloat162float(__float2bfloat16(a)); b -= __bfloat162float(__float2bfloat16(b)); }
+      tile[r][2 * tx] = a; tile[r][2 * tx + 1] = b;
     }
     __syncthreads();
     if (j.transpose) {
@@ -389,7 +421,7 @@ __global__ void derived_bias_kernel(DerivedArgs a) {
 __global__ void first_conv_kernel(const void* __restrict__ xin, int scalar_in, const float* __restrict__ W,
                                   const float* __restrict__ bias, bf16* __restrict__ x, bf16* __restrict__ xd,
                                   long long npos, int R, float p, unsigned long long seed,
-                                  const unsigned long long* __restrict__ step) {
+                                  const unsigned long long* __restrict__ step, int split) {
   // 8 channels per thread (R % 8 == 0): two float4 loads of the embedding row, one 16-byte store per output
   if (step) seed += *step;
   const long long e8 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -412,6 +444,16 @@ __global__ void first_conv_kernel(const void* __restrict__ xin, int scalar_in, c
   }
   const long long e = pos * R + r;
   uint4 o;
+  if (split) {   // rows are [hi(R) | lo(R)]
+    float hi[8], lo8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { hi[j] = __bfloat162float(__float2bfloat16(v[j])); lo8[j] = v[j] - hi[j]; }
+    o.x = pack_bf16x2(hi[0], hi[1]); o.y = pack_bf16x2(hi[2], hi[3]); o.z = pack_bf16x2(hi[4], hi[5]); o.w = pack_bf16x2(hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(x + pos * 2 * R + r) = o;
+    o.x = pack_bf16x2(lo8[0], lo8[1]); o.y = pack_bf16x2(lo8[2], lo8[3]); o.z = pack_bf16x2(lo8[4], lo8[5]); o.w = pack_bf16x2(lo8[6], lo8[7]);
+    *reinterpret_cast<uint4*>(x + pos * 2 * R + R + r) = o;
+    return;
+  }
   o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(x + e) = o;
   if (xd != x && xd != nullptr) {
@@ -478,7 +520,7 @@ __global__ void colsum_kernel(const uint8_t* __restrict__ ws, float* __restrict_
 // ---- conditioning upsampling net (modules.py:539-654 SubPixel, :736-770 ConvTranspose2D) + ReLU -------------
 // in [B][H][W] fp32 -> out [B][H][W*s] fp32 (post-ReLU); optional bf16 channels-last copy [B][W*s][H]
 __global__ void upsample_fwd_kernel(const float* __restrict__ in, const float* __restrict__ K, const float* __restrict__ bias,
-                                    float* __restrict__ out, bf16* __restrict__ out_cl, int B, int H, int W, int s, int type) {
+                                    float* __restrict__ out, bf16* __restrict__ out_cl, int B, int H, int W, int s, int type, int split = 0) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long n = (long long)B * H * W * s;
   if (e >= n) return;
@@ -513,7 +555,12 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ in, const float* _
   }
   acc = fmaxf(acc, 0.f);
   out[e] = acc;
-  if (out_cl) out_cl[((long long)b * Wo + xo) * H + h] = __float2bfloat16(acc);
+  if (out_cl && split) {   // rows are [hi(H) zero-padded to 128 | lo(H) zero-padded to 128]
+    const bf16 hi = __float2bfloat16(acc);
+    bf16* row = out_cl + ((long long)b * Wo + xo) * 256;
+    row[h] = hi;
+    row[128 + h] = __float2bfloat16(acc - __bfloat162float(hi));
+  } else if (out_cl) out_cl[((long long)b * Wo + xo) * H + h] = __float2bfloat16(acc);
 }
 // channels-last fp32 [B][T][C] -> [B][C][T] (tiled transpose) so the upsampling backward reads contiguously
 __global__ void cl_to_chw_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C) {
@@ -641,6 +688,20 @@ ActGemmCall make_gate_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int
   const int d = lo.dil(l);
   ActGemmCall g;
   memset(&g, 0, sizeof(g));
+  if (lo.split) {
+    // rows [hi | lo]: per tap one segment over both halves against [W_hi | W_hi] and one over the hi half against [W_lo]
+    g.a[0] = make_act(ws + lo.w_xd, 2 * lo.R, lo.T, lo.B, lo.L);
+    g.a[1] = make_act(ws + lo.w_cup, 256, lo.T, lo.B, 1);
+    g.na = lo.C > 0 ? 2 : 1;
+    const int shifts[3] = {-2 * d, -d, 0};
+    g.nseg = 0;
+    for (int j = 0; j < 3; ++j) {
+      g.seg[g.nseg++] = Seg{0, shifts[j], 0, 2 * lo.R / kBK, l, 1};
+      g.seg[g.nseg++] = Seg{0, shifts[j], 0, lo.R / kBK, l, 1};
+    }
+    if (lo.C > 0) { g.seg[g.nseg++] = Seg{1, 0, 0, 4, 0, 1}; g.seg[g.nseg++] = Seg{1, 0, 0, 2, 0, 1}; }
+    g.w = pk + lo.k_Wg; g.wN = lo.G; g.wK = 3 * lo.Kg; g.wL = lo.L; g.w_layer = l; g.w_k0 = 0;
+  } else {
   g.a[0] = make_act(ws + lo.w_xd, lo.R, lo.T, lo.B, lo.L);
   g.a[1] = make_act(ws + lo.w_cup, lo.C > 0 ? lo.C : 8, lo.T, lo.B, 1);
   g.na = lo.C > 0 ? 2 : 1;
@@ -650,11 +711,13 @@ ActGemmCall make_gate_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, int
   g.nseg = 3;
   if (lo.C > 0) { g.seg[3] = Seg{1, 0, 0, 2, 0, 1}; g.nseg = 4; }
   g.w = pk + lo.k_Wg; g.wN = lo.G; g.wK = lo.Kg; g.wL = lo.L; g.w_layer = l; g.w_k0 = 0;
+  }
   g.T = lo.T; g.B = lo.B; g.n_tiles = lo.G / 256;
   const long long lofs = (long long)l * BT * lo.Gh;
   g.epi.ptr[0] = save ? reinterpret_cast<bf16*>(ws + lo.w_ta) + lofs : nullptr;
   g.epi.ptr[1] = save ? reinterpret_cast<bf16*>(ws + lo.w_sb) + lofs : nullptr;
-  g.epi.ptr[2] = reinterpret_cast<bf16*>(ws + lo.w_z) + lofs;
+  g.epi.ptr[2] = reinterpret_cast<bf16*>(ws + lo.w_z) + lofs * lo.xm;
+  g.epi.i[11] = lo.split ? 1 : 0;
   g.epi.ptr[3] = const_cast<float*>(reinterpret_cast<const float*>(pk + lo.k_bias_g) + (long long)l * lo.G);
   g.epi.i[0] = lo.Gh;
   return g;
@@ -667,12 +730,14 @@ ActGemmCall make_out_call(const Layout& lo, uint8_t* ws, const uint8_t* pk, cons
   bf16* xd_all = reinterpret_cast<bf16*>(ws + lo.w_xd);
   ActGemmCall o;
   memset(&o, 0, sizeof(o));
-  o.a[0] = make_act(ws + lo.w_z, lo.Gh, lo.T, lo.B, lo.L); o.na = 1;
-  o.seg[0] = Seg{0, 0, 0, lo.Gh / kBK, l, 1}; o.nseg = 1;
-  o.w = pk + lo.k_Wo; o.wN = lo.R; o.wK = lo.Gh; o.wL = lo.L; o.w_layer = l;
+  o.a[0] = make_act(ws + lo.w_z, lo.Gh * lo.xm, lo.T, lo.B, lo.L); o.na = 1;
+  o.seg[0] = Seg{0, 0, 0, lo.Gh * lo.xm / kBK, l, 1}; o.nseg = 1;
+  if (lo.split) { o.seg[1] = Seg{0, 0, 0, lo.Gh / kBK, l, 1}; o.nseg = 2; }
+  o.w = pk + lo.k_Wo; o.wN = lo.R; o.wK = lo.Gh * (lo.split ? 3 : 1); o.wL = lo.L; o.w_layer = l;
   o.T = lo.T; o.B = lo.B; o.n_tiles = 1;
-  o.epi.ptr[0] = x_all + (long long)l * BT * lo.R;
-  o.epi.ptr[1] = x_all + (long long)(l + 1) * BT * lo.R;
+  o.epi.ptr[0] = x_all + (long long)l * BT * lo.R * lo.xm;
+  o.epi.ptr[1] = x_all + (long long)(l + 1) * BT * lo.R * lo.xm;
+  o.epi.i[11] = lo.split ? 1 : 0;
   o.epi.ptr[2] = p > 0.f ? xd_all + (long long)(l + 1) * BT * lo.R : nullptr;
   o.epi.ptr[3] = const_cast<float*>(params + lo.p_o_b[l]);
   o.epi.f[0] = lo.res_scale; o.epi.f[1] = p; o.epi.i[1] = l + 1; o.epi.seed = seed;
@@ -831,8 +896,11 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
   const float p = cfg->dropout;
   T2_CHECK_CUDA(cudaMemsetAsync(scalars, 0, 16 * sizeof(float), st));
 
+  T2_REQUIRE(!lo.split || (!save_for_backward && !cfg->c_pre_upsampled), T2_ERR_INVALID_ARG,
+             "split_bf16 (fp32-class) mode is forward / loss only (save_for_backward = 0) and needs the upsampling net");
   // 1. conditioning -> c_up (bf16 channels-last)
   bf16* c_up = reinterpret_cast<bf16*>(ws + lo.w_cup);
+  if (lo.split) T2_CHECK_CUDA(cudaMemsetAsync(c_up, 0, (size_t)BT * 256 * 2, st));     // the channel padding of both halves must read as zero
   if (lo.C > 0) {
     T2_REQUIRE(d_c != nullptr, T2_ERR_INVALID_ARG, "local conditioning enabled but d_c is NULL");
     if (cfg->c_pre_upsampled) {
@@ -845,7 +913,8 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
         float* out = reinterpret_cast<float*>(ws + lo.w_upout[i]);
         const bool last = i + 1 == lo.up_w.size();
         upsample_fwd_kernel<<<grid1d((long long)lo.B * lo.C * W * s), 256, 0, st>>>(
-            in, d_params + lo.p_up_k[i], d_params + lo.p_up_b[i], out, last ? c_up : nullptr, lo.B, lo.C, W, s, cfg->upsample_type); t2_count_launch();
+            in, d_params + lo.p_up_k[i], d_params + lo.p_up_b[i], out, last ? c_up : nullptr, lo.B, lo.C, W, s, cfg->upsample_type,
+            lo.split ? 1 : 0); t2_count_launch();
         in = out;
         W *= s;
       }
@@ -856,11 +925,11 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
   bf16* x_all = reinterpret_cast<bf16*>(ws + lo.w_x);
   bf16* xd_all = reinterpret_cast<bf16*>(ws + lo.w_xd);
   first_conv_kernel<<<grid1d(BT * (lo.R / 8)), 256, 0, st>>>(d_x, lo.scalar_in ? 1 : 0, d_params + lo.p_in_k, d_params + lo.p_in_b,
-                                                       x_all, p > 0.f ? xd_all : x_all, BT, lo.R, p, seed, d_step); t2_count_launch();
+                                                       x_all, p > 0.f ? xd_all : x_all, BT, lo.R, p, seed, d_step, lo.split ? 1 : 0); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   // 3. residual stack
   bf16* z_all = reinterpret_cast<bf16*>(ws + lo.w_z);
-  const ActT a_z = make_act(z_all, lo.Gh, lo.T, lo.B, lo.L);
+  const ActT a_z = make_act(z_all, lo.Gh * lo.xm, lo.T, lo.B, lo.L);
   for (int l = 0; l < lo.L; ++l) {
     ActGemmCall g = make_gate_call(lo, ws, pk, l, save_for_backward != 0);
     rc = launch_act_gemm(EPI_GATE, 256, g, st);
@@ -878,23 +947,25 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
     ActGemmCall g;
     memset(&g, 0, sizeof(g));
     g.a[0] = a_z; g.na = 1;
-    g.seg[0] = Seg{0, 0, 0, lo.Gh / kBK, 0, lo.L}; g.nseg = 1;
-    g.w = pk + lo.k_Ws; g.wN = lo.S; g.wK = lo.L * lo.Gh; g.wL = 1;
+    g.seg[0] = Seg{0, 0, 0, lo.Gh * lo.xm / kBK, 0, lo.L}; g.nseg = 1;
+    if (lo.split) { g.seg[1] = Seg{0, 0, 0, lo.Gh / kBK, 0, lo.L}; g.nseg = 2; }
+    g.w = pk + lo.k_Ws; g.wN = lo.S; g.wK = lo.L * lo.Gh * (lo.split ? 3 : 1); g.wL = 1;
     g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
     g.epi.ptr[0] = h1; g.epi.ptr[1] = const_cast<float*>(reinterpret_cast<const float*>(pk + lo.k_bias_skip));
-    g.epi.i[0] = lo.S; g.epi.i[1] = 1; g.epi.i[2] = lo.S;
+    g.epi.i[0] = lo.S; g.epi.i[1] = 1; g.epi.i[2] = lo.S; g.epi.i[11] = lo.split ? 1 : 0;
     rc = launch_act_gemm(EPI_BIAS_ACT, lo.S, g, st);
     if (rc) return rc;
   }
   {
     ActGemmCall g;
     memset(&g, 0, sizeof(g));
-    g.a[0] = make_act(h1, lo.S, lo.T, lo.B); g.na = 1;
-    g.seg[0] = Seg{0, 0, 0, lo.S / kBK, 0, 1}; g.nseg = 1;
-    g.w = pk + lo.k_Wf1; g.wN = lo.S; g.wK = lo.S; g.wL = 1;
+    g.a[0] = make_act(h1, lo.S * lo.xm, lo.T, lo.B); g.na = 1;
+    g.seg[0] = Seg{0, 0, 0, lo.S * lo.xm / kBK, 0, 1}; g.nseg = 1;
+    if (lo.split) { g.seg[1] = Seg{0, 0, 0, lo.S / kBK, 0, 1}; g.nseg = 2; }
+    g.w = pk + lo.k_Wf1; g.wN = lo.S; g.wK = lo.S * (lo.split ? 3 : 1); g.wL = 1;
     g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
     g.epi.ptr[0] = h2; g.epi.ptr[1] = const_cast<float*>(d_params + lo.p_f1_b);
-    g.epi.i[0] = lo.S; g.epi.i[1] = 1; g.epi.i[2] = lo.S;
+    g.epi.i[0] = lo.S; g.epi.i[1] = 1; g.epi.i[2] = lo.S; g.epi.i[11] = lo.split ? 1 : 0;
     rc = launch_act_gemm(EPI_BIAS_ACT, lo.S, g, st);
     if (rc) return rc;
   }
@@ -902,9 +973,10 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
   {
     ActGemmCall g;
     memset(&g, 0, sizeof(g));
-    g.a[0] = make_act(h2, lo.S, lo.T, lo.B); g.na = 1;
-    g.seg[0] = Seg{0, 0, 0, lo.S / kBK, 0, 1}; g.nseg = 1;
-    g.w = pk + lo.k_Wf2; g.wN = lo.O; g.wK = lo.S; g.wL = 1;
+    g.a[0] = make_act(h2, lo.S * lo.xm, lo.T, lo.B); g.na = 1;
+    g.seg[0] = Seg{0, 0, 0, lo.S * lo.xm / kBK, 0, 1}; g.nseg = 1;
+    if (lo.split) { g.seg[1] = Seg{0, 0, 0, lo.S / kBK, 0, 1}; g.nseg = 2; }
+    g.w = pk + lo.k_Wf2; g.wN = lo.O; g.wK = lo.S * (lo.split ? 3 : 1); g.wL = 1;
     g.T = lo.T; g.B = lo.B; g.n_tiles = 1;
     g.epi.ptr[0] = const_cast<void*>(d_targets);
     g.epi.ptr[1] = const_cast<int*>(d_lengths);
@@ -917,7 +989,9 @@ extern "C" int t2_wn_forward(const t2_wn_config_t* cfg, const float* d_params, c
       g.epi.f[0] = cfg->log_scale_min;
       g.epi.f[1] = 1.f / float(lo.Q - 1);
       g.epi.f[2] = logf(float(lo.Q - 1) / 2.f);
-      g.epi.i[0] = lo.O / 3;
+      g.epi.i[0] = lo.gauss ? 0 : lo.O / 3;
+      g.epi.i[2] = lo.gauss ? (cfg->cdf_loss ? 2 : 1) : 0;     // 0 mixture of logistics, 1 Gaussian log-density, 2 Gaussian CDF difference
+      g.epi.f[3] = cfg->log_scale_min_gauss;
       rc = launch_act_gemm(EPI_MOL, 32, g, st);
     } else {
       rc = launch_act_gemm(EPI_CE, 256, g, st);
@@ -964,6 +1038,7 @@ extern "C" int t2_wn_backward_phased(const t2_wn_config_t* cfg, const float* d_p
   int rc = build_layout(cfg, lo);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  T2_REQUIRE(!lo.split, T2_ERR_INVALID_ARG, "split_bf16 (fp32-class) mode has no backward pass");
   T2_REQUIRE(n_groups >= 1 && n_groups <= lo.L && (phase == -1 || phase == 100 || (phase >= 0 && phase <= n_groups)), T2_ERR_INVALID_ARG,
              "backward_phased: bad phase %d / n_groups %d", phase, n_groups);
   if (phase >= 1 && phase <= n_groups) {
@@ -1152,7 +1227,7 @@ extern "C" int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_param
   Layout lo;
   int rc = build_layout(cfg, lo);
   if (rc) return rc;
-  T2_REQUIRE(layer >= 0 && layer < lo.L && reps >= 1 && ms_per_launch && which >= 0 && which <= 3, T2_ERR_INVALID_ARG,
+  T2_REQUIRE(layer >= 0 && layer < lo.L && reps >= 1 && ms_per_launch && which >= 0 && which <= 4, T2_ERR_INVALID_ARG,
              "time_kernel: bad arguments");
   T2_REQUIRE(which != 1 || layer + 1 < lo.L, T2_ERR_INVALID_ARG, "the last layer has no out GEMM");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1160,7 +1235,7 @@ extern "C" int t2_wn_time_kernel(const t2_wn_config_t* cfg, const float* d_param
   const uint8_t* pk = static_cast<const uint8_t*>(d_packed);
   ActGemmCall g;
   int epi, bn;
-  if (which == 0) { g = make_gate_call(lo, ws, pk, layer, true); epi = EPI_GATE; bn = 256; }
+  if (which == 0 || which == 4) { g = make_gate_call(lo, ws, pk, layer, which == 0); epi = EPI_GATE; bn = 256; }   // 4: without the tanh / sigmoid stashes
   else if (which == 1) { g = make_out_call(lo, ws, pk, d_params, layer, cfg->dropout, 1, nullptr); epi = EPI_RES; bn = lo.R; }
   else if (which == 2) { g = make_dz_call(lo, ws, pk, layer, nullptr); epi = EPI_GATE_BWD; bn = lo.Gh >= 256 ? 256 : 128; }
   else { g = make_dx_call(lo, ws, pk, layer, cfg->dropout, 1, nullptr, nullptr); epi = EPI_DX; bn = lo.R; }
@@ -1345,7 +1420,7 @@ struct ArArgs {
   int B, T, L, R, G, Gh, S, C, O, Q, scalar_in, layers_per_stack;
   int CS, ZC, RC, SC, FC, OC, K1;
   long long per_rank_layer, o_head1, o_head2;
-  float res_scale, log_scale_min;
+  float res_scale, log_scale_min, log_scale_min_gauss;
   int items_per_cluster;
   int prefetch;             // 1: this CTA's per-layer weight slice is double-buffered in shared memory (bulk async copies)
 };
@@ -1607,7 +1682,20 @@ __global__ void __launch_bounds__(kArThreads, 1) wn_ar_kernel(ArArgs a) {
         if (rank == 0 && a.out_raw)
           for (int j = lane; j < a.O; j += 32) a.out_raw[((long long)bi * a.T + t) * a.O + j] = y[j];
         float nxt;
-        if (a.scalar_in) {
+        if (a.scalar_in && a.O == 2) {
+          // sample_from_gaussian (gaussian.py:39-52): x = mean + exp(max(log_scale, min)) * n, clipped to [-1, 1]; the standard-normal
+          // draw n is injected through u_b or made by Box-Muller from two counter-hash uniforms
+          float n;
+          if (a.u_b) n = a.u_b[(long long)bi * a.T + t];
+          else {
+            const float u1 = 1e-7f + (1.f - 2e-7f) * hash_uniform(a.seed, ((unsigned long long)bi * a.T + t) * 16 + 14);
+            const float u2 = hash_uniform(a.seed, ((unsigned long long)bi * a.T + t) * 16 + 15);
+            n = sqrtf(-2.f * __logf(u1)) * __cosf(6.28318530718f * u2);
+          }
+          const float x = y[0] + __expf(fmaxf(y[1], a.log_scale_min_gauss)) * n;
+          nxt = fminf(fmaxf(x, -1.f), 1.f);
+          if (rank == 0 && lane == 0) static_cast<float*>(a.out_samples)[(long long)bi * a.T + t] = nxt;
+        } else if (a.scalar_in) {
           // sample_from_discretized_mix_logistic (mixture.py:76-107): Gumbel-max over the mixture logits
           float best = -INFINITY;
           int bk = 0;
@@ -1786,7 +1874,7 @@ extern "C" int t2_wn_ar_generate(const t2_wn_config_t* cfg, int cluster_size, co
   a.scalar_in = lo.scalar_in ? 1 : 0; a.layers_per_stack = lo.L / cfg->stacks;
   a.CS = al.CS; a.ZC = al.ZC; a.RC = al.RC; a.SC = al.SC; a.FC = al.FC; a.OC = al.OC; a.K1 = al.K1;
   a.per_rank_layer = al.per_rank_layer; a.o_head1 = al.o_head1; a.o_head2 = al.o_head2;
-  a.res_scale = lo.res_scale; a.log_scale_min = cfg->log_scale_min;
+  a.res_scale = lo.res_scale; a.log_scale_min = cfg->log_scale_min; a.log_scale_min_gauss = cfg->log_scale_min_gauss;
   // clusters: as many as fit on the device, but never more than batch items
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

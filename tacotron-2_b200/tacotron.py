@@ -15,7 +15,8 @@ class TacoConfig(ctypes.Structure):
         "B", "T_in", "T_out", "n_symbols", "num_mels", "embedding_dim", "enc_conv_layers", "enc_conv_kernel",
         "enc_conv_channels", "encoder_lstm_units", "attention_dim", "attention_filters", "attention_kernel", "prenet1",
         "prenet2", "decoder_lstm_units", "postnet_layers", "postnet_kernel", "postnet_channels", "clip_outputs")] + [
-        (n, ctypes.c_float) for n in ("dropout_rate", "zoneout_rate", "reg_weight", "max_abs_value", "lower_bound_decay")]
+        (n, ctypes.c_float) for n in ("dropout_rate", "zoneout_rate", "reg_weight", "max_abs_value", "lower_bound_decay")] + [
+        ("split_bf16", ctypes.c_int)]
 
 
 def unsupported_hparams(hp):
@@ -41,7 +42,9 @@ def unsupported_hparams(hp):
     return bad
 
 
-def make_config(hp, B, T_in, T_out):
+def make_config(hp, B, T_in, T_out, precision="bf16"):
+    if precision not in ("bf16", "fp32-class"):
+        raise L.T2Error("precision must be 'bf16' or 'fp32-class'")
     bad = unsupported_hparams(hp)
     if bad:
         raise L.T2Error("hparams not implemented on the B200 Tacotron path (they would change the model): " + "; ".join(bad))
@@ -60,15 +63,19 @@ def make_config(hp, B, T_in, T_out):
         reg_weight *= 1.0 / (2 * hp.max_abs_value) if hp.symmetric_mels else 1.0 / hp.max_abs_value
     c.dropout_rate, c.zoneout_rate, c.reg_weight = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate, reg_weight
     c.max_abs_value, c.lower_bound_decay = hp.max_abs_value, hp.lower_bound_decay
+    c.split_bf16 = int(precision == "fp32-class")
     return c
 
 
 class Tacotron(object):
-    def __init__(self, hparams, B, T_in, T_out, device="cuda"):
+    def __init__(self, hparams, B, T_in, T_out, device="cuda", precision="bf16"):
+        """precision 'fp32-class': the convolution stacks (encoder convs, postnet) run on bf16 hi + lo operand pairs with fp32
+        pre-batch-norm activations; forward / losses only (include/t2b200.h, t2_taco_config_t.split_bf16)."""
         self.hp = hparams
         self.lib = L.load()
         self.device = torch.device(device)
-        self.cfg = make_config(hparams, B, T_in, T_out)
+        self.precision = precision
+        self.cfg = make_config(hparams, B, T_in, T_out, precision)
         n, pb, wb, nt = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
         L.check(self.lib.t2_taco_sizes(ctypes.byref(self.cfg), ctypes.byref(n), ctypes.byref(pb), ctypes.byref(wb), ctypes.byref(nt)))
         self.n_params = n.value

@@ -22,6 +22,7 @@ class WnConfig(ctypes.Structure):
         ("upsample_type", ctypes.c_int), ("n_upsample", ctypes.c_int), ("upsample_scales", ctypes.c_int * 4),
         ("freq_axis_kernel_size", ctypes.c_int), ("dropout", ctypes.c_float), ("log_scale_min", ctypes.c_float),
         ("B", ctypes.c_int), ("T", ctypes.c_int), ("Tc", ctypes.c_int), ("c_pre_upsampled", ctypes.c_int),
+        ("log_scale_min_gauss", ctypes.c_float), ("cdf_loss", ctypes.c_int), ("split_bf16", ctypes.c_int),
     ]
 
 
@@ -51,7 +52,7 @@ def unsupported_hparams(hp):
     return bad
 
 
-def make_config(hp, B, T, c_pre_upsampled=False, dropout=None):
+def make_config(hp, B, T, c_pre_upsampled=False, dropout=None, precision="bf16"):
     bad = unsupported_hparams(hp)
     if bad:
         raise L.T2Error("hparams not implemented on the B200 WaveNet path (they would change the model): " + "; ".join(bad))
@@ -74,6 +75,11 @@ def make_config(hp, B, T, c_pre_upsampled=False, dropout=None):
     cfg.freq_axis_kernel_size = hp.freq_axis_kernel_size
     cfg.dropout = hp.wavenet_dropout if dropout is None else dropout
     cfg.log_scale_min = hp.log_scale_min
+    cfg.log_scale_min_gauss = getattr(hp, "log_scale_min_gauss", -7.0)
+    cfg.cdf_loss = int(getattr(hp, "cdf_loss", False))
+    if precision not in ("bf16", "fp32-class"):
+        raise L.T2Error("precision must be 'bf16' or 'fp32-class'")
+    cfg.split_bf16 = int(precision == "fp32-class")
     cfg.B, cfg.T = B, T
     hop = 1
     for s in scales:
@@ -91,11 +97,16 @@ def make_config(hp, B, T, c_pre_upsampled=False, dropout=None):
 class WaveNet(object):
     """B200 WaveNet (train path). Parameters live in ONE flat fp32 buffer in TensorFlow variable layouts."""
 
-    def __init__(self, hparams, B, T, device="cuda", c_pre_upsampled=False, dropout=None, training=True):
+    def __init__(self, hparams, B, T, device="cuda", c_pre_upsampled=False, dropout=None, training=True, precision="bf16"):
+        """precision: 'bf16' (training / benchmark path: bf16 operands and stored activations, fp32 accumulate) or 'fp32-class'
+        (forward + loss only: every activation and weight travels as a bf16 hi + lo pair, dropout forced off)."""
         self.hp = hparams
         self.lib = L.load()
         self.device = torch.device(device)
-        self.cfg = make_config(hparams, B, T, c_pre_upsampled, dropout)
+        self.precision = precision
+        if precision == "fp32-class":
+            dropout = 0.0
+        self.cfg = make_config(hparams, B, T, c_pre_upsampled, dropout, precision)
         self.training = training
         sz = WnSizes()
         L.check(self.lib.t2_wn_sizes(ctypes.byref(self.cfg), ctypes.byref(sz)))

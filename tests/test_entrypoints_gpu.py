@@ -57,8 +57,8 @@ def test_cli_workflow(tmp_path):
     assert os.path.isfile(os.path.join(log_dir, "taco_pretrained", "tacotron_model.ckpt-6.npz"))
     assert os.path.isfile(os.path.join(log_dir, "wave_pretrained", "wavenet_model.ckpt-6.npz"))
     gta_map = [l.strip().split("|") for l in open(os.path.join(base, "tacotron_output", "gta", "map.txt"))]
-    assert len(gta_map) == 12 and all(os.path.isfile(r[2]) for r in gta_map)
-    g = np.load(gta_map[0][2])
+    assert len(gta_map) == 12 and all(os.path.isfile(os.path.join(base, r[2])) for r in gta_map)     # paths relative to the run directory, as in the reference
+    g = np.load(os.path.join(base, gta_map[0][2]))
     assert g.shape == np.load(gta_map[0][1]).shape                      # GTA mels are frame-aligned with the ground truth
     # restart: everything is marked done, a second invocation resumes nothing and says so
     out = _run([os.path.join(ROOT, "train.py"), "--model", "Tacotron-2", "--tacotron_train_steps", "6", "--wavenet_train_steps", "6"] + common, base)

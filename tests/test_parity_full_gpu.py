@@ -149,10 +149,10 @@ def taco_batch(hp, B, T_in, T_out, seed):
     return inputs, lens, mel, stop
 
 
-def taco_compare(tag, hp, B, T_in, T_out, seed, tol, backward=True):
+def taco_compare(tag, hp, B, T_in, T_out, seed, tol, backward=True, precision="bf16"):
     params = ot.init_params(hp, seed=seed, random_bias=True)
     inputs, lens, mel, stop = taco_batch(hp, B, T_in, T_out, seed)
-    model = t2.tacotron.Tacotron(hp, B, T_in, T_out)
+    model = t2.tacotron.Tacotron(hp, B, T_in, T_out, precision=precision)
     model.load_params(params)
     model.forward(inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda(), training=True, seed=99)
     if backward:
@@ -182,6 +182,7 @@ def taco_compare(tag, hp, B, T_in, T_out, seed, tol, backward=True):
         rows, worst_rel, worst_cos = grad_report(model.export_grads(), grads_ref, min_norm=1e-6)
         vals["grad_worst_rel"], vals["grad_worst_cos"] = worst_rel, worst_cos
     m = record(tag, **vals)
+    model.measured = m
     assert m["align_max_err"] < tol["align"] and m["dec_l1"] < tol["dec_l1"] and m["mel_l1"] < tol["mel_l1"], m
     assert m["stop_max"] < tol["stop"], m
     for k in ("before", "after", "stop", "reg"):

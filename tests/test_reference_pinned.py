@@ -136,6 +136,23 @@ def test_oracle_mixture_loss_matches_reference_code():
     assert np.abs(s.numpy() - R["mol_sample"]).max() <= 1e-6
 
 
+def test_oracle_gaussian_head_matches_reference_code():
+    from oracle import wavenet as ow
+    gh, y = torch.from_numpy(R["gauss_yhat"]), torch.from_numpy(R["mol_y"])
+    for use_cdf in (1, 0):
+        got = ow.gaussian_maximum_likelihood_estimation_loss(gh, y, -7.0, 65536, use_cdf=bool(use_cdf), reduce=False).numpy()
+        ref = R["gauss_loss_cdf%d" % use_cdf]
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), use_cdf
+    hp = hparams.copy()
+    hp.parse("input_type=raw,quantize_channels=65536,out_channels=2,log_scale_min_gauss=-7.0,cdf_loss=False")
+    lens = torch.from_numpy(R["mol_lengths"])
+    assert abs(float(ow.masked_gaussian_loss(gh, y[:, :, 0], lens, hp)) - float(R["gauss_add_loss"])) <= 1e-5 * abs(float(R["gauss_add_loss"]))
+    hp.cdf_loss = True
+    assert abs(float(ow.masked_gaussian_loss(gh, y[:, :, 0], lens, hp)) - float(R["gauss_add_loss_cdf"])) <= 1e-5 * abs(float(R["gauss_add_loss_cdf"]))
+    s = ow.sample_from_gaussian(gh, -7.0, torch.from_numpy(R["gauss_normal"]))
+    assert np.abs(s.numpy() - R["gauss_sample"]).max() <= 1e-6
+
+
 def test_oracle_masked_cross_entropy_matches_reference_code():
     from oracle import wavenet as ow
     logits, tg = torch.from_numpy(R["ce_logits"]), torch.from_numpy(R["ce_targets"]).long()

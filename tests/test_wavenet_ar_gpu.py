@@ -80,6 +80,29 @@ def test_ar_teacher_forced_mol_raw(cs):
     assert (out.cpu() - ref).abs().max().item() < 1e-4
 
 
+def test_ar_teacher_forced_gaussian_raw():
+    """out_channels = 2: x = mean + exp(max(log_scale, min)) * n clipped to [-1, 1] (gaussian.py:39-52), normal draws injected"""
+    hp = _hp(input_type="raw", out_channels=2)
+    B, T = 2, 48
+    g = torch.Generator().manual_seed(24)
+    params = ow.init_params(hp, seed=24, random_bias=True)
+    w = (torch.rand(B, T, generator=g) * 2 - 1) * 0.8
+    c = torch.rand(B, 80, T // 16, generator=g)
+    y_par = ow.step(w.unsqueeze(1), c, params, hp).transpose(1, 2)   # [B, T, 2]
+    syn = t2.wavenet.WaveNetSynthesizer(hp, B, T, cluster_size=8)
+    syn.load_params(params)
+    ti = torch.cat([w[:, 1:], w[:, -1:]], dim=1).cuda()
+    n = torch.randn(B, T, generator=g)
+    out, raw = syn.generate(c.cuda(), w[:, 0].contiguous().cuda(), test_inputs=ti, u_b=n.cuda(), return_raw=True)
+    torch.cuda.synchronize()
+    err = (raw.cpu() - y_par).abs()
+    assert err.max().item() < 4e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
+    ref = ow.sample_from_gaussian(raw.cpu().transpose(1, 2), hp.log_scale_min_gauss, n)
+    assert (out.cpu() - ref).abs().max().item() < 1e-4
+    free = syn.generate(c.cuda(), w[:, 0].contiguous().cuda(), seed=3).cpu()      # Box-Muller draws from the counter hash
+    assert free.min() >= -1 and free.max() <= 1 and free.std() > 0
+
+
 def test_ar_free_running_is_deterministic_and_in_range():
     hp = _hp(input_type="mulaw-quantize", quantize_channels=256, out_channels=256)
     B, T = 5, 64

@@ -128,6 +128,14 @@ def test_mol_raw_non_legacy_convtranspose():
     _run(hp, B=3, T=256, seed=13, loss_tol=2e-3)
 
 
+@pytest.mark.parametrize("cdf", [False, True])
+def test_gaussian_head_raw(cdf):
+    """the reference's DEFAULT head (hparams.py:187: input_type='raw', out_channels=2): single Gaussian, log-density or CDF-difference
+    loss (wavenet_vocoder/models/gaussian.py:5-37), analytic gradient in the head epilogue"""
+    hp = _hp(input_type="raw", out_channels=2, cdf_loss=cdf, residual_channels=256, gate_channels=512, skip_out_channels=256)
+    _run(hp, B=2, T=256, seed=16, loss_tol=2e-3)
+
+
 def test_adam_step_matches_oracle():
     hp = _hp(input_type="mulaw-quantize", quantize_channels=256, out_channels=256)
     model, params = _run(hp, B=2, T=256, seed=14)

@@ -30,6 +30,9 @@ def run(input_type, B, cs, T=22000):
 
 if __name__ == "__main__":
     res = []
+    if len(sys.argv) > 1:          # profiling: one short run (python tools/bench_ar.py <T>)
+        print(json.dumps(run("mulaw-quantize", 1, 16, T=int(sys.argv[1]) // 275 * 275 or 275)), flush=True)
+        sys.exit(0)
     for it in ("mulaw-quantize", "raw"):
         for B, cs in ((1, 8), (1, 16), (20, 8), (20, 16)):
             r = run(it, B, cs)

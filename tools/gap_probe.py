@@ -46,13 +46,15 @@ prev_exit = None
 for i, name in enumerate(names):
     e, w, x_ = t[i, :, 8] - t0, t[i, :, 9] - t0, t[i, :, 10] - t0
     cyc = (t[i, :, 6] - t[i, :, 0])
+    ph = [(t[i, :, k + 1] - t[i, :, k]).mean().item() for k in range(6)]     # clock64 phases: setup, first stage, MMA issue, acc ready, epilogue, teardown
     rows.append({"launch": name, "entry_min_us": e.min().item() / 1e3, "entry_max_us": e.max().item() / 1e3,
                  "wait_done_min_us": w.min().item() / 1e3, "wait_done_max_us": w.max().item() / 1e3,
                  "exit_min_us": x_.min().item() / 1e3, "exit_max_us": x_.max().item() / 1e3,
                  "cta_life_us_mean": (x_ - e).mean().item() / 1e3, "cta_busy_us_mean": (x_ - w).mean().item() / 1e3,
                  "cta_cycles_mean": cyc.mean().item(),
                  "gap_prev_exit_to_wait_done_us": None if prev_exit is None else (w.min().item() - prev_exit) / 1e3,
-                 "n_sms": int(t[i, :, 11].unique().numel())})
+                 "n_sms": int(t[i, :, 11].unique().numel()), "phase_cycles": ph,
+                 "epi_start_after_entry_cycles": (t[i, :, 4] - t[i, :, 0]).mean().item()})
     prev_exit = x_.max().item()
 print("%-9s %9s %9s %9s %9s %9s %9s %8s %8s %8s" % ("launch", "entry_min", "entry_max", "wait_min", "wait_max", "exit_min", "exit_max", "busy", "gap", "period"))
 for i, r in enumerate(rows):
@@ -60,5 +62,9 @@ for i, r in enumerate(rows):
     print("%-9s %9.2f %9.2f %9.2f %9.2f %9.2f %9.2f %8.2f %8s %8.2f" % (
         r["launch"], r["entry_min_us"], r["entry_max_us"], r["wait_done_min_us"], r["wait_done_max_us"], r["exit_min_us"], r["exit_max_us"],
         r["cta_busy_us_mean"], "-" if r["gap_prev_exit_to_wait_done_us"] is None else "%.2f" % r["gap_prev_exit_to_wait_done_us"], period))
+print("\nclock64 phases (mean cycles per CTA): setup | wait first stage | MMA issue (all k-blocks) | last MMA -> accumulator ready | epilogue (first half start -> last half end; overlaps MMA issue when NT=2) | teardown")
+for r in rows:
+    if r["launch"] in ("gate05", "out05", "gate17", "out17", "skip", "final1", "ce_head", "dz17", "dx17", "dz05", "dx05"):
+        print("%-8s" % r["launch"], " ".join("%8.0f" % v for v in r["phase_cycles"]), " | epilogue starts %.0f cycles after entry, CTA %.0f cycles" % (r["epi_start_after_entry_cycles"], r["cta_cycles_mean"]))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/gap_probe.json", "w"), indent=1)

@@ -15,6 +15,6 @@ for _ in range(2):
     m.forward(x, c, x, ln); m.backward()
 torch.cuda.synchronize()
 out = {"lib": os.environ.get("T2_LIB", "default"), "cluster": os.environ.get("T2_CLUSTER", "1")}
-for which, tag in ((0, "gate"), (1, "out"), (2, "dz"), (3, "dx")):
+for which, tag in ((0, "gate"), (4, "gate_nostash"), (1, "out"), (2, "dz"), (3, "dx")):
     out[tag + "_us"] = round(1e3 * sum(m.time_kernel(which, l, reps=20) for l in (3, 9, 15)) / 3, 2)
 print(json.dumps(out))

@@ -79,12 +79,15 @@ class WaveNet(object):
         self.is_evaluating = not self.is_training and y is not None
         scalar = is_scalar_input(hp.input_type)
         if self.is_training or self.is_evaluating:
-            src = x if x is not None else y
-            if not scalar and src.dim() == 3:                       # one-hot float -> indices (feeder.py:295-306)
-                src = src.argmax(dim=1)
-            if scalar and src.dim() == 3:
-                src = src.squeeze(1) if src.shape[1] == 1 else src.squeeze(-1)
-            tgt = y.squeeze(-1) if y.dim() == 3 else y
+            tgt = y.squeeze(-1) if y.dim() == 3 else y              # targets [B, T, 1] (feeder.py:308-317) or [B, T]
+            if x is None:                                           # evaluation: the targets are also the teacher-forcing inputs
+                src = tgt
+            elif not scalar and x.dim() == 3:                       # one-hot float [B, Q, T] -> indices (feeder.py:295-306)
+                src = x.argmax(dim=1)
+            elif scalar and x.dim() == 3:                           # [B, 1, T]
+                src = x.squeeze(1)
+            else:
+                src = x
             xin = src.float().contiguous() if scalar else src.int().contiguous()
             tin = tgt.float().contiguous() if scalar else tgt.int().contiguous()
             B, T = xin.shape
