@@ -161,6 +161,10 @@ typedef struct {
   int split_bf16;            /* 1 = "fp32-class" convolution stacks: the embedding, the encoder conv blocks + the BiLSTM input projection and
                               * the postnet conv blocks + projection run on bf16 hi + lo operand pairs with fp32 pre-batch-norm activations
                               * (forward / losses only). The recurrences (LSTMs, attention) keep bf16 operands / fp32 state. */
+  int mask_decoder;          /* 1 = masked losses (tacotron/models/modules.py:412-455): MSE terms over the frames t < targets_lengths[b]
+                              * (sum / count_nonzero of the mask), stop-token loss = weighted sigmoid CE over the same frames divided by the
+                              * number of NON-ZERO masked terms; the lengths come from t2_taco_set_target_lengths */
+  float cross_entropy_pos_weight;  /* pos_weight of tf.nn.weighted_cross_entropy_with_logits (masked stop-token loss only) */
 } t2_taco_config_t;
 
 int t2_taco_sizes(const t2_taco_config_t* cfg, long long* n_params, long long* packed_bytes, long long* workspace_bytes,
@@ -177,6 +181,9 @@ int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, const void* d_
                     const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets,
                     const float* d_stop_targets, float* d_loss, int training, unsigned long long seed,
                     const unsigned long long* d_step, void* stream);
+/* mask_decoder = 1: copies the B target lengths (device int32) into the workspace; call before t2_taco_forward (stream-ordered,
+ * capturable). Replaces the `targets_lengths` placeholder of tacotron/models/tacotron.py:28 / tacotron/feeder.py:207. */
+int t2_taco_set_target_lengths(const t2_taco_config_t* cfg, void* d_workspace, const int* d_target_lengths, void* stream);
 /* backward of the last t2_taco_forward(training=1): d(total loss)/d(theta) into the flat gradient buffer (non-trainable
  * batch-norm moving statistics get 0) */
 int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,

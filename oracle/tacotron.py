@@ -333,8 +333,28 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
             "alignments": torch.stack(aligns, dim=1)}
 
 
-def loss_fn(out, mel_targets, stop_targets, params, hp):
-    """tacotron.py:315-354 with mask_decoder=False: plain means over padded tensors + L2 regulariser."""
+def masked_mse(targets, outputs, targets_lengths):
+    """MaskedMSE (modules.py:412-431): tf.losses.mean_squared_error(weights = mask) = sum(mask (t - o)^2) / count_nonzero(mask)."""
+    mask = (torch.arange(targets.shape[1])[None, :] < targets_lengths[:, None]).float().unsqueeze(-1) * torch.ones_like(targets)
+    return (mask * (targets - outputs) ** 2).sum() / torch.count_nonzero(mask).float()
+
+
+def masked_sigmoid_cross_entropy(targets, outputs, targets_lengths, pos_weight):
+    """MaskedSigmoidCrossEntropy (modules.py:433-455): weighted CE, masked, divided by the number of NON-ZERO masked terms."""
+    mask = (torch.arange(targets.shape[1])[None, :] < targets_lengths[:, None]).float()
+    losses = (1 - targets) * outputs + (1 + (pos_weight - 1) * targets) * (torch.log1p(torch.exp(-outputs.abs())) + torch.clamp(-outputs, min=0))
+    masked = losses * mask
+    return masked.sum() / torch.count_nonzero(masked).float()
+
+
+def loss_fn(out, mel_targets, stop_targets, params, hp, targets_lengths=None):
+    """tacotron.py:297-354: plain means over padded tensors (mask_decoder=False) or the masked variants, + L2 regulariser."""
+    if hp.mask_decoder:
+        before = masked_mse(mel_targets, out["decoder_output"], targets_lengths)
+        after = masked_mse(mel_targets, out["mel_outputs"], targets_lengths)
+        stop = masked_sigmoid_cross_entropy(stop_targets, out["stop_logits"], targets_lengths, hp.cross_entropy_pos_weight)
+        reg = sum((v * v).sum() / 2 for k, v in params.items() if is_regularized(k)) * hp.tacotron_reg_weight
+        return before + after + stop + reg, {"before": before, "after": after, "stop": stop, "reg": reg}
     before = F.mse_loss(out["decoder_output"], mel_targets)
     after = F.mse_loss(out["mel_outputs"], mel_targets)
     stop = F.binary_cross_entropy_with_logits(out["stop_logits"], stop_targets)
@@ -351,10 +371,10 @@ def learning_rate(hp, global_step):
     return min(max(lr, hp.tacotron_final_learning_rate), hp.tacotron_initial_learning_rate)
 
 
-def train_step(params, inputs, input_lengths, mel_targets, stop_targets, hp, masks=None):
+def train_step(params, inputs, input_lengths, mel_targets, stop_targets, hp, masks=None, targets_lengths=None):
     ps = {k: (v.clone().requires_grad_(True) if is_trainable(k) else v.clone()) for k, v in params.items()}
     out = forward(ps, inputs, input_lengths, mel_targets, hp, True, masks)
-    loss, parts = loss_fn(out, mel_targets, stop_targets, ps, hp)
+    loss, parts = loss_fn(out, mel_targets, stop_targets, ps, hp, targets_lengths)
     names = [k for k in ps if is_trainable(k)]
     gr = torch.autograd.grad(loss, [ps[k] for k in names], allow_unused=True)
     grads = {k: (g if g is not None else torch.zeros_like(ps[k])) for k, g in zip(names, gr)}

@@ -58,7 +58,7 @@ struct TL {  // layout
   // workspace (bytes)
   long long w_emb, w_encpre[2], w_ench[2], w_encc[2], w_encg[2], w_enct[2], w_memory, w_values, w_keys, w_decin, w_pn1, w_pn2;
   long long w_pre1, w_S1, w_S2, w_PI, w_c1, w_c2, w_g1, w_g2, w_t1, w_t2, w_cum, w_alpha, w_projo, w_decbm, w_decf, w_stop;
-  long long w_resid, w_mel, w_scal, w_zero;
+  long long w_resid, w_mel, w_scal, w_zero, w_tlen;
   // backward
   long long w_dmel, w_dY, w_ddec_tm, w_dPI, w_dh1ext, w_dh2ext, w_dhs1, w_dhs2, w_dcs1, w_dcs2, w_dg1, w_dg2, w_dgstep;
   long long w_dctxl, w_dctx_all, w_dq_all, w_dcum, w_cumrun, w_dkeys, w_dvalues, w_attacc, w_dpn2, w_dpn1;
@@ -244,6 +244,7 @@ int build(const t2_taco_config_t* cfg, TL& lo, std::vector<PJ>* jobs_out) {
   lo.w_projo = takeb(To * B * 128 * 4);
   lo.w_decbm = takeb(split ? B * To * 256 * 2 : B * To * lo.M * 2);     /* split: [hi(M) padded to 128 | lo(M) padded to 128] */ lo.w_decf = takeb(B * To * lo.M * 4); lo.w_stop = takeb(B * To * 4);
   for (auto& L : lo.post) conv_ws(L, To);
+  lo.w_tlen = takeb(B * 4);
   lo.w_resid = takeb(B * To * 128 * 4); lo.w_mel = takeb(B * To * lo.M * 4);
   lo.w_scal = takeb(64 * 4);
   // backward
@@ -699,11 +700,12 @@ __global__ void __launch_bounds__(kAttThreads) att_fwd_kernel(AttArgs a) {
 // loss sums: scal[0] += sum (dec - tgt)^2, scal[2] += sum BCE(stop)
 __global__ void dec_finish_kernel(const float* __restrict__ projo, const float* __restrict__ tgt, const float* __restrict__ stop_tgt,
                                   bf16* __restrict__ dec_bm, float* __restrict__ dec_f, float* __restrict__ stop, float* __restrict__ scal,
-                                  int B, int To, int M, int clip, float lo, float hi, int split) {
+                                  int B, int To, int M, int clip, float lo, float hi, int split, const int* __restrict__ tlen, float pos_w) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  float l0 = 0.f, l2 = 0.f;
+  float l0 = 0.f, l2 = 0.f, nz = 0.f;
   if (e < (long long)B * To * (M + 1)) {
     const int m = int(e % (M + 1)), t = int((e / (M + 1)) % To), b = int(e / ((long long)(M + 1) * To));
+    const bool live = !tlen || t < tlen[b];     // mask_decoder: frames past the target length do not count
     const float v = projo[((long long)t * B + b) * 128 + m];
     if (m < M) {
       const float d = clip ? fminf(fmaxf(v, lo), hi) : v;
@@ -715,18 +717,30 @@ __global__ void dec_finish_kernel(const float* __restrict__ projo, const float* 
         bf16* row = dec_bm + ((long long)b * To + t) * 256 + m;
         row[0] = h; row[128] = __float2bfloat16(d - __bfloat162float(h));
       }
-      if (tgt) { const float df = d - tgt[o]; l0 = df * df; }
+      if (tgt && live) { const float df = d - tgt[o]; l0 = df * df; }
     } else {
       stop[(long long)b * To + t] = v;
-      if (stop_tgt) { const float z = stop_tgt[(long long)b * To + t]; l2 = fmaxf(v, 0.f) - v * z + log1pf(__expf(-fabsf(v))); }
+      if (stop_tgt) {
+        const float z = stop_tgt[(long long)b * To + t];
+        if (!tlen) l2 = fmaxf(v, 0.f) - v * z + log1pf(__expf(-fabsf(v)));
+        else if (live) {   // tf.nn.weighted_cross_entropy_with_logits, then / count_nonzero(masked loss) (modules.py:450-455)
+          l2 = (1.f - z) * v + (1.f + (pos_w - 1.f) * z) * (log1pf(__expf(-fabsf(v))) + fmaxf(-v, 0.f));
+          nz = l2 != 0.f ? 1.f : 0.f;
+        }
+      }
     }
   }
-  l0 = warp_sum(l0); l2 = warp_sum(l2);
-  if ((threadIdx.x & 31) == 0) { if (l0 != 0.f) atomicAdd(scal + 0, l0); if (l2 != 0.f) atomicAdd(scal + 2, l2); }
+  l0 = warp_sum(l0); l2 = warp_sum(l2); nz = warp_sum(nz);
+  if ((threadIdx.x & 31) == 0) {
+    if (l0 != 0.f) atomicAdd(scal + 0, l0);
+    if (l2 != 0.f) atomicAdd(scal + 2, l2);
+    if (nz != 0.f) atomicAdd(scal + 4, nz);
+  }
 }
 // mel = clip(dec + residual); scal[1] += sum (mel - tgt)^2
 __global__ void mel_finish_kernel(const float* __restrict__ dec_f, const float* __restrict__ resid, const float* __restrict__ tgt,
-                                  float* __restrict__ mel, float* __restrict__ scal, long long npos, int M, int clip, float lo, float hi) {
+                                  float* __restrict__ mel, float* __restrict__ scal, long long npos, int M, int clip, float lo, float hi,
+                                  const int* __restrict__ tlen, int To) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   float l = 0.f;
   if (e < npos * M) {
@@ -734,7 +748,7 @@ __global__ void mel_finish_kernel(const float* __restrict__ dec_f, const float* 
     float v = dec_f[e] + resid[pos * 128 + m];
     if (clip) v = fminf(fmaxf(v, lo), hi);
     mel[e] = v;
-    if (tgt) { const float d = v - tgt[e]; l = d * d; }
+    if (tgt && (!tlen || int(pos % To) < tlen[pos / To])) { const float d = v - tgt[e]; l = d * d; }
   }
   l = warp_sum(l);
   if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(scal + 1, l);
@@ -755,8 +769,16 @@ __global__ void proj_bias_kernel(float* p, const float* fb, const float* sb, lon
   const int m = int(e % (M + 1));
   p[(e / (M + 1)) * 128 + m] += m < M ? fb[m] : sb[0];
 }
-__global__ void loss_norm_kernel(const float* s, float* out, float n_mel, float n_stop, float regw) {
-  out[0] = s[0] / n_mel; out[1] = s[1] / n_mel; out[2] = s[2] / n_stop; out[3] = s[3] * regw;
+// normalisers -> s[5] (mel terms), s[6] (stop term); out (nullable) = the four normalised loss terms
+__global__ void loss_norm_kernel(float* s, float* out, float n_mel, float n_stop, float regw, const int* tlen, int B, int To, int M) {
+  if (tlen) {
+    float frames = 0.f;
+    for (int b = 0; b < B; ++b) frames += float(tlen[b] < To ? tlen[b] : To);
+    n_mel = fmaxf(frames * float(M), 1.f);      // count_nonzero of the broadcast mask (tf.losses.mean_squared_error weights)
+    n_stop = fmaxf(s[4], 1.f);                  // count_nonzero of the masked stop-token losses
+  }
+  s[5] = n_mel; s[6] = n_stop;
+  if (out) { out[0] = s[0] / n_mel; out[1] = s[1] / n_mel; out[2] = s[2] / n_stop; out[3] = s[3] * regw; }
 }
 
 // generic helper: 1x1 / k-tap conv GEMM through the engine
@@ -899,14 +921,16 @@ void build_tiles(const TL& lo, std::vector<WgL>& L) {
 // loss seeds: dmel = 2 (mel - tgt) / N * [not clipped] (bf16, 128-col padded) ; ddec_direct = dmel + 2 (dec - tgt) / N
 __global__ void loss_seed_kernel(const float* __restrict__ dec_f, const float* __restrict__ resid, const float* __restrict__ mel,
                                  const float* __restrict__ tgt, bf16* __restrict__ dmel, float* __restrict__ ddec, long long npos, int M,
-                                 int clip, float lo, float hi) {
+                                 int clip, float lo, float hi, const int* __restrict__ tlen, int To, const float* __restrict__ scal) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= npos * 128) return;
   const long long pos = e / 128; const int m = int(e % 128);
   float g = 0.f;
+  if (m < M && tlen && int(pos % To) >= tlen[pos / To]) ddec[pos * M + m] = 0.f;     // masked frame: no loss gradient
+  else
   if (m < M) {
     const long long o = pos * M + m;
-    const float n = float(npos * M);
+    const float n = scal[5];
     const float raw = dec_f[o] + resid[pos * 128 + m];
     g = 2.f * (mel[o] - tgt[o]) / n;
     if (clip && (raw < lo || raw > hi)) g = 0.f;
@@ -916,7 +940,8 @@ __global__ void loss_seed_kernel(const float* __restrict__ dec_f, const float* _
 }
 // ddec_tm[t][b][0..M) = (ddec_direct + ddec_post)[b][t][:] * [decoder clip inactive] ; col M = d BCE / d stop logit
 __global__ void ddec_tm_kernel(const float* __restrict__ ddec, const bf16* __restrict__ dpost, const float* __restrict__ projo,
-                               const float* __restrict__ stop_tgt, bf16* __restrict__ out, int B, int To, int M, int clip, float lo, float hi) {
+                               const float* __restrict__ stop_tgt, bf16* __restrict__ out, int B, int To, int M, int clip, float lo, float hi,
+                               const int* __restrict__ tlen, float pos_w, const float* __restrict__ scal) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= (long long)To * B * 128) return;
   const int m = int(e % 128), b = int((e / 128) % B), t = int(e / (128LL * B));
@@ -928,7 +953,9 @@ __global__ void ddec_tm_kernel(const float* __restrict__ ddec, const bf16* __res
     if (clip && (raw < lo || raw > hi)) g = 0.f;
   } else if (m == M) {
     const float x = projo[((long long)t * B + b) * 128 + M];
-    g = (1.f / (1.f + __expf(-x)) - stop_tgt[(long long)b * To + t]) / float((long long)B * To);
+    const float z = stop_tgt[(long long)b * To + t];
+    if (!tlen) g = (1.f / (1.f + __expf(-x)) - z) / scal[6];
+    else if (t < tlen[b]) g = ((1.f - z) - (1.f + (pos_w - 1.f) * z) / (1.f + __expf(x))) / scal[6];     // d/dx of the weighted CE
   }
   out[e] = __float2bfloat16(g);
 }
@@ -1527,6 +1554,7 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   const int B = lo.B, Ti = lo.Ti, To = lo.To, H = lo.H, D = lo.D;
   float* scal = reinterpret_cast<float*>(ws + lo.w_scal);
   T2_CHECK_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(float), st));
+  const int* tlen = lo.c.mask_decoder ? reinterpret_cast<const int*>(ws + lo.w_tlen) : nullptr;     // t2_taco_set_target_lengths
   rc = encoder_fwd(s, d_inputs, d_input_lengths, training);
   if (rc) return rc;
   const void* x = nullptr;
@@ -1567,7 +1595,7 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
   float* dec_f = reinterpret_cast<float*>(ws + lo.w_decf);
   dec_finish_kernel<<<g1((long long)B * To * (lo.M + 1)), 256, 0, st>>>(projo, d_mel_targets, d_stop_targets, dec_bm, dec_f,
                                                                         reinterpret_cast<float*>(ws + lo.w_stop), scal, B, To, lo.M,
-                                                                        lo.c.clip_outputs, lo_c, hi_c, lo.c.split_bf16); t2_count_launch();
+                                                                        lo.c.clip_outputs, lo_c, hi_c, lo.c.split_bf16, tlen, lo.c.cross_entropy_pos_weight); t2_count_launch();
   // ---- postnet ----
   x = dec_bm;
   for (auto& L : lo.post) { rc = conv_block_fwd(s, L, x, To, training); if (rc) return rc; x = ws + L.w_x; }
@@ -1576,12 +1604,11 @@ extern "C" int t2_taco_forward(const t2_taco_config_t* cfg, float* d_params, con
                  0.f, 0, 0, nullptr, st, lo.c.split_bf16);
   if (rc) return rc;
   mel_finish_kernel<<<g1((long long)B * To * lo.M), 256, 0, st>>>(dec_f, resid, d_mel_targets, reinterpret_cast<float*>(ws + lo.w_mel), scal,
-                                                                  (long long)B * To, lo.M, lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
+                                                                  (long long)B * To, lo.M, lo.c.clip_outputs, lo_c, hi_c, tlen, To); t2_count_launch();
   reg_loss_kernel<<<dim3(8, lo.n_reg), 256, 0, st>>>(d_params, reinterpret_cast<const long long*>(ws + lo.w_regtab), lo.n_reg, scal); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
-  if (d_loss) {
-    loss_norm_kernel<<<1, 1, 0, st>>>(scal, d_loss, float((long long)B * To * lo.M), float((long long)B * To), lo.c.reg_weight); t2_count_launch();
-  }
+  loss_norm_kernel<<<1, 1, 0, st>>>(scal, d_loss, float((long long)B * To * lo.M), float((long long)B * To), lo.c.reg_weight, tlen, B, To, lo.M);
+  t2_count_launch();
   return T2_OK;
 }
 
@@ -1691,7 +1718,7 @@ extern "C" int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params
   float* dec_f = reinterpret_cast<float*>(ws + lo.w_decf);
   dec_finish_kernel<<<g1((long long)B * T_used * (lo.M + 1)), 256, 0, st>>>(reinterpret_cast<float*>(ws + lo.w_projo), nullptr, nullptr, dec_bm, dec_f,
                                                                             reinterpret_cast<float*>(ws + lo.w_stop), scal, B, T_used, lo.M,
-                                                                            lo.c.clip_outputs, lo_c, hi_c, lo.c.split_bf16); t2_count_launch();
+                                                                            lo.c.clip_outputs, lo_c, hi_c, lo.c.split_bf16, nullptr, 1.f); t2_count_launch();
   const void* x = dec_bm;
   for (auto& L : lo.post) { rc = conv_block_fwd(s, L, x, T_used, 0); if (rc) return rc; x = ws + L.w_x; }
   float* resid = reinterpret_cast<float*>(ws + lo.w_resid);
@@ -1699,7 +1726,7 @@ extern "C" int t2_taco_infer_finish(const t2_taco_config_t* cfg, float* d_params
                  0.f, 0, 0, nullptr, st, lo.c.split_bf16);
   if (rc) return rc;
   mel_finish_kernel<<<g1((long long)B * T_used * lo.M), 256, 0, st>>>(dec_f, resid, nullptr, reinterpret_cast<float*>(ws + lo.w_mel), scal,
-                                                                      (long long)B * T_used, lo.M, lo.c.clip_outputs, lo_c, hi_c); t2_count_launch();
+                                                                      (long long)B * T_used, lo.M, lo.c.clip_outputs, lo_c, hi_c, nullptr, T_used); t2_count_launch();
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
@@ -1744,6 +1771,16 @@ extern "C" int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_wor
   return t2_set_error(T2_ERR_INVALID_ARG, "unknown workspace tensor '%s'", name);
 }
 
+extern "C" int t2_taco_set_target_lengths(const t2_taco_config_t* cfg, void* d_workspace, const int* d_target_lengths, void* stream) {
+  TL lo;
+  int rc = build(cfg, lo, nullptr);
+  if (rc) return rc;
+  T2_REQUIRE(d_target_lengths != nullptr, T2_ERR_INVALID_ARG, "null target lengths");
+  T2_CHECK_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d_workspace) + lo.w_tlen, d_target_lengths, lo.B * sizeof(int), cudaMemcpyDeviceToDevice,
+                                static_cast<cudaStream_t>(stream)));
+  return T2_OK;
+}
+
 // backward of the last t2_taco_forward(training=1): writes d(total loss)/d(theta) for every trainable tensor
 extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
                                 const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets, const float* d_stop_targets,
@@ -1774,10 +1811,12 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   bf16* dmel = reinterpret_cast<bf16*>(ws + lo.w_dmel);
   float* ddecf = reinterpret_cast<float*>(ws + lo.w_ddecf);
   bf16* dec_bm = reinterpret_cast<bf16*>(ws + lo.w_decbm);
+  const int* tlen = lo.c.mask_decoder ? reinterpret_cast<const int*>(ws + lo.w_tlen) : nullptr;
+  const float* scal = reinterpret_cast<const float*>(ws + lo.w_scal);      // [5], [6]: the loss normalisers of the forward pass
   // ---- loss seeds + postnet ----
   loss_seed_kernel<<<g1(BTo * 128), 256, 0, st>>>(reinterpret_cast<float*>(ws + lo.w_decf), reinterpret_cast<float*>(ws + lo.w_resid),
                                                   reinterpret_cast<float*>(ws + lo.w_mel), d_mel_targets, dmel, ddecf, BTo, M, lo.c.clip_outputs,
-                                                  lo_c, hi_c); t2_count_launch();
+                                                  lo_c, hi_c, tlen, To, scal); t2_count_launch();
   rc = conv_gemm(dmel, 128, To, B, pk + lo.k_ppT, lo.PC, 128, 1, nullptr, lo.PC % 256 == 0 ? 256 : 128, nullptr, 0, dY0, nullptr, lo.PC, lo.PC, 0.f, 0, 0,
                  nullptr, st);
   if (rc) return rc;
@@ -1796,7 +1835,8 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   // ---- projections ----
   bf16* ddec_tm = reinterpret_cast<bf16*>(ws + lo.w_ddec_tm);
   float* projo = reinterpret_cast<float*>(ws + lo.w_projo);
-  ddec_tm_kernel<<<g1(TB * 128), 256, 0, st>>>(ddecf, ddec_post, projo, d_stop_targets, ddec_tm, B, To, M, lo.c.clip_outputs, lo_c, hi_c);
+  ddec_tm_kernel<<<g1(TB * 128), 256, 0, st>>>(ddecf, ddec_post, projo, d_stop_targets, ddec_tm, B, To, M, lo.c.clip_outputs, lo_c, hi_c, tlen,
+                                               lo.c.cross_entropy_pos_weight, scal);
   t2_count_launch();
   float* dPI = reinterpret_cast<float*>(ws + lo.w_dPI);
   rc = conv_gemm(ddec_tm, 128, TB, 1, pk + lo.k_projT, PIK, 128, 1, nullptr, PIK % 256 == 0 ? 256 : 128, nullptr, 0, nullptr, dPI, PIK, PIK, 0.f, 0, 0,

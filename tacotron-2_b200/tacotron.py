@@ -16,7 +16,7 @@ class TacoConfig(ctypes.Structure):
         "enc_conv_channels", "encoder_lstm_units", "attention_dim", "attention_filters", "attention_kernel", "prenet1",
         "prenet2", "decoder_lstm_units", "postnet_layers", "postnet_kernel", "postnet_channels", "clip_outputs")] + [
         (n, ctypes.c_float) for n in ("dropout_rate", "zoneout_rate", "reg_weight", "max_abs_value", "lower_bound_decay")] + [
-        ("split_bf16", ctypes.c_int)]
+        ("split_bf16", ctypes.c_int), ("mask_decoder", ctypes.c_int), ("cross_entropy_pos_weight", ctypes.c_float)]
 
 
 def unsupported_hparams(hp):
@@ -28,7 +28,6 @@ def unsupported_hparams(hp):
             bad.append("%s=%r (%s)" % (name, getattr(hp, name), why))
     need("outputs_per_step", lambda v: v == 1, "reduction factor r > 1: tacotron.py:141-143, helpers.py:77")
     need("predict_linear", lambda v: not v, "CBHG post-processing net + linear loss: tacotron.py:203-219, modules.py:19-78")
-    need("mask_decoder", lambda v: not v, "masked losses: modules.py:412-455")
     need("prenet_layers", lambda v: len(v) == 2, "2 prenet layers")
     need("decoder_layers", lambda v: v == 2, "2 decoder LSTM layers")
     need("smoothing", lambda v: not v, "smoothing normalisation instead of softmax: attention.py:72-92")
@@ -38,7 +37,8 @@ def unsupported_hparams(hp):
     need("tacotron_teacher_forcing_mode", lambda v: v == "constant", "scheduled teacher forcing: helpers.py:135-169")
     need("tacotron_teacher_forcing_ratio", lambda v: float(v) == 1.0, "per-step teacher-forcing draw: helpers.py:121-124")
     need("tacotron_fine_tuning", lambda v: not v, "frozen embedding / encoder variables: tacotron.py:401")
-    need("cross_entropy_pos_weight", lambda v: float(v) == 1.0, "weighted stop-token loss only exists in the masked loss path")
+    if not getattr(hp, "mask_decoder", False):
+        need("cross_entropy_pos_weight", lambda v: float(v) == 1.0, "the weighted stop-token loss only exists in the masked loss path")
     return bad
 
 
@@ -64,6 +64,8 @@ def make_config(hp, B, T_in, T_out, precision="bf16"):
     c.dropout_rate, c.zoneout_rate, c.reg_weight = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate, reg_weight
     c.max_abs_value, c.lower_bound_decay = hp.max_abs_value, hp.lower_bound_decay
     c.split_bf16 = int(precision == "fp32-class")
+    c.mask_decoder = int(bool(hp.mask_decoder))
+    c.cross_entropy_pos_weight = float(hp.cross_entropy_pos_weight)
     return c
 
 
@@ -125,9 +127,14 @@ class Tacotron(object):
         L.check(self.lib.t2_taco_pack_weights(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace), L.stream_ptr()))
         self._dirty = False
 
-    def forward(self, inputs, input_lengths, mel_targets, stop_targets, training=True, seed=None):
+    def forward(self, inputs, input_lengths, mel_targets, stop_targets, training=True, seed=None, targets_lengths=None):
+        """targets_lengths: int32 [B] device tensor, required when hparams.mask_decoder (masked losses, modules.py:412-455)"""
         if self._dirty:
             self.pack()
+        if self.cfg.mask_decoder:
+            if targets_lengths is None:
+                raise L.T2Error("Model set to mask paddings but no targets lengths provided for the mask!")
+            L.check(self.lib.t2_taco_set_target_lengths(ctypes.byref(self.cfg), L.ptr(self.workspace), L.ptr(targets_lengths), L.stream_ptr()))
         self._last = (inputs, input_lengths, mel_targets, stop_targets)
         self._last_seed = self.seed if seed is None else seed
         L.check(self.lib.t2_taco_forward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace),

@@ -6,7 +6,7 @@ otherwise), `add_loss()` publishes the four loss terms, `add_optimizer(global_st
 + clip_by_global_norm + Adam. Attribute names read by tacotron/train.py and tacotron/synthesizer.py are kept
 (`tower_mel_outputs`, `tower_alignments`, `tower_stop_token_prediction`, `tower_decoder_output`, `loss`,
 `before_loss`, `after_loss`, `stop_token_loss`, `regularization_loss`, `learning_rate`, `gradients`). One process per
-GPU replaces the towers. predict_linear / CBHG, outputs_per_step > 1 and mask_decoder are out of scope."""
+GPU replaces the towers. predict_linear / CBHG and outputs_per_step > 1 are not implemented."""
 import collections
 
 import torch
@@ -72,7 +72,7 @@ class Tacotron(object):
         if is_training and is_evaluating:
             raise RuntimeError("Model can not be in training and evaluation modes at the same time!")
         if hp.predict_linear or hp.outputs_per_step != 1 or hp.mask_decoder:
-            raise NotImplementedError("predict_linear / outputs_per_step > 1 / mask_decoder are out of scope (SURVEY.md §8)")
+            raise NotImplementedError("predict_linear / outputs_per_step > 1 are out of scope (SURVEY.md §8)")
         self.is_training, self.is_evaluating, self.gta = is_training, is_evaluating, gta
         B, T_in = inputs.shape
         ids, lens = inputs.int().contiguous(), input_lengths.int().contiguous()
@@ -83,7 +83,8 @@ class Tacotron(object):
                 eng.global_step = int(global_step)
             stop = stop_token_targets if stop_token_targets is not None else torch.zeros(B, T_out, device=inputs.device)
             eng.step_dev.add_(1)
-            eng.forward(ids, lens, mel_targets.float().contiguous(), stop.float().contiguous(), training=is_training)
+            eng.forward(ids, lens, mel_targets.float().contiguous(), stop.float().contiguous(), training=is_training,
+                        targets_lengths=targets_lengths.int().contiguous() if (hp.mask_decoder and targets_lengths is not None) else None)
             M = hp.num_mels
             self.tower_decoder_output = [eng.workspace_tensor("decoder_output", (B, T_out, M))]
             self.tower_mel_outputs = [eng.workspace_tensor("mel_outputs", (B, T_out, M))]
@@ -106,7 +107,7 @@ class Tacotron(object):
         return self
 
     def add_loss(self):
-        """tacotron.py:273-369 (mask_decoder = False): MSE before + MSE after + stop-token CE + L2 regulariser."""
+        """tacotron.py:273-369: MSE before + MSE after + stop-token CE (masked variants when hparams.mask_decoder) + L2 regulariser."""
         b = self._eng.loss_buf
         self.tower_before_loss, self.tower_after_loss = [b[0]], [b[1]]
         self.tower_stop_token_loss, self.tower_regularization_loss = [b[2]], [b[3]]

@@ -6,9 +6,10 @@ paths (dropout / zoneout masks rebuilt from the library's counter hash and injec
   Cfg-3'  Tacotron full widths (512 / 1024 / 512), B = 32, T_in = 160, T_out = 200, conv dropout 0.5, prenet dropout 0.5,
           zoneout 0.1 all ON with the same masks on both sides
 
-Tolerances are <= 2x the errors measured on B200 (profiles/r02_measured_parity.jsonl); the product runs bf16 GEMM operands /
-bf16-stored activations with fp32 accumulation, the oracle fp32 end to end. The 1e-3 north-star figures are LOSS
-(CE / MoL NLL) and mel-L1 parity; both are asserted at 1e-3 or tighter here."""
+Tolerances are <= 2x the errors measured on B200 (profiles/r02_measured_parity.jsonl: logits max 1.8e-3 / mean 2.8e-4, CE error 8e-6,
+MoL NLL error 6e-5, alignments 3e-4, decoder-output L1 8e-4, stop logits 2.4e-3, mel-L1 on the post-net output 2.8e-2); the product
+runs bf16 GEMM operands / bf16-stored activations with fp32 accumulation here, the oracle fp32 end to end. The north-star 1e-3 figures
+are met by the losses in this mode and by logits / mel-L1 in the fp32-class mode (tests/test_precision_modes_gpu.py)."""
 import math
 
 import pytest
@@ -86,7 +87,7 @@ def _wn_compare(tag, hp, B, T, seed, tol):
 def test_wavenet_cfg2_full_shape_ce():
     hp = _wn_hp("input_type=mulaw-quantize,quantize_channels=256,out_channels=256")
     _wn_compare("wavenet_cfg2_24L_2x7680_ce", hp, 2, 7680, 21,
-                dict(loss=1e-3, logits_max=4e-2, logits_mean=6e-3, grad_rel=0.15, grad_cos=0.985))
+                dict(loss=1e-4, logits_max=4e-3, logits_mean=6e-4, grad_rel=0.15, grad_cos=0.99))
 
 
 def test_wavenet_cfg2_full_shape_ce_dropout_masks():
@@ -94,13 +95,13 @@ def test_wavenet_cfg2_full_shape_ce_dropout_masks():
     and injected into the oracle (wavenet_vocoder/models/modules.py:483-484)."""
     hp = _wn_hp("input_type=mulaw-quantize,quantize_channels=256,out_channels=256,wavenet_dropout=0.05")
     _wn_compare("wavenet_cfg2_24L_2x7680_ce_dropout", hp, 2, 7680, 22,
-                dict(loss=1e-3, logits_max=4e-2, logits_mean=6e-3, grad_rel=0.15, grad_cos=0.985))
+                dict(loss=1e-4, logits_max=4e-3, logits_mean=6e-4, grad_rel=0.15, grad_cos=0.99))
 
 
 def test_wavenet_cfg4_shape_mol():
     hp = _wn_hp("input_type=raw,quantize_channels=65536,out_channels=30")
     _wn_compare("wavenet_cfg4_24L_2x4096_mol", hp, 2, 4096, 23,
-                dict(loss=2e-3, logits_max=4e-2, logits_mean=6e-3, grad_rel=0.15, grad_cos=0.985))
+                dict(loss=2e-4, logits_max=4e-3, logits_mean=6e-4, grad_rel=0.05, grad_cos=0.999))
 
 
 # ------------------------------------------------------------------------------------------------ Tacotron
@@ -212,7 +213,7 @@ def test_tacotron_training_mode_stochastic_paths_small():
     hp = _taco_small_hp()
     assert hp.tacotron_dropout_rate == 0.5 and hp.tacotron_zoneout_rate == 0.1
     taco_compare("tacotron_small_stochastic_B4", hp, 4, 48, 40, 51,
-                 dict(align=2e-2, dec_l1=1e-2, mel_l1=4e-2, stop=5e-2, loss=2e-3, grad_rel=0.25, grad_cos=0.97))
+                 dict(align=6e-4, dec_l1=1.6e-3, mel_l1=4e-2, stop=5e-3, loss=2e-3, grad_rel=0.25, grad_cos=0.97))
 
 
 def test_tacotron_mask_statistics():
@@ -232,11 +233,11 @@ def test_tacotron_cfg3_full_width_B32_stochastic():
     hp = hparams.copy()
     hp.parse("predict_linear=False")
     taco_compare("tacotron_cfg3_fullwidth_B32_Tin160_Tout200_stochastic", hp, 32, 160, 200, 52,
-                 dict(align=2e-2, dec_l1=1e-2, mel_l1=4e-2, stop=5e-2, loss=2e-3, grad_rel=0.25, grad_cos=0.97))
+                 dict(align=6e-4, dec_l1=1.6e-3, mel_l1=4e-2, stop=5e-3, loss=2e-3, grad_rel=0.25, grad_cos=0.97))
 
 
 def test_tacotron_cfg3_full_width_B32_deterministic():
     hp = hparams.copy()
     hp.parse("predict_linear=False,tacotron_dropout_rate=0.0,tacotron_zoneout_rate=0.0")
     taco_compare("tacotron_cfg3_fullwidth_B32_Tin160_Tout200_deterministic", hp, 32, 160, 200, 53,
-                 dict(align=2e-2, dec_l1=1e-2, mel_l1=4e-2, stop=5e-2, loss=2e-3, grad_rel=0.25, grad_cos=0.97), backward=False)
+                 dict(align=6e-4, dec_l1=1.6e-3, mel_l1=4e-2, stop=5e-3, loss=2e-3, grad_rel=0.25, grad_cos=0.97), backward=False)

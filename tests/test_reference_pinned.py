@@ -162,6 +162,15 @@ def test_oracle_masked_cross_entropy_matches_reference_code():
 
 
 # ------------------------------------------------------------------------------------------------ Tacotron pieces
+def test_oracle_masked_tacotron_losses_match_reference_code():
+    from oracle import tacotron as ot
+    tl = torch.from_numpy(R["taco_lengths"]).long()
+    got = ot.masked_mse(torch.from_numpy(R["taco_mel_t"]), torch.from_numpy(R["taco_mel_o"]), tl)
+    assert abs(float(got) - float(R["taco_masked_mse"])) <= 1e-5 * float(R["taco_masked_mse"])
+    got = ot.masked_sigmoid_cross_entropy(torch.from_numpy(R["taco_stop_t"]), torch.from_numpy(R["taco_stop_o"]), tl, float(R["taco_pos_weight"]))
+    assert abs(float(got) - float(R["taco_masked_sigmoid_ce"])) <= 1e-5 * float(R["taco_masked_sigmoid_ce"])
+
+
 def test_oracle_attention_score_matches_reference_code():
     from oracle import tacotron as ot
     wq, wf, wk = (torch.from_numpy(R[k]) for k in ("att_wq", "att_wf", "att_wk"))

@@ -1,6 +1,8 @@
 """CUDA Tacotron (through the C-ABI) vs the fp32 CPU oracle, dropout / zoneout off (rates are hparams), same seeded
-inputs. Tolerances (bf16 GEMM operands, fp32 accumulate / state): losses <= 2e-3 absolute + 1e-3 relative, mel outputs mean abs err
-<= 4e-2 (five batch-normalised postnet layers re-normalise bf16 noise to unit scale), alignments max abs err <= 2e-2.
+inputs. Tolerances (bf16 GEMM operands, fp32 accumulate / state; <= 2x the values measured on B200, profiles/r02_measured_parity.jsonl):
+losses <= 2e-3 absolute + 1e-3 relative, alignments max abs err <= 6e-4, decoder-output L1 <= 1.6e-3, stop logits <= 5e-3, mel outputs
+mean abs err <= 4e-2 (measured 2.5e-2: five batch-normalised postnet layers each add ~0.2 % of a unit-variance activation in bf16 storage
+- tools/taco_layer_diag.py; 6e-4 in the fp32-class mode, tests/test_precision_modes_gpu.py).
 Gradients vs the fp32 oracle: per tensor cosine >= 0.97 and relative error <= 0.25 (conv biases in front of a batch norm: 0.9 / 0.5) (measured: 2-4 % for the large
 tensors; 10-18 % for the small encoder-conv / location-attention tensors of the tiny B=3 problem, shrinking as the batch
 grows — the bf16 sign-flip noise floor discussed in tests/test_wavenet_gpu.py, amplified by batch-norm over ~100 rows)."""
@@ -67,8 +69,8 @@ def test_forward_matches_oracle(B, T_in, T_out):
     record("tacotron_small_fwd_B%d_Tin%d_Tout%d" % (B, T_in, T_out), align_max_err=err_al, dec_l1=e_dec.mean().item(), dec_max=e_dec.max().item(),
            mel_l1=e_mel.mean().item(), mel_max=e_mel.max().item(), stop_max=e_stop.max().item(),
            **{"loss_%s_err" % k: abs(los[k] - parts[k].item()) for k in ("before", "after", "stop", "reg")})
-    assert err_al < 2e-2
-    assert e_dec.mean().item() < 1e-2 and e_mel.mean().item() < 4e-2 and e_stop.max().item() < 5e-2
+    assert err_al < 6e-4                                            # measured 6e-5 .. 3e-4
+    assert e_dec.mean().item() < 1.6e-3 and e_mel.mean().item() < 4e-2 and e_stop.max().item() < 5e-3     # measured 7e-4 / 2.5e-2 / 1.5e-3
     for k in ("before", "after", "stop", "reg"):
         # 2e-3 absolute + 1e-3 relative: the losses here are O(3-5) at random init and the batch-norm statistics / loss sums
         # are fp32 atomics (run-to-run reordering moves the 4th digit)
@@ -150,7 +152,7 @@ def test_free_running_synthesis_matches_oracle():
     print("synthesis: align %.3g | dec max %.3g mean %.3g | mel max %.3g mean %.3g | stop %.3g" % (
         e_al, e_dec.max(), e_dec.mean(), e_mel.max(), e_mel.mean(), e_stop))
     record("tacotron_synthesis_24steps", align_max_err=e_al, dec_l1=e_dec.mean().item(), mel_l1=e_mel.mean().item(), stop_max=e_stop)
-    assert e_al < 2e-2 and e_dec.mean().item() < 1.5e-2 and e_mel.mean().item() < 4e-2 and e_stop < 1e-2
+    assert e_al < 1e-4 and e_dec.mean().item() < 1e-3 and e_mel.mean().item() < 4e-3 and e_stop < 1e-4       # measured 3e-5 / 4e-4 / 1.6e-3 / 2e-6
 
 
 def test_synthesis_stop_rule():
@@ -193,9 +195,40 @@ def test_gta_mode_uses_inference_statistics():
     torch.cuda.synchronize()
     melo = model.workspace_tensor("mel_outputs", (B, T_out, hp.num_mels)).cpu()
     al = model.workspace_tensor("alignments", (T_out, B, T_in)).float().cpu().transpose(0, 1)
-    assert (al - ref["alignments"]).abs().max().item() < 2e-2
+    assert (al - ref["alignments"]).abs().max().item() < 1e-3
     assert (melo - ref["mel_outputs"]).abs().mean().item() < 4e-2
     p_after = model.export_params()
     for k in params:
         if "moving_" in k:
             assert torch.equal(p_after[k], params[k]), k          # inference must not touch the moving statistics
+
+
+def test_masked_decoder_losses_match_oracle():
+    """mask_decoder=True (modules.py:412-455): MSE terms over the frames inside each target length, weighted sigmoid CE (pos_weight 3)
+    divided by the number of non-zero masked terms; forward losses and the gradients they seed"""
+    hp = _hp(mask_decoder=True, cross_entropy_pos_weight=3.0)
+    B, T_in, T_out = 4, 40, 32
+    params = ot.init_params(hp, seed=45, random_bias=True)
+    inputs, lens, mel, stop = _batch(hp, B, T_in, T_out, 45)
+    tl = torch.tensor([32, 27, 20, 9])
+    stop = (torch.arange(T_out)[None, :] >= (tl[:, None] - 1)).float()
+    _, grads_ref, ref, parts = ot.train_step(params, inputs, lens, mel, stop, hp, targets_lengths=tl)
+    model = t2.tacotron.Tacotron(hp, B, T_in, T_out)
+    model.load_params(params)
+    with pytest.raises(t2.lib.T2Error):
+        model.forward(inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda())             # lengths are mandatory, as in the reference
+    model.forward(inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda(), targets_lengths=tl.int().cuda())
+    model.backward()
+    torch.cuda.synchronize()
+    los = model.losses()
+    for k in ("before", "after", "stop", "reg"):
+        assert abs(los[k] - parts[k].item()) < 2e-3 + 1e-3 * abs(parts[k].item()), (k, los[k], parts[k].item())
+    grads = model.export_grads()
+    for name in ("linear_transform_projection/kernel", "stop_token_projection/kernel", "postnet_projection/kernel", "decoder_LSTM/cell_2/kernel"):
+        g, gr = grads[name], grads_ref[name]
+        cos = (g * gr).sum().item() / (g.norm().item() * gr.norm().item())
+        assert cos > 0.97 and abs(g.norm().item() / gr.norm().item() - 1) < 0.1, (name, cos)
+    # the unmasked model gives different losses on the same batch: the mask is really applied
+    hp0 = _hp()
+    _, parts0 = ot.loss_fn(ot.forward(params, inputs, lens, mel, hp0, training=True), mel, stop, params, hp0)
+    assert abs(parts0["before"].item() - parts["before"].item()) > 1e-2

@@ -1,8 +1,11 @@
 """CUDA WaveNet (through the C-ABI) vs the fp32 CPU oracle on the same seeded inputs.
 
 Tolerances: the product path computes its GEMMs with bf16 operands / fp32 accumulation, the oracle in fp32.
-  loss            |cuda - oracle| <= 1e-3                          (north-star: NLL / CE parity within 1e-3)
-  logits          max abs err <= 4e-2, mean abs err <= 6e-3        (bf16 operand rounding through the stack)
+  loss            |cuda - oracle| <= 1e-4 (CE; measured <= 3.4e-5), 6e-4 (MoL; measured 2.6e-4), 3e-3 (Gaussian log-density)
+                  - north-star: NLL / CE parity within 1e-3
+  logits          max abs err <= 8e-3, mean abs err <= 1.5e-3      (bf16 operand rounding through the stack; measured max 1.4e-3 with
+                  mu-law input, 3.7e-3 with raw input; <= 2x measured, profiles/r02_measured_parity.jsonl). The fp32-class mode
+                  (tests/test_precision_modes_gpu.py) reaches 6e-6.
   gradients       per tensor  ||g_cuda - g_ref|| / ||g_ref|| <= 5e-2 against the oracle run with bf16 STORAGE
                   EMULATION (oracle.wavenet.step_sim: same fp32 math, tensors rounded to bf16 where the CUDA path
                   stores bf16) and <= 1e-1 against the plain fp32 oracle. The second bound is loose on purpose: at
@@ -64,7 +67,7 @@ def _inputs(hp, B, T, seed):
     return x, c, y, lengths, xd, yd
 
 
-def _run(hp, B, T, seed, loss_tol=1e-3):
+def _run(hp, B, T, seed, loss_tol=1e-4):
     wn = t2.wavenet
     params = ow.init_params(hp, seed=seed, random_bias=True)
     x, c, y, lengths, xd, yd = _inputs(hp, B, T, seed)
@@ -88,7 +91,7 @@ def _run(hp, B, T, seed, loss_tol=1e-3):
         loss, loss_ref.item(), err.max().item(), err.mean().item(), ref.abs().max().item()))
     record("wavenet_small_%s_L%d_R%d_B%dxT%d" % (hp.input_type, hp.layers, hp.residual_channels, B, T), loss_abs_err=abs(loss - loss_ref.item()),
            logits_max_err=err.max().item(), logits_mean_err=err.mean().item(), cup_max_err=(cup - cup_ref).abs().max().item())
-    assert err.max().item() < 4e-2 and err.mean().item() < 6e-3
+    assert err.max().item() < 8e-3 and err.mean().item() < 1.5e-3
     assert abs(loss - loss_ref.item()) < loss_tol
     grads = model.export_grads()
     loss_sim, grads_sim, _ = ow.train_step_sim(params, x, c, y, lengths, hp)
@@ -125,7 +128,7 @@ def test_ce_paper_widths_ragged_T():
 def test_mol_raw_non_legacy_convtranspose():
     hp = _hp(input_type="raw", out_channels=30, legacy=False, residual_legacy=False, upsample_type="2D",
              residual_channels=256, gate_channels=512, skip_out_channels=256)
-    _run(hp, B=3, T=256, seed=13, loss_tol=2e-3)
+    _run(hp, B=3, T=256, seed=13, loss_tol=6e-4)
 
 
 @pytest.mark.parametrize("cdf", [False, True])
@@ -133,7 +136,7 @@ def test_gaussian_head_raw(cdf):
     """the reference's DEFAULT head (hparams.py:187: input_type='raw', out_channels=2): single Gaussian, log-density or CDF-difference
     loss (wavenet_vocoder/models/gaussian.py:5-37), analytic gradient in the head epilogue"""
     hp = _hp(input_type="raw", out_channels=2, cdf_loss=cdf, residual_channels=256, gate_channels=512, skip_out_channels=256)
-    _run(hp, B=2, T=256, seed=16, loss_tol=2e-3)
+    _run(hp, B=2, T=256, seed=16, loss_tol=3e-3)
 
 
 def test_adam_step_matches_oracle():
