@@ -1,15 +1,40 @@
 """Checkpoint files of the drop-in models: one `.npz` per save holding every variable under its TensorFlow-style name (the names /
 layouts of SURVEY.md Appendix B, so that a converter from / to a TF bundle is a rename), the Adam moments (`adam_m/<name>`,
 `adam_v/<name>`), the EMA shadow (`ema/<name>`, WaveNet) and `global_step`; `<dir>/checkpoint` names the latest file like
-tf.train.get_checkpoint_state does (tacotron/train.py:205-215, wavenet_vocoder/train.py:262-276)."""
+tf.train.get_checkpoint_state does (tacotron/train.py:205-215, wavenet_vocoder/train.py:262-276).
+
+With `fmt="tf"` (or T2_CHECKPOINT_FORMAT=tf in the environment) the same content is written as a TensorFlow checkpoint-V2 bundle
+under the reference graph's variable names (`<prefix>-<step>.index` / `.data-00000-of-00001`, t2_tf_bundle.py) and `load` /
+`latest` read either kind, so checkpoints saved by the reference's tf.train.Saver restore here and vice versa."""
 import os
 
 import numpy as np
 
+import t2_tf_bundle
 
-def save(save_dir, prefix, eng, keep=20):
+
+def _format(fmt):
+    fmt = fmt or os.environ.get("T2_CHECKPOINT_FORMAT", "npz")
+    if fmt not in ("npz", "tf"):
+        raise ValueError("checkpoint format must be 'npz' or 'tf'")
+    return fmt
+
+
+def save(save_dir, prefix, eng, keep=20, fmt=None):
     os.makedirs(save_dir, exist_ok=True)
     step = int(eng.global_step)
+    if _format(fmt) == "tf":
+        model = "Tacotron" if prefix.startswith("tacotron") else "WaveNet"
+        path = os.path.join(save_dir, "%s-%d" % (prefix, step))
+        t2_tf_bundle.export_tf(path, model, eng)
+        idx = sorted((f[:-len(".index")] for f in os.listdir(save_dir) if f.startswith(prefix + "-") and f.endswith(".index")),
+                     key=lambda f: int(f[len(prefix) + 1:]))
+        for old in idx[:-keep]:
+            for ext in (".index", ".data-00000-of-00001"):
+                if os.path.isfile(os.path.join(save_dir, old + ext)):
+                    os.remove(os.path.join(save_dir, old + ext))
+        t2_tf_bundle.write_checkpoint_state(save_dir, os.path.basename(path), idx[-keep:])
+        return path
     path = os.path.join(save_dir, "%s-%d.npz" % (prefix, step))
     out = {"global_step": np.asarray(step, dtype=np.int64)}
     for k, v in eng.export_params().items():
@@ -32,6 +57,10 @@ def latest(save_dir):
     p = os.path.join(save_dir, "checkpoint")
     if not os.path.isfile(p):
         return None
+    name = t2_tf_bundle.read_checkpoint_state(save_dir)          # tf.train.Saver's CheckpointState text proto
+    if name is not None:
+        path = name if os.path.isabs(name) else os.path.join(save_dir, name)
+        return path if os.path.isfile(path + ".index") else None
     name = open(p).read().strip()
     path = os.path.join(save_dir, name)
     return path if os.path.isfile(path) else None
@@ -40,6 +69,11 @@ def latest(save_dir):
 def load(path):
     """-> (variables {name: tensor}, state {'global_step', 'adam_m', 'adam_v', 'ema'})"""
     import torch
+    if not path.endswith(".npz") and os.path.isfile(path + ".index"):
+        variables, state = t2_tf_bundle.load_as_engine_dicts(path)
+        as_t = lambda d: {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)) for k, v in d.items()}
+        return as_t(variables), {"global_step": state["global_step"], "adam_m": as_t(state["adam_m"]),
+                                 "adam_v": as_t(state["adam_v"]), "ema": as_t(state["ema"])}
     z = np.load(path)
     variables, state = {}, {"global_step": int(z["global_step"]), "adam_m": {}, "adam_v": {}, "ema": {}}
     for k in z.files:

@@ -1,0 +1,216 @@
+"""TF checkpoint-V2 reader / writer (t2_tf_bundle.py): CRC-32C known answers, table + bundle round trips, a hand-assembled
+prefix-compressed block, snappy blocks, the reference variable-name map."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import t2_tf_bundle as tb
+
+
+def test_crc32c_known_answers():
+    assert tb.crc32c(b"123456789") == 0xE3069283                       # the CRC-32C check value (RFC 3720 B.4 family)
+    assert tb.crc32c(bytes(32)) == 0x8A9136AA                          # RFC 3720 B.4: 32 bytes of zeros
+    assert tb.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43                 # 32 bytes of 0xff
+    assert tb.crc32c(bytes(range(32))) == 0x46DD794E                   # 0..31 ascending
+    assert tb.unmask_crc(tb.mask_crc(0x12345678)) == 0x12345678
+    # leveldb's crc32c_test: mask(crc("foo")) differs from crc and double masking is not idempotent
+    c = tb.crc32c(b"foo")
+    assert tb.mask_crc(c) != c and tb.mask_crc(tb.mask_crc(c)) != c
+
+
+def test_crc32c_lane_path_matches_serial():
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 256, 4096 * 64 + 1237, dtype=np.uint8).tobytes()
+    table = tb._crc_table().tolist()
+    reg = 0xFFFFFFFF
+    for b in data:
+        reg = table[(reg ^ b) & 0xFF] ^ (reg >> 8)
+    assert tb.crc32c(data) == reg ^ 0xFFFFFFFF
+    # incremental form: crc(a + b) == crc(b, crc(a))
+    assert tb.crc32c(data[1000:], tb.crc32c(data[:1000])) == tb.crc32c(data)
+
+
+def test_table_round_trip_many_blocks(tmp_path):
+    items = [(b"", b"hdr")] + [(("scope/var_%05d/kernel" % i).encode(), os.urandom(1 + i % 37)) for i in range(3000)]
+    p = str(tmp_path / "t.index")
+    tb.write_table(p, items, block_size=2048)                          # forces many data blocks + restart points
+    assert tb.read_table(p) == items
+    raw = bytearray(open(p, "rb").read())
+    raw[100] ^= 0x40
+    open(p, "wb").write(raw)
+    with pytest.raises(ValueError):
+        tb.read_table(p)
+
+
+def test_hand_assembled_block_and_footer(tmp_path):
+    """a table assembled byte by byte from the LevelDB format description (not through write_table)"""
+    def entry(shared, suffix, value):
+        return bytes([shared, len(suffix), len(value)]) + suffix + value
+    block = entry(0, b"", b"H") + entry(0, b"abc/kernel", b"v1") + entry(4, b"bias", b"v2")        # "abc/bias" < "abc/kernel"? no:
+    # keys must ascend: abc/bias then abc/kernel
+    block = entry(0, b"", b"H") + entry(0, b"abc/bias", b"v2") + entry(4, b"kernel", b"v1")
+    block += struct.pack("<I", 0) + struct.pack("<I", 1)
+    def with_trailer(b):
+        return b + b"\x00" + struct.pack("<I", tb.mask_crc(tb.crc32c(b + b"\x00")))
+    data = with_trailer(block)
+    meta_off = len(data)
+    meta = struct.pack("<I", 0) + struct.pack("<I", 1)
+    data += with_trailer(meta)
+    idx_off = len(data)
+    handle = bytes([0, len(block)])
+    idx = bytes([0, 1, len(handle)]) + b"b" + handle + struct.pack("<I", 0) + struct.pack("<I", 1)
+    data += with_trailer(idx)
+    footer = bytes([meta_off, len(meta), idx_off, len(idx)])
+    footer += bytes(40 - len(footer)) + struct.pack("<Q", 0xDB4775248B80FB57)
+    p = str(tmp_path / "h.index")
+    open(p, "wb").write(data + footer)
+    assert tb.read_table(p) == [(b"", b"H"), (b"abc/bias", b"v2"), (b"abc/kernel", b"v1")]
+
+
+def test_snappy_block_decoding():
+    lit = b"tacotron-"
+    # literal(9) + copy(offset 9, len 9) with a 2-byte offset + literal "x"
+    comp = bytes([19]) + bytes([(len(lit) - 1) << 2]) + lit + bytes([((9 - 1) << 2) | 2, 9, 0]) + bytes([0 << 2]) + b"x"
+    assert tb._snappy_decompress(comp) == lit + lit + b"x"
+    # overlapping copy (run-length): "ab" then copy offset 2 length 6 -> "abababab"
+    comp = bytes([8, (2 - 1) << 2]) + b"ab" + bytes([((6 - 4) << 2) | 1 | (0 << 5), 2])
+    assert tb._snappy_decompress(comp) == b"abababab"
+
+
+def test_bundle_round_trip_and_checksums(tmp_path):
+    rng = np.random.default_rng(1)
+    tensors = {"Tacotron_model/inference/inputs_embedding": rng.standard_normal((66, 512)).astype(np.float32),
+               "Tacotron_model/inference/decoder/decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/bias": np.zeros(4096, np.float32),
+               "global_step": np.asarray(1234, dtype=np.int32),
+               "scalar64": np.asarray(7, dtype=np.int64),
+               "empty": np.zeros((0, 3), np.float32)}
+    prefix = str(tmp_path / "taco_pretrained" / "tacotron_model.ckpt-1234")
+    tb.write_bundle(prefix, tensors)
+    assert os.path.isfile(prefix + ".index") and os.path.isfile(prefix + ".data-00000-of-00001")
+    back = tb.read_bundle(prefix)
+    assert set(back) == set(tensors)
+    for k in tensors:
+        assert back[k].dtype == tensors[k].dtype and back[k].shape == tensors[k].shape and np.array_equal(back[k], tensors[k])
+    ent = tb.list_bundle(prefix)
+    assert ent["global_step"]["dtype"] == tb.DT_INT32 and ent["global_step"]["shape"] == ()
+    # BundleEntryProto bytes of a known entry: dtype=1, shape{dim{size:66} dim{size:512}}, offset, size, masked crc (fixed32)
+    e = tb._encode_entry(tb.DT_FLOAT, (66, 512), 16384, 135168, 0xAABBCCDD)
+    assert e == bytes([0x08, 0x01, 0x12, 0x09, 0x12, 0x02, 0x08, 0x42, 0x12, 0x03, 0x08, 0x80, 0x04,
+                       0x20, 0x80, 0x80, 0x01, 0x28, 0x80, 0xA0, 0x08, 0x35, 0xDD, 0xCC, 0xBB, 0xAA])
+    assert tb._encode_header() == bytes([0x08, 0x01, 0x1A, 0x02, 0x08, 0x01])
+    # flipped data byte -> checksum error
+    d = prefix + ".data-00000-of-00001"
+    raw = bytearray(open(d, "rb").read())
+    raw[5] ^= 1
+    open(d, "wb").write(raw)
+    with pytest.raises(ValueError):
+        tb.read_bundle(prefix)
+    tb.write_checkpoint_state(os.path.dirname(prefix), os.path.basename(prefix))
+    assert tb.read_checkpoint_state(os.path.dirname(prefix)) == "tacotron_model.ckpt-1234"
+
+
+def test_reference_variable_names():
+    t = tb.tacotron_tf_name
+    P = "Tacotron_model/inference/"
+    assert t("inputs_embedding") == P + "inputs_embedding"
+    assert t("encoder_convolutions/conv_layer_2/kernel") == P + "encoder_convolutions/conv_layer_2_encoder_convolutions/conv1d/kernel"
+    assert t("postnet_convolutions/conv_layer_5/moving_variance") == (
+        P + "postnet_convolutions/conv_layer_5_postnet_convolutions/batch_normalization/moving_variance")
+    assert t("encoder_LSTM/bw/bias") == P + "encoder_LSTM/bidirectional_rnn/bw/encoder_bw_LSTM/bias"
+    assert t("attention/memory_layer/kernel") == P + "memory_layer/kernel"
+    assert t("attention/attention_bias") == P + "decoder/Location_Sensitive_Attention/attention_bias"
+    assert t("attention/location_features_convolution/kernel") == P + "decoder/Location_Sensitive_Attention/location_features_convolution/kernel"
+    assert t("decoder_prenet/dense_2/bias") == P + "decoder/decoder_prenet/dense_2/bias"
+    assert t("decoder_LSTM/cell_2/kernel") == P + "decoder/decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/kernel"
+    assert t("stop_token_projection/kernel") == P + "decoder/stop_token_projection/projection_stop_token_projection/kernel"
+    assert t("postnet_projection/bias") == P + "postnet_projection/projection_postnet_projection/bias"
+    w = tb.wavenet_tf_name
+    Q = "WaveNet_model/inference/"
+    assert w("input_convolution/kernel") == Q + "input_convolution/kernel"
+    assert w("ResidualConv1DGLU_7/residual_block_cin_conv/bias") == (
+        Q + "ResidualConv1DGLU_7/residual_block_cin_conv_ResidualConv1DGLU_7/bias")
+    assert w("local_conditioning_upsampling_2/kernel", "2D") == Q + "ConvTranspose2D_layer_1/kernel"
+    assert w("local_conditioning_upsampling_1/bias") == Q + "SubPixelConvolution_layer_0/bias"
+    assert w("final_convolution_2/kernel") == Q + "final_convolution_2/kernel"
+
+
+class _FakeEngine(object):
+    """host-only stand-in with the engine attributes export_tf / import_tf use (the real engines need a GPU)"""
+
+    def __init__(self, names_shapes, seed):
+        import torch
+        self.tensors, off = [], 0
+        for n, s in names_shapes:
+            self.tensors.append((n, off, s, True))
+            off += int(np.prod(s))
+        self.n_params, self.device, self.global_step = off, torch.device("cpu"), 0
+        g = torch.Generator().manual_seed(seed)
+        self.params = torch.randn(off, generator=g)
+        self.m, self.v = torch.randn(off, generator=g), torch.rand(off, generator=g)
+
+    def unflatten(self, buf):
+        return {n: buf[o:o + int(np.prod(s))].reshape(s).clone() for n, o, s, _ in self.tensors}
+
+    def export_params(self):
+        return self.unflatten(self.params)
+
+    def load_params(self, params):
+        for n, o, s, _ in self.tensors:
+            self.params[o:o + int(np.prod(s))] = params[n].reshape(-1)
+
+
+def test_export_import_engine_round_trip(tmp_path):
+    import torch
+    shapes = [("inputs_embedding", (66, 8)), ("encoder_convolutions/conv_layer_1/kernel", (5, 8, 8)),
+              ("decoder_LSTM/cell_1/kernel", (24, 32)), ("attention/attention_bias", (8,)),
+              ("stop_token_projection/kernel", (12, 1))]
+    a, b = _FakeEngine(shapes, 1), _FakeEngine(shapes, 2)
+    a.global_step = 4321
+    prefix = str(tmp_path / "tacotron_model.ckpt-4321")
+    names = tb.export_tf(prefix, "Tacotron", a)
+    assert "Tacotron_model/inference/decoder/decoder_LSTM/multi_rnn_cell/cell_0/decoder_LSTM_1/kernel/Adam_1" in names
+    loaded, missing = tb.import_tf(prefix, "Tacotron", b)
+    assert not missing and len(loaded) == len(shapes)
+    assert torch.equal(a.params, b.params) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and b.global_step == 4321
+    # a checkpoint saved under a different outer scope still resolves through the unique-suffix rule
+    t = {k.replace("Tacotron_model/", "model/Tacotron_model/"): v for k, v in tb.read_bundle(prefix).items()}
+    tb.write_bundle(str(tmp_path / "other.ckpt-1"), t)
+    c = _FakeEngine(shapes, 3)
+    tb.import_tf(str(tmp_path / "other.ckpt-1"), "Tacotron", c)
+    assert torch.equal(a.params, c.params)
+    # missing variables are reported
+    t.pop("model/Tacotron_model/inference/inputs_embedding")
+    tb.write_bundle(str(tmp_path / "part.ckpt-1"), t)
+    with pytest.raises(KeyError):
+        tb.import_tf(str(tmp_path / "part.ckpt-1"), "Tacotron", _FakeEngine(shapes, 4))
+
+
+def test_t2_checkpoint_tf_format(tmp_path, monkeypatch):
+    """t2_checkpoint.save(fmt='tf') -> latest() -> load(): the run loops' checkpoint path in the reference's own file format"""
+    import torch
+    import t2_checkpoint
+    shapes = [("input_convolution/kernel", (1, 16, 8)), ("ResidualConv1DGLU_0/residual_block_causal_conv/kernel", (3, 8, 16)),
+              ("ResidualConv1DGLU_0/residual_block_out_conv/bias", (8,)), ("local_conditioning_upsampling_1/kernel", (3, 3, 1, 4))]
+    a = _FakeEngine(shapes, 5)
+    a.ema = a.params * 0.5
+    a.hp = type("HP", (), {"upsample_type": "2D"})()
+    for step in (10, 20, 30):
+        a.global_step = step
+        path = t2_checkpoint.save(str(tmp_path), "wavenet_model.ckpt", a, keep=2, fmt="tf")
+    assert path.endswith("wavenet_model.ckpt-30") and not os.path.exists(str(tmp_path / "wavenet_model.ckpt-10.index"))
+    assert t2_checkpoint.latest(str(tmp_path)) == path
+    assert "WaveNet_model/inference/ConvTranspose2D_layer_0/kernel/ExponentialMovingAverage" in tb.list_bundle(path)
+    variables, state = t2_checkpoint.load(path)
+    assert state["global_step"] == 30 and set(variables) == {s[0] for s in shapes}
+    for n, o, s, _ in a.tensors:
+        k = int(np.prod(s))
+        assert torch.equal(variables[n].reshape(-1), a.params[o:o + k])
+        assert torch.equal(state["ema"][n].reshape(-1), a.ema[o:o + k])
+        assert torch.equal(state["adam_v"][n].reshape(-1), a.v[o:o + k])
+    # the native format still works next to it and `latest` follows whichever was written last
+    monkeypatch.setenv("T2_CHECKPOINT_FORMAT", "npz")
+    a.global_step = 40
+    p2 = t2_checkpoint.save(str(tmp_path), "wavenet_model.ckpt", a)
+    assert p2.endswith(".npz") and t2_checkpoint.latest(str(tmp_path)) == p2

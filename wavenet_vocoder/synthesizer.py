@@ -14,7 +14,9 @@ class Synthesizer(object):
     def load(self, checkpoint_path, hparams, model_name="WaveNet"):
         self._hparams = hparams
         self.model = create_model(model_name, hparams)
-        variables, _ = t2_checkpoint.load(checkpoint_path)
+        variables, state = t2_checkpoint.load(checkpoint_path)
+        if state["ema"]:            # the reference restores the EMA shadows for synthesis (wavenet_vocoder/synthesizer.py:33-36, train.py:75-83)
+            variables = dict(variables, **state["ema"])
         self.model.load_variables(variables)
 
     def synthesize(self, mel_spectrograms, speaker_ids, basenames, out_dir, log_dir):
