@@ -11,6 +11,7 @@
 // The FFT runs in fp64: the reference's spectra come from a double-precision FFT (numpy) and the dB floor sits
 // ~100 dB under the spectral peak, which fp32 butterflies cannot resolve to the 1e-3 parity tolerance.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -219,6 +220,161 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(StftArgs a) {
   }
 }
 
+// ---- v2: register-radix FFT, 4 frames per CTA ------------------------------------------------------------------------------
+// 64 threads own one frame (16 complex points each); 1024 = 16 x 16 x 4 Stockham passes with the radix-16 butterflies held in
+// registers, so a frame crosses shared memory three times instead of ten (5 radix-4 passes x read + write) and never needs a
+// CTA-wide barrier: the two warps of a frame meet on their own named barrier. The first pass reads the windowed samples
+// straight from global memory (no staging pass). Shared-memory rows are padded by one element per 16 (17 j + r) so that the
+// transposing stores of the radix-16 passes are conflict-free for 16-byte elements. Post-FFT arithmetic is the v1 arithmetic.
+constexpr int kFramesPerCta = 4;
+constexpr int kFrameThreads = 64;
+constexpr int kPadN = kN + kN / 16;                 // padded complex buffer
+constexpr int kPwN = kBins + 7;
+constexpr int kV2SmemBytes = kFramesPerCta * (kPadN * 16 + kPwN * 8);
+
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+__device__ __forceinline__ void frame_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// forward DFT-4 in place: (a, b, c, d) -> (X0, X1, X2, X3)
+__device__ __forceinline__ void dft4(double2& a, double2& b, double2& c, double2& d) {
+  const double2 s02 = cadd(a, c), d02 = csub(a, c), s13 = cadd(b, d), d13 = csub(b, d);
+  a = cadd(s02, s13);
+  b = make_double2(d02.x + d13.y, d02.y - d13.x);   // d02 - i d13
+  c = csub(s02, s13);
+  d = make_double2(d02.x - d13.y, d02.y + d13.x);   // d02 + i d13
+}
+// forward DFT-16 of v[0..15] (natural order in, natural order out) as 4 x 4 with the W16 twiddles as constants
+__device__ __forceinline__ void dft16(double2* v) {
+  constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);   // v[4 k1 + n2] = y[n2][k1]
+  // y[n2][k1] *= W16^(n2 k1)
+  v[4 + 1] = cmul(v[4 + 1], make_double2(c1, -s1));     // n2=1,k1=1: W^1
+  v[8 + 1] = cmul(v[8 + 1], make_double2(h, -h));       // n2=1,k1=2: W^2
+  v[12 + 1] = cmul(v[12 + 1], make_double2(s1, -c1));   // n2=1,k1=3: W^3
+  v[4 + 2] = cmul(v[4 + 2], make_double2(h, -h));       // n2=2,k1=1: W^2
+  v[8 + 2] = make_double2(v[8 + 2].y, -v[8 + 2].x);     // n2=2,k1=2: W^4 = -i
+  v[12 + 2] = cmul(v[12 + 2], make_double2(-h, -h));    // n2=2,k1=3: W^6
+  v[4 + 3] = cmul(v[4 + 3], make_double2(s1, -c1));     // n2=3,k1=1: W^3
+  v[8 + 3] = cmul(v[8 + 3], make_double2(-h, -h));      // n2=3,k1=2: W^6
+  v[12 + 3] = cmul(v[12 + 3], make_double2(-c1, s1));   // n2=3,k1=3: W^9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);  // -> X[k1 + 4 k2] at v[4 k1 + k2]
+  // transpose the 4 x 4 register tile so that v[k] = X[k]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i + 1; j < 4; ++j) { const double2 t = v[4 * i + j]; v[4 * i + j] = v[4 * j + i]; v[4 * j + i] = t; }
+}
+
+__global__ void __launch_bounds__(kFramesPerCta * kFrameThreads, 2) stft_mel_kernel_v2(StftArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_v2[];
+  const int slot = threadIdx.x / kFrameThreads;
+  const int j = threadIdx.x % kFrameThreads;
+  double2* buf = reinterpret_cast<double2*>(smem_v2) + slot * kPadN;
+  double* pw = reinterpret_cast<double*>(smem_v2 + kFramesPerCta * kPadN * 16) + slot * kPwN;
+  const long long total = (long long)a.B * a.frames;
+  const int lpad = (kNfft - a.win_size) / 2;
+  for (long long fr = (long long)blockIdx.x * kFramesPerCta + slot; fr < total; fr += (long long)gridDim.x * kFramesPerCta) {
+    const int b = int(fr / a.frames), f = int(fr % a.frames);
+    const float* w = a.wav + (long long)b * a.n_samples;
+    double2 v[16];
+    // pass 1 (radix 16, Ns = 1): v[r] = z[j + 64 r], z[n] = x[2n] + i x[2n+1] (windowed, centred, zero padded)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int q0 = 2 * (j + 64 * r);
+      double c[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int q = q0 + hh, wi = q - lpad;
+        double s = 0.0;
+        if (wi >= 0 && wi < a.win_size) {
+          const long long si = (long long)f * a.hop - kNfft / 2 + q;
+          if (si >= 0 && si < a.n_samples) {
+            double x = double(__ldg(w + si));
+            if (a.preemph != 0.f) x -= double(a.preemph) * (si > 0 ? double(__ldg(w + si - 1)) : 0.0);
+            s = x * double(a.gain) * __ldg(a.win + wi);
+          }
+        }
+        c[hh] = s;
+      }
+      v[r] = make_double2(c[0], c[1]);
+    }
+    dft16(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[17 * j + r] = v[r];          // padi(16 j + r)
+    frame_sync(slot);
+    // pass 2 (radix 16, Ns = 16): twiddle W_256^(r k) = W_1024^(4 r k)
+    {
+      const int k = j & 15;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = buf[padi(j + 64 * r)];
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(a.tw + 4 * r * k));
+      dft16(v);
+      frame_sync(slot);
+      const int base = (j - k) * 16 + k;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[padi(base + 16 * r)] = v[r];
+    }
+    frame_sync(slot);
+    // pass 3 (radix 4, Ns = 256): four butterflies per thread, output in natural order
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + 64 * u;
+      v[4 * u] = buf[padi(jj)];
+#pragma unroll
+      for (int r = 1; r < 4; ++r) v[4 * u + r] = cmul(buf[padi(jj + 256 * r)], __ldg(a.tw + r * jj));
+      dft4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+    frame_sync(slot);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) buf[padi(j + 64 * u + 256 * r)] = v[4 * u + r];
+    frame_sync(slot);
+    // untangle to the real-FFT bins and take |X|^p (v1 arithmetic)
+    for (int k = j; k <= kN; k += kFrameThreads) {
+      const double2 zk = buf[padi(k & (kN - 1))];
+      const double2 zn = buf[padi((kN - k) & (kN - 1))];
+      const double2 e = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+      const double2 o = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
+      const int kk = k <= kN / 2 ? k : kN - k;
+      double2 t2w = __ldg(a.tw2 + kk);
+      if (k > kN / 2) t2w = make_double2(-t2w.x, t2w.y);
+      const double2 ow = cmul(o, t2w);
+      const float ref = float(e.x + ow.x), imf = float(e.y + ow.y);
+      const double mag2 = double(ref) * double(ref) + double(imf) * double(imf);
+      double val;
+      if (a.mag_power == 2.f) {
+        const float m = sqrtf(float(mag2));
+        val = double(m * m);
+      } else {
+        val = double(powf(sqrtf(float(mag2)), a.mag_power));
+      }
+      pw[k] = val;
+      if (a.lin) {
+        const float r = finish(a, val);
+        if (a.time_major) a.lin[((long long)b * a.frames + f) * kBins + k] = r;
+        else a.lin[((long long)b * kBins + k) * a.frames + f] = r;
+      }
+    }
+    frame_sync(slot);
+    // sparse mel filterbank: one thread per filter (the long high-frequency filters pair up with the short low ones)
+    for (int m = j; m < a.nm; m += kFrameThreads) {
+      const int s = __ldg(a.fstart + m), n = __ldg(a.fcount + m);
+      const double* fw = a.fw + __ldg(a.foff + m);
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) acc += __ldg(fw + i) * pw[s + i];
+      const float r = finish(a, acc);
+      if (a.time_major) a.mel[((long long)b * a.frames + f) * a.nm + m] = r;
+      else a.mel[((long long)b * a.nm + m) * a.frames + f] = r;
+    }
+    frame_sync(slot);
+  }
+}
+
 __global__ void preemphasis_kernel(const float* __restrict__ x, float* __restrict__ y, long long n_per, long long n, float k) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= n) return;
@@ -344,9 +500,23 @@ extern "C" int t2_stft_mel_f32(const t2_audio_config_t* cfg, const void* d_plan,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long cap = (long long)sms * 4;  // 4 resident CTAs per SM (41 KB smem, 256 threads each)
-  const unsigned grid = (unsigned)(total < cap ? total : cap);
-  stft_mel_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a); t2_count_launch();
+  static int use_v1 = -1;
+  if (use_v1 < 0) { const char* e = getenv("T2_STFT_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+  if (use_v1) {
+    const long long cap = (long long)sms * 4;  // 4 resident CTAs per SM (41 KB smem, 256 threads each)
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
+    stft_mel_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a); t2_count_launch();
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      T2_CHECK_CUDA(cudaFuncSetAttribute(stft_mel_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes));
+      configured = true;
+    }
+    const long long groups = (total + kFramesPerCta - 1) / kFramesPerCta;
+    const long long cap = (long long)sms * 2;  // 2 resident CTAs per SM (102 KB smem, 256 threads, <= 128 registers each)
+    const unsigned grid = (unsigned)(groups < cap ? groups : cap);
+    stft_mel_kernel_v2<<<grid, kFramesPerCta * kFrameThreads, kV2SmemBytes, static_cast<cudaStream_t>(stream)>>>(a); t2_count_launch();
+  }
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
