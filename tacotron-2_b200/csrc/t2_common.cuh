@@ -217,6 +217,20 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem, const CUtensorMap* 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA STORE of one box (shared::cta -> global through the tensor map; rows / columns outside the tensor are clipped), bulk-group
+// completion: commit after issuing, `bulk_wait_read<N>` returns once all but the N most recent groups have finished READING shared
+// memory (the tile may be overwritten), `bulk_wait_all` once every group's global writes are complete.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// generic-proxy shared-memory writes of this thread become visible to the async proxy (TMA) after the next barrier
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // shared::cluster address of `ptr` (a shared::cta address of this CTA) as seen in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_cluster(const void* ptr, uint32_t rank) {
   uint32_t r;

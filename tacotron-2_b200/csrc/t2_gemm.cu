@@ -49,6 +49,24 @@ static int encode_act_map(CUtensorMap* m, const ActT& a, int box_rows) {
   return T2_OK;
 }
 
+// 3-D map over a channels-last bf16 OUTPUT tensor [B][T][C] for the epilogue's TMA stores: box 64 columns x 32 rows (one TMEM lane
+// quarter), 128-byte swizzle; rows >= T of an item and columns >= C are clipped by the hardware.
+static int encode_out_map(CUtensorMap* m, const void* ptr, int C, int T, int B) {
+  EncodeTiledFn fn = get_encode_fn();
+  T2_REQUIRE(fn != nullptr, T2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  T2_REQUIRE(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && C % 8 == 0, T2_ERR_INVALID_ARG,
+             "epilogue output must be non-null, 16-byte aligned, with a row pitch that is a multiple of 8 elements (C=%d)", C);
+  cuuint64_t dims[3] = {cuuint64_t(C), cuuint64_t(T), cuuint64_t(B)};
+  cuuint64_t strides[2] = {cuuint64_t(C) * 2, cuuint64_t(C) * 2 * T};
+  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  T2_REQUIRE(r == CUDA_SUCCESS, T2_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d (C=%d T=%d B=%d)", int(r), C, T, B);
+  return T2_OK;
+}
+
 // 3-D map over packed bf16 weights [L][N][K]: dims (K, N, L), box (64, rows, 1)
 static int encode_wt_map(CUtensorMap* m, const void* w, int N, int K, int L, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -187,6 +205,20 @@ int launch_act_gemm(int epi, int BN, const ActGemmCall& c, cudaStream_t stream) 
   g.b_k0 = c.w_k0;
   g.dbg = g_timing_buffer;
   g.epi = c.epi;
+  // output tensor maps of the epilogues that store through TMA (bf16 mode only; the split-bf16 mode keeps direct stores)
+  if (!c.epi.i[11]) {
+    const void* outs[3] = {nullptr, nullptr, nullptr};
+    int ldo = 0;
+    if (epi == EPI_GATE) { outs[0] = c.epi.ptr[0]; outs[1] = c.epi.ptr[1]; outs[2] = c.epi.ptr[2]; ldo = c.epi.i[0]; }
+    else if (epi == EPI_RES) { outs[0] = c.epi.ptr[1]; outs[1] = c.epi.ptr[2]; ldo = BN; }
+    else if (epi == EPI_GATE_BWD) { outs[0] = c.epi.ptr[2]; ldo = 2 * c.epi.i[0]; }
+    else if (epi == EPI_DX) { outs[0] = c.epi.ptr[1]; ldo = BN; }
+    for (int i = 0; i < 3; ++i)
+      if (outs[i]) {
+        rc = encode_out_map(&g.omap[i], outs[i], ldo, c.T, c.B);
+        if (rc) return rc;
+      }
+  }
   if (c.ksplit > 1) {
     T2_REQUIRE(epi == EPI_TOUT && c.ksplit * kBK <= ktot, T2_ERR_INVALID_ARG,
                "act_gemm: split-K needs an atomically accumulating epilogue and at least one k-block per slice");

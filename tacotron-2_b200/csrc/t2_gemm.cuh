@@ -86,7 +86,15 @@ __device__ __forceinline__ void load_split32(const __nv_bfloat16* src_hi, const 
 constexpr int kTilePitch = 256 + 16;              // bytes per staged row: 128 bf16 + 16 B pad (bank spread)
 constexpr int kTileBytes = 32 * kTilePitch;       // 8704
 constexpr int kEpiTilesPerWarp = 2;          // dedicated staging (not aliased with the pipeline stages)
-constexpr int kEpiWarpBytes = kEpiTilesPerWarp * kTileBytes;
+// TMA-store staging (EPI_GATE / EPI_RES / EPI_GATE_BWD / EPI_DX): a staged 32-row x 128-column bf16 tile is two 64-column boxes of
+// 32 rows x 128 bytes in the 128-byte swizzle (16-byte chunk index XOR row % 8) the output tensor maps are encoded with, so one
+// elected thread per lane quarter hands a finished tile to the TMA engine instead of 4 warps copying it out through registers.
+// Three tiles per quarter rotate: a tile is rewritten two stores after its own (see tile_store).
+constexpr int kSBoxBytes = 32 * 128;
+constexpr int kSTileBytes = 2 * kSBoxBytes;
+constexpr int kSTiles = 3;
+constexpr int kEpiWarpBytes = kSTiles * kSTileBytes;     // 24 KB per lane quarter (also covers the 2 x 8704-byte pitch-272 tiles)
+static_assert(kEpiWarpBytes >= kEpiTilesPerWarp * kTileBytes && kEpiWarpBytes % 1024 == 0, "staging size / swizzle-atom alignment");
 
 constexpr int kActEpiWarps = 16;                               // 4 TMEM lane quarters x 4 column groups
 constexpr int kActGemmThreads = 64 + 32 * kActEpiWarps;        // + producer warp + MMA warp
@@ -103,6 +111,9 @@ struct EpiCtx {
   uint8_t* wbuf;           // kEpiWarpBytes of shared memory shared by the 4 warps of this lane quarter
   uint8_t* smem_all;       // start of the (free after the mainloop) pipeline shared memory, CTA-wide scratch
   int m_tile;              // index of this CTA's 128-row tile
+  const CUtensorMap* omap; // output tensor maps (GemmArgs::omap) of the TMA-store epilogues
+  int tq;                  // first time step of this lane quarter (row coordinate of its stores)
+  mutable int sk;          // stores issued so far by this quarter (tile rotation)
 };
 
 __device__ __forceinline__ void stage_put(uint8_t* tile, int lane, int cq, const float (&v)[32]) {
@@ -167,6 +178,69 @@ __device__ __forceinline__ void tile_fill(uint8_t* tile, const __nv_bfloat16* g,
     *reinterpret_cast<uint4*>(tile + r * kTilePitch + ch * 16) = u;
   }
   if (NW == 4) quarter_sync(c.qbar); else __syncwarp();
+}
+
+// ---- swizzled staging + TMA store ----------------------------------------------------------------
+__device__ __forceinline__ uint8_t* sw_addr(uint8_t* tile, int row, int chunk) {   // chunk: 16-byte column chunk 0..15 of the 128 columns
+  return tile + (chunk >> 3) * kSBoxBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void stage_put_sw(uint8_t* tile, int lane, int cq, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+    u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+    u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+    u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(sw_addr(tile, lane, cq * 4 + q)) = u;
+  }
+}
+__device__ __forceinline__ void stage_get_sw(uint8_t* tile, int lane, int cq, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(sw_addr(tile, lane, cq * 4 + q));
+    v[q * 8 + 0] = bf16lo(u.x); v[q * 8 + 1] = bf16hi(u.x);
+    v[q * 8 + 2] = bf16lo(u.y); v[q * 8 + 3] = bf16hi(u.y);
+    v[q * 8 + 4] = bf16lo(u.z); v[q * 8 + 5] = bf16hi(u.z);
+    v[q * 8 + 6] = bf16lo(u.w); v[q * 8 + 7] = bf16hi(u.w);
+  }
+}
+// global rows -> swizzled tile (rows >= nrows are zero-filled); the 4 warps of the quarter cooperate, then meet on its barrier
+__device__ __forceinline__ void tile_fill_sw(uint8_t* tile, const __nv_bfloat16* g, size_t ld, int nrows, const EpiCtx& c) {
+  const int ch = c.lane & 15, rh = c.lane >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (c.cg * 4 + i) * 2 + rh;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r < nrows) u = __ldg(reinterpret_cast<const uint4*>(g + size_t(r) * ld + ch * 8));
+    *reinterpret_cast<uint4*>(sw_addr(tile, r, ch)) = u;
+  }
+  quarter_sync(c.qbar);
+}
+// Hand a staged tile (every warp of the quarter has put its 32 columns) to the TMA engine: columns [col0, col0 + 128) of rows
+// [tq, tq + 32) of item b in the tensor behind `map`; rows past the sequence end are clipped by the map. ONE fixed thread per quarter
+// issues, commits and then waits until all but the newest store have finished reading shared memory. Every warp that has passed the
+// barrier of store k therefore knows that stores <= k - 2 have released their tiles: a tile may be rewritten (after that barrier) two
+// stores after its own - the three-tile rotation of the epilogues below.
+__device__ __forceinline__ void tile_store(uint8_t* tile, const CUtensorMap* map, int col0, const EpiCtx& c) {
+  fence_proxy_async_smem();
+  quarter_sync(c.qbar);
+  if (c.cg == 0 && c.lane == 0) {
+    tma_store_3d(map, tile, col0, c.tq, c.b);
+    tma_store_3d(map, tile + kSBoxBytes, col0 + 64, c.tq, c.b);
+    bulk_commit();
+    bulk_wait_read<1>();
+  }
+  ++c.sk;
+}
+// all earlier stores of this quarter have released their tiles (needed before tiles are refilled out of rotation order)
+__device__ __forceinline__ void tile_guard(const EpiCtx& c) {
+  if (c.cg == 0 && c.lane == 0) bulk_wait_read<0>();
+  quarter_sync(c.qbar);
+}
+// end of the epilogue: the issuing thread waits for its stores' global writes before the CTA may exit
+__device__ __forceinline__ void tile_store_drain(const EpiCtx& c) {
+  if (c.cg == 0 && c.lane == 0) bulk_wait_all();
 }
 
 // Column sums across a warp: lane r holds v[0..31] (row r of a 32x32 tile); on return lane j holds sum_r v_r[j].
@@ -235,9 +309,6 @@ struct Epilogue<EPI_GATE, 256> {
     __nv_bfloat16* ta_o = static_cast<__nv_bfloat16*>(e.ptr[0]);
     __nv_bfloat16* sb_o = static_cast<__nv_bfloat16*>(e.ptr[1]);
     __nv_bfloat16* z_o = static_cast<__nv_bfloat16*>(e.ptr[2]);
-    uint8_t* t0 = c.wbuf;
-    uint8_t* t1 = c.wbuf + kTileBytes;
-    const size_t off = c.row0 * Gh + cb;
     if (e.i[11]) {   // split-bf16 mode: accurate tanh / sigmoid, z written as hi | lo (row pitch 2 Gh); forward only (no stashes)
       const int cq = c.cg;
       float a[32], g[32], ba[32], bb[32];
@@ -265,17 +336,25 @@ struct Epilogue<EPI_GATE, 256> {
         a[j] = tanh_approx_(a[j] + ba[j]);
         g[j] = sigmoid_approx_(g[j] + bb[j]);
       }
-      if (ta_o) stage_put(t0, c.lane, cq, a);
+      // three stores per call through the rotating tiles: tanh stash, z, sigmoid stash (omap 0 / 2 / 1)
+      if (ta_o) {
+        uint8_t* t = c.wbuf + (c.sk % kSTiles) * kSTileBytes;
+        stage_put_sw(t, c.lane, cq, a);
+        tile_store(t, c.omap + 0, cb, c);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] *= g[j];
-      stage_put(t1, c.lane, cq, a);
+      {
+        uint8_t* t = c.wbuf + (c.sk % kSTiles) * kSTileBytes;
+        stage_put_sw(t, c.lane, cq, a);
+        tile_store(t, c.omap + 2, cb, c);
+      }
       if (ta_o) {
-        tile_flush<4>(t0, ta_o + off, Gh, c.nrows, c);
-        stage_put(t0, c.lane, cq, g);
-        tile_flush<4>(t0, sb_o + off, Gh, c.nrows, c);
+        uint8_t* t = c.wbuf + (c.sk % kSTiles) * kSTileBytes;
+        stage_put_sw(t, c.lane, cq, g);
+        tile_store(t, c.omap + 1, cb, c);
       }
     }
-    tile_flush<4>(t1, z_o + off, Gh, c.nrows, c);
   }
 };
 
@@ -291,7 +370,7 @@ struct Epilogue<EPI_RES, BN> {
     const __nv_bfloat16* x_in = static_cast<const __nv_bfloat16*>(e.ptr[0]);
 #pragma unroll
     for (int gq = 0; gq < BN / 128; ++gq)
-      tile_fill<4>(c.wbuf + gq * kTileBytes, x_in + c.row0 * BN + gq * 128, BN, c.nrows, c);
+      tile_fill_sw(c.wbuf + gq * kSTileBytes, x_in + c.row0 * BN + gq * 128, BN, c.nrows, c);
   }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int R = BN;
@@ -323,17 +402,20 @@ struct Epilogue<EPI_RES, BN> {
     const size_t row = (size_t(c.b) * c.T + c.t) * R;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
-      uint8_t* tile = c.wbuf + gq * kTileBytes;   // holds x on entry, reused in place for the outputs
+      // tiles: x of group 0 / 1 arrives in tile 0 / 1 and is replaced in place by x_out; the dropped copies go to tile 2 (group 0)
+      // and tile 0 (group 1): store order T0, T2, T1, T0 - never a tile of the two preceding stores (tile_store)
+      uint8_t* tile = c.wbuf + gq * kSTileBytes;
+      uint8_t* tile_d = c.wbuf + (gq == 0 ? 2 : 0) * kSTileBytes;
       const int cq = c.cg;
       const int j0 = gq * 128 + cq * 32;
       float acc[32], x[32], bv[32];
       load_f32x32(bias + j0, bv);
       tmem_ld32f(c.trow + j0, acc);
-      stage_get(tile, c.lane, cq, x);
+      stage_get_sw(tile, c.lane, cq, x);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + bv[j] + x[j]) * rs;
-      stage_put(tile, c.lane, cq, acc);      // same rows/columns this lane just read
-      tile_flush<4>(tile, x_out + c.row0 * R + gq * 128, R, c.nrows, c);
+      stage_put_sw(tile, c.lane, cq, acc);      // same rows/columns this lane just read
+      tile_store(tile, c.omap + 0, gq * 128, c);
       if (xd_out) {
         const uint32_t thr = uint32_t(p * 65536.f);
 #pragma unroll
@@ -342,8 +424,8 @@ struct Epilogue<EPI_RES, BN> {
           acc[j] = (h & 0xFFFFu) >= thr ? acc[j] * keep_inv : 0.f;
           acc[j + 1] = (h >> 16) >= thr ? acc[j + 1] * keep_inv : 0.f;
         }
-        stage_put(tile, c.lane, cq, acc);
-        tile_flush<4>(tile, xd_out + c.row0 * R + gq * 128, R, c.nrows, c);
+        stage_put_sw(tile_d, c.lane, cq, acc);
+        tile_store(tile_d, c.omap + 1, gq * 128, c);
       }
     }
   }
@@ -699,27 +781,27 @@ struct Epilogue<EPI_GATE_BWD, BN> {
   static __device__ __forceinline__ void prefetch(const EpiArgs& e, const EpiCtx& c) {
     const int Gh = e.i[0];
     const int cb = c.n_tile * BN;
-    tile_fill<4>(c.wbuf, static_cast<const __nv_bfloat16*>(e.ptr[0]) + c.row0 * Gh + cb, Gh, c.nrows, c);
-    tile_fill<4>(c.wbuf + kTileBytes, static_cast<const __nv_bfloat16*>(e.ptr[1]) + c.row0 * Gh + cb, Gh, c.nrows, c);
+    tile_fill_sw(c.wbuf, static_cast<const __nv_bfloat16*>(e.ptr[0]) + c.row0 * Gh + cb, Gh, c.nrows, c);
+    tile_fill_sw(c.wbuf + kSTileBytes, static_cast<const __nv_bfloat16*>(e.ptr[1]) + c.row0 * Gh + cb, Gh, c.nrows, c);
   }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int Gh = e.i[0];
     const __nv_bfloat16* ta = static_cast<const __nv_bfloat16*>(e.ptr[0]);
     const __nv_bfloat16* sb = static_cast<const __nv_bfloat16*>(e.ptr[1]);
-    __nv_bfloat16* dg = static_cast<__nv_bfloat16*>(e.ptr[2]);
     uint8_t* t0 = c.wbuf;
-    uint8_t* t1 = c.wbuf + kTileBytes;
+    uint8_t* t1 = c.wbuf + kSTileBytes;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
       const int cb = c.n_tile * BN + gq * 128;
       const int cq = c.cg;
       float dz[32], a[32], s[32];
-      if (gq > 0) {   // group 0 was prefetched during the mainloop
-        tile_fill<4>(t0, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
-        tile_fill<4>(t1, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
+      if (gq > 0) {   // group 0 was prefetched during the mainloop; the tiles of group 0's stores must be released first
+        tile_guard(c);
+        tile_fill_sw(t0, ta + c.row0 * Gh + cb, Gh, c.nrows, c);
+        tile_fill_sw(t1, sb + c.row0 * Gh + cb, Gh, c.nrows, c);
       }
-      stage_get(t0, c.lane, cq, a);
-      stage_get(t1, c.lane, cq, s);
+      stage_get_sw(t0, c.lane, cq, a);
+      stage_get_sw(t1, c.lane, cq, s);
       tmem_ld32f(c.trow + gq * 128 + cq * 32, dz);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -728,10 +810,10 @@ struct Epilogue<EPI_GATE_BWD, BN> {
         a[j] = da;
         s[j] = db;
       }
-      stage_put(t0, c.lane, cq, a);     // in place: this lane's own rows / columns
-      stage_put(t1, c.lane, cq, s);
-      tile_flush<4>(t0, dg + c.row0 * 2 * Gh + cb, 2 * Gh, c.nrows, c);
-      tile_flush<4>(t1, dg + c.row0 * 2 * Gh + Gh + cb, 2 * Gh, c.nrows, c);
+      stage_put_sw(t0, c.lane, cq, a);     // in place: this lane's own rows / columns
+      stage_put_sw(t1, c.lane, cq, s);
+      tile_store(t0, c.omap + 0, cb, c);
+      tile_store(t1, c.omap + 0, Gh + cb, c);
       if (e.ptr[3]) {
         const float ca = warp_colsum32(a, c.lane), cb2 = warp_colsum32(s, c.lane);
         const int col = cb + cq * 32 + colsum32_col(c.lane);
@@ -757,12 +839,11 @@ struct Epilogue<EPI_DX, BN> {
     if (!dxo) return;
 #pragma unroll
     for (int gq = 0; gq < BN / 128; ++gq)
-      tile_fill<4>(c.wbuf + gq * kTileBytes, dxo + c.row0 * BN + gq * 128, BN, c.nrows, c);
+      tile_fill_sw(c.wbuf + gq * kSTileBytes, dxo + c.row0 * BN + gq * 128, BN, c.nrows, c);
   }
   static __device__ __forceinline__ void run(const EpiArgs& e, const EpiCtx& c) {
     const int R = BN;
     const __nv_bfloat16* dxo = static_cast<const __nv_bfloat16*>(e.ptr[0]);
-    __nv_bfloat16* dx = static_cast<__nv_bfloat16*>(e.ptr[1]);
     const float rs = e.f[0], p = e.f[1];
     const float keep_inv = 1.f / (1.f - p);
     const unsigned long long seed = e.seed + (e.ptr[7] ? *static_cast<const unsigned long long*>(e.ptr[7]) : 0ull);
@@ -770,7 +851,7 @@ struct Epilogue<EPI_DX, BN> {
     const size_t row = (size_t(c.b) * c.T + c.t) * R;
 #pragma unroll 1
     for (int gq = 0; gq < BN / 128; ++gq) {
-      uint8_t* tile = c.wbuf + gq * kTileBytes;
+      uint8_t* tile = c.wbuf + gq * kSTileBytes;
       const int cq = c.cg;
       const int j0 = gq * 128 + cq * 32;
       float acc[32], g[32];
@@ -785,12 +866,12 @@ struct Epilogue<EPI_DX, BN> {
         }
       }
       if (dxo) {
-        stage_get(tile, c.lane, cq, g);
+        stage_get_sw(tile, c.lane, cq, g);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] += rs * g[j];
       }
-      stage_put(tile, c.lane, cq, acc);
-      tile_flush<4>(tile, dx + c.row0 * R + gq * 128, R, c.nrows, c);
+      stage_put_sw(tile, c.lane, cq, acc);
+      tile_store(tile, c.omap + 0, gq * 128, c);
       if (e.ptr[2]) {
         const float cs = warp_colsum32(acc, c.lane);
         atomicAdd(static_cast<float*>(e.ptr[2]) + j0 + colsum32_col(c.lane), cs * e.f[2]);
@@ -918,11 +999,12 @@ struct ActGemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // latency-bound pipelines: ~2.3k cycles TMA round trip / stages = cycles per k-block; the narrow swapped GEMMs of the
   // recurrences (BN = 32, 20 KB stages) take 6 stages
+  // (BN = 256 outside a CTA pair - odd tile counts, T2_PAIR=0 - is a fallback: the 96 KB of store staging leave room for 2 stages)
 #ifndef T2_STAGES_256
-#define T2_STAGES_256 3
+#define T2_STAGES_256 2
 #endif
   static constexpr int kStages = (BN >= 256) ? T2_STAGES_256 : (BN <= 32 ? 6 : 4);
-  static constexpr int kStagingBytes = 4 * kEpiWarpBytes;      // 4 lane quarters x 2 tiles, never aliased with the stages
+  static constexpr int kStagingBytes = 4 * kEpiWarpBytes;      // 4 lane quarters x 3 store tiles, never aliased with the stages
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -1061,6 +1143,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
     c.wbuf = staging + q * kEpiWarpBytes;
     c.smem_all = staging;
     c.m_tile = m_tile;
+    c.omap = g.omap; c.tq = tw; c.sk = 0;
     if constexpr (EpiHasPrefetch<EPI>::value && NT == 1) {
       c.n_tile = blockIdx.y;
       Epilogue<EPI, BN>::prefetch(g.epi, c);
@@ -1075,6 +1158,7 @@ __global__ void __launch_bounds__(kActGemmThreads, 1) act_gemm_kernel(const __gr
       Epilogue<EPI, BN>::run(g.epi, c);
       if (dbg && threadIdx.x == 64 && h == NT - 1) dbg[5] = clock64();
     }
+    tile_store_drain(c);
   }
   tc_fence_before();
   __syncthreads();
@@ -1216,6 +1300,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kActGemmThreads, 1) 
     c.wbuf = staging + q * kEpiWarpBytes;
     c.smem_all = staging;
     c.m_tile = m_tile;
+    c.omap = g.omap; c.tq = tw; c.sk = 0;
     if constexpr (EpiHasPrefetch<EPI>::value && NT == 1) {
       c.n_tile = blockIdx.y;
       Epilogue<EPI, BN>::prefetch(g.epi, c);
@@ -1230,6 +1315,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kActGemmThreads, 1) 
       Epilogue<EPI, BN>::run(g.epi, c);
       if (dbg && threadIdx.x == 64 && h == NT - 1) dbg[5] = clock64();
     }
+    tile_store_drain(c);
   }
   tc_fence_before();
   __syncthreads();

@@ -30,6 +30,7 @@ struct EpiArgs {
 struct GemmArgs {
   CUtensorMap amap[4];
   CUtensorMap bmap;
+  CUtensorMap omap[3];  // epilogue OUTPUT tensors (TMA stores): dims (C, T, B), box 64 columns x 32 rows, 128-byte swizzle
   Seg seg[kMaxSeg];
   int nseg;
   int T;             // time steps per batch item
