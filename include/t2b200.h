@@ -190,6 +190,12 @@ int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_params, const v
                      const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets,
                      const float* d_stop_targets, float* d_grads, unsigned long long seed,
                      const unsigned long long* d_step, void* stream);
+/* same, plus an extra upstream gradient on the clipped mel_outputs (fp32 [B][T_out][num_mels], NULL = none): the CBHG head's
+ * t2_cbhg_backward output (tacotron.py:203-219 hangs the post-processing net on mel_outputs) */
+int t2_taco_backward_ex(const t2_taco_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                     const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets,
+                     const float* d_stop_targets, float* d_grads, const float* d_mel_outputs_grad, unsigned long long seed,
+                     const unsigned long long* d_step, void* stream);
 /* Free-running synthesis (TacoTestHelper, tacotron/models/helpers.py:6-59; tacotron.py:150-200 with is_training = False:
  * inference batch-norm, deterministic zoneout blend, prenet dropout still on). cfg->T_out is max_iters (hparams.py:138).
  *   t2_taco_infer_begin   encoder, zero decoder state, go frame
@@ -217,6 +223,48 @@ int t2_dbg_att_stamps(long long* d_buf);
 int t2_dbg_ar_stamps(long long* d_buf);    /* same for one layer pass of the AR synthesis kernel (16 int64) */
 int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, const char* name, void** ptr,
                              long long* count, int* elem_bytes);
+
+/* ---- Tacotron: CBHG post-processing net + linear-spectrogram head (predict_linear = True, the reference default) ----
+ * Replaces tacotron/models/tacotron.py:203-219 (CBHG_postnet, cbhg_linear_specs_projection, clip), :323-330 / the
+ * MaskedLinearLoss of tacotron/models/modules.py:457-485, and modules.py:4-78 (HighwayNet, CBHG: conv bank, max-pool, projections,
+ * highway layers, bidirectional GRU over the whole padded sequence). Field names follow hparams.py:64,162-169.
+ * It is a separate engine chained behind t2_taco_forward: its input is the Tacotron workspace tensor "mel_outputs", its backward
+ * returns d(linear loss + its regulariser)/d(mel_outputs), which t2_taco_backward_ex adds to the mel loss seed. Parameters, gradients
+ * and Adam moments are sub-ranges of the caller's flat buffers (one optimizer step / one global-norm clip over both engines). */
+typedef struct {
+  int B, T;                  /* batch items (multiple of 4), decoder steps (= mel frames) */
+  int num_mels;              /* 80 */
+  int kernels;               /* cbhg_kernels: convolution bank sizes 1..kernels (<= 8) */
+  int conv_channels;         /* cbhg_conv_channels (128) */
+  int pool_size;             /* cbhg_pool_size (2) */
+  int projection;            /* cbhg_projection (256); the second projection maps back to num_mels */
+  int projection_kernel_size;/* cbhg_projection_kernel_size (3) */
+  int highwaynet_layers;     /* cbhg_highwaynet_layers (4) */
+  int highway_units;         /* cbhg_highway_units (128) */
+  int rnn_units;             /* cbhg_rnn_units (128): GRU units per direction */
+  int num_freq;              /* 1025 */
+  int n_priority_freq;       /* int(2000 / (sample_rate / 2) * num_freq): bins carrying the second half of the L1 weight */
+  int clip_outputs, mask_decoder;
+  float max_abs_value, lower_bound_decay, reg_weight;
+} t2_cbhg_config_t;
+int t2_cbhg_sizes(const t2_cbhg_config_t* cfg, long long* n_params, long long* packed_bytes, long long* workspace_bytes, int* n_tensors);
+int t2_cbhg_param_info(const t2_cbhg_config_t* cfg, int i, char* name, int name_cap, long long* offset, int* ndim, int* shape4,
+                       int* trainable);
+int t2_cbhg_init(const t2_cbhg_config_t* cfg, void* d_packed, void* d_workspace, void* stream);          /* synchronises */
+int t2_cbhg_pack_weights(const t2_cbhg_config_t* cfg, const float* d_params, void* d_packed, void* d_workspace, void* stream);
+/* mask_decoder = 1: the B target lengths (device int32), as t2_taco_set_target_lengths */
+int t2_cbhg_set_target_lengths(const t2_cbhg_config_t* cfg, void* d_workspace, const int* d_target_lengths, void* stream);
+/* d_mel: fp32 [B][T][num_mels] (the clipped mel_outputs); d_linear_targets fp32 [B][T][num_freq] or NULL (inference);
+ * d_loss[0] = linear loss, d_loss[1] = reg_weight * sum l2_loss(CBHG kernels) (NULL allowed). training = 1: batch statistics
+ * (+ moving-average update), stashes for the backward pass. Linear outputs: workspace tensor "linear_outputs", fp32 rows of
+ * pitch (num_freq rounded up to a multiple of 8), the first num_freq columns valid. */
+int t2_cbhg_forward(const t2_cbhg_config_t* cfg, float* d_params, const void* d_packed, void* d_workspace, const float* d_mel,
+                    const float* d_linear_targets, float* d_loss, int training, void* stream);
+/* backward of the last t2_cbhg_forward(training = 1 with targets): gradients into d_grads (this engine's range of the flat
+ * buffer; overwritten), d(loss)/d(mel_outputs) into d_mel_grad fp32 [B][T][num_mels] */
+int t2_cbhg_backward(const t2_cbhg_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace, const float* d_mel,
+                     float* d_grads, float* d_mel_grad, void* stream);
+int t2_cbhg_workspace_tensor(const t2_cbhg_config_t* cfg, void* d_workspace, const char* name, void** ptr, long long* count);
 
 /* ---- optimizer: tf.train.AdamOptimizer + per-tensor clip_by_norm/clip_by_value + EMA ------------------------
  * Replaces wavenet.py:586-613 (and tacotron.py:429-437 with global_norm_clip > 0).

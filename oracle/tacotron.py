@@ -77,6 +77,32 @@ def param_shapes(hp):
         cin = P
     sh["postnet_projection/kernel"] = (P, hp.num_mels)
     sh["postnet_projection/bias"] = (hp.num_mels,)
+    if hp.predict_linear:                       # CBHG post-processing net + linear projection (tacotron.py:203-219, modules.py:19-78)
+        cc, hu, ru = hp.cbhg_conv_channels, hp.cbhg_highway_units, hp.cbhg_rnn_units
+
+        def conv(prefix, k, ci, co):
+            sh[prefix + "kernel"] = (k, ci, co)
+            sh[prefix + "bias"] = (co,)
+            for n in ("gamma", "beta", "moving_mean", "moving_variance"):
+                sh[prefix + n] = (co,)
+        for k in range(1, hp.cbhg_kernels + 1):
+            conv("CBHG_postnet/conv_bank/conv1d_%d/" % k, k, hp.num_mels, cc)
+        conv("CBHG_postnet/proj1/", hp.cbhg_projection_kernel_size, hp.cbhg_kernels * cc, hp.cbhg_projection)
+        conv("CBHG_postnet/proj2/", hp.cbhg_projection_kernel_size, hp.cbhg_projection, hp.num_mels)
+        if hp.num_mels != hu:                   # modules.py:62-63
+            sh["CBHG_postnet/dense/kernel"] = (hp.num_mels, hu)
+            sh["CBHG_postnet/dense/bias"] = (hu,)
+        for i in range(hp.cbhg_highwaynet_layers):
+            for n in ("H", "T"):
+                sh["CBHG_postnet/highwaynet_%d/%s/kernel" % (i + 1, n)] = (hu, hu)
+                sh["CBHG_postnet/highwaynet_%d/%s/bias" % (i + 1, n)] = (hu,)
+        for d in ("forward", "backward"):       # tf.nn.rnn_cell.GRUCell: gates kernel [in + n, 2n], candidate kernel [in + n, n]
+            sh["CBHG_postnet/%s_RNN/gates/kernel" % d] = (hu + ru, 2 * ru)
+            sh["CBHG_postnet/%s_RNN/gates/bias" % d] = (2 * ru,)
+            sh["CBHG_postnet/%s_RNN/candidate/kernel" % d] = (hu + ru, ru)
+            sh["CBHG_postnet/%s_RNN/candidate/bias" % d] = (ru,)
+        sh["cbhg_linear_specs_projection/kernel"] = (2 * ru, hp.num_freq)
+        sh["cbhg_linear_specs_projection/bias"] = (hp.num_freq,)
     return sh
 
 
@@ -104,6 +130,10 @@ def init_params(hp, seed=None, random_bias=False):
             params[name] = torch.zeros(shape)
         elif name.endswith("bias"):
             params[name] = torch.randn(shape, generator=gen) * 0.1 if random_bias else torch.zeros(shape)
+            if not random_bias and name.endswith("RNN/gates/bias"):
+                params[name] = torch.ones(shape)            # GRUCell gate bias initialiser 1.0
+            if not random_bias and "/T/bias" in name:
+                params[name] = -torch.ones(shape)           # HighwayNet T gate bias -1 (modules.py:10)
         else:
             if len(shape) == 1:
                 fan_in = fan_out = shape[0]
@@ -124,8 +154,8 @@ def conv_block(x, params, prefix, activation, training, drop_rate, drop_mask=Non
     x [B, T, Cin] channels-last."""
     k = params[prefix + "kernel"]  # [kw, in, out]
     kw = k.shape[0]
-    y = F.conv1d(x.transpose(1, 2), k.permute(2, 1, 0).contiguous(), params[prefix + "bias"],
-                 padding=(kw - 1) // 2).transpose(1, 2)
+    xp = F.pad(x.transpose(1, 2), ((kw - 1) // 2, kw - 1 - (kw - 1) // 2))     # 'same': the extra pad of an even kernel goes right
+    y = F.conv1d(xp, k.permute(2, 1, 0).contiguous(), params[prefix + "bias"]).transpose(1, 2)
     if activation == "relu":
         y = F.relu(y)
     elif activation == "tanh":
@@ -276,8 +306,71 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
     mel_outputs = decoder_output + residual
     if hp.clip_outputs:
         mel_outputs = torch.clamp(mel_outputs, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
-    return {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_logits": stop_logits,
-            "alignments": torch.stack(aligns, dim=1)}
+    out = {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_logits": stop_logits,
+           "alignments": torch.stack(aligns, dim=1)}
+    if hp.predict_linear and "cbhg_linear_specs_projection/kernel" in params:
+        out["linear_outputs"] = linear_head(mel_outputs, params, hp, training, stats_out)
+    return out
+
+
+def gru_cell(x, h, gk, gb, ck, cb):
+    """tf.nn.rnn_cell.GRUCell: r, u = split(sigmoid([x, h] Wg + bg)); c = tanh([x, r * h] Wc + bc); h' = u h + (1 - u) c."""
+    r, u = torch.sigmoid(torch.cat([x, h], dim=-1) @ gk + gb).chunk(2, dim=-1)
+    c = torch.tanh(torch.cat([x, r * h], dim=-1) @ ck + cb)
+    return u * h + (1 - u) * c
+
+
+def cbhg(x, params, hp, training, stats_out=None):
+    """CBHG (modules.py:19-78) as the post-processing net (`CBHG_postnet`, tacotron.py:203-210): conv bank K = 1..8 (ReLU, BN, no
+    dropout) -> max-pool(2, stride 1, 'same') -> two projection convs (ReLU / linear, BN) -> + input -> dense to the highway width ->
+    4 highway layers -> bidirectional GRU over the whole padded sequence (input_lengths = None). x [B, T, num_mels] -> [B, T, 2 n]."""
+    P = "CBHG_postnet/"
+    bank = torch.cat([conv_block(x, params, P + "conv_bank/conv1d_%d/" % k, "relu", training, 0.0, None, stats_out)
+                      for k in range(1, hp.cbhg_kernels + 1)], dim=-1)
+    ps = hp.cbhg_pool_size
+    # tf.layers.max_pooling1d(pool_size, strides=1, padding='same'): pad (ps - 1) // 2 left, the rest right, with -inf
+    mp = F.max_pool1d(F.pad(bank.transpose(1, 2), ((ps - 1) // 2, ps - 1 - (ps - 1) // 2), value=float("-inf")), ps, stride=1).transpose(1, 2)
+    p1 = conv_block(mp, params, P + "proj1/", "relu", training, 0.0, None, stats_out)
+    p2 = conv_block(p1, params, P + "proj2/", None, training, 0.0, None, stats_out)
+    h = p2 + x
+    if P + "dense/kernel" in params:
+        h = h @ params[P + "dense/kernel"] + params[P + "dense/bias"]
+    for i in range(hp.cbhg_highwaynet_layers):
+        q = P + "highwaynet_%d/" % (i + 1)
+        Hh = F.relu(h @ params[q + "H/kernel"] + params[q + "H/bias"])
+        Tt = torch.sigmoid(h @ params[q + "T/kernel"] + params[q + "T/bias"])
+        h = Hh * Tt + h * (1.0 - Tt)
+    B, T, _ = h.shape
+    n = hp.cbhg_rnn_units
+    outs = []
+    for d, order in (("forward", range(T)), ("backward", range(T - 1, -1, -1))):
+        q = P + d + "_RNN/"
+        st = torch.zeros(B, n)
+        seq = [None] * T
+        for t in order:
+            st = gru_cell(h[:, t], st, params[q + "gates/kernel"], params[q + "gates/bias"], params[q + "candidate/kernel"], params[q + "candidate/bias"])
+            seq[t] = st
+        outs.append(torch.stack(seq, dim=1))
+    return torch.cat(outs, dim=-1)
+
+
+def linear_head(mel_outputs, params, hp, training, stats_out=None):
+    """tacotron.py:203-219: CBHG(mel_outputs) -> Dense(num_freq) -> clip"""
+    y = cbhg(mel_outputs, params, hp, training, stats_out)
+    lin = y @ params["cbhg_linear_specs_projection/kernel"] + params["cbhg_linear_specs_projection/bias"]
+    if hp.clip_outputs:
+        lin = torch.clamp(lin, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+    return lin
+
+
+def linear_loss(linear_targets, linear_outputs, hp, targets_lengths=None):
+    """tacotron.py:323-330 (plain) / MaskedLinearLoss (modules.py:457-485): L1 with half of the weight on the bins below 2 kHz."""
+    l1 = (linear_targets - linear_outputs).abs()
+    n_prio = int(2000 / (hp.sample_rate * 0.5) * hp.num_freq)
+    if hp.mask_decoder:
+        mask = (torch.arange(linear_targets.shape[1])[None, :] < targets_lengths[:, None]).float().unsqueeze(-1) * torch.ones_like(linear_targets)
+        return 0.5 * (l1 * mask).sum() / mask.sum() + 0.5 * (l1 * mask)[:, :, :n_prio].sum() / mask.sum()
+    return 0.5 * l1.mean() + 0.5 * l1[:, :, :n_prio].mean()
 
 
 def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=None):
@@ -347,8 +440,14 @@ def masked_sigmoid_cross_entropy(targets, outputs, targets_lengths, pos_weight):
     return masked.sum() / torch.count_nonzero(masked).float()
 
 
-def loss_fn(out, mel_targets, stop_targets, params, hp, targets_lengths=None):
-    """tacotron.py:297-354: plain means over padded tensors (mask_decoder=False) or the masked variants, + L2 regulariser."""
+def loss_fn(out, mel_targets, stop_targets, params, hp, targets_lengths=None, linear_targets=None):
+    """tacotron.py:297-354: plain means over padded tensors (mask_decoder=False) or the masked variants, + L2 regulariser
+    (+ the linear-spectrogram L1 when the CBHG head is on)."""
+    if "linear_outputs" in out and linear_targets is not None:
+        total, parts = loss_fn({k: v for k, v in out.items() if k != "linear_outputs"}, mel_targets, stop_targets, params, hp, targets_lengths)
+        lin = linear_loss(linear_targets, out["linear_outputs"], hp, targets_lengths)
+        parts["linear"] = lin
+        return total + lin, parts
     if hp.mask_decoder:
         before = masked_mse(mel_targets, out["decoder_output"], targets_lengths)
         after = masked_mse(mel_targets, out["mel_outputs"], targets_lengths)
@@ -371,10 +470,10 @@ def learning_rate(hp, global_step):
     return min(max(lr, hp.tacotron_final_learning_rate), hp.tacotron_initial_learning_rate)
 
 
-def train_step(params, inputs, input_lengths, mel_targets, stop_targets, hp, masks=None, targets_lengths=None):
+def train_step(params, inputs, input_lengths, mel_targets, stop_targets, hp, masks=None, targets_lengths=None, linear_targets=None):
     ps = {k: (v.clone().requires_grad_(True) if is_trainable(k) else v.clone()) for k, v in params.items()}
     out = forward(ps, inputs, input_lengths, mel_targets, hp, True, masks)
-    loss, parts = loss_fn(out, mel_targets, stop_targets, ps, hp, targets_lengths)
+    loss, parts = loss_fn(out, mel_targets, stop_targets, ps, hp, targets_lengths, linear_targets)
     names = [k for k in ps if is_trainable(k)]
     gr = torch.autograd.grad(loss, [ps[k] for k in names], allow_unused=True)
     grads = {k: (g if g is not None else torch.zeros_like(ps[k])) for k, g in zip(names, gr)}

@@ -921,20 +921,21 @@ void build_tiles(const TL& lo, std::vector<WgL>& L) {
 // loss seeds: dmel = 2 (mel - tgt) / N * [not clipped] (bf16, 128-col padded) ; ddec_direct = dmel + 2 (dec - tgt) / N
 __global__ void loss_seed_kernel(const float* __restrict__ dec_f, const float* __restrict__ resid, const float* __restrict__ mel,
                                  const float* __restrict__ tgt, bf16* __restrict__ dmel, float* __restrict__ ddec, long long npos, int M,
-                                 int clip, float lo, float hi, const int* __restrict__ tlen, int To, const float* __restrict__ scal) {
+                                 int clip, float lo, float hi, const int* __restrict__ tlen, int To, const float* __restrict__ scal,
+                                 const float* __restrict__ extra) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= npos * 128) return;
   const long long pos = e / 128; const int m = int(e % 128);
   float g = 0.f;
-  if (m < M && tlen && int(pos % To) >= tlen[pos / To]) ddec[pos * M + m] = 0.f;     // masked frame: no loss gradient
-  else
   if (m < M) {
     const long long o = pos * M + m;
     const float n = scal[5];
     const float raw = dec_f[o] + resid[pos * 128 + m];
-    g = 2.f * (mel[o] - tgt[o]) / n;
+    const bool masked = tlen && int(pos % To) >= tlen[pos / To];             // masked frame: no mel-loss gradient
+    g = masked ? 0.f : 2.f * (mel[o] - tgt[o]) / n;
+    if (extra) g += extra[o];          // gradient of the post-processing net w.r.t. the clipped mel_outputs (not masked: its convs / GRU mix frames)
     if (clip && (raw < lo || raw > hi)) g = 0.f;
-    ddec[o] = g + 2.f * (dec_f[o] - tgt[o]) / n;
+    ddec[o] = g + (masked ? 0.f : 2.f * (dec_f[o] - tgt[o]) / n);
   }
   dmel[e] = __float2bfloat16(g);
 }
@@ -1785,6 +1786,14 @@ extern "C" int t2_taco_set_target_lengths(const t2_taco_config_t* cfg, void* d_w
 extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
                                 const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets, const float* d_stop_targets,
                                 float* d_grads, unsigned long long seed, const unsigned long long* d_step, void* stream) {
+  return t2_taco_backward_ex(cfg, d_params, d_packed, d_workspace, d_inputs, d_input_lengths, d_mel_targets, d_stop_targets, d_grads, nullptr, seed,
+                             d_step, stream);
+}
+
+extern "C" int t2_taco_backward_ex(const t2_taco_config_t* cfg, const float* d_params, const void* d_packed, void* d_workspace,
+                                   const int* d_inputs, const int* d_input_lengths, const float* d_mel_targets, const float* d_stop_targets,
+                                   float* d_grads, const float* d_mel_outputs_grad, unsigned long long seed, const unsigned long long* d_step,
+                                   void* stream) {
   TL lo;
   int rc = build(cfg, lo, nullptr);
   if (rc) return rc;
@@ -1816,7 +1825,7 @@ extern "C" int t2_taco_backward(const t2_taco_config_t* cfg, const float* d_para
   // ---- loss seeds + postnet ----
   loss_seed_kernel<<<g1(BTo * 128), 256, 0, st>>>(reinterpret_cast<float*>(ws + lo.w_decf), reinterpret_cast<float*>(ws + lo.w_resid),
                                                   reinterpret_cast<float*>(ws + lo.w_mel), d_mel_targets, dmel, ddecf, BTo, M, lo.c.clip_outputs,
-                                                  lo_c, hi_c, tlen, To, scal); t2_count_launch();
+                                                  lo_c, hi_c, tlen, To, scal, d_mel_outputs_grad); t2_count_launch();
   rc = conv_gemm(dmel, 128, To, B, pk + lo.k_ppT, lo.PC, 128, 1, nullptr, lo.PC % 256 == 0 ? 256 : 128, nullptr, 0, dY0, nullptr, lo.PC, lo.PC, 0.f, 0, 0,
                  nullptr, st);
   if (rc) return rc;

@@ -65,6 +65,10 @@ def tacotron_variables(hp, tensors, seed=None):
     for name, _, shape, _ in tensors:
         if name.endswith(("gamma", "moving_variance")):
             out[name] = torch.ones(shape)
+        elif name.endswith("RNN/gates/bias"):
+            out[name] = torch.ones(shape)            # tf.nn.rnn_cell.GRUCell: gate bias initialiser 1.0
+        elif "/T/bias" in name:
+            out[name] = -torch.ones(shape)           # HighwayNet transform gate, tacotron/models/modules.py:10
         elif name.endswith(("beta", "moving_mean", "bias")):
             out[name] = torch.zeros(shape)
         else:

@@ -19,6 +19,27 @@ class TacoConfig(ctypes.Structure):
         ("split_bf16", ctypes.c_int), ("mask_decoder", ctypes.c_int), ("cross_entropy_pos_weight", ctypes.c_float)]
 
 
+class CbhgConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "B", "T", "num_mels", "kernels", "conv_channels", "pool_size", "projection", "projection_kernel_size", "highwaynet_layers",
+        "highway_units", "rnn_units", "num_freq", "n_priority_freq", "clip_outputs", "mask_decoder")] + [
+        (n, ctypes.c_float) for n in ("max_abs_value", "lower_bound_decay", "reg_weight")]
+
+
+def make_cbhg_config(hp, B, T, reg_weight):
+    """CBHG post-processing net + linear head (tacotron.py:203-219); the shapes the CUDA path implements are checked by t2_cbhg_sizes"""
+    c = CbhgConfig()
+    c.B, c.T, c.num_mels = B, T, hp.num_mels
+    c.kernels, c.conv_channels, c.pool_size = hp.cbhg_kernels, hp.cbhg_conv_channels, hp.cbhg_pool_size
+    c.projection, c.projection_kernel_size = hp.cbhg_projection, hp.cbhg_projection_kernel_size
+    c.highwaynet_layers, c.highway_units, c.rnn_units = hp.cbhg_highwaynet_layers, hp.cbhg_highway_units, hp.cbhg_rnn_units
+    c.num_freq = hp.num_freq
+    c.n_priority_freq = int(2000 / (hp.sample_rate * 0.5) * hp.num_freq)
+    c.clip_outputs, c.mask_decoder = int(hp.clip_outputs), int(bool(hp.mask_decoder))
+    c.max_abs_value, c.lower_bound_decay, c.reg_weight = hp.max_abs_value, hp.lower_bound_decay, reg_weight
+    return c
+
+
 def unsupported_hparams(hp):
     """hparam-gated variants of the reference graph that change the arithmetic and that this path does NOT implement: every one
     is rejected instead of silently training a different model. Returns a list of human-readable reasons."""
@@ -27,7 +48,12 @@ def unsupported_hparams(hp):
         if name in hp and not ok(getattr(hp, name)):
             bad.append("%s=%r (%s)" % (name, getattr(hp, name), why))
     need("outputs_per_step", lambda v: v == 1, "reduction factor r > 1: tacotron.py:141-143, helpers.py:77")
-    need("predict_linear", lambda v: not v, "CBHG post-processing net + linear loss: tacotron.py:203-219, modules.py:19-78")
+    if getattr(hp, "predict_linear", False):
+        need("cbhg_pool_size", lambda v: v == 2, "CBHG max-pool width 2")
+        need("cbhg_kernels", lambda v: 1 <= v <= 8, "CBHG convolution bank of at most 8 kernel sizes")
+        need("cbhg_conv_channels", lambda v: v == 128, "CBHG bank of 128 channels")
+        need("cbhg_highway_units", lambda v: v == 128, "128 highway units")
+        need("cbhg_rnn_units", lambda v: v == 128, "128 GRU units")
     need("prenet_layers", lambda v: len(v) == 2, "2 prenet layers")
     need("decoder_layers", lambda v: v == 2, "2 decoder LSTM layers")
     need("smoothing", lambda v: not v, "smoothing normalisation instead of softmax: attention.py:72-92")
@@ -80,8 +106,23 @@ class Tacotron(object):
         self.cfg = make_config(hparams, B, T_in, T_out, precision)
         n, pb, wb, nt = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
         L.check(self.lib.t2_taco_sizes(ctypes.byref(self.cfg), ctypes.byref(n), ctypes.byref(pb), ctypes.byref(wb), ctypes.byref(nt)))
-        self.n_params = n.value
-        self.params = torch.zeros(n.value, dtype=torch.float32, device=self.device)
+        self.n_taco = n.value
+        self.cbhg = None
+        n_cb = 0
+        if getattr(hparams, "predict_linear", False):       # CBHG + linear head: a second engine chained on mel_outputs (include/t2b200.h)
+            if precision != "bf16":
+                raise L.T2Error("predict_linear has no fp32-class mode")
+            self.cbhg = make_cbhg_config(hparams, B, T_out, self.cfg.reg_weight)
+            cn, cpb, cwb, cnt = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
+            L.check(self.lib.t2_cbhg_sizes(ctypes.byref(self.cbhg), ctypes.byref(cn), ctypes.byref(cpb), ctypes.byref(cwb), ctypes.byref(cnt)))
+            n_cb = cn.value
+            self.cb_packed = torch.empty(cpb.value, dtype=torch.uint8, device=self.device)
+            self.cb_workspace = torch.empty(cwb.value, dtype=torch.uint8, device=self.device)
+            self.cb_loss = torch.zeros(2, dtype=torch.float32, device=self.device)
+            self.cb_dmel = torch.zeros(B * T_out * hparams.num_mels, dtype=torch.float32, device=self.device)
+            self._cb_ntensors = cnt.value
+        self.n_params = n.value + n_cb
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=self.device)
         self.packed = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
         self.workspace = torch.empty(wb.value, dtype=torch.uint8, device=self.device)
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
@@ -92,13 +133,19 @@ class Tacotron(object):
         for i in range(nt.value):
             L.check(self.lib.t2_taco_param_info(ctypes.byref(self.cfg), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp, ctypes.byref(tr)))
             self.tensors.append((name.value.decode(), off.value, tuple(shp[k] for k in range(nd.value)), bool(tr.value)))
-        self.offsets = torch.tensor([t[1] for t in self.tensors] + [n.value], dtype=torch.int64, device=self.device)
+        if self.cbhg is not None:
+            for i in range(self._cb_ntensors):
+                L.check(self.lib.t2_cbhg_param_info(ctypes.byref(self.cbhg), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp, ctypes.byref(tr)))
+                self.tensors.append((name.value.decode(), self.n_taco + off.value, tuple(shp[k] for k in range(nd.value)), bool(tr.value)))
+        self.offsets = torch.tensor([t[1] for t in self.tensors] + [self.n_params], dtype=torch.int64, device=self.device)
         self.opt_scratch = torch.zeros(len(self.tensors) + 2, dtype=torch.float32, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.global_step = 0
         self.seed = int(hparams.tacotron_random_seed)
         with torch.cuda.device(self.device):
             L.check(self.lib.t2_taco_init(ctypes.byref(self.cfg), L.ptr(self.packed), L.ptr(self.workspace), L.stream_ptr()))
+            if self.cbhg is not None:
+                L.check(self.lib.t2_cbhg_init(ctypes.byref(self.cbhg), L.ptr(self.cb_packed), L.ptr(self.cb_workspace), L.stream_ptr()))
         self._dirty = True
 
     def load_params(self, params):
@@ -125,10 +172,14 @@ class Tacotron(object):
 
     def pack(self):
         L.check(self.lib.t2_taco_pack_weights(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace), L.stream_ptr()))
+        if self.cbhg is not None:
+            L.check(self.lib.t2_cbhg_pack_weights(ctypes.byref(self.cbhg), L.ptr(self.params[self.n_taco:]), L.ptr(self.cb_packed),
+                                                  L.ptr(self.cb_workspace), L.stream_ptr()))
         self._dirty = False
 
-    def forward(self, inputs, input_lengths, mel_targets, stop_targets, training=True, seed=None, targets_lengths=None):
-        """targets_lengths: int32 [B] device tensor, required when hparams.mask_decoder (masked losses, modules.py:412-455)"""
+    def forward(self, inputs, input_lengths, mel_targets, stop_targets, training=True, seed=None, targets_lengths=None, linear_targets=None):
+        """targets_lengths: int32 [B] device tensor, required when hparams.mask_decoder (masked losses, modules.py:412-455);
+        linear_targets: fp32 [B, T_out, num_freq], required in training when hparams.predict_linear (tacotron.py:45-46)"""
         if self._dirty:
             self.pack()
         if self.cfg.mask_decoder:
@@ -141,17 +192,65 @@ class Tacotron(object):
                                          L.ptr(inputs), L.ptr(input_lengths), L.ptr(mel_targets), L.ptr(stop_targets),
                                          L.ptr(self.loss_buf), int(training), ctypes.c_ulonglong(self._last_seed),
                                          L.ptr(self.step_dev), L.stream_ptr()))
+        if self.cbhg is not None:
+            if training and linear_targets is None:
+                raise L.T2Error("Model is set to use post processing to predict linear spectrograms in training but no linear targets given!")
+            if self.cfg.mask_decoder:
+                L.check(self.lib.t2_cbhg_set_target_lengths(ctypes.byref(self.cbhg), L.ptr(self.cb_workspace), L.ptr(targets_lengths), L.stream_ptr()))
+            self._last_linear = linear_targets
+            mel = self.workspace_tensor("mel_outputs")
+            L.check(self.lib.t2_cbhg_forward(ctypes.byref(self.cbhg), L.ptr(self.params[self.n_taco:]), L.ptr(self.cb_packed), L.ptr(self.cb_workspace),
+                                             L.ptr(mel), L.ptr(linear_targets), L.ptr(self.cb_loss), int(training), L.stream_ptr()))
         return self.loss_buf
 
     def backward(self):
         if self.grads is None:
             self.grads = torch.zeros_like(self.params)
         inputs, input_lengths, mel_targets, stop_targets = self._last
-        L.check(self.lib.t2_taco_backward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace),
-                                          L.ptr(inputs), L.ptr(input_lengths), L.ptr(mel_targets), L.ptr(stop_targets),
-                                          L.ptr(self.grads), ctypes.c_ulonglong(self._last_seed), L.ptr(self.step_dev),
-                                          L.stream_ptr()))
+        extra = None
+        if self.cbhg is not None:      # the post-processing net first: it yields the extra gradient on mel_outputs
+            L.check(self.lib.t2_cbhg_backward(ctypes.byref(self.cbhg), L.ptr(self.params[self.n_taco:]), L.ptr(self.cb_packed), L.ptr(self.cb_workspace),
+                                              L.ptr(self.workspace_tensor("mel_outputs")), L.ptr(self.grads[self.n_taco:]), L.ptr(self.cb_dmel),
+                                              L.stream_ptr()))
+            extra = self.cb_dmel
+        L.check(self.lib.t2_taco_backward_ex(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed), L.ptr(self.workspace),
+                                             L.ptr(inputs), L.ptr(input_lengths), L.ptr(mel_targets), L.ptr(stop_targets),
+                                             L.ptr(self.grads), L.ptr(extra), ctypes.c_ulonglong(self._last_seed), L.ptr(self.step_dev),
+                                             L.stream_ptr()))
         return self.grads
+
+    def linear_outputs(self):
+        """[B, T_out, num_freq] fp32 (clipped) of the last forward (predict_linear)"""
+        p, cnt = ctypes.c_void_p(), ctypes.c_longlong()
+        L.check(self.lib.t2_cbhg_workspace_tensor(ctypes.byref(self.cbhg), L.ptr(self.cb_workspace), b"linear_outputs", ctypes.byref(p), ctypes.byref(cnt)))
+        off = p.value - self.cb_workspace.data_ptr()
+        nfp = (self.hp.num_freq + 7) // 8 * 8
+        return self.cb_workspace[off:off + cnt.value * 4].view(torch.float32).reshape(self.cfg.B, self.cfg.T_out, nfp)[:, :, :self.hp.num_freq]
+
+    def linear_from_mel(self, mel):
+        """Inference-mode post-processing net on finished mel_outputs [B, T, num_mels] (synthesis: tacotron.py:203-219 with
+        is_training = False) -> linear spectrogram [B, T, num_freq]. Runs a CBHG engine sized for this (B, T)."""
+        if self._dirty:
+            self.pack()
+        B0, T = int(mel.shape[0]), int(mel.shape[1])
+        B = (B0 + 3) // 4 * 4                                   # the recurrent kernel takes items in fours; rows are independent here
+        x = torch.zeros(B, max(T, 2), self.hp.num_mels, dtype=torch.float32, device=self.device)
+        x[:B0, :T] = mel.float()
+        cfg = make_cbhg_config(self.hp, B, max(T, 2), 0.0)
+        cfg.mask_decoder = 0
+        pb, wb = ctypes.c_longlong(), ctypes.c_longlong()
+        L.check(self.lib.t2_cbhg_sizes(ctypes.byref(cfg), None, ctypes.byref(pb), ctypes.byref(wb), None))
+        packed = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
+        ws = torch.empty(wb.value, dtype=torch.uint8, device=self.device)
+        prm = self.params[self.n_taco:]
+        L.check(self.lib.t2_cbhg_init(ctypes.byref(cfg), L.ptr(packed), L.ptr(ws), L.stream_ptr()))
+        L.check(self.lib.t2_cbhg_pack_weights(ctypes.byref(cfg), L.ptr(prm), L.ptr(packed), L.ptr(ws), L.stream_ptr()))
+        L.check(self.lib.t2_cbhg_forward(ctypes.byref(cfg), L.ptr(prm), L.ptr(packed), L.ptr(ws), L.ptr(x), L.ptr(None), L.ptr(None), 0, L.stream_ptr()))
+        p, cnt = ctypes.c_void_p(), ctypes.c_longlong()
+        L.check(self.lib.t2_cbhg_workspace_tensor(ctypes.byref(cfg), L.ptr(ws), b"linear_outputs", ctypes.byref(p), ctypes.byref(cnt)))
+        off = p.value - ws.data_ptr()
+        nfp = (self.hp.num_freq + 7) // 8 * 8
+        return ws[off:off + cnt.value * 4].view(torch.float32).reshape(B, max(T, 2), nfp)[:B0, :T, :self.hp.num_freq].clone()
 
     def synthesize(self, inputs, input_lengths, max_iters=None, chunk=64, seed=None):
         """Free-running synthesis (TacoTestHelper, helpers.py:6-59): feed back the predicted frame, stop after the first
@@ -186,16 +285,17 @@ class Tacotron(object):
                 "stop_token_prediction": torch.sigmoid(self.workspace_tensor("stop_logits", (B, T_used))),
                 "alignments": self.workspace_tensor("alignments", (self.cfg.T_out, B, Ti))[:T_used].transpose(0, 1).clone()}
 
-    def capture(self, inputs, input_lengths, mel_targets, stop_targets):
+    def capture(self, inputs, input_lengths, mel_targets, stop_targets, linear_targets=None, targets_lengths=None):
         """Capture pack + forward + backward (~7.5k kernel nodes at B=32, T_out=800) into one CUDA graph over static inputs."""
         self._static = (inputs, input_lengths, mel_targets, stop_targets)
+        self._static_kw = dict(linear_targets=linear_targets, targets_lengths=targets_lengths)
         if self.grads is None:
             self.grads = torch.zeros_like(self.params)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self.pack()
-            self.forward(*self._static)
+            self.forward(*self._static, **self._static_kw)
             self.backward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -204,22 +304,24 @@ class Tacotron(object):
         with torch.cuda.graph(self._graph):
             self.step_dev.add_(1)
             self.pack()
-            self.forward(*self._static)
+            self.forward(*self._static, **self._static_kw)
             self.backward()
         self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
         return self._graph
 
-    def train_step(self, inputs=None, input_lengths=None, mel_targets=None, stop_targets=None, world_size=1):
+    def train_step(self, inputs=None, input_lengths=None, mel_targets=None, stop_targets=None, world_size=1, linear_targets=None,
+                   targets_lengths=None):
         """forward + losses + backward (+ NCCL all-reduce) + clip_by_global_norm + Adam (tacotron.py:406-437 order)."""
         if getattr(self, "_graph", None) is not None:
-            for dst, src in zip(self._static, (inputs, input_lengths, mel_targets, stop_targets)):
-                if src is not None and src is not dst:
+            for dst, src in zip(self._static + (self._static_kw["linear_targets"], self._static_kw["targets_lengths"]),
+                                (inputs, input_lengths, mel_targets, stop_targets, linear_targets, targets_lengths)):
+                if src is not None and dst is not None and src is not dst:
                     dst.copy_(src, non_blocking=True)
             self._graph.replay()
         else:
             n0 = self.lib.t2_launch_count()
             self.step_dev.add_(1)
-            self.forward(inputs, input_lengths, mel_targets, stop_targets)
+            self.forward(inputs, input_lengths, mel_targets, stop_targets, linear_targets=linear_targets, targets_lengths=targets_lengths)
             self.backward()
             self._fwd_bwd_launches = self.lib.t2_launch_count() - n0
         if world_size > 1:
@@ -285,4 +387,9 @@ class Tacotron(object):
 
     def losses(self):
         b, a, s, r = self.loss_buf.tolist()
-        return {"before": b, "after": a, "stop": s, "reg": r, "total": b + a + s + r}
+        out = {"before": b, "after": a, "stop": s, "reg": r, "linear": 0.0}
+        if self.cbhg is not None:
+            lin, rc = self.cb_loss.tolist()
+            out["linear"], out["reg"] = lin, r + rc       # one regulariser over all variables (tacotron.py:343-345)
+        out["total"] = out["before"] + out["after"] + out["stop"] + out["reg"] + out["linear"]
+        return out

@@ -77,7 +77,9 @@ class Feeder(object):
         ids = np.asarray(text_to_sequence(meta[5], self._cleaner_names), dtype=np.int32)
         mel = np.load(os.path.join(self._mel_dir, meta[1]))
         token = np.zeros(len(mel) - 1, dtype=np.float32)
-        return ids, mel, token, len(mel)
+        # linear-spectrogram target of the post-processing net (tacotron/feeder.py:136-139 loads it unconditionally; here only when used)
+        linear = np.load(os.path.join(self._linear_dir, meta[2])) if getattr(self._hparams, "predict_linear", False) else None
+        return ids, mel, token, linear, len(mel)
 
     def _next_example(self):
         if self._train_offset >= len(self._train_meta):
@@ -88,7 +90,7 @@ class Feeder(object):
         return self._load(meta)
 
     def prepare_batch(self, batch):
-        """list of (ids, mel [frames, num_mels], token [frames - 1], frames) -> dict of numpy arrays"""
+        """list of (ids, mel [frames, num_mels], token [frames - 1], linear [frames, num_freq] | None, frames) -> dict of numpy arrays"""
         r = self._hparams.outputs_per_step
         in_len = max(len(x[0]) for x in batch)
         mel_len = _round_up(max(len(x[1]) for x in batch), r)
@@ -97,7 +99,9 @@ class Feeder(object):
                 "input_lengths": np.asarray([len(x[0]) for x in batch], dtype=np.int32),
                 "mel_targets": np.stack([pad_target(x[1], mel_len, self._target_pad) for x in batch]).astype(np.float32),
                 "token_targets": np.stack([pad_token_target(x[2], tok_len, self._token_pad) for x in batch]).astype(np.float32),
-                "targets_lengths": np.asarray([x[3] for x in batch], dtype=np.int32)}
+                "targets_lengths": np.asarray([x[-1] for x in batch], dtype=np.int32),
+                **({"linear_targets": np.stack([pad_target(x[3], mel_len, self._target_pad) for x in batch]).astype(np.float32)}
+                   if batch[0][3] is not None else {})}
 
     def train_group(self):
         n = self._hparams.tacotron_batch_size

@@ -6,7 +6,8 @@ otherwise), `add_loss()` publishes the four loss terms, `add_optimizer(global_st
 + clip_by_global_norm + Adam. Attribute names read by tacotron/train.py and tacotron/synthesizer.py are kept
 (`tower_mel_outputs`, `tower_alignments`, `tower_stop_token_prediction`, `tower_decoder_output`, `loss`,
 `before_loss`, `after_loss`, `stop_token_loss`, `regularization_loss`, `learning_rate`, `gradients`). One process per
-GPU replaces the towers. predict_linear / CBHG and outputs_per_step > 1 are not implemented."""
+GPU replaces the towers. predict_linear (CBHG post-processing net + linear head, tacotron.py:203-219) runs as a second engine chained on
+mel_outputs; outputs_per_step > 1 is not implemented."""
 import collections
 
 import torch
@@ -71,8 +72,9 @@ class Tacotron(object):
             raise RuntimeError("Model set to mask paddings but no targets lengths provided for the mask!")
         if is_training and is_evaluating:
             raise RuntimeError("Model can not be in training and evaluation modes at the same time!")
-        if hp.predict_linear or hp.outputs_per_step != 1 or hp.mask_decoder:
-            raise NotImplementedError("predict_linear / outputs_per_step > 1 are out of scope (SURVEY.md §8)")
+        if hp.outputs_per_step != 1:
+            raise NotImplementedError("outputs_per_step > 1 is out of scope (SURVEY.md §8)")
+        post_condition = hp.predict_linear and not gta                 # tacotron.py:109
         self.is_training, self.is_evaluating, self.gta = is_training, is_evaluating, gta
         B, T_in = inputs.shape
         ids, lens = inputs.int().contiguous(), input_lengths.int().contiguous()
@@ -83,8 +85,16 @@ class Tacotron(object):
                 eng.global_step = int(global_step)
             stop = stop_token_targets if stop_token_targets is not None else torch.zeros(B, T_out, device=inputs.device)
             eng.step_dev.add_(1)
-            eng.forward(ids, lens, mel_targets.float().contiguous(), stop.float().contiguous(), training=is_training,
-                        targets_lengths=targets_lengths.int().contiguous() if (hp.mask_decoder and targets_lengths is not None) else None)
+            lin_t = linear_targets.float().contiguous() if (post_condition and linear_targets is not None) else None
+            if post_condition and lin_t is None:                     # evaluation without linear targets: run the head without a loss
+                is_lin_train = False
+            else:
+                is_lin_train = is_training
+            eng.forward(ids, lens, mel_targets.float().contiguous(), stop.float().contiguous(), training=is_training and (is_lin_train or not post_condition),
+                        targets_lengths=targets_lengths.int().contiguous() if (hp.mask_decoder and targets_lengths is not None) else None,
+                        linear_targets=lin_t)
+            if post_condition:
+                self.tower_linear_outputs = [eng.linear_outputs()]
             M = hp.num_mels
             self.tower_decoder_output = [eng.workspace_tensor("decoder_output", (B, T_out, M))]
             self.tower_mel_outputs = [eng.workspace_tensor("mel_outputs", (B, T_out, M))]
@@ -99,7 +109,10 @@ class Tacotron(object):
             self.tower_mel_outputs = [out["mel_outputs"]]
             self.tower_alignments = [out["alignments"]]
             self.tower_stop_token_prediction = [out["stop_token_prediction"]]
+            if post_condition:
+                self.tower_linear_outputs = [eng.linear_from_mel(out["mel_outputs"])]
         self._eng = eng
+        self.tower_linear_targets = [linear_targets]
         self.tower_inputs, self.tower_input_lengths = [inputs], [input_lengths]
         self.tower_mel_targets, self.tower_targets_lengths = [mel_targets], [targets_lengths]
         self.tower_stop_token_targets = [stop_token_targets]
@@ -112,9 +125,14 @@ class Tacotron(object):
         self.tower_before_loss, self.tower_after_loss = [b[0]], [b[1]]
         self.tower_stop_token_loss, self.tower_regularization_loss = [b[2]], [b[3]]
         self.tower_linear_loss = [torch.zeros((), device=b.device)]
-        self.before_loss, self.after_loss, self.stop_token_loss, self.regularization_loss = b[0], b[1], b[2], b[3]
+        reg = b[3]
+        if self._eng.cbhg is not None:                               # tacotron.py:323-345: linear L1 + the CBHG kernels in the regulariser
+            self.tower_linear_loss = [self._eng.cb_loss[0]]
+            reg = b[3] + self._eng.cb_loss[1]
+            self.tower_regularization_loss = [reg]
+        self.before_loss, self.after_loss, self.stop_token_loss, self.regularization_loss = b[0], b[1], b[2], reg
         self.linear_loss = self.tower_linear_loss[0]
-        self.tower_loss = [b.sum()]
+        self.tower_loss = [b[0] + b[1] + b[2] + reg + self.linear_loss]
         self.loss = self.tower_loss[0]
         return self.loss
 

@@ -41,8 +41,8 @@ def _cuda(batch):
 
 def _run_model(model, b, step, is_training, is_evaluating=False):
     stop = b["token_targets"]
-    model.initialize(b["inputs"], b["input_lengths"], b["mel_targets"], stop, targets_lengths=b["targets_lengths"],
-                     global_step=step, is_training=is_training, is_evaluating=is_evaluating)
+    model.initialize(b["inputs"], b["input_lengths"], b["mel_targets"], stop, linear_targets=b.get("linear_targets"),
+                     targets_lengths=b["targets_lengths"], global_step=step, is_training=is_training, is_evaluating=is_evaluating)
     return model.add_loss()
 
 

@@ -20,6 +20,7 @@ def _make_dataset(root, n=48, hop=275, seed=0):
         frames = int(rng.integers(20, 90))
         np.save(os.path.join(root, "audio", "audio-%d.npy" % i), rng.integers(0, 256, frames * hop).astype(np.int16))
         np.save(os.path.join(root, "mels", "mel-%d.npy" % i), rng.uniform(-4.5, 4.5, (frames, 80)).astype(np.float32))
+        np.save(os.path.join(root, "linear", "linear-%d.npy" % i), rng.uniform(-4.5, 4.5, (frames, 1025)).astype(np.float32))
         text = "".join(rng.choice(list("abcdefghij klmnop, qrstu!"), int(rng.integers(8, 40))))
         rows.append("audio-%d.npy|mel-%d.npy|linear-%d.npy|%d|%d|%s" % (i, i, i, frames * hop, frames, text))
     path = os.path.join(root, "train.txt")
@@ -67,6 +68,9 @@ def test_tacotron_feeder_batches(tmp_path):
             n, L = int(b["targets_lengths"][i]), int(b["input_lengths"][i])
             assert (b["inputs"][i, L:] == 0).all() and b["inputs"][i, L - 1] == 1               # zero padding after the EOS id
             assert (b["mel_targets"][i, n:] == -hp.max_abs_value).all()                         # symmetric mels: pad with -max_abs_value
+            if hp.predict_linear:       # the reference default: linear targets of the post-processing net, padded like the mels
+                assert b["linear_targets"].shape == (4, b["mel_targets"].shape[1], hp.num_freq)
+                assert (b["linear_targets"][i, n:] == -hp.max_abs_value).all() and (b["linear_targets"][i, :n] != -hp.max_abs_value).any()
             assert (b["token_targets"][i, :n - 1] == 0).all() and (b["token_targets"][i, n - 1:] == 1).all()
     # batches of a group hold utterances of similar length (sorted in groups of 32 batches, then shuffled)
     spans = [int(b["targets_lengths"].max() - b["targets_lengths"].min()) for b in group]

@@ -14,7 +14,7 @@ timeout 900 ncu --metrics $M --clock-control none --cache-control none -s 20000 
   python bench.py --workload tacotron --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r2_ncu_tacotron.log 2>&1
 # full captures: 2 launches of each hot kernel from the middle of the run
 full() {  # name regex skip workload
-  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c 2 -o gpurun_out/r2_full_$1 -f \
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 2 -o gpurun_out/r2_full_$1 -f \
     python bench.py --workload $4 --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/r2_ncu_full_$1.log 2>&1
 }
 full gate  'act_gemm2_kernel<\(int\)0'  40 wavenet_ce
@@ -22,6 +22,7 @@ full out   'act_gemm2_kernel<\(int\)1'  40 wavenet_ce
 full dz    'act_gemm2_kernel<\(int\)6'  40 wavenet_ce
 full dx    'act_gemm2_kernel<\(int\)7'  40 wavenet_ce
 full wgrad 'wgrad_gemm_kernel'          3  wavenet_ce
+full gate_default 'act_gemm2_kernel<\(int\)0'  30 wavenet_default
 full lstm  'act_gemm_kernel<\(int\)8'   2000 tacotron
 full tout  'act_gemm_kernel<\(int\)9'   2000 tacotron
 full attf  'att_fwd_kernel'             1000 tacotron
