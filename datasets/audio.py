@@ -4,7 +4,8 @@ a CUDA device or the built library these functions raise.
 
 Covered (reference datasets/audio.py line numbers): preemphasis :22-25, get_hop_size :54-59, linearspectrogram
 :61-68, melspectrogram :70-77, librosa_pad_lr :210-219; plus the mu-law family of wavenet_vocoder/util.py.
-Griffin-Lim / LWS inversion, wav IO and trim_silence are outside the hot path.
+Inversion: inv_linear_spectrogram :118-133 / inv_mel_spectrogram :97-112 through a GPU Griffin-Lim (:151-161); the LWS option
+(`use_lws`, an external C library) is not provided.
 """
 import numpy as np
 import torch
@@ -51,6 +52,55 @@ def linearspectrogram(wav, hparams):
     """wav: 1-D float array -> [n_fft/2+1, frames] float32 (audio.py:61-68)."""
     _, lin = _fe(hparams)(_to_dev(wav), time_major=False, linear=True)
     return lin[0].cpu().numpy()
+
+
+def _denormalize(D, hparams):
+    """inverse of the [-max_abs, max_abs] (symmetric) / [0, max_abs] scaling of the dB spectrogram (audio.py:272-284)"""
+    m, floor = hparams.max_abs_value, hparams.min_level_db
+    if hparams.allow_clipping_in_normalization:
+        D = np.clip(D, -m if hparams.symmetric_mels else 0, m)
+    if hparams.symmetric_mels:
+        return (D + m) * -floor / (2 * m) + floor
+    return D * -floor / m + floor
+
+
+def _db_to_amp(x):
+    return np.power(10.0, x * 0.05)
+
+
+def _griffin_lim(S, hparams, seed=0):
+    """S: [bins, frames] magnitudes -> waveform (audio.py:151-161); phases are re-estimated hparams.griffin_lim_iters times on the GPU"""
+    mag = torch.from_numpy(np.ascontiguousarray(np.abs(S).T, dtype=np.float32))[None].cuda()
+    return _fe(hparams).griffin_lim(mag, hparams.griffin_lim_iters, seed=seed)[0].cpu().numpy()
+
+
+def _lin_to_wav(S, hparams):
+    if getattr(hparams, "use_lws", False):
+        raise NotImplementedError("use_lws: the LWS phase reconstruction library is not part of this repo (datasets/audio.py:126-130)")
+    return inv_preemphasis(_griffin_lim(S ** hparams.power, hparams), hparams.preemphasis, hparams.preemphasize)
+
+
+def inv_linear_spectrogram(linear_spectrogram, hparams):
+    """[n_fft/2+1, frames] normalised dB spectrogram -> waveform (audio.py:118-133)"""
+    D = _denormalize(linear_spectrogram, hparams) if hparams.signal_normalization else linear_spectrogram
+    return _lin_to_wav(_db_to_amp(D + hparams.ref_level_db) ** (1 / hparams.magnitude_power), hparams)
+
+
+_inv_mel = {}
+
+
+def _mel_to_linear(mel, hparams):
+    """pseudo-inverse of the mel filterbank, floored at 1e-10 (audio.py:231-241)"""
+    fe = _fe(hparams)
+    if id(fe) not in _inv_mel:
+        _inv_mel[id(fe)] = np.linalg.pinv(fe.mel_basis())
+    return np.maximum(1e-10, np.dot(_inv_mel[id(fe)], mel))
+
+
+def inv_mel_spectrogram(mel_spectrogram, hparams):
+    """[num_mels, frames] normalised dB mel spectrogram -> waveform (audio.py:97-112)"""
+    D = _denormalize(mel_spectrogram, hparams) if hparams.signal_normalization else mel_spectrogram
+    return _lin_to_wav(_mel_to_linear(_db_to_amp(D + hparams.ref_level_db) ** (1 / hparams.magnitude_power), hparams), hparams)
 
 
 def melspectrogram_batch(wavs, hparams, preemphasis_coef=0.0, gain=1.0):

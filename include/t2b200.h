@@ -232,7 +232,7 @@ int t2_taco_workspace_tensor(const t2_taco_config_t* cfg, void* d_workspace, con
  * returns d(linear loss + its regulariser)/d(mel_outputs), which t2_taco_backward_ex adds to the mel loss seed. Parameters, gradients
  * and Adam moments are sub-ranges of the caller's flat buffers (one optimizer step / one global-norm clip over both engines). */
 typedef struct {
-  int B, T;                  /* batch items (multiple of 4), decoder steps (= mel frames) */
+  int B, T;                  /* batch items, decoder steps (= mel frames, >= 2) */
   int num_mels;              /* 80 */
   int kernels;               /* cbhg_kernels: convolution bank sizes 1..kernels (<= 8) */
   int conv_channels;         /* cbhg_conv_channels (128) */
@@ -300,6 +300,17 @@ int t2_stft_mel_frames(const t2_audio_config_t* cfg, int n_samples);
  * d_linear: NULL or fp32 [B][frames][n_fft/2+1] / [B][n_fft/2+1][frames]. */
 int t2_stft_mel_f32(const t2_audio_config_t* cfg, const void* d_plan, const float* d_wav, int B, int n_samples,
                     float preemphasis, float gain, float* d_mel, float* d_linear, int time_major, void* stream);
+/* dense Slaney mel filterbank the fused kernel uses (librosa.filters.mel as called by datasets/audio.py:243-246): HOST double
+ * [num_mels][n_fft/2 + 1]; its pseudo-inverse is the reference's _mel_to_linear (audio.py:231-241) */
+int t2_mel_basis_f64(const t2_audio_config_t* cfg, double* h_basis);
+/* Griffin-Lim phase reconstruction on the GPU: replaces datasets/audio.py:151-161 (_griffin_lim: librosa istft / stft iterations)
+ * and :163-176 (the TF-graph variant). d_mag: fp32 [B][frames][n_fft/2+1] magnitudes (already raised to hparams.power);
+ * d_phase_io: optional float2 [B][frames][bins] unit phases (in: initial phases, out: final) - NULL draws exp(2 pi i u) from the
+ * counter hash under `seed` (the reference draws np.random.rand); iters = hparams.griffin_lim_iters re-estimation rounds (iters + 1
+ * inverse transforms); d_wav: fp32 [B][hop * (frames - 1)] (librosa.istft length, centre-trimmed). Workspace: t2_griffin_lim_bytes. */
+int t2_griffin_lim_bytes(const t2_audio_config_t* cfg, int B, int frames, long long* bytes);
+int t2_griffin_lim_f32(const t2_audio_config_t* cfg, const void* d_plan, const float* d_mag, float* d_phase_io, int B, int frames,
+                       int iters, unsigned long long seed, void* d_workspace, float* d_wav, void* stream);
 int t2_preemphasis_f32(const float* d_x, float* d_y, int B, int n_samples, float k, void* stream);
 /* mu-law (mu forced to 255 like util.py:48,67,99,127); quantise truncates toward zero */
 int t2_mulaw_quantize_f32_i32(const float* d_in, int* d_out, long long n, void* stream);

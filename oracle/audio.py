@@ -62,6 +62,32 @@ def stft(y, hparams):
     return np.fft.rfft(frames, axis=1).T.astype(np.complex64)
 
 
+def istft(D, hparams):
+    """librosa.istft(D, hop_length, win_length) as called by datasets/audio.py:184-186: per frame irfft -> synthesis window (the
+    analysis window) -> overlap-add -> division by the window sum of squares where it is not tiny -> centre trim of n_fft / 2."""
+    n_fft, hop = hparams.n_fft, get_hop_size(hparams)
+    w = hann_window_padded(hparams.win_size, n_fft)
+    n_frames = D.shape[1]
+    y = np.zeros(n_fft + hop * (n_frames - 1), dtype=np.float64)
+    wss = np.zeros_like(y)
+    for k in range(n_frames):
+        y[k * hop:k * hop + n_fft] += w * np.fft.irfft(D[:, k], n_fft)
+        wss[k * hop:k * hop + n_fft] += w * w
+    nz = wss > np.finfo(np.float32).tiny
+    y[nz] /= wss[nz]
+    return y[n_fft // 2:len(y) - n_fft // 2].astype(np.float32)
+
+
+def griffin_lim(S, hparams, angles0, iters=None):
+    """datasets/audio.py:151-161 with the initial phases given (the reference draws them with np.random.rand)"""
+    S_complex = np.abs(S).astype(np.complex128)
+    y = istft(S_complex * angles0, hparams)
+    for _ in range(hparams.griffin_lim_iters if iters is None else iters):
+        angles = np.exp(1j * np.angle(stft(y, hparams)))
+        y = istft(S_complex * angles, hparams)
+    return y
+
+
 def _hz_to_mel(f):
     f = np.asanyarray(f, dtype=np.float64)
     f_sp = 200.0 / 3

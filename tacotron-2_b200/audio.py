@@ -62,6 +62,29 @@ class MelFrontEnd(object):
         return (out, out_linear) if linear else out
 
 
+    def mel_basis(self):
+        """dense [num_mels, n_fft/2+1] float64 filterbank of the fused kernel (host copy)"""
+        import numpy as np
+        out = np.zeros((self.cfg.num_mels, self.cfg.n_fft // 2 + 1), dtype=np.float64)
+        L.check(self.lib.t2_mel_basis_f64(ctypes.byref(self.cfg), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def griffin_lim(self, mag, iters, seed=0, phase=None):
+        """mag: fp32 CUDA [B, frames, bins] magnitudes -> waveform fp32 [B, hop * (frames - 1)] after `iters` Griffin-Lim rounds
+        (datasets/audio.py:151-161). phase: optional fp32 [B, frames, bins, 2] initial unit phases (updated in place)."""
+        assert mag.is_cuda and mag.dtype == torch.float32 and mag.dim() == 3 and mag.is_contiguous() and mag.shape[2] == self.cfg.n_fft // 2 + 1
+        B, frames = int(mag.shape[0]), int(mag.shape[1])
+        nb = ctypes.c_longlong()
+        L.check(self.lib.t2_griffin_lim_bytes(ctypes.byref(self.cfg), B, frames, ctypes.byref(nb)))
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=mag.device)
+        wav = torch.empty(B, self.cfg.hop_size * (frames - 1), dtype=torch.float32, device=mag.device)
+        if phase is not None:
+            assert phase.is_cuda and phase.dtype == torch.float32 and phase.is_contiguous() and tuple(phase.shape) == (B, frames, mag.shape[2], 2)
+        L.check(self.lib.t2_griffin_lim_f32(ctypes.byref(self.cfg), L.ptr(self.plan), L.ptr(mag), L.ptr(phase), B, frames, int(iters),
+                                            ctypes.c_ulonglong(seed), L.ptr(ws), L.ptr(wav), L.stream_ptr()))
+        return wav
+
+
 def _eltwise(fn_name, x, out_dtype):
     lib = L.load()
     assert x.is_cuda and x.is_contiguous()

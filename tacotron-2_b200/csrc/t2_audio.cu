@@ -268,6 +268,44 @@ __device__ __forceinline__ void dft16(double2* v) {
     for (int j = i + 1; j < 4; ++j) { const double2 t = v[4 * i + j]; v[4 * i + j] = v[4 * j + i]; v[4 * j + i] = t; }
 }
 
+// The three Stockham passes of the 1024-point forward FFT of one frame. In: v[r] = z[j + 64 r] (thread j of the frame's 64). Out: the
+// transform in natural order in `buf` (padded index padi(k)), visible to all 64 threads of the frame.
+__device__ __forceinline__ void fft1024_passes(double2 (&v)[16], double2* buf, const double2* __restrict__ tw, int slot, int j) {
+    dft16(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[17 * j + r] = v[r];          // padi(16 j + r)
+    frame_sync(slot);
+    // pass 2 (radix 16, Ns = 16): twiddle W_256^(r k) = W_1024^(4 r k)
+    {
+      const int k = j & 15;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = buf[padi(j + 64 * r)];
+#pragma unroll
+      for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + 4 * r * k));
+      dft16(v);
+      frame_sync(slot);
+      const int base = (j - k) * 16 + k;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) buf[padi(base + 16 * r)] = v[r];
+    }
+    frame_sync(slot);
+    // pass 3 (radix 4, Ns = 256): four butterflies per thread, output in natural order
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + 64 * u;
+      v[4 * u] = buf[padi(jj)];
+#pragma unroll
+      for (int r = 1; r < 4; ++r) v[4 * u + r] = cmul(buf[padi(jj + 256 * r)], __ldg(tw + r * jj));
+      dft4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+    frame_sync(slot);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) buf[padi(j + 64 * u + 256 * r)] = v[4 * u + r];
+    frame_sync(slot);
+}
+
 __global__ void __launch_bounds__(kFramesPerCta * kFrameThreads, 2) stft_mel_kernel_v2(StftArgs a) {
   extern __shared__ __align__(16) uint8_t smem_v2[];
   const int slot = threadIdx.x / kFrameThreads;
@@ -301,39 +339,7 @@ __global__ void __launch_bounds__(kFramesPerCta * kFrameThreads, 2) stft_mel_ker
       }
       v[r] = make_double2(c[0], c[1]);
     }
-    dft16(v);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) buf[17 * j + r] = v[r];          // padi(16 j + r)
-    frame_sync(slot);
-    // pass 2 (radix 16, Ns = 16): twiddle W_256^(r k) = W_1024^(4 r k)
-    {
-      const int k = j & 15;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = buf[padi(j + 64 * r)];
-#pragma unroll
-      for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(a.tw + 4 * r * k));
-      dft16(v);
-      frame_sync(slot);
-      const int base = (j - k) * 16 + k;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) buf[padi(base + 16 * r)] = v[r];
-    }
-    frame_sync(slot);
-    // pass 3 (radix 4, Ns = 256): four butterflies per thread, output in natural order
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int jj = j + 64 * u;
-      v[4 * u] = buf[padi(jj)];
-#pragma unroll
-      for (int r = 1; r < 4; ++r) v[4 * u + r] = cmul(buf[padi(jj + 256 * r)], __ldg(a.tw + r * jj));
-      dft4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-    }
-    frame_sync(slot);
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) buf[padi(j + 64 * u + 256 * r)] = v[4 * u + r];
-    frame_sync(slot);
+    fft1024_passes(v, buf, a.tw, slot, j);
     // untangle to the real-FFT bins and take |X|^p (v1 arithmetic)
     for (int k = j; k <= kN; k += kFrameThreads) {
       const double2 zk = buf[padi(k & (kN - 1))];
@@ -381,6 +387,130 @@ __global__ void __launch_bounds__(kFramesPerCta * kFrameThreads, 2) stft_mel_ker
     }
     frame_sync(slot);
   }
+}
+
+// ---- Griffin-Lim (datasets/audio.py:151-161 _griffin_lim, :184-186 _istft = librosa.istft, :178-182 _stft) ------------------------
+// One iteration = three kernels over [B][frames]:
+//   gl_istft_kernel   per frame: X = S * phase -> inverse real FFT (the forward machinery on conj(Z), Z the packed half-length
+//                     spectrum) -> multiply by the synthesis window -> the win_size non-zero samples of the frame
+//   gl_ola_kernel     overlap-add of the <= ceil(win / hop) frames covering a sample, divided by the window sum of squares
+//                     (librosa.istft), centre trim of n_fft / 2
+//   gl_stft_kernel    STFT of the new signal -> unit phases exp(i angle(X)) for the next iteration
+struct GlArgs {
+  const float* mag;       // [B][frames][bins] magnitudes S
+  float2* phase;          // [B][frames][bins] unit phases
+  float* fr;              // [B][frames][win] windowed time-domain frames
+  float* y;               // [B][n_out]
+  const double2* tw; const double2* tw2; const double* win;
+  int B, frames, hop, win_size, n_out;
+};
+__global__ void __launch_bounds__(kFramesPerCta * kFrameThreads, 2) gl_istft_kernel(GlArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_v2[];
+  const int slot = threadIdx.x / kFrameThreads, j = threadIdx.x % kFrameThreads;
+  double2* buf = reinterpret_cast<double2*>(smem_v2) + slot * kPadN;
+  const long long total = (long long)a.B * a.frames;
+  const int lpad = (kNfft - a.win_size) / 2;
+  for (long long fr = (long long)blockIdx.x * kFramesPerCta + slot; fr < total; fr += (long long)gridDim.x * kFramesPerCta) {
+    const float* S = a.mag + fr * kBins;
+    const float2* ph = a.phase + fr * kBins;
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int k = j + 64 * r;                     // Z[k] = E[k] + i O[k], E / O from X[k] and conj(X[N/2 - k])
+      const float sk = S[k], sn = S[kN - k];
+      const float2 pk = ph[k], pn = ph[kN - k];
+      double2 xk = make_double2(double(sk) * pk.x, double(sk) * pk.y);
+      double2 xn = make_double2(double(sn) * pn.x, -double(sn) * pn.y);           // conj(X[N/2 - k])
+      if (k == 0) { xk.y = 0.0; xn.y = 0.0; }       // a real inverse transform ignores the imaginary parts of the DC / Nyquist bins (np.fft.irfft)
+      const double2 e = make_double2(0.5 * (xk.x + xn.x), 0.5 * (xk.y + xn.y));
+      const double2 d = make_double2(0.5 * (xk.x - xn.x), 0.5 * (xk.y - xn.y));
+      const int kk = k <= kN / 2 ? k : kN - k;
+      double2 w = __ldg(a.tw2 + kk);                // W_2048^kk = exp(-2 pi i kk / 2048); needed: exp(+2 pi i k / 2048)
+      w = k <= kN / 2 ? make_double2(w.x, -w.y) : make_double2(-w.x, -w.y);       // k > N/4: exp(+i pi (N/2 - kk) / (N/2)) = -conj(exp(+..kk))
+      const double2 o = cmul(d, w);
+      const double2 z = make_double2(e.x - o.y, e.y + o.x);                       // E + i O
+      v[r] = make_double2(z.x, -z.y);               // conj: the inverse transform is conj(FFT(conj(Z))) / (N/2)
+    }
+    fft1024_passes(v, buf, a.tw, slot, j);
+    float* out = a.fr + fr * a.win_size;
+    for (int wi = j; wi < a.win_size; wi += kFrameThreads) {
+      const int q = wi + lpad;                      // sample q of the n_fft frame = (q even ? Re : Im) z[q / 2], z = conj(W) / (N/2)
+      const double2 wv = buf[padi(q >> 1)];
+      const double x = ((q & 1) ? -wv.y : wv.x) * (1.0 / kN);
+      out[wi] = float(x * __ldg(a.win + wi));
+    }
+    frame_sync(slot);
+  }
+}
+__global__ void gl_ola_kernel(GlArgs a) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)a.B * a.n_out) return;
+  const int b = int(e / a.n_out), n = int(e % a.n_out);
+  const int lpad = (kNfft - a.win_size) / 2;
+  const int p = n + kNfft / 2 - lpad;               // position relative to the window support of frame 0
+  int k1 = p / a.hop;
+  if (k1 > a.frames - 1) k1 = a.frames - 1;
+  float acc = 0.f, wss = 0.f;
+  for (int k = k1; k >= 0; --k) {
+    const int wi = p - k * a.hop;
+    if (wi >= a.win_size) break;
+    const float w = float(__ldg(a.win + wi));
+    acc += a.fr[((long long)b * a.frames + k) * a.win_size + wi];
+    wss += w * w;
+  }
+  a.y[e] = wss > 1.17549435e-38f ? acc / wss : acc;
+}
+__global__ void __launch_bounds__(kFramesPerCta * kFrameThreads, 2) gl_stft_kernel(GlArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_v2[];
+  const int slot = threadIdx.x / kFrameThreads, j = threadIdx.x % kFrameThreads;
+  double2* buf = reinterpret_cast<double2*>(smem_v2) + slot * kPadN;
+  const long long total = (long long)a.B * a.frames;
+  const int lpad = (kNfft - a.win_size) / 2;
+  for (long long fr = (long long)blockIdx.x * kFramesPerCta + slot; fr < total; fr += (long long)gridDim.x * kFramesPerCta) {
+    const int b = int(fr / a.frames), f = int(fr % a.frames);
+    const float* w = a.y + (long long)b * a.n_out;
+    double2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int q0 = 2 * (j + 64 * r);
+      double c[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int q = q0 + hh, wi = q - lpad;
+        double sv = 0.0;
+        if (wi >= 0 && wi < a.win_size) {
+          const long long si = (long long)f * a.hop - kNfft / 2 + q;
+          if (si >= 0 && si < a.n_out) sv = double(__ldg(w + si)) * __ldg(a.win + wi);
+        }
+        c[hh] = sv;
+      }
+      v[r] = make_double2(c[0], c[1]);
+    }
+    fft1024_passes(v, buf, a.tw, slot, j);
+    float2* ph = a.phase + fr * kBins;
+    for (int k = j; k <= kN; k += kFrameThreads) {
+      const double2 zk = buf[padi(k & (kN - 1))];
+      const double2 zn = buf[padi((kN - k) & (kN - 1))];
+      const double2 e = make_double2(0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y));
+      const double2 o = make_double2(0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x));
+      const int kk = k <= kN / 2 ? k : kN - k;
+      double2 t2w = __ldg(a.tw2 + kk);
+      if (k > kN / 2) t2w = make_double2(-t2w.x, t2w.y);
+      const double2 ow = cmul(o, t2w);
+      const float re = float(e.x + ow.x), im = float(e.y + ow.y);   // complex64 like librosa's STFT matrix
+      const float m = sqrtf(re * re + im * im);
+      ph[k] = m > 0.f ? make_float2(re / m, im / m) : make_float2(1.f, 0.f);      // np.angle(0) = 0
+    }
+    frame_sync(slot);
+  }
+}
+// initial phases exp(2 pi i u), u from the counter hash (the reference draws np.random.rand)
+__global__ void gl_init_phase_kernel(float2* __restrict__ ph, long long n, unsigned long long seed) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float sn, cs;
+  sincospif(2.f * hash_uniform(seed, (unsigned long long)e), &sn, &cs);
+  ph[e] = make_float2(cs, sn);
 }
 
 __global__ void preemphasis_kernel(const float* __restrict__ x, float* __restrict__ y, long long n_per, long long n, float k) {
@@ -524,6 +654,64 @@ extern "C" int t2_stft_mel_f32(const t2_audio_config_t* cfg, const void* d_plan,
     const long long cap = (long long)sms * 2;  // 2 resident CTAs per SM (102 KB smem, 256 threads, <= 128 registers each)
     const unsigned grid = (unsigned)(groups < cap ? groups : cap);
     stft_mel_kernel_v2<<<grid, kFramesPerCta * kFrameThreads, kV2SmemBytes, static_cast<cudaStream_t>(stream)>>>(a); t2_count_launch();
+  }
+  T2_CHECK_CUDA(cudaGetLastError());
+  return T2_OK;
+}
+
+extern "C" int t2_mel_basis_f64(const t2_audio_config_t* cfg, double* h_basis) {
+  Plan p;
+  std::vector<double> W;
+  int rc = make_plan(cfg, p, &W);
+  if (rc) return rc;
+  T2_REQUIRE(h_basis != nullptr, T2_ERR_INVALID_ARG, "mel_basis: null output");
+  memcpy(h_basis, W.data(), W.size() * sizeof(double));
+  return T2_OK;
+}
+
+extern "C" int t2_griffin_lim_bytes(const t2_audio_config_t* cfg, int B, int frames, long long* bytes) {
+  T2_REQUIRE(cfg && bytes && B >= 1 && frames >= 2, T2_ERR_INVALID_ARG, "griffin_lim_bytes: bad arguments");
+  *bytes = al((long long)B * frames * kBins * 8) + al((long long)B * frames * cfg->win_size * 4);
+  return T2_OK;
+}
+
+extern "C" int t2_griffin_lim_f32(const t2_audio_config_t* cfg, const void* d_plan, const float* d_mag, float* d_phase_io, int B, int frames,
+                                  int iters, unsigned long long seed, void* d_workspace, float* d_wav, void* stream) {
+  Plan p;
+  int rc = make_plan(cfg, p, nullptr);
+  if (rc) return rc;
+  T2_REQUIRE(d_plan && d_mag && d_workspace && d_wav && B >= 1 && frames >= 2 && iters >= 0, T2_ERR_INVALID_ARG, "griffin_lim: bad arguments");
+  const uint8_t* pl = static_cast<const uint8_t*>(d_plan);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GlArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mag = d_mag;
+  a.phase = d_phase_io ? reinterpret_cast<float2*>(d_phase_io) : reinterpret_cast<float2*>(ws);
+  a.fr = reinterpret_cast<float*>(ws + al((long long)B * frames * kBins * 8));
+  a.y = d_wav;
+  a.tw = reinterpret_cast<const double2*>(pl + p.o_tw);
+  a.tw2 = reinterpret_cast<const double2*>(pl + p.o_tw2);
+  a.win = reinterpret_cast<const double*>(pl + p.o_win);
+  a.B = B; a.frames = frames; a.hop = cfg->hop_size; a.win_size = cfg->win_size; a.n_out = cfg->hop_size * (frames - 1);
+  static bool configured = false;
+  if (!configured) {
+    T2_CHECK_CUDA(cudaFuncSetAttribute(gl_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes));
+    T2_CHECK_CUDA(cudaFuncSetAttribute(gl_stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes));
+    configured = true;
+  }
+  const long long total = (long long)B * frames;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long groups = (total + kFramesPerCta - 1) / kFramesPerCta, cap = (long long)sms * 2;
+  const unsigned grid = (unsigned)(groups < cap ? groups : cap);
+  const long long ny = (long long)B * a.n_out;
+  if (!d_phase_io) { gl_init_phase_kernel<<<nblk(total * kBins), 256, 0, st>>>(a.phase, total * kBins, seed); t2_count_launch(); }
+  for (int it = 0; it <= iters; ++it) {
+    gl_istft_kernel<<<grid, kFramesPerCta * kFrameThreads, kV2SmemBytes, st>>>(a); t2_count_launch();
+    gl_ola_kernel<<<nblk(ny), 256, 0, st>>>(a); t2_count_launch();
+    if (it < iters) { gl_stft_kernel<<<grid, kFramesPerCta * kFrameThreads, kV2SmemBytes, st>>>(a); t2_count_launch(); }
   }
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;

@@ -92,7 +92,7 @@ int build(const t2_cbhg_config_t* cfg, CL& lo, std::vector<PJ>* jobs_out) {
   lo.NFP = (lo.NF + 7) / 8 * 8;                 // row pitch of the bf16 gradient of the linear outputs
   lo.NFR = (lo.NF + 127) / 128 * 128;           // rows of the packed projection (whole 128-column output tiles)
   lo.N = (long long)lo.B * lo.T;
-  T2_REQUIRE(lo.B >= 1 && lo.T >= 2 && lo.B % kGruItems == 0, T2_ERR_UNSUPPORTED_SHAPE, "CBHG: B must be a multiple of %d, T >= 2", kGruItems);
+  T2_REQUIRE(lo.B >= 1 && lo.T >= 2, T2_ERR_UNSUPPORTED_SHAPE, "CBHG: B >= 1, T >= 2");
   T2_REQUIRE(lo.M % 8 == 0 && lo.M <= 128, T2_ERR_UNSUPPORTED_SHAPE, "CBHG: num_mels must be a multiple of 8, <= 128");
   T2_REQUIRE(lo.K >= 1 && lo.K <= 8 && lo.CC == 128, T2_ERR_UNSUPPORTED_SHAPE, "CBHG: 1..8 bank kernels of 128 channels");
   T2_REQUIRE(cfg->pool_size == 2, T2_ERR_UNSUPPORTED_SHAPE, "CBHG: pool_size must be 2");
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(GruArgs a) {
     // phase 1: gate column `tid` (r: 0..127, u: 128..255) of all items
     float acc[kGruItems];
 #pragma unroll
-    for (int i = 0; i < kGruItems; ++i) acc[i] = a.XP[((long long)(b0 + i) * a.T + t) * XPW + d * 3 * kRU + tid] + bg;
+    for (int i = 0; i < kGruItems; ++i) acc[i] = b0 + i < a.B ? a.XP[((long long)(b0 + i) * a.T + t) * XPW + d * 3 * kRU + tid] + bg : 0.f;
 #pragma unroll 4
     for (int kp = 0; kp < 64; ++kp) {
       const uint32_t w = Wg[kp * 256 + tid];
@@ -510,20 +510,21 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(GruArgs a) {
       if (tid < kRU) {
         const float rhv = g * h[i * kRU + tid];
         rhs[i * kRU + tid] = rhv;
-        if (a.r[d]) {
+        if (a.r[d] && b0 + i < a.B) {
           const long long o = ((long long)(b0 + i) * a.T + t) * kRU + tid;
           a.r[d][o] = __float2bfloat16(g); a.rh[d][o] = __float2bfloat16(rhv);
         }
       } else {
         us[i * kRU + tid - kRU] = g;
-        if (a.u[d]) a.u[d][((long long)(b0 + i) * a.T + t) * kRU + tid - kRU] = __float2bfloat16(g);
+        if (a.u[d] && b0 + i < a.B) a.u[d][((long long)(b0 + i) * a.T + t) * kRU + tid - kRU] = __float2bfloat16(g);
       }
     }
     __syncthreads();
     // phase 2: candidate column j2 for two items, then the state update
     float cc[2];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) cc[q] = a.XP[((long long)(b0 + 2 * half + q) * a.T + t) * XPW + d * 3 * kRU + 2 * kRU + j2] + bc;
+    for (int q = 0; q < 2; ++q)
+      cc[q] = b0 + 2 * half + q < a.B ? a.XP[((long long)(b0 + 2 * half + q) * a.T + t) * XPW + d * 3 * kRU + 2 * kRU + j2] + bc : 0.f;
 #pragma unroll 4
     for (int kp = 0; kp < 64; ++kp) {
       const uint32_t w = Wc[kp * 128 + j2];
@@ -542,8 +543,10 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_fwd_kernel(GruArgs a) {
       const float uv = us[i * kRU + j2];
       hn[q] = uv * h[i * kRU + j2] + (1.f - uv) * cv;
       const long long row = (long long)(b0 + i) * a.T + t;
-      a.out[row * 2 * kRU + d * kRU + j2] = __float2bfloat16(hn[q]);
-      if (a.c[d]) a.c[d][row * kRU + j2] = __float2bfloat16(cv);
+      if (b0 + i < a.B) {
+        a.out[row * 2 * kRU + d * kRU + j2] = __float2bfloat16(hn[q]);
+        if (a.c[d]) a.c[d][row * kRU + j2] = __float2bfloat16(cv);
+      }
     }
     __syncthreads();          // every thread has read h / us / rhs of this step
 #pragma unroll
@@ -591,17 +594,18 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(GruBwdArgs a) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int i = 2 * half + q;
-      const long long row = (long long)(b0 + i) * a.T + t;
-      g[q] = dh[i * kRU + k2] + a.dout[row * 2 * kRU + d * kRU + k2];
-      hp[q] = s > 0 ? __bfloat162float(a.out[((long long)(b0 + i) * a.T + tp) * 2 * kRU + d * kRU + k2]) : 0.f;
-      uv[q] = __bfloat162float(a.u[d][row * kRU + k2]);
-      rv[q] = __bfloat162float(a.r[d][row * kRU + k2]);
-      const float cv = __bfloat162float(a.c[d][row * kRU + k2]);
+      const bool live = b0 + i < a.B;               // a batch that is not a multiple of the CTA's item count: idle lanes carry zeros
+      const long long row = live ? (long long)(b0 + i) * a.T + t : 0;
+      g[q] = live ? dh[i * kRU + k2] + a.dout[row * 2 * kRU + d * kRU + k2] : 0.f;
+      hp[q] = (live && s > 0) ? __bfloat162float(a.out[((long long)(b0 + i) * a.T + tp) * 2 * kRU + d * kRU + k2]) : 0.f;
+      uv[q] = live ? __bfloat162float(a.u[d][row * kRU + k2]) : 0.f;
+      rv[q] = live ? __bfloat162float(a.r[d][row * kRU + k2]) : 0.f;
+      const float cv = live ? __bfloat162float(a.c[d][row * kRU + k2]) : 0.f;
       du[q] = g[q] * (hp[q] - cv);
       const float dc = g[q] * (1.f - uv[q]);
       const float dcpv = dc * (1.f - cv * cv);
       dcp[i * kRU + k2] = dcpv;
-      a.dXP[row * XPW + d * 3 * kRU + 2 * kRU + k2] = __float2bfloat16(dcpv);
+      if (live) a.dXP[row * XPW + d * 3 * kRU + 2 * kRU + k2] = __float2bfloat16(dcpv);
       part[q] = g[q] * uv[q];
     }
     __syncthreads();
@@ -624,8 +628,10 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_bwd_kernel(GruBwdArgs a) {
       const float drp = drh[q] * hp[q] * rv[q] * (1.f - rv[q]);
       const float dup = du[q] * uv[q] * (1.f - uv[q]);
       dgp[i * 2 * kRU + k2] = drp; dgp[i * 2 * kRU + kRU + k2] = dup;
-      a.dXP[row * XPW + d * 3 * kRU + k2] = __float2bfloat16(drp);
-      a.dXP[row * XPW + d * 3 * kRU + kRU + k2] = __float2bfloat16(dup);
+      if (b0 + i < a.B) {
+        a.dXP[row * XPW + d * 3 * kRU + k2] = __float2bfloat16(drp);
+        a.dXP[row * XPW + d * 3 * kRU + kRU + k2] = __float2bfloat16(dup);
+      }
       part[q] += drh[q] * rv[q];
     }
     __syncthreads();
@@ -887,7 +893,7 @@ extern "C" int t2_cbhg_forward(const t2_cbhg_config_t* cfg, float* d_params, con
       if (training) { a.r[d] = W<bf16>(s, lo.w_gr[d]); a.u[d] = W<bf16>(s, lo.w_gu[d]); a.c[d] = W<bf16>(s, lo.w_gc[d]); a.rh[d] = W<bf16>(s, lo.w_grh[d]); }
     }
     a.XP = XP; a.out = W<bf16>(s, lo.w_out); a.B = B; a.T = T; a.HU = HU; a.RU = RU;
-    gru_fwd_kernel<<<dim3(B / kGruItems, 2), kGruThreads, gru_fwd_smem(), st>>>(a); t2_count_launch();
+    gru_fwd_kernel<<<dim3((B + kGruItems - 1) / kGruItems, 2), kGruThreads, gru_fwd_smem(), st>>>(a); t2_count_launch();
     T2_CHECK_CUDA(cudaGetLastError());
   }
   // ---- linear projection, clip, loss ----
@@ -949,7 +955,7 @@ extern "C" int t2_cbhg_backward(const t2_cbhg_config_t* cfg, const float* d_para
       a.r[d] = W<bf16>(s, lo.w_gr[d]); a.u[d] = W<bf16>(s, lo.w_gu[d]); a.c[d] = W<bf16>(s, lo.w_gc[d]);
     }
     a.dout = dout; a.out = out; a.dXP = dXP; a.B = B; a.T = T; a.HU = HU; a.RU = RU;
-    gru_bwd_kernel<<<dim3(B / kGruItems, 2), kGruThreads, gru_bwd_smem(), st>>>(a); t2_count_launch();
+    gru_bwd_kernel<<<dim3((B + kGruItems - 1) / kGruItems, 2), kGruThreads, gru_bwd_smem(), st>>>(a); t2_count_launch();
     T2_CHECK_CUDA(cudaGetLastError());
   }
   {

@@ -18,7 +18,9 @@ def _checkpoint(checkpoint):
 
 def run_eval(args, checkpoint_path, output_dir, hparams, sentences):
     eval_dir = os.path.join(output_dir, "eval")
+    log_dir = os.path.join(output_dir, "logs-eval")          # tacotron/synthesize.py:38-45: Griffin-Lim previews go to logs-eval/wavs
     os.makedirs(eval_dir, exist_ok=True)
+    os.makedirs(os.path.join(log_dir, "wavs"), exist_ok=True)
     synth = Synthesizer()
     synth.load(checkpoint_path, hparams)
     n = hparams.tacotron_synthesis_batch_size
@@ -27,7 +29,7 @@ def run_eval(args, checkpoint_path, output_dir, hparams, sentences):
     with open(os.path.join(eval_dir, "map.txt"), "w", encoding="utf-8") as f:
         for i, texts in enumerate(batches):
             basenames = ["batch_%d_sentence_%d" % (i, j) for j in range(len(texts))]
-            mel_filenames, speaker_ids = synth.synthesize(texts, basenames, eval_dir, None, None)
+            mel_filenames, speaker_ids = synth.synthesize(texts, basenames, eval_dir, log_dir, None)
             for elems in zip(texts, mel_filenames, speaker_ids):
                 f.write("|".join(str(x) for x in elems) + "\n")
     log("synthesized mel spectrograms at %s" % eval_dir)

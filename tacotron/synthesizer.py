@@ -1,13 +1,15 @@
 """Tacotron Synthesizer (reference tacotron/synthesizer.py): load a checkpoint, then `synthesize(texts, basenames, out_dir, log_dir,
 mel_filenames)` writes `mel-<basename>.npy` ([frames, num_mels] float32). GTA mode teacher-forces on the ground-truth mels
-(mel_filenames given); natural mode runs the free-running decoder until every row's stop token fires. Griffin-Lim previews and
-plots of the reference's eval mode are not produced (Griffin-Lim is outside the hot path)."""
+(mel_filenames given); natural mode runs the free-running decoder until every row's stop token fires. With a log_dir (eval mode) the
+Griffin-Lim previews of the reference are written too (`wavs/wav-<b>-mel.wav`, and `wav-<b>-linear.wav` + `linear-<b>.npy` when the
+post-processing net is on; GPU Griffin-Lim of datasets/audio.py); plots are not produced."""
 import os
 
 import numpy as np
 import torch
 
 import t2_checkpoint
+from datasets import audio
 from tacotron.feeder import pad_input, pad_target
 from tacotron.models import create_model
 from tacotron.utils.text import text_to_sequence
@@ -44,10 +46,23 @@ class Synthesizer(object):
             # cut each row at its own first <stop> (synthesizer.py:170-176 _get_output_lengths)
             cut = [int(np.argmax(np.round(s) > 0)) + 1 if (np.round(s) > 0).any() else len(s) for s in stop]
             mels = [m[:n] for m, n in zip(mels, cut)]
+            if hp.predict_linear:       # post-processing net (tacotron.py:203-219): linear spectrograms of the same frames
+                linears = [l[:n] for l, n in zip(self.model.tower_linear_outputs[0].cpu().numpy(), cut)]
         mels = [np.clip(m, -hp.max_abs_value - hp.lower_bound_decay if hp.symmetric_mels else 0.0, hp.max_abs_value) for m in mels]
         names = []
         for m, b in zip(mels, basenames):
             path = os.path.join(out_dir, "mel-%s.npy" % b)
             np.save(path, m.astype(np.float32), allow_pickle=False)
             names.append(path)
+        if log_dir is not None and not self.gta:
+            # evaluation artefacts of the reference (synthesizer.py:199-224): Griffin-Lim inversions of the mel and, with the
+            # post-processing net, of the linear spectrogram (GPU Griffin-Lim, datasets/audio.py)
+            os.makedirs(os.path.join(log_dir, "wavs"), exist_ok=True)
+            for i, (m, b) in enumerate(zip(mels, basenames)):
+                if len(m) < 2:
+                    continue
+                audio.save_wav(audio.inv_mel_spectrogram(m.T, hp), os.path.join(log_dir, "wavs", "wav-%s-mel.wav" % b), hp.sample_rate)
+                if hp.predict_linear:
+                    np.save(os.path.join(out_dir, "linear-%s.npy" % b), linears[i].astype(np.float32), allow_pickle=False)
+                    audio.save_wav(audio.inv_linear_spectrogram(linears[i].T, hp), os.path.join(log_dir, "wavs", "wav-%s-linear.wav" % b), hp.sample_rate)
         return names, ["<no_g>"] * len(names)

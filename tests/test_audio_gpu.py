@@ -88,3 +88,46 @@ def test_dropin_module_surface():
     assert np.abs(audio.melspectrogram(w, hparams) - oa.melspectrogram(w, hparams)).max() < 1e-3
     assert audio.mulaw_quantize(np.float32(0.0)) == 127
     assert audio.librosa_pad_lr(np.zeros(22050), 2048, 275) == oa.librosa_pad_lr(np.zeros(22050), 2048, 275)
+
+
+def test_griffin_lim_matches_oracle_with_injected_phases():
+    """GPU Griffin-Lim (t2_griffin_lim_f32) vs the librosa-semantics oracle from the SAME initial phases: waveform after 0 and 3 rounds;
+    reference datasets/audio.py:151-161,184-186. Tolerance: the oracle's STFT matrix is complex64 (librosa), phases of near-silent bins are
+    ill-conditioned, so the comparison is relative to the signal level."""
+    import numpy as np
+    import torch
+    from hparams import hparams
+    from oracle import audio as oa
+    from t2_import import t2
+    rng = np.random.default_rng(4)
+    hop = oa.get_hop_size(hparams)
+    frames = 24
+    y0 = (0.4 * np.sin(np.arange(hop * (frames - 1)) * 0.05) + 0.05 * rng.standard_normal(hop * (frames - 1))).astype(np.float32)
+    S = np.abs(oa.stft(y0, hparams)).astype(np.float64)              # [bins, frames]
+    u = rng.random(S.shape)
+    ang = np.exp(2j * np.pi * u)
+    fe = t2.audio.MelFrontEnd(hparams)
+    mag = torch.from_numpy(np.ascontiguousarray(S.T, dtype=np.float32))[None].cuda()
+    for iters, tol in ((0, 2e-4), (3, 5e-3)):
+        ref = oa.griffin_lim(S, hparams, ang, iters=iters)
+        ph = torch.from_numpy(np.stack([ang.real.T, ang.imag.T], axis=-1).astype(np.float32))[None].contiguous().cuda()
+        wav = fe.griffin_lim(mag, iters, phase=ph)[0].cpu().numpy()
+        assert wav.shape == ref.shape == (hop * (frames - 1),)
+        rel = np.abs(wav - ref).max() / np.abs(ref).max()
+        print("griffin-lim iters %d: max err / max |y| = %.3g" % (iters, rel))
+        assert rel < tol
+    # spectral convergence of the self-seeded path, and the drop-in inversion of a real linear spectrogram
+    e = []
+    for iters in (0, 30):
+        w = fe.griffin_lim(mag, iters, seed=7)[0].cpu().numpy()
+        e.append(np.abs(np.abs(oa.stft(w, hparams)) - S).mean())
+    assert e[1] < 0.5 * e[0]
+    from datasets import audio
+    lin = audio.linearspectrogram(y0, hparams)
+    wav = audio.inv_linear_spectrogram(lin, hparams)
+    assert wav.shape == (hop * (lin.shape[1] - 1),) and np.isfinite(wav).all()
+    # (no faithful round trip is expected: the inversion sharpens with S ** hparams.power and undoes a pre-emphasis the input never had)
+    lin2 = audio.linearspectrogram(wav.astype(np.float32), hparams)
+    assert abs(int(lin2[:, 2:-2].mean(axis=1).argmax()) - int(lin[:, 2:-2].mean(axis=1).argmax())) <= 2      # the sine's bin survives
+    mel_wav = audio.inv_mel_spectrogram(audio.melspectrogram(y0, hparams), hparams)
+    assert mel_wav.shape == wav.shape and np.isfinite(mel_wav).all()

@@ -45,7 +45,7 @@ def _is_cbhg(name):
     return name.startswith(("CBHG_postnet", "cbhg_"))
 
 
-@pytest.mark.parametrize("B,T,mask", [(4, 37, False), (8, 64, True)])
+@pytest.mark.parametrize("B,T,mask", [(5, 37, False), (8, 64, True)])
 def test_cbhg_engine_matches_oracle(B, T, mask):
     hp = _hp(mask_decoder=mask)
     params = ot.init_params(hp, seed=11, random_bias=True)
@@ -132,7 +132,9 @@ def test_tacotron_train_step_with_linear_head():
     rows, worst_rel, worst_cos = grad_report(grads, grads_ref)
     for name, rel, cos, den in rows:
         print("%-70s rel %.4f cos %.5f |g| %.3g" % (name, rel, cos, den))
-    post = [r for r in rows if r[0].startswith(("postnet", "decoder_LSTM", "linear_transform"))]
+    # tensors upstream of mel_outputs receive the head's gradient through t2_taco_backward_ex (conv biases in front of a batch norm
+    # have a true gradient of zero: excluded by their norm)
+    post = [r for r in rows if r[0].startswith(("postnet", "decoder_LSTM", "linear_transform")) and r[3] >= 1e-6]
     m = record("tacotron_linear_head_B4_Tin30_Tout28", lin_mean_err=e.mean().item(), loss_linear_err=abs(los["linear"] - parts["linear"].item()),
                loss_linear_ref=parts["linear"].item(), loss_total_err=abs(los["total"] - loss_ref.item()), loss_total_ref=loss_ref.item(),
                loss_reg_err=abs(los["reg"] - parts["reg"].item()), grad_worst_rel=worst_rel, grad_worst_cos=worst_cos,

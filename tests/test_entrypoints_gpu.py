@@ -75,3 +75,36 @@ def test_cli_workflow(tmp_path):
     assert len(wavs) == 2
     rate, data = wavfile.read(os.path.join(base, "wavenet_output", "wavs", wavs[0]))
     assert rate == 22050 and data.dtype == np.int16 and len(data) % 275 == 0 and len(data) > 0
+
+
+def test_cli_tacotron_with_the_default_linear_head(tmp_path):
+    """`predict_linear=True` is the reference's default (hparams.py:175): train.py --model Tacotron with the CBHG post-processing net and
+    linear targets from training_data/linear, then synthesize.py --mode eval writes the linear spectrogram and its Griffin-Lim inversion."""
+    from scipy.io import wavfile
+    base = str(tmp_path)
+    ds = os.path.join(base, "LJSpeech-1.1")
+    os.makedirs(os.path.join(ds, "wavs"))
+    rng = np.random.default_rng(1)
+    rows = []
+    for i in range(8):
+        n = int(rng.integers(9000, 14000))
+        t = np.arange(n) / 22050.0
+        w = 0.4 * np.sin(2 * np.pi * (220 + 30 * i) * t) + 0.02 * rng.standard_normal(n)
+        wavfile.write(os.path.join(ds, "wavs", "LJ%03d.wav" % i), 22050, (w * 32767).astype(np.int16))
+        rows.append("LJ%03d|Sentence %d.|sentence number %d of the toy corpus." % (i, i, i))
+    open(os.path.join(ds, "metadata.csv"), "w").write("\n".join(rows) + "\n")
+    hp = HP.replace("predict_linear=False,", "")          # the stock default: predict_linear=True
+    _run([os.path.join(ROOT, "preprocess.py"), "--base_dir", base, "--hparams", hp], base)
+    td = os.path.join(base, "training_data")
+    common = ["--base_dir", base, "--hparams", hp, "--name", "lin", "--input_dir", td, "--checkpoint_interval", "4", "--eval_interval", "4"]
+    out = _run([os.path.join(ROOT, "train.py"), "--model", "Tacotron", "--tacotron_train_steps", "4"] + common, base)
+    assert os.path.isfile(os.path.join(base, "logs-lin", "taco_pretrained", "tacotron_model.ckpt-4.npz"))
+    txt = os.path.join(base, "sentences.txt")
+    open(txt, "w").write("A short test.\n")
+    _run([os.path.join(ROOT, "synthesize.py"), "--model", "Tacotron", "--mode", "eval", "--name", "lin", "--hparams", hp, "--text_list", txt], base)
+    ev = os.path.join(base, "tacotron_output", "eval")
+    lin = np.load(os.path.join(ev, "linear-batch_0_sentence_0.npy"))
+    mel = np.load(os.path.join(ev, "mel-batch_0_sentence_0.npy"))
+    assert lin.shape == (mel.shape[0], 1025) and np.isfinite(lin).all() and np.abs(lin).max() <= 4.1
+    rate, data = wavfile.read(os.path.join(base, "tacotron_output", "logs-eval", "wavs", "wav-batch_0_sentence_0-linear.wav"))
+    assert rate == 22050 and len(data) == 275 * (mel.shape[0] - 1)

@@ -83,3 +83,21 @@ def test_mulaw_properties():
         assert np.abs(back - q).max() <= 1
     check()
     assert audio.mulaw_quantize(np.zeros(0, np.float32)).shape == (0,)          # empty input
+
+
+def test_istft_inverts_stft_and_griffin_lim_reduces_the_spectral_error():
+    from oracle import audio as oa
+    """librosa.istft semantics of the oracle (datasets/audio.py:184-186): exact inverse of the STFT where the window sum is non-zero,
+    output length hop * (frames - 1); Griffin-Lim (audio.py:151-161) lowers | |STFT(y)| - S | from its random-phase start."""
+    from hparams import hparams
+    rng = np.random.default_rng(3)
+    hop = oa.get_hop_size(hparams)
+    y = (0.4 * np.sin(np.arange(hop * 30) * 0.07) + 0.05 * rng.standard_normal(hop * 30)).astype(np.float32)
+    D = oa.stft(y, hparams)
+    back = oa.istft(D, hparams)
+    assert back.shape == (hop * (D.shape[1] - 1),) == y.shape
+    assert np.abs(back - y).max() < 1e-5
+    S = np.abs(D).astype(np.float64)
+    ang = np.exp(2j * np.pi * rng.random(S.shape))
+    err = [np.abs(np.abs(oa.stft(oa.griffin_lim(S, hparams, ang, iters=n), hparams)) - S).mean() for n in (0, 8)]
+    assert err[1] < 0.6 * err[0]

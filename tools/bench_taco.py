@@ -29,23 +29,28 @@ def batch(hp, B, T_in, T_out, seed=3):
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 5
     hp = hparams.copy()
-    hp.parse("predict_linear=False")
+    linear = "--linear" in sys.argv               # with the CBHG post-processing net + linear head (the reference's default)
+    hp.parse("predict_linear=%s" % linear)
     B, T_in, T_out = 32, 160, 800
     inputs, lens, mel, stop = batch(hp, B, T_in, T_out)
     model = t2.tacotron.Tacotron(hp, B, T_in, T_out)
     model.init_variables(seed=5339)
     args = (inputs.int().cuda(), lens.int().cuda(), mel.cuda(), stop.cuda())
+    kw = {}
+    if linear:
+        g = torch.Generator().manual_seed(9)
+        kw["linear_targets"] = (torch.randn(B, T_out, hp.num_freq, generator=g) * 1.5 - 1).clamp(-4, 4).cuda()
     lib = t2.lib.load()
 
     use_graph = "--graph" in sys.argv
     if use_graph:
-        model.capture(*args)
+        model.capture(*args, **kw)
 
     def step():
         if use_graph:
             model.train_step()
         else:
-            model.train_step(*args)
+            model.train_step(*args, **kw)
 
     for _ in range(2):
         step()
