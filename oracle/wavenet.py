@@ -71,7 +71,7 @@ def param_shapes(hp):
     sh["final_convolution_1/bias"] = (S,)
     sh["final_convolution_2/kernel"] = (1, S, hp.out_channels)
     sh["final_convolution_2/bias"] = (hp.out_channels,)
-    if C > 0:
+    if C > 0 and hp.upsample_type != "NearestNeighbor":      # NearestNeighborUpsample has no variables (modules.py:524-536)
         for i, s in enumerate(hp.upsample_scales):
             p = "local_conditioning_upsampling_%d/" % (i + 1)
             if hp.upsample_type == "SubPixel":
@@ -152,7 +152,10 @@ def causal_conv(x, kernel, bias, dilation):
 
 
 def upsample(c, params, hp):
-    """c [B, cin, Tc] -> [B, cin, T] through the learnable upsampling net + ReLU (wavenet.py:680-702)."""
+    """c [B, cin, Tc] -> [B, cin, T] through the learnable upsampling net + ReLU (wavenet.py:680-702), or the non-learnable
+    nearest-neighbour resize by the hop size (wavenet.py:165-167, modules.py:524-536: no activation follows it)."""
+    if hp.upsample_type == "NearestNeighbor":
+        return c.repeat_interleave(hp.hop_size, dim=-1)
     for i, s in enumerate(hp.upsample_scales):
         k = params["local_conditioning_upsampling_%d/kernel" % (i + 1)]
         b = params["local_conditioning_upsampling_%d/bias" % (i + 1)]

@@ -62,7 +62,6 @@ def unsupported_hparams(hp):
     need("mask_encoder", lambda v: bool(v), "un-masked encoder memory")
     need("tacotron_teacher_forcing_mode", lambda v: v == "constant", "scheduled teacher forcing: helpers.py:135-169")
     need("tacotron_teacher_forcing_ratio", lambda v: float(v) == 1.0, "per-step teacher-forcing draw: helpers.py:121-124")
-    need("tacotron_fine_tuning", lambda v: not v, "frozen embedding / encoder variables: tacotron.py:401")
     if not getattr(hp, "mask_decoder", False):
         need("cross_entropy_pos_weight", lambda v: float(v) == 1.0, "the weighted stop-token loss only exists in the masked loss path")
     return bad
@@ -352,6 +351,12 @@ class Tacotron(object):
             self.m = torch.zeros_like(self.params)
             self.v = torch.zeros_like(self.params)
         lr = self.learning_rate()
+        if getattr(hp, "tacotron_fine_tuning", False):
+            # tacotron.py:401: gradients are only computed for variables without 'inputs_embedding' / 'encoder_' in their names; the
+            # frozen tensors lead the flat buffer, so zero their gradient (they drop out of the global norm) and first moment (no update)
+            end = next(t[1] for t in self.tensors if not (t[0].startswith("inputs_embedding") or t[0].startswith("encoder_")))
+            self.grads[:end].zero_()
+            self.m[:end].zero_()
         L.check(self.lib.t2_adam_step(
             L.ptr(self.params), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v), L.ptr(None), L.ptr(self.offsets),
             len(self.tensors), ctypes.c_longlong(self.n_params), ctypes.c_float(lr), ctypes.c_float(hp.tacotron_adam_beta1),

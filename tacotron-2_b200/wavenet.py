@@ -45,7 +45,7 @@ def unsupported_hparams(hp):
     need("use_bias", lambda v: bool(v), "bias-free convolutions")
     need("gin_channels", lambda v: v is None or v <= 0, "global (speaker) conditioning: wavenet.py:151-158,669-678")
     need("kernel_size", lambda v: v == 3, "kernel_size 3")
-    need("upsample_type", lambda v: v in _UPSAMPLE_TYPES, "Resize / 1D / NearestNeighbor upsamplers: modules.py:524-536,657-733")
+    need("upsample_type", lambda v: v in _UPSAMPLE_TYPES or v == "NearestNeighbor", "Resize / 1D upsamplers: modules.py:657-733")
     need("upsample_activation", lambda v: v in ("Relu", "relu", "RELU"), "LeakyRelu / linear upsampling activations: wavenet.py:190-201")
     need("freq_axis_kernel_size", lambda v: v == 3, "freq_axis_kernel_size 3")
     need("input_type", lambda v: v in _INPUT_TYPES, "raw | mulaw | mulaw-quantize")
@@ -65,9 +65,11 @@ def make_config(hp, B, T, c_pre_upsampled=False, dropout=None, precision="bf16")
     cfg.out_channels, cfg.quantize_channels = hp.out_channels, hp.quantize_channels
     cfg.input_type = _INPUT_TYPES[hp.input_type]
     cfg.legacy, cfg.residual_legacy = int(hp.legacy), int(hp.residual_legacy)
-    if hp.upsample_type not in _UPSAMPLE_TYPES:
+    if hp.upsample_type == "NearestNeighbor":     # non-learnable repeat (modules.py:524-536, wavenet.py:165-167): done by nn_upsample() below
+        c_pre_upsampled = True
+    elif hp.upsample_type not in _UPSAMPLE_TYPES:
         raise L.T2Error("upsample_type %r is not implemented on the B200 path" % hp.upsample_type)
-    cfg.upsample_type = _UPSAMPLE_TYPES[hp.upsample_type]
+    cfg.upsample_type = _UPSAMPLE_TYPES.get(hp.upsample_type, 0)
     scales = list(hp.upsample_scales)
     cfg.n_upsample = len(scales)
     for i, s in enumerate(scales):
@@ -92,6 +94,16 @@ def make_config(hp, B, T, c_pre_upsampled=False, dropout=None, precision="bf16")
     else:
         cfg.Tc = T
     return cfg
+
+
+def nn_upsample(hp, c, T):
+    """NearestNeighborUpsample (modules.py:524-536: tf.image.resize_images(method=NEAREST) by the hop size along time):
+    c fp32 [B, cin, Tc] -> the channels-last pre-upsampled layout [B, T, cin] the engine takes with c_pre_upsampled = 1"""
+    hop = hp.hop_size
+    up = c.transpose(1, 2).repeat_interleave(hop, dim=1)
+    if up.shape[1] < T:
+        raise L.T2Error("conditioning of %d frames x hop %d is shorter than T=%d" % (c.shape[2], hop, T))
+    return up[:, :T].contiguous()
 
 
 class WaveNet(object):
@@ -175,6 +187,8 @@ class WaveNet(object):
         """x: int32 [B,T] (mulaw-quantize) or fp32 [B,T]; c: fp32 [B,cin,Tc]; returns loss_buf (sum, normaliser)."""
         if self._packed_dirty:
             self.pack()
+        if self.hp.upsample_type == "NearestNeighbor" and c is not None and c.dim() == 3 and c.shape[1] == self.cfg.cin_channels and c.shape[2] != self.cfg.T:
+            c = nn_upsample(self.hp, c, self.cfg.T)
         self._last_x, self._last_c = x, c
         self._last_seed = self.seed if seed is None else seed
         L.check(self.lib.t2_wn_forward(ctypes.byref(self.cfg), L.ptr(self.params), L.ptr(self.packed),
@@ -401,6 +415,8 @@ class WaveNetSynthesizer(object):
     def generate(self, c, initial, test_inputs=None, u_a=None, u_b=None, seed=0, return_raw=False):
         """c: fp32 [B,cin,Tc]; initial: int32/fp32 [B]. Returns samples [B,T] (and raw outputs [B,T,out])."""
         B, T = self.cfg.B, self.cfg.T
+        if self.hp.upsample_type == "NearestNeighbor" and c is not None and c.dim() == 3 and c.shape[1] == self.cfg.cin_channels and c.shape[2] != T:
+            c = nn_upsample(self.hp, c, T)
         scalar = self.cfg.input_type != 2
         out = torch.empty(B, T, dtype=torch.float32 if scalar else torch.int32, device=self.device)
         raw = torch.empty(B, T, self.cfg.out_channels, dtype=torch.float32, device=self.device) if return_raw else None

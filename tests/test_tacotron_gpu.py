@@ -121,6 +121,29 @@ def test_adam_global_norm_clip_matches_oracle():
         assert (p_new[k] - p_ref[k]).abs().max().item() < 2e-6, k
 
 
+def test_fine_tuning_freezes_embedding_and_encoder():
+    """tacotron_fine_tuning (tacotron.py:401): only variables without 'inputs_embedding' / 'encoder_' in their names are optimised, and
+    only their gradients enter the global-norm clip"""
+    hp = _hp(tacotron_fine_tuning=True)
+    B, T_in, T_out = 2, 24, 12
+    model, params, ref, parts, _ = _run_forward(hp, B, T_in, T_out, 35)
+    model.backward()
+    grads = model.export_grads()
+    frozen = lambda k: "inputs_embedding" in k or "encoder_" in k
+    p_ref = {k: v.clone() for k, v in params.items() if ot.is_trainable(k) and not frozen(k)}
+    ot.adam_step(p_ref, {k: grads[k] for k in p_ref}, {}, hp, 0)
+    model.optimizer_step()
+    torch.cuda.synchronize()
+    p_new = model.export_params()
+    for k, v in params.items():
+        if not ot.is_trainable(k):
+            continue
+        if frozen(k):
+            assert torch.equal(p_new[k], v), k
+        else:
+            assert (p_new[k] - p_ref[k]).abs().max().item() < 2e-6, k
+
+
 def _trained_like_stats(params, seed):
     """non-trivial batch-norm moving statistics so that the inference path is really exercised"""
     g = torch.Generator().manual_seed(seed)

@@ -139,6 +139,12 @@ def test_gaussian_head_raw(cdf):
     _run(hp, B=2, T=256, seed=16, loss_tol=3e-3)
 
 
+def test_nearest_neighbor_upsampling():
+    """upsample_type='NearestNeighbor' (wavenet.py:165-167): the conditioning is repeated hop_size times, no upsampling variables"""
+    model, params = _run(_hp(input_type="mulaw-quantize", quantize_channels=256, out_channels=256, upsample_type="NearestNeighbor"), 2, 256, 9)
+    assert not any(n.startswith("local_conditioning_upsampling") for n, _, _ in model.tensors)
+
+
 def test_adam_step_matches_oracle():
     hp = _hp(input_type="mulaw-quantize", quantize_channels=256, out_channels=256)
     model, params = _run(hp, B=2, T=256, seed=14)
