@@ -197,7 +197,7 @@ class WaveNetWorkload(object):
             # data parallel: the step is cut into 3 graphs after each third of the stack's weight gradients so that the NCCL
             # all-reduce of a third overlaps the next third's GEMM (3 x 8 layers = 3 x 144 tiles = 3 full waves of 148 SMs)
             world = int(os.environ.get("WORLD_SIZE", "1"))
-            self.model.capture(*self.static, overlap_groups=3 if (world > 1 and self.hp.layers % 3 == 0 and os.environ.get("T2_AR_OVERLAP", "1") != "0") else 1)
+            self.model.capture(*self.static, overlap_groups=3 if (world >= 4 and self.hp.layers % 3 == 0 and os.environ.get("T2_AR_OVERLAP", "1") != "0") else 1)
 
     def step(self, e2e, world):
         import torch

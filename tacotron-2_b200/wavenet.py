@@ -239,9 +239,9 @@ class WaveNet(object):
             self.backward()
             if G > 1:
                 self.backward(0, G)
+                self.backward(100, G)
                 for g in range(G):
                     self.backward(1 + g, G)
-                self.backward(100, G)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = self.lib.t2_launch_count()
@@ -263,9 +263,10 @@ class WaveNet(object):
                         self.pack()
                         self.forward(x, c, targets, lengths)
                         self.backward(0, G)
-                    self.backward(1 + g, G)
-                    if g == G - 1:
+                        # every captured graph must end with all forked streams joined: the library's side stream (conditioning
+                        # tails forked in phase 0) is joined HERE, inside graph 0, not after the last group
                         self.backward(100, G)
+                    self.backward(1 + g, G)
                 pool = gr.pool()
                 self._graphs.append(gr)
             self._graph = self._graphs[0]
