@@ -542,6 +542,18 @@ def tacotron_tf_name(name):
     if head in ("postnet_projection", "cbhg_linear_specs_projection"):
         return "%s%s/projection_%s/%s" % (P, head, head, leaf)
     if head.startswith("CBHG_postnet"):
+        # modules.py:19-78 under variable_scope('CBHG_postnet'): conv1d() scopes wrap tf.layers.conv1d / batch_normalization
+        # (modules.py:379-391), highway layers are named '<scope>_highwaynet_<i>' (:33), the GRU cells '<scope>_forward_RNN' /
+        # '<scope>_backward_RNN' inside bidirectional_dynamic_rnn's fw / bw scopes (:34-35,69-75), the width adapter is tf.layers.dense
+        parts = head.split("/")
+        if parts[1] in ("conv_bank", "proj1", "proj2"):
+            sub = "conv1d" if leaf in ("kernel", "bias") else "batch_normalization"
+            return "%s%s/%s/%s" % (P, head, sub, leaf)
+        if parts[1].startswith("highwaynet_"):
+            return "%sCBHG_postnet/CBHG_postnet_%s/%s/%s" % (P, parts[1], parts[2], leaf)
+        if parts[1] in ("forward_RNN", "backward_RNN"):
+            d = "fw" if parts[1].startswith("forward") else "bw"
+            return "%sCBHG_postnet/bidirectional_rnn/%s/CBHG_postnet_%s/%s/%s" % (P, d, parts[1], parts[2], leaf)
         return P + name
     raise KeyError("no TensorFlow name known for engine tensor %r" % name)
 
@@ -590,6 +602,15 @@ def engine_name(tf_name):
     m = re.fullmatch(r"decoder/decoder_LSTM/multi_rnn_cell/cell_\d+/decoder_LSTM_(\d+)/(\w+)", tail)
     if m:
         return "decoder_LSTM/cell_%s/%s" % m.groups()
+    m = re.fullmatch(r"(CBHG_postnet/(?:conv_bank/conv1d_\d+|proj\d))/(?:conv1d|batch_normalization)/(\w+)", tail)
+    if m:
+        return "%s/%s" % m.groups()
+    m = re.fullmatch(r"CBHG_postnet/CBHG_postnet_(highwaynet_\d+)/(H|T)/(\w+)", tail)
+    if m:
+        return "CBHG_postnet/%s/%s/%s" % m.groups()
+    m = re.fullmatch(r"CBHG_postnet/bidirectional_rnn/(?:fw|bw)/CBHG_postnet_((?:forward|backward)_RNN)/(gates|candidate)/(\w+)", tail)
+    if m:
+        return "CBHG_postnet/%s/%s/%s" % m.groups()
     m = re.fullmatch(r"(?:decoder/)?(\w+)/projection_\1/(\w+)", tail)
     if m:
         return "%s/%s" % m.groups()

@@ -126,6 +126,17 @@ def test_reference_variable_names():
     assert t("decoder_LSTM/cell_2/kernel") == P + "decoder/decoder_LSTM/multi_rnn_cell/cell_1/decoder_LSTM_2/kernel"
     assert t("stop_token_projection/kernel") == P + "decoder/stop_token_projection/projection_stop_token_projection/kernel"
     assert t("postnet_projection/bias") == P + "postnet_projection/projection_postnet_projection/bias"
+    # CBHG post-processing net (predict_linear)
+    cb = {"CBHG_postnet/conv_bank/conv1d_3/kernel": "CBHG_postnet/conv_bank/conv1d_3/conv1d/kernel",
+          "CBHG_postnet/conv_bank/conv1d_3/moving_mean": "CBHG_postnet/conv_bank/conv1d_3/batch_normalization/moving_mean",
+          "CBHG_postnet/proj2/gamma": "CBHG_postnet/proj2/batch_normalization/gamma",
+          "CBHG_postnet/dense/kernel": "CBHG_postnet/dense/kernel",
+          "CBHG_postnet/highwaynet_4/T/bias": "CBHG_postnet/CBHG_postnet_highwaynet_4/T/bias",
+          "CBHG_postnet/backward_RNN/candidate/kernel": "CBHG_postnet/bidirectional_rnn/bw/CBHG_postnet_backward_RNN/candidate/kernel",
+          "CBHG_postnet/forward_RNN/gates/bias": "CBHG_postnet/bidirectional_rnn/fw/CBHG_postnet_forward_RNN/gates/bias",
+          "cbhg_linear_specs_projection/kernel": "cbhg_linear_specs_projection/projection_cbhg_linear_specs_projection/kernel"}
+    for ours, theirs in cb.items():
+        assert t(ours) == P + theirs and tb.engine_name(P + theirs) == ours, ours
     w = tb.wavenet_tf_name
     Q = "WaveNet_model/inference/"
     assert w("input_convolution/kernel") == Q + "input_convolution/kernel"
@@ -214,3 +225,17 @@ def test_t2_checkpoint_tf_format(tmp_path, monkeypatch):
     a.global_step = 40
     p2 = t2_checkpoint.save(str(tmp_path), "wavenet_model.ckpt", a)
     assert p2.endswith(".npz") and t2_checkpoint.latest(str(tmp_path)) == p2
+
+
+def test_every_model_variable_has_an_invertible_reference_name():
+    """all 162 Tacotron (with the CBHG head) and all WaveNet variables map to a reference name and back"""
+    from hparams import hparams
+    from oracle import tacotron as ot, wavenet as ow
+    names = list(ot.param_shapes(hparams))
+    assert len(names) == 162 and len({tb.tacotron_tf_name(n) for n in names}) == 162
+    for n in names:
+        assert tb.engine_name(tb.tacotron_tf_name(n)) == n, n
+    hp = hparams.copy()
+    hp.parse("out_channels=30,upsample_type=2D")
+    for n in ow.param_shapes(hp):
+        assert tb.engine_name(tb.wavenet_tf_name(n, "2D")) == n, n
