@@ -68,7 +68,7 @@ def summarize_list(workload, marker):
     rd, wr = sum(a[2] for a in agg.values()), sum(a[3] for a in agg.values())
     lines.append("%-70s %6d %10.1f %6.1f%% %12.2f %12.2f" % ("TOTAL", sum(a[0] for a in agg.values()), tot, 100.0, rd / 1e6, wr / 1e6))
     open(os.path.join(PR, "r02_launch_summary_%s.txt" % workload), "w").write("\n".join(lines) + "\n")
-    gate = [l for l in ls if "act_gemm2_kernel<(int)0" in l["name"] or "act_gemm_kernel<(int)0" in l["name"]]
+    gate = [l for l in ls if re.search(r"act_gemm2?_kernel<(\(int\))?0,", l["name"])]
     res = {workload + "_step_dram_bytes": rd + wr, workload + "_step_dram_read_bytes": rd, workload + "_step_dram_write_bytes": wr,
            workload + "_step_kernel_time_us_serialised": tot}
     if gate:
@@ -131,7 +131,13 @@ def main():
         if r:
             traffic.update(r)
     if len(traffic) > 1:
-        json.dump(traffic, open(os.path.join(PR, "r02_dram_traffic.json"), "w"), indent=1)
+        path = os.path.join(PR, "r02_dram_traffic.json")
+        try:                       # keep the figures of workloads whose launch list is not in gpurun_out/ this time
+            old = json.load(open(path))
+            traffic = dict({k: v for k, v in old.items() if k not in traffic}, **traffic)
+        except Exception:
+            pass
+        json.dump(traffic, open(path, "w"), indent=1)
     for tag in ("gate", "out", "dz", "dx", "wgrad", "lstm", "tout", "attf", "attb", "ar", "stft"):
         summarize_full(tag)
     print("\n".join(sorted(f for f in os.listdir(PR) if f.startswith("r02_"))))
