@@ -138,7 +138,7 @@ def main():
         except Exception:
             pass
         json.dump(traffic, open(path, "w"), indent=1)
-    for tag in ("gate", "out", "dz", "dx", "wgrad", "lstm", "tout", "attf", "attb", "ar", "stft"):
+    for tag in ("gate", "out", "dz", "dx", "wgrad", "lstm", "tout", "attf", "attb", "ar", "stft", "gru"):
         summarize_full(tag)
     print("\n".join(sorted(f for f in os.listdir(PR) if f.startswith("r02_"))))
 
