@@ -32,6 +32,9 @@ extern "C" {
 
 const char* t2_last_error(void);
 int t2_abi_version(void);
+/* sizeof() of a POD struct of this header by name ("t2_wn_config_t", "t2_wn_sizes_t", "t2_taco_config_t", "t2_cbhg_config_t",
+ * "t2_audio_config_t"), -1 for an unknown name: a binding asserts that its mirror of the struct matches the library it loaded */
+int t2_struct_size(const char* name);
 /* kernels launched (or captured) by this library so far in this process */
 long long t2_launch_count(void);
 

@@ -99,3 +99,14 @@ extern "C" int t2_rng_uniform_f32(unsigned long long seed, unsigned int stream_i
   T2_CHECK_CUDA(cudaGetLastError());
   return T2_OK;
 }
+
+// sizeof of the POD structs that cross the C-ABI: lets a binding (ctypes, cgo, ...) assert that its mirror matches this build
+extern "C" int t2_struct_size(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "t2_wn_config_t")) return int(sizeof(t2_wn_config_t));
+  if (!strcmp(name, "t2_wn_sizes_t")) return int(sizeof(t2_wn_sizes_t));
+  if (!strcmp(name, "t2_taco_config_t")) return int(sizeof(t2_taco_config_t));
+  if (!strcmp(name, "t2_cbhg_config_t")) return int(sizeof(t2_cbhg_config_t));
+  if (!strcmp(name, "t2_audio_config_t")) return int(sizeof(t2_audio_config_t));
+  return -1;
+}

@@ -147,3 +147,16 @@ def test_reference_python_surface_validates_like_the_reference():
         util.is_mulaw("pcm")
     mask = util.sequence_mask([3, 1], max_len=4, expand=False)
     assert mask.tolist() == [[1, 1, 1, 0], [1, 0, 0, 0]] and util.sequence_mask([2, 1]).shape == (2, 2, 1)
+
+
+def test_ctypes_struct_mirrors_match_the_library():
+    """every POD struct that crosses the C-ABI has the same size in the Python mirror (field order is checked by the GPU tests)"""
+    import ctypes
+    from t2_import import t2
+    lib = t2.lib.load()
+    lib.t2_struct_size.argtypes = [ctypes.c_char_p]
+    pairs = {"t2_wn_config_t": t2.wavenet.WnConfig, "t2_wn_sizes_t": t2.wavenet.WnSizes, "t2_taco_config_t": t2.tacotron.TacoConfig,
+             "t2_cbhg_config_t": t2.tacotron.CbhgConfig, "t2_audio_config_t": t2.audio.AudioConfig}
+    for name, mirror in pairs.items():
+        assert lib.t2_struct_size(name.encode()) == ctypes.sizeof(mirror), name
+    assert lib.t2_struct_size(b"nope") == -1
