@@ -171,6 +171,17 @@ def test_oracle_masked_tacotron_losses_match_reference_code():
     assert abs(float(got) - float(R["taco_masked_sigmoid_ce"])) <= 1e-5 * float(R["taco_masked_sigmoid_ce"])
 
 
+def test_oracle_masked_linear_loss_matches_reference_code():
+    """MaskedLinearLoss (tacotron/models/modules.py:457-485) executed from the reference's source: L1 with half of the weight on the
+    bins below 2 kHz, BOTH terms divided by sum(mask) - the loss of the CBHG linear head when mask_decoder is on"""
+    from hparams import hparams
+    from oracle import tacotron as ot
+    hp = hparams.copy()
+    hp.parse("mask_decoder=True")
+    got = ot.linear_loss(torch.from_numpy(R["taco_lin_t"]), torch.from_numpy(R["taco_lin_o"]), hp, torch.from_numpy(R["taco_lin_lengths"]).long())
+    assert abs(float(got) - float(R["taco_masked_linear"])) <= 1e-5 * float(R["taco_masked_linear"])
+
+
 def test_oracle_attention_score_matches_reference_code():
     from oracle import tacotron as ot
     wq, wf, wk = (torch.from_numpy(R[k]) for k in ("att_wq", "att_wf", "att_wk"))
