@@ -88,6 +88,29 @@ def griffin_lim(S, hparams, angles0, iters=None):
     return y
 
 
+def _db_to_amp(x):  # datasets/audio.py:252-253
+    return np.power(10.0, np.asarray(x) * 0.05)
+
+
+def _spectrogram_to_wav(S, hparams, angles0, iters):
+    """tail of inv_*_spectrogram (audio.py:126-133 without LWS): Griffin-Lim on S ** power, then the inverse pre-emphasis"""
+    return inv_preemphasis(griffin_lim(S ** hparams.power, hparams, angles0, iters), hparams.preemphasis, hparams.preemphasize)
+
+
+def inv_linear_spectrogram(linear_spectrogram, hparams, angles0, iters=None):
+    """datasets/audio.py:118-133 with the initial Griffin-Lim phases given"""
+    D = _denormalize(linear_spectrogram, hparams) if hparams.signal_normalization else linear_spectrogram
+    return _spectrogram_to_wav(_db_to_amp(D + hparams.ref_level_db) ** (1 / hparams.magnitude_power), hparams, angles0, iters)
+
+
+def inv_mel_spectrogram(mel_spectrogram, hparams, angles0, iters=None):
+    """datasets/audio.py:97-112: the mel spectrogram goes back to linear through the pseudo-inverse of the filterbank, floored at
+    1e-10 (audio.py:231-241)"""
+    D = _denormalize(mel_spectrogram, hparams) if hparams.signal_normalization else mel_spectrogram
+    S = np.maximum(1e-10, np.dot(np.linalg.pinv(build_mel_basis(hparams)), _db_to_amp(D + hparams.ref_level_db) ** (1 / hparams.magnitude_power)))
+    return _spectrogram_to_wav(S, hparams, angles0, iters)
+
+
 def _hz_to_mel(f):
     f = np.asanyarray(f, dtype=np.float64)
     f_sp = 200.0 / 3

@@ -16,7 +16,8 @@ What is executed, and how honest each fixture is:
   * datasets/audio.py melspectrogram / linearspectrogram: the reference's glue (power, mel matmul, dB, normalise, call
     signatures, hparams values) runs AS IS; the two librosa primitives it calls (librosa.stft, librosa.filters.mel) are NOT
     available and are substituted by the oracle's restatements (cross-checked against torch.stft / torchaudio in
-    tests/test_oracle_audio.py). These vectors pin the composition, not the primitives.
+    tests/test_oracle_audio.py). These vectors pin the composition, not the primitives. The same holds for the inversion path
+    (inv_linear_spectrogram / inv_mel_spectrogram / _griffin_lim with librosa.istft substituted).
 Layers built from tf.layers / tf.nn.rnn_cell / seq2seq (convolutions, LSTM cells, BahdanauAttention) are NOT executed: they
 remain restated from the TF documentation."""
 import json
@@ -237,6 +238,32 @@ def main():
     out["feeder_round_up"] = np.array([fd._round_up(n, 3) for n in range(0, 8)])
     out["feeder_round_down"] = np.array([fd._round_down(n, 3) for n in range(0, 8)])
     out["wn_ensure_divisible"] = np.array([[rwf._ensure_divisible(n, 275, True), rwf._ensure_divisible(n, 275, False)] for n in (274, 275, 276, 8000, 12000)])
+
+    # ---------------- H. spectrogram inversion (datasets/audio.py:97-133 inv_*_spectrogram, :151-161 _griffin_lim) -------------
+    # The reference's code runs AS IS (denormalise, dB -> amplitude, magnitude_power / power exponents, pseudo-inverse mel basis, the
+    # Griffin-Lim loop with its np.random.rand phases, inverse pre-emphasis); librosa.stft / librosa.istft are substituted by the
+    # oracle's restatements like above, and `np.complex` (removed from numpy 1.24) is aliased to the builtin it used to be.
+    def istft_stub(D, hop_length=None, win_length=None, **kw):
+        assert not kw, "the reference calls librosa.istft(y, hop_length, win_length)"
+        return oa.istft(D, NS(n_fft=rhp.n_fft, hop_size=hop_length, win_size=win_length))
+    librosa.istft = istft_stub
+    if not hasattr(np, "complex"):
+        np.complex = complex
+    iters_saved = rhp.griffin_lim_iters
+    rhp.griffin_lim_iters = 4
+    hop = ra.get_hop_size(rhp)
+    seg = pre[:hop * 19]
+    lin_in = ra.linearspectrogram(seg, rhp).astype(np.float32)           # [1025, 20]
+    mel_in = ra.melspectrogram(seg, rhp).astype(np.float32)              # [80, 20]
+    out["gl_iters"] = np.array(4)
+    out["gl_linear_in"], out["gl_mel_in"] = lin_in, mel_in
+    np.random.seed(4321)
+    out["gl_u"] = np.random.rand(*lin_in.shape)                          # the draws _griffin_lim makes first (audio.py:155)
+    np.random.seed(4321)
+    out["gl_wav_from_linear"] = np.asarray(ra.inv_linear_spectrogram(lin_in, rhp), dtype=np.float64)
+    np.random.seed(4321)
+    out["gl_wav_from_mel"] = np.asarray(ra.inv_mel_spectrogram(mel_in, rhp), dtype=np.float64)
+    rhp.griffin_lim_iters = iters_saved
 
     np.savez_compressed(os.path.join(HERE, "reference_exec.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote %d arrays, %d hparams" % (len(out), len(hp_json)))

@@ -161,6 +161,27 @@ def test_oracle_masked_cross_entropy_matches_reference_code():
     assert float(R["ce_add_loss"]) != float(R["ce_masked"])           # the shift by one sample matters in the vector
 
 
+def test_oracle_spectrogram_inversion_matches_reference_code():
+    """inv_linear_spectrogram / inv_mel_spectrogram / _griffin_lim of the reference (datasets/audio.py:97-161) executed from its source
+    with seeded np.random phases (librosa.stft / istft substituted by the restatements): the oracle reproduces the waveform from the same
+    initial phases; the product's pure-numpy helpers agree with the reference's too."""
+    from oracle import audio as oa
+    it = int(R["gl_iters"])
+    ang = np.exp(2j * np.pi * R["gl_u"])
+    for key, fn, src in (("gl_wav_from_linear", oa.inv_linear_spectrogram, "gl_linear_in"), ("gl_wav_from_mel", oa.inv_mel_spectrogram, "gl_mel_in")):
+        got = fn(R[src], hparams, ang, iters=it)
+        ref = R[key]
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), key          # float32 istft outputs, float64 everywhere else
+    from datasets import audio as pa
+    for sym in (0, 1):
+        for clip in (0, 1):
+            hp = hparams.copy()
+            hp.parse("symmetric_mels=%s,allow_clipping_in_normalization=%s" % (bool(sym), bool(clip)))
+            assert np.abs(pa._denormalize(R["denorm_in_sym%d_clip%d" % (sym, clip)], hp) - R["denormalize_sym%d_clip%d" % (sym, clip)]).max() < 1e-12
+    assert np.abs(pa._db_to_amp(R["amp_to_db"]) - R["db_to_amp"]).max() <= 1e-12 * np.abs(R["db_to_amp"]).max()
+
+
 # ------------------------------------------------------------------------------------------------ Tacotron pieces
 def test_oracle_masked_tacotron_losses_match_reference_code():
     from oracle import tacotron as ot
