@@ -265,6 +265,21 @@ def main():
     out["gl_wav_from_mel"] = np.asarray(ra.inv_mel_spectrogram(mel_in, rhp), dtype=np.float64)
     rhp.griffin_lim_iters = iters_saved
 
+    # ---------------- I. learning-rate schedules (tacotron.py:439-463, wavenet.py:615-633) ---------------------------------------
+    # the model classes' own methods, run on instances created without __init__ (only self._hparams is read)
+    from tacotron.models import tacotron as rtaco
+    from wavenet_vocoder.models import wavenet as rwn
+    tm, wm = object.__new__(rtaco.Tacotron), object.__new__(rwn.WaveNet)
+    tm._hparams = wm._hparams = rhp
+    tm.decay_steps, tm.decay_rate = rhp.tacotron_decay_steps, rhp.tacotron_decay_rate       # set in add_optimizer (tacotron.py:387-388)
+    steps = np.array([0, 1, 1000, 3999, 4000, 4001, 20000, 39999, 40000, 50000, 100000, 200000, 310000, 400000, 1000000], dtype=np.int64)
+    out["lr_steps"] = steps
+    out["lr_tacotron"] = np.array([float(tm._learning_rate_decay(rhp.tacotron_initial_learning_rate, torch.tensor(int(s_)))) for s_ in steps])
+    out["lr_wavenet_noam"] = np.array([float(wm._noam_learning_rate_decay(rhp.wavenet_learning_rate, torch.tensor(int(s_)), warmup_steps=rhp.wavenet_warmup))
+                                       for s_ in steps])
+    out["lr_wavenet_exponential"] = np.array([float(wm._exponential_learning_rate_decay(rhp.wavenet_learning_rate, torch.tensor(int(s_)), rhp.wavenet_decay_rate,
+                                                                                         rhp.wavenet_decay_steps)) for s_ in steps])
+
     np.savez_compressed(os.path.join(HERE, "reference_exec.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote %d arrays, %d hparams" % (len(out), len(hp_json)))
 

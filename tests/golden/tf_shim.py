@@ -177,6 +177,10 @@ def build():
             assert n.shape == self.loc.shape
             return self.loc + self.scale * n
     tf.contrib.distributions.Normal = Normal
+    # tf.train.exponential_decay (non-staircase): lr * rate ^ (step / decay_steps), float32 like the TF op
+    tf.train.exponential_decay = lambda learning_rate, global_step, decay_steps, decay_rate, staircase=False, name=None: (
+        torch.as_tensor(learning_rate, dtype=torch.float32) * torch.pow(torch.as_tensor(decay_rate, dtype=torch.float32),
+                                                                          torch.as_tensor(global_step).to(torch.float32) / float(decay_steps)))
     tf.contrib.layers.xavier_initializer = lambda *a, **k: None
     tf.zeros_initializer = lambda *a, **k: None
     return tf

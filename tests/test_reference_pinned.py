@@ -182,6 +182,29 @@ def test_oracle_spectrogram_inversion_matches_reference_code():
     assert np.abs(pa._db_to_amp(R["amp_to_db"]) - R["db_to_amp"]).max() <= 1e-12 * np.abs(R["db_to_amp"]).max()
 
 
+def test_learning_rate_schedules_match_reference_code():
+    """Tacotron._learning_rate_decay (tacotron.py:439-463) and WaveNet's noam / exponential schedules (wavenet.py:615-633) executed from
+    the reference's classes: the oracle's and the PRODUCT's host-side schedules (engine.learning_rate()) give the same values"""
+    from oracle import tacotron as ot, wavenet as ow
+    from t2_import import t2
+    steps = R["lr_steps"]
+
+    class Eng(object):                       # the engines' learning_rate() only reads self.hp and self.global_step
+        pass
+    for key, sched, oracle_fn, cls in (("lr_tacotron", None, ot.learning_rate, t2.tacotron.Tacotron),
+                                       ("lr_wavenet_noam", "noam", ow.learning_rate, t2.wavenet.WaveNet),
+                                       ("lr_wavenet_exponential", "exponential", ow.learning_rate, t2.wavenet.WaveNet)):
+        hp = hparams.copy()
+        if sched:
+            hp.parse("wavenet_lr_schedule=%s" % sched)
+        e = Eng()
+        e.hp = hp
+        for s_, ref in zip(steps, R[key]):
+            e.global_step = int(s_)
+            assert abs(oracle_fn(hp, int(s_)) - ref) <= 2e-6 * ref, (key, s_)          # float32 pow in the TF op
+            assert abs(cls.learning_rate(e) - ref) <= 2e-6 * ref, (key, s_)
+
+
 # ------------------------------------------------------------------------------------------------ Tacotron pieces
 def test_oracle_masked_tacotron_losses_match_reference_code():
     from oracle import tacotron as ot
