@@ -10,12 +10,16 @@ Restates datasets/audio.py of the reference with numpy/scipy only (librosa is no
   melspectrogram         datasets/audio.py:70-77
   linearspectrogram      datasets/audio.py:61-68
   librosa_pad_lr         datasets/audio.py:210-219
+  inv_linear_spectrogram / inv_mel_spectrogram / _griffin_lim / _istft   datasets/audio.py:97-133,151-161,184-186
 and wavenet_vocoder/util.py:30-129 (mu-law family, mu hard-wired to 255).
 
-PARITY UNPINNED by the reference: it ships no tests or golden vectors for this path and neither TensorFlow nor
-librosa can be imported in the build container. The restatement is pinned instead against (a) the invariants the
-reference implies and (b) an independent implementation, torchaudio's Slaney mel filterbank and
-torch.stft (tests/test_oracle_audio.py).
+PINNING. The reference ships no tests or golden vectors and librosa cannot be imported in the build container. Pinned by EXECUTING
+the reference's own source (tests/golden/make_reference_vectors.py -> reference_exec.npz, checked by tests/test_reference_pinned.py):
+the mu-law family (numpy and tensor code paths, every quantiser bin edge), preemphasis / inv_preemphasis, _amp_to_db / _db_to_amp,
+_normalize / _denormalize (4 flag combinations), the padding helpers, start_and_end_indices, and the COMPOSITIONS melspectrogram /
+linearspectrogram / inv_linear_spectrogram / inv_mel_spectrogram / _griffin_lim. PARITY UNPINNED for the three librosa primitives
+those compositions call (librosa.stft, librosa.istft, librosa.filters.mel): they are restatements of librosa's documented behaviour,
+cross-checked against independent implementations (torch.stft, torchaudio's Slaney filterbank: tests/test_oracle_audio.py).
 """
 import numpy as np
 from scipy import signal

@@ -1,5 +1,6 @@
 """ORACLE (test infrastructure, not product code): fp32 PyTorch-CPU restatement of the reference's Tacotron-2
-mel-spectrogram predictor (training / GTA graph, teacher forcing, outputs_per_step = 1, predict_linear = False).
+mel-spectrogram predictor (training / GTA graph, teacher forcing, outputs_per_step = 1) and of the CBHG post-processing net +
+linear head (predict_linear = True: tacotron.py:203-219, modules.py:4-78,457-485).
 
 Only tests/, __graft_entry__.smoke() and bench / tools CPU-baseline legs may import this.
 
@@ -15,10 +16,14 @@ TF-layer semantics (LSTMCell gate order i,j,f,o + forget_bias 1, BahdanauAttenti
 eps 1e-3 with biased batch variance, 'same' conv padding, tf.losses.mean_squared_error) are restated from the public
 TF 1.x definitions.
 
-PARITY UNPINNED by the reference (no tests / golden vectors; TensorFlow 1.x is not importable here). Pinned instead:
-parameter count 27.19 M, alignments are a masked probability distribution, zero-length-padding
-invariance of the encoder, zoneout / dropout off == deterministic, gradient check of the hand-derived pieces the CUDA
-path mirrors (tests/test_oracle_tacotron.py).
+PINNING. Pinned by EXECUTING the reference's own source on a TF-1 shim of elementary ops (tests/golden/make_reference_vectors.py,
+tests/test_reference_pinned.py): MaskedMSE, MaskedSigmoidCrossEntropy, MaskedLinearLoss, sequence_mask (modules.py:400-485), the
+location-sensitive score and the smoothing normalisation (attention.py:38-92), the learning-rate schedule (tacotron.py:439-463), the
+feeder padding helpers. PARITY UNPINNED for everything built from tf.layers / tf.nn.rnn_cell / tf.contrib.seq2seq (convolutions,
+batch norm, LSTM / GRU cells, zoneout wrapper, BahdanauAttention memory masking, dynamic_decode, CBHG): restated from the TF 1.x
+definitions and checked through known answers - parameter counts 27.19 M / 29.02 M with the CBHG head, alignments
+are a masked probability distribution, zero-length-padding invariance of the encoder, zoneout / dropout off == deterministic, gradient
+checks of the hand-derived pieces the CUDA path mirrors (tests/test_oracle_tacotron.py).
 """
 import math
 

@@ -11,11 +11,14 @@ Follows, function by function:
 Parameters are kept in the reference's TensorFlow variable layouts (conv kernels [kw, in, out]) under the names of
 SURVEY.md Appendix B so that a parameter dict is interchangeable with the CUDA model (tacotron-2_b200/wavenet.py).
 
-PARITY UNPINNED by the reference (no tests / golden vectors; TensorFlow 1.x is not importable here): the TF-layer
-semantics (left-padded VALID dilated cross-correlation, transposed-conv 'same' arithmetic, glorot init, Adam)
-are restated from the public TF 1.x definitions. What IS pinned: receptive_field_size
-known answers, incremental == parallel forward under teacher forcing, NN_init == nearest-neighbour repeat,
-mulaw_quantize(0) == 127 (tests/test_oracle_wavenet.py).
+PINNING. Pinned by EXECUTING the reference's own source on a TF-1 shim of elementary ops (tests/golden/make_reference_vectors.py,
+tests/test_reference_pinned.py): discretized_mix_logistic_loss / sample_from_discretized_mix_logistic (mixture.py), the Gaussian
+loss and sampler (gaussian.py), MaskedCrossEntropyLoss / DiscretizedMixtureLogisticLoss / GaussianMaximumLikelihoodEstimation with
+their masks and normalisers (modules.py:781-852, wavenet.py:476-519), the learning-rate schedules (wavenet.py:615-633), the mu-law
+tensor path. PARITY UNPINNED for the layers built from tf.layers (left-padded VALID dilated cross-correlation, Conv2D /
+Conv2DTranspose 'same' arithmetic, glorot init) and tf.train (Adam, EMA): restated from the public TF 1.x definitions (SURVEY.md
+Appendix A) and checked through known answers: receptive_field_size, incremental == parallel forward under teacher forcing, NN_init ==
+nearest-neighbour repeat, mulaw_quantize(0) == 127 (tests/test_oracle_wavenet.py).
 """
 import math
 
