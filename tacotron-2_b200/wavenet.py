@@ -96,6 +96,33 @@ def make_config(hp, B, T, c_pre_upsampled=False, dropout=None, precision="bf16")
     return cfg
 
 
+def param_table(cfg):
+    """[(name, offset, shape)] + n_params of the flat parameter buffer for a config: host-only library calls (no CUDA device needed)"""
+    lib = L.load()
+    sz = WnSizes()
+    L.check(lib.t2_wn_sizes(ctypes.byref(cfg), ctypes.byref(sz)))
+    name = ctypes.create_string_buffer(160)
+    off, nd, shp = ctypes.c_longlong(), ctypes.c_int(), (ctypes.c_int * 4)()
+    out = []
+    for i in range(sz.n_tensors):
+        L.check(lib.t2_wn_param_info(ctypes.byref(cfg), i, name, 160, ctypes.byref(off), ctypes.byref(nd), shp))
+        out.append((name.value.decode(), off.value, tuple(shp[k] for k in range(nd.value))))
+    return out, sz.n_params
+
+
+def grad_buckets(tensors, n_layers, n_params, n_groups):
+    """[(start, end)] element ranges of the flat gradient buffer for the overlapped data-parallel all-reduce: one per layer group (final
+    after that group's weight-gradient launch) followed by the ranges outside the residual stack (input conv; head + upsampling net:
+    final after the join). Together they cover [0, n_params) exactly once."""
+    off = {t[0]: t[1] for t in tensors}
+    first = lambda l: off["ResidualConv1DGLU_%d/residual_block_causal_conv/kernel" % l]
+    stack_end = off["final_convolution_1/kernel"]
+    bounds = [first(n_layers * g // n_groups) for g in range(n_groups)] + [stack_end]
+    groups = [(bounds[g], bounds[g + 1]) for g in range(n_groups)]
+    rest = [(0, first(0)), (stack_end, n_params)]
+    return groups, [r for r in rest if r[1] > r[0]]
+
+
 def nn_upsample(hp, c, T):
     """NearestNeighborUpsample (modules.py:524-536: tf.image.resize_images(method=NEAREST) by the hop size along time):
     c fp32 [B, cin, Tc] -> the channels-last pre-upsampled layout [B, T, cin] the engine takes with c_pre_upsampled = 1"""
@@ -209,16 +236,7 @@ class WaveNet(object):
         return self.grads
 
     def grad_buckets(self, n_groups):
-        """[(start, end)] element ranges of the flat gradient buffer: one per layer group (final after that group's weight-gradient
-        launch) followed by the two ranges outside the residual stack (input conv; head + upsampling net: final after the join)."""
-        off = {name: o for name, o, _ in self.tensors}
-        L_ = self.cfg.layers
-        first = lambda l: off["ResidualConv1DGLU_%d/residual_block_causal_conv/kernel" % l]
-        stack_end = off["final_convolution_1/kernel"]
-        bounds = [first(L_ * g // n_groups) for g in range(n_groups)] + [stack_end]
-        groups = [(bounds[g], bounds[g + 1]) for g in range(n_groups)]
-        rest = [(0, first(0)), (stack_end, self.n_params)]
-        return groups, [r for r in rest if r[1] > r[0]]
+        return grad_buckets(self.tensors, self.cfg.layers, self.n_params, n_groups)
 
     # ---- training step (the call a user makes) -----------------------------------------------------------
     def capture(self, x, c, targets, lengths, overlap_groups=1):

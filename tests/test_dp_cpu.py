@@ -68,3 +68,40 @@ def test_allreduce_mean_then_clip_then_adam(tmp_path):
     res = torch.load(out)
     assert res["err"] < 1e-6
     assert res["same"]
+
+
+def _bucket_worker(rank, world, port, out):
+    """PRODUCT host logic of the overlapped data-parallel step (tacotron-2_b200/wavenet.py train_step): the gradient buffer is reduced in
+    the bucket ranges of grad_buckets(), in the order the captured graphs finish them; here on CPU tensors over gloo"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from t2_import import t2
+    from bench import workload_hparams
+    hp = workload_hparams("wavenet_ce")
+    cfg = t2.wavenet.make_config(hp, 2, 7680)
+    tensors, n_params = t2.wavenet.param_table(cfg)
+    g = torch.Generator().manual_seed(10 + rank)
+    grads = torch.randn(n_params, generator=g)
+    mono = grads.clone()
+    dist.all_reduce(mono, op=dist.ReduceOp.SUM)
+    res = {}
+    for G in (1, 3, 6):
+        groups, rest = t2.wavenet.grad_buckets(tensors, hp.layers, n_params, G)
+        cover = sorted(groups + rest)
+        assert cover[0][0] == 0 and cover[-1][1] == n_params and all(a[1] == b[0] for a, b in zip(cover, cover[1:])), cover
+        buf = grads.clone()
+        works = [dist.all_reduce(buf[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in groups + rest]
+        for w in works:
+            w.wait()
+        res[G] = torch.equal(buf, mono)
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_product_gradient_buckets_over_gloo(tmp_path):
+    out = str(tmp_path / "buckets.pt")
+    mp.spawn(_bucket_worker, args=(2, 31500 + os.getpid() % 2000, out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res == {1: True, 3: True, 6: True}
