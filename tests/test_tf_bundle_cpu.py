@@ -239,3 +239,19 @@ def test_every_model_variable_has_an_invertible_reference_name():
     hp.parse("out_channels=30,upsample_type=2D")
     for n in ow.param_shapes(hp):
         assert tb.engine_name(tb.wavenet_tf_name(n, "2D")) == n, n
+
+
+def test_table_round_trip_property(tmp_path):
+    """random sorted key sets (shared prefixes, empty values, keys longer than a block) at random block sizes survive write -> read"""
+    from hypothesis import given, settings, strategies as st
+
+    keys = st.lists(st.binary(min_size=0, max_size=40), min_size=1, max_size=120, unique=True).map(sorted)
+
+    @settings(max_examples=40, deadline=None)
+    @given(keys, st.integers(min_value=16, max_value=4096), st.randoms(use_true_random=False))
+    def run(ks, block, rnd):
+        items = [(k, bytes(rnd.getrandbits(8) for _ in range(rnd.randint(0, 50)))) for k in ks]
+        p = str(tmp_path / "prop.index")
+        tb.write_table(p, items, block_size=block)
+        assert tb.read_table(p) == items
+    run()
