@@ -1,9 +1,12 @@
-"""Text cleaners (reference tacotron/utils/cleaners.py). `basic_cleaners` and `transliteration_cleaners` are complete;
-`english_cleaners` lower-cases, collapses whitespace and expands the reference's abbreviation list, but spells numbers
-digit-by-digit is NOT attempted: the reference relies on the `inflect` / `unidecode` packages for number expansion and ASCII
-folding, which are not available here (digits and non-ASCII characters are simply not in the symbol table and are dropped by
-text_to_sequence, exactly as the reference drops unknown symbols)."""
+"""Text cleaners (reference tacotron/utils/cleaners.py:1-91). `english_cleaners` follows the reference's pipeline: ASCII folding, number
+expansion (tacotron/utils/numbers.py), abbreviation expansion, whitespace collapse - and, like the reference (cleaners.py:87: the
+lowercase step is commented out), it KEEPS the case: the symbol table has both cases. ASCII folding: the reference calls `unidecode`,
+which is not installable here; accented Latin letters are folded through Unicode NFKD decomposition, other non-ASCII characters are
+dropped (unidecode would transliterate them)."""
 import re
+import unicodedata
+
+from .numbers import normalize_numbers
 
 _whitespace_re = re.compile(r"\s+")
 _abbreviations = [(re.compile(r"\b%s\." % a, re.IGNORECASE), b) for a, b in [
@@ -30,10 +33,18 @@ def basic_cleaners(text):
     return collapse_whitespace(lowercase(text))
 
 
+def convert_to_ascii(text):
+    # the pound sign survives the folding so that the "£100 -> one hundred pounds" rule of the number normaliser can fire
+    return "".join(c if c == "£" else unicodedata.normalize("NFKD", c).encode("ascii", "ignore").decode("ascii") for c in text)
+
+
+def expand_numbers(text):
+    return normalize_numbers(text)
+
+
 def transliteration_cleaners(text):
-    return collapse_whitespace(lowercase(text.encode("ascii", "ignore").decode("ascii")))
+    return collapse_whitespace(lowercase(convert_to_ascii(text)))
 
 
 def english_cleaners(text):
-    text = text.encode("ascii", "ignore").decode("ascii")
-    return collapse_whitespace(expand_abbreviations(lowercase(text)))
+    return collapse_whitespace(expand_abbreviations(expand_numbers(convert_to_ascii(text))))

@@ -45,7 +45,22 @@ def test_text_front_end():
     from tacotron.utils.text import sequence_to_text, text_to_sequence
     assert len(symbols) == 66 and symbols[0] == "_" and symbols[1] == "~"
     seq = text_to_sequence("Hello,  World_~ 9!", ["english_cleaners"])
-    assert seq[-1] == 1 and 0 not in seq and sequence_to_text(seq) == "hello, world !~"      # digits / pad / eos symbols dropped, EOS appended
+    # case is kept (the reference's english_cleaners does not lowercase, cleaners.py:87), numbers are spelled out, pad / eos symbols
+    # inside the text are dropped, EOS is appended
+    assert seq[-1] == 1 and 0 not in seq and sequence_to_text(seq) == "Hello, World nine!~"
+    assert sequence_to_text(text_to_sequence("Hello,  World 9!", ["basic_cleaners"])) == "hello, world !~"
+    from tacotron.utils.cleaners import english_cleaners
+    from tacotron.utils.numbers import number_to_words
+    known = {"In 1984 he paid $5.50 for 3 books.": "In nineteen eighty-four he paid five dollars, fifty cents for three books.",
+             "1905, 2000, 2005, 1900, 2015, 1010": "nineteen oh five, two thousand, two thousand five, nineteen hundred, twenty fifteen, ten ten",
+             "It costs £1,000 or $1.": "It costs one thousand pounds or one dollar.",
+             "Pi is 3.14; the 22nd of May, 101st.": "Pi is three point fourteen; the twenty-second of May, one hundred and first.",
+             "Dr. Smith and Mr. Jones at Café Noël": "doctor Smith and mister Jones at Cafe Noel",
+             "12,345 and 1,000,000": "twelve thousand, three hundred forty-five and one million"}
+    for text, want in known.items():
+        assert english_cleaners(text) == want, (text, english_cleaners(text))
+    assert number_to_words(1001, andword="") == "one thousand one" and number_to_words(1001) == "one thousand and one"
+    assert number_to_words(1234) == "one thousand, two hundred and thirty-four" and number_to_words("12th") == "twelfth"
 
 
 def test_tacotron_feeder_batches(tmp_path):
