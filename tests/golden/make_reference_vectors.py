@@ -280,6 +280,24 @@ def main():
     out["lr_wavenet_exponential"] = np.array([float(wm._exponential_learning_rate_decay(rhp.wavenet_learning_rate, torch.tensor(int(s_)), rhp.wavenet_decay_rate,
                                                                                          rhp.wavenet_decay_steps)) for s_ in steps])
 
+    # ---------------- J. WaveNet feeder: random hop-aligned crop + conditioning normalisation (wavenet_vocoder/feeder.py:319-401) ---
+    wfd = rwf.Feeder.__new__(rwf.Feeder)
+    wfd._hparams = rhp
+    rj = np.random.RandomState(77)
+    hopj = ra.get_hop_size(rhp)
+    frames_j = [70, 41, 40, 55]                         # 41+ frames exceed max_time_steps = 11000 (40 frames): those are cropped
+    xs = [rj.randint(0, 256, f * hopj).astype(np.int16) for f in frames_j]
+    cs_ = [rj.uniform(-4.6, 4.6, (f, 80)).astype(np.float32) for f in frames_j]
+    out["wnf_frames"] = np.array(frames_j)
+    for i, (x_, c_) in enumerate(zip(xs, cs_)):
+        out["wnf_x%d" % i], out["wnf_c%d" % i] = x_, c_
+    np.random.seed(2024)
+    cropped = wfd._adjust_time_resolution([(x_, c_, 0, len(x_)) for x_, c_ in zip(xs, cs_)], True, wfd._limit_time())
+    for i, (x_, c_, _, _) in enumerate(cropped):
+        out["wnf_crop_x%d" % i], out["wnf_crop_c%d" % i] = x_, c_
+    out["wnf_local_conditions"] = wfd._prepare_local_conditions(True, [b_[1] for b_ in cropped])
+    out["wnf_max_time_steps"] = np.array(wfd._limit_time())
+
     np.savez_compressed(os.path.join(HERE, "reference_exec.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote %d arrays, %d hparams" % (len(out), len(hp_json)))
 

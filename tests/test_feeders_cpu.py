@@ -129,3 +129,24 @@ def test_wavenet_feeder_batches(tmp_path):
         assert c.shape == (4, 80, x.shape[1] // hop) and c.min() >= 0.0 and c.max() <= 1.0      # clip +-4 -> [0, 1] (feeder.py:323-335)
         for i in range(4):
             assert (x[i, L[i]:] == 0).all() and (c[i, :, L[i] // hop:] == 0).all()             # audio zero-padded, mels padded with the range minimum -> 0
+
+
+def test_wavenet_feeder_crop_and_conditioning_match_reference_executed_vectors():
+    """the reference's OWN _adjust_time_resolution / _prepare_local_conditions (wavenet_vocoder/feeder.py:319-401) executed with
+    np.random.seed(2024): the same random hop-aligned crops (np.random.randint stream) and the same clipped + [0, 1]-rescaled conditioning"""
+    from wavenet_vocoder.feeder import Feeder
+    hp = hparams.copy()
+    f = Feeder.__new__(Feeder)
+    f._hparams, f.local_condition = hp, True
+    f._rng = np.random.RandomState(2024)
+    assert f._limit_time() == int(R["wnf_max_time_steps"])
+    n = len(R["wnf_frames"])
+    batch = [(R["wnf_x%d" % i], R["wnf_c%d" % i], len(R["wnf_x%d" % i])) for i in range(n)]
+    crops = [f._crop(x, c) for x, c, _ in batch]
+    for i, (x, c) in enumerate(crops):
+        assert np.array_equal(x, R["wnf_crop_x%d" % i]) and np.array_equal(c, R["wnf_crop_c%d" % i]), i
+    f._rng = np.random.RandomState(2024)
+    out = f.prepare_batch(batch)
+    assert np.array_equal(out["local_condition_features"], R["wnf_local_conditions"])
+    assert out["local_condition_features"].min() >= 0.0 and out["local_condition_features"].max() <= 1.0
+    assert out["inputs"].shape == (n, 11000) and (out["input_lengths"] == 11000).all()
