@@ -298,6 +298,19 @@ def main():
     out["wnf_local_conditions"] = wfd._prepare_local_conditions(True, [b_[1] for b_ in cropped])
     out["wnf_max_time_steps"] = np.array(wfd._limit_time())
 
+    # ---------------- K. Tacotron feeder: one whole batch through the reference's _prepare_batch (tacotron/feeder.py:198-229) ----
+    rk = np.random.RandomState(88)
+    ex = []
+    for i, (nin, nfr) in enumerate([(12, 31), (7, 18), (15, 40), (9, 25)]):
+        ex.append((rk.randint(2, 66, nin).astype(np.int32), rk.uniform(-4, 4, (nfr, 80)).astype(np.float32), np.zeros(nfr - 1, dtype=np.float32),
+                   rk.uniform(-4, 4, (nfr, 20)).astype(np.float32), nfr))
+        out["tf_in%d" % i], out["tf_mel%d" % i], out["tf_lin%d" % i] = ex[-1][0], ex[-1][1], ex[-1][3]
+    fd._hparams = rhp
+    np.random.seed(99)
+    res = fd._prepare_batch(list(ex), 1)
+    for name, arr in zip(("inputs", "input_lengths", "mel_targets", "token_targets", "linear_targets", "targets_lengths", "split_infos"), res):
+        out["tf_batch_" + name] = arr
+
     np.savez_compressed(os.path.join(HERE, "reference_exec.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote %d arrays, %d hparams" % (len(out), len(hp_json)))
 

@@ -150,3 +150,20 @@ def test_wavenet_feeder_crop_and_conditioning_match_reference_executed_vectors()
     assert np.array_equal(out["local_condition_features"], R["wnf_local_conditions"])
     assert out["local_condition_features"].min() >= 0.0 and out["local_condition_features"].max() <= 1.0
     assert out["inputs"].shape == (n, 11000) and (out["input_lengths"] == 11000).all()
+
+
+def test_tacotron_feeder_batch_matches_reference_executed_vectors():
+    """one whole batch through the reference's OWN Feeder._prepare_batch (tacotron/feeder.py:198-229; its in-batch np.random.shuffle
+    replayed): inputs, lengths, mel / stop-token / linear targets with the reference's padding values, bit for bit"""
+    from tacotron.feeder import Feeder
+    hp = hparams.copy()
+    f = Feeder.__new__(Feeder)
+    f._hparams, f._pad, f._token_pad, f._target_pad = hp, 0, 1.0, float(R["taco_target_pad"])
+    ex = [(R["tf_in%d" % i], R["tf_mel%d" % i], np.zeros(len(R["tf_mel%d" % i]) - 1, dtype=np.float32), R["tf_lin%d" % i], len(R["tf_mel%d" % i]))
+          for i in range(4)]
+    np.random.RandomState(99).shuffle(ex)
+    b = f.prepare_batch(ex)
+    for ours, theirs in (("inputs", "inputs"), ("input_lengths", "input_lengths"), ("mel_targets", "mel_targets"), ("token_targets", "token_targets"),
+                         ("linear_targets", "linear_targets"), ("targets_lengths", "targets_lengths")):
+        assert np.array_equal(b[ours], R["tf_batch_" + theirs]), ours
+    assert R["tf_batch_split_infos"].tolist() == [[b["inputs"].shape[1], b["mel_targets"].shape[1], b["token_targets"].shape[1], b["linear_targets"].shape[1]]]
