@@ -7,7 +7,7 @@
 // Dataflow (rows = b * T + t, batch-major; N = B * T):
 //   mel_outputs fp32 [N][M] -> bf16
 //   conv bank: k = 1..K convolutions M -> CC ('same' padding, the extra pad of an even kernel on the right) + bias + ReLU, each one a
-//     tap-shifted GEMM on the tcgen05 engine writing its 128-column slice of Y [N][K*CC]; ONE batch norm over the K*CC channels
+//     tap-shifted GEMM on the tcgen05 engine writing its 128-column slice of Y [N][K*CC]; every layer's batch norm runs on its slice
 //   max-pool (2, stride 1, 'same': max(x[t], x[t+1]))
 //   proj1 (k = 3, K*CC -> PJ, ReLU, BN), proj2 (k = 3, PJ -> M, linear, BN), + mel_outputs, dense M -> HU
 //   NH highway layers: one GEMM with N = 2 HU ([H | T] pre-activations) + an elementwise kernel
@@ -66,7 +66,6 @@ struct CL {
   long long w_dlin, w_dout, w_dXP, w_dh, w_dhb, w_dHT, w_dhin, w_dY2b, w_d1, w_d2, w_dP, w_dbank, w_dx0[3], w_bsum, w_tiles, w_jobs, w_regtab;
   long long workspace_bytes;
   int n_jobs, n_reg;
-  std::vector<int> tile_off, tile_cnt;
 };
 
 long long addp(CL& lo, const std::string& name, std::initializer_list<int> shape, bool trainable = true) {
