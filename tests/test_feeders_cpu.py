@@ -167,3 +167,42 @@ def test_tacotron_feeder_batch_matches_reference_executed_vectors():
                          ("linear_targets", "linear_targets"), ("targets_lengths", "targets_lengths")):
         assert np.array_equal(b[ours], R["tf_batch_" + theirs]), ours
     assert R["tf_batch_split_infos"].tolist() == [[b["inputs"].shape[1], b["mel_targets"].shape[1], b["token_targets"].shape[1], b["linear_targets"].shape[1]]]
+
+
+def test_wavenet_preprocessor_layout_on_cpu(tmp_path, monkeypatch):
+    """datasets/wavenet_preprocessor.py (reference :11-154) end to end with the three GPU-backed audio calls replaced by the oracle's
+    restatements (the kernels have their own GPU parity tests): file naming, dtypes, hop alignment, map.txt rows, and the rows feed the
+    WaveNet feeder"""
+    from scipy.io import wavfile
+    from oracle import audio as oa
+    from datasets import audio, wavenet_preprocessor as wp
+    import wavenet_vocoder.util as wu
+    monkeypatch.setattr(audio, "melspectrogram", lambda w, hp: oa.melspectrogram(np.asarray(w, dtype=np.float32), hp).astype(np.float32))
+    monkeypatch.setattr(audio, "preemphasis", lambda w, k, p=True: oa.preemphasis(w, k, p))
+    monkeypatch.setattr(wp, "mulaw_quantize", lambda x, mu=256: oa.mulaw_quantize(np.asarray(x, dtype=np.float32)))
+    src = tmp_path / "wavs"
+    src.mkdir()
+    rng = np.random.default_rng(5)
+    for i in range(9):
+        n = int(rng.integers(6000, 9000))
+        w = 0.3 * np.sin(np.arange(n) * (0.03 + 0.004 * i)) + 0.01 * rng.standard_normal(n)
+        wavfile.write(str(src / ("utt%02d.wav" % i)), 22050, (w * 32767).astype(np.int16))
+    hp = hparams.copy()
+    hp.parse("input_type=mulaw-quantize,quantize_channels=256,out_channels=256,trim_silence=False,wavenet_batch_size=2,wavenet_test_size=2,"
+             "wavenet_test_batches=None,max_time_steps=5500,train_with_GTA=False")
+    mel_dir, wav_dir = tmp_path / "out" / "mels", tmp_path / "out" / "audio"
+    mel_dir.mkdir(parents=True)
+    wav_dir.mkdir(parents=True)
+    rows = wp.build_from_path(hp, str(src), str(mel_dir), str(wav_dir))
+    assert len(rows) == 9
+    for a_path, m_path, m2, g, steps, frames in rows:
+        a, m = np.load(a_path), np.load(m_path)
+        assert m2 == m_path and g == "<no_g>" and a.dtype == np.int16 and m.dtype == np.float32
+        assert m.shape == (frames, 80) and len(a) == steps == frames * 275 and 0 <= a.min() and a.max() <= 255
+    import wavenet_preprocess
+    wavenet_preprocess.write_metadata(rows, str(tmp_path / "out"), hp)
+    from wavenet_vocoder.feeder import Feeder
+    f = Feeder(str(tmp_path / "out" / "map.txt"), "", hp)
+    b = f.train_group()[0]
+    assert b["inputs"].shape[0] == 2 and b["inputs"].shape[1] <= 5500 and b["inputs"].shape[1] % 275 == 0
+    assert b["local_condition_features"].shape[1:] == (80, b["inputs"].shape[1] // 275)
