@@ -53,7 +53,8 @@ def test_text_front_end():
     from tacotron.utils.numbers import number_to_words
     known = {"In 1984 he paid $5.50 for 3 books.": "In nineteen eighty-four he paid five dollars, fifty cents for three books.",
              "1905, 2000, 2005, 1900, 2015, 1010": "nineteen oh five, two thousand, two thousand five, nineteen hundred, twenty fifteen, ten ten",
-             "It costs £1,000 or $1.": "It costs one thousand pounds or one dollar.",
+             "It costs £1,000 or $1.": "It costs PSone thousand or one dollar.",       # unidecode turns the pound sign into "PS" before the rule
+             "“Quoted” — naïve straße…": "\"Quoted\" -- naive strasse...",
              "Pi is 3.14; the 22nd of May, 101st.": "Pi is three point fourteen; the twenty-second of May, one hundred and first.",
              "Dr. Smith and Mr. Jones at Café Noël": "doctor Smith and mister Jones at Cafe Noel",
              "12,345 and 1,000,000": "twelve thousand, three hundred forty-five and one million"}
@@ -206,3 +207,27 @@ def test_wavenet_preprocessor_layout_on_cpu(tmp_path, monkeypatch):
     b = f.train_group()[0]
     assert b["inputs"].shape[0] == 2 and b["inputs"].shape[1] <= 5500 and b["inputs"].shape[1] % 275 == 0
     assert b["local_condition_features"].shape[1:] == (80, b["inputs"].shape[1] // 275)
+
+
+def test_text_front_end_matches_reference_executed_vectors():
+    """tests/golden/reference_text.json is written by executing the reference's tacotron/utils/text.py + cleaners.py + cmudict.py
+    (make_reference_text.py): cleaner pipelines on ASCII text, the {ARPAbet} cutting rule, dropped symbols, EOS, the dictionary parser"""
+    import io
+    import json
+    from tacotron.utils import cmudict
+    from tacotron.utils.symbols import symbols
+    from tacotron.utils.text import sequence_to_text, text_to_sequence
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_text.json")) as f:
+        R = json.load(f)
+    assert symbols == R["symbols"] and cmudict.valid_symbols == R["valid_symbols"]
+    assert len(R["cases"]) >= 30
+    for c in R["cases"]:
+        seq = text_to_sequence(c["text"], c["cleaners"])
+        assert seq == c["sequence"], (c["text"], c["cleaners"])
+        assert sequence_to_text(seq) == c["round_trip"]
+    for keep in (1, 0):
+        d = cmudict.CMUDict(io.StringIO(R["dict_text"]), keep_ambiguous=bool(keep))
+        want = R["cmudict_keep_%d" % keep]
+        assert len(d) == want["len"]
+        for w, p in want["lookups"].items():
+            assert d.lookup(w) == p, w
