@@ -98,7 +98,7 @@ class Tacotron(object):
             M = hp.num_mels
             self.tower_decoder_output = [eng.workspace_tensor("decoder_output", (B, T_out, M))]
             self.tower_mel_outputs = [eng.workspace_tensor("mel_outputs", (B, T_out, M))]
-            self.tower_alignments = [eng.workspace_tensor("alignments", (T_out, B, T_in)).transpose(0, 1)]
+            self.tower_alignments = [eng.workspace_tensor("alignments", (T_out, B, T_in)).permute(1, 2, 0)]  # [B, T_in, T_out] (tacotron.py:222)
             logits = eng.workspace_tensor("stop_logits", (B, T_out))
             self.tower_stop_token_prediction = [logits if (is_training or is_evaluating) else torch.sigmoid(logits)]
         else:                                                       # TacoTestHelper (free running)
@@ -107,7 +107,7 @@ class Tacotron(object):
             out = eng.synthesize(ids, lens)
             self.tower_decoder_output = [out["decoder_output"]]
             self.tower_mel_outputs = [out["mel_outputs"]]
-            self.tower_alignments = [out["alignments"]]
+            self.tower_alignments = [out["alignments"].transpose(1, 2)]
             self.tower_stop_token_prediction = [out["stop_token_prediction"]]
             if post_condition:
                 self.tower_linear_outputs = [eng.linear_from_mel(out["mel_outputs"])]

@@ -2,7 +2,8 @@
 mel_filenames)` writes `mel-<basename>.npy` ([frames, num_mels] float32). GTA mode teacher-forces on the ground-truth mels
 (mel_filenames given); natural mode runs the free-running decoder until every row's stop token fires. With a log_dir (eval mode) the
 Griffin-Lim previews of the reference are written too (`wavs/wav-<b>-mel.wav`, and `wav-<b>-linear.wav` + `linear-<b>.npy` when the
-post-processing net is on; GPU Griffin-Lim of datasets/audio.py); plots are not produced."""
+post-processing net is on; GPU Griffin-Lim of datasets/audio.py) and so are the plots (`plots/alignment-<b>.png`, `plots/mel-<b>.png`,
+`plots/linear-<b>.png`; tacotron/utils/plot.py writes the PNGs itself)."""
 import os
 
 import numpy as np
@@ -12,6 +13,7 @@ import t2_checkpoint
 from datasets import audio
 from tacotron.feeder import pad_input, pad_target
 from tacotron.models import create_model
+from tacotron.utils import plot
 from tacotron.utils.text import text_to_sequence
 
 
@@ -58,9 +60,17 @@ class Synthesizer(object):
             # evaluation artefacts of the reference (synthesizer.py:199-224): Griffin-Lim inversions of the mel and, with the
             # post-processing net, of the linear spectrogram (GPU Griffin-Lim, datasets/audio.py)
             os.makedirs(os.path.join(log_dir, "wavs"), exist_ok=True)
+            os.makedirs(os.path.join(log_dir, "plots"), exist_ok=True)
+            alignments = self.model.tower_alignments[0].cpu().numpy()                 # [B, T_in, T_out]
             for i, (m, b) in enumerate(zip(mels, basenames)):
                 if len(m) < 2:
                     continue
+                plot.plot_alignment(alignments[i], os.path.join(log_dir, "plots", "alignment-%s.png" % b), title=texts[i], split_title=True,
+                                    max_len=len(m))
+                plot.plot_spectrogram(m, os.path.join(log_dir, "plots", "mel-%s.png" % b), title=texts[i], split_title=True)
+                if hp.predict_linear:
+                    plot.plot_spectrogram(linears[i], os.path.join(log_dir, "plots", "linear-%s.png" % b), title=texts[i], split_title=True,
+                                          auto_aspect=True)
                 audio.save_wav(audio.inv_mel_spectrogram(m.T, hp), os.path.join(log_dir, "wavs", "wav-%s-mel.wav" % b), hp.sample_rate)
                 if hp.predict_linear:
                     np.save(os.path.join(out_dir, "linear-%s.npy" % b), linears[i].astype(np.float32), allow_pickle=False)

@@ -11,6 +11,7 @@ import infolog
 import t2_checkpoint
 from tacotron.feeder import Feeder
 from tacotron.models import create_model
+from tacotron.utils import plot
 
 log = infolog.log
 
@@ -106,6 +107,13 @@ def train(log_dir, args, hparams):
                 log("Eval loss for global step %d: %.3f (before %.3f, after %.3f, stop %.3f)" % (step, m[0], m[1], m[2], m[3]))
                 np.save(os.path.join(eval_dir, "step-%d-eval-mel-prediction.npy" % step), model.tower_mel_outputs[0][0].cpu().numpy())
                 np.save(os.path.join(eval_dir, "step-%d-eval-align.npy" % step), model.tower_alignments[0][0].cpu().numpy())
+                if rank == 0:           # plots of the last held-out batch's first utterance (tacotron/train.py:296-311)
+                    n = int(tb["targets_lengths"][0])
+                    title = "Tacotron, step=%d, loss=%.5f" % (step, m[0])
+                    plot.plot_alignment(model.tower_alignments[0][0].cpu().numpy(), os.path.join(eval_dir, "step-%d-eval-align.png" % step),
+                                        title=title, max_len=n)
+                    plot.plot_spectrogram(model.tower_mel_outputs[0][0].cpu().numpy(), os.path.join(eval_dir, "step-%d-eval-mel-spectrogram.png"
+                                          % step), title=title, target_spectrogram=tb["mel_targets"][0].cpu().numpy(), max_len=n)
             if (step % args.checkpoint_interval == 0 or step == args.tacotron_train_steps) and rank == 0:
                 path = t2_checkpoint.save(save_dir, "tacotron_model.ckpt", model._eng)
                 log("\nSaving Model at step %d: %s" % (step, path))

@@ -90,7 +90,7 @@ def test_tacotron_create_model_train_gta_synthesize():
         losses.append(float(model.add_loss()))
         model.add_optimizer(step)
     assert losses[-1] < 0.9 * losses[0], losses
-    assert model.tower_mel_outputs[0].shape == (B, T_out, 80) and model.tower_alignments[0].shape == (B, T_out, T_in)
+    assert model.tower_mel_outputs[0].shape == (B, T_out, 80) and model.tower_alignments[0].shape == (B, T_in, T_out)
     model.initialize(inputs, lens, mel, gta=True)                                    # GTA: teacher forced, inference statistics
     assert model.tower_mel_outputs[0].shape == (B, T_out, 80)
     model.initialize(inputs, lens)                                                   # free-running synthesis
