@@ -231,3 +231,15 @@ def test_text_front_end_matches_reference_executed_vectors():
         assert len(d) == want["len"]
         for w, p in want["lookups"].items():
             assert d.lookup(w) == p, w
+
+
+def test_paper_hparams_is_a_superset_of_the_defaults():
+    import paper_hparams
+    base, paper = hparams.values(), paper_hparams.hparams.values()
+    assert set(base) | {"upsample_conditional_features"} == set(paper)
+    changed = {k for k in base if base[k] != paper[k]}
+    assert {"layers", "stacks", "residual_channels", "gate_channels", "skip_out_channels", "out_channels", "upsample_type",
+            "upsample_scales", "predict_linear"} <= changed and len(changed) == 23
+    assert (paper["layers"], paper["stacks"], paper["out_channels"], paper["upsample_scales"]) == (24, 4, 30, [5, 5, 11])
+    assert int(np.prod(paper["upsample_scales"])) == paper["hop_size"]
+    assert hparams.layers == 20 and hparams.predict_linear is True           # the defaults were not touched by the import
