@@ -16,14 +16,24 @@ TF-layer semantics (LSTMCell gate order i,j,f,o + forget_bias 1, BahdanauAttenti
 eps 1e-3 with biased batch variance, 'same' conv padding, tf.losses.mean_squared_error) are restated from the public
 TF 1.x definitions.
 
-PINNING. Pinned by EXECUTING the reference's own source on a TF-1 shim of elementary ops (tests/golden/make_reference_vectors.py,
-tests/test_reference_pinned.py): MaskedMSE, MaskedSigmoidCrossEntropy, MaskedLinearLoss, sequence_mask (modules.py:400-485), the
-location-sensitive score and the smoothing normalisation (attention.py:38-92), the learning-rate schedule (tacotron.py:439-463), the
-feeder padding helpers. PARITY UNPINNED for everything built from tf.layers / tf.nn.rnn_cell / tf.contrib.seq2seq (convolutions,
-batch norm, LSTM / GRU cells, zoneout wrapper, BahdanauAttention memory masking, dynamic_decode, CBHG): restated from the TF 1.x
-definitions and checked through known answers - parameter counts 27.19 M / 29.02 M with the CBHG head, alignments
-are a masked probability distribution, zero-length-padding invariance of the encoder, zoneout / dropout off == deterministic, gradient
-checks of the hand-derived pieces the CUDA path mirrors (tests/test_oracle_tacotron.py).
+PINNING, two levels.
+(1) Elementary-op code (tests/golden/make_reference_vectors.py, tests/test_reference_pinned.py): MaskedMSE, MaskedSigmoidCrossEntropy,
+MaskedLinearLoss, sequence_mask (modules.py:400-485), the location-sensitive score and the smoothing normalisation
+(attention.py:38-92), the learning-rate schedule (tacotron.py:439-463), the feeder padding helpers - the reference's source runs AS IS.
+(2) The whole graph (tests/golden/make_reference_graph_vectors.py, tests/test_reference_graph.py): the reference's
+`Tacotron.initialize()` + `add_loss()` are EXECUTED - tacotron.py, modules.py, attention.py, Architecture_wrappers.py, helpers.py,
+custom_decoder.py unchanged - on a stand-in for the tf.layers / rnn_cell / seq2seq classes they compose (tests/golden/tf_shim_graph.py),
+in training (every dropout / zoneout mask recorded and injected here), masked-loss training, evaluation, GTA and free-running
+synthesis. forward / loss_fn / synthesize / linear_head reproduce the executed reference to <= 4e-6 (outputs), 1e-7 (loss terms) and
+1e-5 relative (d loss / d variable, all 102 trainable variables), and the variable names the reference's scopes generate equal
+t2_tf_bundle.tacotron_tf_name over the parameter table. This pins the reference's COMPOSITION: layer order, scopes, activation /
+batch-norm / dropout placement, the zoneout wrapper and its un-zoned output, decoder-cell wiring, helpers, stop rule, CBHG, loss terms,
+regularisation filter.
+STILL A RESTATEMENT: the primitives under that composition (Dense, Conv1D 'same', BatchNormalization eps 1e-3 / biased variance,
+LSTMCell i,j,f,o + forget_bias 1, GRUCell, dynamic_rnn length handling, BahdanauAttention memory / score masking, dynamic_decode) - in
+the stand-in as in this file they follow the public TF 1.x definitions; TensorFlow itself cannot run here.
+Known answers on top: parameter counts 27.19 M / 29.02 M with the CBHG head, alignments are a masked probability distribution,
+zero-length-padding invariance of the encoder (tests/test_oracle_tacotron.py).
 """
 import math
 

@@ -1,0 +1,212 @@
+"""Generates tests/golden/reference_graph.npz by EXECUTING the reference's own Tacotron graph-construction code
+(/root/reference/tacotron/models/tacotron.py `Tacotron.initialize` + `add_loss`, with modules.py, attention.py,
+Architecture_wrappers.py, helpers.py and custom_decoder.py underneath) on the TF-1 stand-in of tf_shim.py + tf_shim_graph.py.
+
+  python tests/golden/make_reference_graph_vectors.py        # needs /root/reference; only the committed .npz travels
+
+Scenarios (small widths so that the fixture stays a few hundred KB; every hparam not listed keeps the reference's default):
+  train     is_training=True, predict_linear=True, mask_decoder=False: all dropout / zoneout paths on; outputs, the five loss terms
+            and d loss / d variable for every trainable variable (autograd through the executed reference graph)
+  train_md  is_training=True, predict_linear=False, mask_decoder=True: the masked losses inside the whole graph
+  eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
+  gta       gta=True: as eval without the post-processing net
+  synth     free running (TacoTestHelper), stop rule, max_iters
+The variables are created by the reference code's own tf.get_variable / layer calls (values drawn here from a seeded generator) and
+are stored under the names the reference's scopes give them - tests/test_reference_graph.py checks those names against
+t2_tf_bundle.tacotron_tf_name, i.e. the checkpoint name map is pinned by the reference's code, not by a reading of it.
+Dropout / zoneout masks are recorded in execution order and stored in the oracle's convention.
+
+Honesty: the layer primitives under the reference's code (Dense, Conv1D, BatchNormalization, LSTMCell, GRUCell, dynamic_rnn,
+BahdanauAttention, dynamic_decode) are tf_shim_graph.py's restatement of the TF 1.x definitions; what is executed unchanged is the
+reference's composition of them. See tf_shim_graph.py's header."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+SMALL = dict(
+    embedding_dim=16, enc_conv_num_layers=3, enc_conv_kernel_size=5, enc_conv_channels=16, encoder_lstm_units=8,
+    attention_dim=12, attention_filters=4, attention_kernel=7, prenet_layers=[16, 16], decoder_layers=2, decoder_lstm_units=24,
+    num_mels=10, num_freq=33, postnet_num_layers=5, postnet_kernel_size=5, postnet_channels=16,
+    cbhg_kernels=4, cbhg_conv_channels=8, cbhg_pool_size=2, cbhg_projection=16, cbhg_projection_kernel_size=3,
+    cbhg_highwaynet_layers=2, cbhg_highway_units=12, cbhg_rnn_units=6,
+    outputs_per_step=1, tacotron_num_gpus=1, split_on_cpu=True, max_iters=9,
+)
+
+
+def main():
+    assert os.path.isdir(REF), "the reference tree is needed to (re)generate these fixtures"
+    sys.path.insert(0, HERE)
+    import tf_shim
+    import tf_shim_graph as G
+    G.install()
+    sys.path.insert(0, REF)
+    import hparams as ref_hparams_mod
+    rhp = ref_hparams_mod.hparams
+    from tacotron.models.tacotron import Tacotron
+
+    for k, v in SMALL.items():
+        assert hasattr(rhp, k), k
+        setattr(rhp, k, v)
+    out = {"small_hparams_keys": np.array(sorted(SMALL)), "small_hparams_values": np.array([repr(SMALL[k]) for k in sorted(SMALL)])}
+
+    g = torch.Generator().manual_seed(77)
+    B, T_in, T_out = 3, 7, 6
+    in_len = torch.tensor([7, 5, 4], dtype=torch.int32)
+    tgt_len = torch.tensor([6, 4, 5], dtype=torch.int32)
+    inputs = torch.randint(2, 66, (B, T_in), generator=g, dtype=torch.int32)
+    for b in range(B):
+        inputs[b, in_len[b]:] = 0
+    mel = torch.randn(B, T_out, rhp.num_mels, generator=g)
+    lin = torch.randn(B, T_out, rhp.num_freq, generator=g)
+    stop = (torch.arange(T_out)[None, :] >= (tgt_len[:, None] - 1)).float()
+    split_infos = np.array([[T_in, T_out * rhp.num_mels, T_out, T_out * rhp.num_freq]], dtype=np.int32)
+    out.update(inputs=inputs.numpy(), input_lengths=in_len.numpy(), targets_lengths=tgt_len.numpy(), mel_targets=mel.numpy(),
+               linear_targets=lin.numpy(), stop_targets=stop.numpy())
+    Tt = tf_shim.T
+
+    def run(tag, variables, seed, **kw):
+        """one execution of the reference's initialize(); returns the model and the recorded random masks"""
+        G.reset(seed=seed, variables=variables)
+        model = Tacotron(rhp)
+        args = dict(mel_targets=Tt(mel.clone()), stop_token_targets=Tt(stop.clone()), targets_lengths=Tt(tgt_len.clone()),
+                    split_infos=split_infos)
+        args.update(kw)
+        for k in [k for k, v in args.items() if v is None]:
+            del args[k]
+        model.initialize(Tt(inputs.clone()), Tt(in_len.clone()), **args)
+        return model, list(G.S.drops)
+
+    def names_of(drops):
+        return [(scope, kind, tuple(m.shape)) for scope, kind, m in drops]
+
+    def masks_to_oracle(tag, drops, training, T_steps, with_post=True):
+        """execution order of the recorded draws (see the scenario list) -> the oracle's mask dict, flattened into arrays"""
+        q = list(drops)
+        H, D = rhp.encoder_lstm_units, rhp.decoder_lstm_units
+        keep = 1.0 - rhp.tacotron_dropout_rate
+
+        def pop(scope_part, kind, shape):
+            scope, k, m = q.pop(0)
+            assert scope_part in scope and k == kind and tuple(m.shape) == tuple(shape), (tag, scope, k, tuple(m.shape), scope_part, shape)
+            return m
+        if training:
+            for i in range(rhp.enc_conv_num_layers):
+                out["%s_mask_enc_drop_%d" % (tag, i)] = (pop("encoder_convolutions", "layers.dropout", (B, T_in, rhp.enc_conv_channels)) / keep).numpy()
+            for d in ("fw", "bw"):
+                c = torch.stack([torch.zeros(B, H)] * T_in)
+                h = torch.stack([torch.zeros(B, H)] * T_in)
+                for tau in range(T_in):
+                    mc = pop("bidirectional_rnn/" + d, "nn.dropout", (B, H))
+                    mh = pop("bidirectional_rnn/" + d, "nn.dropout", (B, H))
+                    for b in range(B):
+                        # loop step tau of the (per-length reversed) backward pass is original time len - 1 - tau
+                        t = tau if d == "fw" else int(in_len[b]) - 1 - tau
+                        if 0 <= t < T_in and tau < int(in_len[b]):
+                            c[t, b], h[t, b] = mc[b], mh[b]
+                out["%s_mask_enc_zone_%s_c" % (tag, d)], out["%s_mask_enc_zone_%s_h" % (tag, d)] = c.numpy(), h.numpy()
+        pre = [[], []]
+        zone = {(l, s): [] for l in (1, 2) for s in "ch"}
+        for t in range(T_steps):
+            for i, n in enumerate(rhp.prenet_layers):
+                pre[i].append(pop("decoder_prenet", "layers.dropout", (B, n)) / keep)
+            if training:
+                for l in (1, 2):
+                    for s in "ch":
+                        zone[(l, s)].append(pop("decoder_LSTM", "nn.dropout", (B, D)))
+        for i in range(len(rhp.prenet_layers)):
+            out["%s_mask_prenet_drop_%d" % (tag, i)] = torch.stack(pre[i], dim=1).numpy()               # [B, T, n]
+        if training:
+            for (l, s), v in zone.items():
+                out["%s_mask_dec_zone_%d_%s" % (tag, l, s)] = torch.stack(v).numpy()                      # [T, B, D]
+            for i in range(rhp.postnet_num_layers):
+                out["%s_mask_post_drop_%d" % (tag, i)] = (pop("postnet_convolutions", "layers.dropout", (B, T_steps, rhp.postnet_channels)) / keep).numpy()
+        assert not q, (tag, names_of(q))
+
+    def save_outputs(tag, model, linear):
+        out[tag + "_decoder_output"] = model.tower_decoder_output[0].detach().numpy()
+        out[tag + "_mel_outputs"] = model.tower_mel_outputs[0].detach().numpy()
+        out[tag + "_alignments"] = model.tower_alignments[0].detach().numpy()                               # [B, T_in, T_out]
+        out[tag + "_stop_token_prediction"] = model.tower_stop_token_prediction[0].detach().numpy()
+        if linear:
+            out[tag + "_linear_outputs"] = model.tower_linear_outputs[0].detach().numpy()
+
+    def save_losses(tag, model):
+        for k in ("before_loss", "after_loss", "stop_token_loss", "regularization_loss", "linear_loss", "loss"):
+            out["%s_%s" % (tag, k)] = np.asarray(float(getattr(model, k)), dtype=np.float64)
+
+    # ---- train: creates the variables -------------------------------------------------------------------------------------------
+    rhp.predict_linear, rhp.mask_decoder = True, False
+    model, drops = run("train", None, 1, linear_targets=Tt(lin.clone()), is_training=True, global_step=Tt(torch.tensor(0)))
+    variables = {k: v.detach().clone() for k, v in G.S.vars.items()}
+    out["var_names"] = np.array(list(variables))
+    out["var_trainable"] = np.array([bool(v.requires_grad) for v in G.S.vars.values()])
+    for k, v in variables.items():
+        out["var/" + k] = v.numpy()
+    masks_to_oracle("train", drops, True, T_out)
+    save_outputs("train", model, True)
+    model.add_loss()
+    save_losses("train", model)
+    model.loss.backward()
+    for k, v in G.S.vars.items():
+        if v.requires_grad:
+            out["grad/" + k] = (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy()
+    n_params = sum(int(v.numel()) for v in G.S.vars.values() if v.requires_grad)
+    print("train: %d variables (%d trainable parameters), loss %.6f" % (len(variables), n_params, float(model.loss)))
+
+    # ---- train with masked losses, no linear head --------------------------------------------------------------------------------
+    rhp.predict_linear, rhp.mask_decoder = False, True
+    no_cbhg = {k: v for k, v in variables.items() if "CBHG" not in k and "cbhg" not in k}
+    model, drops = run("train_md", no_cbhg, 2, is_training=True, global_step=Tt(torch.tensor(0)))
+    masks_to_oracle("train_md", drops, True, T_out)
+    save_outputs("train_md", model, False)
+    model.add_loss()
+    save_losses("train_md", model)
+
+    # ---- eval / GTA ------------------------------------------------------------------------------------------------------------------
+    rhp.predict_linear, rhp.mask_decoder = True, False
+    model, drops = run("eval", variables, 3, linear_targets=Tt(lin.clone()), is_evaluating=True)
+    masks_to_oracle("eval", drops, False, T_out)
+    save_outputs("eval", model, True)
+    model.add_loss()
+    save_losses("eval", model)
+    model, drops = run("gta", variables, 4, stop_token_targets=None, targets_lengths=None, gta=True)
+    masks_to_oracle("gta", drops, False, T_out)
+    save_outputs("gta", model, False)
+
+    # ---- free-running synthesis ------------------------------------------------------------------------------------------------------
+    model, drops = run("synth", variables, 5, mel_targets=None, stop_token_targets=None, targets_lengths=None)
+    steps = int(model.tower_mel_outputs[0].shape[1])
+    masks_to_oracle("synth", drops, False, steps)
+    save_outputs("synth", model, True)
+    print("synth: %d decoder steps (max_iters %d), stop predictions %s" % (steps, rhp.max_iters,
+          np.round(out["synth_stop_token_prediction"][:, -1], 3)))
+    # a second synthesis in which the stop rule (not max_iters) ends the loop: the stop logits above fall with time, so the stop
+    # projection is negated (rising logits) and its bias shifted to put every row's crossing of 0.5 between step index 2 and 3
+    biased = dict(variables)
+    sk = [k for k in variables if "stop_token_projection/projection_stop_token_projection/" in k]
+    assert len(sk) == 2
+    neg = -torch.logit(torch.as_tensor(out["synth_stop_token_prediction"]).clamp(1e-6, 1 - 1e-6))          # [B, steps]
+    low = neg.min(0).values
+    assert float(low[3]) > float(low[:3].max())
+    shift = -0.5 * (float(low[3]) + float(low[:3].max()))
+    for k in sk:
+        biased[k] = -variables[k] + (shift if k.endswith("bias") else 0.0)
+    model, drops = run("synth_stop", biased, 5, mel_targets=None, stop_token_targets=None, targets_lengths=None)
+    steps2 = int(model.tower_mel_outputs[0].shape[1])
+    masks_to_oracle("synth_stop", drops, False, steps2)
+    save_outputs("synth_stop", model, True)
+    out["synth_stop_bias_shift"] = np.asarray(shift, dtype=np.float64)
+    print("synth_stop: %d decoder steps" % steps2)
+
+    path = os.path.join(HERE, "reference_graph.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -18,8 +18,8 @@ What is executed, and how honest each fixture is:
     available and are substituted by the oracle's restatements (cross-checked against torch.stft / torchaudio in
     tests/test_oracle_audio.py). These vectors pin the composition, not the primitives. The same holds for the inversion path
     (inv_linear_spectrogram / inv_mel_spectrogram / _griffin_lim with librosa.istft substituted).
-Layers built from tf.layers / tf.nn.rnn_cell / seq2seq (convolutions, LSTM cells, BahdanauAttention) are NOT executed: they
-remain restated from the TF documentation."""
+Layers built from tf.layers / tf.nn.rnn_cell / seq2seq (convolutions, LSTM cells, BahdanauAttention) are not executed HERE; the
+reference's whole Tacotron graph code runs in make_reference_graph_vectors.py on tf_shim_graph.py's stand-in for those classes."""
 import json
 import os
 import sys

@@ -56,6 +56,11 @@ class Dim(int):
     value = property(lambda self: int(self))
 
 
+class Shape(tuple):
+    def as_list(self):
+        return [int(d) for d in self]
+
+
 class T(torch.Tensor):
     """torch tensor that also answers the TF shape protocol (x.get_shape(), x.shape[-1].value)"""
 
@@ -64,7 +69,7 @@ class T(torch.Tensor):
         return torch.Tensor._make_subclass(cls, torch.as_tensor(data))
 
     def get_shape(self):
-        return tuple(Dim(d) for d in torch.Tensor.size(self))
+        return Shape(Dim(d) for d in torch.Tensor.size(self))
 
     shape = property(get_shape)
 
@@ -208,7 +213,7 @@ def install(extra_stubs=("librosa", "librosa.filters", "librosa.display", "libro
             if "." in name:
                 parent, child = name.rsplit(".", 1)
                 setattr(sys.modules[parent], child, sys.modules[name])
-    torch.Tensor.get_shape = lambda self: tuple(Dim(d) for d in self.size())   # TF static-shape protocol (this process only)
+    torch.Tensor.get_shape = lambda self: Shape(Dim(d) for d in self.size())   # TF static-shape protocol (this process only)
     if not hasattr(np, "int"):
         np.int = int          # removed in numpy 1.24; the reference (numpy 1.14) spells astype(np.int)
     return tf

@@ -1,0 +1,537 @@
+"""TEST INFRASTRUCTURE - the graph-building half of the TF-1 stand-in (tf_shim.py holds the elementary ops). With it the reference's
+own model files (tacotron/models/{tacotron,modules,attention,Architecture_wrappers,helpers,custom_decoder}.py) can be imported and
+`Tacotron.initialize()` / `add_loss()` EXECUTED eagerly on torch-CPU tensors: variable scopes with TensorFlow's naming and
+uniquification rules, tf.get_variable backed by a recording store, the tf.layers / tf.nn.rnn_cell / tf.contrib.seq2seq classes the
+reference composes (Dense, Conv1D, BatchNormalization, Dropout, MaxPooling1D, LSTMCell, GRUCell, MultiRNNCell, dynamic_rnn,
+BahdanauAttention, dynamic_decode, TensorArray).
+
+What this pins and what it does not: the LAYERS below restate the documented TF 1.x semantics - they are
+this repo's reading of TensorFlow, like the oracle's. What is the reference's own and gets executed unchanged is everything
+above the layers: which layers exist under which variable scope and name, their order, activation / batch-norm / dropout
+placement, the zoneout wrapper, the encoder / decoder cell wiring (prenet -> LSTM stack -> attention -> projections, input feeding,
+cumulative alignments), the helpers' teacher forcing and stop rule, the post-net, the CBHG block, the loss terms and the
+regularisation filter. Random draws (dropout / zoneout masks) are generated here from a seeded generator and RECORDED so that the
+oracle can be run with exactly the same masks.
+
+Used only by tests/golden/make_reference_graph_vectors.py."""
+import collections
+import contextlib
+import math
+import re
+import types
+
+import numpy as np
+import torch
+
+import tf_shim
+from tf_shim import T
+
+S = types.SimpleNamespace(scope=[""], opened={}, layer_uid={}, vars=collections.OrderedDict(), gen=None, drops=[], create=True)
+
+
+def reset(seed=0, variables=None):
+    """new graph: empty scope stack / name counters; `variables` (name -> tensor) are reused instead of created when given"""
+    S.scope[:] = [""]
+    S.opened.clear()
+    S.layer_uid.clear()
+    S.vars.clear()
+    S.drops[:] = []
+    S.gen = torch.Generator().manual_seed(seed)
+    S.create = variables is None
+    for k, v in (variables or {}).items():
+        S.vars[k] = _as_var(k, torch.as_tensor(v, dtype=torch.float32).clone())
+
+
+# ---- variable scopes -------------------------------------------------------------------------------------------------------------
+class VarScope(object):
+    def __init__(self, name):
+        self.name = name
+
+
+def _join(a, b):
+    return b if not a else a + "/" + b
+
+
+@contextlib.contextmanager
+def variable_scope(name_or_scope=None, default_name=None, values=None, reuse=None, **kw):
+    """tf.variable_scope: an explicit name nests under the current scope as is; a scope object re-enters that scope; with
+    name_or_scope=None the default_name is made unique among the scopes opened so far (variable_scope.py
+    _get_unique_variable_scope: prefix, prefix_1, prefix_2, ...)"""
+    cur = S.scope[-1]
+    if isinstance(name_or_scope, VarScope):
+        full = name_or_scope.name
+    elif name_or_scope is None:
+        base = _join(cur, default_name)
+        full, i = base, 0
+        while S.opened.get(full, 0) > 0:
+            i += 1
+            full = "%s_%d" % (base, i)
+    else:
+        full = _join(cur, name_or_scope)
+    S.opened[full] = S.opened.get(full, 0) + 1
+    S.scope.append(full)
+    try:
+        yield VarScope(full)
+    finally:
+        S.scope.pop()
+
+
+def loop_snapshot():
+    """A while_loop body is BUILT once in TensorFlow; run eagerly it is executed once per step. Restoring the name counters to their
+    value before the first iteration makes every iteration resolve the same scope / variable names."""
+    return dict(S.opened), dict(S.layer_uid)
+
+
+def loop_restore(snap):
+    S.opened.clear()
+    S.opened.update(snap[0])
+    S.layer_uid.clear()
+    S.layer_uid.update(snap[1])
+
+
+class V(T):
+    """a variable: a tensor that answers `.name` like tf.Variable ('<scope>/<name>:0')"""
+    name = property(lambda self: getattr(self, "var_name", "") + ":0")
+
+
+def _as_var(full, value):
+    v = V(value)
+    v.requires_grad_(not full.endswith(("moving_mean", "moving_variance")))
+    v.var_name = full
+    return v
+
+
+def _new_value(full, shape):
+    leaf = full.rsplit("/", 1)[1]
+    g = S.gen
+    shape = [int(s) for s in shape]
+    if leaf == "gamma":
+        return 1.0 + 0.2 * torch.randn(shape, generator=g)
+    if leaf == "moving_variance":
+        return 0.5 + torch.rand(shape, generator=g)
+    if leaf in ("beta", "bias", "moving_mean", "attention_bias"):
+        return 0.2 * torch.randn(shape, generator=g)
+    fan_in = int(np.prod(shape[:-1])) if len(shape) > 1 else 4
+    return torch.randn(shape, generator=g) / math.sqrt(fan_in)
+
+
+def get_variable(name, shape=None, dtype=torch.float32, initializer=None, trainable=True, **kw):
+    full = _join(S.scope[-1], name)
+    if full in S.vars:
+        v = S.vars[full]
+        assert shape is None or list(v.shape) == [int(s) for s in shape], (full, tuple(v.shape), shape)
+        return v
+    assert S.create, "variable %s is not in the injected set" % full
+    v = _as_var(full, _new_value(full, shape))
+    S.vars[full] = v
+    return v
+
+
+def trainable_variables():
+    return [v for v in S.vars.values() if v.requires_grad]
+
+
+# ---- random draws ----------------------------------------------------------------------------------------------------------------
+def _dropout(x, keep_prob, kind):
+    """tf.nn.dropout: x / keep_prob * floor(keep_prob + U[0, 1)); keep_prob == 1 returns x"""
+    keep_prob = float(keep_prob)
+    if keep_prob >= 1.0:
+        return x
+    mask = torch.floor(keep_prob + torch.rand(tuple(x.shape), generator=S.gen))
+    S.drops.append((S.scope[-1], kind, mask))
+    return x / keep_prob * mask
+
+
+# ---- layers ----------------------------------------------------------------------------------------------------------------------
+def _snake(name):
+    return re.sub(r"(?<=[a-z0-9])(?=[A-Z])|(?<=[A-Z])(?=[A-Z][a-z])", "_", name).lower().replace("conv1_d", "conv1d").replace("pooling1_d", "pooling1d")
+
+
+def _unique_layer_name(base):
+    key = (S.scope[-1], base)
+    n = S.layer_uid.get(key, 0)
+    S.layer_uid[key] = n + 1
+    return base if n == 0 else "%s_%d" % (base, n)
+
+
+class Layer(object):
+    """tf.layers.Layer naming: the variable scope is fixed at the first call - variable_scope(None, default_name=<name>) under the
+    scope current at that moment (functional layers with an explicit name: variable_scope(<name>), no uniquification)"""
+
+    def __init__(self, name=None, _scope=None, **kw):
+        self._name_arg, self._explicit_scope, self._scope = name, _scope, None
+        self._base_name = name or _snake(type(self).__name__)
+        self.built = False
+
+    def _enter(self):
+        if getattr(self, "_scope", None) is None:
+            if getattr(self, "_explicit_scope", None):
+                cm = variable_scope(self._explicit_scope)
+            else:
+                cm = variable_scope(None, default_name=getattr(self, "_name_arg", None) or _unique_layer_name(_snake(type(self).__name__)))
+            with cm as sc:
+                self._scope = sc
+        return variable_scope(self._scope)
+
+    def __call__(self, inputs, *args, **kwargs):
+        kwargs.pop("scope", None)
+        with self._enter():
+            return self.call(inputs, *args, **kwargs)
+
+
+def _act(fn, y):
+    return y if fn is None else fn(y)
+
+
+class Dense(Layer):
+    def __init__(self, units, activation=None, use_bias=True, name=None, **kw):
+        Layer.__init__(self, name=name, _scope=kw.get("_scope"))
+        self.units, self.activation, self.use_bias = int(units), activation, use_bias
+
+    def call(self, x):
+        y = x @ get_variable("kernel", [x.shape[-1], self.units])
+        if self.use_bias:
+            y = y + get_variable("bias", [self.units])
+        return _act(self.activation, y)
+
+
+class Conv1D(Layer):
+    """stride-1 cross-correlation over [batch, time, channels]; 'same' = kw - 1 zeros in total, the extra one of an even kernel on
+    the right (TF's SAME rule: pad_left = total // 2)"""
+
+    def __init__(self, filters, kernel_size, padding="valid", activation=None, use_bias=True, name=None, **kw):
+        Layer.__init__(self, name=name, _scope=kw.get("_scope"))
+        self.filters, self.kw, self.padding, self.activation, self.use_bias = int(filters), int(kernel_size), padding, activation, use_bias
+
+    def call(self, x):
+        k = get_variable("kernel", [self.kw, x.shape[-1], self.filters])
+        if self.padding == "same":
+            total = self.kw - 1
+            x = torch.cat([x.new_zeros(x.shape[0], total // 2, x.shape[2]), x, x.new_zeros(x.shape[0], total - total // 2, x.shape[2])], dim=1)
+        windows = x.unfold(1, self.kw, 1)                                   # [B, T, Cin, kw]
+        y = torch.einsum("btck,kcf->btf", windows, k)
+        if self.use_bias:
+            y = y + get_variable("bias", [self.filters])
+        return _act(self.activation, y)
+
+
+class BatchNormalization(Layer):
+    """tf.layers.batch_normalization defaults: axis -1, epsilon 1e-3; training: moments of the batch over every other axis (biased
+    variance); inference: the moving statistics. (The moving-average update ops live in UPDATE_OPS; they do not change the outputs.)"""
+
+    def call(self, x, training=False):
+        C = x.shape[-1]
+        gamma, beta = get_variable("gamma", [C]), get_variable("beta", [C])
+        mm, mv = get_variable("moving_mean", [C], trainable=False), get_variable("moving_variance", [C], trainable=False)
+        if training:
+            flat = x.reshape(-1, int(C))
+            mean = flat.mean(0)
+            var = ((flat - mean) ** 2).mean(0)
+        else:
+            mean, var = mm, mv
+        return (x - mean) * torch.rsqrt(var + 1e-3) * gamma + beta
+
+
+class MaxPooling1D(Layer):
+    pass
+
+
+def max_pooling1d(x, pool_size, strides, padding="valid", **kw):
+    assert strides == 1 and padding == "same"
+    total = int(pool_size) - 1
+    neg = x.new_full((x.shape[0], 1, x.shape[2]), -float("inf"))
+    xp = torch.cat([neg] * (total // 2) + [x] + [neg] * (total - total // 2), dim=1)
+    return xp.unfold(1, int(pool_size), 1).amax(-1)
+
+
+def layers_dropout(x, rate=0.5, training=False, name=None, **kw):
+    return _dropout(x, 1.0 - float(rate), "layers.dropout") if training else x
+
+
+LSTMStateTuple = collections.namedtuple("LSTMStateTuple", ("c", "h"))
+
+
+def map_structure(fn, *structs):
+    s0 = structs[0]
+    if isinstance(s0, tuple) and hasattr(s0, "_fields"):
+        return type(s0)(*[map_structure(fn, *[s[i] for s in structs]) for i in range(len(s0))])
+    if isinstance(s0, (tuple, list)):
+        return type(s0)(map_structure(fn, *[s[i] for s in structs]) for i in range(len(s0)))
+    return fn(*structs)
+
+
+def _zero_state_tensors(state_size, batch_size, dtype):
+    return map_structure(lambda n: T(torch.zeros(int(batch_size), int(n), dtype=dtype)), state_size)
+
+
+class RNNCell(Layer):
+    def __init__(self, *a, **kw):
+        Layer.__init__(self, name=kw.get("name"))
+
+    def zero_state(self, batch_size, dtype):
+        return _zero_state_tensors(self.state_size, batch_size, dtype)
+
+    def __call__(self, inputs, state, scope=None):
+        assert scope is None
+        return Layer.__call__(self, inputs, state)
+
+
+class LSTMCell(RNNCell):
+    """tf.nn.rnn_cell.LSTMCell without peepholes / projection: [x, h] W + b -> i, j, f, o; c' = c sigmoid(f + forget_bias) + sigmoid(i)
+    tanh(j); h' = tanh(c') sigmoid(o); forget_bias = 1"""
+
+    def __init__(self, num_units, state_is_tuple=True, name=None, **kw):
+        RNNCell.__init__(self, name=name)
+        self._num_units, self._num_proj = int(num_units), None
+        assert state_is_tuple
+
+    state_size = property(lambda self: LSTMStateTuple(self._num_units, self._num_units))
+    output_size = property(lambda self: self._num_units)
+
+    def call(self, x, state):
+        c, h = state
+        n = self._num_units
+        z = torch.cat([x, h], dim=1) @ get_variable("kernel", [x.shape[-1] + n, 4 * n]) + get_variable("bias", [4 * n])
+        i, j, f, o = z[:, :n], z[:, n:2 * n], z[:, 2 * n:3 * n], z[:, 3 * n:]
+        new_c = c * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
+        new_h = torch.tanh(new_c) * torch.sigmoid(o)
+        return new_h, LSTMStateTuple(new_c, new_h)
+
+
+class GRUCell(RNNCell):
+    """tf.nn.rnn_cell.GRUCell: [r, u] = sigmoid([x, h] W_gates + b_gates); c = tanh([x, r h] W_cand + b_cand); h' = u h + (1 - u) c"""
+
+    def __init__(self, num_units, name=None, **kw):
+        RNNCell.__init__(self, name=name)
+        self._num_units = int(num_units)
+
+    state_size = property(lambda self: self._num_units)
+    output_size = property(lambda self: self._num_units)
+
+    def call(self, x, h):
+        n = self._num_units
+        d = x.shape[-1] + n
+        g = torch.sigmoid(torch.cat([x, h], 1) @ get_variable("gates/kernel", [d, 2 * n]) + get_variable("gates/bias", [2 * n]))
+        r, u = g[:, :n], g[:, n:]
+        c = torch.tanh(torch.cat([x, r * h], 1) @ get_variable("candidate/kernel", [d, n]) + get_variable("candidate/bias", [n]))
+        new_h = u * h + (1 - u) * c
+        return new_h, new_h
+
+
+class MultiRNNCell(RNNCell):
+    def __init__(self, cells, state_is_tuple=True):
+        RNNCell.__init__(self)
+        self._cells = list(cells)
+        assert state_is_tuple
+
+    state_size = property(lambda self: tuple(c.state_size for c in self._cells))
+    output_size = property(lambda self: self._cells[-1].output_size)
+
+    def zero_state(self, batch_size, dtype):
+        return tuple(c.zero_state(batch_size, dtype) for c in self._cells)
+
+    def call(self, x, state):
+        new_states = []
+        for i, cell in enumerate(self._cells):
+            with variable_scope("cell_%d" % i):
+                x, ns = cell(x, state[i])
+            new_states.append(ns)
+        return x, tuple(new_states)
+
+
+def _reverse_sequence(x, lengths):
+    if lengths is None:
+        return x.flip(1)
+    out = x.clone()
+    for b in range(x.shape[0]):
+        n = int(lengths[b])
+        out[b, :n] = x[b, :n].flip(0)
+    return out
+
+
+def _dynamic_rnn(cell, x, lengths, scope):
+    """tf.nn.dynamic_rnn with sequence_length: past a row's length the output is zero and the state is copied through"""
+    with variable_scope(scope):
+        state = cell.zero_state(x.shape[0], torch.float32)
+        outs, snap = [], None
+        for t in range(int(x.shape[1])):
+            if snap is None:
+                snap = loop_snapshot()
+            else:
+                loop_restore(snap)
+            out, new_state = cell(x[:, t], state)
+            if lengths is not None:
+                live = (t < torch.as_tensor(lengths).reshape(-1)).unsqueeze(1)
+                out = torch.where(live, out, torch.zeros_like(out))
+                state = map_structure(lambda n, o: torch.where(live, n, o), new_state, state)
+            else:
+                state = new_state
+            outs.append(out)
+        return torch.stack(outs, dim=1), state
+
+
+def bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, dtype=None, swap_memory=False, scope=None, **kw):
+    with variable_scope(scope or "bidirectional_rnn"):
+        with variable_scope("fw") as fw_scope:
+            out_fw, st_fw = _dynamic_rnn(cell_fw, inputs, sequence_length, fw_scope)
+        with variable_scope("bw") as bw_scope:
+            rev = _reverse_sequence(inputs, sequence_length)
+            out_bw, st_bw = _dynamic_rnn(cell_bw, rev, sequence_length, bw_scope)
+            out_bw = _reverse_sequence(out_bw, sequence_length)
+    return (out_fw, out_bw), (st_fw, st_bw)
+
+
+# ---- seq2seq ---------------------------------------------------------------------------------------------------------------------
+class BahdanauAttention(object):
+    """tf.contrib.seq2seq.BahdanauAttention as far as the reference's subclass uses it (attention_wrapper.py _BaseAttentionMechanism):
+    memory masked by its lengths (_prepare_memory), keys = memory_layer(values) built right here, query_layer built at the first
+    step, probability_fn = softmax over scores whose padded positions are set to -inf (_maybe_mask_score)"""
+
+    def __init__(self, num_units, memory, memory_sequence_length=None, normalize=False, probability_fn=None, score_mask_value=None,
+                 dtype=None, name="BahdanauAttention"):
+        fn = probability_fn if probability_fn is not None else (lambda score: torch.softmax(score, dim=-1))
+        Tm = int(memory.shape[1])
+        if memory_sequence_length is not None:
+            seq_mask = torch.arange(Tm)[None, :] < torch.as_tensor(memory_sequence_length).reshape(-1, 1)
+            memory = memory * seq_mask.unsqueeze(-1).to(memory.dtype)
+            mask_value = -float("inf") if score_mask_value is None else score_mask_value
+            self._probability_fn = lambda score, prev: fn(torch.where(seq_mask, score, torch.full_like(score, mask_value)))
+        else:
+            self._probability_fn = lambda score, prev: fn(score)
+        self.query_layer = Dense(num_units, name="query_layer", use_bias=False)
+        self.memory_layer = Dense(num_units, name="memory_layer", use_bias=False)
+        self._values = memory
+        self._keys = self.memory_layer(memory)
+        self._batch_size, self._alignments_size = int(memory.shape[0]), Tm
+
+    values = property(lambda self: self._values)
+    keys = property(lambda self: self._keys)
+    batch_size = property(lambda self: self._batch_size)
+    alignments_size = property(lambda self: self._alignments_size)
+
+    def initial_alignments(self, batch_size, dtype):
+        return T(torch.zeros(int(batch_size), self._alignments_size, dtype=dtype))
+
+    initial_state = initial_alignments
+
+
+class TensorArray(object):
+    def __init__(self, dtype=None, size=0, dynamic_size=True, **kw):
+        self._items = []
+
+    def write(self, index, value):
+        assert int(index) == len(self._items)
+        new = TensorArray()
+        new._items = self._items + [value]
+        return new
+
+    def stack(self):
+        return torch.stack(self._items, dim=0)
+
+
+class Helper(object):
+    pass
+
+
+class Decoder(object):
+    pass
+
+
+def dynamic_decode(decoder, output_time_major=False, impute_finished=False, maximum_iterations=None, swap_memory=False, scope=None, **kw):
+    """tf.contrib.seq2seq.dynamic_decode (decoder.py): variable scope 'decoder'; loop while not all(finished); a step's `finished`
+    is OR-ed with the running flags and with time + 1 >= maximum_iterations; outputs are stacked over time and returned batch-major"""
+    assert not impute_finished and not output_time_major
+    with variable_scope(scope, default_name="decoder"):
+        finished, inputs, state = decoder.initialize()
+        finished = torch.as_tensor(finished).clone()
+        lengths = torch.zeros_like(finished, dtype=torch.int64)
+        time, steps, snap = 0, [], None
+        while not bool(finished.all()):
+            if snap is None:
+                snap = loop_snapshot()
+            else:
+                loop_restore(snap)
+            outputs, state, inputs, dec_finished = decoder.step(time, inputs, state)
+            nxt = torch.logical_or(torch.as_tensor(dec_finished), finished)
+            if maximum_iterations is not None:
+                nxt = torch.logical_or(nxt, torch.as_tensor(time + 1 >= int(maximum_iterations)))
+            lengths = torch.where(finished, lengths, torch.full_like(lengths, time + 1))
+            steps.append(outputs)
+            finished, time = nxt, time + 1
+        stacked = type(steps[0])(*[torch.stack([torch.as_tensor(s[i]) for s in steps], dim=1) for i in range(len(steps[0]))])
+    return stacked, state, lengths
+
+
+# ---- install ---------------------------------------------------------------------------------------------------------------------
+def install():
+    """tf_shim.install() + the graph-building surface; returns the `tensorflow` stand-in"""
+    tf = tf_shim.install()
+    wrap = lambda f: (lambda *a, **k: T(f(*a, **k)))
+    tf.variable_scope, tf.get_variable, tf.trainable_variables = variable_scope, get_variable, trainable_variables
+    tf.name_scope = lambda *a, **k: contextlib.nullcontext()
+    tf.device = lambda *a, **k: contextlib.nullcontext()
+    tf.train.replica_device_setter = lambda *a, **k: None
+    tf.constant_initializer = lambda *a, **k: None
+    tf.identity = lambda x, name=None: x
+    tf.zeros, tf.ones = wrap(tf.zeros), wrap(tf.ones)
+    tf.convert_to_tensor = lambda x, dtype=None, **k: T(torch.as_tensor(x, dtype=dtype))
+    tf.tile = lambda x, multiples: T(torch.as_tensor(x).repeat(*[int(m) for m in multiples]))
+    tf.less = lambda a, b: torch.as_tensor(a) < torch.as_tensor(b)
+    tf.logical_or = torch.logical_or
+    tf.reduce_all = lambda x, axis=None, **k: torch.as_tensor(x).all() if axis is None else torch.as_tensor(x).all(dim=int(axis))
+    tf.reduce_any = lambda x, axis=None, **k: torch.as_tensor(x).any() if axis is None else torch.as_tensor(x).any(dim=int(axis))
+    tf.split = lambda value, num_or_size_splits, axis=0, **k: list(torch.chunk(value, int(num_or_size_splits), dim=int(axis)))
+    tf.add_n = lambda xs: sum(xs[1:], xs[0])
+    tf.matmul = torch.matmul
+    base_uniform = tf.random_uniform
+
+    def random_uniform(shape, minval=0.0, maxval=1.0, dtype=torch.float32, **k):
+        if tf_shim._uniform_queue:
+            return base_uniform(shape, minval, maxval, dtype)
+        return T(minval + (maxval - minval) * torch.rand([int(s) for s in shape], generator=S.gen))
+    tf.random_uniform = random_uniform
+
+    def py_func(func, inp, Tout, **k):
+        out = func(*[np.asarray(torch.as_tensor(x).detach().cpu().numpy()) for x in inp])
+        return [T(torch.as_tensor(np.ascontiguousarray(o))) for o in out]
+    tf.py_func = py_func
+
+    nn = tf.nn
+    nn.embedding_lookup = lambda table, ids, **k: table[torch.as_tensor(ids).long()]
+    nn.l2_loss = lambda v: (v * v).sum() / 2
+    nn.dropout = lambda x, keep_prob, **k: _dropout(x, keep_prob, "nn.dropout")
+    nn.bidirectional_dynamic_rnn = bidirectional_dynamic_rnn
+    cells = nn.rnn_cell
+    cells.RNNCell, cells.LSTMCell, cells.GRUCell, cells.LSTMStateTuple, cells.MultiRNNCell = RNNCell, LSTMCell, GRUCell, LSTMStateTuple, MultiRNNCell
+    tf.contrib.rnn.RNNCell, tf.contrib.rnn.MultiRNNCell, tf.contrib.rnn.LSTMStateTuple = RNNCell, MultiRNNCell, LSTMStateTuple
+
+    L = tf.layers
+    L.Layer, L.Dense, L.Conv1D = Layer, Dense, Conv1D
+    L.dense = lambda inputs, units, activation=None, use_bias=True, name=None, **k: Dense(units, activation, use_bias, name=name, _scope=name)(inputs)
+    L.conv1d = lambda inputs, filters, kernel_size, padding="valid", activation=None, use_bias=True, name=None, **k: Conv1D(
+        filters, kernel_size, padding, activation, use_bias, name=name, _scope=name)(inputs)
+    L.batch_normalization = lambda inputs, training=False, name=None, **k: BatchNormalization(name=name, _scope=name)(inputs, training=training)
+    L.dropout = layers_dropout
+    L.max_pooling1d = max_pooling1d
+
+    s2s = tf.contrib.seq2seq
+    s2s.dynamic_decode, s2s.Helper, s2s.BahdanauAttention = dynamic_decode, Helper, BahdanauAttention
+    s2s.python.ops.attention_wrapper.BahdanauAttention = BahdanauAttention
+    s2s.python.ops.helper.Helper = Helper
+    s2s.python.ops.decoder.Decoder = Decoder
+
+    py = tf.python
+    py.layers.base.Layer = Layer
+    ao = py.ops.array_ops
+    ao.expand_dims, ao.squeeze, ao.concat, ao.shape, ao.identity = tf.expand_dims, tf.squeeze, tf.concat, tf.shape, tf.identity
+    ao.zeros = tf.zeros
+    py.ops.math_ops.matmul = torch.matmul
+    py.ops.variable_scope.variable_scope = variable_scope
+    py.ops.check_ops.assert_equal = lambda *a, **k: None
+    py.ops.rnn_cell_impl._zero_state_tensors = _zero_state_tensors
+    py.ops.rnn_cell_impl.assert_like_rnncell = lambda *a, **k: None
+    py.ops.tensor_array_ops.TensorArray = TensorArray
+    py.framework.ops.name_scope = lambda *a, **k: contextlib.nullcontext()
+    py.framework.ops.control_dependencies = lambda *a, **k: contextlib.nullcontext()
+    py.util.nest.map_structure = map_structure
+    return tf

@@ -1,0 +1,180 @@
+"""The oracle against the reference's OWN Tacotron graph code, executed: tests/golden/reference_graph.npz holds what
+`Tacotron.initialize()` + `add_loss()` of /root/reference/tacotron/models/tacotron.py produce when they run (with modules.py,
+attention.py, Architecture_wrappers.py, helpers.py, custom_decoder.py underneath) on the TF-1 stand-in of tests/golden/tf_shim*.py
+(make_reference_graph_vectors.py; the layer primitives there restate TF 1.x, the composition above them is the reference's).
+Checked here, on CPU:
+  * the variable names / shapes the reference's scopes produce == t2_tf_bundle.tacotron_tf_name over the engine's parameter table
+    (the TF-checkpoint name map), and the regularisation filter picks the same variables;
+  * oracle.forward / loss_fn / synthesize / linear_head reproduce the executed reference in training (all dropout / zoneout masks
+    injected), masked-loss training, evaluation, GTA and free-running synthesis (stop rule and max_iters);
+  * d loss / d variable through the oracle == autograd through the executed reference graph, for every trainable variable."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import t2_tf_bundle
+from hparams import hparams
+from oracle import tacotron as ot
+
+PATH = os.path.join(os.path.dirname(__file__), "golden", "reference_graph.npz")
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def R():
+    return np.load(PATH)
+
+
+def _hp(R, **kw):
+    hp = hparams.copy()
+    for k, v in zip(R["small_hparams_keys"], R["small_hparams_values"]):
+        setattr(hp, str(k), eval(str(v)))
+    for k, v in kw.items():
+        setattr(hp, k, v)
+    return hp
+
+
+def _params(R, drop=()):
+    """fixture variables (reference scope names) -> the oracle's parameter dict, through the checkpoint name map"""
+    out = {}
+    for name in R["var_names"]:
+        eng = t2_tf_bundle.engine_name("Tacotron_model/" + str(name))
+        assert eng is not None, name
+        if not any(d in eng for d in drop):
+            out[eng] = torch.from_numpy(R["var/" + str(name)]).clone()
+    return out
+
+
+def _inputs(R):
+    t = lambda k, dt=None: torch.from_numpy(R[k]).to(dt) if dt else torch.from_numpy(R[k])
+    return (t("inputs", torch.int64), t("input_lengths", torch.int64), t("mel_targets"), t("stop_targets"), t("linear_targets"),
+            t("targets_lengths", torch.int64))
+
+
+def _masks(R, tag, training, hp):
+    m = {"prenet_drop": [torch.from_numpy(R["%s_mask_prenet_drop_%d" % (tag, i)]) for i in range(len(hp.prenet_layers))]}
+    if training:
+        for i in range(hp.enc_conv_num_layers):
+            m[("enc_drop", i)] = torch.from_numpy(R["%s_mask_enc_drop_%d" % (tag, i)])
+        for i in range(hp.postnet_num_layers):
+            m[("post_drop", i)] = torch.from_numpy(R["%s_mask_post_drop_%d" % (tag, i)])
+        ez, dz = {}, {}
+        for d in ("fw", "bw"):
+            for s in "ch":
+                a = torch.from_numpy(R["%s_mask_enc_zone_%s_%s" % (tag, d, s)])
+                for t in range(a.shape[0]):
+                    ez[(d, s, t)] = a[t]
+        for l in (1, 2):
+            for s in "ch":
+                a = torch.from_numpy(R["%s_mask_dec_zone_%d_%s" % (tag, l, s)])
+                for t in range(a.shape[0]):
+                    dz[(l, s, t)] = a[t]
+        m["enc_zone"], m["dec_zone"] = ez, dz
+    return m
+
+
+def _close(a, b, tol=TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a - b).max() if a.size else 0.0
+    assert err <= tol * max(1.0, np.abs(b).max()), err
+    return err
+
+
+def _check_outputs(R, tag, out, stop_is_logit):
+    _close(out["decoder_output"].detach(), R[tag + "_decoder_output"])
+    _close(out["mel_outputs"].detach(), R[tag + "_mel_outputs"])
+    _close(out["alignments"].detach().transpose(1, 2), R[tag + "_alignments"])                 # reference layout [B, T_in, T_out]
+    _close(out["stop_logits" if stop_is_logit else "stop_token_prediction"].detach(), R[tag + "_stop_token_prediction"])
+
+
+def test_variable_names_of_the_executed_reference_graph_match_the_checkpoint_name_map(R):
+    hp = _hp(R, predict_linear=True)
+    got = {"Tacotron_model/" + str(n): tuple(R["var/" + str(n)].shape) for n in R["var_names"]}
+    want = {t2_tf_bundle.tacotron_tf_name(k): tuple(v) for k, v in ot.param_shapes(hp).items()}
+    assert set(got) == set(want), (sorted(set(got) - set(want))[:5], sorted(set(want) - set(got))[:5])
+    assert got == want
+    # trainable flags and the regularisation filter (tacotron.py:343-345 runs on the TF names, the oracle's on the engine names)
+    for n, tr in zip(R["var_names"], R["var_trainable"]):
+        tf_name = "Tacotron_model/" + str(n)
+        eng = t2_tf_bundle.engine_name(tf_name)
+        assert ot.is_trainable(eng) == bool(tr)
+        ref_reg = bool(tr) and not any(s in tf_name for s in ("bias", "Bias", "_projection", "inputs_embedding", "RNN", "LSTM"))
+        assert ot.is_regularized(eng) == ref_reg, tf_name
+
+
+def test_training_graph_outputs_losses_and_gradients(R):
+    hp = _hp(R, predict_linear=True, mask_decoder=False)
+    params = {k: v.requires_grad_(ot.is_trainable(k)) for k, v in _params(R).items()}
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    out = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train", True, hp))
+    _check_outputs(R, "train", out, True)
+    _close(out["linear_outputs"].detach(), R["train_linear_outputs"])
+    total, parts = ot.loss_fn(out, mel, stop, params, hp, tgt_len, lin)
+    for k, ref in (("before", "before_loss"), ("after", "after_loss"), ("stop", "stop_token_loss"), ("reg", "regularization_loss"),
+                   ("linear", "linear_loss")):
+        assert abs(float(parts[k].detach()) - float(R["train_" + ref])) <= 1e-5 * max(1e-3, abs(float(R["train_" + ref]))), k
+    assert abs(float(total.detach()) - float(R["train_loss"])) <= 1e-5 * abs(float(R["train_loss"]))
+    total.backward()
+    worst = 0.0
+    # a conv bias in front of a training-mode batch norm has an exactly-zero gradient (rounding noise on both sides): errors are
+    # measured against max(|reference gradient|, 1e-3 x the largest gradient entry of the whole model)
+    floor = 1e-3 * max(np.abs(R[k]).max() for k in R.files if k.startswith("grad/"))
+    for name in R["var_names"]:
+        eng = t2_tf_bundle.engine_name("Tacotron_model/" + str(name))
+        if not ot.is_trainable(eng):
+            continue
+        ref = R["grad/" + str(name)]
+        g = params[eng].grad
+        g = np.zeros_like(ref) if g is None else g.numpy()
+        scale = max(np.abs(ref).max(), floor)
+        err = np.abs(g - ref).max() / scale
+        worst = max(worst, err)
+        assert err <= 2e-4, (eng, err)
+    assert worst > 0.0
+
+
+def test_training_graph_with_masked_losses(R):
+    hp = _hp(R, predict_linear=False, mask_decoder=True)
+    params = _params(R, drop=("CBHG", "cbhg"))
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    out = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train_md", True, hp))
+    _check_outputs(R, "train_md", out, True)
+    total, parts = ot.loss_fn(out, mel, stop, params, hp, tgt_len)
+    for k, ref in (("before", "before_loss"), ("after", "after_loss"), ("stop", "stop_token_loss"), ("reg", "regularization_loss")):
+        assert abs(float(parts[k]) - float(R["train_md_" + ref])) <= 1e-5 * max(1e-3, abs(float(R["train_md_" + ref]))), k
+    assert abs(float(total) - float(R["train_md_loss"])) <= 1e-5 * abs(float(R["train_md_loss"]))
+    assert float(R["train_md_linear_loss"]) == 0.0
+
+
+def test_evaluation_and_gta_graphs(R):
+    hp = _hp(R, predict_linear=True, mask_decoder=False)
+    params = _params(R)
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    out = ot.forward(params, ids, in_len, mel, hp, training=False, masks=_masks(R, "eval", False, hp))
+    _check_outputs(R, "eval", out, True)                                   # evaluation keeps the stop LOGITS (modules.py:340-341)
+    _close(out["linear_outputs"], R["eval_linear_outputs"])
+    total, parts = ot.loss_fn(out, mel, stop, params, hp, tgt_len, lin)
+    assert abs(float(total) - float(R["eval_loss"])) <= 1e-5 * abs(float(R["eval_loss"]))
+    out = ot.forward(params, ids, in_len, mel, hp, training=False, masks=_masks(R, "gta", False, hp))
+    out["stop_token_prediction"] = torch.sigmoid(out["stop_logits"])      # GTA is a synthesis mode: sigmoid applied
+    _check_outputs(R, "gta", out, False)
+
+
+@pytest.mark.parametrize("tag", ["synth", "synth_stop"])
+def test_free_running_synthesis_and_stop_rule(R, tag):
+    hp = _hp(R, predict_linear=True)
+    params = _params(R)
+    if tag == "synth_stop":                       # the generator negated the stop projection and shifted its bias (see its comments)
+        params["stop_token_projection/kernel"] = -params["stop_token_projection/kernel"]
+        params["stop_token_projection/bias"] = -params["stop_token_projection/bias"] + float(R["synth_stop_bias_shift"])
+    ids, in_len = _inputs(R)[:2]
+    pm = [torch.from_numpy(R["%s_mask_prenet_drop_%d" % (tag, i)]) for i in range(len(hp.prenet_layers))]
+    steps = pm[0].shape[1]
+    assert steps == (hp.max_iters if tag == "synth" else 4)
+    out = ot.synthesize(params, ids, in_len, hp, prenet_masks=[[m[:, t] for m in pm] for t in range(steps)] + [None] * 4)
+    assert out["mel_outputs"].shape[1] == steps                            # same number of decoder steps as the executed reference
+    _check_outputs(R, tag, out, False)
+    _close(ot.linear_head(out["mel_outputs"], params, hp, False), R[tag + "_linear_outputs"])
