@@ -11,14 +11,26 @@ Follows, function by function:
 Parameters are kept in the reference's TensorFlow variable layouts (conv kernels [kw, in, out]) under the names of
 SURVEY.md Appendix B so that a parameter dict is interchangeable with the CUDA model (tacotron-2_b200/wavenet.py).
 
-PINNING. Pinned by EXECUTING the reference's own source on a TF-1 shim of elementary ops (tests/golden/make_reference_vectors.py,
-tests/test_reference_pinned.py): discretized_mix_logistic_loss / sample_from_discretized_mix_logistic (mixture.py), the Gaussian
-loss and sampler (gaussian.py), MaskedCrossEntropyLoss / DiscretizedMixtureLogisticLoss / GaussianMaximumLikelihoodEstimation with
-their masks and normalisers (modules.py:781-852, wavenet.py:476-519), the learning-rate schedules (wavenet.py:615-633), the mu-law
-tensor path. PARITY UNPINNED for the layers built from tf.layers (left-padded VALID dilated cross-correlation, Conv2D /
-Conv2DTranspose 'same' arithmetic, glorot init) and tf.train (Adam, EMA): restated from the public TF 1.x definitions (SURVEY.md
-Appendix A) and checked through known answers: receptive_field_size, incremental == parallel forward under teacher forcing, NN_init ==
-nearest-neighbour repeat, mulaw_quantize(0) == 127 (tests/test_oracle_wavenet.py).
+PINNING, two levels.
+(1) Elementary-op code (tests/golden/make_reference_vectors.py, tests/test_reference_pinned.py): discretized_mix_logistic_loss /
+sample_from_discretized_mix_logistic (mixture.py), the Gaussian loss and sampler (gaussian.py), MaskedCrossEntropyLoss /
+DiscretizedMixtureLogisticLoss / GaussianMaximumLikelihoodEstimation with their masks and normalisers (modules.py:781-852,
+wavenet.py:476-519), the learning-rate schedules (wavenet.py:615-633), the mu-law tensor path - the reference's source runs AS IS.
+(2) The whole graph (tests/golden/make_reference_wavenet_graph_vectors.py, tests/test_reference_wavenet_graph.py): the reference's
+`WaveNet.__init__` / `initialize` / `step` / `incremental` / `add_loss` are EXECUTED - wavenet.py and modules.py (CausalConv1D,
+Conv1D1x1, ResidualConv1DGLU, SubPixelConvolution, ConvTranspose2D, NearestNeighborUpsample) unchanged - on a stand-in for
+tf.layers.Conv1D / Conv2D / Conv2DTranspose and the keras Wrapper they are built from (tests/golden/tf_shim_graph.py): the training
+graph in three configurations (mu-law CE + SubPixel, MoL + ConvTranspose2D, Gaussian + NearestNeighbor; dropout masks recorded and
+injected), the evaluation branch (teacher-forced incremental pass through the convolution queues + eval loss) and the free-running
+synthesis branch (every categorical / mixture / logistic draw recorded and injected). step / upsample / loss_fn / incremental
+reproduce the executed reference: outputs <= 2e-5, losses 1e-5, d loss / d variable 2e-4 relative for every variable, the sampled
+waveforms sample by sample; incremental == parallel forward on the same inputs; the variable names the reference's scopes generate
+equal t2_tf_bundle.wavenet_tf_name over the parameter table; the NN_init kernels its `_init_kernel` methods produce equal
+_upsample_init_kernel here and the product initialiser.
+STILL A RESTATEMENT: the convolution primitives under that composition (VALID / SAME cross-correlation with dilation, Conv2DTranspose
+'same' arithmetic) and tf.train (Adam, EMA, glorot init) follow the public TF 1.x definitions in the stand-in
+as in this file; TensorFlow itself cannot run here. Known answers on top: receptive_field_size, mulaw_quantize(0) == 127
+(tests/test_oracle_wavenet.py).
 """
 import math
 

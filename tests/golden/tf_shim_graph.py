@@ -13,7 +13,11 @@ cumulative alignments), the helpers' teacher forcing and stop rule, the post-net
 regularisation filter. Random draws (dropout / zoneout masks) are generated here from a seeded generator and RECORDED so that the
 oracle can be run with exactly the same masks.
 
-Used only by tests/golden/make_reference_graph_vectors.py."""
+The WaveNet side (wavenet_vocoder/models/{wavenet,modules,mixture,gaussian}.py) runs on the same stand-in: tf.layers.Conv1D / Conv2D /
+Conv2DTranspose with build() / call() / data_format / dilation_rate as the reference's keras wrappers use them, tf.keras.layers.Wrapper,
+tf.while_loop, tf.TensorArray, tf.multinomial (inverse CDF, draw recorded), tf.pad, tf.batch_to_space_nd, tf.image.resize_images.
+
+Used only by tests/golden/make_reference_graph_vectors.py and make_reference_wavenet_graph_vectors.py."""
 import collections
 import contextlib
 import math
@@ -26,7 +30,7 @@ import torch
 import tf_shim
 from tf_shim import T
 
-S = types.SimpleNamespace(scope=[""], opened={}, layer_uid={}, vars=collections.OrderedDict(), gen=None, drops=[], create=True)
+S = types.SimpleNamespace(scope=[""], opened={}, layer_uid={}, vars=collections.OrderedDict(), gen=None, drops=[], create=True, inits={}, uniforms=[])
 
 
 def reset(seed=0, variables=None):
@@ -36,6 +40,8 @@ def reset(seed=0, variables=None):
     S.layer_uid.clear()
     S.vars.clear()
     S.drops[:] = []
+    S.inits.clear()
+    S.uniforms[:] = []
     S.gen = torch.Generator().manual_seed(seed)
     S.create = variables is None
     for k, v in (variables or {}).items():
@@ -121,6 +127,10 @@ def get_variable(name, shape=None, dtype=torch.float32, initializer=None, traina
         v = S.vars[full]
         assert shape is None or list(v.shape) == [int(s) for s in shape], (full, tuple(v.shape), shape)
         return v
+    if isinstance(getattr(initializer, "value", None), np.ndarray) and initializer.value.ndim >= 2:
+        S.inits[full] = np.array(initializer.value)      # NN_init kernels (modules.py:642-654,761-770): kept for a known-answer test
+    if full in S.vars:
+        return S.vars[full]
     assert S.create, "variable %s is not in the injected set" % full
     v = _as_var(full, _new_value(full, shape))
     S.vars[full] = v
@@ -175,8 +185,27 @@ class Layer(object):
 
     def __call__(self, inputs, *args, **kwargs):
         kwargs.pop("scope", None)
+        if hasattr(self, "build") and not getattr(self, "built", False):
+            self.build(inputs.shape)
         with self._enter():
             return self.call(inputs, *args, **kwargs)
+
+
+def _tuple(v, n):
+    return tuple(int(x) for x in v) if isinstance(v, (tuple, list)) else (int(v),) * n
+
+
+class TensorShape(list):
+    def __init__(self, dims=()):
+        list.__init__(self, [None if d is None else int(d) for d in dims])
+
+    def as_list(self):
+        return list(self)
+
+
+class ConstantInitializer(object):
+    def __init__(self, value=0, dtype=None, **kw):
+        self.value = value
 
 
 def _act(fn, y):
@@ -195,24 +224,122 @@ class Dense(Layer):
         return _act(self.activation, y)
 
 
-class Conv1D(Layer):
-    """stride-1 cross-correlation over [batch, time, channels]; 'same' = kw - 1 zeros in total, the extra one of an even kernel on
-    the right (TF's SAME rule: pad_left = total // 2)"""
+class _Conv(Layer):
+    """tf.layers.Conv1D / Conv2D / Conv2DTranspose constructor surface; variables are made in build() (kernel, then bias) under the
+    layer's scope - also when build() is called directly (the reference's keras wrappers do that: add_weight sets the scope)"""
+    rank = 1
 
-    def __init__(self, filters, kernel_size, padding="valid", activation=None, use_bias=True, name=None, **kw):
+    def __init__(self, filters, kernel_size, strides=1, padding="valid", data_format="channels_last", dilation_rate=1, activation=None,
+                 use_bias=True, kernel_initializer=None, bias_initializer=None, name=None, **kw):
         Layer.__init__(self, name=name, _scope=kw.get("_scope"))
-        self.filters, self.kw, self.padding, self.activation, self.use_bias = int(filters), int(kernel_size), padding, activation, use_bias
+        self.filters, self.kernel_size, self.strides = int(filters), _tuple(kernel_size, self.rank), _tuple(strides, self.rank)
+        self.padding, self.data_format, self.dilation_rate = padding.lower(), data_format, _tuple(dilation_rate, self.rank)
+        self.activation, self.use_bias, self.kernel_initializer = activation, use_bias, kernel_initializer
+        self.kernel = self.bias = None
+
+    def _cin(self, input_shape):
+        return int(input_shape[1] if self.data_format == "channels_first" else input_shape[-1])
+
+    def _kernel_shape(self, cin):
+        return list(self.kernel_size) + [cin, self.filters]
+
+    def build(self, input_shape):
+        with self._enter():
+            self.kernel = get_variable("kernel", self._kernel_shape(self._cin(input_shape)), initializer=self.kernel_initializer)
+            self.bias = get_variable("bias", [self.filters]) if self.use_bias else None
+        self.built = True
+
+    def _finish(self, y, channel_axis):
+        if self.use_bias:
+            shape = [1] * y.dim()
+            shape[channel_axis] = self.filters
+            y = y + self.bias.reshape(shape)
+        return _act(self.activation, y)
+
+
+def _same_pad(x, axis, kernel_extent):
+    """TF SAME for stride 1: extent - 1 zeros in total, total // 2 of them in front"""
+    total = kernel_extent - 1
+    if total <= 0:
+        return x
+    shape = list(x.shape)
+    shape[axis] = total // 2
+    front = x.new_zeros(shape)
+    shape[axis] = total - total // 2
+    return torch.cat([front, x, x.new_zeros(shape)], dim=axis)
+
+
+class Conv1D(_Conv):
+    """cross-correlation over time with dilation; 'valid' or 'same'; channels_last [B, T, C] or channels_first [B, C, T]"""
+    rank = 1
 
     def call(self, x):
-        k = get_variable("kernel", [self.kw, x.shape[-1], self.filters])
+        assert self.strides == (1,)
+        if self.data_format == "channels_first":
+            x = x.transpose(1, 2)
+        kw, d = self.kernel_size[0], self.dilation_rate[0]
+        extent = (kw - 1) * d + 1
         if self.padding == "same":
-            total = self.kw - 1
-            x = torch.cat([x.new_zeros(x.shape[0], total // 2, x.shape[2]), x, x.new_zeros(x.shape[0], total - total // 2, x.shape[2])], dim=1)
-        windows = x.unfold(1, self.kw, 1)                                   # [B, T, Cin, kw]
-        y = torch.einsum("btck,kcf->btf", windows, k)
-        if self.use_bias:
-            y = y + get_variable("bias", [self.filters])
-        return _act(self.activation, y)
+            x = _same_pad(x, 1, extent)
+        windows = x.unfold(1, extent, 1)[..., ::d]                           # [B, T', Cin, kw]
+        y = torch.einsum("btck,kcf->btf", windows, self.kernel)
+        if self.data_format == "channels_first":
+            return self._finish(y.transpose(1, 2), 1)
+        return self._finish(y, -1)
+
+
+class Conv2D(_Conv):
+    """stride-1 cross-correlation, channels_last [B, H, W, C], kernel [kh, kw, in, out]"""
+    rank = 2
+
+    def call(self, x):
+        assert self.strides == (1, 1) and self.dilation_rate == (1, 1) and self.data_format == "channels_last"
+        kh, kw = self.kernel_size
+        if self.padding == "same":
+            x = _same_pad(_same_pad(x, 1, kh), 2, kw)
+        windows = x.unfold(1, kh, 1).unfold(2, kw, 1)                        # [B, H', W', Cin, kh, kw]
+        return self._finish(torch.einsum("bhwcij,ijcf->bhwf", windows, self.kernel), -1)
+
+
+class Conv2DTranspose(_Conv):
+    """tf.layers.Conv2DTranspose, channels_first [B, C, H, W], kernel [kh, kw, out, in]: the gradient of a strided SAME convolution -
+    input pixel (y, x) adds x * kernel[i, j] at output (y sy + i - pad_top, x sx + j - pad_left); with 'same' the output is
+    [H sy, W sx] and pad = max(k - s, 0) // 2 per axis"""
+    rank = 2
+
+    def _kernel_shape(self, cin):
+        return list(self.kernel_size) + [self.filters, cin]
+
+    def call(self, x):
+        assert self.data_format == "channels_first" and self.padding == "same" and self.dilation_rate == (1, 1)
+        B, C, H, W = [int(v) for v in x.shape]
+        (kh, kw), (sy, sx) = self.kernel_size, self.strides
+        full = x.new_zeros(B, self.filters, (H - 1) * sy + kh, (W - 1) * sx + kw)
+        for i in range(kh):
+            for j in range(kw):
+                contrib = torch.einsum("bchw,oc->bohw", x, self.kernel[i, j])
+                full[:, :, i:i + (H - 1) * sy + 1:sy, j:j + (W - 1) * sx + 1:sx] += contrib
+        top, left = max(kh - sy, 0) // 2, max(kw - sx, 0) // 2
+        return self._finish(full[:, :, top:top + H * sy, left:left + W * sx], 1)
+
+
+class Wrapper(object):
+    """tf.keras.layers.Wrapper: holds `layer`; __call__ builds once (with the input's shape) and then calls `call`. keras' base
+    Layer.__call__ opens a NAME scope only, so nothing here touches the variable scopes."""
+
+    def __init__(self, layer, name=None, **kw):
+        self.layer, self._name, self.built = layer, name, False
+
+    def build(self, input_shape=None):
+        self.built = True
+
+    def _track_checkpointable(self, *a, **kw):
+        pass
+
+    def __call__(self, inputs, *args, **kwargs):
+        if not self.built:
+            self.build(inputs.shape)
+        return self.call(inputs, *args, **kwargs)
 
 
 class BatchNormalization(Layer):
@@ -471,7 +598,6 @@ def install():
     tf.name_scope = lambda *a, **k: contextlib.nullcontext()
     tf.device = lambda *a, **k: contextlib.nullcontext()
     tf.train.replica_device_setter = lambda *a, **k: None
-    tf.constant_initializer = lambda *a, **k: None
     tf.identity = lambda x, name=None: x
     tf.zeros, tf.ones = wrap(tf.zeros), wrap(tf.ones)
     tf.convert_to_tensor = lambda x, dtype=None, **k: T(torch.as_tensor(x, dtype=dtype))
@@ -488,8 +614,38 @@ def install():
     def random_uniform(shape, minval=0.0, maxval=1.0, dtype=torch.float32, **k):
         if tf_shim._uniform_queue:
             return base_uniform(shape, minval, maxval, dtype)
-        return T(minval + (maxval - minval) * torch.rand([int(s) for s in shape], generator=S.gen))
+        u = T(minval + (maxval - minval) * torch.rand([int(s) for s in shape], generator=S.gen))
+        S.uniforms.append(("random_uniform", u))
+        return u
     tf.random_uniform = random_uniform
+
+    def multinomial(logits, num_samples, **k):
+        """one categorical draw per row by inverse CDF over softmax(logits) - tf.multinomial takes LOGITS; the uniform is recorded"""
+        assert int(num_samples) == 1
+        u = torch.rand(int(logits.shape[0]), 1, generator=S.gen)
+        S.uniforms.append(("multinomial", u))
+        cdf = torch.cumsum(torch.softmax(logits, dim=-1), dim=-1)
+        return (cdf < u).sum(-1, keepdim=True).clamp(max=int(logits.shape[-1]) - 1)
+    tf.multinomial = multinomial
+    tf.Print = lambda x, data=None, **k: x
+    tf.TensorArray = TensorArray
+    tf.one_hot = lambda indices, depth, dtype=torch.float32, **k: torch.nn.functional.one_hot(torch.as_tensor(indices).long(), int(depth)).to(dtype)
+
+    def while_loop(cond, body, loop_vars, **k):
+        state, snap = list(loop_vars), None
+        while bool(torch.as_tensor(cond(*state))):
+            if snap is None:
+                snap = loop_snapshot()
+            else:
+                loop_restore(snap)
+            state = list(body(*state))
+        return state
+    tf.while_loop = while_loop
+    base_reduce_max = tf.reduce_max
+    tf.reduce_max = lambda x, *a, **k: base_reduce_max(x if isinstance(x, torch.Tensor) else torch.as_tensor([int(v) for v in x]), *a, **k)
+    base_sequence_mask = tf.sequence_mask
+    tf.sequence_mask = lambda lengths, maxlen=None, dtype=torch.bool, **k: base_sequence_mask(
+        lengths if isinstance(lengths, torch.Tensor) else torch.as_tensor([int(v) for v in lengths]), maxlen, dtype)
 
     def py_func(func, inp, Tout, **k):
         out = func(*[np.asarray(torch.as_tensor(x).detach().cpu().numpy()) for x in inp])
@@ -497,6 +653,17 @@ def install():
     tf.py_func = py_func
 
     nn = tf.nn
+    nn.relu = lambda x, name=None: torch.relu(x)
+    nn.leaky_relu = lambda x, alpha=0.2, name=None: torch.where(x >= 0, x, alpha * x)
+    nn.bias_add = lambda x, b, **k: x + b
+    base_normal = tf.contrib.distributions.Normal
+
+    class Normal(base_normal):
+        def sample(self):
+            if tf_shim._normal_queue:
+                return base_normal.sample(self)
+            return self.loc + self.scale * torch.randn(tuple(self.loc.shape), generator=S.gen)
+    tf.contrib.distributions.Normal = Normal
     nn.embedding_lookup = lambda table, ids, **k: table[torch.as_tensor(ids).long()]
     nn.l2_loss = lambda v: (v * v).sum() / 2
     nn.dropout = lambda x, keep_prob, **k: _dropout(x, keep_prob, "nn.dropout")
@@ -509,7 +676,43 @@ def install():
     L.Layer, L.Dense, L.Conv1D = Layer, Dense, Conv1D
     L.dense = lambda inputs, units, activation=None, use_bias=True, name=None, **k: Dense(units, activation, use_bias, name=name, _scope=name)(inputs)
     L.conv1d = lambda inputs, filters, kernel_size, padding="valid", activation=None, use_bias=True, name=None, **k: Conv1D(
-        filters, kernel_size, padding, activation, use_bias, name=name, _scope=name)(inputs)
+        filters, kernel_size, padding=padding, activation=activation, use_bias=use_bias, name=name, _scope=name)(inputs)
+    L.Conv2D, L.Conv2DTranspose = Conv2D, Conv2DTranspose
+    tf.keras.layers.Wrapper = Wrapper
+    tf.TensorShape = TensorShape
+    tf.constant_initializer = ConstantInitializer
+    tf.constant = lambda v, *a, **k: v
+
+    def pad(x, paddings, **k):
+        for axis, (before, after) in enumerate([[int(a) for a in p] for p in paddings]):
+            if before or after:
+                shape = list(x.shape)
+                shape[axis] = before
+                front = x.new_zeros(shape)
+                shape[axis] = after
+                x = torch.cat([front, x, x.new_zeros(shape)], dim=axis)
+        return x
+    tf.pad = pad
+
+    def batch_to_space_nd(x, block_shape, crops, **k):
+        """one block dimension, no crops: batch index = j * (batch / b) + n  ->  out[n, i * b + j]"""
+        (b,) = [int(v) for v in block_shape]
+        assert [list(c) for c in crops] == [[0, 0]]
+        shape = [int(v) for v in x.shape]
+        y = x.reshape([b, shape[0] // b] + shape[1:])
+        y = y.permute([1, 2, 0] + list(range(3, y.dim())))
+        return y.reshape([shape[0] // b, shape[1] * b] + shape[2:])
+    tf.batch_to_space_nd = batch_to_space_nd
+
+    def resize_images(images, size, method=0, **k):
+        """method 1 = nearest neighbour, align_corners False: out[i] = in[floor(i * in / out)]"""
+        assert method == 1
+        H, W = int(images.shape[1]), int(images.shape[2])
+        oh, ow = int(size[0]), int(size[1])
+        rows = (torch.arange(oh) * H) // oh
+        cols = (torch.arange(ow) * W) // ow
+        return images[:, rows][:, :, cols]
+    tf.image.resize_images = resize_images
     L.batch_normalization = lambda inputs, training=False, name=None, **k: BatchNormalization(name=name, _scope=name)(inputs, training=training)
     L.dropout = layers_dropout
     L.max_pooling1d = max_pooling1d
