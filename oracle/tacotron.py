@@ -23,8 +23,8 @@ MaskedLinearLoss, sequence_mask (modules.py:400-485), the location-sensitive sco
 (2) The whole graph (tests/golden/make_reference_graph_vectors.py, tests/test_reference_graph.py): the reference's
 `Tacotron.initialize()` + `add_loss()` are EXECUTED - tacotron.py, modules.py, attention.py, Architecture_wrappers.py, helpers.py,
 custom_decoder.py unchanged - on a stand-in for the tf.layers / rnn_cell / seq2seq classes they compose (tests/golden/tf_shim_graph.py),
-in training (every dropout / zoneout mask recorded and injected here), masked-loss training, evaluation, GTA and free-running
-synthesis. forward / loss_fn / synthesize / linear_head reproduce the executed reference to <= 4e-6 (outputs), 1e-7 (loss terms) and
+in training (every dropout / zoneout mask recorded and injected here), masked-loss training, evaluation, GTA, free-running
+synthesis, and one add_optimizer step (LR schedule, global-norm clip, Adam, batch-norm moving averages == adam_step here). forward / loss_fn / synthesize / linear_head reproduce the executed reference to <= 4e-6 (outputs), 1e-7 (loss terms) and
 1e-5 relative (d loss / d variable, all 102 trainable variables), and the variable names the reference's scopes generate equal
 t2_tf_bundle.tacotron_tf_name over the parameter table. This pins the reference's COMPOSITION: layer order, scopes, activation /
 batch-norm / dropout placement, the zoneout wrapper and its un-zoned output, decoder-cell wiring, helpers, stop rule, CBHG, loss terms,

@@ -22,7 +22,8 @@ Conv1D1x1, ResidualConv1DGLU, SubPixelConvolution, ConvTranspose2D, NearestNeigh
 tf.layers.Conv1D / Conv2D / Conv2DTranspose and the keras Wrapper they are built from (tests/golden/tf_shim_graph.py): the training
 graph in three configurations (mu-law CE + SubPixel, MoL + ConvTranspose2D, Gaussian + NearestNeighbor; dropout masks recorded and
 injected), the evaluation branch (teacher-forced incremental pass through the convolution queues + eval loss) and the free-running
-synthesis branch (every categorical / mixture / logistic draw recorded and injected). step / upsample / loss_fn / incremental
+synthesis branch (every categorical / mixture / logistic draw recorded and injected), and one add_optimizer step (LR schedule,
+per-tensor clip_by_norm + clip_by_value, Adam, EMA of the updated variables == adam_step here). step / upsample / loss_fn / incremental
 reproduce the executed reference: outputs <= 2e-5, losses 1e-5, d loss / d variable 2e-4 relative for every variable, the sampled
 waveforms sample by sample; incremental == parallel forward on the same inputs; the variable names the reference's scopes generate
 equal t2_tf_bundle.wavenet_tf_name over the parameter table; the NN_init kernels its `_init_kernel` methods produce equal

@@ -5,8 +5,9 @@ Architecture_wrappers.py, helpers.py and custom_decoder.py underneath) on the TF
   python tests/golden/make_reference_graph_vectors.py        # needs /root/reference; only the committed .npz travels
 
 Scenarios (small widths so that the fixture stays a few hundred KB; every hparam not listed keeps the reference's default):
-  train     is_training=True, predict_linear=True, mask_decoder=False: all dropout / zoneout paths on; outputs, the five loss terms
-            and d loss / d variable for every trainable variable (autograd through the executed reference graph)
+  train     is_training=True, predict_linear=True, mask_decoder=False: all dropout / zoneout paths on; outputs, the five loss terms,
+            d loss / d variable for every trainable variable (autograd through the executed reference graph) and every variable
+            after one `add_optimizer` step (LR schedule, global-norm clip, Adam, batch-norm moving averages)
   train_md  is_training=True, predict_linear=False, mask_decoder=True: the masked losses inside the whole graph
   eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
   gta       gta=True: as eval without the post-processing net
@@ -151,6 +152,15 @@ def main():
     save_outputs("train", model, True)
     model.add_loss()
     save_losses("train", model)
+    # one optimizer step (tacotron.py:371-437): learning-rate schedule at global step 60000, clip_by_global_norm(1.0), Adam; plus the
+    # batch-norm moving-average updates it runs under (UPDATE_OPS)
+    model.add_optimizer(Tt(torch.tensor(60000)))
+    out["train_global_step"] = np.asarray(60000)
+    out["train_learning_rate"] = np.asarray(float(model.learning_rate), dtype=np.float64)
+    for k, v in model.optimize.new_values.items():
+        out["train_new/" + k] = v.numpy()
+    for k, v in G.S.updates.items():
+        out["train_new/" + k] = v.numpy()
     model.loss.backward()
     for k, v in G.S.vars.items():
         if v.requires_grad:

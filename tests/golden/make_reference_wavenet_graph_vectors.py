@@ -26,7 +26,8 @@ REF = "/root/reference"
 
 SMALL = dict(layers=4, stacks=2, residual_channels=8, gate_channels=16, skip_out_channels=8, kernel_size=3, num_mels=6, cin_channels=6,
              gin_channels=-1, hop_size=6, upsample_scales=[2, 3], freq_axis_kernel_size=3, wavenet_num_gpus=1, split_on_cpu=True,
-             wavenet_weight_normalization=False)
+             wavenet_weight_normalization=False,
+             wavenet_ema_decay=0.9)       # 0.9999 would move the shadow by less than fp32 spacing in one step: nothing to compare
 SCENARIOS = {
     "ce_subpixel": dict(input_type="mulaw-quantize", quantize_channels=256, out_channels=256, upsample_type="SubPixel"),   # util.py hard-codes mu = 255
     "mol_2d": dict(input_type="raw", quantize_channels=256, out_channels=6, upsample_type="2D"),      # 256 bins: the fp32 cdf difference is not rounding noise
@@ -95,6 +96,15 @@ def main():
         out[tag + "_y_hat"] = model.tower_y_hat_train[0].detach().numpy()                                  # [B, out_channels, T]
         out[tag + "_upsampled_c"] = model.tower_upsampled_local_features[0].detach().numpy()
         out[tag + "_loss"] = np.asarray(float(model.loss.detach()), dtype=np.float64)
+        # one optimizer step (wavenet.py:522-613): LR schedule at global step 30000, per-tensor clip_by_norm + clip_by_value, Adam, EMA
+        model.add_optimizer(Tt(torch.tensor(30000)))
+        out[tag + "_global_step"] = np.asarray(30000)
+        out[tag + "_learning_rate"] = np.asarray(float(model.learning_rate), dtype=np.float64)
+        assert model.optimize is model.ema
+        for k, v in G.S.assigned.items():
+            out["%s_new/%s" % (tag, k)] = v.numpy()
+        for k, v in model.ema.shadow.items():
+            out["%s_ema/%s" % (tag, k)] = v.numpy()
         model.loss.backward()
         names = list(G.S.vars)
         out[tag + "_var_names"] = np.array(names)

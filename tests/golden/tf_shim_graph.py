@@ -30,7 +30,7 @@ import torch
 import tf_shim
 from tf_shim import T
 
-S = types.SimpleNamespace(scope=[""], opened={}, layer_uid={}, vars=collections.OrderedDict(), gen=None, drops=[], create=True, inits={}, uniforms=[])
+S = types.SimpleNamespace(scope=[""], opened={}, layer_uid={}, vars=collections.OrderedDict(), gen=None, drops=[], create=True, inits={}, uniforms=[], updates=collections.OrderedDict(), assigned={})
 
 
 def reset(seed=0, variables=None):
@@ -42,6 +42,8 @@ def reset(seed=0, variables=None):
     S.drops[:] = []
     S.inits.clear()
     S.uniforms[:] = []
+    S.updates.clear()
+    S.assigned.clear()
     S.gen = torch.Generator().manual_seed(seed)
     S.create = variables is None
     for k, v in (variables or {}).items():
@@ -354,6 +356,10 @@ class BatchNormalization(Layer):
             flat = x.reshape(-1, int(C))
             mean = flat.mean(0)
             var = ((flat - mean) ** 2).mean(0)
+            # UPDATE_OPS (momentum 0.99; the non-fused path of tf.layers - the fused kernel needs 4-D inputs - feeds the same biased
+            # batch variance into the moving average): moving <- moving * 0.99 + batch * 0.01
+            S.updates[mm.var_name] = (mm * 0.99 + mean * 0.01).detach()
+            S.updates[mv.var_name] = (mv * 0.99 + var * 0.01).detach()
         else:
             mean, var = mm, mv
         return (x - mean) * torch.rsqrt(var + 1e-3) * gamma + beta
@@ -589,6 +595,65 @@ def dynamic_decode(decoder, output_time_major=False, impute_finished=False, maxi
     return stacked, state, lengths
 
 
+# ---- tf.train --------------------------------------------------------------------------------------------------------------------
+class AdamOptimizer(object):
+    """tf.train.AdamOptimizer: slots m, v start at zero, beta powers at beta1 / beta2, so the first apply_gradients uses t = 1:
+    lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t); m <- b1 m + (1 - b1) g; v <- b2 v + (1 - b2) g^2; var <- var - lr_t m / (sqrt(v) + eps).
+    apply_gradients does not assign in place: the new values land in `self.new_values` (name -> tensor) for the generator to store."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, **kw):
+        self.lr, self.b1, self.b2, self.eps, self.t = learning_rate, float(beta1), float(beta2), float(epsilon), 0
+        self.m, self.v, self.new_values = {}, {}, collections.OrderedDict()
+
+    def compute_gradients(self, loss, var_list=None, **kw):
+        variables = list(var_list) if var_list is not None else trainable_variables()
+        grads = torch.autograd.grad(loss, variables, retain_graph=True, allow_unused=True)
+        return list(zip(grads, variables))
+
+    def apply_gradients(self, grads_and_vars, global_step=None, **kw):
+        self.t += 1
+        lr = float(torch.as_tensor(self.lr))
+        lr_t = lr * math.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        for g, var in grads_and_vars:
+            if g is None:
+                continue
+            k = var.var_name
+            g = g.detach()
+            self.m[k] = self.b1 * self.m.get(k, torch.zeros_like(g)) + (1 - self.b1) * g
+            self.v[k] = self.b2 * self.v.get(k, torch.zeros_like(g)) + (1 - self.b2) * g * g
+            self.new_values[k] = var.detach() - lr_t * self.m[k] / (torch.sqrt(self.v[k]) + self.eps)
+            S.assigned[k] = self.new_values[k]
+        return self
+
+
+class ExponentialMovingAverage(object):
+    """tf.train.ExponentialMovingAverage(decay) without num_updates: the shadow starts at the variable's value when apply() builds
+    it and moves by shadow -= (1 - decay) (shadow - variable); apply() runs after the optimizer (the reference puts it under a control
+    dependency on the Adam op, wavenet.py:611-613), so `variable` is the value Adam just assigned (S.assigned)"""
+
+    def __init__(self, decay=0.999, **kw):
+        self.decay, self.shadow = float(decay), collections.OrderedDict()
+
+    def apply(self, var_list=None):
+        for var in var_list:
+            k = var.var_name
+            start = var.detach()
+            self.shadow[k] = start - (1 - self.decay) * (start - S.assigned.get(k, start))
+        return self
+
+
+def clip_by_global_norm(t_list, clip_norm, **kw):
+    """t * clip_norm / max(global_norm, clip_norm)"""
+    gn = torch.sqrt(sum((t.detach() ** 2).sum() for t in t_list if t is not None))
+    scale = float(clip_norm) / max(float(gn), float(clip_norm))
+    return [None if t is None else t * scale for t in t_list], gn
+
+
+def clip_by_norm(t, clip_norm, **kw):
+    n = torch.sqrt((t * t).sum())
+    return t * float(clip_norm) / torch.clamp(n, min=float(clip_norm))
+
+
 # ---- install ---------------------------------------------------------------------------------------------------------------------
 def install():
     """tf_shim.install() + the graph-building surface; returns the `tensorflow` stand-in"""
@@ -598,6 +663,11 @@ def install():
     tf.name_scope = lambda *a, **k: contextlib.nullcontext()
     tf.device = lambda *a, **k: contextlib.nullcontext()
     tf.train.replica_device_setter = lambda *a, **k: None
+    tf.train.AdamOptimizer, tf.train.ExponentialMovingAverage = AdamOptimizer, ExponentialMovingAverage
+    tf.clip_by_global_norm, tf.clip_by_norm = clip_by_global_norm, clip_by_norm
+    tf.clip_by_value = lambda t, lo, hi, **k: torch.clamp(t, float(lo), float(hi))
+    tf.get_collection = lambda key, *a, **k: list(S.updates.items())
+    tf.GraphKeys.UPDATE_OPS = "update_ops"
     tf.identity = lambda x, name=None: x
     tf.zeros, tf.ones = wrap(tf.zeros), wrap(tf.ones)
     tf.convert_to_tensor = lambda x, dtype=None, **k: T(torch.as_tensor(x, dtype=dtype))
@@ -608,6 +678,7 @@ def install():
     tf.reduce_any = lambda x, axis=None, **k: torch.as_tensor(x).any() if axis is None else torch.as_tensor(x).any(dim=int(axis))
     tf.split = lambda value, num_or_size_splits, axis=0, **k: list(torch.chunk(value, int(num_or_size_splits), dim=int(axis)))
     tf.add_n = lambda xs: sum(xs[1:], xs[0])
+    tf.concat = lambda values=None, axis=0, **k: torch.cat(list(values), dim=int(axis))
     tf.matmul = torch.matmul
     base_uniform = tf.random_uniform
 

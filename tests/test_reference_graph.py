@@ -178,3 +178,41 @@ def test_free_running_synthesis_and_stop_rule(R, tag):
     assert out["mel_outputs"].shape[1] == steps                            # same number of decoder steps as the executed reference
     _check_outputs(R, tag, out, False)
     _close(ot.linear_head(out["mel_outputs"], params, hp, False), R[tag + "_linear_outputs"])
+
+
+def test_one_optimizer_step_of_the_executed_reference(R):
+    """tacotron.py:371-463 executed: LR schedule at step 60000, clip_by_global_norm(1.0), Adam; and the batch-norm moving averages its
+    UPDATE_OPS dependency advances. oracle.train_step + adam_step land on the same variables; moving statistics follow
+    0.99 old + 0.01 batch with the (biased) batch moments the oracle reports."""
+    hp = _hp(R, predict_linear=True, mask_decoder=False)
+    params = _params(R)
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    step = int(R["train_global_step"])
+    assert abs(ot.learning_rate(hp, step) - float(R["train_learning_rate"])) <= 1e-6 * float(R["train_learning_rate"])
+    assert hp.tacotron_final_learning_rate < ot.learning_rate(hp, step) < hp.tacotron_initial_learning_rate      # inside the decay
+    loss, grads, out, parts = ot.train_step(params, ids, in_len, mel, stop, hp, masks=_masks(R, "train", True, hp), targets_lengths=tgt_len,
+                                            linear_targets=lin)
+    gn = float(torch.sqrt(sum((g * g).sum() for g in grads.values())))
+    assert gn > 1.0                                                                        # the clip is active in this fixture
+    new = {k: v.clone() for k, v in params.items()}
+    ot.adam_step(new, grads, {}, hp, step)
+    lr = float(R["train_learning_rate"])
+    stats = {}
+    ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train", True, hp), stats_out=stats)
+    n_moving = 0
+    for name in R["var_names"]:
+        eng = t2_tf_bundle.engine_name("Tacotron_model/" + str(name))
+        ref = R["train_new/" + str(name)]
+        if ot.is_trainable(eng):
+            delta_ref = ref - R["var/" + str(name)]
+            delta = new[eng].numpy() - params[eng].numpy()
+            # Adam's first step is lr * g / (|g| + eps): measured against the learning rate (elements whose gradient is rounding noise
+            # around eps = 1e-6 move by an arbitrary fraction of lr on both sides), plus fp32 spacing of the parameter itself
+            assert np.abs(delta - delta_ref).max() <= 5e-3 * lr + 2e-7 * np.abs(ref).max(), eng
+        else:
+            prefix, leaf = eng.rsplit("/", 1)
+            mean, var = stats[prefix + "/"]
+            want = 0.99 * params[eng] + 0.01 * (mean if leaf == "moving_mean" else var)
+            assert np.abs(want.numpy() - ref).max() <= 1e-6, eng
+            n_moving += 1
+    assert n_moving == 2 * (hp.enc_conv_num_layers + hp.postnet_num_layers + hp.cbhg_kernels + 2)

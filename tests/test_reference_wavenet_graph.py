@@ -155,3 +155,37 @@ def test_synthesis_branch_free_running_with_the_recorded_draws(R, tag):
     ref = R[tag + "_synth_y_hat"]
     assert wav.shape == ref.shape == (B, T) and np.abs(wav - ref).max() <= 2e-5
     assert np.unique(np.round(ref, 4)).size > T // 2                                   # a real sampled sequence, not a constant
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_one_optimizer_step_of_the_executed_reference(R, tag):
+    """wavenet.py:522-633 executed: LR schedule at step 30000, clip_by_norm(100) + clip_by_value(5) per tensor, Adam, then the EMA
+    of the UPDATED variables (decay 0.9999). oracle.train_step + adam_step land on the same variables and shadows."""
+    hp = _hp(R, tag)
+    params = {k: v.detach().clone() for k, v in _plain_params(R, tag).items()}
+    x, c = torch.from_numpy(R[tag + "_x"]), torch.from_numpy(R["c"])
+    lengths = torch.from_numpy(R["input_lengths"]).long()
+    masks = [torch.from_numpy(R["%s_mask_%d" % (tag, l)]) for l in range(hp.layers)]
+    y = torch.from_numpy(R[tag + "_y"])[:, :, 0]
+    y = y.long() if ow.is_mulaw_quantize(hp.input_type) else y
+    step = int(R[tag + "_global_step"])
+    assert abs(ow.learning_rate(hp, step) - float(R[tag + "_learning_rate"])) <= 1e-6 * float(R[tag + "_learning_rate"])
+    loss, grads, _ = ow.train_step(params, x, c, y, lengths, hp, dropout_masks=masks)
+    new, state = {k: v.clone() for k, v in params.items()}, {}
+    lr = ow.adam_step(new, grads, state, hp, step)
+    for name in R[tag + "_var_names"]:
+        eng = t2_tf_bundle.engine_name("WaveNet_model/" + str(name))
+        old = R["%s_var/%s" % (tag, name)]
+        key = "%s_new/%s" % (tag, name)
+        if key not in R.files:          # a variable the loss does not reach (the last block's residual output conv): TF hands back a None
+            assert eng.startswith("ResidualConv1DGLU_%d/residual_block_out_conv" % (hp.layers - 1)) and float(grads[eng].abs().max()) == 0.0
+            delta_ref = np.zeros_like(old)                                       # gradient, the reference skips it (wavenet.py:566-576)
+        else:
+            delta_ref = R[key] - old
+        delta = new[eng].numpy() - params[eng].numpy()
+        # measured against the learning rate: Adam's first step is lr * g / (|g| + eps), arbitrary where g is rounding noise around eps
+        tol = 5e-3 * lr + 2e-7 * np.abs(old).max()
+        assert np.abs(delta - delta_ref).max() <= tol, eng
+        ema_ref = R["%s_ema/%s" % (tag, name)] - old
+        ema = state["ema"][eng].numpy() - params[eng].numpy()
+        assert np.abs(ema - ema_ref).max() <= (1 - hp.wavenet_ema_decay) * tol + 1.2e-7 * np.abs(old).max(), eng
