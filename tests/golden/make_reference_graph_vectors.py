@@ -213,6 +213,42 @@ def main():
     out["synth_stop_bias_shift"] = np.asarray(shift, dtype=np.float64)
     print("synth_stop: %d decoder steps" % steps2)
 
+    # ---- error contract (tacotron.py:41-54, models/__init__.py of both packages): exception class + message of every rejected call -----
+    import json
+    from tacotron.models import create_model as taco_create
+    from wavenet_vocoder.models import create_model as wn_create
+    errors = {}
+
+    def record(key, fn):
+        try:
+            fn()
+            errors[key] = None
+        except Exception as e:                                      # noqa: BLE001 - the class is what gets recorded
+            errors[key] = [type(e).__name__, str(e)]
+    rhp.predict_linear, rhp.mask_decoder = True, True
+    base = dict(mel_targets=Tt(mel.clone()), stop_token_targets=Tt(stop.clone()), linear_targets=Tt(lin.clone()),
+                targets_lengths=Tt(tgt_len.clone()), split_infos=split_infos)
+    cases = {
+        "stop_without_mel": dict(base, mel_targets=None, is_training=True),
+        "mel_without_stop": dict(base, stop_token_targets=None, is_training=True),
+        "linear_missing_in_training": dict(base, linear_targets=None, is_training=True),
+        "linear_given_in_gta": dict(base, gta=True),
+        "mask_without_lengths": dict(base, targets_lengths=None, is_training=True),
+        "training_and_evaluating": dict(base, is_training=True, is_evaluating=True),
+    }
+    for key, kw in cases.items():
+        kw = {k: v for k, v in kw.items() if v is not None}
+        G.reset(seed=9, variables=None)
+        record("tacotron_initialize/" + key, lambda kw=kw: Tacotron(rhp).initialize(Tt(inputs.clone()), Tt(in_len.clone()), **kw))
+    record("tacotron_create_model/unknown", lambda: taco_create("Tacotron-3", rhp))
+    rhp.input_type, rhp.quantize_channels, rhp.out_channels = "mulaw-quantize", 256, 30
+    record("wavenet_create_model/out_channels_mismatch", lambda: wn_create("WaveNet", rhp))
+    rhp.out_channels = 256
+    record("wavenet_create_model/unknown", lambda: wn_create("WaveRNN", rhp))
+    assert all(v is not None for v in errors.values()), errors
+    with open(os.path.join(HERE, "reference_errors.json"), "w") as f:
+        json.dump(errors, f, indent=1, sort_keys=True)
+
     path = os.path.join(HERE, "reference_graph.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(out), os.path.getsize(path) / 1024))

@@ -216,3 +216,41 @@ def test_one_optimizer_step_of_the_executed_reference(R):
             assert np.abs(want.numpy() - ref).max() <= 1e-6, eng
             n_moving += 1
     assert n_moving == 2 * (hp.enc_conv_num_layers + hp.postnet_num_layers + hp.cbhg_kernels + 2)
+
+
+def test_error_contract_of_the_drop_in_models_matches_the_executed_reference(R):
+    """tests/golden/reference_errors.json: exception class + message of every call the reference rejects (tacotron.py:41-54 and both
+    create_model functions), recorded while executing it. The drop-in surface raises the same ones - before touching the GPU, so on CPU."""
+    import json
+    from tacotron.models import create_model as taco_create
+    from wavenet_vocoder.models import create_model as wn_create
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_errors.json")) as f:
+        want = json.load(f)
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    hp = _hp(R, predict_linear=True, mask_decoder=True)
+    base = dict(mel_targets=mel, stop_token_targets=stop, linear_targets=lin, targets_lengths=tgt_len)
+    cases = {
+        "stop_without_mel": dict(base, mel_targets=None, is_training=True),
+        "mel_without_stop": dict(base, stop_token_targets=None, is_training=True),
+        "linear_missing_in_training": dict(base, linear_targets=None, is_training=True),
+        "linear_given_in_gta": dict(base, gta=True),
+        "mask_without_lengths": dict(base, targets_lengths=None, is_training=True),
+        "training_and_evaluating": dict(base, is_training=True, is_evaluating=True),
+    }
+    got = {}
+
+    def record(key, fn):
+        try:
+            fn()
+            got[key] = None
+        except Exception as e:                                       # noqa: BLE001
+            got[key] = [type(e).__name__, str(e)]
+    for key, kw in cases.items():
+        record("tacotron_initialize/" + key, lambda kw=kw: taco_create("Tacotron", hp).initialize(ids, in_len, **kw))
+    record("tacotron_create_model/unknown", lambda: taco_create("Tacotron-3", hp))
+    wh = hparams.copy()
+    wh.input_type, wh.quantize_channels, wh.out_channels = "mulaw-quantize", 256, 30
+    record("wavenet_create_model/out_channels_mismatch", lambda: wn_create("WaveNet", wh))
+    wh.out_channels = 256
+    record("wavenet_create_model/unknown", lambda: wn_create("WaveRNN", wh))
+    assert got == want
