@@ -17,6 +17,16 @@ from tacotron.utils import plot
 from tacotron.utils.text import text_to_sequence
 
 
+def get_output_lengths(stop_tokens):
+    """synthesizer.py:254-257 _get_output_lengths: a row's length is the INDEX of its first rounded stop prediction of 1 (the frame the
+    stop fires on is not kept), the whole row when it never fires"""
+    out = []
+    for row in np.round(np.asarray(stop_tokens)):
+        hit = np.nonzero(row == 1)[0]
+        out.append(int(hit[0]) if hit.size else len(row))
+    return out
+
+
 class Synthesizer(object):
     def load(self, checkpoint_path, hparams, gta=False, model_name="Tacotron"):
         self._hparams, self.gta = hparams, gta
@@ -45,8 +55,7 @@ class Synthesizer(object):
             self.model.initialize(inputs, lens)
             mels = self.model.tower_mel_outputs[0].cpu().numpy()
             stop = self.model.tower_stop_token_prediction[0].cpu().numpy()
-            # cut each row at its own first <stop> (synthesizer.py:170-176 _get_output_lengths)
-            cut = [int(np.argmax(np.round(s) > 0)) + 1 if (np.round(s) > 0).any() else len(s) for s in stop]
+            cut = get_output_lengths(stop)
             mels = [m[:n] for m, n in zip(mels, cut)]
             if hp.predict_linear:       # post-processing net (tacotron.py:203-219): linear spectrograms of the same frames
                 linears = [l[:n] for l, n in zip(self.model.tower_linear_outputs[0].cpu().numpy(), cut)]

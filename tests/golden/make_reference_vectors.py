@@ -311,6 +311,24 @@ def main():
     for name, arr in zip(("inputs", "input_lengths", "mel_targets", "token_targets", "linear_targets", "targets_lengths", "split_infos"), res):
         out["tf_batch_" + name] = arr
 
+    # ---------------- L. Tacotron synthesizer helpers (tacotron/synthesizer.py:236-257): output lengths from the stop tokens ----
+    for name in ("pyaudio", "sounddevice"):
+        sys.modules.setdefault(name, tf_shim._NoopStub(name))
+    from tacotron.synthesizer import Synthesizer as RefTacoSynth
+    rl = np.random.default_rng(5)
+    stop_rows = rl.random((64, 12)).astype(np.float32)
+    stop_rows[0] = 0.1                 # never fires -> the whole row
+    stop_rows[1, 0] = 0.9              # fires on the first frame -> length 0
+    stop_rows[2, :-1], stop_rows[2, -1] = 0.2, 0.51
+    stop_rows[3] = 0.5                 # np.round is half-to-even: 0.5 -> 0, never fires
+    out["synth_stop_rows"] = stop_rows
+    out["synth_output_lengths"] = np.asarray(RefTacoSynth._get_output_lengths(None, stop_rows))
+    rs = RefTacoSynth()
+    rs._pad, rs._target_pad = 0, -4.1
+    out["synth_pad_input"] = rs._pad_input(np.arange(1, 6, dtype=np.int32), 8)
+    out["synth_pad_target"] = rs._pad_target(np.ones((3, 2), dtype=np.float32), 5)
+    out["synth_round_up"] = np.asarray([rs._round_up(x, 4) for x in range(0, 10)])
+
     np.savez_compressed(os.path.join(HERE, "reference_exec.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote %d arrays, %d hparams" % (len(out), len(hp_json)))
 

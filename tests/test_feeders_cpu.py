@@ -243,3 +243,18 @@ def test_paper_hparams_is_a_superset_of_the_defaults():
     assert (paper["layers"], paper["stacks"], paper["out_channels"], paper["upsample_scales"]) == (24, 4, 30, [5, 5, 11])
     assert int(np.prod(paper["upsample_scales"])) == paper["hop_size"]
     assert hparams.layers == 20 and hparams.predict_linear is True           # the defaults were not touched by the import
+
+
+def test_synthesizer_output_lengths_match_reference_executed_vectors():
+    """tacotron/synthesizer.py:254-257 executed (reference_exec.npz section L): the length of a synthesized row is the INDEX of the first
+    rounded stop prediction of 1 - the frame the stop fires on is dropped; 0.5 rounds to 0 (half to even)."""
+    import ast
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "tacotron", "synthesizer.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_output_lengths")
+    ns = {"np": np}
+    exec(compile(ast.Module([fn], []), "synthesizer.py", "exec"), ns)          # the module itself imports torch + the CUDA binding
+    assert ns["get_output_lengths"](R["synth_stop_rows"]) == R["synth_output_lengths"].tolist()
+    assert R["synth_output_lengths"][:4].tolist() == [12, 0, 11, 12]
+    from tacotron.feeder import pad_input, pad_target
+    assert pad_input(np.arange(1, 6, dtype=np.int32), 8, 0).tolist() == R["synth_pad_input"].tolist()
+    assert np.array_equal(pad_target(np.ones((3, 2), dtype=np.float32), 5, -4.1), R["synth_pad_target"])
