@@ -16,6 +16,23 @@ def _checkpoint(checkpoint):
     return path
 
 
+def run_live(args, checkpoint_path, hparams):
+    """tacotron/synthesize.py:18-38: read lines from stdin, synthesize each one, Griffin-Lim it into temp.wav and play it"""
+    synth = Synthesizer()
+    synth.load(checkpoint_path, hparams)
+    greetings = "Hello, Welcome to the Live testing tool. Please type a message and I will try to read it!"
+    log(greetings)
+    synth.synthesize([greetings], None, None, None, None)
+    while True:
+        try:
+            synth.synthesize([input()], None, None, None, None)
+        except (KeyboardInterrupt, EOFError):
+            leave = "Thank you for testing our features. see you soon."
+            log(leave)
+            synth.synthesize([leave], None, None, None, None)
+            break
+
+
 def run_eval(args, checkpoint_path, output_dir, hparams, sentences):
     eval_dir = os.path.join(output_dir, "eval")
     log_dir = os.path.join(output_dir, "logs-eval")          # tacotron/synthesize.py:38-45: Griffin-Lim previews go to logs-eval/wavs
@@ -70,4 +87,4 @@ def tacotron_synthesize(args, hparams, checkpoint, sentences=None):
         return run_eval(args, checkpoint_path, output_dir, hparams, sentences)
     if args.mode == "synthesis":
         return run_synthesis(args, checkpoint_path, output_dir, hparams)
-    raise ValueError("live mode needs an audio device and Griffin-Lim; not available on the B200 path")
+    return run_live(args, checkpoint_path, hparams)

@@ -60,6 +60,16 @@ class Synthesizer(object):
             if hp.predict_linear:       # post-processing net (tacotron.py:203-219): linear spectrograms of the same frames
                 linears = [l[:n] for l, n in zip(self.model.tower_linear_outputs[0].cpu().numpy(), cut)]
         mels = [np.clip(m, -hp.max_abs_value - hp.lower_bound_decay if hp.symmetric_mels else 0.0, hp.max_abs_value) for m in mels]
+        if basenames is None:
+            # live mode (synthesizer.py:162-182): Griffin-Lim of the first utterance into temp.wav, then the platform's player - `aplay`
+            # on Linux, skipped when the machine has no player / audio device
+            import shutil
+            if len(mels[0]) < 2:
+                return None
+            audio.save_wav(audio.inv_mel_spectrogram(mels[0].T, hp), "temp.wav", hp.sample_rate)
+            if shutil.which("aplay"):
+                os.system("aplay temp.wav")
+            return None
         names = []
         for m, b in zip(mels, basenames):
             path = os.path.join(out_dir, "mel-%s.npy" % b)
