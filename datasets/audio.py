@@ -183,7 +183,10 @@ def start_and_end_indices(quantized, silence_threshold=2):
 
 def trim_silence(wav, hparams):
     """librosa.effects.trim(wav, top_db, frame_length, hop_length)[0] (audio.py:46-52): keep from the first to the last frame whose
-    RMS power is within trim_top_db of the loudest frame (centred frames, zero-padded edges... reflect-padded in librosa)."""
+    RMS power is within trim_top_db of the loudest frame; start = first_frame * hop, end = min(len, (last_frame + 1) * hop).
+    UNPINNED (librosa is not installable here): frames are CENTRED on t * hop with reflect padding, librosa's rmse behaviour from 0.6
+    on; the reference pins librosa 0.5.1, whose rmse may frame the unpadded signal instead (frame t = samples [t hop, t hop + n)), which
+    would move both cut points by up to frame_length / 2 samples."""
     n, hop, top_db = hparams.trim_fft_size, hparams.trim_hop_size, hparams.trim_top_db
     y = np.pad(np.asarray(wav, dtype=np.float64), n // 2, mode="reflect")
     frames = 1 + (len(y) - n) // hop
