@@ -14,18 +14,17 @@ from wavenet_vocoder.util import is_mulaw, is_mulaw_quantize, mulaw, mulaw_quant
 def build_from_path(hparams, input_dirs, mel_dir, linear_dir, wav_dir, n_jobs=1, tqdm=lambda x: x):
     """LJSpeech-style folders: `<dir>/metadata.csv` with rows `basename|raw text|normalised text` and `<dir>/wavs/<basename>.wav`."""
     rows = []
-    index = 1
     for input_dir in input_dirs:
         with open(os.path.join(input_dir, "metadata.csv"), encoding="utf-8") as f:
             for line in f:
                 parts = line.strip().split("|")
                 if len(parts) < 2:
                     continue
-                rows.append((index, os.path.join(input_dir, "wavs", "%s.wav" % parts[0]), parts[-1]))
-                index += 1
+                # the utterance's basename names its files: audio-<basename>.npy ... (preprocessor.py:33-38); text = third column
+                rows.append((parts[0], os.path.join(input_dir, "wavs", "%s.wav" % parts[0]), parts[2] if len(parts) > 2 else parts[-1]))
     out = []
-    for index, wav_path, text in tqdm(rows):
-        r = _process_utterance(mel_dir, linear_dir, wav_dir, index, wav_path, text, hparams)
+    for basename, wav_path, text in tqdm(rows):
+        r = _process_utterance(mel_dir, linear_dir, wav_dir, basename, wav_path, text, hparams)
         if r is not None:
             out.append(r)
     return out
@@ -68,7 +67,7 @@ def _process_utterance(mel_dir, linear_dir, wav_dir, index, wav_path, text, hpar
     assert len(out) >= mel_frames * hop
     out = out[:mel_frames * hop]
     time_steps = len(out)
-    audio_filename, mel_filename, linear_filename = "audio-%d.npy" % index, "mel-%d.npy" % index, "linear-%d.npy" % index
+    audio_filename, mel_filename, linear_filename = "audio-%s.npy" % index, "mel-%s.npy" % index, "linear-%s.npy" % index
     np.save(os.path.join(wav_dir, audio_filename), out.astype(out_dtype), allow_pickle=False)
     np.save(os.path.join(mel_dir, mel_filename), mel.T, allow_pickle=False)
     np.save(os.path.join(linear_dir, linear_filename), linear.T, allow_pickle=False)

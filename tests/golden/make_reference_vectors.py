@@ -329,6 +329,42 @@ def main():
     out["synth_pad_target"] = rs._pad_target(np.ones((3, 2), dtype=np.float32), 5)
     out["synth_round_up"] = np.asarray([rs._round_up(x, 4) for x in range(0, 10)])
 
+    # ---------------- M. the two preprocessors, one utterance each way (datasets/preprocessor.py:40-165, wavenet_preprocessor.py:39-154) --
+    # _process_utterance runs AS IS; substituted underneath: librosa.core.load (scipy wav read -> float32 / 32768, what librosa does for
+    # int16 PCM at the native rate), librosa.stft / filters.mel (as in section B), and util._log1p so that a float32 signal stays
+    # float32 through mulaw() as it did under numpy 1.14's value-based casting (see this file's header).
+    import tempfile
+    from scipy.io import wavfile
+    import librosa.core
+    from datasets import preprocessor as rpre, wavenet_preprocessor as rwpre
+    librosa.core.load = lambda path, sr=None, **kw: (wavfile.read(path)[1].astype(np.float32) / 32768.0, sr)
+    ru._log1p = lambda x: np.log1p(x) if isinstance(x, np.ndarray) else float(np.log1p(x))
+    tmp = tempfile.mkdtemp()
+    rm = np.random.default_rng(31337)
+    n_m = 6000
+    sig = 0.35 * np.sin(np.cumsum(np.linspace(0.02, 0.5, n_m))) * np.hanning(n_m) + 0.004 * rm.standard_normal(n_m)
+    sig[:400] = 0.0                                              # leading digital silence: start_and_end_indices has something to cut
+    wavfile.write(os.path.join(tmp, "utt.wav"), rhp.sample_rate, (sig * 32767).astype(np.int16))
+    out["pre_wav_i16"] = (sig * 32767).astype(np.int16)
+    keep = dict(trim_silence=rhp.trim_silence, input_type=rhp.input_type, quantize_channels=rhp.quantize_channels)
+    rhp.trim_silence = False
+    for itype, qc in (("mulaw-quantize", 256), ("mulaw", 256), ("raw", 65536)):
+        rhp.input_type, rhp.quantize_channels = itype, qc
+        tag = itype.replace("-", "_")
+        d = tempfile.mkdtemp()
+        row = rpre._process_utterance(d, d, d, "utt", os.path.join(tmp, "utt.wav"), "some text", rhp)
+        out["pre_%s_row" % tag] = np.array([str(x) for x in row])
+        out["pre_%s_audio" % tag] = np.load(os.path.join(d, row[0]))
+        out["pre_%s_mel" % tag] = np.load(os.path.join(d, row[1]))
+        out["pre_%s_linear_cols" % tag] = np.load(os.path.join(d, row[2]))[:, ::16]
+        d = tempfile.mkdtemp()
+        row = rwpre._process_utterance(d, d, "utt", os.path.join(tmp, "utt.wav"), rhp)
+        out["wpre_%s_row" % tag] = np.array([os.path.basename(str(x)) for x in row])
+        out["wpre_%s_audio" % tag] = np.load(row[0])
+        out["wpre_%s_mel" % tag] = np.load(row[1])
+    for k, v in keep.items():
+        setattr(rhp, k, v)
+
     np.savez_compressed(os.path.join(HERE, "reference_exec.npz"), **{k: np.asarray(v) for k, v in out.items()})
     print("wrote %d arrays, %d hparams" % (len(out), len(hp_json)))
 

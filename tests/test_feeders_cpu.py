@@ -258,3 +258,46 @@ def test_synthesizer_output_lengths_match_reference_executed_vectors():
     from tacotron.feeder import pad_input, pad_target
     assert pad_input(np.arange(1, 6, dtype=np.int32), 8, 0).tolist() == R["synth_pad_input"].tolist()
     assert np.array_equal(pad_target(np.ones((3, 2), dtype=np.float32), 5, -4.1), R["synth_pad_target"])
+
+
+@pytest.mark.parametrize("itype,qc", [("mulaw-quantize", 256), ("mulaw", 256), ("raw", 65536)])
+def test_preprocessors_match_the_executed_reference(tmp_path, monkeypatch, itype, qc):
+    """reference_exec.npz section M: the reference's two `_process_utterance` functions executed on one synthetic utterance per input
+    type (librosa primitives substituted by the oracle restatements). The product preprocessors, with their GPU-backed calls replaced by
+    the same restatements, write the same files: names by basename, rows, lengths, silence cut, padding, dtypes, values."""
+    from scipy.io import wavfile
+    from oracle import audio as oa
+    from datasets import audio, preprocessor as pre, wavenet_preprocessor as wpre
+    f32 = lambda w: np.asarray(w, dtype=np.float32)
+    monkeypatch.setattr(audio, "melspectrogram", lambda w, hp: oa.melspectrogram(f32(w), hp).astype(np.float32))
+    monkeypatch.setattr(audio, "linearspectrogram", lambda w, hp: oa.linearspectrogram(f32(w), hp).astype(np.float32))
+    monkeypatch.setattr(audio, "preemphasis", lambda w, k, p=True: oa.preemphasis(w, k, p))
+    for mod in (pre, wpre):
+        monkeypatch.setattr(mod, "mulaw_quantize", lambda x, mu=256: oa.mulaw_quantize(f32(x)))
+        monkeypatch.setattr(mod, "mulaw", lambda x, mu=256: oa.mulaw(f32(x)))
+    wav_path = str(tmp_path / "utt.wav")
+    wavfile.write(wav_path, 22050, R["pre_wav_i16"])
+    hp = hparams.copy()
+    hp.parse("trim_silence=False,input_type=%s,quantize_channels=%d" % (itype, qc))
+    tag = itype.replace("-", "_")
+    d = str(tmp_path / "taco")
+    os.makedirs(d)
+    row = pre._process_utterance(d, d, d, "utt", wav_path, "some text", hp)
+    assert [str(x) for x in row] == R["pre_%s_row" % tag].tolist()
+    a, mel, lin = (np.load(os.path.join(d, row[i])) for i in range(3))
+    ref_a = R["pre_%s_audio" % tag]
+    assert a.dtype == ref_a.dtype and a.shape == ref_a.shape
+    if itype == "mulaw-quantize":
+        assert np.array_equal(a, ref_a)
+    else:
+        assert np.abs(a - ref_a).max() <= 1e-6
+    assert mel.dtype == np.float32 and np.abs(mel - R["pre_%s_mel" % tag]).max() <= 2e-4
+    assert np.abs(lin[:, ::16] - R["pre_%s_linear_cols" % tag]).max() <= 2e-4
+    d = str(tmp_path / "wn")
+    os.makedirs(d)
+    row = wpre._process_utterance(d, d, "utt", wav_path, hp)
+    assert [os.path.basename(str(x)) for x in row] == R["wpre_%s_row" % tag].tolist()
+    a, mel = np.load(row[0]), np.load(row[1])
+    ref_a = R["wpre_%s_audio" % tag]
+    assert a.dtype == ref_a.dtype and a.shape == ref_a.shape and (np.array_equal(a, ref_a) if itype == "mulaw-quantize" else np.abs(a - ref_a).max() <= 1e-6)
+    assert np.abs(mel - R["wpre_%s_mel" % tag]).max() <= 2e-4
