@@ -10,8 +10,9 @@ from wavenet_vocoder.synthesizer import Synthesizer
 
 
 def run_synthesis(args, checkpoint_path, output_dir, hparams):
-    wav_dir = os.path.join(output_dir, "wavs")
+    wav_dir, log_dir = os.path.join(output_dir, "wavs"), os.path.join(output_dir, "plots")
     os.makedirs(wav_dir, exist_ok=True)
+    os.makedirs(log_dir, exist_ok=True)
     synth = Synthesizer()
     synth.load(checkpoint_path, hparams)
     if args.model == "Tacotron-2":
@@ -28,7 +29,7 @@ def run_synthesis(args, checkpoint_path, output_dir, hparams):
             batch = mel_files[i:i + n]
             mels = [np.load(m) for m in batch]
             basenames = [os.path.basename(m).replace(".npy", "") for m in batch]
-            audio_files = synth.synthesize(mels, None, basenames, wav_dir, None)
+            audio_files = synth.synthesize(mels, None, basenames, wav_dir, log_dir)
             for j, mel_file in enumerate(batch):
                 f.write(("%s|%s\n" % (mel_file, audio_files[j])) if texts is None else ("%s|%s|%s\n" % (texts[i + j], mel_file, audio_files[j])))
     log("synthesized audio waveforms at %s" % wav_dir)

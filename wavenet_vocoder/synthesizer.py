@@ -6,7 +6,8 @@ import numpy as np
 import torch
 
 import t2_checkpoint
-from datasets.audio import get_hop_size, save_wavenet_wav
+from datasets.audio import get_hop_size, melspectrogram, save_wavenet_wav
+from wavenet_vocoder import util
 from wavenet_vocoder.models import create_model
 
 
@@ -37,4 +38,12 @@ class Synthesizer(object):
             path = os.path.join(out_dir, "wavenet-audio-%s.wav" % b)
             save_wavenet_wav(w[:n], path, sr=hp.sample_rate, inv_preemphasize=hp.preemphasize, k=hp.preemphasis)
             names.append(path)
+        if log_dir is not None:         # wavenet_vocoder/synthesizer.py:116-128: the waveform and its mel next to the conditioning mel
+            for w, n, b, m in zip(wavs, audio_lengths, basenames, mel_spectrograms):
+                if n < hp.n_fft:
+                    continue
+                util.waveplot(os.path.join(log_dir, "wavenet-waveplot-%s.png" % b), w[:n], None, hp, title="WaveNet generated Waveform.")
+                generated_mel = melspectrogram(np.ascontiguousarray(w[:n], dtype=np.float32), hp).T
+                util.plot_spectrogram(generated_mel, os.path.join(log_dir, "wavenet-mel-spectrogram-%s.png" % b),
+                                      title="Local Condition vs Reconstructed Audio Mel-Spectrogram analysis", target_spectrogram=m)
         return names

@@ -41,3 +41,16 @@ def sequence_mask(input_lengths, max_len=None, expand=True):
     max_len = int(lengths.max()) if max_len is None else int(max_len)
     m = (np.arange(max_len)[None, :] < lengths[:, None]).astype(np.float32)
     return m[:, :, None] if expand else m
+
+
+def waveplot(path, y_hat, y_target, hparams, title=None):
+    """util.py:174-196"""
+    from tacotron.utils import plot
+    plot.waveplot(path, y_hat, y_target, hparams, title=title)
+
+
+def plot_spectrogram(pred_spectrogram, path, title=None, split_title=False, target_spectrogram=None, max_len=None, auto_aspect=False):
+    """util.py:198-237 (the same figure as tacotron/utils/plot.py's)"""
+    from tacotron.utils import plot
+    plot.plot_spectrogram(pred_spectrogram, path, title=title, split_title=split_title, target_spectrogram=target_spectrogram, max_len=max_len,
+                          auto_aspect=auto_aspect)
