@@ -164,6 +164,18 @@ def init_params(hp, seed=None, random_bias=False):
 # ---------------------------------------------------------------------------------------------------------
 # layers
 # ---------------------------------------------------------------------------------------------------------
+def _clip_low(hp):
+    """tacotron.py:89,176,199: T2_output_range[0] - lower_bound_decay, the range starting at -max_abs_value (symmetric mels) or 0"""
+    return (-hp.max_abs_value if hp.symmetric_mels else 0.0) - hp.lower_bound_decay
+
+
+def _reg_weight(hp):
+    """tacotron.py:334-338"""
+    if getattr(hp, "tacotron_scale_regularization", False):
+        return hp.tacotron_reg_weight * (1.0 / (2 * hp.max_abs_value) if hp.symmetric_mels else 1.0 / hp.max_abs_value)
+    return hp.tacotron_reg_weight
+
+
 def conv_block(x, params, prefix, activation, training, drop_rate, drop_mask=None, stats_out=None):
     """modules.py:379-391 with batch_norm_position='after': conv('same') -> activation -> BN -> dropout.
     x [B, T, Cin] channels-last."""
@@ -311,7 +323,7 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
     decoder_output = torch.stack(frames, dim=1)
     stop_logits = torch.stack(stops, dim=1).squeeze(-1)
     if hp.clip_outputs:
-        decoder_output = torch.clamp(decoder_output, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+        decoder_output = torch.clamp(decoder_output, _clip_low(hp), hp.max_abs_value)
     y = decoder_output
     for i in range(hp.postnet_num_layers):
         act = "tanh" if i < hp.postnet_num_layers - 1 else None
@@ -320,7 +332,7 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
     residual = y @ params["postnet_projection/kernel"] + params["postnet_projection/bias"]
     mel_outputs = decoder_output + residual
     if hp.clip_outputs:
-        mel_outputs = torch.clamp(mel_outputs, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+        mel_outputs = torch.clamp(mel_outputs, _clip_low(hp), hp.max_abs_value)
     out = {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_logits": stop_logits,
            "alignments": torch.stack(aligns, dim=1)}
     if hp.predict_linear and "cbhg_linear_specs_projection/kernel" in params:
@@ -374,7 +386,7 @@ def linear_head(mel_outputs, params, hp, training, stats_out=None):
     y = cbhg(mel_outputs, params, hp, training, stats_out)
     lin = y @ params["cbhg_linear_specs_projection/kernel"] + params["cbhg_linear_specs_projection/bias"]
     if hp.clip_outputs:
-        lin = torch.clamp(lin, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+        lin = torch.clamp(lin, _clip_low(hp), hp.max_abs_value)
     return lin
 
 
@@ -429,14 +441,14 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
             break
     decoder_output = torch.stack(frames, dim=1)
     if hp.clip_outputs:
-        decoder_output = torch.clamp(decoder_output, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+        decoder_output = torch.clamp(decoder_output, _clip_low(hp), hp.max_abs_value)
     y = decoder_output
     for i in range(hp.postnet_num_layers):
         act = "tanh" if i < hp.postnet_num_layers - 1 else None
         y = conv_block(y, params, "postnet_convolutions/conv_layer_%d/" % (i + 1), act, False, hp.tacotron_dropout_rate)
     mel_outputs = decoder_output + y @ params["postnet_projection/kernel"] + params["postnet_projection/bias"]
     if hp.clip_outputs:
-        mel_outputs = torch.clamp(mel_outputs, -hp.max_abs_value - hp.lower_bound_decay, hp.max_abs_value)
+        mel_outputs = torch.clamp(mel_outputs, _clip_low(hp), hp.max_abs_value)
     return {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_token_prediction": torch.stack(stops, dim=1).squeeze(-1),
             "alignments": torch.stack(aligns, dim=1)}
 
@@ -467,12 +479,12 @@ def loss_fn(out, mel_targets, stop_targets, params, hp, targets_lengths=None, li
         before = masked_mse(mel_targets, out["decoder_output"], targets_lengths)
         after = masked_mse(mel_targets, out["mel_outputs"], targets_lengths)
         stop = masked_sigmoid_cross_entropy(stop_targets, out["stop_logits"], targets_lengths, hp.cross_entropy_pos_weight)
-        reg = sum((v * v).sum() / 2 for k, v in params.items() if is_regularized(k)) * hp.tacotron_reg_weight
+        reg = sum((v * v).sum() / 2 for k, v in params.items() if is_regularized(k)) * _reg_weight(hp)
         return before + after + stop + reg, {"before": before, "after": after, "stop": stop, "reg": reg}
     before = F.mse_loss(out["decoder_output"], mel_targets)
     after = F.mse_loss(out["mel_outputs"], mel_targets)
     stop = F.binary_cross_entropy_with_logits(out["stop_logits"], stop_targets)
-    reg = sum((v * v).sum() / 2 for k, v in params.items() if is_regularized(k)) * hp.tacotron_reg_weight
+    reg = sum((v * v).sum() / 2 for k, v in params.items() if is_regularized(k)) * _reg_weight(hp)
     return before + after + stop + reg, {"before": before, "after": after, "stop": stop, "reg": reg}
 
 

@@ -26,6 +26,13 @@ class CbhgConfig(ctypes.Structure):
         (n, ctypes.c_float) for n in ("max_abs_value", "lower_bound_decay", "reg_weight")]
 
 
+def _decay_field(hp):
+    """The kernels clip outputs to [-max_abs_value - lower_bound_decay, max_abs_value]. The reference's lower bound is
+    T2_output_range[0] - lower_bound_decay with T2_output_range[0] = -max_abs_value for symmetric mels and 0 otherwise
+    (tacotron.py:89,176,199): the asymmetric case is expressed through the same two fields by folding max_abs_value into the decay."""
+    return hp.lower_bound_decay if hp.symmetric_mels else hp.lower_bound_decay - hp.max_abs_value
+
+
 def make_cbhg_config(hp, B, T, reg_weight):
     """CBHG post-processing net + linear head (tacotron.py:203-219); the shapes the CUDA path implements are checked by t2_cbhg_sizes"""
     c = CbhgConfig()
@@ -36,7 +43,7 @@ def make_cbhg_config(hp, B, T, reg_weight):
     c.num_freq = hp.num_freq
     c.n_priority_freq = int(2000 / (hp.sample_rate * 0.5) * hp.num_freq)
     c.clip_outputs, c.mask_decoder = int(hp.clip_outputs), int(bool(hp.mask_decoder))
-    c.max_abs_value, c.lower_bound_decay, c.reg_weight = hp.max_abs_value, hp.lower_bound_decay, reg_weight
+    c.max_abs_value, c.lower_bound_decay, c.reg_weight = hp.max_abs_value, _decay_field(hp), reg_weight
     return c
 
 
@@ -87,7 +94,7 @@ def make_config(hp, B, T_in, T_out, precision="bf16"):
     if getattr(hp, "tacotron_scale_regularization", False):       # tacotron.py:334-338
         reg_weight *= 1.0 / (2 * hp.max_abs_value) if hp.symmetric_mels else 1.0 / hp.max_abs_value
     c.dropout_rate, c.zoneout_rate, c.reg_weight = hp.tacotron_dropout_rate, hp.tacotron_zoneout_rate, reg_weight
-    c.max_abs_value, c.lower_bound_decay = hp.max_abs_value, hp.lower_bound_decay
+    c.max_abs_value, c.lower_bound_decay = hp.max_abs_value, _decay_field(hp)
     c.split_bf16 = int(precision == "fp32-class")
     c.mask_decoder = int(bool(hp.mask_decoder))
     c.cross_entropy_pos_weight = float(hp.cross_entropy_pos_weight)

@@ -59,7 +59,10 @@ class Synthesizer(object):
             mels = [m[:n] for m, n in zip(mels, cut)]
             if hp.predict_linear:       # post-processing net (tacotron.py:203-219): linear spectrograms of the same frames
                 linears = [l[:n] for l, n in zip(self.model.tower_linear_outputs[0].cpu().numpy(), cut)]
-        mels = [np.clip(m, -hp.max_abs_value - hp.lower_bound_decay if hp.symmetric_mels else 0.0, hp.max_abs_value) for m in mels]
+        lo = -hp.max_abs_value if hp.symmetric_mels else 0.0          # T2_output_range (synthesizer.py:78,157,160): no decay margin here
+        mels = [np.clip(m, lo, hp.max_abs_value) for m in mels]
+        if hp.predict_linear and not self.gta:
+            linears = [np.clip(l, lo, hp.max_abs_value) for l in linears]
         if basenames is None:
             # live mode (synthesizer.py:162-182): Griffin-Lim of the first utterance into temp.wav, then the platform's player - `aplay`
             # on Linux, skipped when the machine has no player / audio device

@@ -9,6 +9,7 @@ Scenarios (small widths so that the fixture stays a few hundred KB; every hparam
             d loss / d variable for every trainable variable (autograd through the executed reference graph) and every variable
             after one `add_optimizer` step (LR schedule, global-norm clip, Adam, batch-norm moving averages)
   train_md  is_training=True, predict_linear=False, mask_decoder=True: the masked losses inside the whole graph
+  train_asym  symmetric_mels=False + tacotron_scale_regularization=True: the other output-clipping range and the scaled regulariser
   eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
   gta       gta=True: as eval without the post-processing net
   synth     free running (TacoTestHelper), stop rule, max_iters
@@ -176,6 +177,16 @@ def main():
     save_outputs("train_md", model, False)
     model.add_loss()
     save_losses("train_md", model)
+
+    # ---- training with the non-default range flags: asymmetric mels (outputs clipped to [0 - decay, max]) + scaled regulariser ---------
+    rhp.predict_linear, rhp.mask_decoder, rhp.symmetric_mels, rhp.tacotron_scale_regularization = True, False, False, True
+    model, drops = run("train_asym", variables, 6, linear_targets=Tt(lin.clone()), is_training=True, global_step=Tt(torch.tensor(0)))
+    masks_to_oracle("train_asym", drops, True, T_out)
+    save_outputs("train_asym", model, True)
+    model.add_loss()
+    save_losses("train_asym", model)
+    assert float((model.tower_decoder_output[0] == -rhp.lower_bound_decay).float().mean()) > 0.05       # the lower clip is active
+    rhp.symmetric_mels, rhp.tacotron_scale_regularization = True, False
 
     # ---- eval / GTA ------------------------------------------------------------------------------------------------------------------
     rhp.predict_linear, rhp.mask_decoder = True, False

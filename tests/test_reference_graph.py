@@ -254,3 +254,26 @@ def test_error_contract_of_the_drop_in_models_matches_the_executed_reference(R):
     wh.out_channels = 256
     record("wavenet_create_model/unknown", lambda: wn_create("WaveRNN", wh))
     assert got == want
+
+
+def test_training_graph_with_asymmetric_mels_and_scaled_regulariser(R):
+    """symmetric_mels=False moves the output clip to [0 - lower_bound_decay, max_abs_value] (tacotron.py:89,176,199,216) and
+    tacotron_scale_regularization=True divides the L2 weight by max_abs_value (:334-338); executed reference vs oracle"""
+    hp = _hp(R, predict_linear=True, mask_decoder=False, symmetric_mels=False, tacotron_scale_regularization=True)
+    params = _params(R)
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    out = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train_asym", True, hp))
+    _check_outputs(R, "train_asym", out, True)
+    _close(out["linear_outputs"], R["train_asym_linear_outputs"])
+    lo = torch.tensor(-hp.lower_bound_decay)                                 # float32(-0.1)
+    assert out["decoder_output"].min() == lo and float((out["decoder_output"] == lo).float().mean()) > 0.05
+    total, parts = ot.loss_fn(out, mel, stop, params, hp, tgt_len, lin)
+    for k, ref in (("before", "before_loss"), ("after", "after_loss"), ("stop", "stop_token_loss"), ("reg", "regularization_loss"),
+                   ("linear", "linear_loss")):
+        assert abs(float(parts[k]) - float(R["train_asym_" + ref])) <= 1e-5 * max(1e-3, abs(float(R["train_asym_" + ref]))), k
+    assert abs(float(R["train_asym_regularization_loss"]) / float(R["train_regularization_loss"]) - 1.0 / hp.max_abs_value) < 1e-4
+    # the product config folds the asymmetric lower bound into the two fields its kernels clip with
+    import importlib
+    taco = importlib.import_module("tacotron-2_b200.tacotron")
+    assert abs((-hp.max_abs_value - taco._decay_field(hp)) - (0.0 - hp.lower_bound_decay)) < 1e-7
+    assert taco._decay_field(_hp(R)) == hp.lower_bound_decay
