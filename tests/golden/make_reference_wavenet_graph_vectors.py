@@ -9,6 +9,7 @@ Scenarios (small widths; every hparam not listed keeps the reference's default -
   ce_subpixel   input_type mulaw-quantize (256 classes), SubPixel conditioning upsampling, masked cross entropy
   mol_2d        input_type raw, 2-component mixture-of-logistics head, ConvTranspose2D upsampling
   gauss_nn      input_type raw, single-Gaussian head (out_channels 2, the reference default), NearestNeighbor upsampling
+  gauss_paper_2d  the paper configuration's flags: legacy / residual_legacy off, cdf_loss on, ConvTranspose2D upsampling
 Each stores the variables under the names the reference's scopes give them, the recorded dropout masks, the network output, the
 loss and d loss / d variable (autograd through the executed reference graph), plus the NN_init kernels the reference hands to its
 upsampling layers (`_init_kernel`, modules.py:642-654,761-770).
@@ -32,6 +33,10 @@ SCENARIOS = {
     "ce_subpixel": dict(input_type="mulaw-quantize", quantize_channels=256, out_channels=256, upsample_type="SubPixel"),   # util.py hard-codes mu = 255
     "mol_2d": dict(input_type="raw", quantize_channels=256, out_channels=6, upsample_type="2D"),      # 256 bins: the fp32 cdf difference is not rounding noise
     "gauss_nn": dict(input_type="raw", quantize_channels=65536, out_channels=2, upsample_type="NearestNeighbor"),
+    # the flags of the reference's paper configuration (paper_hparams.py:187-195): no sqrt(0.5) scaling of skips / residuals, CDF form
+    # of the Gaussian loss with its own log-scale floor (256 bins here: with 65536 the fp32 CDF difference is rounding noise, see mol_2d)
+    "gauss_paper_2d": dict(input_type="raw", quantize_channels=256, out_channels=2, upsample_type="2D", legacy=False, residual_legacy=False,
+                           cdf_loss=True, log_scale_min_gauss=-7.000000006091266),
 }
 
 
@@ -115,7 +120,7 @@ def main():
             out["%s_init/%s" % (tag, k)] = v
         print("%s: %d variables, loss %.6f, NN_init kernels recorded: %d" % (tag, len(names), float(model.loss), len(G.S.inits)))
         variables = {k: v.detach().clone() for k, v in G.S.vars.items()}
-        if tag == "gauss_nn":
+        if tag.startswith("gauss"):
             continue
         cat = rhp.input_type == "mulaw-quantize"
 

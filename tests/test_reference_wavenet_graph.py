@@ -19,7 +19,7 @@ from hparams import hparams
 from oracle import wavenet as ow
 
 PATH = os.path.join(os.path.dirname(__file__), "golden", "reference_wavenet_graph.npz")
-TAGS = ["ce_subpixel", "mol_2d", "gauss_nn"]
+TAGS = ["ce_subpixel", "mol_2d", "gauss_nn", "gauss_paper_2d"]
 
 
 @pytest.fixture(scope="module")
