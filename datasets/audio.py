@@ -155,7 +155,8 @@ def load_wav(path, sr):
 
 def save_wav(wav, path, sr):
     from scipy.io import wavfile
-    wav = wav * (32767 / max(0.01, np.max(np.abs(wav))))
+    wav = np.asarray(wav)
+    wav = wav * (32767 / max(0.01, np.max(np.abs(wav)) if wav.size else 0.0))          # an empty signal (a 0-frame mel) writes an empty file
     wavfile.write(path, sr, wav.astype(np.int16))
 
 

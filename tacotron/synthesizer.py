@@ -85,7 +85,9 @@ class Synthesizer(object):
             os.makedirs(os.path.join(log_dir, "plots"), exist_ok=True)
             alignments = self.model.tower_alignments[0].cpu().numpy()                 # [B, T_in, T_out]
             for i, (m, b) in enumerate(zip(mels, basenames)):
-                if len(m) < 2:
+                if hp.predict_linear:
+                    np.save(os.path.join(out_dir, "linear-%s.npy" % b), linears[i].astype(np.float32), allow_pickle=False)
+                if len(m) < 2:          # nothing to invert or draw (an untrained model can fire its stop token on the first frames)
                     continue
                 plot.plot_alignment(alignments[i], os.path.join(log_dir, "plots", "alignment-%s.png" % b), title=texts[i], split_title=True,
                                     max_len=len(m))
@@ -95,6 +97,5 @@ class Synthesizer(object):
                                           auto_aspect=True)
                 audio.save_wav(audio.inv_mel_spectrogram(m.T, hp), os.path.join(log_dir, "wavs", "wav-%s-mel.wav" % b), hp.sample_rate)
                 if hp.predict_linear:
-                    np.save(os.path.join(out_dir, "linear-%s.npy" % b), linears[i].astype(np.float32), allow_pickle=False)
                     audio.save_wav(audio.inv_linear_spectrogram(linears[i].T, hp), os.path.join(log_dir, "wavs", "wav-%s-linear.wav" % b), hp.sample_rate)
         return names, ["<no_g>"] * len(names)

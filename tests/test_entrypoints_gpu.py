@@ -73,8 +73,9 @@ def test_cli_workflow(tmp_path):
           "--mels_dir", "tacotron_output/eval/"], base)
     wavs = [f for f in os.listdir(os.path.join(base, "wavenet_output", "wavs")) if f.endswith(".wav")]
     assert len(wavs) == 2
-    rate, data = wavfile.read(os.path.join(base, "wavenet_output", "wavs", wavs[0]))
-    assert rate == 22050 and data.dtype == np.int16 and len(data) % 275 == 0 and len(data) > 0
+    for w in wavs:      # whole hops; a row whose stop token fires on the first frame has length 0 (synthesizer.py:254-257 keeps the INDEX)
+        rate, data = wavfile.read(os.path.join(base, "wavenet_output", "wavs", w))
+        assert rate == 22050 and data.dtype == np.int16 and len(data) % 275 == 0
 
 
 def test_cli_tacotron_with_the_default_linear_head(tmp_path):
@@ -106,5 +107,9 @@ def test_cli_tacotron_with_the_default_linear_head(tmp_path):
     lin = np.load(os.path.join(ev, "linear-batch_0_sentence_0.npy"))
     mel = np.load(os.path.join(ev, "mel-batch_0_sentence_0.npy"))
     assert lin.shape == (mel.shape[0], 1025) and np.isfinite(lin).all() and np.abs(lin).max() <= 4.1
-    rate, data = wavfile.read(os.path.join(base, "tacotron_output", "logs-eval", "wavs", "wav-batch_0_sentence_0-linear.wav"))
-    assert rate == 22050 and len(data) == 275 * (mel.shape[0] - 1)
+    preview = os.path.join(base, "tacotron_output", "logs-eval", "wavs", "wav-batch_0_sentence_0-linear.wav")
+    if mel.shape[0] >= 2:       # previews need two frames; the length is the index of the first fired stop token (synthesizer.py:254-257)
+        rate, data = wavfile.read(preview)
+        assert rate == 22050 and len(data) == 275 * (mel.shape[0] - 1)
+    else:
+        assert not os.path.exists(preview)

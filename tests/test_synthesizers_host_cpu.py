@@ -158,3 +158,34 @@ def test_tacotron_training_loop_eval_artefacts(tmp_path, monkeypatch):
         assert os.path.getsize(os.path.join(ev, "step-%d-eval-align.png" % step)) > 500
         assert os.path.getsize(os.path.join(ev, "step-%d-eval-mel-spectrogram.png" % step)) > 500
     assert len(saved) == 1 and fake.calls == 4 + 2 * 2
+
+
+def test_zero_length_outputs_flow_through_both_synthesizers(tmp_path, monkeypatch):
+    """an untrained model can fire its stop token on frame 0: the reference's rule gives that row length 0. Files are still written
+    (empty mel / linear / wav), previews are skipped, nothing crashes"""
+    from scipy.io import wavfile
+    from datasets import audio
+    from tacotron import synthesizer as ts
+    from wavenet_vocoder import synthesizer as ws
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    hp = hparams.copy()
+
+    class Fires(_FakeTacotron):
+        def initialize(self, inputs, lens, mel=None, gta=False, **kw):
+            _FakeTacotron.initialize(self, inputs, lens, mel, gta, **kw)
+            self.tower_stop_token_prediction[0][:] = 0.9
+    s = ts.Synthesizer()
+    s._hparams, s.gta, s.model, s._pad, s._target_pad = hp, False, Fires(hp), 0, -hp.max_abs_value
+    out_dir, log_dir = str(tmp_path / "eval"), str(tmp_path / "logs-eval")
+    os.makedirs(out_dir)
+    names, _ = s.synthesize(["One.", "Two."], ["a", "b"], out_dir, log_dir, None)
+    assert [np.load(n).shape for n in names] == [(0, hp.num_mels)] * 2
+    assert np.load(os.path.join(out_dir, "linear-a.npy")).shape == (0, hp.num_freq) and os.listdir(os.path.join(log_dir, "wavs")) == []
+    w = ws.Synthesizer()
+    w._hparams, w.model = hp, None                                   # the model must not even be called
+    wav_dir = str(tmp_path / "wavs")
+    os.makedirs(wav_dir)
+    out = w.synthesize([np.load(n) for n in names], None, ["mel-a", "mel-b"], wav_dir, str(tmp_path))
+    for p in out:
+        rate, data = wavfile.read(p)
+        assert rate == hp.sample_rate and len(data) == 0

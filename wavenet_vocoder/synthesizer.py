@@ -31,8 +31,11 @@ class Synthesizer(object):
         c = np.stack([np.pad(x, [(0, maxlen - len(x)), (0, 0)], mode="constant", constant_values=lo) for x in mel_spectrograms]).astype(np.float32)
         if hp.normalize_for_wavenet:
             c = ((c - lo) / (hi - lo)).astype(np.float32)
-        self.model.initialize(None, torch.from_numpy(c).cuda(), None, None)       # c: [batch, frames, num_mels] (wavenet.py:408-427)
-        wavs = self.model.tower_y_hat[0].cpu().numpy()
+        if maxlen == 0:             # every mel is empty (an untrained Tacotron can fire its stop token on the first frame)
+            wavs = np.zeros((len(mel_spectrograms), 0), dtype=np.float32)
+        else:
+            self.model.initialize(None, torch.from_numpy(c).cuda(), None, None)   # c: [batch, frames, num_mels] (wavenet.py:408-427)
+            wavs = self.model.tower_y_hat[0].cpu().numpy()
         names = []
         for w, n, b in zip(wavs, audio_lengths, basenames):
             path = os.path.join(out_dir, "wavenet-audio-%s.wav" % b)
