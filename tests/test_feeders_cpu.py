@@ -301,3 +301,19 @@ def test_preprocessors_match_the_executed_reference(tmp_path, monkeypatch, itype
     ref_a = R["wpre_%s_audio" % tag]
     assert a.dtype == ref_a.dtype and a.shape == ref_a.shape and (np.array_equal(a, ref_a) if itype == "mulaw-quantize" else np.abs(a - ref_a).max() <= 1e-6)
     assert np.abs(mel - R["wpre_%s_mel" % tag]).max() <= 2e-4
+
+
+def test_stock_configurations_pass_the_engine_config_checks():
+    """hparams.py and paper_hparams.py as shipped are inside the supported matrix of both engines; flags that would silently change
+    the arithmetic are rejected by name"""
+    import importlib
+    import paper_hparams
+    taco, wn = importlib.import_module("tacotron-2_b200.tacotron"), importlib.import_module("tacotron-2_b200.wavenet")
+    for hp in (hparams, paper_hparams.hparams):
+        assert taco.unsupported_hparams(hp) == [] and wn.unsupported_hparams(hp) == []
+    for name, value in (("tacotron_natural_eval", True), ("wavenet_natural_eval", True), ("outputs_per_step", 2), ("smoothing", True),
+                        ("wavenet_weight_normalization", True), ("upsample_type", "Resize"), ("tacotron_teacher_forcing_mode", "scheduled")):
+        hp = hparams.copy()
+        setattr(hp, name, value)
+        bad = taco.unsupported_hparams(hp) + wn.unsupported_hparams(hp)
+        assert len(bad) == 1 and bad[0].startswith(name + "="), (name, bad)
