@@ -69,6 +69,7 @@ def unsupported_hparams(hp):
     need("mask_encoder", lambda v: bool(v), "un-masked encoder memory")
     need("tacotron_teacher_forcing_mode", lambda v: v == "constant", "scheduled teacher forcing: helpers.py:135-169")
     need("tacotron_teacher_forcing_ratio", lambda v: float(v) == 1.0, "per-step teacher-forcing draw: helpers.py:121-124")
+    need("synthesis_constraint", lambda v: not v, "attention window / monotonic constraint at synthesis: attention.py:201-214")
     need("tacotron_natural_eval", lambda v: not v, "evaluation that feeds the model its own predictions: helpers.py:97-100")
     if not getattr(hp, "mask_decoder", False):
         need("cross_entropy_pos_weight", lambda v: float(v) == 1.0, "the weighted stop-token loss only exists in the masked loss path")

@@ -49,6 +49,7 @@ def unsupported_hparams(hp):
     need("upsample_activation", lambda v: v in ("Relu", "relu", "RELU"), "LeakyRelu / linear upsampling activations: wavenet.py:190-201")
     need("freq_axis_kernel_size", lambda v: v == 3, "freq_axis_kernel_size 3")
     need("input_type", lambda v: v in _INPUT_TYPES, "raw | mulaw | mulaw-quantize")
+    need("wavenet_synth_debug", lambda v: not v, "teacher-forced synthesis debugging from wavenet_debug_wavs: synthesizer.py:54-57,85-97")
     need("wavenet_natural_eval", lambda v: not v, "free-running evaluation: wavenet.py:386 (evaluation here is teacher forced)")
     return bad
 

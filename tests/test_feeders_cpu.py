@@ -311,7 +311,7 @@ def test_stock_configurations_pass_the_engine_config_checks():
     taco, wn = importlib.import_module("tacotron-2_b200.tacotron"), importlib.import_module("tacotron-2_b200.wavenet")
     for hp in (hparams, paper_hparams.hparams):
         assert taco.unsupported_hparams(hp) == [] and wn.unsupported_hparams(hp) == []
-    for name, value in (("tacotron_natural_eval", True), ("wavenet_natural_eval", True), ("outputs_per_step", 2), ("smoothing", True),
+    for name, value in (("tacotron_natural_eval", True), ("wavenet_natural_eval", True), ("synthesis_constraint", True), ("wavenet_synth_debug", True), ("outputs_per_step", 2), ("smoothing", True),
                         ("wavenet_weight_normalization", True), ("upsample_type", "Resize"), ("tacotron_teacher_forcing_mode", "scheduled")):
         hp = hparams.copy()
         setattr(hp, name, value)
