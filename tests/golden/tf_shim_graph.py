@@ -809,3 +809,74 @@ def install():
     py.framework.ops.control_dependencies = lambda *a, **k: contextlib.nullcontext()
     py.util.nest.map_structure = map_structure
     return tf
+
+
+def selfcheck():
+    """The layer stand-ins against torch.nn.functional's own kernels (an implementation none of this repo's code shares): convolutions
+    (VALID / SAME incl. even kernels and dilation, 2-D, transposed 2-D with SAME cropping), batch norm, max pool, LSTM cell (torch's
+    gate order i, f, g, o re-ordered to TF's i, j, f, o with forget_bias folded into the bias)."""
+    import torch.nn.functional as F
+    install()
+    g = torch.Generator().manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    worst = {}
+
+    def check(name, a, b):
+        worst[name] = float((a - b).abs().max())
+        assert worst[name] < 5e-5, (name, worst[name])
+    reset(seed=1)
+    x = rnd(2, 11, 5)
+    for kw, d, pad in ((3, 1, "same"), (4, 1, "same"), (2, 1, "same"), (3, 2, "valid"), (5, 3, "same")):
+        with variable_scope("c%d_%d_%s" % (kw, d, pad)):
+            layer = Conv1D(7, kw, padding=pad, dilation_rate=d)
+            y = layer(x)
+        w = layer.kernel.detach().permute(2, 1, 0)                      # [out, in, kw]
+        xi = x.transpose(1, 2)
+        if pad == "same":
+            total = (kw - 1) * d
+            xi = F.pad(xi, (total // 2, total - total // 2))
+        check("conv1d k%d d%d %s" % (kw, d, pad), y.detach(), F.conv1d(xi, w, layer.bias.detach(), dilation=d).transpose(1, 2))
+    x4 = rnd(2, 6, 9, 3)
+    with variable_scope("c2d"):
+        layer = Conv2D(4, (3, 3), padding="same")
+        y = layer(x4)
+    check("conv2d same", y.detach(), F.conv2d(x4.permute(0, 3, 1, 2), layer.kernel.detach().permute(3, 2, 0, 1), layer.bias.detach(),
+                                              padding=1).permute(0, 2, 3, 1))
+    xt = rnd(2, 1, 6, 5)
+    for kh, kw, s in ((3, 4, 4), (3, 2, 2), (3, 5, 5)):
+        with variable_scope("ct_%d_%d" % (kw, s)):
+            layer = Conv2DTranspose(1, (kh, kw), strides=(1, s), padding="same", data_format="channels_first")
+            y = layer(xt)
+        ref = F.conv_transpose2d(xt, layer.kernel.detach().permute(3, 2, 0, 1), layer.bias.detach(), stride=(1, s), padding=(kh // 2, 0))
+        check("conv2d_transpose k%d s%d" % (kw, s), y.detach(), ref)
+    xb = rnd(3, 7, 6)
+    with variable_scope("bn"):
+        bn = BatchNormalization()
+        y_train, y_inf = bn(xb, training=True), bn(xb, training=False)
+    v = {k.rsplit("/", 1)[1]: t.detach() for k, t in S.vars.items() if k.startswith("bn/")}
+    flat = xb.reshape(-1, 6)
+    check("batch_norm training", y_train.detach().reshape(-1, 6), F.batch_norm(flat, None, None, v["gamma"], v["beta"], True, 0.0, 1e-3))
+    check("batch_norm inference", y_inf.detach().reshape(-1, 6), F.batch_norm(flat, v["moving_mean"], v["moving_variance"], v["gamma"], v["beta"], False, 0.0, 1e-3))
+    check("max_pool same", max_pooling1d(xb, 2, 1, "same"), F.max_pool1d(F.pad(xb.transpose(1, 2), (0, 1), value=-float("inf")), 2, 1).transpose(1, 2))
+    n, xin = 5, rnd(4, 3)
+    with variable_scope("lstm"):
+        cell = LSTMCell(n, name="cell")
+        c0, h0 = rnd(4, n), rnd(4, n)
+        out, (c1, h1) = cell(xin, LSTMStateTuple(c0, h0))
+    K, b = S.vars["lstm/cell/kernel"].detach(), S.vars["lstm/cell/bias"].detach()
+    i, j, f, o = (K[:, k * n:(k + 1) * n] for k in range(4))
+    bi, bj, bf, bo = (b[k * n:(k + 1) * n] for k in range(4))
+    Wt = torch.cat([i, f, j, o], dim=1).t()                              # torch order: input, forget, cell (g), output
+    bt = torch.cat([bi, bf + 1.0, bj, bo])
+    h_ref, c_ref = torch._VF.lstm_cell(xin, (h0, c0), Wt[:, :3].contiguous(), Wt[:, 3:].contiguous(), bt, torch.zeros_like(bt))
+    check("lstm_cell h", h1.detach(), h_ref)
+    check("lstm_cell c", c1.detach(), c_ref)
+    return worst
+
+
+if __name__ == "__main__":
+    import sys
+    if "--selfcheck" in sys.argv:
+        for k, v in selfcheck().items():
+            print("%-32s %.2e" % (k, v))
+        print("selfcheck ok")

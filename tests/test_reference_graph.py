@@ -277,3 +277,14 @@ def test_training_graph_with_asymmetric_mels_and_scaled_regulariser(R):
     taco = importlib.import_module("tacotron-2_b200.tacotron")
     assert abs((-hp.max_abs_value - taco._decay_field(hp)) - (0.0 - hp.lower_bound_decay)) < 1e-7
     assert taco._decay_field(_hp(R)) == hp.lower_bound_decay
+
+
+def test_stand_in_layer_primitives_against_torch_kernels():
+    """tests/golden/tf_shim_graph.py --selfcheck: the Conv1D / Conv2D / Conv2DTranspose / BatchNormalization / max-pool / LSTMCell stand-ins
+    the reference's code was executed on, against torch.nn.functional's own kernels (run in a subprocess: the stand-in installs a fake
+    `tensorflow` module)."""
+    import subprocess
+    import sys
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    r = subprocess.run([sys.executable, "tf_shim_graph.py", "--selfcheck"], cwd=golden, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "selfcheck ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
