@@ -102,8 +102,11 @@ def _expand_dollars(m):
     parts = match.split(".")
     if len(parts) > 2:
         return match + " dollars"          # unexpected format
-    dollars = int(parts[0]) if parts[0] else 0
-    cents = int(parts[1]) if len(parts) > 1 and parts[1] else 0
+    try:
+        dollars = int(parts[0]) if parts[0] else 0
+        cents = int(parts[1]) if len(parts) > 1 and parts[1] else 0
+    except ValueError:                     # "$,85": a stray separator the comma rule did not remove (the reference raises here)
+        return match.replace(",", "") + " dollars"
     d_unit = "dollar" if dollars == 1 else "dollars"
     c_unit = "cent" if cents == 1 else "cents"
     if dollars and cents:

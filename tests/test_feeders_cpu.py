@@ -317,3 +317,14 @@ def test_stock_configurations_pass_the_engine_config_checks():
         setattr(hp, name, value)
         bad = taco.unsupported_hparams(hp) + wn.unsupported_hparams(hp)
         assert len(bad) == 1 and bad[0].startswith(name + "="), (name, bad)
+
+
+def test_number_normaliser_never_raises_and_leaves_no_digits():
+    from hypothesis import given, settings, strategies as st
+    from tacotron.utils.cleaners import english_cleaners
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.text(alphabet="0123456789$£.,-stndrh aA{}%", max_size=30))
+    def run(s):
+        assert not any(c.isdigit() for c in english_cleaners(s))
+    run()
