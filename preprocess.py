@@ -27,7 +27,16 @@ def norm_data(args):
         raise ValueError("dataset value entered %s does not belong to supported datasets: %s" % (args.dataset, supported))
     if args.dataset.startswith("LJSpeech"):
         return [os.path.join(args.base_dir, args.dataset)]
-    path = os.path.join(args.base_dir, args.language, "by_book", args.voice, args.reader)
+    languages = ["en_US", "en_UK", "fr_FR", "it_IT", "de_DE", "es_ES", "ru_RU", "uk_UK", "pl_PL", "nl_NL", "pt_PT", "fi_FI", "se_SE", "tr_TR", "ar_SA"]
+    if args.language not in languages:
+        raise ValueError("Please enter a supported language to use from M-AILABS dataset! \n%s" % languages)
+    if args.voice not in ("female", "male", "mix"):
+        raise ValueError("Please enter a supported voice option to use from M-AILABS dataset! \n%s" % ["female", "male", "mix"])
+    path = os.path.join(args.base_dir, args.language, "by_book", args.voice)
+    readers = [e for e in os.listdir(path) if os.path.isdir(os.path.join(path, e))]
+    if args.reader not in readers:
+        raise ValueError("Please enter a valid reader for your language and voice settings! \n%s" % readers)
+    path = os.path.join(path, args.reader)
     books = [e for e in os.listdir(path) if os.path.isdir(os.path.join(path, e))]
     if args.merge_books == "True":
         return [os.path.join(path, b) for b in books]
