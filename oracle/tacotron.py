@@ -514,6 +514,8 @@ def adam_step(params, grads, state, hp, global_step):
     state["t"] = state.get("t", 0) + 1
     t = state["t"]
     lr_t = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    if getattr(hp, "tacotron_fine_tuning", False):          # tacotron.py:401: no gradient (and no Adam update) for the embedding and the encoder
+        grads = {k: g for k, g in grads.items() if not ("inputs_embedding" in k or "encoder_" in k)}
     if hp.tacotron_clip_gradients:
         gn = torch.sqrt(sum((g * g).sum() for g in grads.values()))
         scale = 1.0 / max(gn.item(), 1.0)

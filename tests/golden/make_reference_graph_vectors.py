@@ -162,6 +162,13 @@ def main():
         out["train_new/" + k] = v.numpy()
     for k, v in G.S.updates.items():
         out["train_new/" + k] = v.numpy()
+    # the same step with tacotron_fine_tuning: gradients only for the variables without 'inputs_embedding' / 'encoder_' in their names
+    # (tacotron.py:401); the global norm of the clip is taken over those only
+    rhp.tacotron_fine_tuning = True
+    model.add_optimizer(Tt(torch.tensor(60000)))
+    rhp.tacotron_fine_tuning = False
+    for k, v in model.optimize.new_values.items():
+        out["train_ft_new/" + k] = v.numpy()
     model.loss.backward()
     for k, v in G.S.vars.items():
         if v.requires_grad:

@@ -288,3 +288,39 @@ def test_stand_in_layer_primitives_against_torch_kernels():
     golden = os.path.join(os.path.dirname(__file__), "golden")
     r = subprocess.run([sys.executable, "tf_shim_graph.py", "--selfcheck"], cwd=golden, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "selfcheck ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_fine_tuning_optimizer_step_of_the_executed_reference(R):
+    """tacotron.py:401 executed with tacotron_fine_tuning=True: the embedding and every `encoder_*` variable get no gradient and no Adam
+    update, and the global-norm clip sees the remaining gradients only. oracle.adam_step follows; the product freezes the same leading
+    range of its flat buffer (tacotron-2_b200/tacotron.py optimizer_step)."""
+    hp = _hp(R, predict_linear=True, mask_decoder=False, tacotron_fine_tuning=True)
+    params = _params(R)
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    loss, grads, _, _ = ot.train_step(params, ids, in_len, mel, stop, hp, masks=_masks(R, "train", True, hp), targets_lengths=tgt_len,
+                                      linear_targets=lin)
+    new = {k: v.clone() for k, v in params.items()}
+    lr = ot.adam_step(new, grads, {}, hp, int(R["train_global_step"]))
+    frozen = updated = 0
+    for name in R["var_names"]:
+        eng = t2_tf_bundle.engine_name("Tacotron_model/" + str(name))
+        if not ot.is_trainable(eng):
+            continue
+        key = "train_ft_new/" + str(name)
+        if eng.startswith(("inputs_embedding", "encoder_")):
+            assert key not in R.files and torch.equal(new[eng], params[eng]), eng
+            frozen += 1
+        else:
+            delta_ref = R[key] - R["var/" + str(name)]
+            delta = new[eng].numpy() - params[eng].numpy()
+            assert np.abs(delta - delta_ref).max() <= 5e-3 * lr + 2e-7 * np.abs(R[key]).max(), eng
+            updated += 1
+    assert frozen == 1 + 4 * hp.enc_conv_num_layers + 4 and updated > 50
+    # the clip really differs between the two modes in this fixture (so the norm's membership is exercised)
+    k = "inference/postnet_projection/projection_postnet_projection/kernel"
+    assert np.abs(R["train_ft_new/" + k] - R["train_new/" + k]).max() > 0
+    # the product's frozen range = the leading tensors of its parameter table
+    names = list(ot.param_shapes(hp))
+    first_free = next(i for i, n in enumerate(names) if not n.startswith(("inputs_embedding", "encoder_")))
+    assert all(n.startswith(("inputs_embedding", "encoder_")) for n in names[:first_free]) and not any(
+        n.startswith(("inputs_embedding", "encoder_")) or "encoder_" in n or "inputs_embedding" in n for n in names[first_free:])
