@@ -255,3 +255,76 @@ def test_table_round_trip_property(tmp_path):
         tb.write_table(p, items, block_size=block)
         assert tb.read_table(p) == items
     run()
+
+
+def test_crc32c_and_mask_against_tensorboards_implementation():
+    """an implementation this repo did not write: tensorboard's TensorFlow stub carries the CRC-32C + masking TFRecord / table files use"""
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    import t2_tf_bundle as tb
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 3, 7, 8, 9, 63, 64, 65, 1000, 4097, 100003):
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert tb.crc32c(data) == pw.crc32c(data)
+        assert tb.mask_crc(tb.crc32c(data)) == pw.masked_crc32c(data)
+        assert tb.unmask_crc(pw.masked_crc32c(data)) == pw.crc32c(data)
+
+
+def _bundle_message_classes():
+    """BundleHeaderProto / BundleEntryProto (tensorflow/core/protobuf/tensor_bundle.proto) built with protobuf's descriptor API on top of
+    tensorboard's GENERATED TensorShapeProto / DataType / VersionDef classes (real TensorFlow schemas shipped in the image)"""
+    pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    from tensorboard.compat.proto import tensor_shape_pb2, types_pb2, versions_pb2
+    pkg = tensor_shape_pb2.DESCRIPTOR.package                             # "tensorboard" in this build
+    fd = descriptor_pb2.FileDescriptorProto(name="t2_test_tensor_bundle.proto", package="t2test", syntax="proto3")
+    fd.dependency.extend([tensor_shape_pb2.DESCRIPTOR.name, types_pb2.DESCRIPTOR.name, versions_pb2.DESCRIPTOR.name])
+    F = descriptor_pb2.FieldDescriptorProto
+    h = fd.message_type.add(name="BundleHeaderProto")
+    en = h.enum_type.add(name="Endianness")
+    en.value.add(name="LITTLE", number=0)
+    en.value.add(name="BIG", number=1)
+    h.field.add(name="num_shards", number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    h.field.add(name="endianness", number=2, type=F.TYPE_ENUM, type_name=".t2test.BundleHeaderProto.Endianness", label=F.LABEL_OPTIONAL)
+    h.field.add(name="version", number=3, type=F.TYPE_MESSAGE, type_name=".%s.VersionDef" % pkg, label=F.LABEL_OPTIONAL)
+    e = fd.message_type.add(name="BundleEntryProto")
+    e.field.add(name="dtype", number=1, type=F.TYPE_ENUM, type_name=".%s.DataType" % pkg, label=F.LABEL_OPTIONAL)
+    e.field.add(name="shape", number=2, type=F.TYPE_MESSAGE, type_name=".%s.TensorShapeProto" % pkg, label=F.LABEL_OPTIONAL)
+    e.field.add(name="shard_id", number=3, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    e.field.add(name="offset", number=4, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+    e.field.add(name="size", number=5, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+    e.field.add(name="crc32c", number=6, type=F.TYPE_FIXED32, label=F.LABEL_OPTIONAL)
+    pool = descriptor_pool.Default()
+    try:
+        filed = pool.AddSerializedFile(fd.SerializeToString())
+    except Exception:                                                    # already registered by an earlier test in this process
+        filed = pool.FindFileByName(fd.name)
+    get = getattr(message_factory, "GetMessageClass", None)
+    mk = (lambda d: get(d)) if get else (lambda d: message_factory.MessageFactory(pool).GetPrototype(d))
+    return mk(filed.message_types_by_name["BundleHeaderProto"]), mk(filed.message_types_by_name["BundleEntryProto"]), types_pb2
+
+
+def test_hand_encoded_bundle_protos_against_the_protobuf_library():
+    """the hand-written protobuf encoder / decoder of t2_tf_bundle.py against Google's protobuf runtime: our bytes parse into the expected
+    messages, and messages serialised by the runtime decode to the same entries here (both directions, several dtypes / shapes / offsets)"""
+    Header, Entry, types_pb2 = _bundle_message_classes()
+    import t2_tf_bundle as tb
+    hdr = Header()
+    hdr.ParseFromString(tb._encode_header(1))
+    assert hdr.num_shards == 1 and hdr.endianness == 0 and hdr.version.producer == 1
+    assert hdr.SerializeToString() == tb._encode_header(1)
+    assert tb._decode_header(Header(num_shards=3, endianness=1).SerializeToString()) == {"num_shards": 3, "endianness": 1}
+    assert (tb.DT_FLOAT, tb.DT_DOUBLE, tb.DT_INT32, tb.DT_UINT8, tb.DT_INT16, tb.DT_INT8, tb.DT_INT64, tb.DT_BOOL) == tuple(
+        getattr(types_pb2, n) for n in ("DT_FLOAT", "DT_DOUBLE", "DT_INT32", "DT_UINT8", "DT_INT16", "DT_INT8", "DT_INT64", "DT_BOOL"))
+    cases = [(tb.DT_FLOAT, (5, 512, 512), 0, 5 * 512 * 512 * 4, 0x12345678), (tb.DT_INT64, (), 1 << 33, 8, 0xFFFFFFFF),
+             (tb.DT_FLOAT, (0, 80), 12, 0, 1), (tb.DT_INT32, (1,), 300, 4, 0x80000000), (tb.DT_FLOAT, (31, 1, 32), 77, 3968, 7)]
+    for dtype, shape, offset, size, crc in cases:
+        raw = tb._encode_entry(dtype, shape, offset, size, crc)
+        m = Entry()
+        m.ParseFromString(raw)
+        assert (m.dtype, tuple(d.size for d in m.shape.dim), m.shard_id, m.offset, m.size, m.crc32c) == (dtype, shape, 0, offset, size, crc)
+        assert m.SerializeToString() == raw                              # byte-identical to the runtime's canonical serialisation
+        back = tb._decode_entry(m.SerializeToString())
+        assert (back["dtype"], back["shape"], back["offset"], back["size"], back["crc32c"]) == (dtype, shape, offset, size, crc)
+    m = Entry(dtype=tb.DT_FLOAT, shard_id=2, offset=5, size=6, crc32c=9)
+    m.shape.dim.add(size=4)
+    assert tb._decode_entry(m.SerializeToString())["shard_id"] == 2
