@@ -265,8 +265,9 @@ def location_sensitive_score(W_query, W_fil, W_keys, v_a, b_a):
     return (v_a * torch.tanh(W_keys + W_query + W_fil + b_a)).sum(-1)
 
 
-def attention_step(query, cum, keys, values, mask, params):
-    """attention.py:169-226 + _compute_attention :10-35. query [B, D]; cum [B, T_in]; returns (context, alignments)."""
+def attention_step(query, cum, keys, values, mask, params, smoothing=False):
+    """attention.py:169-226 + _compute_attention :10-35. query [B, D]; cum [B, T_in] = the attention state (cumulated alignments, or
+    the previous alignments with cumulative_weights=False); mask None = mask_encoder False; returns (context, alignments)."""
     pq = (query @ params["attention/query_layer/kernel"]).unsqueeze(1)              # [B, 1, A]
     kf = params["attention/location_features_convolution/kernel"]                      # [31, 1, 32]
     f = F.conv1d(cum.unsqueeze(1), kf.permute(2, 1, 0).contiguous(), params["attention/location_features_convolution/bias"],
@@ -274,8 +275,12 @@ def attention_step(query, cum, keys, values, mask, params):
     pl = f @ params["attention/location_features_layer/kernel"]                        # [B, T_in, A]
     e = location_sensitive_score(pq, pl, keys, params["attention/attention_variable_projection"],
                                  params["attention/attention_bias"])                   # [B, T_in]
-    e = torch.where(mask > 0, e, torch.full_like(e, -float("inf")))                    # _maybe_mask_score
-    a = torch.softmax(e, dim=-1)
+    if mask is not None:
+        e = torch.where(mask > 0, e, torch.full_like(e, -float("inf")))                # _maybe_mask_score
+    if smoothing:                                                                      # attention.py:72-92
+        a = torch.sigmoid(e) / torch.sigmoid(e).sum(dim=-1, keepdim=True)
+    else:
+        a = torch.softmax(e, dim=-1)
     ctx = torch.bmm(a.unsqueeze(1), values).squeeze(1)
     return ctx, a
 
@@ -294,7 +299,9 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
                        hp.tacotron_dropout_rate, masks.get(("enc_drop", i)), stats_out)
     memory = encoder_rnn(x, input_lengths, params, hp, training, masks.get("enc_zone"))
     mask = (torch.arange(T_in)[None, :] < input_lengths[:, None]).float()
-    values = memory * mask.unsqueeze(-1)                                     # BahdanauAttention memory masking
+    if not getattr(hp, "mask_encoder", True):                                # attention.py:140-141: neither memory nor scores are masked
+        mask = None
+    values = memory * mask.unsqueeze(-1) if mask is not None else memory     # BahdanauAttention memory masking
     keys = values @ params["attention/memory_layer/kernel"]
     # TacoTrainingHelper: step t consumes the go frame (t = 0) or target frame t - 1 (teacher forcing, r = 1)
     dec_in = torch.cat([torch.zeros(B, 1, hp.num_mels), mel_targets[:, :-1, :]], dim=1)
@@ -314,8 +321,8 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
         c2n = zoneout(c2, nc2, zr, training, zm[(2, "c", t)] if zm else None)
         h2n = zoneout(h2, nh2, zr, training, zm[(2, "h", t)] if zm else None)
         c1, h1, c2, h2 = c1n, h1n, c2n, h2n
-        ctx, a = attention_step(nh2, cum, keys, values, mask, params)
-        cum = cum + a                                                        # cumulative_weights
+        ctx, a = attention_step(nh2, cum, keys, values, mask, params, getattr(hp, "smoothing", False))
+        cum = cum + a if getattr(hp, "cumulative_weights", True) else a      # attention.py:220-224
         pin = torch.cat([nh2, ctx], dim=-1)
         frames.append(pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"])
         stops.append(pin @ params["stop_token_projection/kernel"] + params["stop_token_projection/bias"])

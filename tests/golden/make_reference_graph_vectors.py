@@ -9,6 +9,7 @@ Scenarios (small widths so that the fixture stays a few hundred KB; every hparam
             d loss / d variable for every trainable variable (autograd through the executed reference graph) and every variable
             after one `add_optimizer` step (LR schedule, global-norm clip, Adam, batch-norm moving averages)
   train_md  is_training=True, predict_linear=False, mask_decoder=True: the masked losses inside the whole graph
+  train_smooth / train_nomask  smoothing normalisation + non-cumulative attention state; un-masked encoder memory
   train_asym  symmetric_mels=False + tacotron_scale_regularization=True: the other output-clipping range and the scaled regulariser
   eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
   gta       gta=True: as eval without the post-processing net
@@ -194,6 +195,18 @@ def main():
     save_losses("train_asym", model)
     assert float((model.tower_decoder_output[0] == -rhp.lower_bound_decay).float().mean()) > 0.05       # the lower clip is active
     rhp.symmetric_mels, rhp.tacotron_scale_regularization = True, False
+
+    # ---- attention variants the product rejects (kept for the oracle: the kernels of a later round are checked against it) --------------
+    rhp.predict_linear, rhp.mask_decoder = False, False
+    rhp.smoothing, rhp.cumulative_weights = True, False
+    model, drops = run("train_smooth", no_cbhg, 7, is_training=True, global_step=Tt(torch.tensor(0)))
+    masks_to_oracle("train_smooth", drops, True, T_out)
+    save_outputs("train_smooth", model, False)
+    rhp.smoothing, rhp.cumulative_weights, rhp.mask_encoder = False, True, False
+    model, drops = run("train_nomask", no_cbhg, 8, is_training=True, global_step=Tt(torch.tensor(0)))
+    masks_to_oracle("train_nomask", drops, True, T_out)
+    save_outputs("train_nomask", model, False)
+    rhp.mask_encoder = True
 
     # ---- eval / GTA ------------------------------------------------------------------------------------------------------------------
     rhp.predict_linear, rhp.mask_decoder = True, False

@@ -324,3 +324,23 @@ def test_fine_tuning_optimizer_step_of_the_executed_reference(R):
     first_free = next(i for i, n in enumerate(names) if not n.startswith(("inputs_embedding", "encoder_")))
     assert all(n.startswith(("inputs_embedding", "encoder_")) for n in names[:first_free]) and not any(
         n.startswith(("inputs_embedding", "encoder_")) or "encoder_" in n or "inputs_embedding" in n for n in names[first_free:])
+
+
+@pytest.mark.parametrize("tag,flags", [("train_smooth", dict(smoothing=True, cumulative_weights=False)), ("train_nomask", dict(mask_encoder=False))])
+def test_attention_variants_of_the_executed_reference(R, tag, flags):
+    """attention.py:72-92 (smoothing normalisation), :220-224 (state = last alignments when cumulative_weights is off), :140-141
+    (mask_encoder off: neither memory nor scores masked). The product rejects these flags; the oracle carries them for later kernels."""
+    hp = _hp(R, predict_linear=False, mask_decoder=False, **flags)
+    params = _params(R, drop=("CBHG", "cbhg"))
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    out = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, tag, True, hp))
+    _check_outputs(R, tag, out, True)
+    a = out["alignments"]
+    assert torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)), atol=1e-5)
+    pad = (torch.arange(a.shape[2])[None, :] >= in_len[:, None])                       # padded encoder positions
+    if tag == "train_nomask":
+        assert float(a[1][:, pad[1]].min()) > 0                                         # attention mass leaks onto the padding
+    else:
+        assert float(a[1][:, pad[1]].abs().max()) == 0
+    base = ot.forward(params, ids, in_len, mel, _hp(R, predict_linear=False, mask_decoder=False), training=True, masks=_masks(R, tag, True, hp))
+    assert float((base["alignments"] - a).abs().max()) > 1e-3                          # the flags do change the result
