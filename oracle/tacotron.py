@@ -78,8 +78,8 @@ def param_shapes(hp):
         sh["decoder_LSTM/cell_%d/kernel" % (i + 1)] = (lin + D, 4 * D)
         sh["decoder_LSTM/cell_%d/bias" % (i + 1)] = (4 * D,)
         lin = D
-    sh["linear_transform_projection/kernel"] = (D + 2 * H, M)
-    sh["linear_transform_projection/bias"] = (M,)
+    sh["linear_transform_projection/kernel"] = (D + 2 * H, M * hp.outputs_per_step)        # r frames per decoder step (tacotron.py:141)
+    sh["linear_transform_projection/bias"] = (M * hp.outputs_per_step,)
     sh["stop_token_projection/kernel"] = (D + 2 * H, hp.outputs_per_step)
     sh["stop_token_projection/bias"] = (hp.outputs_per_step,)
     cin = hp.num_mels
@@ -303,8 +303,12 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
         mask = None
     values = memory * mask.unsqueeze(-1) if mask is not None else memory     # BahdanauAttention memory masking
     keys = values @ params["attention/memory_layer/kernel"]
-    # TacoTrainingHelper: step t consumes the go frame (t = 0) or target frame t - 1 (teacher forcing, r = 1)
-    dec_in = torch.cat([torch.zeros(B, 1, hp.num_mels), mel_targets[:, :-1, :]], dim=1)
+    # TacoTrainingHelper (helpers.py:62-128): r = outputs_per_step frames per decoder step; step t consumes the go frame (t = 0) or the
+    # LAST target frame of group t - 1 (targets[:, r-1::r], teacher forcing)
+    r = hp.outputs_per_step
+    assert T_out % r == 0, "the feeder pads targets to a multiple of outputs_per_step (feeder.py:240-243)"
+    fed = mel_targets[:, r - 1::r, :]
+    dec_in = torch.cat([torch.zeros(B, 1, hp.num_mels), fed[:, :-1, :]], dim=1)
     pre = prenet(dec_in, params, hp, masks.get("prenet_drop"))               # [B, T_out, 256]
     c1 = torch.zeros(B, D); h1 = torch.zeros(B, D); c2 = torch.zeros(B, D); h2 = torch.zeros(B, D)
     ctx = torch.zeros(B, values.shape[-1])
@@ -313,7 +317,7 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
     K2, b2 = params["decoder_LSTM/cell_2/kernel"], params["decoder_LSTM/cell_2/bias"]
     frames, stops, aligns = [], [], []
     zm = masks.get("dec_zone")
-    for t in range(T_out):
+    for t in range(T_out // r):
         nc1, nh1 = lstm_cell(torch.cat([pre[:, t], ctx], dim=-1), c1, h1, K1, b1)
         c1n = zoneout(c1, nc1, zr, training, zm[(1, "c", t)] if zm else None)
         h1n = zoneout(h1, nh1, zr, training, zm[(1, "h", t)] if zm else None)
@@ -327,8 +331,8 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
         frames.append(pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"])
         stops.append(pin @ params["stop_token_projection/kernel"] + params["stop_token_projection/bias"])
         aligns.append(a)
-    decoder_output = torch.stack(frames, dim=1)
-    stop_logits = torch.stack(stops, dim=1).squeeze(-1)
+    decoder_output = torch.stack(frames, dim=1).reshape(B, -1, hp.num_mels)     # [B, T_out / r, r M] -> [B, T_out, M] (tacotron.py:176)
+    stop_logits = torch.stack(stops, dim=1).reshape(B, -1)
     if hp.clip_outputs:
         decoder_output = torch.clamp(decoder_output, _clip_low(hp), hp.max_abs_value)
     y = decoder_output
@@ -410,7 +414,7 @@ def linear_loss(linear_targets, linear_outputs, hp, targets_lengths=None):
 def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=None):
     """Free-running inference graph (tacotron.py:150-200 with is_training = is_evaluating = gta = False):
     TacoTestHelper (helpers.py:6-59) feeds the last predicted frame back (raw, before clipping) and finishes after the
-    first step where round(sigmoid(stop)) is 1 for EVERY batch row (r = 1 makes stop_at_any irrelevant), or at
+    first step where round(sigmoid(stop)) is 1 for EVERY batch row - in any of the r outputs of the step (stop_at_any) or in all of them - or at
     hparams.max_iters; batch-norm uses moving statistics, zoneout its deterministic blend, prenet dropout stays on
     (prenet_masks[t] = list of per-layer masks to inject; None with rate 0). Stop output is the sigmoid (modules.py:340-342)."""
     B, T_in = inputs.shape
@@ -422,7 +426,9 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
         x = conv_block(x, params, "encoder_convolutions/conv_layer_%d/" % (i + 1), "relu", False, hp.tacotron_dropout_rate)
     memory = encoder_rnn(x, input_lengths, params, hp, False)
     mask = (torch.arange(T_in)[None, :] < input_lengths[:, None]).float()
-    values = memory * mask.unsqueeze(-1)
+    if not getattr(hp, "mask_encoder", True):
+        mask = None
+    values = memory * mask.unsqueeze(-1) if mask is not None else memory
     keys = values @ params["attention/memory_layer/kernel"]
     c1 = torch.zeros(B, D); h1 = torch.zeros(B, D); c2 = torch.zeros(B, D); h2 = torch.zeros(B, D)
     ctx = torch.zeros(B, values.shape[-1])
@@ -432,21 +438,22 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
     frame = torch.zeros(B, hp.num_mels)                                           # go frame
     frames, stops, aligns = [], [], []
     for t in range(max_iters):
-        pre = prenet(frame, params, hp, prenet_masks[t] if prenet_masks else None)
+        pre = prenet(frame[:, -hp.num_mels:], params, hp, prenet_masks[t] if prenet_masks else None)      # the LAST of the r frames is fed back
         nc1, nh1 = lstm_cell(torch.cat([pre, ctx], dim=-1), c1, h1, K1, b1)
         c1n, h1n = zoneout(c1, nc1, zr, False), zoneout(h1, nh1, zr, False)
         nc2, nh2 = lstm_cell(nh1, c2, h2, K2, b2)
         c2n, h2n = zoneout(c2, nc2, zr, False), zoneout(h2, nh2, zr, False)
         c1, h1, c2, h2 = c1n, h1n, c2n, h2n
-        ctx, a = attention_step(nh2, cum, keys, values, mask, params)
-        cum = cum + a
+        ctx, a = attention_step(nh2, cum, keys, values, mask, params, getattr(hp, "smoothing", False))
+        cum = cum + a if getattr(hp, "cumulative_weights", True) else a
         pin = torch.cat([nh2, ctx], dim=-1)
         frame = pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"]
         stop = torch.sigmoid(pin @ params["stop_token_projection/kernel"] + params["stop_token_projection/bias"])
         frames.append(frame); stops.append(stop); aligns.append(a)
-        if bool(torch.round(stop).bool().all()):
+        fired = torch.round(stop).bool()                              # [B, r]; helpers.py:40-46: all rows, then any (stop_at_any) / all of the r
+        if bool(fired.all(dim=0).any() if hp.stop_at_any else fired.all()):
             break
-    decoder_output = torch.stack(frames, dim=1)
+    decoder_output = torch.stack(frames, dim=1).reshape(B, -1, hp.num_mels)
     if hp.clip_outputs:
         decoder_output = torch.clamp(decoder_output, _clip_low(hp), hp.max_abs_value)
     y = decoder_output
@@ -456,7 +463,7 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
     mel_outputs = decoder_output + y @ params["postnet_projection/kernel"] + params["postnet_projection/bias"]
     if hp.clip_outputs:
         mel_outputs = torch.clamp(mel_outputs, _clip_low(hp), hp.max_abs_value)
-    return {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_token_prediction": torch.stack(stops, dim=1).squeeze(-1),
+    return {"decoder_output": decoder_output, "mel_outputs": mel_outputs, "stop_token_prediction": torch.stack(stops, dim=1).reshape(B, -1),
             "alignments": torch.stack(aligns, dim=1)}
 
 

@@ -10,6 +10,7 @@ Scenarios (small widths so that the fixture stays a few hundred KB; every hparam
             after one `add_optimizer` step (LR schedule, global-norm clip, Adam, batch-norm moving averages)
   train_md  is_training=True, predict_linear=False, mask_decoder=True: the masked losses inside the whole graph
   train_smooth / train_nomask  smoothing normalisation + non-cumulative attention state; un-masked encoder memory
+  train_r2 / synth_r2  outputs_per_step = 2
   train_asym  symmetric_mels=False + tacotron_scale_regularization=True: the other output-clipping range and the scaled regulariser
   eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
   gta       gta=True: as eval without the post-processing net
@@ -72,9 +73,9 @@ def main():
                linear_targets=lin.numpy(), stop_targets=stop.numpy())
     Tt = tf_shim.T
 
-    def run(tag, variables, seed, **kw):
+    def run(tag, variables, seed, allow_create=False, **kw):
         """one execution of the reference's initialize(); returns the model and the recorded random masks"""
-        G.reset(seed=seed, variables=variables)
+        G.reset(seed=seed, variables=variables, allow_create=allow_create)
         model = Tacotron(rhp)
         args = dict(mel_targets=Tt(mel.clone()), stop_token_targets=Tt(stop.clone()), targets_lengths=Tt(tgt_len.clone()),
                     split_infos=split_infos)
@@ -127,7 +128,8 @@ def main():
             for (l, s), v in zone.items():
                 out["%s_mask_dec_zone_%d_%s" % (tag, l, s)] = torch.stack(v).numpy()                      # [T, B, D]
             for i in range(rhp.postnet_num_layers):
-                out["%s_mask_post_drop_%d" % (tag, i)] = (pop("postnet_convolutions", "layers.dropout", (B, T_steps, rhp.postnet_channels)) / keep).numpy()
+                out["%s_mask_post_drop_%d" % (tag, i)] = (pop("postnet_convolutions", "layers.dropout", (B, T_steps * rhp.outputs_per_step,
+                                                                                                       rhp.postnet_channels)) / keep).numpy()
         assert not q, (tag, names_of(q))
 
     def save_outputs(tag, model, linear):
@@ -207,6 +209,28 @@ def main():
     masks_to_oracle("train_nomask", drops, True, T_out)
     save_outputs("train_nomask", model, False)
     rhp.mask_encoder = True
+
+    # ---- reduction factor r = 2 (rejected by the product; oracle only): two frames per decoder step, the last one fed back ----------------
+    rhp.outputs_per_step = 2
+    keep = {k: v for k, v in no_cbhg.items() if "linear_transform_projection" not in k and "stop_token_projection" not in k}
+    model, drops = run("train_r2", keep, 9, allow_create=True, is_training=True, global_step=Tt(torch.tensor(0)))
+    r2_vars = {k: v.detach().clone() for k, v in G.S.vars.items()}
+    for k in r2_vars:
+        if k not in keep:
+            out["r2_var/" + k] = r2_vars[k].numpy()
+    masks_to_oracle("train_r2", drops, True, T_out // 2)
+    save_outputs("train_r2", model, False)
+    model.add_loss()
+    save_losses("train_r2", model)
+    sb = [k for k in r2_vars if k.endswith("stop_token_projection/projection_stop_token_projection/bias")][0]
+    r2_synth = dict(r2_vars)
+    r2_synth[sb] = r2_vars[sb] - 5.0            # keep the stop token quiet: the fed-back frames run for max_iters steps
+    out["r2_synth_stop_bias"] = r2_synth[sb].numpy()
+    model, drops = run("synth_r2", r2_synth, 10, mel_targets=None, stop_token_targets=None, targets_lengths=None)
+    masks_to_oracle("synth_r2", drops, False, int(model.tower_mel_outputs[0].shape[1]) // 2)
+    save_outputs("synth_r2", model, False)
+    print("synth_r2: %d frames" % int(model.tower_mel_outputs[0].shape[1]))
+    rhp.outputs_per_step = 1
 
     # ---- eval / GTA ------------------------------------------------------------------------------------------------------------------
     rhp.predict_linear, rhp.mask_decoder = True, False

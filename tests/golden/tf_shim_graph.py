@@ -33,8 +33,9 @@ from tf_shim import T
 S = types.SimpleNamespace(scope=[""], opened={}, layer_uid={}, vars=collections.OrderedDict(), gen=None, drops=[], create=True, inits={}, uniforms=[], updates=collections.OrderedDict(), assigned={})
 
 
-def reset(seed=0, variables=None):
-    """new graph: empty scope stack / name counters; `variables` (name -> tensor) are reused instead of created when given"""
+def reset(seed=0, variables=None, allow_create=False):
+    """new graph: empty scope stack / name counters; `variables` (name -> tensor) are reused instead of created when given (missing
+    ones are an error unless allow_create)"""
     S.scope[:] = [""]
     S.opened.clear()
     S.layer_uid.clear()
@@ -45,7 +46,7 @@ def reset(seed=0, variables=None):
     S.updates.clear()
     S.assigned.clear()
     S.gen = torch.Generator().manual_seed(seed)
-    S.create = variables is None
+    S.create = variables is None or allow_create
     for k, v in (variables or {}).items():
         S.vars[k] = _as_var(k, torch.as_tensor(v, dtype=torch.float32).clone())
 

@@ -344,3 +344,31 @@ def test_attention_variants_of_the_executed_reference(R, tag, flags):
         assert float(a[1][:, pad[1]].abs().max()) == 0
     base = ot.forward(params, ids, in_len, mel, _hp(R, predict_linear=False, mask_decoder=False), training=True, masks=_masks(R, tag, True, hp))
     assert float((base["alignments"] - a).abs().max()) > 1e-3                          # the flags do change the result
+
+
+def _params_r2(R):
+    params = _params(R, drop=("CBHG", "cbhg", "linear_transform_projection", "stop_token_projection"))
+    for k in R.files:
+        if k.startswith("r2_var/"):
+            params[t2_tf_bundle.engine_name("Tacotron_model/" + k[len("r2_var/"):])] = torch.from_numpy(R[k]).clone()
+    return params
+
+
+def test_reduction_factor_two_of_the_executed_reference(R):
+    """outputs_per_step = 2 (tacotron.py:141-143,176-177; helpers.py:77,113-124,40-50): r frames per decoder step, the LAST frame of a
+    group is what gets fed (teacher forcing and free running), stop tokens come r per step. Rejected by the product; oracle only."""
+    hp = _hp(R, predict_linear=False, mask_decoder=False, outputs_per_step=2)
+    params = _params_r2(R)
+    assert params["linear_transform_projection/kernel"].shape[1] == 2 * hp.num_mels and params["stop_token_projection/kernel"].shape[1] == 2
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    out = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train_r2", True, hp))
+    assert out["alignments"].shape[1] == mel.shape[1] // 2
+    _check_outputs(R, "train_r2", out, True)
+    total, parts = ot.loss_fn(out, mel, stop, params, hp, tgt_len)
+    assert abs(float(total) - float(R["train_r2_loss"])) <= 1e-5 * abs(float(R["train_r2_loss"]))
+    params["stop_token_projection/bias"] = torch.from_numpy(R["r2_synth_stop_bias"]).clone()
+    pm = [torch.from_numpy(R["synth_r2_mask_prenet_drop_%d" % i]) for i in range(len(hp.prenet_layers))]
+    steps = pm[0].shape[1]
+    syn = ot.synthesize(params, ids, in_len, hp, prenet_masks=[[m[:, t] for m in pm] for t in range(steps)])
+    assert steps == hp.max_iters and syn["mel_outputs"].shape[1] == 2 * steps
+    _check_outputs(R, "synth_r2", syn, False)
