@@ -285,7 +285,28 @@ def attention_step(query, cum, keys, values, mask, params, smoothing=False):
     return ctx, a
 
 
-def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks=None, stats_out=None):
+def teacher_forcing_ratio(hp, global_step, training=True, evaluating=False, gta=False):
+    """helpers.py:86-100,135-169: GTA always feeds the ground truth; evaluation with tacotron_natural_eval always feeds predictions;
+    'scheduled' mode = init ratio until start_decay, then tf.train.cosine_decay of it towards alpha * init over decay_steps."""
+    if gta:
+        return 1.0
+    if evaluating and hp.tacotron_natural_eval:
+        return 0.0
+    if hp.tacotron_teacher_forcing_mode != "scheduled" or not training:
+        return float(hp.tacotron_teacher_forcing_ratio)
+    init = hp.tacotron_teacher_forcing_init_ratio
+    if hp.tacotron_teacher_forcing_final_ratio is not None:
+        alpha = float(hp.tacotron_teacher_forcing_final_ratio / init)
+    else:
+        alpha = hp.tacotron_teacher_forcing_decay_alpha
+    if global_step < hp.tacotron_teacher_forcing_start_decay:
+        return float(init)
+    step = min(global_step - hp.tacotron_teacher_forcing_start_decay, hp.tacotron_teacher_forcing_decay_steps)
+    cosine = 0.5 * (1.0 + math.cos(math.pi * step / hp.tacotron_teacher_forcing_decay_steps))
+    return float(init * ((1.0 - alpha) * cosine + alpha))
+
+
+def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks=None, stats_out=None, tf_ratio=1.0, tf_draws=None):
     """Training / GTA graph with teacher forcing ratio 1. inputs [B, T_in] int64; mel_targets [B, T_out, num_mels].
     Returns dict(decoder_output, mel_outputs, stop_logits, alignments [B, T_out, T_in])."""
     masks = masks or {}
@@ -308,8 +329,10 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
     r = hp.outputs_per_step
     assert T_out % r == 0, "the feeder pads targets to a multiple of outputs_per_step (feeder.py:240-243)"
     fed = mel_targets[:, r - 1::r, :]
-    dec_in = torch.cat([torch.zeros(B, 1, hp.num_mels), fed[:, :-1, :]], dim=1)
-    pre = prenet(dec_in, params, hp, masks.get("prenet_drop"))               # [B, T_out, 256]
+    # per step ONE uniform draw for the whole batch decides between the ground truth and the model's own last frame
+    # (helpers.py:121-124 tf.cond(random_uniform([]) < ratio, ...)); tf_draws[t] is the draw made at the END of step t
+    forced = [True] * (T_out // r) if tf_ratio >= 1.0 and tf_draws is None else [bool(float(u) < tf_ratio) for u in tf_draws]
+    pmask = masks.get("prenet_drop")
     c1 = torch.zeros(B, D); h1 = torch.zeros(B, D); c2 = torch.zeros(B, D); h2 = torch.zeros(B, D)
     ctx = torch.zeros(B, values.shape[-1])
     cum = torch.zeros(B, T_in)
@@ -317,8 +340,10 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
     K2, b2 = params["decoder_LSTM/cell_2/kernel"], params["decoder_LSTM/cell_2/bias"]
     frames, stops, aligns = [], [], []
     zm = masks.get("dec_zone")
+    frame_in = torch.zeros(B, hp.num_mels)                                    # go frame
     for t in range(T_out // r):
-        nc1, nh1 = lstm_cell(torch.cat([pre[:, t], ctx], dim=-1), c1, h1, K1, b1)
+        pre_t = prenet(frame_in, params, hp, [m[:, t] for m in pmask] if pmask else None)
+        nc1, nh1 = lstm_cell(torch.cat([pre_t, ctx], dim=-1), c1, h1, K1, b1)
         c1n = zoneout(c1, nc1, zr, training, zm[(1, "c", t)] if zm else None)
         h1n = zoneout(h1, nh1, zr, training, zm[(1, "h", t)] if zm else None)
         nc2, nh2 = lstm_cell(nh1, c2, h2, K2, b2)                            # layer 2 sees the UN-zoned output
@@ -329,6 +354,7 @@ def forward(params, inputs, input_lengths, mel_targets, hp, training=True, masks
         cum = cum + a if getattr(hp, "cumulative_weights", True) else a      # attention.py:220-224
         pin = torch.cat([nh2, ctx], dim=-1)
         frames.append(pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"])
+        frame_in = fed[:, t] if forced[t] else frames[-1][:, -hp.num_mels:]   # no stop_gradient: the loss back-propagates through it
         stops.append(pin @ params["stop_token_projection/kernel"] + params["stop_token_projection/bias"])
         aligns.append(a)
     decoder_output = torch.stack(frames, dim=1).reshape(B, -1, hp.num_mels)     # [B, T_out / r, r M] -> [B, T_out, M] (tacotron.py:176)

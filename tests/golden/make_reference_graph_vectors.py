@@ -10,6 +10,7 @@ Scenarios (small widths so that the fixture stays a few hundred KB; every hparam
             after one `add_optimizer` step (LR schedule, global-norm clip, Adam, batch-norm moving averages)
   train_md  is_training=True, predict_linear=False, mask_decoder=True: the masked losses inside the whole graph
   train_smooth / train_nomask  smoothing normalisation + non-cumulative attention state; un-masked encoder memory
+  train_sched  scheduled teacher forcing (cosine-decayed ratio, per-step batch-wide draw, gradients through the fed-back frames)
   train_r2 / synth_r2  outputs_per_step = 2
   train_asym  symmetric_mels=False + tacotron_scale_regularization=True: the other output-clipping range and the scaled regulariser
   eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
@@ -209,6 +210,24 @@ def main():
     masks_to_oracle("train_nomask", drops, True, T_out)
     save_outputs("train_nomask", model, False)
     rhp.mask_encoder = True
+
+    # ---- scheduled teacher forcing (rejected by the product; oracle only): cosine-decayed ratio, one draw per step for the whole batch ---
+    rhp.tacotron_teacher_forcing_mode = "scheduled"
+    model, drops = run("train_sched", no_cbhg, 11, is_training=True, global_step=Tt(torch.tensor(30000)))
+    draws = [u for kind, u in G.S.uniforms if kind == "random_uniform"]
+    assert len(draws) == T_out and all(u.dim() == 0 for u in draws)
+    out["train_sched_tf_draws"] = torch.stack(draws).numpy()
+    out["train_sched_ratio"] = np.asarray(float(model.ratio), dtype=np.float64)
+    out["train_sched_global_step"] = np.asarray(30000)
+    assert 0 < float((torch.stack(draws) < model.ratio).float().mean()) < 1          # both branches taken in this fixture
+    masks_to_oracle("train_sched", drops, True, T_out)
+    save_outputs("train_sched", model, False)
+    model.add_loss()
+    save_losses("train_sched", model)
+    model.loss.backward()
+    out["train_sched_grad_embedding"] = G.S.vars["inference/inputs_embedding"].grad.numpy()
+    out["train_sched_grad_prenet"] = G.S.vars["inference/decoder/decoder_prenet/dense_1/kernel"].grad.numpy()
+    rhp.tacotron_teacher_forcing_mode = "constant"
 
     # ---- reduction factor r = 2 (rejected by the product; oracle only): two frames per decoder step, the last one fed back ----------------
     rhp.outputs_per_step = 2

@@ -665,6 +665,13 @@ def install():
     tf.device = lambda *a, **k: contextlib.nullcontext()
     tf.train.replica_device_setter = lambda *a, **k: None
     tf.train.AdamOptimizer, tf.train.ExponentialMovingAverage = AdamOptimizer, ExponentialMovingAverage
+
+    def cosine_decay(learning_rate, global_step, decay_steps, alpha=0.0, name=None):
+        """tf.train.cosine_decay: step = min(global_step, decay_steps); lr ((1 - alpha) 0.5 (1 + cos(pi step / decay_steps)) + alpha)"""
+        step = min(float(torch.as_tensor(global_step)), float(decay_steps))
+        return T(torch.tensor(float(learning_rate) * ((1.0 - alpha) * 0.5 * (1.0 + math.cos(math.pi * step / float(decay_steps))) + alpha),
+                              dtype=torch.float32))
+    tf.train.cosine_decay = cosine_decay
     tf.clip_by_global_norm, tf.clip_by_norm = clip_by_global_norm, clip_by_norm
     tf.clip_by_value = lambda t, lo, hi, **k: torch.clamp(t, float(lo), float(hi))
     tf.get_collection = lambda key, *a, **k: list(S.updates.items())

@@ -372,3 +372,27 @@ def test_reduction_factor_two_of_the_executed_reference(R):
     syn = ot.synthesize(params, ids, in_len, hp, prenet_masks=[[m[:, t] for m in pm] for t in range(steps)])
     assert steps == hp.max_iters and syn["mel_outputs"].shape[1] == 2 * steps
     _check_outputs(R, "synth_r2", syn, False)
+
+
+def test_scheduled_teacher_forcing_of_the_executed_reference(R):
+    """helpers.py:86-128,135-169: ratio = cosine decay of the initial ratio (0.5 at the fixture's global step), ONE uniform draw per
+    decoder step for the whole batch chooses between the ground-truth frame and the model's own last frame, and the loss back-propagates
+    through the fed-back frames. Rejected by the product; oracle only."""
+    hp = _hp(R, predict_linear=False, mask_decoder=False, tacotron_teacher_forcing_mode="scheduled")
+    step = int(R["train_sched_global_step"])
+    ratio = ot.teacher_forcing_ratio(hp, step)
+    assert abs(ratio - float(R["train_sched_ratio"])) < 1e-6 and abs(ratio - 0.5) < 1e-6
+    assert ot.teacher_forcing_ratio(hp, 5000) == 1.0 and abs(ot.teacher_forcing_ratio(hp, 10 ** 6)) < 1e-7 and ot.teacher_forcing_ratio(hp, step, gta=True) == 1.0
+    params = {k: v.requires_grad_(ot.is_trainable(k)) for k, v in _params(R, drop=("CBHG", "cbhg")).items()}
+    ids, in_len, mel, stop, lin, tgt_len = _inputs(R)
+    draws = torch.from_numpy(R["train_sched_tf_draws"])
+    out = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train_sched", True, hp), tf_ratio=ratio, tf_draws=draws)
+    _check_outputs(R, "train_sched", out, True)
+    total, _ = ot.loss_fn(out, mel, stop, params, hp, tgt_len)
+    assert abs(float(total.detach()) - float(R["train_sched_loss"])) <= 1e-5 * abs(float(R["train_sched_loss"]))
+    total.backward()
+    for eng, key in (("inputs_embedding", "train_sched_grad_embedding"), ("decoder_prenet/dense_1/kernel", "train_sched_grad_prenet")):
+        ref = R[key]
+        assert np.abs(params[eng].grad.numpy() - ref).max() <= 2e-4 * np.abs(ref).max(), eng
+    forced = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train_sched", True, hp))
+    assert float((forced["decoder_output"] - out["decoder_output"]).detach().abs().max()) > 1e-3      # feeding predictions changes the result
