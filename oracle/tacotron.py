@@ -265,7 +265,21 @@ def location_sensitive_score(W_query, W_fil, W_keys, v_a, b_a):
     return (v_a * torch.tanh(W_keys + W_query + W_fil + b_a)).sum(-1)
 
 
-def attention_step(query, cum, keys, values, mask, params, smoothing=False):
+def _constraint_mask(prev_max, T_in, win, kind):
+    """attention.py:201-214: positions the synthesis constraint forbids, from the previous step's argmax. 'monotonic': before the
+    previous maximum or more than `win` ahead of it; 'window': outside a window of `win` positions centred on it."""
+    pos = torch.arange(T_in)[None, :]
+    if kind == "monotonic":
+        before = pos < prev_max[:, None]
+        after = pos >= T_in - (T_in - win - prev_max)[:, None]                     # reversed sequence_mask(Tx - win - prev_max)
+    else:
+        assert kind == "window"
+        before = pos < (prev_max - (win // 2 + (win % 2 != 0)))[:, None]
+        after = pos >= T_in - (T_in - win // 2 - prev_max)[:, None]
+    return before | after
+
+
+def attention_step(query, cum, keys, values, mask, params, smoothing=False, constraint=None):
     """attention.py:169-226 + _compute_attention :10-35. query [B, D]; cum [B, T_in] = the attention state (cumulated alignments, or
     the previous alignments with cumulative_weights=False); mask None = mask_encoder False; returns (context, alignments)."""
     pq = (query @ params["attention/query_layer/kernel"]).unsqueeze(1)              # [B, 1, A]
@@ -275,6 +289,8 @@ def attention_step(query, cum, keys, values, mask, params, smoothing=False):
     pl = f @ params["attention/location_features_layer/kernel"]                        # [B, T_in, A]
     e = location_sensitive_score(pq, pl, keys, params["attention/attention_variable_projection"],
                                  params["attention/attention_bias"])                   # [B, T_in]
+    if constraint is not None:                                                         # (prev_max [B] int, win, kind), synthesis only
+        e = torch.where(_constraint_mask(constraint[0], e.shape[1], constraint[1], constraint[2]), torch.full_like(e, float(-2 ** 32 + 1)), e)
     if mask is not None:
         e = torch.where(mask > 0, e, torch.full_like(e, -float("inf")))                # _maybe_mask_score
     if smoothing:                                                                      # attention.py:72-92
@@ -462,6 +478,7 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
     K1, b1 = params["decoder_LSTM/cell_1/kernel"], params["decoder_LSTM/cell_1/bias"]
     K2, b2 = params["decoder_LSTM/cell_2/kernel"], params["decoder_LSTM/cell_2/bias"]
     frame = torch.zeros(B, hp.num_mels)                                           # go frame
+    prev_max = torch.zeros(B, dtype=torch.int64)                                  # Architecture_wrappers.py:166 max_attentions
     frames, stops, aligns = [], [], []
     for t in range(max_iters):
         pre = prenet(frame[:, -hp.num_mels:], params, hp, prenet_masks[t] if prenet_masks else None)      # the LAST of the r frames is fed back
@@ -470,7 +487,9 @@ def synthesize(params, inputs, input_lengths, hp, max_iters=None, prenet_masks=N
         nc2, nh2 = lstm_cell(nh1, c2, h2, K2, b2)
         c2n, h2n = zoneout(c2, nc2, zr, False), zoneout(h2, nh2, zr, False)
         c1, h1, c2, h2 = c1n, h1n, c2n, h2n
-        ctx, a = attention_step(nh2, cum, keys, values, mask, params, getattr(hp, "smoothing", False))
+        cons = (prev_max, hp.attention_win_size, hp.synthesis_constraint_type) if getattr(hp, "synthesis_constraint", False) else None
+        ctx, a = attention_step(nh2, cum, keys, values, mask, params, getattr(hp, "smoothing", False), cons)
+        prev_max = a.argmax(dim=-1)
         cum = cum + a if getattr(hp, "cumulative_weights", True) else a
         pin = torch.cat([nh2, ctx], dim=-1)
         frame = pin @ params["linear_transform_projection/kernel"] + params["linear_transform_projection/bias"]

@@ -15,7 +15,7 @@ Scenarios (small widths so that the fixture stays a few hundred KB; every hparam
   train_asym  symmetric_mels=False + tacotron_scale_regularization=True: the other output-clipping range and the scaled regulariser
   eval      is_evaluating=True: teacher forced, inference statistics, zoneout blend, prenet dropout still on
   gta       gta=True: as eval without the post-processing net
-  synth     free running (TacoTestHelper), stop rule, max_iters
+  synth     free running (TacoTestHelper), stop rule, max_iters; synth_window / synth_mono add the synthesis attention constraints
 The variables are created by the reference code's own tf.get_variable / layer calls (values drawn here from a seeded generator) and
 are stored under the names the reference's scopes give them - tests/test_reference_graph.py checks those names against
 t2_tf_bundle.tacotron_tf_name, i.e. the checkpoint name map is pinned by the reference's code, not by a reading of it.
@@ -269,6 +269,15 @@ def main():
     save_outputs("synth", model, True)
     print("synth: %d decoder steps (max_iters %d), stop predictions %s" % (steps, rhp.max_iters,
           np.round(out["synth_stop_token_prediction"][:, -1], 3)))
+    # synthesis with the attention constraints (rejected by the product; oracle only): scores outside a window around / ahead of the
+    # previous step's argmax are pushed to -2^32 + 1 (attention.py:201-214)
+    for tag_c, kind, win in (("synth_window", "window", 3), ("synth_mono", "monotonic", 2)):
+        rhp.synthesis_constraint, rhp.synthesis_constraint_type, rhp.attention_win_size = True, kind, win
+        model, drops = run(tag_c, variables, 12, mel_targets=None, stop_token_targets=None, targets_lengths=None)
+        masks_to_oracle(tag_c, drops, False, int(model.tower_mel_outputs[0].shape[1]))
+        save_outputs(tag_c, model, True)
+    rhp.synthesis_constraint, rhp.synthesis_constraint_type, rhp.attention_win_size = False, "window", 7
+
     # a second synthesis in which the stop rule (not max_iters) ends the loop: the stop logits above fall with time, so the stop
     # projection is negated (rising logits) and its bias shifted to put every row's crossing of 0.5 between step index 2 and 3
     biased = dict(variables)

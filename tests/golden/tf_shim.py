@@ -73,6 +73,23 @@ class T(torch.Tensor):
 
     shape = property(get_shape)
 
+    def __getitem__(self, idx):
+        """numpy / TF style reversed slices (x[:, ::-1]), which torch does not index"""
+        items = idx if isinstance(idx, tuple) else (idx,)
+        if not any(isinstance(i, slice) and i.step == -1 and i.start is None and i.stop is None for i in items):
+            return torch.Tensor.__getitem__(self, idx)
+        plain = tuple(slice(None) if (isinstance(i, slice) and i.step == -1) else i for i in items)
+        out = torch.Tensor.__getitem__(self, plain)
+        dims, d = [], 0
+        for i in items:
+            if isinstance(i, slice):
+                if i.step == -1:
+                    dims.append(d)
+                d += 1
+            elif i is None:
+                d += 1
+        return torch.flip(out, dims)
+
 
 def _t(x, like=None):
     if isinstance(x, torch.Tensor):

@@ -723,8 +723,8 @@ def install():
     base_reduce_max = tf.reduce_max
     tf.reduce_max = lambda x, *a, **k: base_reduce_max(x if isinstance(x, torch.Tensor) else torch.as_tensor([int(v) for v in x]), *a, **k)
     base_sequence_mask = tf.sequence_mask
-    tf.sequence_mask = lambda lengths, maxlen=None, dtype=torch.bool, **k: base_sequence_mask(
-        lengths if isinstance(lengths, torch.Tensor) else torch.as_tensor([int(v) for v in lengths]), maxlen, dtype)
+    tf.sequence_mask = lambda lengths, maxlen=None, dtype=torch.bool, **k: T(base_sequence_mask(
+        lengths if isinstance(lengths, torch.Tensor) else torch.as_tensor([int(v) for v in lengths]), maxlen, dtype))
 
     def py_func(func, inp, Tout, **k):
         out = func(*[np.asarray(torch.as_tensor(x).detach().cpu().numpy()) for x in inp])

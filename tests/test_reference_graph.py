@@ -396,3 +396,22 @@ def test_scheduled_teacher_forcing_of_the_executed_reference(R):
         assert np.abs(params[eng].grad.numpy() - ref).max() <= 2e-4 * np.abs(ref).max(), eng
     forced = ot.forward(params, ids, in_len, mel, hp, training=True, masks=_masks(R, "train_sched", True, hp))
     assert float((forced["decoder_output"] - out["decoder_output"]).detach().abs().max()) > 1e-3      # feeding predictions changes the result
+
+
+@pytest.mark.parametrize("tag,kind,win", [("synth_window", "window", 3), ("synth_mono", "monotonic", 2)])
+def test_synthesis_attention_constraints_of_the_executed_reference(R, tag, kind, win):
+    """attention.py:201-214 with synthesis_constraint on: energies outside the allowed span around the previous argmax are replaced by
+    -2^32 + 1 before the (masked) softmax. Rejected by the product; oracle only."""
+    hp = _hp(R, predict_linear=True, synthesis_constraint=True, synthesis_constraint_type=kind, attention_win_size=win)
+    params = _params(R)
+    ids, in_len = _inputs(R)[:2]
+    pm = [torch.from_numpy(R["%s_mask_prenet_drop_%d" % (tag, i)]) for i in range(len(hp.prenet_layers))]
+    steps = pm[0].shape[1]
+    out = ot.synthesize(params, ids, in_len, hp, prenet_masks=[[m[:, t] for m in pm] for t in range(steps)] + [None] * 4)
+    assert out["mel_outputs"].shape[1] == steps
+    _check_outputs(R, tag, out, False)
+    free = ot.synthesize(params, ids, in_len, _hp(R, predict_linear=True), prenet_masks=[[m[:, t] for m in pm] for t in range(steps)] + [None] * 4)
+    n = min(free["alignments"].shape[1], steps)
+    assert float((free["alignments"][:, :n] - out["alignments"][:, :n]).abs().max()) > 1e-3      # the constraint bites in this fixture
+    a = out["alignments"]                                                                            # [B, steps, T_in]
+    assert float(a[:, 1:].sum(-1).min()) > 0.999
