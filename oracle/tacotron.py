@@ -1,5 +1,5 @@
 """ORACLE (test infrastructure, not product code): fp32 PyTorch-CPU restatement of the reference's Tacotron-2
-mel-spectrogram predictor (training / GTA graph, teacher forcing, outputs_per_step = 1) and of the CBHG post-processing net +
+mel-spectrogram predictor (training / evaluation / GTA / free-running graphs) and of the CBHG post-processing net +
 linear head (predict_linear = True: tacotron.py:203-219, modules.py:4-78,457-485).
 
 Only tests/, __graft_entry__.smoke() and bench / tools CPU-baseline legs may import this.
@@ -29,6 +29,9 @@ synthesis, and one add_optimizer step (LR schedule, global-norm clip, Adam, batc
 t2_tf_bundle.tacotron_tf_name over the parameter table. This pins the reference's COMPOSITION: layer order, scopes, activation /
 batch-norm / dropout placement, the zoneout wrapper and its un-zoned output, decoder-cell wiring, helpers, stop rule, CBHG, loss terms,
 regularisation filter.
+Variants the CUDA path rejects are carried here too and pinned the same way, so that their kernels have a checker when they are
+written: outputs_per_step > 1, scheduled teacher forcing (cosine-decayed ratio, one draw per step, gradients through fed-back frames),
+smoothing normalisation, non-cumulative attention state, un-masked encoder memory, the synthesis window / monotonic constraints.
 STILL A RESTATEMENT: the primitives under that composition (Dense, Conv1D 'same', BatchNormalization eps 1e-3 / biased variance,
 LSTMCell i,j,f,o + forget_bias 1, GRUCell, dynamic_rnn length handling, BahdanauAttention memory / score masking, dynamic_decode) - in
 the stand-in as in this file they follow the public TF 1.x definitions; TensorFlow itself cannot run here.
