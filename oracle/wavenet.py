@@ -28,6 +28,8 @@ reproduce the executed reference: outputs <= 2e-5, losses 1e-5, d loss / d varia
 waveforms sample by sample; incremental == parallel forward on the same inputs; the variable names the reference's scopes generate
 equal t2_tf_bundle.wavenet_tf_name over the parameter table; the NN_init kernels its `_init_kernel` methods produce equal
 _upsample_init_kernel here and the product initialiser.
+Variants the CUDA path rejects are carried here too and pinned the same way (their kernels then have a checker): global (speaker)
+conditioning through gc_embedding + residual_block_gin_conv, the ResizeConvolution and ConvTranspose1D upsamplers with their NN_init kernels.
 STILL A RESTATEMENT: the convolution primitives under that composition (VALID / SAME cross-correlation with dilation, Conv2DTranspose
 'same' arithmetic) and tf.train (Adam, EMA, glorot init) follow the public TF 1.x definitions in the stand-in
 as in this file; TensorFlow itself cannot run here. Known answers on top: receptive_field_size, mulaw_quantize(0) == 127
@@ -79,6 +81,9 @@ def param_shapes(hp):
         if C > 0:
             sh[p + "residual_block_cin_conv/kernel"] = (1, C, G)
             sh[p + "residual_block_cin_conv/bias"] = (G,)
+        if getattr(hp, "gin_channels", -1) > 0:
+            sh[p + "residual_block_gin_conv/kernel"] = (1, hp.gin_channels, G)
+            sh[p + "residual_block_gin_conv/bias"] = (G,)
         sh[p + "residual_block_skip_conv/kernel"] = (1, G // 2, S)
         sh[p + "residual_block_skip_conv/bias"] = (S,)
         sh[p + "residual_block_out_conv/kernel"] = (1, G // 2, R)
@@ -87,6 +92,8 @@ def param_shapes(hp):
     sh["final_convolution_1/bias"] = (S,)
     sh["final_convolution_2/kernel"] = (1, S, hp.out_channels)
     sh["final_convolution_2/bias"] = (hp.out_channels,)
+    if getattr(hp, "gin_channels", -1) > 0 and hp.use_speaker_embedding:      # modules.py:12-21; created outside the `inference` scope
+        sh["gc_embedding"] = (hp.n_speakers, hp.gin_channels)
     if C > 0 and hp.upsample_type != "NearestNeighbor":      # NearestNeighborUpsample has no variables (modules.py:524-536)
         for i, s in enumerate(hp.upsample_scales):
             p = "local_conditioning_upsampling_%d/" % (i + 1)
@@ -96,8 +103,14 @@ def param_shapes(hp):
             elif hp.upsample_type == "2D":
                 sh[p + "kernel"] = (hp.freq_axis_kernel_size, s, 1, 1)
                 sh[p + "bias"] = (1,)
+            elif hp.upsample_type == "Resize":                           # ResizeConvolution (modules.py:657-693): NN resize, then this conv
+                sh[p + "kernel"] = (hp.freq_axis_kernel_size, s, 1, 1)
+                sh[p + "bias"] = (1,)
+            elif hp.upsample_type == "1D":                               # ConvTranspose1D (modules.py:695-733): mixes the cin channels
+                sh[p + "kernel"] = (1, s, C, C)
+                sh[p + "bias"] = (C,)
             else:
-                raise NotImplementedError("upsample_type %s is out of scope (SURVEY.md §2 #4)" % hp.upsample_type)
+                raise NotImplementedError("unknown upsample_type %s" % hp.upsample_type)
     return sh
 
 
@@ -125,6 +138,19 @@ def _upsample_init_kernel(hp, i, s):
         for j in js:
             k[ii, j] = 1. / max(overlap, 1.) if ks[1] % 2 == 0 else 1.
         k = np.tile(k[:, :, None, None], [1, 1, 1, s])
+        return torch.from_numpy(k * hp.NN_scaler ** (1 / n))
+    if hp.upsample_type == "Resize":                                      # modules.py:683-693
+        ks = (hp.freq_axis_kernel_size, s)
+        overlap = ks[1] // s
+        k = np.zeros(ks, dtype=np.float32)
+        js = [ks[1] // 2 - 1, ks[1] // 2] if ks[1] % 2 == 0 else [ks[1] // 2]
+        for j in js:
+            k[ks[0] // 2, j] = 1. / max(overlap, 1.) if ks[1] % 2 == 0 else 1.
+        return torch.from_numpy((k * hp.NN_scaler ** (1 / n))[:, :, None, None])
+    if hp.upsample_type == "1D":                                          # modules.py:723-733: identity over channels on every tap
+        C = hp.cin_channels
+        k = np.tile(np.eye(C, dtype=np.float32).reshape(1, 1, C, C), [1, s, 1, 1])
+        k = k / max(float(s // s), 1.) if s % 2 == 0 else k
         return torch.from_numpy(k * hp.NN_scaler ** (1 / n))
     ks = (hp.freq_axis_kernel_size, s)
     overlap = ks[1] // s
@@ -181,6 +207,13 @@ def upsample(c, params, hp):
             y = F.conv2d(x, w, b, padding=(k.shape[0] // 2, k.shape[1] // 2))  # [B, s, H, W]
             B_, _, H, W = y.shape
             c = y.permute(0, 2, 3, 1).reshape(B_, H, W * s)  # periodic shuffle: out[.., w*s + k] = y[k, .., w]
+        elif hp.upsample_type == "Resize":  # nearest-neighbour repeat by s along time, then a (kh, s) 'same' convolution, 1 -> 1 channel
+            xr = x.repeat_interleave(s, dim=-1)
+            kh, kw = k.shape[0], k.shape[1]
+            xr = F.pad(xr, ((kw - 1) // 2, kw - 1 - (kw - 1) // 2, (kh - 1) // 2, kh - 1 - (kh - 1) // 2))
+            c = F.conv2d(xr, k.permute(3, 2, 0, 1).contiguous(), b).squeeze(1)
+        elif hp.upsample_type == "1D":      # transposed convolution over time that mixes channels, kernel s = stride s
+            c = F.conv_transpose1d(c, k[0].permute(2, 1, 0).contiguous(), b, stride=s)
         else:  # '2D' ConvTranspose2D, kernel (kh, s), strides (1, s), 'same'
             w = k.permute(3, 2, 0, 1).contiguous()  # TF [kh, kw, out, in] -> torch [in, out, kh, kw]
             y = F.conv_transpose2d(x, w, b, stride=(1, s), padding=(k.shape[0] // 2, 0))
@@ -192,7 +225,7 @@ def upsample(c, params, hp):
     return c
 
 
-def residual_block(x, c, params, hp, l, dropout_mask=None):
+def residual_block(x, c, params, hp, l, dropout_mask=None, gcond=None):
     """ResidualConv1DGLU.step, parallel mode (modules.py:471-521). Returns (x_out, skip)."""
     p = "ResidualConv1DGLU_%d/" % l
     residual = x
@@ -205,6 +238,10 @@ def residual_block(x, c, params, hp, l, dropout_mask=None):
         cc = conv1x1(c, params[p + "residual_block_cin_conv/kernel"], params[p + "residual_block_cin_conv/bias"])
         ca, cb = cc.chunk(2, dim=1)
         a, b = a + ca, b + cb
+    if gcond is not None:                                                # [B, gin, 1]: the same vector at every time step (modules.py:503-508)
+        gg = conv1x1(gcond, params[p + "residual_block_gin_conv/kernel"], params[p + "residual_block_gin_conv/bias"])
+        ga, gb = gg.chunk(2, dim=1)
+        a, b = a + ga, b + gb
     z = torch.tanh(a) * torch.sigmoid(b)
     s = conv1x1(z, params[p + "residual_block_skip_conv/kernel"], params[p + "residual_block_skip_conv/bias"])
     o = conv1x1(z, params[p + "residual_block_out_conv/kernel"], params[p + "residual_block_out_conv/bias"])
@@ -212,15 +249,18 @@ def residual_block(x, c, params, hp, l, dropout_mask=None):
     return x_out, s
 
 
-def step(x, c, params, hp, dropout_masks=None, c_is_upsampled=False):
-    """WaveNet.step (wavenet.py:650-721): x [B, Cin, T] (one-hot float or scalar), c [B, cin, Tc] -> [B, out, T]."""
+def step(x, c, params, hp, dropout_masks=None, c_is_upsampled=False, g=None):
+    """WaveNet.step (wavenet.py:650-721): x [B, Cin, T] (one-hot float or scalar), c [B, cin, Tc] -> [B, out, T]. g: speaker ids [B, 1]
+    (embedded through gc_embedding, wavenet.py:669-678) or None."""
+    if g is not None:
+        g = params["gc_embedding"][g.reshape(-1).long()].unsqueeze(-1)     # [B, gin, 1]
     if c is not None and not c_is_upsampled:
         c = upsample(c, params, hp)
         assert c.shape[-1] == x.shape[-1]
     h = conv1x1(x, params["input_convolution/kernel"], params["input_convolution/bias"])
     skips = None
     for l in range(hp.layers):
-        h, s = residual_block(h, c, params, hp, l, None if dropout_masks is None else dropout_masks[l])
+        h, s = residual_block(h, c, params, hp, l, None if dropout_masks is None else dropout_masks[l], g)
         if skips is None:
             skips = s
         else:

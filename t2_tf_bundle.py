@@ -573,7 +573,7 @@ def wavenet_tf_name(name, upsample_type="SubPixel"):
         return "%s%s/%s_%s/%s" % (P, parts[0], parts[1], parts[0], leaf)
     if parts[0].startswith("local_conditioning_upsampling_"):
         i = int(parts[0].rsplit("_", 1)[1]) - 1
-        kind = "ConvTranspose2D" if upsample_type == "2D" else "SubPixelConvolution"
+        kind = {"2D": "ConvTranspose2D", "1D": "ConvTranspose1D", "Resize": "ResizeConvolution"}.get(upsample_type, "SubPixelConvolution")
         return "%s%s_layer_%d/%s" % (P, kind, i, leaf)
     return P + name
 
@@ -589,7 +589,7 @@ def engine_name(tf_name):
         m = re.fullmatch(r"(ResidualConv1DGLU_\d+)/(residual_block_\w+?_conv)_\1/(\w+)", tail)
         if m:
             return "%s/%s/%s" % m.groups()
-        m = re.fullmatch(r"(?:SubPixelConvolution|ConvTranspose2D)_layer_(\d+)/(\w+)", tail)
+        m = re.fullmatch(r"(?:SubPixelConvolution|ConvTranspose2D|ConvTranspose1D|ResizeConvolution)_layer_(\d+)/(\w+)", tail)
         if m:
             return "local_conditioning_upsampling_%d/%s" % (int(m.group(1)) + 1, m.group(2))
         return tail

@@ -9,6 +9,7 @@ Scenarios (small widths; every hparam not listed keeps the reference's default -
   ce_subpixel   input_type mulaw-quantize (256 classes), SubPixel conditioning upsampling, masked cross entropy
   mol_2d        input_type raw, 2-component mixture-of-logistics head, ConvTranspose2D upsampling
   gauss_nn      input_type raw, single-Gaussian head (out_channels 2, the reference default), NearestNeighbor upsampling
+  ce_resize / ce_1d / mol_gin  oracle-only variants: ResizeConvolution and ConvTranspose1D upsamplers, global (speaker) conditioning
   gauss_paper_2d  the paper configuration's flags: legacy / residual_legacy off, cdf_loss on, ConvTranspose2D upsampling
 Each stores the variables under the names the reference's scopes give them, the recorded dropout masks, the network output, the
 loss and d loss / d variable (autograd through the executed reference graph), plus the NN_init kernels the reference hands to its
@@ -35,6 +36,11 @@ SCENARIOS = {
     "gauss_nn": dict(input_type="raw", quantize_channels=65536, out_channels=2, upsample_type="NearestNeighbor"),
     # the flags of the reference's paper configuration (paper_hparams.py:187-195): no sqrt(0.5) scaling of skips / residuals, CDF form
     # of the Gaussian loss with its own log-scale floor (256 bins here: with 65536 the fp32 CDF difference is rounding noise, see mol_2d)
+    # variants the product rejects (oracle only): the two other learnable upsamplers and global (speaker) conditioning
+    "ce_resize": dict(input_type="mulaw-quantize", quantize_channels=256, out_channels=256, upsample_type="Resize"),
+    "ce_1d": dict(input_type="mulaw-quantize", quantize_channels=256, out_channels=256, upsample_type="1D"),
+    "mol_gin": dict(input_type="raw", quantize_channels=256, out_channels=6, upsample_type="SubPixel", gin_channels=5, n_speakers=3,
+                    use_speaker_embedding=True),
     "gauss_paper_2d": dict(input_type="raw", quantize_channels=256, out_channels=2, upsample_type="2D", legacy=False, residual_legacy=False,
                            cdf_loss=True, log_scale_min_gauss=-7.000000006091266),
 }
@@ -56,6 +62,8 @@ def main():
     # row-major order, i.e. as a reshape.
     _expand = np.expand_dims
     np.expand_dims = lambda a, axis: _expand(a, min(axis, np.ndim(a)) if isinstance(axis, int) and axis >= 0 else axis)
+    import keras.utils
+    keras.utils.np_utils.to_categorical = lambda y, num_classes=None: np.eye(int(num_classes), dtype=np.float32)[np.asarray(y, dtype=np.int64)]
     sys.path.insert(0, REF)
     import hparams as ref_hparams_mod
     rhp = ref_hparams_mod.hparams
@@ -73,7 +81,10 @@ def main():
     c = torch.rand(B, rhp.cin_channels, Tc, generator=g)
     out.update(c=c.numpy(), input_lengths=lengths.numpy())
 
+    defaults = {k: getattr(rhp, k) for over in SCENARIOS.values() for k in over}
     for tag, over in SCENARIOS.items():
+        for k, v in defaults.items():
+            setattr(rhp, k, v)
         for k, v in over.items():
             assert hasattr(rhp, k), k
             setattr(rhp, k, v)
@@ -90,7 +101,10 @@ def main():
 
         G.reset(seed=len(tag))
         model = WaveNet(rhp, init=False)
-        model.initialize(Tt(y.clone()), Tt(c.clone()), None, Tt(lengths.clone()), x=Tt(x.clone()))
+        gids = torch.tensor([[2], [0]], dtype=torch.int32) if rhp.gin_channels > 0 else None
+        if gids is not None:
+            out[tag + "_g"] = gids.numpy()
+        model.initialize(Tt(y.clone()), Tt(c.clone()), None if gids is None else Tt(gids.clone()), Tt(lengths.clone()), x=Tt(x.clone()))
         model.add_loss()
         drops = list(G.S.drops)
         assert len(drops) == rhp.layers and all(k == "layers.dropout" and tuple(m.shape) == (B, rhp.residual_channels, T) for _, k, m in drops), \
@@ -120,7 +134,7 @@ def main():
             out["%s_init/%s" % (tag, k)] = v
         print("%s: %d variables, loss %.6f, NN_init kernels recorded: %d" % (tag, len(names), float(model.loss), len(G.S.inits)))
         variables = {k: v.detach().clone() for k, v in G.S.vars.items()}
-        if tag.startswith("gauss"):
+        if tag not in ("ce_subpixel", "mol_2d"):
             continue
         cat = rhp.input_type == "mulaw-quantize"
 

@@ -111,7 +111,7 @@ def _as_var(full, value):
 
 
 def _new_value(full, shape):
-    leaf = full.rsplit("/", 1)[1]
+    leaf = full.rsplit("/", 1)[-1]
     g = S.gen
     shape = [int(s) for s in shape]
     if leaf == "gamma":
@@ -678,8 +678,9 @@ def install():
     tf.GraphKeys.UPDATE_OPS = "update_ops"
     tf.identity = lambda x, name=None: x
     tf.zeros, tf.ones = wrap(tf.zeros), wrap(tf.ones)
-    tf.convert_to_tensor = lambda x, dtype=None, **k: T(torch.as_tensor(x, dtype=dtype))
-    tf.tile = lambda x, multiples: T(torch.as_tensor(x).repeat(*[int(m) for m in multiples]))
+    keep = lambda t: t if isinstance(t, T) else T(t)          # T(...) makes a new leaf: never re-wrap a tensor that is already in the graph
+    tf.convert_to_tensor = lambda x, dtype=None, **k: keep(x if isinstance(x, torch.Tensor) and dtype in (None, x.dtype) else torch.as_tensor(x, dtype=dtype))
+    tf.tile = lambda x, multiples: keep((x if isinstance(x, torch.Tensor) else torch.as_tensor(x)).repeat(*[int(m) for m in multiples]))
     tf.less = lambda a, b: torch.as_tensor(a) < torch.as_tensor(b)
     tf.logical_or = torch.logical_or
     tf.reduce_all = lambda x, axis=None, **k: torch.as_tensor(x).all() if axis is None else torch.as_tensor(x).all(dim=int(axis))
@@ -760,6 +761,7 @@ def install():
     tf.keras.layers.Wrapper = Wrapper
     tf.TensorShape = TensorShape
     tf.constant_initializer = ConstantInitializer
+    tf.truncated_normal_initializer = lambda *a, **k: None
     tf.constant = lambda v, *a, **k: v
 
     def pad(x, paddings, **k):

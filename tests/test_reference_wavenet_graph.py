@@ -19,7 +19,8 @@ from hparams import hparams
 from oracle import wavenet as ow
 
 PATH = os.path.join(os.path.dirname(__file__), "golden", "reference_wavenet_graph.npz")
-TAGS = ["ce_subpixel", "mol_2d", "gauss_nn", "gauss_paper_2d"]
+TAGS = ["ce_subpixel", "mol_2d", "gauss_nn", "gauss_paper_2d", "ce_resize", "ce_1d", "mol_gin"]
+SUPPORTED = ["ce_subpixel", "mol_2d", "gauss_nn", "gauss_paper_2d"]          # configurations the CUDA path accepts; the rest is oracle only
 
 
 @pytest.fixture(scope="module")
@@ -35,10 +36,16 @@ def _hp(R, tag):
     return hp
 
 
+def _eng(name):
+    """reference variable name -> oracle / engine name (the speaker embedding is created outside the `inference` scope, modules.py:12-21)"""
+    name = str(name)
+    return "gc_embedding" if name == "gc_embedding" else t2_tf_bundle.engine_name("WaveNet_model/" + name)
+
+
 def _params(R, tag, hp):
     out = {}
     for name in R[tag + "_var_names"]:
-        eng = t2_tf_bundle.engine_name("WaveNet_model/" + str(name))
+        eng = _eng(name)
         assert eng is not None, name
         out[eng] = torch.from_numpy(R["%s_var/%s" % (tag, name)]).clone().requires_grad_(True)
     return out
@@ -48,7 +55,8 @@ def _params(R, tag, hp):
 def test_variable_names_match_the_checkpoint_name_map(R, tag):
     hp = _hp(R, tag)
     got = {"WaveNet_model/" + str(n): tuple(R["%s_var/%s" % (tag, n)].shape) for n in R[tag + "_var_names"]}
-    want = {t2_tf_bundle.wavenet_tf_name(k, hp.upsample_type): tuple(v) for k, v in ow.param_shapes(hp).items()}
+    want = {("WaveNet_model/gc_embedding" if k == "gc_embedding" else t2_tf_bundle.wavenet_tf_name(k, hp.upsample_type)): tuple(v)
+            for k, v in ow.param_shapes(hp).items()}
     assert set(got) == set(want), (sorted(set(got) - set(want))[:4], sorted(set(want) - set(got))[:4])
     assert got == want
 
@@ -62,7 +70,8 @@ def test_training_graph_output_loss_and_gradients(R, tag):
     masks = [torch.from_numpy(R["%s_mask_%d" % (tag, l)]) for l in range(hp.layers)]
     up = ow.upsample(c, params, hp)
     assert np.abs(up.detach().numpy() - R[tag + "_upsampled_c"]).max() <= 2e-6
-    y_hat = ow.step(x, c, params, hp, dropout_masks=masks)
+    g = torch.from_numpy(R[tag + "_g"]) if tag + "_g" in R.files else None
+    y_hat = ow.step(x, c, params, hp, dropout_masks=masks, g=g)
     ref = R[tag + "_y_hat"]
     assert y_hat.shape == ref.shape and np.abs(y_hat.detach().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
     y = torch.from_numpy(R[tag + "_y"])[:, :, 0]
@@ -72,14 +81,14 @@ def test_training_graph_output_loss_and_gradients(R, tag):
     loss.backward()
     floor = 1e-3 * max(np.abs(R[k]).max() for k in R.files if k.startswith(tag + "_grad/"))
     for name in R[tag + "_var_names"]:
-        eng = t2_tf_bundle.engine_name("WaveNet_model/" + str(name))
+        eng = _eng(name)
         ref = R["%s_grad/%s" % (tag, name)]
         g = params[eng].grad
         g = np.zeros_like(ref) if g is None else g.numpy()
         assert np.abs(g - ref).max() <= 2e-4 * max(np.abs(ref).max(), floor), eng
 
 
-@pytest.mark.parametrize("tag", ["ce_subpixel", "mol_2d"])
+@pytest.mark.parametrize("tag", ["ce_subpixel", "mol_2d", "ce_resize", "ce_1d"])
 def test_nn_init_kernels_of_the_reference_match_oracle_and_product_initialisers(R, tag):
     hp = _hp(R, tag)
     init = importlib.import_module("tacotron-2_b200.init")
@@ -91,13 +100,14 @@ def test_nn_init_kernels_of_the_reference_match_oracle_and_product_initialisers(
         shape = ow.param_shapes(hp)[eng]
         ref = R[k].reshape(shape)         # tf.constant_initializer fills the variable in row-major order (see the generator's note)
         assert np.abs(ow._upsample_init_kernel(hp, i, hp.upsample_scales[i]).numpy() - ref).max() <= 1e-7
-        prod = init.nn_upsample_kernel(shape, hp.upsample_scales[i], len(hp.upsample_scales), hp.NN_scaler, hp.upsample_type == "SubPixel")
-        assert np.abs(prod.numpy() - ref).max() <= 1e-7
+        if tag in SUPPORTED:
+            prod = init.nn_upsample_kernel(shape, hp.upsample_scales[i], len(hp.upsample_scales), hp.NN_scaler, hp.upsample_type == "SubPixel")
+            assert np.abs(prod.numpy() - ref).max() <= 1e-7
         assert float(np.abs(ref).sum()) > 0
 
 
 def _plain_params(R, tag):
-    return {t2_tf_bundle.engine_name("WaveNet_model/" + str(n)): torch.from_numpy(R["%s_var/%s" % (tag, n)]) for n in R[tag + "_var_names"]}
+    return {_eng(n): torch.from_numpy(R["%s_var/%s" % (tag, n)]) for n in R[tag + "_var_names"]}
 
 
 @pytest.mark.parametrize("tag", ["ce_subpixel", "mol_2d"])
@@ -170,11 +180,13 @@ def test_one_optimizer_step_of_the_executed_reference(R, tag):
     y = y.long() if ow.is_mulaw_quantize(hp.input_type) else y
     step = int(R[tag + "_global_step"])
     assert abs(ow.learning_rate(hp, step) - float(R[tag + "_learning_rate"])) <= 1e-6 * float(R[tag + "_learning_rate"])
+    if tag + "_g" in R.files:
+        pytest.skip("train_step has no speaker-id argument; the forward / gradient test covers this configuration")
     loss, grads, _ = ow.train_step(params, x, c, y, lengths, hp, dropout_masks=masks)
     new, state = {k: v.clone() for k, v in params.items()}, {}
     lr = ow.adam_step(new, grads, state, hp, step)
     for name in R[tag + "_var_names"]:
-        eng = t2_tf_bundle.engine_name("WaveNet_model/" + str(name))
+        eng = _eng(name)
         old = R["%s_var/%s" % (tag, name)]
         key = "%s_new/%s" % (tag, name)
         if key not in R.files:          # a variable the loss does not reach (the last block's residual output conv): TF hands back a None
