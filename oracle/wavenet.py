@@ -494,7 +494,7 @@ def sample_from_discretized_mix_logistic(y, log_scale_min, u_mix, u_logistic):
 # incremental (Fast-WaveNet) forward — wavenet.py:724-911, modules.py:273-303
 # ---------------------------------------------------------------------------------------------------------
 def incremental(initial_input, c, params, hp, time_length, test_inputs=None, u_mix=None, u_logistic=None,
-                u_cat=None, c_is_upsampled=False, softmax=False):
+                u_cat=None, c_is_upsampled=False, softmax=False, normal=None):
     """initial_input [B, 1, Cin]; c [B, cin, Tc]; test_inputs [B, T, Cin] (teacher forcing) or None.
     Returns (outputs [B, T, Cin-like], raw network outputs [B, T, out])."""
     B = initial_input.shape[0]
@@ -537,7 +537,12 @@ def incremental(initial_input, c, params, hp, time_length, test_inputs=None, u_m
         y = F.relu(y @ params["final_convolution_1/kernel"][0] + params["final_convolution_1/bias"])
         y = y @ params["final_convolution_2/kernel"][0] + params["final_convolution_2/bias"]
         raws.append(y)
-        if is_scalar_input(hp.input_type):
+        if is_scalar_input(hp.input_type) and hp.out_channels == 2:          # single Gaussian head (wavenet.py:853-856, gaussian.py:39-52)
+            nz = normal[:, t:t + 1] if normal is not None else torch.randn(B, 1)
+            smp = sample_from_gaussian(y.unsqueeze(-1), hp.log_scale_min_gauss, nz)   # [B, 1]
+            nxt = smp.unsqueeze(-1)
+            outs.append(smp)
+        elif is_scalar_input(hp.input_type):
             um = u_mix[:, t:t + 1, :] if u_mix is not None else torch.rand(B, 1, hp.out_channels // 3).clamp(1e-5, 1 - 1e-5)
             ul = u_logistic[:, t:t + 1] if u_logistic is not None else torch.rand(B, 1).clamp(1e-5, 1 - 1e-5)
             smp = sample_from_discretized_mix_logistic(y.unsqueeze(-1), hp.log_scale_min, um, ul)  # [B, 1]

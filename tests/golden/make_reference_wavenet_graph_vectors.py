@@ -134,7 +134,7 @@ def main():
             out["%s_init/%s" % (tag, k)] = v
         print("%s: %d variables, loss %.6f, NN_init kernels recorded: %d" % (tag, len(names), float(model.loss), len(G.S.inits)))
         variables = {k: v.detach().clone() for k, v in G.S.vars.items()}
-        if tag not in ("ce_subpixel", "mol_2d"):
+        if tag not in ("ce_subpixel", "mol_2d", "gauss_nn", "gauss_paper_2d"):
             continue
         cat = rhp.input_type == "mulaw-quantize"
 
@@ -162,8 +162,12 @@ def main():
         out[tag + "_synth_raw"] = model.tower_y_hat_eval[0].detach().numpy()
         draws = list(G.S.uniforms)
         kinds = sorted(set(k for k, _ in draws))
-        assert len(draws) == (T if cat else 2 * T) and kinds == (["multinomial"] if cat else ["random_uniform"]), (len(draws), kinds)
-        if cat:
+        gauss = rhp.out_channels == 2
+        assert len(draws) == (2 * T if not (cat or gauss) else T) and kinds == (["multinomial"] if cat else ["normal"] if gauss else ["random_uniform"]), \
+            (len(draws), kinds)
+        if gauss:
+            out[tag + "_synth_normal"] = torch.cat([u.reshape(B, 1) for _, u in draws], dim=1).numpy()                # [B, T]
+        elif cat:
             out[tag + "_synth_u_cat"] = torch.cat([u for _, u in draws], dim=1).numpy()                       # [B, T]
         else:
             out[tag + "_synth_u_mix"] = torch.cat([draws[2 * t][1] for t in range(T)], dim=1).numpy()           # [B, T, nr_mix]

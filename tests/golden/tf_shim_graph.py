@@ -742,7 +742,9 @@ def install():
         def sample(self):
             if tf_shim._normal_queue:
                 return base_normal.sample(self)
-            return self.loc + self.scale * torch.randn(tuple(self.loc.shape), generator=S.gen)
+            n = torch.randn(tuple(self.loc.shape), generator=S.gen)
+            S.uniforms.append(("normal", n))
+            return self.loc + self.scale * n
     tf.contrib.distributions.Normal = Normal
     nn.embedding_lookup = lambda table, ids, **k: table[torch.as_tensor(ids).long()]
     nn.l2_loss = lambda v: (v * v).sum() / 2

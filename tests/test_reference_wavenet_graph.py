@@ -110,7 +110,10 @@ def _plain_params(R, tag):
     return {_eng(n): torch.from_numpy(R["%s_var/%s" % (tag, n)]) for n in R[tag + "_var_names"]}
 
 
-@pytest.mark.parametrize("tag", ["ce_subpixel", "mol_2d"])
+AR_TAGS = ["ce_subpixel", "mol_2d", "gauss_nn", "gauss_paper_2d"]
+
+
+@pytest.mark.parametrize("tag", AR_TAGS)
 def test_evaluation_branch_teacher_forced_incremental_pass(R, tag):
     """wavenet.py:382-440 + incremental (:724-911): item 0, Fast-WaveNet queues, next input = the ground-truth sample; the raw network
     outputs of the incremental pass equal the oracle's incremental AND its parallel forward; eval loss (:497-507) restated here"""
@@ -126,7 +129,8 @@ def test_evaluation_branch_teacher_forced_incremental_pass(R, tag):
     else:
         test_inputs, initial = y0, torch.zeros(1, 1, 1)
     outs, raws = ow.incremental(initial, c0, params, hp, n, test_inputs=test_inputs, u_cat=torch.full((1, n), 0.5),
-                                u_mix=torch.full((1, n, max(hp.out_channels // 3, 1)), 0.5), u_logistic=torch.full((1, n), 0.5))
+                                u_mix=torch.full((1, n, max(hp.out_channels // 3, 1)), 0.5), u_logistic=torch.full((1, n), 0.5),
+                                normal=torch.zeros(1, n))
     ref = torch.from_numpy(R[tag + "_eval_raw"])
     ref = ref if ow.is_mulaw_quantize(hp.input_type) else ref.transpose(1, 2)         # -> [1, T, out]
     assert (raws - ref).abs().max() <= 2e-5 * max(1.0, float(ref.abs().max()))
@@ -135,13 +139,16 @@ def test_evaluation_branch_teacher_forced_incremental_pass(R, tag):
     assert (par - ref).abs().max() <= 5e-5 * max(1.0, float(ref.abs().max()))
     if ow.is_mulaw_quantize(hp.input_type):
         loss = torch.nn.functional.cross_entropy(ref[0], y0[0, :, 0].long())
+    elif hp.out_channels == 2:
+        loss = ow.gaussian_maximum_likelihood_estimation_loss(ref.transpose(1, 2), y0, hp.log_scale_min_gauss, hp.quantize_channels,
+                                                              use_cdf=hp.cdf_loss, reduce=False).mean()
     else:
         loss = ow.discretized_mix_logistic_loss(ref.transpose(1, 2), y0, num_classes=hp.quantize_channels, log_scale_min=hp.log_scale_min,
                                                 reduce=False).mean()
     assert abs(float(loss) - float(R[tag + "_eval_loss"])) <= 2e-5 * abs(float(R[tag + "_eval_loss"]))
 
 
-@pytest.mark.parametrize("tag", ["ce_subpixel", "mol_2d"])
+@pytest.mark.parametrize("tag", AR_TAGS)
 def test_synthesis_branch_free_running_with_the_recorded_draws(R, tag):
     """wavenet.py:441-478: conditioning [B, Tc, cin] in, Tc * hop samples out; every categorical / mixture / logistic draw of the
     executed reference is injected into the oracle, so the sampled waveforms must agree sample by sample"""
@@ -156,6 +163,10 @@ def test_synthesis_branch_free_running_with_the_recorded_draws(R, tag):
         outs, raws = ow.incremental(initial, c, params, hp, T, u_cat=torch.from_numpy(R[tag + "_synth_u_cat"]))
         ref_raw = torch.from_numpy(R[tag + "_synth_raw"])                              # [B, T, Q]
         wav = oa.inv_mulaw_quantize(outs.argmax(-1).numpy(), Q)
+    elif hp.out_channels == 2:
+        outs, raws = ow.incremental(torch.zeros(B, 1, 1), c, params, hp, T, normal=torch.from_numpy(R[tag + "_synth_normal"]))
+        ref_raw = torch.from_numpy(R[tag + "_synth_raw"]).transpose(1, 2)
+        wav = outs.numpy().reshape(B, T)
     else:
         outs, raws = ow.incremental(torch.zeros(B, 1, 1), c, params, hp, T, u_mix=torch.from_numpy(R[tag + "_synth_u_mix"]),
                                     u_logistic=torch.from_numpy(R[tag + "_synth_u_logistic"]))
