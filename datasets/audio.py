@@ -185,9 +185,9 @@ def start_and_end_indices(quantized, silence_threshold=2):
 def trim_silence(wav, hparams):
     """librosa.effects.trim(wav, top_db, frame_length, hop_length)[0] (audio.py:46-52): keep from the first to the last frame whose
     RMS power is within trim_top_db of the loudest frame; start = first_frame * hop, end = min(len, (last_frame + 1) * hop).
-    UNPINNED (librosa is not installable here): frames are CENTRED on t * hop with reflect padding, librosa's rmse behaviour from 0.6
-    on; the reference pins librosa 0.5.1, whose rmse may frame the unpadded signal instead (frame t = samples [t hop, t hop + n)), which
-    would move both cut points by up to frame_length / 2 samples."""
+    UNPINNED (librosa is not installable here). Frames are CENTRED on t * hop with reflect padding - librosa's rmse from 0.6 on. The
+    reference's requirements.txt says librosa 0.5.1, but its call passes `frame_length=`, a keyword effects.trim only has from 0.6 (0.5.x
+    named it n_fft and framed the unpadded signal), so the code as written needs the centred variant."""
     n, hop, top_db = hparams.trim_fft_size, hparams.trim_hop_size, hparams.trim_top_db
     y = np.pad(np.asarray(wav, dtype=np.float64), n // 2, mode="reflect")
     frames = 1 + (len(y) - n) // hop
